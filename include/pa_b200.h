@@ -1,0 +1,212 @@
+/*
+ * pa_b200.h -- C-ABI of libpa_b200.so: the B200 (sm_100a) implementation of the
+ * reference's decode hot path (paged attention over the tiled KV cache + INT8
+ * quantise / dequantise / int8 matmul).  Plain pointers and sizes only; every
+ * pointer named d_* (and every tensor argument unless stated otherwise) is a
+ * DEVICE pointer; `stream` is a cudaStream_t passed as void*.
+ *
+ * Every entry point returns an int status: 0 = PA_OK, <0 = PA_ERR_* (argument /
+ * support errors, nothing launched), >0 = a cudaError_t from the launch.
+ * pa_error_string() renders any of them.  There is no CPU fallback anywhere.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to
+ * the reference repository root).
+ */
+#ifndef PA_B200_H_
+#define PA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_OK 0
+#define PA_ERR_INVALID_ARG (-1)  /* null pointer, non-positive size, misaligned buffer */
+#define PA_ERR_UNSUPPORTED (-2)  /* head_dim / tile_size / activation outside the built set */
+#define PA_ERR_WORKSPACE (-3)    /* workspace too small; see pa_decode_workspace_bytes */
+#define PA_ERR_NO_DEVICE (-4)    /* no sm_100 device is current */
+
+#define PA_ACT_NONE 0
+#define PA_ACT_RELU 1
+#define PA_ACT_GELU 2 /* gelu_erf, dnnl_matmul_int8.cpp:48-49 */
+
+typedef void* pa_stream_t; /* cudaStream_t */
+
+/* ---------------------------------------------------------------- runtime */
+int pa_version(void);
+const char* pa_error_string(int status);
+/* sm count / compute capability of the current device. */
+int pa_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------- page table */
+/* kv_cache/page_table.cpp:14-26,41-47  PageTable::init / clear:
+ * every entry := -1 (unmapped). */
+int pa_page_table_clear(int32_t* d_table, int64_t n_entries, pa_stream_t stream);
+
+/* kv_cache/page_table.cpp:49-53 PageTable::assign and :64-67 remove, batched:
+ * d_table[d_idx[i]] = d_page[i] for i < n (page -1 == remove).  Replaces the
+ * reference's one blocking 4-byte cudaMemcpy per entry.  idx is the flat index
+ * beam*(H*Tiles) + head*Tiles + tile (page_table.hpp:39-42); out-of-range
+ * indices are ignored (the reference asserts). */
+int pa_page_table_update(int32_t* d_table, int64_t n_entries, const int32_t* d_idx,
+                         const int32_t* d_page, int n, pa_stream_t stream);
+
+/* kv_cache/page_table.hpp:44-49 PageTable::lookup (device), batched: d_out[i] =
+ * table entry of (d_beam[i], d_head[i], d_tile[i]) or -1 when the flat index
+ * is out of range. */
+int pa_page_table_lookup(const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                         const int32_t* d_beam, const int32_t* d_head, const int32_t* d_tile,
+                         int32_t* d_out, int n, pa_stream_t stream);
+
+/* -------------------------------------------------------- page pool: gather */
+/* kv_cache/kv_tile_cache.hpp:21-26 KVTileCache<T>::get, materialised: copies
+ * the pages of rows r < R (table row = d_beam_ids ? d_beam_ids[r] : r) of one
+ * pool into dense [R, H, num_tiles*tile_size, D]; unmapped / out-of-range pages
+ * are filled with `fill_byte`.  elem_bytes = sizeof(T) (1, 2 or 4).
+ * Bit-exact byte mover. */
+int pa_kv_gather(const void* d_pool, void* d_dense, const int32_t* d_table, int num_beams,
+                 int num_heads, int num_tiles, int total_pages, int tile_size, int head_dim,
+                 int elem_bytes, const int32_t* d_beam_ids, int R, int fill_byte,
+                 pa_stream_t stream);
+
+/* -------------------------------------------------------- page pool: append */
+/* kv_cache/kv_tile_cache.hpp:29-34 KVTileCache<T>::get_write_ptr + the row
+ * write the caller performs: row (d_positions[r] % tile_size) of page
+ * (beam, head, d_positions[r] / tile_size) := new_k/new_v[r, head, :].
+ * Unmapped pages are skipped.  new_k/new_v are [R, H, D].
+ *   _f16      : new rows already fp16, byte copy.
+ *   _f32_f16  : new rows fp32, rounded to nearest-even fp16 on write.
+ *   _f32_i8   : new rows fp32; per (row, head) scale = compute_minmax_scale
+ *               (int8_quant.cpp:59-64), q = batch_quantize (int8_quant.cpp:15-28);
+ *               scale stored at d_*_scales[page*tile_size + row_in_page]. */
+int pa_kv_append_f16(void* d_k_pool, void* d_v_pool, const int32_t* d_table, int num_beams,
+                     int num_heads, int num_tiles, int total_pages, int tile_size, int head_dim,
+                     const void* d_new_k, const void* d_new_v, const int32_t* d_beam_ids,
+                     const int32_t* d_positions, int R, pa_stream_t stream);
+int pa_kv_append_f32_f16(void* d_k_pool, void* d_v_pool, const int32_t* d_table, int num_beams,
+                         int num_heads, int num_tiles, int total_pages, int tile_size,
+                         int head_dim, const float* d_new_k, const float* d_new_v,
+                         const int32_t* d_beam_ids, const int32_t* d_positions, int R,
+                         pa_stream_t stream);
+int pa_kv_append_f32_i8(int8_t* d_k_pool, int8_t* d_v_pool, float* d_k_scales, float* d_v_scales,
+                        const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                        int total_pages, int tile_size, int head_dim, const float* d_new_k,
+                        const float* d_new_v, const int32_t* d_beam_ids,
+                        const int32_t* d_positions, int R, pa_stream_t stream);
+
+/* ------------------------------------------------ paged decode attention */
+/* Bytes of scratch the decode entry points need for (B rows, H heads, D). */
+size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim);
+
+/*
+ * attention/paged_flash_attention_kernel_fused.cu:5-90 (launched by
+ * attention/attention_tile_launcher.hpp:35-90, dispatched by
+ * attention/attention_cuda.cu:41-95), with the math of
+ * attention_cpu/cpu_attention_kernel.cpp:36-129 (global softmax; SURVEY App. A
+ * D1-D9): for every (b, h)
+ *     beam   = d_beam_ids ? d_beam_ids[b] : b
+ *     s[t]   = dot(q[b,h,:], K[beam,h,t,:]) / temperature      t < ctx(b)
+ *     p      = exp(s - max s) / (sum exp(s - max s) + 1e-6)
+ *     out[b,h,:] = sum_t p[t] * V[beam,h,t,:]
+ * K/V rows come from pages: page = table[beam][h][t / tile_size]; unmapped or
+ * out-of-range pages contribute nothing.  ctx(b) = d_ctx_lens ? d_ctx_lens[b] : T.
+ * q, out: [B, H, D] f32 (out may alias q).  Pools: [total_pages][tile_size][D].
+ * d_rope: optional [D] interleaved cos/sin, pairwise rotation of q
+ * (cpu_attention_kernel.cpp:13-19); NULL = off.  d_lse_out: optional [B, H]
+ * log-sum-exp of the scaled scores (replaces the racy rerank_scores side
+ * output, ...fused.cu:53-55).  head_dim in {64, 128}; tile_size % 16 == 0.
+ *
+ * _f16: fp16 K/V pages, split-KV grid kernel, 128-bit page-indirect global
+ *       loads, warp-shuffle online softmax, LSE combine.
+ * _f16_overlap: paged_flash_attention_kernel_fused_overlap.cu:5-91 -- same
+ *       results through the persistent kernel that stages pages into shared
+ *       memory with the TMA bulk-copy engine (multi-stage mbarrier ring) so
+ *       loads and math overlap.
+ * _i8 / _i8_overlap: int8 K/V pages with per-(page,row) f32 scales, dequantised
+ *       in the kernel as q/scale (int8_quant.cpp:46-57).
+ */
+int pa_paged_decode_f16(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                        const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                        int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_lens,
+                        int B, int T, int head_dim, int tile_size, float temperature,
+                        const float* d_rope, float* d_lse_out, void* d_workspace,
+                        size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_decode_f16_overlap(const float* d_q, float* d_out, const void* d_k_pool,
+                                const void* d_v_pool, const int32_t* d_table, int num_beams,
+                                int num_heads, int num_tiles, int total_pages,
+                                const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B,
+                                int T, int head_dim, int tile_size, float temperature,
+                                const float* d_rope, float* d_lse_out, void* d_workspace,
+                                size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_decode_i8(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                       const int8_t* d_v_pool, const float* d_k_scales, const float* d_v_scales,
+                       const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                       int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_lens,
+                       int B, int T, int head_dim, int tile_size, float temperature,
+                       const float* d_rope, float* d_lse_out, void* d_workspace,
+                       size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                               const int8_t* d_v_pool, const float* d_k_scales,
+                               const float* d_v_scales, const int32_t* d_table, int num_beams,
+                               int num_heads, int num_tiles, int total_pages,
+                               const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B, int T,
+                               int head_dim, int tile_size, float temperature,
+                               const float* d_rope, float* d_lse_out, void* d_workspace,
+                               size_t workspace_bytes, pa_stream_t stream);
+
+/* Split-KV across GPUs (north-star long-context mode): same computation over
+ * this rank's pages only, emitting UN-normalised partials for an LSE combine:
+ *   d_part_m[b,h] = max_t s[t] (natural-log units; -inf if no key)
+ *   d_part_l[b,h] = sum_t exp(s[t]-m),  d_part_o[b,h,:] = sum_t exp(s[t]-m) V[t,:]
+ * `token_offset` is unused by the math (no positional terms) and reserved. */
+int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
+                                float* d_part_o, const void* d_k_pool, const void* d_v_pool,
+                                const int32_t* d_table, int num_beams, int num_heads,
+                                int num_tiles, int total_pages, const int32_t* d_beam_ids,
+                                const int32_t* d_ctx_lens, int B, int T, int head_dim,
+                                int tile_size, float temperature, const float* d_rope,
+                                void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+
+/* LSE combine of n_parts partials (layout [n_parts][rows] for m/l and
+ * [n_parts][rows][D] for o, as gathered from n_parts ranks):
+ *   M = max_i m_i; w_i = exp(m_i - M); out = sum w_i o_i / (sum w_i l_i + 1e-6). */
+int pa_lse_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                   int n_parts, int rows, int head_dim, float* d_out, float* d_lse_out,
+                   pa_stream_t stream);
+
+/* --------------------------------------------------------------- int8_quant */
+/* attention_cpu/int8_quant.cpp:5-13  q = clamp(round_half_away(x*scale),-128,127) */
+int pa_quantize_i8(const float* d_x, int64_t n, float scale, int8_t* d_q, pa_stream_t stream);
+/* attention_cpu/int8_quant.cpp:15-28 per-row scale, x [rows, dim] */
+int pa_batch_quantize_i8(const float* d_x, const float* d_scales, int rows, int dim, int8_t* d_q,
+                         pa_stream_t stream);
+/* attention_cpu/int8_quant.cpp:30-36 -> *d_out (one float, device) */
+int pa_absmax(const float* d_x, int64_t n, float* d_out, pa_stream_t stream);
+/* attention_cpu/int8_quant.cpp:59-64 127/(absmax+1e-6) -> *d_out */
+int pa_minmax_scale(const float* d_x, int64_t n, float* d_out, pa_stream_t stream);
+/* the same, one scale per row of x [rows, dim] -> d_scales[rows] */
+int pa_batch_minmax_scale(const float* d_x, int rows, int dim, float* d_scales, pa_stream_t stream);
+/* attention_cpu/int8_quant.cpp:38-44  x = (float)q / scale (IEEE division) */
+int pa_dequantize_i8(const int8_t* d_q, int64_t n, float scale, float* d_x, pa_stream_t stream);
+/* attention_cpu/int8_quant.cpp:46-57 */
+int pa_batch_dequantize_i8(const int8_t* d_q, const float* d_scales, int rows, int dim, float* d_x,
+                           pa_stream_t stream);
+
+/* ------------------------------------------------------------ int8 matmul */
+/* attention_cpu/dnnl_matmul_int8.cpp:7-76:
+ *   acc[b,m,n] = sum_k A[b,m,k] * B[b,k,n]              (s8 x s8 -> s32, exact)
+ *   C_s8       = sat_s8(rne(act(alpha*acc + bias[n]))),  alpha = scaleA*scaleB/scaleC
+ * A [BATCH,M,K], B [BATCH,K,N], C [BATCH,M,N] row-major (format_tag::abc).
+ * d_C_s8 and/or d_C_s32 may be NULL (at least one must be given); d_C_s32
+ * receives the raw int32 accumulators (the bit-exact parity target).
+ * tcgen05 kind::i8 tensor-core kernel; K % 16 == 0 and N % 16 == 0 required. */
+int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH,
+               int M, int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias,
+               int act, pa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H_ */

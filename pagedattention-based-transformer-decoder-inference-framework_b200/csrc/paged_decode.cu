@@ -1,0 +1,833 @@
+// paged_decode.cu -- single-query (decode) attention over the paged KV cache.
+//
+// Replaces attention/paged_flash_attention_kernel_fused.cu:5-90 (a1) and
+// attention/paged_flash_attention_kernel_fused_overlap.cu:5-91 (a2) with the math of
+// attention_cpu/cpu_attention_kernel.cpp:36-129 (global softmax).
+//
+// The op is HBM-bound (~1 flop/B): every K/V byte is read once.  Design:
+//   * the unit of work is a 16-token sub-tile of one page: K [16][D] + V [16][D],
+//     contiguous in the pools, located through the dense int32 page table;
+//   * a warp owns a unit: lane = 8*g + c reads token rows 4p+g (p = 0..3) and the
+//     16 B dim chunk c of each row, so each quarter-warp touches 128 contiguous
+//     bytes (coalesced in global memory, conflict-free in shared memory);
+//     QK^T is reduced over the 8 chunk lanes with 3 xor-shuffles per token row
+//     and the online softmax (running m, l) lives per lane group -- no shared
+//     memory or block barrier in the steady state;
+//   * direct kernel (a1): grid (rows, splits), 128-bit ld.global.nc loads
+//     straight into registers, split-KV partials + LSE combine kernel;
+//   * overlap kernel (a2): persistent, one CTA per SM, every warp runs its own
+//     multi-stage ring of TMA bulk copies (cp.async.bulk -> UBLKCP, mbarrier
+//     complete_tx) so ~190 KB of page loads per SM stay in flight while the math
+//     runs; the linear (row, unit) space is cut into equal contiguous shares
+//     per CTA (stream-K style), rows cut by a share boundary emit (m, l, O)
+//     partials that a tiny combine kernel merges.
+#include "pa_common.cuh"
+
+namespace pa {
+
+constexpr int kUnitTok = 16;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct DecodeArgs {
+    const float* q;
+    float* out;
+    float* lse_out;
+    float* part_m;  // non-null => emit un-normalised partials (multi-GPU split-KV)
+    float* part_l;
+    float* part_o;
+    const uint8_t* k_pool;
+    const uint8_t* v_pool;
+    const float* k_scales;
+    const float* v_scales;
+    const int32_t* table;
+    const int32_t* beam_ids;
+    const int32_t* ctx_lens;
+    const float* rope;
+    float* ws_m;  // split / stream-K partials, log2 domain
+    float* ws_l;
+    float* ws_o;
+    int num_beams, H, num_tiles, total_pages;
+    int B, T, tile_size;
+    int num_splits;   // direct kernel
+    int evict_first;  // overlap kernel L2 hint
+    float qscale;     // log2(e) / temperature
+};
+
+template <int D, int KV>
+struct Cfg {
+    static constexpr int ES = KV == 0 ? 2 : 1;                 // bytes per element
+    static constexpr int ROWB = D * ES;                        // bytes per token row
+    static constexpr int VB = (ROWB / 8 >= 16) ? 16 : ROWB / 8;  // bytes per lane vector
+    static constexpr int NV = ROWB / (8 * VB);                 // vectors per lane per row
+    static constexpr int EV = VB / ES;                         // elements per vector
+    static constexpr int E = NV * EV;                          // = D / 8 elements per lane
+    static constexpr int WPV = VB / 4;
+    static constexpr int W = NV * WPV;                         // 32-bit words per lane per row
+    static constexpr int UNIT_BYTES = kUnitTok * ROWB;         // one K (or V) unit
+    static constexpr int SCALE_BYTES = KV == 0 ? 0 : kUnitTok * 4;
+    static constexpr int STAGE_BYTES = 2 * UNIT_BYTES + 2 * SCALE_BYTES;
+    // head dim owned by (chunk lane c, element e)
+    __device__ static __forceinline__ int dim_of(int c, int e) {
+        return (e / EV) * 8 * EV + c * EV + (e % EV);
+    }
+    __device__ static __forceinline__ int byte_off(int c, int v) { return v * 8 * VB + c * VB; }
+};
+
+template <int D, int KV>
+struct Acc {
+    float m, l;
+    float o[Cfg<D, KV>::E];
+    __device__ __forceinline__ void reset() {
+        m = -INFINITY;
+        l = 0.f;
+#pragma unroll
+        for (int e = 0; e < Cfg<D, KV>::E; ++e) o[e] = 0.f;
+    }
+};
+
+template <int KV, int W>
+__device__ __forceinline__ void words_to_float(const uint32_t (&w)[W], float* f) {
+    if (KV == 0) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            f[4 * i + 0] = (float)(int8_t)(w[i] & 0xff);
+            f[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xff);
+            f[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xff);
+            f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
+        }
+    }
+}
+
+// One 16-token unit: 4 token rows per lane group.  kf/vf: this lane's words of rows
+// 4p+g.  ksc/vsc: reciprocal scales of those rows (int8 only).  Scores are in log2
+// units (q pre-multiplied by log2(e)/temperature).
+template <int D, int KV>
+__device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::W],
+                                            uint32_t (&vf)[4][Cfg<D, KV>::W], const float (&ksc)[4],
+                                            const float (&vsc)[4], const float (&q)[Cfg<D, KV>::E],
+                                            int nvalid, int g, Acc<D, KV>& a) {
+    using C = Cfg<D, KV>;
+    float s[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float f[C::E];
+        words_to_float<KV, C::W>(kf[p], f);
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) acc = fmaf(q[e], f[e], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (KV == 1) acc *= ksc[p];
+        s[p] = (4 * p + g < nvalid) ? acc : -INFINITY;
+    }
+    const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    if (mx > -INFINITY) {
+        const float m_new = fmaxf(a.m, mx);
+        const float corr = fast_exp2(a.m - m_new);  // a.m == -inf -> 0
+        float pw[4];
+        float ps = 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            pw[p] = fast_exp2(s[p] - m_new);  // masked rows -> 0
+            ps += pw[p];
+        }
+        a.l = fmaf(a.l, corr, ps);
+        a.m = m_new;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) a.o[e] *= corr;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (4 * p + g >= nvalid) continue;  // never touch bytes past the context end
+            float f[C::E];
+            words_to_float<KV, C::W>(vf[p], f);
+            const float w = (KV == 1) ? pw[p] * vsc[p] : pw[p];
+#pragma unroll
+            for (int e = 0; e < C::E; ++e) a.o[e] = fmaf(w, f[e], a.o[e]);
+        }
+    }
+}
+
+// Merge the 4 lane groups of a warp (xor 8, 16); afterwards every lane holds the
+// warp-wide (m, l, o) for its dim chunk.
+template <int D, int KV>
+__device__ __forceinline__ void warp_merge(Acc<D, KV>& a) {
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, a.m, off);
+        const float lo = __shfl_xor_sync(0xffffffffu, a.l, off);
+        const float mn = fmaxf(a.m, mo);
+        const float wa = (a.m == -INFINITY) ? 0.f : fast_exp2(a.m - mn);
+        const float wb = (mo == -INFINITY) ? 0.f : fast_exp2(mo - mn);
+        a.l = a.l * wa + lo * wb;
+#pragma unroll
+        for (int e = 0; e < Cfg<D, KV>::E; ++e) {
+            const float oo = __shfl_xor_sync(0xffffffffu, a.o[e], off);
+            a.o[e] = a.o[e] * wa + oo * wb;
+        }
+        a.m = mn;
+    }
+}
+
+enum EmitKind { kEmitFinal = 0, kEmitWorkspace = 1 };
+
+// Final / partial write of one row's merged (M, L, O[d]) by thread d (< D).
+__device__ __forceinline__ void emit_row(const DecodeArgs& a, int kind, int64_t row, int64_t slot,
+                                         int D, int d, float M, float L, float O) {
+    if (kind == kEmitWorkspace) {
+        a.ws_o[slot * D + d] = O;
+        if (d == 0) {
+            a.ws_m[slot] = M;
+            a.ws_l[slot] = L;
+        }
+    } else if (a.part_m) {
+        a.part_o[row * D + d] = O;
+        if (d == 0) {
+            a.part_m[row] = M * kLn2;  // natural-log units at the API
+            a.part_l[row] = L;
+        }
+    } else {
+        a.out[row * D + d] = O / (L + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+        if (d == 0 && a.lse_out) a.lse_out[row] = (L > 0.f) ? (M + log2f(L)) * kLn2 : -INFINITY;
+    }
+}
+
+// Cross-warp merge through shared memory.  red: [NW][D+2].  Must be called by all
+// threads of the CTA (contains one __syncthreads).
+template <int D, int KV, int NW>
+__device__ __forceinline__ void cta_merge_emit(float* red, Acc<D, KV>& acc, int warp, int lane,
+                                               const DecodeArgs& a, int kind, int64_t row,
+                                               int64_t slot) {
+    using C = Cfg<D, KV>;
+    warp_merge<D, KV>(acc);
+    if (lane < 8) {
+        float* r = red + warp * (D + 2);
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) r[C::dim_of(lane, e)] = acc.o[e];
+        if (lane == 0) {
+            r[D] = acc.m;
+            r[D + 1] = acc.l;
+        }
+    }
+    __syncthreads();
+    const int d = threadIdx.x;
+    if (d < D) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) M = fmaxf(M, red[w * (D + 2) + D]);
+        float L = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float mw = red[w * (D + 2) + D];
+            const float wt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - M);
+            L = fmaf(red[w * (D + 2) + D + 1], wt, L);
+            O = fmaf(red[w * (D + 2) + d], wt, O);
+        }
+        emit_row(a, kind, row, slot, D, d, M, L, O);
+    }
+}
+
+// q row -> registers, pre-scaled; optional pairwise RoPE (cpu_attention_kernel.cpp:13-19).
+template <int D, int KV>
+__device__ __forceinline__ void load_q(const DecodeArgs& a, int64_t row, int c,
+                                       float (&q)[Cfg<D, KV>::E]) {
+    using C = Cfg<D, KV>;
+    const float* qr = a.q + row * D;
+#pragma unroll
+    for (int e = 0; e < C::E; e += 2) {
+        const int d0 = C::dim_of(c, e);  // even, and dim_of(c, e+1) == d0 + 1
+        float x0 = qr[d0], x1 = qr[d0 + 1];
+        if (a.rope) {
+            const float cs = a.rope[d0], sn = a.rope[d0 + 1];
+            const float r0 = x0 * cs - x1 * sn, r1 = x0 * sn + x1 * cs;
+            x0 = r0;
+            x1 = r1;
+        }
+        q[e] = x0 * a.qscale;
+        q[e + 1] = x1 * a.qscale;
+    }
+}
+
+__device__ __forceinline__ int row_ctx(const DecodeArgs& a, int b) {
+    int ctx = a.ctx_lens ? a.ctx_lens[b] : a.T;
+    const int cap = a.num_tiles * a.tile_size;
+    return ctx < 0 ? 0 : (ctx > cap ? cap : ctx);
+}
+
+// page_table.hpp:44-49 + kv_tile_cache.hpp:23: -1 when unmapped / out of range.
+__device__ __forceinline__ int lookup_page(const DecodeArgs& a, int beam, int h, int tile) {
+    const int64_t idx = ((int64_t)beam * a.H + h) * a.num_tiles + tile;
+    if (idx < 0 || idx >= (int64_t)a.num_beams * a.H * a.num_tiles) return -1;
+    const int page = __ldg(a.table + idx);
+    return (page < 0 || page >= a.total_pages) ? -1 : page;
+}
+
+// ------------------------------------------------------------------ direct (a1)
+template <int D, int KV>
+__global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeArgs a) {
+    using C = Cfg<D, KV>;
+    constexpr int NW = 4;
+    __shared__ float red[NW * (D + 2)];
+    const int64_t row = blockIdx.x;
+    const int split = blockIdx.y;
+    const int b = (int)(row / a.H), h = (int)(row % a.H);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 3, c = lane & 7;
+    const int ctx = row_ctx(a, b);
+    const int units = (ctx + kUnitTok - 1) / kUnitTok;
+    const int per = (units + a.num_splits - 1) / a.num_splits;
+    const int u0 = split * per;
+    const int u1 = min(units, u0 + per);
+    const int beam = a.beam_ids ? a.beam_ids[b] : b;
+    const int upt = a.tile_size / kUnitTok;
+
+    float q[C::E];
+    load_q<D, KV>(a, row, c, q);
+    Acc<D, KV> acc;
+    acc.reset();
+
+    for (int u = u0 + warp; u < u1; u += NW) {
+        const int tile = u / upt, sub = u - tile * upt;
+        const int page = lookup_page(a, beam, h, tile);
+        if (page < 0) continue;  // ...fused.cu:32 / cpu_attention_kernel.cpp:73
+        const int nvalid = min(kUnitTok, ctx - u * kUnitTok);
+        const int64_t tok0 = (int64_t)page * a.tile_size + sub * kUnitTok;
+        const uint8_t* kb = a.k_pool + tok0 * C::ROWB;
+        const uint8_t* vb = a.v_pool + tok0 * C::ROWB;
+        uint32_t kf[4][C::W], vf[4][C::W];
+        float ksc[4] = {1.f, 1.f, 1.f, 1.f}, vsc[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int t = 4 * p + g;
+#pragma unroll
+            for (int v = 0; v < C::NV; ++v) {
+                const uint8_t* ka = kb + t * C::ROWB + C::byte_off(c, v);
+                const uint8_t* va = vb + t * C::ROWB + C::byte_off(c, v);
+                if (C::VB == 16) {
+                    uint4 x = ldg_stream_128(ka), y = ldg_stream_128(va);
+                    kf[p][v * 4 + 0] = x.x; kf[p][v * 4 + 1] = x.y; kf[p][v * 4 + 2] = x.z; kf[p][v * 4 + 3] = x.w;
+                    vf[p][v * 4 + 0] = y.x; vf[p][v * 4 + 1] = y.y; vf[p][v * 4 + 2] = y.z; vf[p][v * 4 + 3] = y.w;
+                } else {
+                    uint2 x = ldg_stream_64(ka), y = ldg_stream_64(va);
+                    kf[p][v * 2 + 0] = x.x; kf[p][v * 2 + 1] = x.y;
+                    vf[p][v * 2 + 0] = y.x; vf[p][v * 2 + 1] = y.y;
+                }
+            }
+            if (KV == 1) {
+                ksc[p] = __frcp_rn(__ldg(a.k_scales + tok0 + t));
+                vsc[p] = __frcp_rn(__ldg(a.v_scales + tok0 + t));
+            }
+        }
+        unit_update<D, KV>(kf, vf, ksc, vsc, q, nvalid, g, acc);
+    }
+
+    const bool final_row = (a.num_splits == 1);
+    cta_merge_emit<D, KV, NW>(red, acc, warp, lane, a, final_row ? kEmitFinal : kEmitWorkspace, row,
+                              row * a.num_splits + split);
+}
+
+// Combine the direct kernel's splits: one CTA of D threads per row.
+template <int D>
+__global__ void combine_splits_kernel(const DecodeArgs a) {
+    const int64_t row = blockIdx.x;
+    const int d = threadIdx.x;
+    const int ns = a.num_splits;
+    float M = -INFINITY;
+    for (int s = 0; s < ns; ++s) M = fmaxf(M, a.ws_m[row * ns + s]);
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < ns; ++s) {
+        const float ms = a.ws_m[row * ns + s];
+        const float wt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
+        L = fmaf(a.ws_l[row * ns + s], wt, L);
+        O = fmaf(a.ws_o[(row * ns + s) * D + d], wt, O);
+    }
+    emit_row(a, kEmitFinal, row, 0, D, d, M, L, O);
+}
+
+// ---------------------------------------------------------------- overlap (a2)
+// Linear (row, unit) space.  Rows are ordered b-major then h; row (b, h) owns
+// units(b) = ceil(ctx(b) / 16) consecutive positions.
+struct RowMap {
+    const int* prefix;  // shared memory: prefix[b] = sum_{b'<b} units(b'), B+1 entries; null => uniform
+    int B, H, U;        // U: units per row when uniform
+    __device__ __forceinline__ int64_t total() const {
+        return prefix ? (int64_t)prefix[B] * H : (int64_t)B * H * U;
+    }
+    __device__ __forceinline__ int units_of(int b) const { return prefix ? prefix[b + 1] - prefix[b] : U; }
+    __device__ __forceinline__ int64_t row_start(int b, int h) const {
+        return prefix ? (int64_t)prefix[b] * H + (int64_t)h * (prefix[b + 1] - prefix[b])
+                      : ((int64_t)b * H + h) * U;
+    }
+    __device__ __forceinline__ void locate(int64_t lin, int& b, int& h, int& u, int& Ub) const {
+        if (!prefix) {
+            const int64_t per_b = (int64_t)H * U;
+            b = (int)(lin / per_b);
+            const int rem = (int)(lin - (int64_t)b * per_b);
+            h = rem / U;
+            u = rem - h * U;
+            Ub = U;
+        } else {
+            int lo = 0, hi = B;  // largest b with prefix[b]*H <= lin
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)prefix[mid] * H <= lin) lo = mid; else hi = mid;
+            }
+            b = lo;
+            Ub = prefix[b + 1] - prefix[b];
+            const int64_t rem = lin - (int64_t)prefix[b] * H;
+            h = (int)(rem / Ub);
+            u = (int)(rem - (int64_t)h * Ub);
+        }
+    }
+};
+
+__device__ __forceinline__ int64_t share_start(int64_t total, int G, int c) {
+    return (total * c) / G;
+}
+
+struct Walker {
+    int64_t lin, lin_end;
+    int b, h, U, u0, u1, u;
+    __device__ __forceinline__ bool next_segment(const RowMap& rm) {
+        if (lin >= lin_end) return false;
+        int uu;
+        rm.locate(lin, b, h, uu, U);
+        u0 = uu;
+        const int64_t left = lin_end - lin;
+        u1 = (int)min((int64_t)U, (int64_t)u0 + left);
+        lin += (u1 - u0);
+        return true;
+    }
+};
+
+template <int D, int KV, int NW, int S>
+__global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const DecodeArgs a) {
+    using C = Cfg<D, KV>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    // carve: stages | barriers | meta | red[2] | prefix
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)NW * S * C::STAGE_BYTES);
+    int* meta = reinterpret_cast<int*>(bars + NW * S);
+    float* red = reinterpret_cast<float*>(meta + NW * S);
+    int* prefix = reinterpret_cast<int*>(red + 2 * NW * (D + 2));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 3, c = lane & 7;
+    const int G = gridDim.x, cta = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NW * S; ++i) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+    }
+    RowMap rm;
+    rm.B = a.B;
+    rm.H = a.H;
+    rm.U = (row_ctx(a, 0) + kUnitTok - 1) / kUnitTok;
+    rm.prefix = nullptr;
+    if (a.ctx_lens) {
+        // Block-serial prefix of units per b (B is small; one pass, thread 0 finishes it).
+        for (int i = threadIdx.x; i < a.B; i += blockDim.x)
+            prefix[i + 1] = (row_ctx(a, i) + kUnitTok - 1) / kUnitTok;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            prefix[0] = 0;
+            for (int i = 0; i < a.B; ++i) prefix[i + 1] += prefix[i];
+        }
+        rm.prefix = prefix;
+    }
+    __syncthreads();
+
+    const int64_t total = rm.total();
+    const int64_t my_start = share_start(total, G, cta), my_end = share_start(total, G, cta + 1);
+    const int upt = a.tile_size / kUnitTok;
+    const uint64_t policy = l2_policy_evict_first();
+
+    // ---- producer state (warp-uniform; lane 0 issues) ----
+    Walker pw;
+    pw.lin = my_start;
+    pw.lin_end = my_end;
+    bool p_has = false;
+    int p_page = -1, p_ctx = 0;
+    uint32_t issued = 0;
+    auto p_fetch = [&]() {  // page id + ctx for the producer's current (b, h, u)
+        const int beam = a.beam_ids ? a.beam_ids[pw.b] : pw.b;
+        p_page = lookup_page(a, beam, pw.h, pw.u / upt);
+    };
+    auto p_advance_segment = [&]() -> bool {
+        while (pw.next_segment(rm)) {
+            pw.u = pw.u0 + warp;
+            if (pw.u < pw.u1) {
+                p_ctx = row_ctx(a, pw.b);
+                return true;
+            }
+        }
+        return false;
+    };
+    p_has = p_advance_segment();
+    if (p_has) p_fetch();
+
+    const uint32_t my_stage0 = smem_u32(stage_base + (size_t)warp * S * C::STAGE_BYTES);
+    const uint32_t my_bar0 = smem_u32(bars + warp * S);
+    int* my_meta = meta + warp * S;
+
+    auto produce = [&]() {
+        if (!p_has) return;
+        const uint32_t st = issued % S;
+        if (lane == 0) {
+            const int nvalid = (p_page >= 0) ? min(kUnitTok, p_ctx - pw.u * kUnitTok) : 0;
+            my_meta[st] = nvalid;
+            const uint32_t bar = my_bar0 + st * 8;
+            if (nvalid > 0) {
+                const int sub = pw.u % upt;
+                const int64_t tok0 = (int64_t)p_page * a.tile_size + sub * kUnitTok;
+                const uint32_t dst = my_stage0 + st * C::STAGE_BYTES;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+                if (a.evict_first) {
+                    bulk_g2s(dst, a.k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
+                    bulk_g2s(dst + C::UNIT_BYTES, a.v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
+                } else {
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(dst), "l"(a.k_pool + tok0 * C::ROWB), "r"(C::UNIT_BYTES), "r"(bar) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(dst + C::UNIT_BYTES), "l"(a.v_pool + tok0 * C::ROWB), "r"(C::UNIT_BYTES), "r"(bar) : "memory");
+                }
+                if (KV == 1) {
+                    bulk_g2s(dst + 2 * C::UNIT_BYTES, a.k_scales + tok0, C::SCALE_BYTES, bar, policy);
+                    bulk_g2s(dst + 2 * C::UNIT_BYTES + C::SCALE_BYTES, a.v_scales + tok0, C::SCALE_BYTES, bar, policy);
+                }
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+        ++issued;
+        pw.u += NW;
+        if (pw.u >= pw.u1) p_has = p_advance_segment();
+        if (p_has) p_fetch();
+    };
+
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) produce();
+
+    // ---- consumer ----
+    Walker cw;
+    cw.lin = my_start;
+    cw.lin_end = my_end;
+    uint32_t consumed = 0;
+    int seg_idx = 0;
+    Acc<D, KV> acc;
+    float q[C::E];
+
+    while (cw.next_segment(rm)) {
+        const int64_t row = (int64_t)cw.b * a.H + cw.h;
+        load_q<D, KV>(a, row, c, q);
+        acc.reset();
+        for (int u = cw.u0 + warp; u < cw.u1; u += NW) {
+            const uint32_t st = consumed % S;
+            mbar_wait(my_bar0 + st * 8, (consumed / S) & 1);
+            const int nvalid = my_meta[st];
+            if (nvalid > 0) {
+                const uint32_t sb = my_stage0 + st * C::STAGE_BYTES;
+                uint32_t kf[4][C::W], vf[4][C::W];
+                float ksc[4] = {1.f, 1.f, 1.f, 1.f}, vsc[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int t = 4 * p + g;
+#pragma unroll
+                    for (int v = 0; v < C::NV; ++v) {
+                        const uint32_t ka = sb + t * C::ROWB + C::byte_off(c, v);
+                        const uint32_t va = ka + C::UNIT_BYTES;
+                        if (C::VB == 16) {
+                            uint4 x = lds_128(ka), y = lds_128(va);
+                            kf[p][v * 4 + 0] = x.x; kf[p][v * 4 + 1] = x.y; kf[p][v * 4 + 2] = x.z; kf[p][v * 4 + 3] = x.w;
+                            vf[p][v * 4 + 0] = y.x; vf[p][v * 4 + 1] = y.y; vf[p][v * 4 + 2] = y.z; vf[p][v * 4 + 3] = y.w;
+                        } else {
+                            uint2 x = lds_64(ka), y = lds_64(va);
+                            kf[p][v * 2 + 0] = x.x; kf[p][v * 2 + 1] = x.y;
+                            vf[p][v * 2 + 0] = y.x; vf[p][v * 2 + 1] = y.y;
+                        }
+                    }
+                    if (KV == 1) {
+                        float ks, vs;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ks) : "r"(sb + 2 * C::UNIT_BYTES + t * 4));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vs) : "r"(sb + 2 * C::UNIT_BYTES + C::SCALE_BYTES + t * 4));
+                        ksc[p] = __frcp_rn(ks);
+                        vsc[p] = __frcp_rn(vs);
+                    }
+                }
+                unit_update<D, KV>(kf, vf, ksc, vsc, q, nvalid, g, acc);
+            }
+            __syncwarp();
+            ++consumed;
+            produce();  // refill the stage just drained
+        }
+        // Row boundary: full rows go straight to the output, cut rows to a partial slot.
+        const bool full = (cw.u0 == 0 && cw.u1 == cw.U);
+        const int64_t slot = (cw.u0 > 0) ? 2 * (int64_t)cta : 2 * (int64_t)cta + 1;
+        cta_merge_emit<D, KV, NW>(red + (seg_idx & 1) * NW * (D + 2), acc, warp, lane, a,
+                                  full ? kEmitFinal : kEmitWorkspace, row, slot);
+        ++seg_idx;
+    }
+}
+
+// Finish rows that were cut by a share boundary in the overlap kernel, and zero rows
+// with no keys.  One warp-group of D threads per row; recomputes the share geometry.
+template <int D>
+__global__ void combine_shares_kernel(const DecodeArgs a, int G) {
+    extern __shared__ int prefix_sm[];
+    RowMap rm;
+    rm.B = a.B;
+    rm.H = a.H;
+    rm.U = (row_ctx(a, 0) + kUnitTok - 1) / kUnitTok;
+    rm.prefix = nullptr;
+    if (a.ctx_lens) {
+        if (threadIdx.x == 0) {
+            prefix_sm[0] = 0;
+            for (int i = 0; i < a.B; ++i)
+                prefix_sm[i + 1] = prefix_sm[i] + (row_ctx(a, i) + kUnitTok - 1) / kUnitTok;
+        }
+        __syncthreads();
+        rm.prefix = prefix_sm;
+    }
+    const int64_t total = rm.total();
+    const int d = threadIdx.x % D;
+    const int rows_per_cta = blockDim.x / D;
+    const int64_t nrows = (int64_t)a.B * a.H;
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x / D; row < nrows;
+         row += (int64_t)gridDim.x * rows_per_cta) {
+        const int b = (int)(row / a.H), h = (int)(row % a.H);
+        const int U = rm.units_of(b);
+        if (U == 0) {
+            emit_row(a, kEmitFinal, row, 0, D, d, -INFINITY, 0.f, 0.f);
+            continue;
+        }
+        const int64_t L0 = rm.row_start(b, h), L1 = L0 + U;
+        // first / last share touching the row: largest c with share_start(c) <= x
+        auto share_of = [&](int64_t x) {
+            int cc = (int)((x * G) / total);
+            if (cc >= G) cc = G - 1;
+            while (cc + 1 < G && share_start(total, G, cc + 1) <= x) ++cc;
+            while (cc > 0 && share_start(total, G, cc) > x) --cc;
+            return cc;
+        };
+        const int c0 = share_of(L0), c1 = share_of(L1 - 1);
+        if (c0 == c1) continue;  // whole row handled inside one share -> already final
+        float M = -INFINITY;
+        for (int cc = c0; cc <= c1; ++cc) {
+            const int64_t slot = (share_start(total, G, cc) > L0) ? 2 * (int64_t)cc : 2 * (int64_t)cc + 1;
+            M = fmaxf(M, a.ws_m[slot]);
+        }
+        float L = 0.f, O = 0.f;
+        for (int cc = c0; cc <= c1; ++cc) {
+            const int64_t slot = (share_start(total, G, cc) > L0) ? 2 * (int64_t)cc : 2 * (int64_t)cc + 1;
+            const float ms = a.ws_m[slot];
+            const float wt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
+            L = fmaf(a.ws_l[slot], wt, L);
+            O = fmaf(a.ws_o[slot * D + d], wt, O);
+        }
+        emit_row(a, kEmitFinal, row, 0, D, d, M, L, O);
+    }
+}
+
+// Public LSE combine (natural-log m), n_parts x rows layout.
+__global__ void lse_combine_kernel(const float* __restrict__ pm, const float* __restrict__ pl,
+                                   const float* __restrict__ po, int n_parts, int64_t rows, int D,
+                                   float* __restrict__ out, float* __restrict__ lse_out) {
+    const int64_t row = blockIdx.x;
+    float M = -INFINITY;
+    for (int i = 0; i < n_parts; ++i) M = fmaxf(M, pm[i * rows + row]);
+    float L = 0.f;
+    for (int i = 0; i < n_parts; ++i) {
+        const float m = pm[i * rows + row];
+        L += (m == -INFINITY) ? 0.f : pl[i * rows + row] * __expf(m - M);
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float O = 0.f;
+        for (int i = 0; i < n_parts; ++i) {
+            const float m = pm[i * rows + row];
+            const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
+            O = fmaf(po[(i * rows + row) * D + d], w, O);
+        }
+        out[row * D + d] = O / (L + 1e-6f);
+    }
+    if (threadIdx.x == 0 && lse_out) lse_out[row] = (L > 0.f) ? M + logf(L) : -INFINITY;
+}
+
+// -------------------------------------------------------------------- host side
+constexpr int kOvWarps = 8;
+template <int D, int KV>
+struct OvCfg {
+    static constexpr int S = (KV == 0 && D == 128) ? 3 : ((KV == 0 || D == 128) ? 6 : 8);
+};
+
+static size_t ws_floats(int B, int H, int D) { return (size_t)(4096 + 2 * (size_t)B * H) * (D + 2); }
+
+static int choose_splits(int64_t rows, int max_units, int sm_count) {
+    const int64_t target = (int64_t)sm_count * 15;  // ~5 resident CTAs/SM x 3 waves
+    int64_t ns = (target + rows - 1) / rows;
+    const int cap_units = max_units / 4 > 0 ? max_units / 4 : 1;  // >= 4 units (1 per warp) per split
+    if (ns > cap_units) ns = cap_units;
+    if (ns > 64) ns = 64;
+    if (ns < 1) ns = 1;
+    return (int)ns;
+}
+
+template <int D, int KV>
+static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return PA_ERR_NO_DEVICE;
+    const int64_t rows = (int64_t)a.B * a.H;
+    if (ws_bytes < ws_floats(a.B, a.H, D) * sizeof(float) || !ws) return PA_ERR_WORKSPACE;
+    float* w = static_cast<float*>(ws);
+    const size_t nslots = 4096 + 2 * (size_t)rows;
+    a.ws_m = w;
+    a.ws_l = w + nslots;
+    a.ws_o = w + 2 * nslots;
+    if (!overlap) {
+        const int max_units = (a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok;
+        a.num_splits = choose_splits(rows, max_units, di.sm_count);
+        while ((size_t)rows * a.num_splits > nslots) --a.num_splits;
+        dim3 grid((unsigned)rows, (unsigned)a.num_splits);
+        paged_decode_direct_kernel<D, KV><<<grid, 128, 0, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        if (a.num_splits > 1) {
+            combine_splits_kernel<D><<<(unsigned)rows, D, 0, st>>>(a);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+        }
+        return PA_OK;
+    }
+    constexpr int S = OvCfg<D, KV>::S;
+    using C = Cfg<D, KV>;
+    const int G = di.sm_count;
+    const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
+    const size_t smem = (size_t)kOvWarps * S * C::STAGE_BYTES + (size_t)kOvWarps * S * (8 + 4) +
+                        2 * (size_t)kOvWarps * (D + 2) * sizeof(float) + prefix_bytes;
+    if (smem > (size_t)di.max_smem_optin) return PA_ERR_UNSUPPORTED;  // B too large for the prefix table
+    auto kern = paged_decode_overlap_kernel<D, KV, kOvWarps, S>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<G, kOvWarps * 32, smem, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int rows_per_cta = 256 / D;
+    int cgrid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
+    if (cgrid > G * 8) cgrid = G * 8;
+    combine_shares_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, G);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? PA_OK : (int)e;
+}
+
+static int decode_entry(int kv, bool overlap, const float* q, float* out, float* part_m,
+                        float* part_l, float* part_o, const void* k_pool, const void* v_pool,
+                        const float* k_scales, const float* v_scales, const int32_t* table,
+                        int num_beams, int H, int num_tiles, int total_pages,
+                        const int32_t* beam_ids, const int32_t* ctx_lens, int B, int T, int D,
+                        int tile_size, float temperature, const float* rope, float* lse_out,
+                        void* ws, size_t ws_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(q && k_pool && v_pool && table);
+    PA_CHECK_ARG(part_m ? (part_l && part_o) : (out != nullptr));
+    PA_CHECK_ARG(num_beams > 0 && H > 0 && num_tiles > 0 && total_pages > 0 && B >= 0 && T >= 0);
+    PA_CHECK_ARG(temperature != 0.f && tile_size > 0);
+    PA_CHECK_ARG((uintptr_t)k_pool % 16 == 0 && (uintptr_t)v_pool % 16 == 0);
+    if (kv == 1) PA_CHECK_ARG(k_scales && v_scales && (uintptr_t)k_scales % 16 == 0 && (uintptr_t)v_scales % 16 == 0);
+    if ((D != 64 && D != 128) || tile_size % kUnitTok != 0) return PA_ERR_UNSUPPORTED;
+    if (B == 0) return PA_OK;
+    DecodeArgs a{};
+    a.q = q; a.out = out; a.lse_out = lse_out;
+    a.part_m = part_m; a.part_l = part_l; a.part_o = part_o;
+    a.k_pool = static_cast<const uint8_t*>(k_pool);
+    a.v_pool = static_cast<const uint8_t*>(v_pool);
+    a.k_scales = k_scales; a.v_scales = v_scales;
+    a.table = table; a.beam_ids = beam_ids; a.ctx_lens = ctx_lens; a.rope = rope;
+    a.num_beams = num_beams; a.H = H; a.num_tiles = num_tiles; a.total_pages = total_pages;
+    a.B = B; a.T = T; a.tile_size = tile_size;
+    a.num_splits = 1;
+    a.evict_first = beam_ids ? 0 : 1;  // shared-prefix pages are re-read by sibling beams: keep them in L2
+    a.qscale = kLog2e / temperature;
+    cudaStream_t st = as_stream(stream);
+    if (kv == 0) {
+        return D == 128 ? launch_decode<128, 0>(a, overlap, ws, ws_bytes, st)
+                        : launch_decode<64, 0>(a, overlap, ws, ws_bytes, st);
+    }
+    return D == 128 ? launch_decode<128, 1>(a, overlap, ws, ws_bytes, st)
+                    : launch_decode<64, 1>(a, overlap, ws, ws_bytes, st);
+}
+
+}  // namespace pa
+
+using namespace pa;
+
+PA_API size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim) {
+    if (B < 0 || num_heads <= 0 || head_dim <= 0) return 0;
+    return ws_floats(B, num_heads, head_dim) * sizeof(float);
+}
+
+#define PA_DECODE_COMMON_PARAMS                                                                  \
+    const int32_t *d_table, int num_beams, int num_heads, int num_tiles, int total_pages,        \
+        const int32_t *d_beam_ids, const int32_t *d_ctx_lens, int B, int T, int head_dim,        \
+        int tile_size, float temperature, const float *d_rope
+#define PA_DECODE_COMMON_ARGS                                                                    \
+    d_table, num_beams, num_heads, num_tiles, total_pages, d_beam_ids, d_ctx_lens, B, T,         \
+        head_dim, tile_size, temperature, d_rope
+
+PA_API int pa_paged_decode_f16(const float* d_q, float* d_out, const void* d_k_pool,
+                               const void* d_v_pool, PA_DECODE_COMMON_PARAMS, float* d_lse_out,
+                               void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
+    return decode_entry(0, false, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
+                        nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_f16_overlap(const float* d_q, float* d_out, const void* d_k_pool,
+                                       const void* d_v_pool, PA_DECODE_COMMON_PARAMS,
+                                       float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                                       pa_stream_t stream) {
+    return decode_entry(0, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
+                        nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_i8(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                              const int8_t* d_v_pool, const float* d_k_scales,
+                              const float* d_v_scales, PA_DECODE_COMMON_PARAMS, float* d_lse_out,
+                              void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
+    return decode_entry(1, false, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool,
+                        d_k_scales, d_v_scales, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace,
+                        workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                                      const int8_t* d_v_pool, const float* d_k_scales,
+                                      const float* d_v_scales, PA_DECODE_COMMON_PARAMS,
+                                      float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                                      pa_stream_t stream) {
+    return decode_entry(1, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool,
+                        d_k_scales, d_v_scales, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace,
+                        workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
+                                       float* d_part_o, const void* d_k_pool, const void* d_v_pool,
+                                       PA_DECODE_COMMON_PARAMS, void* d_workspace,
+                                       size_t workspace_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
+    return decode_entry(0, true, d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+                        nullptr, nullptr, PA_DECODE_COMMON_ARGS, nullptr, d_workspace,
+                        workspace_bytes, stream);
+}
+
+PA_API int pa_lse_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                          int n_parts, int rows, int head_dim, float* d_out, float* d_lse_out,
+                          pa_stream_t stream) {
+    PA_CHECK_ARG(d_part_m && d_part_l && d_part_o && d_out && n_parts > 0 && rows >= 0 && head_dim > 0);
+    if (rows == 0) return PA_OK;
+    lse_combine_kernel<<<rows, 128, 0, as_stream(stream)>>>(d_part_m, d_part_l, d_part_o, n_parts,
+                                                             rows, head_dim, d_out, d_lse_out);
+    PA_RETURN_LAUNCH_STATUS();
+}

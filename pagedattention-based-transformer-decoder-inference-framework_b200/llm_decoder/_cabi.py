@@ -1,0 +1,95 @@
+"""ctypes binding of libpa_b200.so (include/pa_b200.h).
+
+torch tensors only supply device pointers (`.data_ptr()`) and the current stream; every
+computation on the path happens inside the hand-written sm_100a kernels.  There is no
+fallback: a missing or unloadable library raises at first use.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libpa_b200.so")
+
+PA_OK = 0
+ACT = {"": 0, None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+_lib = None
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+_DECODE_COMMON = [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]
+
+_SIGS = {
+    "pa_version": ([], _i32),
+    "pa_error_string": ([_i32], C.c_char_p),
+    "pa_device_info": ([C.POINTER(_i32)] * 3, _i32),
+    "pa_page_table_clear": ([_vp, _i64, _vp], _i32),
+    "pa_page_table_update": ([_vp, _i64, _vp, _vp, _i32, _vp], _i32),
+    "pa_page_table_lookup": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_kv_gather": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp], _i32),
+    "pa_kv_append_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_kv_append_f32_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_kv_append_f32_i8": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_decode_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_paged_decode_f16": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_f16_overlap": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_i8": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_i8_overlap": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_f16_partial": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
+    "pa_lse_combine": ([_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pa_quantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
+    "pa_batch_quantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),
+    "pa_absmax": ([_vp, _i64, _vp, _vp], _i32),
+    "pa_minmax_scale": ([_vp, _i64, _vp, _vp], _i32),
+    "pa_batch_minmax_scale": ([_vp, _i32, _i32, _vp, _vp], _i32),
+    "pa_dequantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
+    "pa_batch_dequantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),
+    "pa_gemm_i8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp], _i32),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+class PAError(RuntimeError):
+    """A non-zero status from libpa_b200.so (mirrors the reference's C++ exception ->
+    pybind11 -> RuntimeError path, SURVEY 8b 'Errors')."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PAError(
+                f"{LIB_PATH} is missing: build it with `python build.py` in {_PKG} "
+                "(there is no CPU or PyTorch fallback for this path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(handle, name)  # AttributeError if the header and the .so disagree
+            fn.argtypes = args
+            fn.restype = res
+        _lib = handle
+    return _lib
+
+
+def check(status, what=""):
+    if status != PA_OK:
+        msg = lib().pa_error_string(status).decode()
+        raise PAError(f"{what or 'pa_b200'} failed: {msg} (status {status})")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    sm, maj, mnr = _i32(), _i32(), _i32()
+    check(lib().pa_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "pa_device_info")
+    return sm.value, maj.value, mnr.value

@@ -1,0 +1,163 @@
+"""AttentionCUDA / AttentionTileLauncher -- the reference's attention entry points over
+libpa_b200.so.
+
+Mirrors attention/attention_config.hpp:5-26 (`AttentionCUDA::forward`, 17 positional
+arguments, same names and order) and attention/attention_tile_launcher.hpp:35-90.
+Differences that are decisions: the KV storage dtype comes from the
+`kv_cache` object, not from runtime heuristics on temperature/top_k (D-a4); softmax is
+global over the context (D1); `out` is overwritten (D9); in-attention top-k/top-p is
+rejected unless disabled (D6; the launcher default top_k=1 would zero every key but one);
+`rerank_scores`, when given, receives the per-(b,h) log-sum-exp (D10).
+
+q / out may be CUDA tensors (zero copy) or HOST buffers (numpy arrays or CPU tensors); host
+buffers are staged through pinned memory and copied inside the call, which is what the
+end-to-end bench measures.
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+class _HostStage:
+    """Pinned staging buffers reused across calls (per shape)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, shape, dtype, device):
+        k = (key, tuple(shape), dtype, str(device))
+        if k not in self.bufs:
+            self.bufs[k] = (torch.empty(shape, dtype=dtype).pin_memory(),
+                            torch.empty(shape, dtype=dtype, device=device))
+        return self.bufs[k]
+
+
+_stage = _HostStage()
+
+
+def _is_host(x):
+    return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+
+
+def _to_device(x, key, device, dtype):
+    """Host buffer -> device tensor via a pinned staging buffer (async H2D on the current stream)."""
+    src = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+    pinned, dev = _stage.get(key, src.shape, dtype, device)
+    pinned.copy_(src)
+    dev.copy_(pinned, non_blocking=True)
+    return dev
+
+
+class AttentionTileLauncher:
+    """attention/attention_tile_launcher.hpp:35-90."""
+
+    @staticmethod
+    def launch(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
+               use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
+               rerank_scores=None, debug=False, ctx_lens=None):
+        if kv_cache is None:
+            raise ValueError("AttentionTileLauncher.launch: kv_cache is required (paged path only)")
+        if top_k not in (0, None) or top_p < 1.0:
+            raise NotImplementedError(
+                "in-attention top-k/top-p filtering is not on the GPU path (SURVEY App. A D6); "
+                "pass top_k=0, top_p=1.0")
+        pt = kv_cache.page_table_
+        dev = kv_cache.key_buffer_.device
+        assert H == pt.num_heads_ and D == kv_cache.head_dim_
+        host_io = _is_host(q)
+        d_q = _to_device(q, "q", dev, torch.float32) if host_io else q
+        host_out = _is_host(out)
+        d_out = _stage.get("out", (B, H, D), torch.float32, dev)[1] if host_out else out
+        assert d_q.dtype == torch.float32 and d_q.is_contiguous() and d_q.numel() == B * H * D
+        assert d_out.dtype == torch.float32 and d_out.is_contiguous() and d_out.numel() == B * H * D
+        d_beam = None
+        if beam_ids is not None:
+            d_beam = beam_ids if (isinstance(beam_ids, torch.Tensor) and beam_ids.is_cuda) else \
+                torch.as_tensor(np.asarray(beam_ids), dtype=torch.int32).to(dev)
+            assert d_beam.dtype == torch.int32
+        d_ctx = None
+        if ctx_lens is not None:
+            d_ctx = ctx_lens if (isinstance(ctx_lens, torch.Tensor) and ctx_lens.is_cuda) else \
+                torch.as_tensor(np.asarray(ctx_lens), dtype=torch.int32).to(dev)
+        d_rope = None
+        if rotary_emb is not None:
+            d_rope = rotary_emb if (isinstance(rotary_emb, torch.Tensor) and rotary_emb.is_cuda) else \
+                torch.as_tensor(np.asarray(rotary_emb), dtype=torch.float32).to(dev)
+        d_lse = None
+        host_lse = rerank_scores is not None and _is_host(rerank_scores)
+        if rerank_scores is not None:
+            d_lse = torch.empty((B, H), dtype=torch.float32, device=dev) if host_lse else rerank_scores
+        table = pt.device_data()
+        ws = kv_cache.workspace(B)
+        lib = _cabi.lib()
+        common = (table.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kv_cache.total_pages_,
+                  _cabi.ptr(d_beam), _cabi.ptr(d_ctx), B, T, D, kv_cache.tile_size_, float(temperature),
+                  _cabi.ptr(d_rope), _cabi.ptr(d_lse), ws.data_ptr(), ws.numel(), None)
+        with torch.cuda.device(dev):
+            common = common[:-1] + (_cabi.stream(),)
+            if kv_cache.dtype == "f16":
+                fn = lib.pa_paged_decode_f16_overlap if use_overlap else lib.pa_paged_decode_f16
+                st = fn(d_q.data_ptr(), d_out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                        kv_cache.value_buffer_.data_ptr(), *common)
+            else:
+                fn = lib.pa_paged_decode_i8_overlap if use_overlap else lib.pa_paged_decode_i8
+                st = fn(d_q.data_ptr(), d_out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                        kv_cache.value_buffer_.data_ptr(), kv_cache.k_scales_.data_ptr(),
+                        kv_cache.v_scales_.data_ptr(), *common)
+            _cabi.check(st, "pa_paged_decode")
+            if debug:  # attention_tile_launcher.hpp:84-88
+                torch.cuda.synchronize(dev)
+            if host_out:
+                pinned = _stage.get("out", (B, H, D), torch.float32, dev)[0]
+                pinned.copy_(d_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                dst = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+                dst.view(B, H, D).copy_(pinned)
+            if host_lse:
+                dst = torch.from_numpy(rerank_scores) if isinstance(rerank_scores, np.ndarray) else rerank_scores
+                dst.view(B, H).copy_(d_lse.cpu())
+        return out
+
+
+class AttentionCUDA:
+    """attention/attention_config.hpp:5-26 / attention_cuda.cu:41-95."""
+
+    @staticmethod
+    def forward(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
+                use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
+                rerank_scores=None, debug=False, ctx_lens=None):
+        return AttentionTileLauncher.launch(q, out, B, H, D, T, beam_ids, kv_cache, rotary_emb,
+                                            is_prefill, use_fp16, use_overlap, temperature, top_k,
+                                            top_p, rerank_scores, debug, ctx_lens)
+
+
+def paged_decode_partial(q, kv_cache, B, T, temperature=1.0, beam_ids=None, ctx_lens=None, rotary_emb=None):
+    """Un-normalised (m, l, O) of this rank's pages (multi-GPU split-KV)."""
+    pt = kv_cache.page_table_
+    dev = kv_cache.key_buffer_.device
+    H, D = pt.num_heads_, kv_cache.head_dim_
+    pm = torch.empty((B, H), dtype=torch.float32, device=dev)
+    pl = torch.empty((B, H), dtype=torch.float32, device=dev)
+    po = torch.empty((B, H, D), dtype=torch.float32, device=dev)
+    ws = kv_cache.workspace(B)
+    with torch.cuda.device(dev):
+        st = _cabi.lib().pa_paged_decode_f16_partial(
+            q.data_ptr(), pm.data_ptr(), pl.data_ptr(), po.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+            kv_cache.value_buffer_.data_ptr(), pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_,
+            kv_cache.total_pages_, _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T, D, kv_cache.tile_size_,
+            float(temperature), _cabi.ptr(rotary_emb), ws.data_ptr(), ws.numel(), _cabi.stream())
+    _cabi.check(st, "pa_paged_decode_f16_partial")
+    return pm, pl, po
+
+
+def lse_combine(part_m, part_l, part_o, out=None, lse_out=None):
+    """part_m/l [n_parts, rows], part_o [n_parts, rows, D] -> out [rows, D]."""
+    n_parts, rows, D = part_o.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.float32, device=part_o.device)
+    with torch.cuda.device(part_o.device):
+        _cabi.check(_cabi.lib().pa_lse_combine(part_m.data_ptr(), part_l.data_ptr(), part_o.data_ptr(),
+                                               n_parts, rows, D, out.data_ptr(), _cabi.ptr(lse_out),
+                                               _cabi.stream()), "pa_lse_combine")
+    return out

@@ -1,0 +1,191 @@
+"""KVTileCache -- GPU page pool + page table + LRU registration.
+
+Mirrors kv_cache/kv_tile_cache.hpp:9-80 / kv_tile_cache.cpp:7-128: two device pools
+(`key_buffer_`, `value_buffer_`) of `total_pages * tile_size * head_dim` elements, page p
+of either pool starting at element p*tile_size*head_dim (cpp:52-62), K and V of a tile
+sharing one page id.  Storage dtype: 'f16' (fp16 pages) or 'i8' (int8 pages plus one f32
+scale per (page, row) for K and for V).
+
+Decisions taken where the reference contradicts itself: page ids come
+from a free list (the reference's `map.size()` re-issues live ids after an eviction),
+eviction clears the device entry, and the page-table dimensions are given explicitly with
+`configure_table(num_beams, num_heads, num_tiles)` (the reference passes
+(total_pages, head_dim, tile_size) into PageTable::init by mistake, cpp:23).  64-bit page
+offsets (D17).
+"""
+import threading
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .page_table import PageTable
+
+_DTYPES = {"f16": torch.float16, "i8": torch.int8}
+
+
+class KVTileCache:
+    def __init__(self, dtype="f16", device=None):
+        if dtype not in _DTYPES:
+            raise ValueError("KVTileCache dtype must be 'f16' or 'i8'")
+        self.dtype = dtype
+        self._device = torch.device(device) if device is not None else None
+        self.key_buffer_ = self.value_buffer_ = None
+        self.k_scales_ = self.v_scales_ = None
+        self.tile_size_ = self.head_dim_ = self.total_pages_ = 0
+        self.page_table_ = PageTable(device)
+        self.tile_to_page_map_ = OrderedDict()  # (beam, head, tile) -> page, LRU order (oldest first)
+        self._free = []
+        self.mutex_ = threading.Lock()
+        self._ws = None
+
+    # ---- kv_tile_cache.cpp:18-24, 39-50 ------------------------------------------------
+    def init(self, num_pages, tile_size, head_dim):
+        if min(num_pages, tile_size, head_dim) <= 0:
+            raise ValueError("KVTileCache.init: sizes must be positive")
+        self.tile_size_, self.head_dim_, self.total_pages_ = int(tile_size), int(head_dim), int(num_pages)
+        self._allocate_buffers()
+        self.tile_to_page_map_.clear()
+        self._free = list(range(self.total_pages_ - 1, -1, -1))
+
+    def configure_table(self, num_beams, num_heads, num_tiles):
+        self.page_table_.init(num_beams, num_heads, num_tiles)
+
+    def _dev(self):
+        return self._device or torch.device("cuda", torch.cuda.current_device())
+
+    def _allocate_buffers(self):
+        shape = (self.total_pages_, self.tile_size_, self.head_dim_)
+        dev = self._dev()
+        self.key_buffer_ = torch.zeros(shape, dtype=_DTYPES[self.dtype], device=dev)
+        self.value_buffer_ = torch.zeros(shape, dtype=_DTYPES[self.dtype], device=dev)
+        if self.dtype == "i8":
+            self.k_scales_ = torch.ones(shape[:2], dtype=torch.float32, device=dev)
+            self.v_scales_ = torch.ones(shape[:2], dtype=torch.float32, device=dev)
+
+    def adopt_buffers(self, key_buffer, value_buffer, k_scales=None, v_scales=None):
+        """Use caller-provided pools [total_pages, tile_size, head_dim] (no copy)."""
+        assert key_buffer.shape == value_buffer.shape and key_buffer.is_contiguous() and value_buffer.is_contiguous()
+        assert key_buffer.dtype == _DTYPES[self.dtype]
+        self.total_pages_, self.tile_size_, self.head_dim_ = key_buffer.shape
+        self.key_buffer_, self.value_buffer_ = key_buffer, value_buffer
+        self.k_scales_, self.v_scales_ = k_scales, v_scales
+        self.tile_to_page_map_.clear()
+        self._free = list(range(self.total_pages_ - 1, -1, -1))
+
+    # ---- kv_tile_cache.cpp:27-37 -------------------------------------------------------
+    def resize(self, new_num_pages, new_tile_size):
+        with self.mutex_:
+            self.tile_size_, self.total_pages_ = int(new_tile_size), int(new_num_pages)
+            self._allocate_buffers()
+            self.tile_to_page_map_.clear()
+            self._free = list(range(self.total_pages_ - 1, -1, -1))
+            self.page_table_.clear()
+
+    # ---- kv_tile_cache.cpp:52-62 (device addresses) ------------------------------------
+    def _page_offset_bytes(self, page_id):
+        assert 0 <= page_id < self.total_pages_, "page_id out of range"
+        return page_id * self.tile_size_ * self.head_dim_ * self.key_buffer_.element_size()
+
+    def get_key_ptr(self, page_id):
+        return self.key_buffer_.data_ptr() + self._page_offset_bytes(page_id)
+
+    def get_value_ptr(self, page_id):
+        return self.value_buffer_.data_ptr() + self._page_offset_bytes(page_id)
+
+    # ---- kv_tile_cache.cpp:65-98 -------------------------------------------------------
+    def register_tile(self, beam_id, head_id, tile_id):
+        with self.mutex_:
+            key = (int(beam_id), int(head_id), int(tile_id))
+            page = self.tile_to_page_map_.get(key)
+            if page is None:
+                self._evict_if_needed()
+                page = self._free.pop()
+                self.tile_to_page_map_[key] = page
+                self.page_table_.assign(*key, page)
+            self.tile_to_page_map_.move_to_end(key)  # update_lru
+            return page
+
+    def _evict_if_needed(self):
+        if not self._free:
+            last, page = self.tile_to_page_map_.popitem(last=False)  # least recently used
+            self.page_table_.remove(*last)
+            self._free.append(page)
+
+    def sync_page_table_to_gpu(self):
+        self.page_table_.sync_to_gpu()
+
+    # ---- kv_tile_cache.cpp:105-125: raw K pool then raw V pool, no header ----------------
+    def save_to_file(self, path):
+        with open(path, "wb") as f:
+            f.write(self.key_buffer_.cpu().numpy().tobytes())
+            f.write(self.value_buffer_.cpu().numpy().tobytes())
+            if self.dtype == "i8":  # extension: scales follow the reference payload
+                f.write(self.k_scales_.cpu().numpy().tobytes())
+                f.write(self.v_scales_.cpu().numpy().tobytes())
+
+    def load_from_file(self, path):
+        n = self.key_buffer_.numel()
+        npdt = np.float16 if self.dtype == "f16" else np.int8
+        with open(path, "rb") as f:
+            k = np.frombuffer(f.read(n * np.dtype(npdt).itemsize), dtype=npdt)
+            v = np.frombuffer(f.read(n * np.dtype(npdt).itemsize), dtype=npdt)
+            if k.size != n or v.size != n:
+                raise RuntimeError(f"Failed to read KV pools from file: {path}")
+            self.key_buffer_.copy_(torch.from_numpy(k.copy()).view(self.key_buffer_.shape))
+            self.value_buffer_.copy_(torch.from_numpy(v.copy()).view(self.value_buffer_.shape))
+            if self.dtype == "i8":
+                ns = self.k_scales_.numel()
+                ks = np.frombuffer(f.read(ns * 4), dtype=np.float32)
+                vs = np.frombuffer(f.read(ns * 4), dtype=np.float32)
+                if ks.size == ns and vs.size == ns:
+                    self.k_scales_.copy_(torch.from_numpy(ks.copy()).view(self.k_scales_.shape))
+                    self.v_scales_.copy_(torch.from_numpy(vs.copy()).view(self.v_scales_.shape))
+
+    # ---- hot path: append (get_write_ptr + row write, hpp:29-34) -------------------------
+    def append(self, new_k, new_v, positions, beam_ids=None):
+        """new_k/new_v: [R, H, D] device tensors (f16 or f32); positions: [R] int32 device."""
+        pt = self.page_table_
+        table = pt.device_data()
+        R = new_k.shape[0]
+        assert new_k.is_contiguous() and new_v.is_contiguous() and new_k.shape == new_v.shape
+        assert new_k.shape[1] == pt.num_heads_ and new_k.shape[2] == self.head_dim_
+        lib = _cabi.lib()
+        common = (table.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, self.total_pages_,
+                  self.tile_size_, self.head_dim_, new_k.data_ptr(), new_v.data_ptr(),
+                  _cabi.ptr(beam_ids), positions.data_ptr(), R, _cabi.stream())
+        with torch.cuda.device(table.device):
+            if self.dtype == "i8":
+                assert new_k.dtype == torch.float32
+                st = lib.pa_kv_append_f32_i8(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(),
+                                             self.k_scales_.data_ptr(), self.v_scales_.data_ptr(), *common)
+            elif new_k.dtype == torch.float16:
+                st = lib.pa_kv_append_f16(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), *common)
+            else:
+                assert new_k.dtype == torch.float32
+                st = lib.pa_kv_append_f32_f16(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), *common)
+        _cabi.check(st, "pa_kv_append")
+
+    # ---- hot path: gather (KVTileCache::get materialised, hpp:21-26) ----------------------
+    def gather(self, which="k", beam_ids=None, rows=None, fill_byte=0):
+        pt = self.page_table_
+        table = pt.device_data()
+        pool = self.key_buffer_ if which == "k" else self.value_buffer_
+        R = rows if rows is not None else (beam_ids.numel() if beam_ids is not None else pt.num_beams_)
+        dense = torch.empty((R, pt.num_heads_, pt.num_tiles_ * self.tile_size_, self.head_dim_),
+                            dtype=pool.dtype, device=pool.device)
+        with torch.cuda.device(pool.device):
+            _cabi.check(_cabi.lib().pa_kv_gather(pool.data_ptr(), dense.data_ptr(), table.data_ptr(),
+                                                 pt.num_beams_, pt.num_heads_, pt.num_tiles_,
+                                                 self.total_pages_, self.tile_size_, self.head_dim_,
+                                                 pool.element_size(), _cabi.ptr(beam_ids), R, fill_byte,
+                                                 _cabi.stream()), "pa_kv_gather")
+        return dense
+
+    def workspace(self, B):
+        """Scratch for the decode kernels, cached per cache object."""
+        need = _cabi.lib().pa_decode_workspace_bytes(B, self.page_table_.num_heads_, self.head_dim_)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.key_buffer_.device)
+        return self._ws
