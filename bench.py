@@ -43,7 +43,7 @@ LAYERS, HEADS, HDIM, CTX, TILE = 32, 32, 128, 4096, 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="rows per GPU")
@@ -110,45 +110,51 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    """Polls SM clock, power and throttle reasons through NVML every ~10 ms on a thread while the
+    timed region runs (the profiling recipe's clocks line, without nvidia-smi's 100 ms floor)."""
 
     def __init__(self, index):
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.ok = False
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append((time.perf_counter(), ln.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if ts < t0 or ts > t1 + 0.1:
-                continue
-            f = [x.strip() for x in ln.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[6]))
-            except Exception:
-                continue
-            for n, val in zip(names, f[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        flags = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        reasons = sorted({n for s in win for n, bit in flags.items() if s[2] & bit})
+        return {"sm_mhz": statistics.median([s[1] for s in win]) if win else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(win), "power_w_max": max([s[3] for s in win]) if win else None}
 
 
 # --------------------------------------------------------------------------- ours

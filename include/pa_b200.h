@@ -97,8 +97,9 @@ int pa_kv_append_f32_i8(int8_t* d_k_pool, int8_t* d_v_pool, float* d_k_scales, f
                         const int32_t* d_positions, int R, pa_stream_t stream);
 
 /* ------------------------------------------------ paged decode attention */
-/* Bytes of scratch the decode entry points need for (B rows, H heads, D). */
-size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim);
+/* Bytes of scratch the decode entry points need for B rows x H heads of head_dim D over a
+ * page table of num_tiles tiles of tile_size tokens. */
+size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim, int num_tiles, int tile_size);
 
 /*
  * attention/paged_flash_attention_kernel_fused.cu:5-90 (launched by

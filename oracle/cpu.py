@@ -62,18 +62,20 @@ def num_threads():
 
 # ---- page table / pool addressing -------------------------------------------------
 def pt_index(beam, head, tile, num_heads, num_tiles):
-    return int(lib().orc_pt_index(beam, head, tile, num_heads, num_tiles))
+    return int(lib().orc_pt_index(int(beam), int(head), int(tile), int(num_heads), int(num_tiles)))
 
 
 def pt_lookup(table, beam, head, tile, num_heads, num_tiles):
     table = _i32(table)
-    return int(lib().orc_pt_lookup(_p(table, _i32p), table.size, beam, head, tile, num_heads, num_tiles))
+    return int(lib().orc_pt_lookup(_p(table, _i32p), table.size, int(beam), int(head), int(tile),
+                                   int(num_heads), int(num_tiles)))
 
 
 def kv_page_offset(table, beam, head, tile, num_heads, num_tiles, total_pages, tile_size, head_dim):
     table = _i32(table)
-    return int(lib().orc_kv_page_offset(_p(table, _i32p), table.size, beam, head, tile, num_heads,
-                                        num_tiles, total_pages, tile_size, head_dim))
+    return int(lib().orc_kv_page_offset(_p(table, _i32p), table.size, int(beam), int(head), int(tile),
+                                        int(num_heads), int(num_tiles), int(total_pages),
+                                        int(tile_size), int(head_dim)))
 
 
 def gather_pages(pool, table, num_beams, num_heads, num_tiles, tile_size, head_dim, beam_ids=None,

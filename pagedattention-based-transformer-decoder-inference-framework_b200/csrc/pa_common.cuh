@@ -128,4 +128,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
         : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                                uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
 }  // namespace pa

@@ -15,12 +15,13 @@
 //     memory or block barrier in the steady state;
 //   * direct kernel (a1): grid (rows, splits), 128-bit ld.global.nc loads
 //     straight into registers, split-KV partials + LSE combine kernel;
-//   * overlap kernel (a2): persistent, one CTA per SM, every warp runs its own
-//     multi-stage ring of TMA bulk copies (cp.async.bulk -> UBLKCP, mbarrier
-//     complete_tx) so ~190 KB of page loads per SM stay in flight while the math
-//     runs; the linear (row, unit) space is cut into equal contiguous shares
-//     per CTA (stream-K style), rows cut by a share boundary emit (m, l, O)
-//     partials that a tiny combine kernel merges.
+//   * overlap kernel (a2): persistent, one CTA per SM, every warp is an
+//     independent streaming engine with its own multi-stage ring of TMA bulk
+//     copies (cp.async.bulk -> UBLKCP, mbarrier complete_tx), ~190 KB of page
+//     loads in flight per SM while the math runs; chunks of <= 16 units are
+//     handed out through a global atomic counter (dynamic balance; a static
+//     equal split lost ~4% to SM-to-SM rate differences, profiles/), each chunk
+//     emits an (m, l, O) partial that a small combine kernel merges per row.
 #include "pa_common.cuh"
 
 namespace pa {
@@ -353,140 +354,139 @@ __global__ void combine_splits_kernel(const DecodeArgs a) {
 }
 
 // ---------------------------------------------------------------- overlap (a2)
-// Linear (row, unit) space.  Rows are ordered b-major then h; row (b, h) owns
-// units(b) = ceil(ctx(b) / 16) consecutive positions.
-struct RowMap {
-    const int* prefix;  // shared memory: prefix[b] = sum_{b'<b} units(b'), B+1 entries; null => uniform
-    int B, H, U;        // U: units per row when uniform
+// Work is cut into CHUNKS of `cu` consecutive 16-token units of one row.  Chunks are
+// ordered b-major, then h, then position; row (b, h) owns nchunks(b) = ceil(units(b) / cu)
+// consecutive chunk ids.  Every WARP is an independent streaming engine: it pulls chunk ids
+// from a global atomic counter, keeps its own ring of S TMA bulk-copy stages in flight
+// (running up to S units ahead, across chunk boundaries), and writes one (m, l, O) partial
+// per chunk -- or the final row when the row is a single chunk.  No block barrier after
+// the prologue; load balance is dynamic.
+struct ChunkMap {
+    const int* prefix;  // shared: prefix[b] = sum_{b'<b} nchunks(b'); null => uniform
+    int B, H, NC, cu;   // NC: chunks per row when uniform
     __device__ __forceinline__ int64_t total() const {
-        return prefix ? (int64_t)prefix[B] * H : (int64_t)B * H * U;
+        return prefix ? (int64_t)prefix[B] * H : (int64_t)B * H * NC;
     }
-    __device__ __forceinline__ int units_of(int b) const { return prefix ? prefix[b + 1] - prefix[b] : U; }
+    __device__ __forceinline__ int nchunks_of(int b) const { return prefix ? prefix[b + 1] - prefix[b] : NC; }
     __device__ __forceinline__ int64_t row_start(int b, int h) const {
         return prefix ? (int64_t)prefix[b] * H + (int64_t)h * (prefix[b + 1] - prefix[b])
-                      : ((int64_t)b * H + h) * U;
+                      : ((int64_t)b * H + h) * NC;
     }
-    __device__ __forceinline__ void locate(int64_t lin, int& b, int& h, int& u, int& Ub) const {
+    __device__ __forceinline__ void locate(int64_t id, int& b, int& h, int& j, int& nc) const {
         if (!prefix) {
-            const int64_t per_b = (int64_t)H * U;
-            b = (int)(lin / per_b);
-            const int rem = (int)(lin - (int64_t)b * per_b);
-            h = rem / U;
-            u = rem - h * U;
-            Ub = U;
+            const int64_t per_b = (int64_t)H * NC;
+            b = (int)(id / per_b);
+            const int rem = (int)(id - (int64_t)b * per_b);
+            h = rem / NC;
+            j = rem - h * NC;
+            nc = NC;
         } else {
-            int lo = 0, hi = B;  // largest b with prefix[b]*H <= lin
+            int lo = 0, hi = B;  // largest b with prefix[b]*H <= id
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if ((int64_t)prefix[mid] * H <= lin) lo = mid; else hi = mid;
+                if ((int64_t)prefix[mid] * H <= id) lo = mid; else hi = mid;
             }
             b = lo;
-            Ub = prefix[b + 1] - prefix[b];
-            const int64_t rem = lin - (int64_t)prefix[b] * H;
-            h = (int)(rem / Ub);
-            u = (int)(rem - (int64_t)h * Ub);
+            nc = prefix[b + 1] - prefix[b];
+            const int64_t rem = id - (int64_t)prefix[b] * H;
+            h = (int)(rem / nc);
+            j = (int)(rem - (int64_t)h * nc);
         }
     }
 };
 
-__device__ __forceinline__ int64_t share_start(int64_t total, int G, int c) {
-    return (total * c) / G;
-}
-
-struct Walker {
-    int64_t lin, lin_end;
-    int b, h, U, u0, u1, u;
-    __device__ __forceinline__ bool next_segment(const RowMap& rm) {
-        if (lin >= lin_end) return false;
-        int uu;
-        rm.locate(lin, b, h, uu, U);
-        u0 = uu;
-        const int64_t left = lin_end - lin;
-        u1 = (int)min((int64_t)U, (int64_t)u0 + left);
-        lin += (u1 - u0);
-        return true;
-    }
-};
+__device__ __forceinline__ int units_of_ctx(int ctx) { return (ctx + kUnitTok - 1) / kUnitTok; }
 
 template <int D, int KV, int NW, int S>
-__global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const DecodeArgs a, int cu,
+                                                                          unsigned int* counter) {
     using C = Cfg<D, KV>;
+    constexpr int QN = 16;  // per-warp chunk-id ring (producer runs <= S chunks ahead)
     extern __shared__ __align__(128) uint8_t smem[];
-    // carve: stages | barriers | meta | red[2] | prefix
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)NW * S * C::STAGE_BYTES);
     int* meta = reinterpret_cast<int*>(bars + NW * S);
-    float* red = reinterpret_cast<float*>(meta + NW * S);
-    int* prefix = reinterpret_cast<int*>(red + 2 * NW * (D + 2));
+    int64_t* cq = reinterpret_cast<int64_t*>(meta + NW * S + ((NW * S) & 1));
+    int* prefix = reinterpret_cast<int*>(cq + NW * QN);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, c = lane & 7;
-    const int G = gridDim.x, cta = blockIdx.x;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NW * S; ++i) mbar_init(smem_u32(bars + i), 1);
         mbar_fence_init();
     }
-    RowMap rm;
-    rm.B = a.B;
-    rm.H = a.H;
-    rm.U = (row_ctx(a, 0) + kUnitTok - 1) / kUnitTok;
-    rm.prefix = nullptr;
+    ChunkMap cm;
+    cm.B = a.B;
+    cm.H = a.H;
+    cm.cu = cu;
+    cm.NC = (units_of_ctx(row_ctx(a, 0)) + cu - 1) / cu;
+    cm.prefix = nullptr;
     if (a.ctx_lens) {
-        // Block-serial prefix of units per b (B is small; one pass, thread 0 finishes it).
         for (int i = threadIdx.x; i < a.B; i += blockDim.x)
-            prefix[i + 1] = (row_ctx(a, i) + kUnitTok - 1) / kUnitTok;
+            prefix[i + 1] = (units_of_ctx(row_ctx(a, i)) + cu - 1) / cu;
         __syncthreads();
         if (threadIdx.x == 0) {
             prefix[0] = 0;
             for (int i = 0; i < a.B; ++i) prefix[i + 1] += prefix[i];
         }
-        rm.prefix = prefix;
+        cm.prefix = prefix;
     }
     __syncthreads();
 
-    const int64_t total = rm.total();
-    const int64_t my_start = share_start(total, G, cta), my_end = share_start(total, G, cta + 1);
+    const int64_t total = cm.total();
+    const int64_t total_warps = (int64_t)gridDim.x * NW;
+    const int64_t gw = (int64_t)blockIdx.x * NW + warp;
     const int upt = a.tile_size / kUnitTok;
     const uint64_t policy = l2_policy_evict_first();
-
-    // ---- producer state (warp-uniform; lane 0 issues) ----
-    Walker pw;
-    pw.lin = my_start;
-    pw.lin_end = my_end;
-    bool p_has = false;
-    int p_page = -1, p_ctx = 0;
-    uint32_t issued = 0;
-    auto p_fetch = [&]() {  // page id + ctx for the producer's current (b, h, u)
-        const int beam = a.beam_ids ? a.beam_ids[pw.b] : pw.b;
-        p_page = lookup_page(a, beam, pw.h, pw.u / upt);
-    };
-    auto p_advance_segment = [&]() -> bool {
-        while (pw.next_segment(rm)) {
-            pw.u = pw.u0 + warp;
-            if (pw.u < pw.u1) {
-                p_ctx = row_ctx(a, pw.b);
-                return true;
-            }
-        }
-        return false;
-    };
-    p_has = p_advance_segment();
-    if (p_has) p_fetch();
 
     const uint32_t my_stage0 = smem_u32(stage_base + (size_t)warp * S * C::STAGE_BYTES);
     const uint32_t my_bar0 = smem_u32(bars + warp * S);
     int* my_meta = meta + warp * S;
+    int64_t* my_cq = cq + warp * QN;
+
+    // ---- producer state (warp-uniform; lane 0 issues) ----
+    bool p_has = false, p_first = true;
+    int p_b = 0, p_h = 0, p_u = 0, p_uend = 0, p_ctx = 0, p_beam = 0, p_page = -1;
+    uint32_t issued = 0, p_chunks = 0;
+
+    auto p_next_chunk = [&]() -> bool {
+        int64_t id;
+        if (p_first) {
+            id = gw;  // first chunk is static: no atomic on the critical path of the prologue
+            p_first = false;
+        } else {
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(counter, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            id = total_warps + (int64_t)t;
+        }
+        if (id >= total) return false;
+        int j, nc;
+        cm.locate(id, p_b, p_h, j, nc);
+        p_ctx = row_ctx(a, p_b);
+        p_u = j * cu;
+        p_uend = min(units_of_ctx(p_ctx), p_u + cu);
+        p_beam = a.beam_ids ? a.beam_ids[p_b] : p_b;
+        if (lane == 0) my_cq[p_chunks % QN] = id;
+        ++p_chunks;
+        __syncwarp();
+        return true;
+    };
+    auto p_fetch = [&]() { p_page = lookup_page(a, p_beam, p_h, p_u / upt); };
+
+    p_has = p_next_chunk();
+    if (p_has) p_fetch();
 
     auto produce = [&]() {
         if (!p_has) return;
         const uint32_t st = issued % S;
         if (lane == 0) {
-            const int nvalid = (p_page >= 0) ? min(kUnitTok, p_ctx - pw.u * kUnitTok) : 0;
+            const int nvalid = (p_page >= 0) ? min(kUnitTok, p_ctx - p_u * kUnitTok) : 0;
             my_meta[st] = nvalid;
             const uint32_t bar = my_bar0 + st * 8;
             if (nvalid > 0) {
-                const int sub = pw.u % upt;
+                const int sub = p_u % upt;
                 const int64_t tok0 = (int64_t)p_page * a.tile_size + sub * kUnitTok;
                 const uint32_t dst = my_stage0 + st * C::STAGE_BYTES;
                 fence_proxy_async();
@@ -495,24 +495,20 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
                     bulk_g2s(dst, a.k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
                     bulk_g2s(dst + C::UNIT_BYTES, a.v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
                 } else {
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                        ::"r"(dst), "l"(a.k_pool + tok0 * C::ROWB), "r"(C::UNIT_BYTES), "r"(bar) : "memory");
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                        ::"r"(dst + C::UNIT_BYTES), "l"(a.v_pool + tok0 * C::ROWB), "r"(C::UNIT_BYTES), "r"(bar) : "memory");
+                    bulk_g2s_nohint(dst, a.k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
+                    bulk_g2s_nohint(dst + C::UNIT_BYTES, a.v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
                 }
                 if (KV == 1) {
-                    bulk_g2s(dst + 2 * C::UNIT_BYTES, a.k_scales + tok0, C::SCALE_BYTES, bar, policy);
-                    bulk_g2s(dst + 2 * C::UNIT_BYTES + C::SCALE_BYTES, a.v_scales + tok0, C::SCALE_BYTES, bar, policy);
+                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES, a.k_scales + tok0, C::SCALE_BYTES, bar);
+                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES + C::SCALE_BYTES, a.v_scales + tok0, C::SCALE_BYTES, bar);
                 }
             } else {
                 mbar_arrive(bar);
             }
         }
         ++issued;
-        pw.u += NW;
-        if (pw.u >= pw.u1) p_has = p_advance_segment();
+        ++p_u;
+        if (p_u >= p_uend) p_has = p_next_chunk();
         if (p_has) p_fetch();
     };
 
@@ -520,19 +516,22 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
     for (int s = 0; s < S; ++s) produce();
 
     // ---- consumer ----
-    Walker cw;
-    cw.lin = my_start;
-    cw.lin_end = my_end;
-    uint32_t consumed = 0;
-    int seg_idx = 0;
+    uint32_t consumed = 0, c_chunks = 0;
     Acc<D, KV> acc;
     float q[C::E];
 
-    while (cw.next_segment(rm)) {
-        const int64_t row = (int64_t)cw.b * a.H + cw.h;
+    while (c_chunks < p_chunks) {  // the producer is always >= 1 chunk ahead unless it is done
+        const int64_t id = my_cq[c_chunks % QN];
+        ++c_chunks;
+        int b, h, j, nc;
+        cm.locate(id, b, h, j, nc);
+        const int64_t row = (int64_t)b * a.H + h;
+        const int u0 = j * cu;
+        const int u1 = min(units_of_ctx(row_ctx(a, b)), u0 + cu);
         load_q<D, KV>(a, row, c, q);
         acc.reset();
-        for (int u = cw.u0 + warp; u < cw.u1; u += NW) {
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
             const uint32_t st = consumed % S;
             mbar_wait(my_bar0 + st * 8, (consumed / S) & 1);
             const int nvalid = my_meta[st];
@@ -569,71 +568,78 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
             }
             __syncwarp();
             ++consumed;
-            produce();  // refill the stage just drained
+            produce();  // refill the stage just drained (may pull the next chunk id)
         }
-        // Row boundary: full rows go straight to the output, cut rows to a partial slot.
-        const bool full = (cw.u0 == 0 && cw.u1 == cw.U);
-        const int64_t slot = (cw.u0 > 0) ? 2 * (int64_t)cta : 2 * (int64_t)cta + 1;
-        cta_merge_emit<D, KV, NW>(red + (seg_idx & 1) * NW * (D + 2), acc, warp, lane, a,
-                                  full ? kEmitFinal : kEmitWorkspace, row, slot);
-        ++seg_idx;
+        // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
+        warp_merge<D, KV>(acc);
+        if (lane < 8) {
+            const bool final_row = (nc == 1);
+            if (final_row && !a.part_m) {
+                const float inv = 1.f / (acc.l + 1e-6f);
+#pragma unroll
+                for (int e = 0; e < C::E; ++e) a.out[row * D + C::dim_of(lane, e)] = acc.o[e] * inv;
+                if (lane == 0 && a.lse_out)
+                    a.lse_out[row] = (acc.l > 0.f) ? (acc.m + log2f(acc.l)) * kLn2 : -INFINITY;
+            } else if (final_row) {
+#pragma unroll
+                for (int e = 0; e < C::E; ++e) a.part_o[row * D + C::dim_of(lane, e)] = acc.o[e];
+                if (lane == 0) {
+                    a.part_m[row] = acc.m * kLn2;
+                    a.part_l[row] = acc.l;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < C::E; ++e) a.ws_o[id * D + C::dim_of(lane, e)] = acc.o[e];
+                if (lane == 0) {
+                    a.ws_m[id] = acc.m;
+                    a.ws_l[id] = acc.l;
+                }
+            }
+        }
     }
 }
 
-// Finish rows that were cut by a share boundary in the overlap kernel, and zero rows
-// with no keys.  One warp-group of D threads per row; recomputes the share geometry.
+// Merge the per-chunk partials of every row with more than one chunk; rows with no keys are
+// zeroed.  D threads per row.
 template <int D>
-__global__ void combine_shares_kernel(const DecodeArgs a, int G) {
+__global__ void combine_chunks_kernel(const DecodeArgs a, int cu) {
     extern __shared__ int prefix_sm[];
-    RowMap rm;
-    rm.B = a.B;
-    rm.H = a.H;
-    rm.U = (row_ctx(a, 0) + kUnitTok - 1) / kUnitTok;
-    rm.prefix = nullptr;
+    ChunkMap cm;
+    cm.B = a.B;
+    cm.H = a.H;
+    cm.cu = cu;
+    cm.NC = (units_of_ctx(row_ctx(a, 0)) + cu - 1) / cu;
+    cm.prefix = nullptr;
     if (a.ctx_lens) {
         if (threadIdx.x == 0) {
             prefix_sm[0] = 0;
             for (int i = 0; i < a.B; ++i)
-                prefix_sm[i + 1] = prefix_sm[i] + (row_ctx(a, i) + kUnitTok - 1) / kUnitTok;
+                prefix_sm[i + 1] = prefix_sm[i] + (units_of_ctx(row_ctx(a, i)) + cu - 1) / cu;
         }
         __syncthreads();
-        rm.prefix = prefix_sm;
+        cm.prefix = prefix_sm;
     }
-    const int64_t total = rm.total();
     const int d = threadIdx.x % D;
     const int rows_per_cta = blockDim.x / D;
     const int64_t nrows = (int64_t)a.B * a.H;
     for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x / D; row < nrows;
          row += (int64_t)gridDim.x * rows_per_cta) {
         const int b = (int)(row / a.H), h = (int)(row % a.H);
-        const int U = rm.units_of(b);
-        if (U == 0) {
+        const int nc = cm.nchunks_of(b);
+        if (nc == 1) continue;  // written by the main kernel
+        if (nc == 0) {
             emit_row(a, kEmitFinal, row, 0, D, d, -INFINITY, 0.f, 0.f);
             continue;
         }
-        const int64_t L0 = rm.row_start(b, h), L1 = L0 + U;
-        // first / last share touching the row: largest c with share_start(c) <= x
-        auto share_of = [&](int64_t x) {
-            int cc = (int)((x * G) / total);
-            if (cc >= G) cc = G - 1;
-            while (cc + 1 < G && share_start(total, G, cc + 1) <= x) ++cc;
-            while (cc > 0 && share_start(total, G, cc) > x) --cc;
-            return cc;
-        };
-        const int c0 = share_of(L0), c1 = share_of(L1 - 1);
-        if (c0 == c1) continue;  // whole row handled inside one share -> already final
+        const int64_t s0 = cm.row_start(b, h);
         float M = -INFINITY;
-        for (int cc = c0; cc <= c1; ++cc) {
-            const int64_t slot = (share_start(total, G, cc) > L0) ? 2 * (int64_t)cc : 2 * (int64_t)cc + 1;
-            M = fmaxf(M, a.ws_m[slot]);
-        }
+        for (int j = 0; j < nc; ++j) M = fmaxf(M, a.ws_m[s0 + j]);
         float L = 0.f, O = 0.f;
-        for (int cc = c0; cc <= c1; ++cc) {
-            const int64_t slot = (share_start(total, G, cc) > L0) ? 2 * (int64_t)cc : 2 * (int64_t)cc + 1;
-            const float ms = a.ws_m[slot];
+        for (int j = 0; j < nc; ++j) {
+            const float ms = a.ws_m[s0 + j];
             const float wt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
-            L = fmaf(a.ws_l[slot], wt, L);
-            O = fmaf(a.ws_o[slot * D + d], wt, O);
+            L = fmaf(a.ws_l[s0 + j], wt, L);
+            O = fmaf(a.ws_o[(s0 + j) * D + d], wt, O);
         }
         emit_row(a, kEmitFinal, row, 0, D, d, M, L, O);
     }
@@ -670,7 +676,10 @@ struct OvCfg {
     static constexpr int S = (KV == 0 && D == 128) ? 3 : ((KV == 0 || D == 128) ? 6 : 8);
 };
 
-static size_t ws_floats(int B, int H, int D) { return (size_t)(4096 + 2 * (size_t)B * H) * (D + 2); }
+static int units_of_ctx_host(int T, int cap) {
+    int ctx = T < 0 ? 0 : (T > cap ? cap : T);
+    return (ctx + kUnitTok - 1) / kUnitTok;
+}
 
 static int choose_splits(int64_t rows, int max_units, int sm_count) {
     const int64_t target = (int64_t)sm_count * 15;  // ~5 resident CTAs/SM x 3 waves
@@ -682,21 +691,47 @@ static int choose_splits(int64_t rows, int max_units, int sm_count) {
     return (int)ns;
 }
 
+// Units per chunk of the overlap kernel: 16 (128 KiB of fp16 K+V at D=128) when that still
+// yields >= 4 chunks per resident warp, fewer for small problems so every warp gets work.
+static int choose_cu(int64_t rows, int max_units, int sm_count) {
+    const int64_t warps = (int64_t)sm_count * kOvWarps;
+    int64_t cu = (rows * max_units) / (4 * warps);
+    if (cu > 16) cu = 16;
+    if (cu < 2) cu = 2;
+    int p = 2;
+    while (p * 2 <= cu) p *= 2;
+    return p;
+}
+
+static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
+    const int cu = choose_cu(rows, max_units, sm_count);
+    const size_t ov = (size_t)rows * ((max_units + cu - 1) / cu);
+    const size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
+    return (ov > dr ? ov : dr) + 64;
+}
+
+static size_t ws_bytes_needed(int B, int H, int D, int num_tiles, int tile_size, int sm_count) {
+    const int max_units = (int)(((int64_t)num_tiles * tile_size + kUnitTok - 1) / kUnitTok);
+    return ws_slots((int64_t)B * H, max_units, sm_count) * (size_t)(D + 2) * sizeof(float) + 256;
+}
+
 template <int D, int KV>
 static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes, cudaStream_t st) {
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
     const int64_t rows = (int64_t)a.B * a.H;
-    if (ws_bytes < ws_floats(a.B, a.H, D) * sizeof(float) || !ws) return PA_ERR_WORKSPACE;
-    float* w = static_cast<float*>(ws);
-    const size_t nslots = 4096 + 2 * (size_t)rows;
+    const int max_units = (int)(((int64_t)a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok);
+    if (!ws || ws_bytes < ws_bytes_needed(a.B, a.H, D, a.num_tiles, a.tile_size, di.sm_count))
+        return PA_ERR_WORKSPACE;
+    // layout: [counter (256 B)] [m: nslots] [l: nslots] [o: nslots * D]
+    unsigned int* counter = static_cast<unsigned int*>(ws);
+    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+    const size_t nslots = ws_slots(rows, max_units, di.sm_count);
     a.ws_m = w;
     a.ws_l = w + nslots;
     a.ws_o = w + 2 * nslots;
     if (!overlap) {
-        const int max_units = (a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok;
         a.num_splits = choose_splits(rows, max_units, di.sm_count);
-        while ((size_t)rows * a.num_splits > nslots) --a.num_splits;
         dim3 grid((unsigned)rows, (unsigned)a.num_splits);
         paged_decode_direct_kernel<D, KV><<<grid, 128, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();
@@ -711,21 +746,29 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     constexpr int S = OvCfg<D, KV>::S;
     using C = Cfg<D, KV>;
     const int G = di.sm_count;
+    const int cu = choose_cu(rows, max_units, di.sm_count);
     const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
-    const size_t smem = (size_t)kOvWarps * S * C::STAGE_BYTES + (size_t)kOvWarps * S * (8 + 4) +
-                        2 * (size_t)kOvWarps * (D + 2) * sizeof(float) + prefix_bytes;
+    const size_t smem = (size_t)kOvWarps * S * C::STAGE_BYTES + (size_t)kOvWarps * S * (8 + 4) + 8 +
+                        (size_t)kOvWarps * 16 * sizeof(int64_t) + prefix_bytes;
     if (smem > (size_t)di.max_smem_optin) return PA_ERR_UNSUPPORTED;  // B too large for the prefix table
     auto kern = paged_decode_overlap_kernel<D, KV, kOvWarps, S>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<G, kOvWarps * 32, smem, st>>>(a);
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<G, kOvWarps * 32, smem, st>>>(a, cu, counter);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    const int rows_per_cta = 256 / D;
-    int cgrid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-    if (cgrid > G * 8) cgrid = G * 8;
-    combine_shares_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, G);
-    e = cudaGetLastError();
+    // Rows of a single chunk were finished by the main kernel; everything else is merged here.
+    const int nc_uniform = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
+    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1;
+    if (need_combine) {
+        const int rows_per_cta = 256 / D;
+        int cgrid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
+        if (cgrid > G * 8) cgrid = G * 8;
+        combine_chunks_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, cu);
+        e = cudaGetLastError();
+    }
     return e == cudaSuccess ? PA_OK : (int)e;
 }
 
@@ -769,9 +812,11 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
 
 using namespace pa;
 
-PA_API size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim) {
-    if (B < 0 || num_heads <= 0 || head_dim <= 0) return 0;
-    return ws_floats(B, num_heads, head_dim) * sizeof(float);
+PA_API size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim, int num_tiles,
+                                        int tile_size) {
+    if (B < 0 || num_heads <= 0 || head_dim <= 0 || num_tiles <= 0 || tile_size <= 0) return 0;
+    const DeviceInfo& di = device_info();
+    return ws_bytes_needed(B, num_heads, head_dim, num_tiles, tile_size, di.ok ? di.sm_count : 148);
 }
 
 #define PA_DECODE_COMMON_PARAMS                                                                  \

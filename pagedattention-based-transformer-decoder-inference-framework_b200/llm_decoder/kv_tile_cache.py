@@ -185,7 +185,8 @@ class KVTileCache:
 
     def workspace(self, B):
         """Scratch for the decode kernels, cached per cache object."""
-        need = _cabi.lib().pa_decode_workspace_bytes(B, self.page_table_.num_heads_, self.head_dim_)
+        need = _cabi.lib().pa_decode_workspace_bytes(B, self.page_table_.num_heads_, self.head_dim_,
+                                                     self.page_table_.num_tiles_, self.tile_size_)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.key_buffer_.device)
         return self._ws

@@ -53,8 +53,8 @@ def test_invalid_arguments_rejected_without_device(cabi):
     assert lib.pa_paged_decode_f16(0x1000, 0x1000, 0x1000, 0x1000, *common, 96, 16, 1.0, None, None, None, 0, None) == -2
     assert lib.pa_paged_decode_f16(0x1000, 0x1000, 0x1000, 0x1000, *common, 128, 8, 1.0, None, None, None, 0, None) == -2
     assert lib.pa_paged_decode_f16(0x1000, 0x1000, 0x1000, 0x1000, *common, 128, 16, 0.0, None, None, None, 0, None) == -1
-    assert lib.pa_decode_workspace_bytes(64, 32, 128) > 0
-    assert lib.pa_decode_workspace_bytes(-1, 32, 128) == 0
+    assert lib.pa_decode_workspace_bytes(64, 32, 128, 256, 16) > 0
+    assert lib.pa_decode_workspace_bytes(-1, 32, 128, 256, 16) == 0
 
 
 def test_missing_library_fails_loudly(cabi, monkeypatch):
