@@ -1,0 +1,84 @@
+"""INT8 MLP GEMM micro-benchmark (BASELINE config C4): [M x 4096].[4096 x 16384] and back, M = 256.
+
+Reports TOP/s against the nominal 4.5 POP/s int8 dense peak and achieved weight-streaming GB/s
+against the measured HBM peak, next to cuBLASLt (torch._int_mm on CUDA) and oneDNN on the host
+(torch._int_mm on CPU) as reported baselines.  Prints one JSON line.
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pagedattention-based-transformer-decoder-inference-framework_b200"))
+import llm_decoder as ld  # noqa: E402
+
+
+def time_cuda(fn, iters=50, warm=10, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    M = int(os.environ.get("M", 256))
+    hidden, inter = 4096, 16384
+    dev = "cuda"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    res = {"M": M, "shapes": {}}
+    peak_hbm = 6547.2
+    try:
+        peak_hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    for name, (K, N) in {"fc1": (hidden, inter), "fc2": (inter, hidden)}.items():
+        A = torch.randint(-127, 128, (1, M, K), dtype=torch.int8, device=dev)
+        B = torch.randint(-127, 128, (1, K, N), dtype=torch.int8, device=dev)
+        C = torch.empty((1, M, N), dtype=torch.int8, device=dev)
+        bias = torch.randn(N, device=dev)
+        ours = lambda: ld.dnnl_matmul_int8(A, B, C, 1, M, N, K, 1 / 16, 1 / 16, 8.0, bias, "relu")
+        assert ours()
+        med, best = time_cuda(ours, flush=flush)
+        ops = 2.0 * M * N * K
+        byts = K * N + M * K + M * N
+        r = {"ms_median": med, "ms_min": best, "tops": ops / (med * 1e-3) / 1e12,
+             "frac_of_4.5POPS": ops / (med * 1e-3) / 4.5e15, "gbs": byts / (med * 1e-3) / 1e9,
+             "frac_hbm_measured": byts / (med * 1e-3) / 1e9 / peak_hbm}
+        try:
+            a2, b2 = A[0], B[0]
+            lib = lambda: torch._int_mm(a2, b2)
+            lm, lb = time_cuda(lib, flush=flush)
+            r["cublaslt_int_mm_ms_median"] = lm
+            r["cublaslt_tops"] = ops / (lm * 1e-3) / 1e12
+        except Exception as e:  # pragma: no cover
+            r["cublaslt_error"] = repr(e)[:200]
+        ac, bc = A[0].cpu(), B[0].cpu()
+        torch._int_mm(ac, bc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch._int_mm(ac, bc)
+        r["onednn_cpu_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        r["onednn_cpu_threads"] = torch.get_num_threads()
+        res["shapes"][name] = r
+    pair = sum(v["ms_median"] for v in res["shapes"].values())
+    res["pair_us"] = pair * 1e3
+    res["pair_tops"] = 2 * 2.0 * M * hidden * inter / (pair * 1e-3) / 1e12
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,7 +1,406 @@
-// gemm_i8.cu -- placeholder until the tcgen05 kind::i8 kernel lands (same round).
+// gemm_i8.cu -- s8 x s8 -> s32 GEMM on the 5th-gen tensor cores (tcgen05.mma kind::i8) with
+// the fused oneDNN-style epilogue of attention_cpu/dnnl_matmul_int8.cpp:7-76.
+//
+//   acc[b,m,n] = sum_k A[b,m,k] * B[b,k,n]                (exact int32)
+//   C_s8       = sat_s8(rne(act(alpha*acc + bias[n])))     alpha = scaleA*scaleB/scaleC
+//
+// Shapes of interest (decoder MLP, decoder/mlp.hpp:23-41): M = decode batch (<= 256),
+// [M x hidden] . [hidden x 4*hidden] and back.  At M = 256 the GEMM sits on the ridge: the
+// weight matrix B must stream from HBM exactly once, so a CTA owns a 128-column slab of B over
+// (a split of) K and computes ALL rows of M against it (two 128-row accumulators in TMEM).
+//
+// Pipeline (one CTA per SM, 192 threads):
+//   warp 0   : TMA producer -- cp.async.bulk.tensor (UTMALDG) of A tiles [128 x 128 B] (K-major,
+//              128B swizzle) and the B tile [128 k-rows x 128 B] (N contiguous = "MN-major",
+//              128B swizzle) into a 4-stage shared-memory ring, mbarrier complete_tx.
+//   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::i8
+//              (M=128, N=128, K=32 per instruction), tcgen05.commit releases ring slots and
+//              finally signals the epilogue.
+//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), scale/bias/activation/
+//              round-to-nearest-even/saturate, 128-bit stores of s8 (or raw s32 / split-K
+//              red.add.s32).
+// B is consumed in the reference's own [K, N] row-major layout through an MN-major UMMA
+// descriptor: no transpose pass, no repacking of weights.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "pa_common.cuh"
 
-PA_API int pa_gemm_i8(const int8_t*, const int8_t*, int8_t*, int32_t*, int, int, int, int, float,
-                      float, float, const float*, int, pa_stream_t) {
-    return PA_ERR_UNSUPPORTED;
+namespace pa {
+namespace gemm {
+
+constexpr int BM = 128;      // rows per UMMA / TMEM accumulator
+constexpr int BN = 128;      // columns per CTA slab
+constexpr int BK = 128;      // bytes of K per pipeline stage (one 128B swizzle row)
+constexpr int UK = 32;       // K per tcgen05.mma kind::i8
+constexpr int STAGES = 4;
+constexpr int TILE_BYTES = BM * BK;          // 16 KiB: one A tile or one B tile
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;  // A0, A1, B
+constexpr int TMEM_COLS = 2 * BN;            // two accumulators
+constexpr int NTHREADS = 192;
+
+struct Args {
+    int8_t* C8;
+    int32_t* C32;        // raw accumulators out (may be null)
+    int32_t* acc_ws;     // split-K accumulation buffer (zeroed), null when ksplit == 1
+    const float* bias;
+    float alpha;
+    int act;
+    int M, N, K;
+    int ksplit;          // K splits
+    int kb_per_split;    // BK blocks per split
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (InstrDescriptor): c=S32 (2) [4,6), a=INT8 (1) [7,10), b=INT8 (1) [10,13),
+// a K-major (0) [15], b MN-major (1) [16], N>>3 [17,23), M>>4 [24,29).
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ int epilogue_one(int acc, float alpha, float bias, bool has_bias, int act) {
+    float v = __fmul_rn(alpha, (float)acc);
+    if (has_bias) v = __fadd_rn(v, bias);
+    if (act == PA_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == PA_ACT_GELU) v = gelu_erf(v);
+    v = fminf(127.f, fmaxf(-128.f, rintf(v)));  // rne, saturate (NaN -> -128)
+    return (int)v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled tiles.
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + STAGES * STAGE_BYTES;  // full[S], empty[S], tmem_full
+    const uint32_t tmem_slot = bar0 + (2 * STAGES + 1) * 8;
+    auto full_bar = [&](int s) { return bar0 + s * 8; };
+    auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
+    const uint32_t tmem_full_bar = bar0 + 2 * STAGES * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m_chunk = blockIdx.y / g.ksplit, split = blockIdx.y % g.ksplit;
+    const int m0 = m_chunk * 2 * BM;
+    const int batch = blockIdx.z;
+    const int m_tiles = (g.M - m0 > BM) ? 2 : 1;
+    const int total_kb = (g.K + BK - 1) / BK;
+    const int kb0 = split * g.kb_per_split;
+    const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB));
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+                const uint32_t st = base + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(full_bar(s), (uint32_t)(m_tiles + 1) * TILE_BYTES);
+                const int k0 = (kb0 + i) * BK;
+                tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));
+                if (m_tiles == 2) tma_load_3d(st + TILE_BYTES, &tmA, k0, m0 + BM, batch, full_bar(s));
+                tma_load_3d(st + 2 * TILE_BYTES, &tmB, n0, k0, batch, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(full_bar(s), (i / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (mt < m_tiles) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / UK; ++ks) {
+                            // A: K-major SW128, 8-row groups 1024 B apart; +32 B per K step inside the swizzle row.
+                            const uint64_t da = make_desc(st + mt * TILE_BYTES + ks * UK, 16, 1024);
+                            // B: MN-major SW128, 8 k-rows per 1024 B group; 32 k-rows = 4096 B per K step.
+                            const uint64_t db = make_desc(st + 2 * TILE_BYTES + ks * UK * BK, TILE_BYTES, 1024);
+                            umma_i8(tmem_base + mt * BN, da, db, kIdesc, (i > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // Epilogue warps 2..5 own TMEM lane quarters (warp % 4).
+        const int qtr = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const bool has_bias = g.bias != nullptr;
+        for (int mt = 0; mt < m_tiles; ++mt) {
+            const int row = m0 + mt * BM + qtr * 32 + lane;
+            const bool row_ok = row < g.M;
+            const int64_t out_row = ((int64_t)batch * g.M + row) * g.N;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(qtr * 32) << 16) + mt * BN + cc * 32, r);
+                const int col0 = n0 + cc * 32;
+                if (!row_ok || col0 >= g.N) continue;
+                if (g.acc_ws) {  // split-K: exact integer reduction
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < g.N) atomicAdd(g.acc_ws + out_row + col0 + j, (int)r[j]);
+                    continue;
+                }
+                const bool full = col0 + 32 <= g.N;
+                if (g.C32) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<int4*>(g.C32 + out_row + col0 + j) =
+                                make_int4((int)r[j], (int)r[j + 1], (int)r[j + 2], (int)r[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < g.N; ++j) g.C32[out_row + col0 + j] = (int)r[j];
+                    }
+                }
+                if (g.C8) {
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        uint32_t p = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * w + e;
+                            const float bj = (has_bias && col0 + j < g.N) ? __ldg(g.bias + col0 + j) : 0.f;
+                            p |= (uint32_t)(epilogue_one((int)r[j], g.alpha, bj, has_bias, g.act) & 0xff) << (8 * e);
+                        }
+                        packed[w] = p;
+                    }
+                    if (full) {
+                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < g.N; ++j)
+                            g.C8[out_row + col0 + j] = (int8_t)((packed[j >> 2] >> (8 * (j & 3))) & 0xff);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Split-K second pass: acc_ws (s32) -> C32 copy and/or C8 epilogue.
+__global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
+    const int64_t n4 = rows * g.N / 4;
+    const bool has_bias = g.bias != nullptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 a = reinterpret_cast<const int4*>(g.acc_ws)[i];
+        if (g.C32) reinterpret_cast<int4*>(g.C32)[i] = a;
+        if (g.C8) {
+            const int col = (int)((i * 4) % g.N);
+            const int v[4] = {a.x, a.y, a.z, a.w};
+            uint32_t p = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float bj = has_bias ? __ldg(g.bias + col + e) : 0.f;
+                p |= (uint32_t)(epilogue_one(v[e], g.alpha, bj, has_bias, g.act) & 0xff) << (8 * e);
+            }
+            reinterpret_cast<uint32_t*>(g.C8)[i] = p;
+        }
+    }
+}
+
+// ---- host: tensor maps --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 3-D u8 tensor [batch][rows][cols] (cols contiguous), box [1][box_rows][128 B], 128B swizzle.
+static bool make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {cols, rows, batch};
+    cuuint64_t strides[2] = {cols, cols * rows};  // bytes, dims 1..2
+    cuuint32_t box[3] = {128, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Split-K accumulation scratch, one per device, grown on demand (stream-ordered reuse: all
+// pa_gemm_i8 calls of a process are expected on one stream per device).
+struct Scratch {
+    int32_t* p = nullptr;
+    size_t bytes = 0;
+};
+static Scratch& scratch_for_device() {
+    static Scratch s[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return s[dev & 63];
+}
+
+}  // namespace gemm
+}  // namespace pa
+
+using namespace pa;
+using namespace pa::gemm;
+
+PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH, int M,
+                      int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias, int act,
+                      pa_stream_t stream) {
+    PA_CHECK_ARG(d_A && d_B && (d_C_s8 || d_C_s32));
+    PA_CHECK_ARG(BATCH > 0 && M > 0 && N > 0 && K > 0 && scaleC != 0.f);
+    PA_CHECK_ARG(act == PA_ACT_NONE || act == PA_ACT_RELU || act == PA_ACT_GELU);
+    if (K % 16 != 0 || N % 16 != 0) return PA_ERR_UNSUPPORTED;
+    PA_CHECK_ARG((uintptr_t)d_A % 16 == 0 && (uintptr_t)d_B % 16 == 0);
+    PA_CHECK_ARG(!d_C_s8 || (uintptr_t)d_C_s8 % 16 == 0);
+    PA_CHECK_ARG(!d_C_s32 || (uintptr_t)d_C_s32 % 16 == 0);
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return PA_ERR_NO_DEVICE;
+    cudaStream_t st = as_stream(stream);
+
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, BM)) return PA_ERR_UNSUPPORTED;
+    if (!make_map(&tmB, d_B, (uint64_t)N, (uint64_t)K, (uint64_t)BATCH, BK)) return PA_ERR_UNSUPPORTED;
+
+    Args g{};
+    g.C8 = d_C_s8;
+    g.C32 = d_C_s32;
+    g.bias = d_bias;
+    g.alpha = scaleA * scaleB / scaleC;  // dnnl_matmul_int8.cpp:40, fp32, left to right
+    g.act = act;
+    g.M = M; g.N = N; g.K = K;
+    const int n_slabs = (N + BN - 1) / BN;
+    const int m_chunks = (M + 2 * BM - 1) / (2 * BM);
+    const int total_kb = (K + BK - 1) / BK;
+    const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH;
+    int ksplit = (int)(di.sm_count / ctas);
+    if (ksplit > total_kb / 8) ksplit = total_kb / 8;  // >= 8 K blocks (1 KiB of K) per split
+    if (ksplit < 1) ksplit = 1;
+    g.kb_per_split = (total_kb + ksplit - 1) / ksplit;
+    ksplit = (total_kb + g.kb_per_split - 1) / g.kb_per_split;
+    g.ksplit = ksplit;
+    const int64_t rows = (int64_t)BATCH * M;
+    if (ksplit > 1) {
+        Scratch& sc = scratch_for_device();
+        const size_t need = (size_t)rows * N * sizeof(int32_t);
+        if (sc.bytes < need) {
+            if (sc.p) cudaFree(sc.p);
+            sc.p = nullptr;
+            sc.bytes = 0;
+            cudaError_t e = cudaMalloc(&sc.p, need);
+            if (e != cudaSuccess) return (int)e;
+            sc.bytes = need;
+        }
+        g.acc_ws = sc.p;
+        cudaError_t e = cudaMemsetAsync(sc.p, 0, need, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[dev & 63] = true;
+    }
+    dim3 grid((unsigned)n_slabs, (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
+    gemm_i8_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmB, g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (ksplit > 1) {
+        const int64_t n4 = rows * N / 4;
+        int blocks = (int)((n4 + 255) / 256);
+        if (blocks > di.sm_count * 8) blocks = di.sm_count * 8;
+        gemm_i8_splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(g, rows);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return PA_OK;
 }

@@ -315,3 +315,76 @@ def test_c2_full_size_properties(ld, oracle):
     out = torch.empty((B, H, D), device="cuda")
     ld.AttentionCUDA.forward(q, out, B, H, D, T, None, kvc, None, False, True, True, temp)
     np.testing.assert_allclose(out.cpu().numpy(), 0.75, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ int8 GEMM (tcgen05 kind::i8)
+GEMM_SHAPES = [
+    (1, 5, 32, 48),        # BATCH, M, N, K : tiny, ragged M
+    (2, 130, 144, 272),    # batched, two M tiles, N/K tails inside a tile
+    (1, 256, 384, 1024),
+    (1, 1, 3072, 768),     # C1 fc1 (GPT-2 small), M = 1
+    (1, 1, 768, 3072),     # C1 fc2
+    (1, 300, 256, 512),    # M > 256: two M chunks
+    (1, 64, 128, 8192),    # one slab -> split-K path
+    (3, 17, 16, 16),       # minimum N, K
+]
+
+
+@pytest.mark.parametrize("shape", GEMM_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_gemm_i8_accumulators_bit_exact(ld, oracle, shape):
+    BATCH, M, N, K = shape
+    rng = np.random.default_rng(sum(shape))
+    A = rng.integers(-127, 128, size=(BATCH, M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, size=(BATCH, K, N), dtype=np.int8)
+    bias = rng.standard_normal(N).astype(np.float32)
+    acc_ref = oracle.cpu.gemm_s8s8s32(A, B)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    acc = torch.full((BATCH, M, N), -7, dtype=torch.int32, device="cuda")
+    C = torch.full((BATCH, M, N), -7, dtype=torch.int8, device="cuda")
+    sa = sb = 1.0 / 16
+    sc = 8.0 * K / 1024
+    for act in ("", "relu", "gelu"):
+        ok = ld.dnnl_matmul_int8(dA, dB, C, BATCH, M, N, K, sa, sb, sc, torch.from_numpy(bias).cuda(), act, acc_out=acc)
+        assert ok
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(acc.cpu().numpy(), acc_ref)          # int32: bit-exact
+        exp = oracle.cpu.matmul_int8_epilogue(acc_ref, sa, sb, sc, bias, act)
+        diff = np.abs(C.cpu().numpy().astype(np.int32) - exp.astype(np.int32))
+        assert diff.max() <= 1                                             # oneDNN epilogue: +-1 LSB (parity unpinned)
+        if act != "gelu":
+            assert diff.max() == 0
+    # no bias, s8 only
+    C2 = torch.empty_like(C)
+    assert ld.dnnl_matmul_int8(dA, dB, C2, BATCH, M, N, K, sa, sb, sc)
+    np.testing.assert_array_equal(C2.cpu().numpy(), oracle.cpu.matmul_int8_epilogue(acc_ref, sa, sb, sc))
+
+
+def test_gemm_i8_rejects_bad_shapes(ld):
+    A = torch.zeros((1, 4, 24), dtype=torch.int8, device="cuda")
+    B = torch.zeros((1, 24, 16), dtype=torch.int8, device="cuda")
+    C = torch.zeros((1, 4, 16), dtype=torch.int8, device="cuda")
+    assert ld.dnnl_matmul_int8(A, B, C, 1, 4, 16, 24, 1.0, 1.0) is False       # K % 16 != 0
+    assert ld.dnnl_matmul_int8(A, B, C, 1, 4, 16, 16, 1.0, 1.0, activation="tanh") is False
+
+
+@pytest.mark.parametrize("shape", [(256, 16384, 4096), (256, 4096, 16384)], ids=["C4_fc1", "C4_fc2"])
+def test_gemm_i8_c4_full_size_vs_onednn(ld, shape):
+    """BASELINE config C4 MLP shapes; exact int32 accumulators against oneDNN's s8 GEMM on the
+    host (torch._int_mm on CPU tensors = the only linkable oneDNN here)."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(1238)
+    A = torch.randint(-127, 128, (M, K), generator=g, dtype=torch.int8)
+    B = torch.randint(-127, 128, (K, N), generator=g, dtype=torch.int8)
+    ref = torch._int_mm(A, B)
+    acc = torch.empty((1, M, N), dtype=torch.int32, device="cuda")
+    assert ld.dnnl_matmul_int8(A.cuda(), B.cuda(), None, 1, M, N, K, 1.0, 1.0, acc_out=acc)
+    torch.cuda.synchronize()
+    assert torch.equal(acc[0].cpu(), ref)
+    # linearity property: (A1 + A2) B == A1 B + A2 B on disjoint-support operands
+    A1, A2 = A.clone(), A.clone()
+    A1[:, K // 2:] = 0
+    A2[:, :K // 2] = 0
+    acc1, acc2 = torch.empty_like(acc), torch.empty_like(acc)
+    assert ld.dnnl_matmul_int8(A1.cuda(), B.cuda(), None, 1, M, N, K, 1.0, 1.0, acc_out=acc1)
+    assert ld.dnnl_matmul_int8(A2.cuda(), B.cuda(), None, 1, M, N, K, 1.0, 1.0, acc_out=acc2)
+    assert torch.equal(acc1 + acc2, acc)
