@@ -18,13 +18,13 @@
 //              finally signals the epilogue.
 //   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), scale/bias/activation/
 //              round-to-nearest-even/saturate, 128-bit stores of s8 (or raw s32 / split-K
-//              red.add.s32).
+//              partial tiles that a second kernel sums exactly and finishes).
 // B is consumed in the reference's own [K, N] row-major layout through an MN-major UMMA
 // descriptor: no transpose pass, no repacking of weights.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
-#include <unordered_map>
 
 #include "pa_common.cuh"
 
@@ -35,7 +35,10 @@ constexpr int BM = 128;      // rows per UMMA / TMEM accumulator
 constexpr int BN = 128;      // columns per CTA slab
 constexpr int BK = 128;      // bytes of K per pipeline stage (one 128B swizzle row)
 constexpr int UK = 32;       // K per tcgen05.mma kind::i8
-constexpr int STAGES = 4;
+#ifndef PA_GEMM_STAGES
+#define PA_GEMM_STAGES 4
+#endif
+constexpr int STAGES = PA_GEMM_STAGES;
 constexpr int TILE_BYTES = BM * BK;          // 16 KiB: one A tile or one B tile
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;  // A0, A1, B
 constexpr int TMEM_COLS = 2 * BN;            // two accumulators
@@ -44,13 +47,17 @@ constexpr int NTHREADS = 192;
 struct Args {
     int8_t* C8;
     int32_t* C32;        // raw accumulators out (may be null)
-    int32_t* acc_ws;     // split-K accumulation buffer (zeroed), null when ksplit == 1
+    int32_t* acc_ws;     // split-K partial tiles [ksplit][BATCH*M][N], null when ksplit == 1
     const float* bias;
     float alpha;
     int act;
     int M, N, K;
     int ksplit;          // K splits
     int kb_per_split;    // BK blocks per split
+    int64_t BATCH_rows;  // BATCH * M
+#ifdef PA_GEMM_PROBE
+    unsigned long long* probe;  // [0] producer wait cycles, [1] mma wait cycles, [2] total cycles (CTA 0)
+#endif
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -60,6 +67,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
@@ -81,6 +105,10 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -108,15 +136,23 @@ constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ int epilogue_one(int acc, float alpha, float bias, bool has_bias, int act) {
-    float v = __fmul_rn(alpha, (float)acc);
-    if (has_bias) v = __fadd_rn(v, bias);
-    if (act == PA_ACT_RELU) v = fmaxf(v, 0.f);
-    else if (act == PA_ACT_GELU) v = gelu_erf(v);
+template <int ACT>
+__device__ __forceinline__ int epilogue_one(int acc, float alpha, float bias) {
+    // alpha*acc and +bias round separately, as the reference epilogue restated in the oracle
+    // (adding a 0.0f bias is exact, so "no bias" passes 0).
+    float v = __fadd_rn(__fmul_rn(alpha, (float)acc), bias);
+    if (ACT == PA_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (ACT == PA_ACT_GELU) v = gelu_erf(v);
     v = fminf(127.f, fmaxf(-128.f, rintf(v)));  // rne, saturate (NaN -> -128)
     return (int)v;
 }
 
+// EPI: 0 = integer outputs only (raw s32 and/or split-K reduction), 1/2/3 = s8 output with
+// activation none/relu/gelu (plus optional raw s32).
+// CL: thread-block cluster size along N.  The CL CTAs of a cluster work on adjacent B slabs and
+// need the same A tiles: each loads 1/CL of the A rows and TMA-multicasts them to all CL CTAs,
+// which divides the L2 -> SM traffic for A by CL (the main loop is L2-read bound otherwise).
+template <int EPI, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -128,6 +164,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
     const uint32_t tmem_full_bar = bar0 + 2 * STAGES * 8;
 
+#ifdef PA_GEMM_PROBE
+    const long long t_entry = clock64();
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int m_chunk = blockIdx.y / g.ksplit, split = blockIdx.y % g.ksplit;
@@ -142,7 +181,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL);  // every CTA of the cluster must have drained slot s
         }
         mbar_init(tmem_full_bar, 1);
         mbar_fence_init();
@@ -152,28 +191,65 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();  // peers' barriers are initialised before any remote arrive lands
     tc_fence_after();
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+#ifdef PA_GEMM_PROBE
+    long long t_epi0 = 0;
+    const long long t_setup = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 5 && g.probe) g.probe[4] = t_setup - t_entry;
+#endif
 
     if (warp == 0) {
         if (lane == 0) {
+#ifdef PA_GEMM_PROBE
+            long long pw = 0, t_start = clock64();
+#endif
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
+#ifdef PA_GEMM_PROBE
+                long long t0 = clock64();
+#endif
                 mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+#ifdef PA_GEMM_PROBE
+                pw += clock64() - t0;
+#endif
                 const uint32_t st = base + s * STAGE_BYTES;
                 mbar_arrive_expect_tx(full_bar(s), (uint32_t)(m_tiles + 1) * TILE_BYTES);
                 const int k0 = (kb0 + i) * BK;
-                tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));
-                if (m_tiles == 2) tma_load_3d(st + TILE_BYTES, &tmA, k0, m0 + BM, batch, full_bar(s));
+                if (CL == 1) {
+                    tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));
+                    if (m_tiles == 2) tma_load_3d(st + TILE_BYTES, &tmA, k0, m0 + BM, batch, full_bar(s));
+                } else {
+                    // This CTA's share of the A rows of the stage (tmA's box holds a_rows rows),
+                    // delivered to the same offset in every CTA of the cluster.
+                    const int a_rows = m_tiles * BM / CL;
+                    const int r0 = (int)crank * a_rows;
+                    tma_load_3d_mc(st + r0 * BK, &tmA, k0, m0 + r0, batch, full_bar(s), kMask);
+                }
                 tma_load_3d(st + 2 * TILE_BYTES, &tmB, n0, k0, batch, full_bar(s));
             }
+#ifdef PA_GEMM_PROBE
+            if (blockIdx.x == 5 && g.probe) { g.probe[0] = pw; g.probe[2] = clock64() - t_start; }
+#endif
         }
     } else if (warp == 1) {
         if (lane == 0) {
+#ifdef PA_GEMM_PROBE
+            long long mw = 0, t_start = clock64();
+#endif
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
+#ifdef PA_GEMM_PROBE
+                long long t0 = clock64();
+#endif
                 mbar_wait(full_bar(s), (i / STAGES) & 1);
+#ifdef PA_GEMM_PROBE
+                mw += clock64() - t0;
+#endif
                 tc_fence_after();
                 const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
@@ -189,16 +265,26 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                umma_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+                // slot reusable once these MMAs have read it (signalled to every CTA of the cluster)
+                if (CL == 1) umma_commit(empty_bar(s));
+                else umma_commit_mc(empty_bar(s), kMask);
             }
             umma_commit(tmem_full_bar);
+#ifdef PA_GEMM_PROBE
+            if (blockIdx.x == 5 && g.probe) { g.probe[1] = mw; g.probe[3] = clock64() - t_start; }
+#endif
         }
     } else {
-        // Epilogue warps 2..5 own TMEM lane quarters (warp % 4).
+        // Epilogue warps 2..5 own TMEM lane quarters (warp % 4).  N % 16 == 0, so a 32-column
+        // chunk is either fully valid, half valid (16 columns) or out of range: all register
+        // indices below are compile-time (nothing spills to local memory).
+        constexpr int ACT = EPI == 2 ? PA_ACT_RELU : (EPI == 3 ? PA_ACT_GELU : PA_ACT_NONE);
         const int qtr = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const bool has_bias = g.bias != nullptr;
+#ifdef PA_GEMM_PROBE
+        t_epi0 = clock64();
+#endif
         for (int mt = 0; mt < m_tiles; ++mt) {
             const int row = m0 + mt * BM + qtr * 32 + lane;
             const bool row_ok = row < g.M;
@@ -209,72 +295,75 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_32x32(tmem_base + ((uint32_t)(qtr * 32) << 16) + mt * BN + cc * 32, r);
                 const int col0 = n0 + cc * 32;
                 if (!row_ok || col0 >= g.N) continue;
-                if (g.acc_ws) {  // split-K: exact integer reduction
+                const bool hi_ok = col0 + 32 <= g.N;  // else exactly 16 valid columns
+                if (g.acc_ws) {  // split-K: this split's partial tile, 128 B per thread per chunk
+                    int32_t* wp = g.acc_ws + (int64_t)split * g.BATCH_rows * g.N + out_row + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < g.N) atomicAdd(g.acc_ws + out_row + col0 + j, (int)r[j]);
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < 16 || hi_ok)
+                            *reinterpret_cast<int4*>(wp + j) = make_int4((int)r[j], (int)r[j + 1], (int)r[j + 2], (int)r[j + 3]);
                     continue;
                 }
-                const bool full = col0 + 32 <= g.N;
                 if (g.C32) {
-                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < 16 || hi_ok)
                             *reinterpret_cast<int4*>(g.C32 + out_row + col0 + j) =
                                 make_int4((int)r[j], (int)r[j + 1], (int)r[j + 2], (int)r[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < g.N; ++j) g.C32[out_row + col0 + j] = (int)r[j];
-                    }
                 }
-                if (g.C8) {
+                if (EPI != 0) {
                     uint32_t packed[8];
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
-                        uint32_t p = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = 4 * w + e;
-                            const float bj = (has_bias && col0 + j < g.N) ? __ldg(g.bias + col0 + j) : 0.f;
-                            p |= (uint32_t)(epilogue_one((int)r[j], g.alpha, bj, has_bias, g.act) & 0xff) << (8 * e);
-                        }
-                        packed[w] = p;
+                        float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (g.bias && (w < 4 || hi_ok)) bj = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + w);
+                        packed[w] = (uint32_t)(epilogue_one<ACT>((int)r[4 * w + 0], g.alpha, bj.x) & 0xff) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 1], g.alpha, bj.y) & 0xff) << 8) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 2], g.alpha, bj.z) & 0xff) << 16) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 3], g.alpha, bj.w) & 0xff) << 24);
                     }
-                    if (full) {
-                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (hi_ok)
                         *reinterpret_cast<uint4*>(g.C8 + out_row + col0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < g.N; ++j)
-                            g.C8[out_row + col0 + j] = (int8_t)((packed[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    }
                 }
             }
         }
     }
+#ifdef PA_GEMM_PROBE
+    if (warp == 2 && lane == 0 && blockIdx.x == 5 && g.probe) {
+        g.probe[5] = t_epi0 - t_setup;       // setup -> accumulators ready
+        g.probe[6] = clock64() - t_epi0;     // epilogue
+    }
+#endif
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();  // no CTA exits while peers may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-// Split-K second pass: acc_ws (s32) -> C32 copy and/or C8 epilogue.
+// Split-K second pass: sum the ksplit partial tiles (exact int32), then C32 copy and/or C8 epilogue.
+template <int ACT>
 __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
     const int64_t n4 = rows * g.N / 4;
-    const bool has_bias = g.bias != nullptr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int4 a = reinterpret_cast<const int4*>(g.acc_ws)[i];
+        int4 a = __ldcs(reinterpret_cast<const int4*>(g.acc_ws) + i);
+        for (int sp = 1; sp < g.ksplit; ++sp) {
+            const int4 b = __ldcs(reinterpret_cast<const int4*>(g.acc_ws) + sp * n4 + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
         if (g.C32) reinterpret_cast<int4*>(g.C32)[i] = a;
         if (g.C8) {
             const int col = (int)((i * 4) % g.N);
-            const int v[4] = {a.x, a.y, a.z, a.w};
-            uint32_t p = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float bj = has_bias ? __ldg(g.bias + col + e) : 0.f;
-                p |= (uint32_t)(epilogue_one(v[e], g.alpha, bj, has_bias, g.act) & 0xff) << (8 * e);
-            }
-            reinterpret_cast<uint32_t*>(g.C8)[i] = p;
+            float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) bj = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+            reinterpret_cast<uint32_t*>(g.C8)[i] =
+                (uint32_t)(epilogue_one<ACT>(a.x, g.alpha, bj.x) & 0xff) |
+                ((uint32_t)(epilogue_one<ACT>(a.y, g.alpha, bj.y) & 0xff) << 8) |
+                ((uint32_t)(epilogue_one<ACT>(a.z, g.alpha, bj.z) & 0xff) << 16) |
+                ((uint32_t)(epilogue_one<ACT>(a.w, g.alpha, bj.w) & 0xff) << 24);
         }
     }
 }
@@ -311,7 +400,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Split-K accumulation scratch, one per device, grown on demand (stream-ordered reuse: all
+// Split-K partial-tile scratch, one per device, grown on demand (stream-ordered reuse: all
 // pa_gemm_i8 calls of a process are expected on one stream per device).
 struct Scratch {
     int32_t* p = nullptr;
@@ -344,8 +433,28 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
     if (!di.ok) return PA_ERR_NO_DEVICE;
     cudaStream_t st = as_stream(stream);
 
+    const int n_slabs = (N + BN - 1) / BN;
+    const int m_chunks = (M + 2 * BM - 1) / (2 * BM);
+    const int m_tiles0 = M > BM ? 2 : 1;
+    // Cluster multicast of A needs one M chunk (uniform m_tiles) and n_slabs divisible by CL.
+    int CLs = 1;
+    // Measured (profiles/r01_gemm_notes.md): equal speed for CL = 1/2/4 at the C4 shapes -- the
+    // loop is bound by B bytes in flight, not by L2 reads -- so default to pairs, which cut the
+    // L2 read traffic for A in half and never strand SMs.  PA_GEMM_CLUSTER=1|2|4 overrides.
+    if (m_chunks == 1) {
+        if (n_slabs % 4 == 0) CLs = 4;
+        else if (n_slabs % 2 == 0) CLs = 2;
+    }
+    const int cl_max = CLs;
+    if (CLs > 2) CLs = 2;
+    const char* cl_env = getenv("PA_GEMM_CLUSTER");
+    if (cl_env) {
+        const int want = atoi(cl_env);
+        if (want == 1 || (want == 2 && cl_max >= 2) || (want == 4 && cl_max == 4)) CLs = want;
+    }
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, BM)) return PA_ERR_UNSUPPORTED;
+    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, CLs == 1 ? BM : m_tiles0 * BM / CLs))
+        return PA_ERR_UNSUPPORTED;
     if (!make_map(&tmB, d_B, (uint64_t)N, (uint64_t)K, (uint64_t)BATCH, BK)) return PA_ERR_UNSUPPORTED;
 
     Args g{};
@@ -355,8 +464,10 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
     g.alpha = scaleA * scaleB / scaleC;  // dnnl_matmul_int8.cpp:40, fp32, left to right
     g.act = act;
     g.M = M; g.N = N; g.K = K;
-    const int n_slabs = (N + BN - 1) / BN;
-    const int m_chunks = (M + 2 * BM - 1) / (2 * BM);
+#ifdef PA_GEMM_PROBE
+    extern unsigned long long* pa_gemm_probe_buf;
+    g.probe = pa_gemm_probe_buf;
+#endif
     const int total_kb = (K + BK - 1) / BK;
     const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH;
     int ksplit = (int)(di.sm_count / ctas);
@@ -368,7 +479,7 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
     const int64_t rows = (int64_t)BATCH * M;
     if (ksplit > 1) {
         Scratch& sc = scratch_for_device();
-        const size_t need = (size_t)rows * N * sizeof(int32_t);
+        const size_t need = (size_t)ksplit * rows * N * sizeof(int32_t);
         if (sc.bytes < need) {
             if (sc.p) cudaFree(sc.p);
             sc.p = nullptr;
@@ -378,27 +489,48 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
             sc.bytes = need;
         }
         g.acc_ws = sc.p;
-        cudaError_t e = cudaMemsetAsync(sc.p, 0, need, st);
-        if (e != cudaSuccess) return (int)e;
     }
+    g.BATCH_rows = rows;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
-    static bool attr_set[64] = {false};
+    const int epi = (ksplit > 1 || !d_C_s8) ? 0 : 1 + act;
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
+    static const KernelFn kernels[3][4] = {
+        {gemm_i8_kernel<0, 1>, gemm_i8_kernel<1, 1>, gemm_i8_kernel<2, 1>, gemm_i8_kernel<3, 1>},
+        {gemm_i8_kernel<0, 2>, gemm_i8_kernel<1, 2>, gemm_i8_kernel<2, 2>, gemm_i8_kernel<3, 2>},
+        {gemm_i8_kernel<0, 4>, gemm_i8_kernel<1, 4>, gemm_i8_kernel<2, 4>, gemm_i8_kernel<3, 4>}};
+    const int cli = CLs == 4 ? 2 : (CLs == 2 ? 1 : 0);
+    KernelFn kern = kernels[cli][epi];
+    static bool attr_set[64][3][4] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!attr_set[dev & 63][cli][epi]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set[dev & 63] = true;
+        attr_set[dev & 63][cli][epi] = true;
     }
-    dim3 grid((unsigned)n_slabs, (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
-    gemm_i8_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmB, g);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_slabs, (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CLs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (ksplit > 1) {
         const int64_t n4 = rows * N / 4;
         int blocks = (int)((n4 + 255) / 256);
         if (blocks > di.sm_count * 8) blocks = di.sm_count * 8;
-        gemm_i8_splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(g, rows);
+        if (act == PA_ACT_RELU) gemm_i8_splitk_epilogue_kernel<PA_ACT_RELU><<<blocks, 256, 0, st>>>(g, rows);
+        else if (act == PA_ACT_GELU) gemm_i8_splitk_epilogue_kernel<PA_ACT_GELU><<<blocks, 256, 0, st>>>(g, rows);
+        else gemm_i8_splitk_epilogue_kernel<PA_ACT_NONE><<<blocks, 256, 0, st>>>(g, rows);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
