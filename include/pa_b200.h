@@ -207,6 +207,48 @@ int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_
                int M, int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias,
                int act, pa_stream_t stream);
 
+/* Dynamic-quantisation form of the same GEMM, used by the INT8 decoder MLP ("int8_quant ->
+ * dnnl_matmul_int8 -> dequant", attention_cpu/README.md:80-86):
+ *   C_f32[b,m,n] = act(alpha_row*acc + bias[n]),  alpha_row = b_dequant / d_a_qscales[b*M+m]
+ * d_a_qscales [BATCH*M] are the DEVICE-resident per-row quantisation scales of A in the
+ * int8_quant.cpp convention (A_s8 = batch_quantize(x, scales, K), int8_quant.cpp:15-28,
+ * so x ~ A_s8 / scale); b_dequant is the dequantisation multiplier of the weights
+ * (w ~ B_s8 * b_dequant).  No host synchronisation: the scales produced by
+ * pa_batch_minmax_scale feed this call directly. */
+int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f32, int BATCH, int M, int N,
+                       int K, const float* d_a_qscales, float b_dequant, const float* d_bias, int act,
+                       pa_stream_t stream);
+
+/* ------------------------------------------------- decoder glue (row a14) */
+/* decoder/token_embedding.hpp:19-26: d_out[r,:] = E[d_ids[r],:] (ids outside [0,vocab) give
+ * zeros; the reference reads out of bounds).  _i8: int8 table dequantised as q/qscale
+ * (int8_quant.cpp:38-44). */
+int pa_embedding_f32(const float* d_E, const int32_t* d_ids, int rows, int hidden, int vocab,
+                     float* d_out, pa_stream_t stream);
+int pa_embedding_i8(const int8_t* d_E, float qscale, const int32_t* d_ids, int rows, int hidden,
+                    int vocab, float* d_out, pa_stream_t stream);
+/* decoder/layer_norm.hpp:20-37: biased variance, inv_std = 1/sqrt(var+eps), y = (x-mean)*inv_std*gamma+beta.
+ * d_out may alias d_x. */
+int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float* d_beta, int rows,
+                      int hidden, float eps, float* d_out, pa_stream_t stream);
+/* decoder/mlp.hpp:23-41, one layer of the float MLP: out[r,n] = act(bias[n] + sum_k x[r,k]*W[k*N+n]),
+ * act in {PA_ACT_NONE, PA_ACT_RELU}.  d_out must not alias d_x. */
+int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N,
+                  int act, float* d_out, pa_stream_t stream);
+/* logits[r,v] = dot(x[r,:], E[v,:]) against the (tied) embedding table E [vocab, hidden]
+ * (the reference reads logits out of the hidden state, cuda_decoder.cu:58). */
+int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidden, int vocab,
+                  float* d_logits, pa_stream_t stream);
+int pa_logits_i8(const float* d_x, const int8_t* d_E, float qscale, int rows, int hidden, int vocab,
+                 float* d_logits, pa_stream_t stream);
+/* decoder/cuda_decoder.cu:7-14 sample_from_logits (divide=1: argmax logits/T) and
+ * decoder/int8_decoder.cpp:97-104 sample_from_int8_logits (divide=0: argmax logits*T);
+ * first maximum wins (std::max_element). */
+int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature, int divide,
+                  int32_t* d_out_ids, pa_stream_t stream);
+/* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
+int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,4 +9,4 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this package.  The product (llm_decoder + libpa_b200.so) never does.
 """
-from . import cpu, ref  # noqa: F401
+from . import cpu, decoder_ref, ref  # noqa: F401

@@ -41,6 +41,7 @@ def lib():
         _lib.orc_compute_minmax_scale.restype = C.c_float
         _lib.orc_kv_page_offset.restype = C.c_int64
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_quantize_weights_file.restype = C.c_float
     return _lib
 
 
@@ -315,3 +316,11 @@ def mlp_f32(x, fc1_w, fc1_b, fc2_w, fc2_b):
     lib().orc_mlp_f32(_p(x, _f32p), _p(out, _f32p), _p(fc1_w, _f32p), _p(fc1_b, _f32p),
                       _p(fc2_w, _f32p), _p(fc2_b, _f32p), rows, hidden, inter)
     return out
+
+
+def quantize_weights_file(w):
+    """decoder/int8_decoder.cpp:52-56 -> (int8 array, scale)."""
+    w = _f32(w).reshape(-1)
+    out = np.empty(w.size, dtype=np.int8)
+    scale = lib().orc_quantize_weights_file(_p(w, _f32p), C.c_int64(w.size), _p(out, _i8p))
+    return out, float(scale)

@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the decoder layer loop, built from the oracle's
+pinned pieces.  PARITY UNPINNED as a whole: the reference's decoders do not compile and do not
+append K/V; this restates the SAME decisions llm_decoder/decoders.py
+documents, step by step, so the GPU `generate` can be checked against an independent CPU path.
+
+  decoder/token_embedding.hpp:19-26  embedding lookup
+  decoder/decoder_block.hpp:41-62    LN1 -> attention(q = LN1 out) -> LN2 -> MLP, no residuals
+  decoder/layer_norm.hpp:20-37       oracle.cpu.layer_norm
+  decoder/mlp.hpp:23-41              oracle.cpu.mlp_f32 (float) / int8_quant + dnnl_matmul_int8 (int8)
+  attention_cpu/cpu_attention_kernel.cpp:36-129  oracle.cpu.paged_attention
+  decoder/cuda_decoder.cu:7-14, int8_decoder.cpp:97-104  greedy argmax (first maximum)
+"""
+import numpy as np
+
+from . import cpu
+
+
+def _pages_from_rows(rows, H, D, tile, dtype):
+    """rows: list of [H, D] arrays (one per cached token) -> pool [H*nt, tile, D], table [1,H,nt]."""
+    t = len(rows)
+    nt = max(1, (t + tile - 1) // tile)
+    pool = np.zeros((H * nt, tile, D), dtype=dtype)
+    for i, r in enumerate(rows):
+        for h in range(H):
+            pool[h * nt + i // tile, i % tile] = r[h]
+    table = np.arange(H * nt, dtype=np.int32).reshape(1, H, nt)
+    return pool, table, nt
+
+
+class RefDecoder:
+    """Teacher-forced CPU decoder: feed tokens one at a time, get the logits of each step."""
+
+    def __init__(self, weights, H, D, tile=16, int8=False, attn_temperature=1.0, eps=1e-5):
+        self.w, self.H, self.D, self.tile, self.int8 = weights, H, D, tile, int8
+        self.attn_temperature, self.eps = attn_temperature, eps
+        L = len(weights["layers"])
+        self.k_rows = [[] for _ in range(L)]   # per layer: list of [H, D] (fp16-rounded f32, or int8)
+        self.k_scales = [[] for _ in range(L)]  # int8: list of [H] scales
+
+    def _attend(self, li, n1):
+        H, D, tile = self.H, self.D, self.tile
+        if not self.int8:
+            self.k_rows[li].append(n1.reshape(H, D).astype(np.float16).astype(np.float32))
+            pool, table, nt = _pages_from_rows(self.k_rows[li], H, D, tile, np.float32)
+            return cpu.paged_attention(n1.reshape(1, H, D), pool, pool, table, num_beams=1, num_tiles=nt,
+                                       tile_size=tile, T=len(self.k_rows[li]),
+                                       temperature=self.attn_temperature).reshape(-1)
+        sc = cpu.batch_minmax_scale(n1, D)                      # one scale per (token, head) row
+        q = cpu.batch_quantize(n1, sc, D).reshape(H, D)
+        self.k_rows[li].append(q)
+        self.k_scales[li].append(sc.reshape(H))
+        pool, table, nt = _pages_from_rows(self.k_rows[li], H, D, tile, np.int8)
+        spool = np.ones((H * nt, tile), dtype=np.float32)
+        for i, s in enumerate(self.k_scales[li]):
+            for h in range(H):
+                spool[h * nt + i // tile, i % tile] = s[h]
+        return cpu.paged_attention(n1.reshape(1, H, D), pool, pool, table, num_beams=1, num_tiles=nt, tile_size=tile,
+                                   T=len(self.k_rows[li]), temperature=self.attn_temperature, k_scales=spool,
+                                   v_scales=spool).reshape(-1)
+
+    def _mlp_i8(self, n2, L):
+        def lin(x, wq, deq, bias, relu):
+            s = cpu.batch_minmax_scale(x, x.size)
+            xq = cpu.batch_quantize(x, s, x.size).reshape(1, 1, -1)
+            acc = cpu.gemm_s8s8s32(xq, wq[None])[0, 0].astype(np.float32)
+            alpha = np.float32(deq) / np.float32(s[0])
+            v = (alpha * acc).astype(np.float32) + bias.astype(np.float32)
+            return np.maximum(v, np.float32(0)) if relu else v
+        h = lin(n2, L["fc1_w"], L["fc1_deq"], L["fc1_b"], True)
+        return lin(h.astype(np.float32), L["fc2_w"], L["fc2_deq"], L["fc2_b"], False)
+
+    def step(self, token):
+        w = self.w
+        if self.int8:
+            x = w["embedding"][token].astype(np.float32) / np.float32(w["emb_qscale"])
+        else:
+            x = w["embedding"][token].astype(np.float32)
+        for li, L in enumerate(w["layers"]):
+            n1 = cpu.layer_norm(x[None], L["ln1_g"], L["ln1_b"], self.eps)[0]
+            a = self._attend(li, n1)
+            n2 = cpu.layer_norm(a[None], L["ln2_g"], L["ln2_b"], self.eps)[0]
+            if self.int8:
+                x = self._mlp_i8(n2, L)
+            else:
+                x = cpu.mlp_f32(n2[None], L["fc1_w"], L["fc1_b"], L["fc2_w"], L["fc2_b"])[0]
+        if self.int8:
+            logits = (w["embedding"].astype(np.float32) @ x.astype(np.float32)) / np.float32(w["emb_qscale"])
+        else:
+            logits = w["embedding"].astype(np.float32) @ x.astype(np.float32)
+        return logits.astype(np.float32)
+
+
+def sample(logits, temperature, divide):
+    """cuda_decoder.cu:7-14 (divide) / int8_decoder.cpp:97-104 (multiply); first maximum."""
+    t = np.float32(temperature)
+    v = logits / t if divide else logits * t
+    return int(np.argmax(v))

@@ -573,6 +573,20 @@ ORC_API void orc_mlp_f32(const float* in, float* out, const float* fc1_w, const 
     }
 }
 
+
+/* ------------------------------------------------------------------ */
+/* INT8Decoder::quantize_weights arithmetic (decoder/int8_decoder.cpp:52-56,  */
+/* also INT8Quantizer::quantize :20-25): scale = *max_element (signed max),   */
+/* int8 = static_cast<int8_t>(fp32 / scale * 127): truncation, no clamp.      */
+/* ------------------------------------------------------------------ */
+ORC_API float orc_quantize_weights_file(const float* w, int64_t n, int8_t* out) {
+    float scale = w[0];
+    for (int64_t i = 1; i < n; ++i)
+        if (w[i] > scale) scale = w[i];
+    for (int64_t i = 0; i < n; ++i) out[i] = (int8_t)(int32_t)(w[i] / scale * 127);
+    return scale;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

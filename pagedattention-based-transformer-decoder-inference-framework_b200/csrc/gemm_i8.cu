@@ -46,6 +46,8 @@ constexpr int NTHREADS = 192;
 
 struct Args {
     int8_t* C8;
+    float* Cf;           // f32 output act(alpha*acc + bias) (dequantising epilogue; may be null)
+    const float* a_qscale;  // [BATCH*M] per-row: alpha_row = alpha / a_qscale[row] (dynamic activation scales)
     int32_t* C32;        // raw accumulators out (may be null)
     int32_t* acc_ws;     // split-K partial tiles [ksplit][BATCH*M][N], null when ksplit == 1
     const float* bias;
@@ -135,6 +137,14 @@ constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1
                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int ACT>
+__device__ __forceinline__ float epilogue_f32(int acc, float alpha, float bias) {
+    float v = __fadd_rn(__fmul_rn(alpha, (float)acc), bias);
+    if (ACT == PA_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (ACT == PA_ACT_GELU) v = gelu_erf(v);
+    return v;
+}
 
 template <int ACT>
 __device__ __forceinline__ int epilogue_one(int acc, float alpha, float bias) {
@@ -289,6 +299,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row = m0 + mt * BM + qtr * 32 + lane;
             const bool row_ok = row < g.M;
             const int64_t out_row = ((int64_t)batch * g.M + row) * g.N;
+            // per-row dynamic activation scale (batch_quantize's scales[], int8_quant.cpp:15-28)
+            const float alpha = (g.a_qscale && row_ok) ? __fdiv_rn(g.alpha, __ldg(g.a_qscale + (int64_t)batch * g.M + row))
+                                                       : g.alpha;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 32; ++cc) {
                 uint32_t r[32];
@@ -311,16 +324,29 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             *reinterpret_cast<int4*>(g.C32 + out_row + col0 + j) =
                                 make_int4((int)r[j], (int)r[j + 1], (int)r[j + 2], (int)r[j + 3]);
                 }
-                if (EPI != 0) {
+                if (EPI != 0 && g.Cf) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        if (w < 4 || hi_ok) {
+                            float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (g.bias) bj = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + w);
+                            *reinterpret_cast<float4*>(g.Cf + out_row + col0 + 4 * w) =
+                                make_float4(epilogue_f32<ACT>((int)r[4 * w + 0], alpha, bj.x),
+                                            epilogue_f32<ACT>((int)r[4 * w + 1], alpha, bj.y),
+                                            epilogue_f32<ACT>((int)r[4 * w + 2], alpha, bj.z),
+                                            epilogue_f32<ACT>((int)r[4 * w + 3], alpha, bj.w));
+                        }
+                    }
+                } else if (EPI != 0) {
                     uint32_t packed[8];
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
                         float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (g.bias && (w < 4 || hi_ok)) bj = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + w);
-                        packed[w] = (uint32_t)(epilogue_one<ACT>((int)r[4 * w + 0], g.alpha, bj.x) & 0xff) |
-                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 1], g.alpha, bj.y) & 0xff) << 8) |
-                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 2], g.alpha, bj.z) & 0xff) << 16) |
-                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 3], g.alpha, bj.w) & 0xff) << 24);
+                        packed[w] = (uint32_t)(epilogue_one<ACT>((int)r[4 * w + 0], alpha, bj.x) & 0xff) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 1], alpha, bj.y) & 0xff) << 8) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 2], alpha, bj.z) & 0xff) << 16) |
+                                    ((uint32_t)(epilogue_one<ACT>((int)r[4 * w + 3], alpha, bj.w) & 0xff) << 24);
                     }
                     *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     if (hi_ok)
@@ -355,15 +381,21 @@ __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
         if (g.C32) reinterpret_cast<int4*>(g.C32)[i] = a;
-        if (g.C8) {
+        if (g.C8 || g.Cf) {
             const int col = (int)((i * 4) % g.N);
+            const float alpha = g.a_qscale ? __fdiv_rn(g.alpha, __ldg(g.a_qscale + (i * 4) / g.N)) : g.alpha;
             float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g.bias) bj = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-            reinterpret_cast<uint32_t*>(g.C8)[i] =
-                (uint32_t)(epilogue_one<ACT>(a.x, g.alpha, bj.x) & 0xff) |
-                ((uint32_t)(epilogue_one<ACT>(a.y, g.alpha, bj.y) & 0xff) << 8) |
-                ((uint32_t)(epilogue_one<ACT>(a.z, g.alpha, bj.z) & 0xff) << 16) |
-                ((uint32_t)(epilogue_one<ACT>(a.w, g.alpha, bj.w) & 0xff) << 24);
+            if (g.Cf)
+                reinterpret_cast<float4*>(g.Cf)[i] =
+                    make_float4(epilogue_f32<ACT>(a.x, alpha, bj.x), epilogue_f32<ACT>(a.y, alpha, bj.y),
+                                epilogue_f32<ACT>(a.z, alpha, bj.z), epilogue_f32<ACT>(a.w, alpha, bj.w));
+            else
+                reinterpret_cast<uint32_t*>(g.C8)[i] =
+                    (uint32_t)(epilogue_one<ACT>(a.x, alpha, bj.x) & 0xff) |
+                    ((uint32_t)(epilogue_one<ACT>(a.y, alpha, bj.y) & 0xff) << 8) |
+                    ((uint32_t)(epilogue_one<ACT>(a.z, alpha, bj.z) & 0xff) << 16) |
+                    ((uint32_t)(epilogue_one<ACT>(a.w, alpha, bj.w) & 0xff) << 24);
         }
     }
 }
@@ -419,11 +451,12 @@ static Scratch& scratch_for_device() {
 using namespace pa;
 using namespace pa::gemm;
 
-PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH, int M,
-                      int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias, int act,
-                      pa_stream_t stream) {
-    PA_CHECK_ARG(d_A && d_B && (d_C_s8 || d_C_s32));
-    PA_CHECK_ARG(BATCH > 0 && M > 0 && N > 0 && K > 0 && scaleC != 0.f);
+static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, float* d_C_f32, int32_t* d_C_s32,
+                          int BATCH, int M, int N, int K, float alpha_host, const float* d_a_qscale,
+                          const float* d_bias, int act, pa_stream_t stream) {
+    PA_CHECK_ARG(d_A && d_B && (d_C_s8 || d_C_s32 || d_C_f32));
+    PA_CHECK_ARG(BATCH > 0 && M > 0 && N > 0 && K > 0);
+    PA_CHECK_ARG(!d_C_f32 || (uintptr_t)d_C_f32 % 16 == 0);
     PA_CHECK_ARG(act == PA_ACT_NONE || act == PA_ACT_RELU || act == PA_ACT_GELU);
     if (K % 16 != 0 || N % 16 != 0) return PA_ERR_UNSUPPORTED;
     PA_CHECK_ARG((uintptr_t)d_A % 16 == 0 && (uintptr_t)d_B % 16 == 0);
@@ -459,9 +492,11 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
 
     Args g{};
     g.C8 = d_C_s8;
+    g.Cf = d_C_f32;
+    g.a_qscale = d_a_qscale;
     g.C32 = d_C_s32;
     g.bias = d_bias;
-    g.alpha = scaleA * scaleB / scaleC;  // dnnl_matmul_int8.cpp:40, fp32, left to right
+    g.alpha = alpha_host;
     g.act = act;
     g.M = M; g.N = N; g.K = K;
 #ifdef PA_GEMM_PROBE
@@ -492,7 +527,7 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
     }
     g.BATCH_rows = rows;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
-    const int epi = (ksplit > 1 || !d_C_s8) ? 0 : 1 + act;
+    const int epi = (ksplit > 1 || !(d_C_s8 || d_C_f32)) ? 0 : 1 + act;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
     static const KernelFn kernels[3][4] = {
         {gemm_i8_kernel<0, 1>, gemm_i8_kernel<1, 1>, gemm_i8_kernel<2, 1>, gemm_i8_kernel<3, 1>},
@@ -535,4 +570,22 @@ PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int3
         if (e != cudaSuccess) return (int)e;
     }
     return PA_OK;
+}
+
+PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH, int M,
+                      int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias, int act,
+                      pa_stream_t stream) {
+    PA_CHECK_ARG(d_C_s8 || d_C_s32);
+    PA_CHECK_ARG(scaleC != 0.f);
+    // dnnl_matmul_int8.cpp:40, fp32, left to right
+    return gemm_i8_launch(d_A, d_B, d_C_s8, nullptr, d_C_s32, BATCH, M, N, K, scaleA * scaleB / scaleC, nullptr,
+                          d_bias, act, stream);
+}
+
+PA_API int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f32, int BATCH, int M, int N, int K,
+                              const float* d_a_qscale, float b_dequant, const float* d_bias, int act,
+                              pa_stream_t stream) {
+    PA_CHECK_ARG(d_C_f32 && d_a_qscale);
+    return gemm_i8_launch(d_A, d_B, nullptr, d_C_f32, nullptr, BATCH, M, N, K, b_dequant, d_a_qscale, d_bias, act,
+                          stream);
 }

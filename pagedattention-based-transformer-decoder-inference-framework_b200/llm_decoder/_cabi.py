@@ -45,6 +45,15 @@ _SIGS = {
     "pa_dequantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
     "pa_batch_dequantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),
     "pa_gemm_i8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp], _i32),
+    "pa_gemm_i8_dequant": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _vp], _i32),
+    "pa_embedding_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_embedding_i8": ([_vp, _f32, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_layer_norm_f32": ([_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp], _i32),
+    "pa_linear_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_logits_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_logits_i8": ([_vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),
+    "pa_advance_positions": ([_vp, _vp, _i32, _vp], _i32),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -1,0 +1,417 @@
+"""CUDADecoder / INT8Decoder -- drop-in for the two classes the reference binds
+(src/bindings.cpp:5-29): same constructor (six ints), `load_weights` /
+`load_quantized_weights` / `quantize_weights`, and `generate(input_ids, max_len, temperature)`
+returning prompt + generated ids.
+
+The layer loop is the reference's (decoder/decoder_block.hpp:41-62): LN1 -> attention (q := LN1
+output, B=1 per sequence, no QKV/O projections, no residuals) -> LN2 -> MLP(ReLU, 4x hidden,
+decoder/mlp.hpp:23-41), greedy argmax sampling (cuda_decoder.cu:7-14 / int8_decoder.cpp:97-104).
+Decisions where the reference is not well defined, stated here because
+token-level parity with a program that never appends K/V and recomputes the whole sequence on
+the host with aliased buffers is meaningless:
+  * decode is incremental: each step appends the new token's K/V rows (K = V = the LN1 output
+    split per head -- the only tensor the reference feeds to attention) to a per-layer paged
+    KV cache (pa_kv_append_*), then attends over the cached context (pa_paged_decode_*);
+  * logits = final hidden state . E^T (tied embedding); the reference reads the first
+    vocab_size floats of the hidden buffer (cuda_decoder.cu:58);
+  * INT8Decoder: int8 weights + int8 KV pages; activations are quantised per row with
+    compute_minmax_scale/batch_quantize (int8_quant.cpp), the MLP runs on the tcgen05 kind::i8
+    GEMM with the dequantising epilogue (pa_gemm_i8_dequant) -- the "int8_quant ->
+    dnnl_matmul_int8 -> dequant" pipeline of attention_cpu/README.md:80-86 instead of
+    MLP<int8_t>'s overflowing int8 accumulators (mlp.hpp:28).
+
+Every step runs on the device through libpa_b200.so (no host math, no per-step
+synchronisation); the steady-state step is captured in a CUDA graph.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .kv_tile_cache import KVTileCache
+
+_LAYER_FILES = ("ln1.bin", "ln2.bin", "mlp_fc1.bin", "mlp_fc2.bin", "mlp_biases.bin")  # int8_decoder.cpp:66-70
+
+
+def _read_bin(path, dtype, count, what):
+    """load_vector_from_file (decoder/decoder_block.hpp:10-20): raw little-endian flat buffer."""
+    if not os.path.isfile(path):
+        raise RuntimeError(f"Failed to open weight file: {path}")
+    a = np.fromfile(path, dtype=dtype)
+    if a.size < count:
+        raise RuntimeError(f"Failed to read from file: {path} ({what}: need {count} elements, file has {a.size})")
+    return a[:count]
+
+
+class _Layer:
+    pass
+
+
+class _DecoderBase:
+    KV_DTYPE = "f16"
+    ARGMAX_DIVIDE = 1  # cuda_decoder.cu:10-13 logits / temperature
+
+    def __init__(self, num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len, *, device=None,
+                 tile_size=16, batch_size=1, attn_temperature=1.0, use_overlap=True, use_cuda_graph=True):
+        if min(num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len) <= 0:
+            raise ValueError("decoder dimensions must be positive")
+        if hidden_dim != num_heads * head_dim:
+            raise ValueError("hidden_dim must equal num_heads * head_dim: the block feeds the LN1 output "
+                             "[hidden] to attention as q [H, D] (decoder_block.hpp:45-50)")
+        if head_dim not in (64, 128):
+            raise ValueError("head_dim must be 64 or 128 (kernels built for these)")
+        self.num_layers_, self.num_heads_, self.head_dim_ = num_layers, num_heads, head_dim
+        self.hidden_dim_, self.vocab_size_, self.max_seq_len_ = hidden_dim, vocab_size, max_seq_len
+        self.inter_dim_ = hidden_dim * 4  # decoder_block.hpp:28
+        self.tile_size_ = tile_size
+        self.attn_temperature = float(attn_temperature)  # AttentionCUDA::forward default (attention_config.hpp:19)
+        self.use_overlap = use_overlap
+        self.use_cuda_graph = use_cuda_graph
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._lib = _cabi.lib()  # fails loudly when the CUDA library is missing
+        self.eps = 1e-5  # layer_norm.hpp:10
+        self.layers = [_Layer() for _ in range(num_layers)]
+        self._alloc_default_weights()
+        self._batch = 0
+        self._graph = None
+        self._setup_batch(batch_size)
+
+    # ------------------------------------------------------------------ state
+    def _setup_batch(self, B):
+        if B == self._batch:
+            return
+        H, D, hid, dev = self.num_heads_, self.head_dim_, self.hidden_dim_, self.device
+        nt = (self.max_seq_len_ + self.tile_size_ - 1) // self.tile_size_
+        self._batch, self._num_tiles = B, nt
+        table = np.arange(B * H * nt, dtype=np.int32).reshape(B, H, nt)
+        self.kv_caches = []
+        for _ in range(self.num_layers_):
+            kvc = KVTileCache(self.KV_DTYPE, device=dev)
+            kvc.init(B * H * nt, self.tile_size_, D)
+            kvc.configure_table(B, H, nt)
+            kvc.page_table_.load_host_table(table)
+            self.kv_caches.append(kvc)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.ids = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.positions = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.ctx_lens = torch.ones(B, dtype=torch.int32, device=dev)
+        self.x = torch.zeros((B, hid), **f32)
+        self.n = torch.zeros((B, hid), **f32)
+        self.a = torch.zeros((B, hid), **f32)
+        self.h = torch.zeros((B, self.inter_dim_), **f32)
+        self.logits = torch.zeros((B, self.vocab_size_), **f32)
+        self.xq = torch.zeros((B, hid), dtype=torch.int8, device=dev)
+        self.hq = torch.zeros((B, self.inter_dim_), dtype=torch.int8, device=dev)
+        self.xs = torch.ones(B, **f32)
+        self.hs = torch.ones(B, **f32)
+        self._ws = self.kv_caches[0].workspace(B)
+        self._graph = None
+
+    def reset(self):
+        """Forget all cached context (positions back to 0; pages keep their assignment)."""
+        self.positions.zero_()
+        self.ctx_lens.fill_(1)
+
+    # ------------------------------------------------------------------ device step
+    def _chk(self, st, what):
+        _cabi.check(st, what)
+
+    def _attention(self, layer_idx, q, out):
+        kvc = self.kv_caches[layer_idx]
+        pt = kvc.page_table_
+        lib, B = self._lib, self._batch
+        common = (pt.d_table_.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kvc.total_pages_, None,
+                  self.ctx_lens.data_ptr(), B, self.max_seq_len_, self.head_dim_, kvc.tile_size_,
+                  self.attn_temperature, None, None, self._ws.data_ptr(), self._ws.numel(), _cabi.stream())
+        if kvc.dtype == "f16":
+            fn = lib.pa_paged_decode_f16_overlap if self.use_overlap else lib.pa_paged_decode_f16
+            st = fn(q.data_ptr(), out.data_ptr(), kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr(), *common)
+        else:
+            fn = lib.pa_paged_decode_i8_overlap if self.use_overlap else lib.pa_paged_decode_i8
+            st = fn(q.data_ptr(), out.data_ptr(), kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr(),
+                    kvc.k_scales_.data_ptr(), kvc.v_scales_.data_ptr(), *common)
+        self._chk(st, "pa_paged_decode")
+
+    def _step(self):
+        """One decode step for the B tokens in self.ids at self.positions; writes the greedy next
+        ids back into self.ids and advances positions.  Device work only."""
+        lib, B, hid, s = self._lib, self._batch, self.hidden_dim_, _cabi.stream()
+        self._embed()
+        for li, L in enumerate(self.layers):
+            self._chk(lib.pa_layer_norm_f32(self.x.data_ptr(), L.ln1_g.data_ptr(), L.ln1_b.data_ptr(), B, hid,
+                                            self.eps, self.n.data_ptr(), s), "pa_layer_norm_f32")
+            nview = self.n.view(B, self.num_heads_, self.head_dim_)
+            self.kv_caches[li].append(nview, nview, self.positions)  # K = V = LN1 output (see module doc)
+            self._attention(li, self.n, self.a)
+            self._chk(lib.pa_layer_norm_f32(self.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), B, hid,
+                                            self.eps, self.n.data_ptr(), s), "pa_layer_norm_f32")
+            self._mlp(L)
+        self._logits()
+        self._chk(lib.pa_argmax_f32(self.logits.data_ptr(), B, self.vocab_size_, self._temperature,
+                                    self.ARGMAX_DIVIDE, self.ids.data_ptr(), s), "pa_argmax_f32")
+        self._chk(lib.pa_advance_positions(self.positions.data_ptr(), self.ctx_lens.data_ptr(), B, s),
+                  "pa_advance_positions")
+
+    # ------------------------------------------------------------------ generate
+    def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None):
+        """generate(input_ids, max_len, temperature) -> prompt + generated ids (bindings.cpp:8-15).
+        Also tolerated (callers in api/, cli/): generate(input_ids, output_ids_list, max_tokens,
+        temperature) -- the list is extended in place and returned -- and max_gen_len=."""
+        out_list = None
+        if isinstance(max_len, list):  # 4-arg out-param form (api/router.py:23)
+            out_list, max_len = max_len, temperature
+            temperature = extra[0] if extra else 1.0
+        if max_gen_len is not None:
+            max_len = max_gen_len
+        if max_len is None:
+            raise TypeError("generate() missing max_len")
+        seqs = self.generate_batch([list(input_ids)], int(max_len), float(temperature))
+        if out_list is not None:
+            out_list[:] = seqs[0]
+            return out_list
+        return seqs[0]
+
+    def generate_batch(self, prompts, max_len, temperature=1.0):
+        """Greedy decode of several sequences at once (equal prompt lengths): rows are independent."""
+        B = len(prompts)
+        n_prompt = len(prompts[0])
+        if n_prompt == 0 or any(len(p) != n_prompt for p in prompts):
+            raise ValueError("prompts must be non-empty and of equal length")
+        if n_prompt + max_len - 1 > self.max_seq_len_:
+            raise ValueError("prompt + max_len exceeds max_seq_len")
+        if max_len <= 0:
+            return [list(p) for p in prompts]
+        self._setup_batch(B)
+        self.reset()
+        self._temperature = float(temperature)
+        dev = self.device
+        with torch.cuda.device(dev):
+            prompt = torch.tensor(prompts, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)  # [B, n]
+            gen = torch.empty((max_len, B), dtype=torch.int32, device=dev)
+            for t in range(n_prompt):  # prompt tokens one step each (a prefill kernel is a "next" row)
+                self.ids.copy_(prompt[:, t])
+                self._step_or_replay()
+            for i in range(max_len):  # self.ids holds the token sampled by the previous step
+                gen[i].copy_(self.ids)
+                if i + 1 < max_len:
+                    self._step_or_replay()
+            gen_host = gen.t().cpu().tolist()  # the only synchronisation of the call
+        return [list(p) + g for p, g in zip(prompts, gen_host)]
+
+    def forward_tokens(self, token_ids, temperature=1.0):
+        """One eager decode step for `token_ids` ([B] ints) at the current positions: appends their K/V,
+        returns the logits [B, vocab] (device tensor, valid until the next step).  The sampled next ids are
+        in `self.ids`.  Call `reset()` first to start a new sequence."""
+        self._setup_batch(len(token_ids))
+        self._temperature = float(temperature)
+        with torch.cuda.device(self.device):
+            self.ids.copy_(torch.tensor(list(token_ids), dtype=torch.int32))
+            self._step()
+        return self.logits
+
+    def _step_or_replay(self):
+        if not self.use_cuda_graph:
+            self._step()
+        elif self._graph is not None and self._graph_temp == self._temperature:
+            self._graph.replay()
+        else:
+            self._step_warm = getattr(self, "_step_warm", 0)
+            if self._step_warm < 1:
+                self._step()  # one eager step first: lazy one-time init inside the library
+                self._step_warm += 1
+            else:
+                # capture a graph of the step; capture itself does not run it, so replay once
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step()
+                self._graph, self._graph_temp = g, self._temperature
+                g.replay()
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, a, dtype=torch.float32):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device).to(dtype)
+
+
+class CUDADecoder(_DecoderBase):
+    """py::class_<CUDADecoder<float>>(m, "CUDADecoder") -- src/bindings.cpp:5-15;
+    decoder/cuda_decoder.hpp:6-19, cuda_decoder.cu:23-61.  fp32 weights, fp16 KV pages."""
+    KV_DTYPE = "f16"
+    ARGMAX_DIVIDE = 1
+
+    def _alloc_default_weights(self):
+        hid, inter, dev = self.hidden_dim_, self.inter_dim_, self.device
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731  std::vector<T>(n) zero-init
+        self.embedding = z(self.vocab_size_, hid)
+        for L in self.layers:
+            L.ln1_g, L.ln1_b = torch.ones(hid, device=dev), z(hid)  # layer_norm.hpp:11 gamma=1, beta=0
+            L.ln2_g, L.ln2_b = torch.ones(hid, device=dev), z(hid)
+            L.fc1_w, L.fc1_b, L.fc2_w, L.fc2_b = z(hid, inter), z(inter), z(inter, hid), z(hid)
+
+    def load_weights(self, path):
+        """cuda_decoder.cu:35-45: <path>/embedding.bin, <path>/layer_<i>/{ln1.bin, ln2.bin} (gamma then
+        beta, layer_norm.hpp:13-18) and the MLP.  The reference's MLP::load_weights opens the layer
+        DIRECTORY as a file (decoder_block.hpp:38, mlp.hpp:15), which cannot work; accepted here:
+        <layer>/mlp.bin = fc1_w, fc1_b, fc2_w, fc2_b concatenated (the order mlp.hpp:17-20 reads), or the
+        split files mlp_fc1.bin / mlp_fc2.bin / mlp_biases.bin of weights/README.md and quantize_weights."""
+        hid, inter, V = self.hidden_dim_, self.inter_dim_, self.vocab_size_
+        self.embedding = self._dev(_read_bin(os.path.join(path, "embedding.bin"), np.float32, V * hid,
+                                             "embedding").reshape(V, hid))
+        for i, L in enumerate(self.layers):
+            lp = os.path.join(path, f"layer_{i}")
+            ln1 = _read_bin(os.path.join(lp, "ln1.bin"), np.float32, 2 * hid, "ln1 gamma+beta")
+            ln2 = _read_bin(os.path.join(lp, "ln2.bin"), np.float32, 2 * hid, "ln2 gamma+beta")
+            L.ln1_g, L.ln1_b = self._dev(ln1[:hid]), self._dev(ln1[hid:])
+            L.ln2_g, L.ln2_b = self._dev(ln2[:hid]), self._dev(ln2[hid:])
+            packed = os.path.join(lp, "mlp.bin")
+            if os.path.isfile(packed):
+                m = _read_bin(packed, np.float32, hid * inter * 2 + inter + hid, "mlp")
+                o = 0
+                fc1 = m[o:o + hid * inter]; o += hid * inter
+                b1 = m[o:o + inter]; o += inter
+                fc2 = m[o:o + inter * hid]; o += inter * hid
+                b2 = m[o:o + hid]
+            elif os.path.isfile(os.path.join(lp, "mlp_fc1.bin")):
+                fc1 = _read_bin(os.path.join(lp, "mlp_fc1.bin"), np.float32, hid * inter, "mlp_fc1")
+                fc2 = _read_bin(os.path.join(lp, "mlp_fc2.bin"), np.float32, inter * hid, "mlp_fc2")
+                bb = _read_bin(os.path.join(lp, "mlp_biases.bin"), np.float32, inter + hid, "mlp_biases")
+                b1, b2 = bb[:inter], bb[inter:]
+            else:
+                raise RuntimeError("Cannot open MLP weights file")  # mlp.hpp:16
+            L.fc1_w, L.fc1_b = self._dev(fc1.reshape(hid, inter)), self._dev(b1)
+            L.fc2_w, L.fc2_b = self._dev(fc2.reshape(inter, hid)), self._dev(b2)
+        self._graph = None
+
+    def _embed(self):
+        self._chk(self._lib.pa_embedding_f32(self.embedding.data_ptr(), self.ids.data_ptr(), self._batch,
+                                             self.hidden_dim_, self.vocab_size_, self.x.data_ptr(), _cabi.stream()),
+                  "pa_embedding_f32")
+
+    def _mlp(self, L):
+        lib, B, hid, inter, s = self._lib, self._batch, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        self._chk(lib.pa_linear_f32(self.n.data_ptr(), L.fc1_w.data_ptr(), L.fc1_b.data_ptr(), B, hid, inter,
+                                    _cabi.ACT["relu"], self.h.data_ptr(), s), "pa_linear_f32")
+        self._chk(lib.pa_linear_f32(self.h.data_ptr(), L.fc2_w.data_ptr(), L.fc2_b.data_ptr(), B, inter, hid,
+                                    _cabi.ACT[""], self.x.data_ptr(), s), "pa_linear_f32")
+
+    def _logits(self):
+        self._chk(self._lib.pa_logits_f32(self.x.data_ptr(), self.embedding.data_ptr(), self._batch,
+                                          self.hidden_dim_, self.vocab_size_, self.logits.data_ptr(), _cabi.stream()),
+                  "pa_logits_f32")
+
+
+def quantize_file_reference(w):
+    """INT8Quantizer / quantize_weights arithmetic (int8_decoder.cpp:52-56): scale = max_element
+    (SIGNED max, not absmax), q = static_cast<int8_t>(w / scale * 127): truncation toward zero,
+    no clamp (out-of-range values wrap as an x86 float->int32->int8 conversion does)."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    scale = np.float32(w.max())
+    with np.errstate(all="ignore"):
+        v = (w / scale) * np.float32(127)
+        q = np.trunc(v)
+        q = np.where(np.isfinite(q), q, 0).astype(np.int64).astype(np.int32).astype(np.int8)
+    return q, float(scale)
+
+
+class INT8Decoder(_DecoderBase):
+    """py::class_<INT8Decoder>(m, "INT8Decoder") -- src/bindings.cpp:18-29;
+    decoder/int8_decoder.hpp:6-19, int8_decoder.cpp:34-119.  int8 weights, int8 KV pages."""
+    KV_DTYPE = "i8"
+    ARGMAX_DIVIDE = 0  # int8_decoder.cpp:100 logits * temperature
+    SCALES_FILE = "quant_scales.json"
+
+    def _alloc_default_weights(self):
+        hid, inter, dev = self.hidden_dim_, self.inter_dim_, self.device
+        zi = lambda *s: torch.zeros(s, dtype=torch.int8, device=dev)  # noqa: E731
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        self.embedding = zi(self.vocab_size_, hid)
+        self.emb_qscale = 127.0
+        for L in self.layers:
+            L.ln1_g, L.ln1_b = torch.ones(hid, device=dev), z(hid)
+            L.ln2_g, L.ln2_b = torch.ones(hid, device=dev), z(hid)
+            L.fc1_w, L.fc2_w = zi(hid, inter), zi(inter, hid)
+            L.fc1_deq = L.fc2_deq = 1.0 / 127.0
+            L.fc1_b, L.fc2_b = z(inter), z(hid)
+
+    def quantize_weights(self, path_fp32, path_int8):
+        """int8_decoder.cpp:43-89: embedding.bin and, per layer, ln1/ln2/mlp_fc1/mlp_fc2/mlp_biases .bin are
+        quantised file by file with the reference's arithmetic (quantize_file_reference) and written as raw
+        int8.  The reference drops the per-file scale, which makes the int8 files undecodable; it is kept
+        here in a sidecar <path_int8>/quant_scales.json (an addition, ignored by the reference)."""
+        os.makedirs(path_int8, exist_ok=True)
+        scales = {}
+
+        def one(rel):
+            src = os.path.join(path_fp32, rel)
+            if not os.path.isfile(src):
+                raise RuntimeError(f"Failed to open weight file: {src}")
+            q, sc = quantize_file_reference(np.fromfile(src, dtype=np.float32))
+            q.tofile(os.path.join(path_int8, rel))
+            scales[rel] = sc
+
+        one("embedding.bin")
+        for i in range(self.num_layers_):
+            os.makedirs(os.path.join(path_int8, f"layer_{i}"), exist_ok=True)
+            for fname in _LAYER_FILES:
+                one(f"layer_{i}/{fname}")
+        with open(os.path.join(path_int8, self.SCALES_FILE), "w") as f:
+            json.dump(scales, f, indent=1)
+        print(f"[INT8Decoder] Quantized weights saved to {path_int8}")  # int8_decoder.cpp:88
+
+    def load_quantized_weights(self, path_int8):
+        """int8_decoder.cpp:91-95.  Dequantisation multiplier of a file = scale/127 (w ~ q*scale/127);
+        scale comes from quant_scales.json, 1.0 when the sidecar is missing."""
+        hid, inter, V = self.hidden_dim_, self.inter_dim_, self.vocab_size_
+        scales = {}
+        sp = os.path.join(path_int8, self.SCALES_FILE)
+        if os.path.isfile(sp):
+            with open(sp) as f:
+                scales = json.load(f)
+        deq = lambda rel: float(scales.get(rel, 1.0)) / 127.0  # noqa: E731
+        emb = _read_bin(os.path.join(path_int8, "embedding.bin"), np.int8, V * hid, "embedding")
+        self.embedding = self._dev(emb.reshape(V, hid), torch.int8)
+        self.emb_qscale = 1.0 / deq("embedding.bin")
+        for i, L in enumerate(self.layers):
+            rel = lambda f: f"layer_{i}/{f}"  # noqa: E731
+            rd = lambda f, n: _read_bin(os.path.join(path_int8, rel(f)), np.int8, n, f).astype(np.float32)  # noqa: E731
+            ln1 = rd("ln1.bin", 2 * hid) * np.float32(deq(rel("ln1.bin")))
+            ln2 = rd("ln2.bin", 2 * hid) * np.float32(deq(rel("ln2.bin")))
+            L.ln1_g, L.ln1_b = self._dev(ln1[:hid]), self._dev(ln1[hid:])
+            L.ln2_g, L.ln2_b = self._dev(ln2[:hid]), self._dev(ln2[hid:])
+            L.fc1_w = self._dev(_read_bin(os.path.join(path_int8, rel("mlp_fc1.bin")), np.int8, hid * inter,
+                                          "mlp_fc1").reshape(hid, inter), torch.int8)
+            L.fc2_w = self._dev(_read_bin(os.path.join(path_int8, rel("mlp_fc2.bin")), np.int8, inter * hid,
+                                          "mlp_fc2").reshape(inter, hid), torch.int8)
+            L.fc1_deq, L.fc2_deq = deq(rel("mlp_fc1.bin")), deq(rel("mlp_fc2.bin"))
+            bb = rd("mlp_biases.bin", inter + hid) * np.float32(deq(rel("mlp_biases.bin")))
+            L.fc1_b, L.fc2_b = self._dev(bb[:inter]), self._dev(bb[inter:])
+        self._graph = None
+
+    def _embed(self):
+        self._chk(self._lib.pa_embedding_i8(self.embedding.data_ptr(), float(self.emb_qscale), self.ids.data_ptr(),
+                                            self._batch, self.hidden_dim_, self.vocab_size_, self.x.data_ptr(),
+                                            _cabi.stream()), "pa_embedding_i8")
+
+    def _quant_rows(self, x, q, scales, dim):
+        lib, B, s = self._lib, self._batch, _cabi.stream()
+        self._chk(lib.pa_batch_minmax_scale(x.data_ptr(), B, dim, scales.data_ptr(), s), "pa_batch_minmax_scale")
+        self._chk(lib.pa_batch_quantize_i8(x.data_ptr(), scales.data_ptr(), B, dim, q.data_ptr(), s),
+                  "pa_batch_quantize_i8")
+
+    def _mlp(self, L):
+        lib, B, hid, inter, s = self._lib, self._batch, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        self._quant_rows(self.n, self.xq, self.xs, hid)
+        self._chk(lib.pa_gemm_i8_dequant(self.xq.data_ptr(), L.fc1_w.data_ptr(), self.h.data_ptr(), 1, B, inter, hid,
+                                         self.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(),
+                                         _cabi.ACT["relu"], s), "pa_gemm_i8_dequant")
+        self._quant_rows(self.h, self.hq, self.hs, inter)
+        self._chk(lib.pa_gemm_i8_dequant(self.hq.data_ptr(), L.fc2_w.data_ptr(), self.x.data_ptr(), 1, B, hid, inter,
+                                         self.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], s),
+                  "pa_gemm_i8_dequant")
+
+    def _logits(self):
+        self._chk(self._lib.pa_logits_i8(self.x.data_ptr(), self.embedding.data_ptr(), float(self.emb_qscale),
+                                         self._batch, self.hidden_dim_, self.vocab_size_, self.logits.data_ptr(),
+                                         _cabi.stream()), "pa_logits_i8")

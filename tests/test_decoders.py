@@ -1,0 +1,269 @@
+"""Decoder surface: CUDADecoder / INT8Decoder constructor, weight files,
+generate() -- checked against the CPU restatement oracle/decoder_ref.py with teacher forcing
+(token-level equality is only asserted where the oracle's own top-2 margin exceeds the numeric
+noise), plus the small decoder kernels one by one."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+def _quantize_ref_numpy():
+    from llm_decoder.decoders import quantize_file_reference
+    return quantize_file_reference
+
+
+# ------------------------------------------------------------------ CPU: file-format arithmetic
+def test_quantize_weights_arithmetic_matches_restatement(oracle):
+    """int8_decoder.cpp:52-56: signed-max scale, truncation toward zero, no clamp (wraps)."""
+    q = _quantize_ref_numpy()
+    rng = np.random.default_rng(7)
+    for w in (np.array([0.5, -1.0, 0.25, -0.26, 0.499], np.float32),
+              rng.standard_normal(4097).astype(np.float32),
+              (rng.standard_normal(1000) * 1e-3).astype(np.float32)):
+        got, sc = q(w)
+        exp, esc = oracle.cpu.quantize_weights_file(w)
+        assert sc == esc == float(w.max())
+        np.testing.assert_array_equal(got, exp)
+    got, _ = q(np.array([0.5, -1.0], np.float32))
+    np.testing.assert_array_equal(got, np.array([127, 2], np.int8))  # -254 wraps: no clamp in the reference
+
+
+# ------------------------------------------------------------------ helpers
+def make_weights(rng, L, hid, V, scale=1.0):
+    inter = 4 * hid
+    w = {"embedding": (rng.standard_normal((V, hid)) * scale).astype(np.float32), "layers": []}
+    for _ in range(L):
+        w["layers"].append(dict(
+            ln1_g=(1 + 0.1 * rng.standard_normal(hid)).astype(np.float32),
+            ln1_b=(0.1 * rng.standard_normal(hid)).astype(np.float32),
+            ln2_g=(1 + 0.1 * rng.standard_normal(hid)).astype(np.float32),
+            ln2_b=(0.1 * rng.standard_normal(hid)).astype(np.float32),
+            fc1_w=(rng.standard_normal((hid, inter)) / np.sqrt(hid)).astype(np.float32),
+            fc1_b=(0.1 * rng.standard_normal(inter)).astype(np.float32),
+            fc2_w=(rng.standard_normal((inter, hid)) / np.sqrt(inter)).astype(np.float32),
+            fc2_b=(0.1 * rng.standard_normal(hid)).astype(np.float32)))
+    return w
+
+
+def write_fp32_tree(w, path, packed_mlp):
+    os.makedirs(path, exist_ok=True)
+    w["embedding"].tofile(os.path.join(path, "embedding.bin"))
+    for i, L in enumerate(w["layers"]):
+        lp = os.path.join(path, f"layer_{i}")
+        os.makedirs(lp, exist_ok=True)
+        np.concatenate([L["ln1_g"], L["ln1_b"]]).tofile(os.path.join(lp, "ln1.bin"))
+        np.concatenate([L["ln2_g"], L["ln2_b"]]).tofile(os.path.join(lp, "ln2.bin"))
+        if packed_mlp:   # the order MLP::load_weights reads (mlp.hpp:17-20)
+            np.concatenate([L["fc1_w"].ravel(), L["fc1_b"], L["fc2_w"].ravel(), L["fc2_b"]]).tofile(
+                os.path.join(lp, "mlp.bin"))
+        else:            # weights/README.md:31-39 / int8_decoder.cpp:66-70
+            L["fc1_w"].tofile(os.path.join(lp, "mlp_fc1.bin"))
+            L["fc2_w"].tofile(os.path.join(lp, "mlp_fc2.bin"))
+            np.concatenate([L["fc1_b"], L["fc2_b"]]).tofile(os.path.join(lp, "mlp_biases.bin"))
+
+
+def check_teacher_forced(seq, n_prompt, ref, temperature, divide, dec_logits_last, tol):
+    """Feed `seq` to the CPU oracle; every generated token must be the oracle's argmax, or within
+    `tol` of the oracle's maximum (numeric near-tie)."""
+    from oracle.decoder_ref import sample
+    logits = None
+    for t, tok in enumerate(seq[:-1]):
+        logits = ref.step(tok)
+        if t + 1 >= n_prompt:
+            v = logits / np.float32(temperature) if divide else logits * np.float32(temperature)
+            got = seq[t + 1]
+            if got != sample(logits, temperature, divide):
+                assert v.max() - v[got] <= tol * max(1.0, np.abs(v).max()), (t, got, int(np.argmax(v)))
+    return logits
+
+
+# ------------------------------------------------------------------ GPU: kernels one by one
+@pytest.mark.gpu
+def test_decoder_kernels_match_oracle(oracle):
+    import llm_decoder as ld
+    from llm_decoder import _cabi
+    lib, s = _cabi.lib(), None
+    rng = np.random.default_rng(11)
+    rows, hid, V = 5, 192, 301
+    x = rng.standard_normal((rows, hid)).astype(np.float32) * 3 + 0.5
+    g, b = rng.standard_normal(hid).astype(np.float32), rng.standard_normal(hid).astype(np.float32)
+    dx, dg, db = (torch.from_numpy(a).cuda() for a in (x, g, b))
+    out = torch.empty_like(dx)
+    _cabi.check(lib.pa_layer_norm_f32(dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, hid, 1e-5, out.data_ptr(), s))
+    np.testing.assert_allclose(out.cpu().numpy(), oracle.cpu.layer_norm(x, g, b), rtol=2e-5, atol=2e-5)
+    # linear (mlp.hpp:23-41), rows > 8 exercises the row-chunk loop, N not a multiple of 32
+    rows2, K, N = 11, 192, 100
+    x2 = rng.standard_normal((rows2, K)).astype(np.float32)
+    W = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    dx2, dW, dbias = (torch.from_numpy(a).cuda() for a in (x2, W, bias))
+    for act in (0, 1):
+        o = torch.empty((rows2, N), device="cuda")
+        _cabi.check(lib.pa_linear_f32(dx2.data_ptr(), dW.data_ptr(), dbias.data_ptr(), rows2, K, N, act, o.data_ptr(), s))
+        exp = x2.astype(np.float64) @ W.astype(np.float64) + bias
+        if act:
+            exp = np.maximum(exp, 0)
+        np.testing.assert_allclose(o.cpu().numpy(), exp, rtol=1e-4, atol=1e-4)
+    # embedding f32 / i8 (+ out-of-range id -> zeros)
+    E = rng.standard_normal((V, hid)).astype(np.float32)
+    ids = np.array([0, 5, V - 1, V, -1], np.int32)
+    dE, dids = torch.from_numpy(E).cuda(), torch.from_numpy(ids).cuda()
+    o = torch.empty((5, hid), device="cuda")
+    _cabi.check(lib.pa_embedding_f32(dE.data_ptr(), dids.data_ptr(), 5, hid, V, o.data_ptr(), s))
+    exp = np.zeros((5, hid), np.float32)
+    exp[:3] = E[ids[:3]]
+    np.testing.assert_array_equal(o.cpu().numpy(), exp)
+    Eq = rng.integers(-127, 128, (V, hid), dtype=np.int8)
+    dEq = torch.from_numpy(Eq).cuda()
+    _cabi.check(lib.pa_embedding_i8(dEq.data_ptr(), 42.5, dids.data_ptr(), 5, hid, V, o.data_ptr(), s))
+    exp[:3] = oracle.cpu.dequantize_from_int8(Eq[ids[:3]].reshape(-1), 42.5).reshape(3, hid)
+    np.testing.assert_array_equal(o.cpu().numpy(), exp)
+    # logits + argmax (first maximum; divide / multiply forms)
+    lg = torch.empty((rows, V), device="cuda")
+    _cabi.check(lib.pa_logits_f32(dx.data_ptr(), dE.data_ptr(), rows, hid, V, lg.data_ptr(), s))
+    np.testing.assert_allclose(lg.cpu().numpy(), x.astype(np.float64) @ E.T.astype(np.float64), rtol=1e-4, atol=1e-3)
+    _cabi.check(lib.pa_logits_i8(dx.data_ptr(), dEq.data_ptr(), 42.5, rows, hid, V, lg.data_ptr(), s))
+    np.testing.assert_allclose(lg.cpu().numpy(), (x.astype(np.float64) @ Eq.T.astype(np.float64)) / 42.5, rtol=1e-4, atol=1e-3)
+    l2 = rng.standard_normal((rows, V)).astype(np.float32)
+    l2[0, 7] = l2[0, 200] = 9.0     # tie -> first index
+    l2[1, :] = -np.inf
+    dl2 = torch.from_numpy(l2).cuda()
+    am = torch.empty(rows, dtype=torch.int32, device="cuda")
+    for t, divide in ((0.7, 1), (2.0, 0), (-1.0, 0)):
+        _cabi.check(lib.pa_argmax_f32(dl2.data_ptr(), rows, V, t, divide, am.data_ptr(), s))
+        v = l2 / np.float32(t) if divide else l2 * np.float32(t)
+        np.testing.assert_array_equal(am.cpu().numpy(), np.argmax(v, axis=1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 3, 64, 256), (2, 70, 144, 272), (1, 16, 128, 8192)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_gemm_i8_dequant_matches_oracle(oracle, shape):
+    """pa_gemm_i8_dequant: per-row dynamic scales, f32 output (direct and split-K epilogues)."""
+    from llm_decoder import _cabi
+    BATCH, M, N, K = shape
+    rng = np.random.default_rng(sum(shape))
+    A = rng.integers(-127, 128, (BATCH, M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, (BATCH, K, N), dtype=np.int8)
+    bias = rng.standard_normal(N).astype(np.float32)
+    qs = rng.uniform(5, 60, BATCH * M).astype(np.float32)
+    acc = oracle.cpu.gemm_s8s8s32(A, B).astype(np.float32)
+    dA, dB, dbias, dqs = (torch.from_numpy(a).cuda() for a in (A, B, bias, qs))
+    for act in ("", "relu", "gelu"):
+        C = torch.full((BATCH, M, N), float("nan"), device="cuda")
+        _cabi.check(_cabi.lib().pa_gemm_i8_dequant(dA.data_ptr(), dB.data_ptr(), C.data_ptr(), BATCH, M, N, K,
+                                                   dqs.data_ptr(), 0.013, dbias.data_ptr(), _cabi.ACT[act], None))
+        alpha = (np.float32(0.013) / qs).reshape(BATCH, M, 1)
+        exp = (alpha * acc).astype(np.float32) + bias
+        if act == "relu":
+            exp = np.maximum(exp, 0)
+            np.testing.assert_array_equal(C.cpu().numpy(), exp)   # same fp32 op order: bit-exact
+        elif act == "gelu":
+            from math import erf
+            exp = 0.5 * exp * (1 + np.vectorize(erf)(exp.astype(np.float64) * 0.7071067811865476))
+            np.testing.assert_allclose(C.cpu().numpy(), exp, rtol=1e-5, atol=1e-5)
+        else:
+            np.testing.assert_array_equal(C.cpu().numpy(), exp)
+
+
+# ------------------------------------------------------------------ GPU: CUDADecoder
+@pytest.mark.gpu
+@pytest.mark.parametrize("packed_mlp", [True, False])
+def test_cuda_decoder_generate_vs_oracle(oracle, tmp_path, packed_mlp):
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(31)
+    L, H, D, V, S = 2, 2, 64, 211, 48
+    hid = H * D
+    w = make_weights(rng, L, hid, V)
+    write_fp32_tree(w, str(tmp_path / "w"), packed_mlp)
+    dec = ld.CUDADecoder(L, H, D, hid, V, S)            # bindings.cpp:5-6: six ints
+    dec.load_weights(str(tmp_path / "w"))
+    prompt = [3, 17, 101, 5]
+    out = dec.generate(prompt, 12, 0.8)                  # bindings.cpp:8-15
+    assert out[:4] == prompt and len(out) == 16 and all(0 <= t < V for t in out)
+    ref = RefDecoder(w, H, D)
+    check_teacher_forced(out, len(prompt), ref, 0.8, 1, None, 1e-4)
+    # CUDA-graph replay == eager
+    dec2 = ld.CUDADecoder(L, H, D, hid, V, S, use_cuda_graph=False, use_overlap=False)
+    dec2.load_weights(str(tmp_path / "w"))
+    assert dec2.generate(prompt, 12, 0.8) == out
+    # tolerated caller variants (api/router.py:23, cli/chat_cli.py:24)
+    lst = []
+    assert dec.generate(prompt, lst, 5, 1.0) is lst and lst[:4] == prompt and len(lst) == 9
+    assert dec.generate(prompt, max_gen_len=3) == out[:7] or len(dec.generate(prompt, max_gen_len=3)) == 7
+    # logits of one eager step against the oracle
+    dec.reset()
+    ref2 = RefDecoder(w, H, D)
+    for tok in prompt:
+        lg = dec.forward_tokens([tok]).cpu().numpy()[0]
+        np.testing.assert_allclose(lg, ref2.step(tok), rtol=2e-3, atol=2e-3)
+    # batch of independent sequences == one at a time
+    outs = dec.generate_batch([prompt, [9, 8, 7, 6]], 6, 0.8)
+    assert outs[0] == out[:10]
+    assert outs[1] == dec.generate([9, 8, 7, 6], 6, 0.8)
+
+
+@pytest.mark.gpu
+def test_decoder_errors():
+    import llm_decoder as ld
+    with pytest.raises(ValueError):
+        ld.CUDADecoder(1, 2, 64, 100, 50, 32)            # hidden != H*D
+    dec = ld.CUDADecoder(1, 2, 64, 128, 50, 32)
+    with pytest.raises(RuntimeError):
+        dec.load_weights("/nonexistent/path")            # "Cannot open file" -> RuntimeError via pybind
+    with pytest.raises(ValueError):
+        dec.generate([1] * 30, 10, 1.0)
+    # zero-initialised weights (std::vector<T>(n)): every logit 0 -> argmax = token 0
+    assert dec.generate([4, 5], 3, 1.0) == [4, 5, 0, 0, 0]
+
+
+# ------------------------------------------------------------------ GPU: INT8Decoder
+@pytest.mark.gpu
+def test_int8_decoder_quantize_load_generate(oracle, tmp_path):
+    import json
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(32)
+    L, H, D, V, S = 2, 2, 64, 203, 40
+    hid, inter = H * D, 4 * H * D
+    w = make_weights(rng, L, hid, V)
+    fp32, int8 = str(tmp_path / "fp32"), str(tmp_path / "int8")
+    write_fp32_tree(w, fp32, packed_mlp=False)
+    dec = ld.INT8Decoder(L, H, D, hid, V, S)             # bindings.cpp:18-19
+    dec.quantize_weights(fp32, int8)                     # bindings.cpp:21
+    # files are byte-identical to the reference's arithmetic (restated in the oracle)
+    for rel in ["embedding.bin"] + [f"layer_{i}/{f}" for i in range(L)
+                                    for f in ("ln1.bin", "ln2.bin", "mlp_fc1.bin", "mlp_fc2.bin", "mlp_biases.bin")]:
+        exp, _ = oracle.cpu.quantize_weights_file(np.fromfile(os.path.join(fp32, rel), np.float32))
+        assert np.fromfile(os.path.join(int8, rel), np.int8).tobytes() == exp.tobytes(), rel
+    dec.load_quantized_weights(int8)                     # bindings.cpp:20
+    out = dec.generate([1, 2, 3], 10, 1.0)
+    assert len(out) == 13 and out[:3] == [1, 2, 3]
+    # oracle weights = what the decoder loaded (int8 payload + per-file scale)
+    scales = json.load(open(os.path.join(int8, "quant_scales.json")))
+    deq = lambda rel: np.float32(scales[rel] / 127.0)   # noqa: E731
+    rd = lambda rel: np.fromfile(os.path.join(int8, rel), np.int8)  # noqa: E731
+    wq = {"embedding": rd("embedding.bin").reshape(V, hid), "emb_qscale": 1.0 / (scales["embedding.bin"] / 127.0),
+          "layers": []}
+    for i in range(L):
+        r = lambda f: f"layer_{i}/{f}"  # noqa: E731
+        ln1 = rd(r("ln1.bin")).astype(np.float32) * deq(r("ln1.bin"))
+        ln2 = rd(r("ln2.bin")).astype(np.float32) * deq(r("ln2.bin"))
+        bb = rd(r("mlp_biases.bin")).astype(np.float32) * deq(r("mlp_biases.bin"))
+        wq["layers"].append(dict(ln1_g=ln1[:hid], ln1_b=ln1[hid:], ln2_g=ln2[:hid], ln2_b=ln2[hid:],
+                                 fc1_w=rd(r("mlp_fc1.bin")).reshape(hid, inter), fc1_deq=float(deq(r("mlp_fc1.bin"))),
+                                 fc2_w=rd(r("mlp_fc2.bin")).reshape(inter, hid), fc2_deq=float(deq(r("mlp_fc2.bin"))),
+                                 fc1_b=bb[:inter], fc2_b=bb[inter:]))
+    ref = RefDecoder(wq, H, D, int8=True)
+    check_teacher_forced(out, 3, ref, 1.0, 0, None, 2e-3)
+    dec.reset()
+    ref2 = RefDecoder(wq, H, D, int8=True)
+    for tok in out[:6]:
+        lg = dec.forward_tokens([tok]).cpu().numpy()[0]
+        exp = ref2.step(tok)
+        np.testing.assert_allclose(lg, exp, rtol=5e-3, atol=5e-3 * np.abs(exp).max())
+    with pytest.raises(RuntimeError):
+        dec.load_quantized_weights(str(tmp_path / "missing"))
