@@ -249,6 +249,42 @@ int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature,
 /* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
 int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
 
+/* --------------------------------- inter-GPU split-KV exchange over peer memory */
+/* North-star long-context mode (the reference has no multi-device code).
+ * pa_p2p_alloc: cudaMalloc'd, zero-filled exchange buffer + its 64-byte CUDA IPC handle;
+ * pa_p2p_open: map a peer process's buffer (NVLink P2P); pa_p2p_close / pa_p2p_free. */
+size_t pa_splitkv_exchange_bytes(int world, int rows, int head_dim);
+int pa_p2p_alloc(size_t bytes, void** d_ptr, unsigned char* handle64);
+int pa_p2p_open(const unsigned char* handle64, void** d_peer_ptr);
+int pa_p2p_close(void* d_peer_ptr);
+int pa_p2p_free(void* d_ptr);
+/* ONE kernel = exchange + combine: stores this rank's partial rows (as produced by
+ * pa_paged_decode_f16_partial) into slot `rank` of every peer's exchange buffer
+ * (d_peer_bufs: DEVICE array of `world` buffer base pointers, own buffer at [rank]),
+ * publishes them with release.sys flags, waits for all ranks' rows and LSE-combines
+ * them (same math as pa_lse_combine).  d_epochs: [rows] uint32 step counters in device
+ * memory, zero-initialised once and advanced by the kernel itself (all ranks must call
+ * in lock step; keeping the counter on the device makes the launch CUDA-graph
+ * replayable).  *d_status (optional) is set to 1 if a peer did not arrive
+ * within ~2 s (outputs are then undefined; the kernel never hangs the GPU). */
+/* Decode + exchange in TWO launches: pa_paged_decode_f16_overlap's streaming kernel over this
+ * rank's pages, then the chunk-merge kernel whose epilogue performs the exchange above for
+ * each (row, head) directly from registers (no partial round trip through HBM, no separate
+ * collective).  d_out [B,H,D] holds the attention over ALL ranks' pages on every rank.  The
+ * exchange buffers must have been sized for rows = B*num_heads. */
+int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_pool,
+                                const void* d_v_pool, const int32_t* d_table, int num_beams,
+                                int num_heads, int num_tiles, int total_pages,
+                                const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B, int T,
+                                int head_dim, int tile_size, float temperature, const float* d_rope,
+                                float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                                void* const* d_peer_bufs, int rank, int world, uint32_t* d_epochs,
+                                int* d_status, pa_stream_t stream);
+int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                                void* const* d_peer_bufs, int rank, int world, int rows,
+                                int head_dim, uint32_t* d_epochs, float* d_out, float* d_lse_out,
+                                int* d_status, pa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

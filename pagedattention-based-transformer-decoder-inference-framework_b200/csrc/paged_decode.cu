@@ -53,6 +53,11 @@ struct DecodeArgs {
     int num_splits;   // direct kernel
     int evict_first;  // overlap kernel L2 hint
     float qscale;     // log2(e) / temperature
+    // fused inter-GPU exchange (split-KV of one sequence across ranks; p2p_combine.cu layout)
+    uint8_t* const* xch_peers;  // device array [xch_world] of exchange-buffer base pointers; null = off
+    uint32_t* xch_epochs;       // [rows] step counters
+    int* xch_status;
+    int xch_rank, xch_world;
 };
 
 template <int D, int KV>
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
         warp_merge<D, KV>(acc);
         if (lane < 8) {
-            const bool final_row = (nc == 1);
+            const bool final_row = (nc == 1) && !a.xch_peers;
             if (final_row && !a.part_m) {
                 const float inv = 1.f / (acc.l + 1e-6f);
 #pragma unroll
@@ -599,11 +604,36 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
     }
 }
 
-// Merge the per-chunk partials of every row with more than one chunk; rows with no keys are
-// zeroed.  D threads per row.
+// Exchange-buffer layout shared with p2p_combine.cu.
+__device__ __forceinline__ size_t xbuf_data_floats_dev(int world, int64_t rows, int D) {
+    return (size_t)2 * world * rows * (D + 2);
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_volatile_f32g(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Merge the per-chunk partials of every row (rows of a single chunk were finished by the main
+// kernel unless the exchange is on; rows with no keys are zeroed).  A CTA of 8 warps handles
+// 8 / WPR rows: WPR warps share a row's chunks (strided), each lane owns D/32 output dims, chunk
+// weights are computed by lanes in parallel and broadcast with shuffles, so a row of 256 chunks
+// (C5: 16K tokens per GPU) costs ~32 dependent 512-byte loads per warp instead of 512 serial
+// scalar loads per thread.  With xch_peers set, the warp that owns the merged row also performs the
+// inter-GPU exchange (store to peers, release flag, acquire all ranks' flags, LSE combine).
 template <int D>
-__global__ void combine_chunks_kernel(const DecodeArgs a, int cu) {
+__global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a, int cu, int wpr) {
+    constexpr int VEC = D / 32;
     extern __shared__ int prefix_sm[];
+    __shared__ float red[8][D + 2];
     ChunkMap cm;
     cm.B = a.B;
     cm.H = a.H;
@@ -619,30 +649,160 @@ __global__ void combine_chunks_kernel(const DecodeArgs a, int cu) {
         __syncthreads();
         cm.prefix = prefix_sm;
     }
-    const int d = threadIdx.x % D;
-    const int rows_per_cta = blockDim.x / D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rpc = 8 / wpr;
+    const int wsub = warp % wpr;
     const int64_t nrows = (int64_t)a.B * a.H;
-    for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x / D; row < nrows;
-         row += (int64_t)gridDim.x * rows_per_cta) {
+    const int64_t row = (int64_t)blockIdx.x * rpc + warp / wpr;
+    const bool row_ok = row < nrows;
+    int nc = 0;
+    int64_t s0 = 0;
+    if (row_ok) {
         const int b = (int)(row / a.H), h = (int)(row % a.H);
-        const int nc = cm.nchunks_of(b);
-        if (nc == 1) continue;  // written by the main kernel
-        if (nc == 0) {
-            emit_row(a, kEmitFinal, row, 0, D, d, -INFINITY, 0.f, 0.f);
-            continue;
-        }
-        const int64_t s0 = cm.row_start(b, h);
-        float M = -INFINITY;
-        for (int j = 0; j < nc; ++j) M = fmaxf(M, a.ws_m[s0 + j]);
-        float L = 0.f, O = 0.f;
-        for (int j = 0; j < nc; ++j) {
-            const float ms = a.ws_m[s0 + j];
-            const float wt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
-            L = fmaf(a.ws_l[s0 + j], wt, L);
-            O = fmaf(a.ws_o[(s0 + j) * D + d], wt, O);
-        }
-        emit_row(a, kEmitFinal, row, 0, D, d, M, L, O);
+        nc = cm.nchunks_of(b);
+        s0 = cm.row_start(b, h);
     }
+    const bool skip = !row_ok || (nc == 1 && !a.xch_peers);  // nc == 1: written by the main kernel
+    // chunks of this warp: j = wsub + wpr * i, i < n_mine
+    const int n_mine = (skip || nc <= wsub) ? 0 : (nc - wsub + wpr - 1) / wpr;
+    float mloc = -INFINITY;
+    for (int i = lane; i < n_mine; i += 32) mloc = fmaxf(mloc, a.ws_m[s0 + wsub + (int64_t)wpr * i]);
+    const float Mw = warp_max(mloc);
+    float Lw = 0.f;
+    float O[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) O[e] = 0.f;
+    for (int base = 0; base < n_mine; base += 32) {
+        const int i = base + lane;
+        float wt = 0.f;
+        if (i < n_mine) {
+            const int64_t j = s0 + wsub + (int64_t)wpr * i;
+            const float mj = a.ws_m[j];
+            wt = (mj == -INFINITY) ? 0.f : fast_exp2(mj - Mw);
+            Lw = fmaf(a.ws_l[j], wt, Lw);
+        }
+        const int cnt = min(32, n_mine - base);
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const float w = __shfl_sync(0xffffffffu, wt, t);
+            const int64_t j = s0 + wsub + (int64_t)wpr * (base + t);
+            const float* src = a.ws_o + j * D + lane * VEC;
+            if (VEC == 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src));
+                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
+                O[2 % VEC] = fmaf(v.z, w, O[2 % VEC]); O[3 % VEC] = fmaf(v.w, w, O[3 % VEC]);
+            } else {
+                const float2 v = __ldcs(reinterpret_cast<const float2*>(src));
+                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
+            }
+        }
+    }
+    Lw = warp_sum(Lw);
+    float M = Mw, L = Lw;
+    if (wpr > 1) {  // cross-warp merge (uniform branch: wpr is a kernel argument)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) red[warp][lane * VEC + e] = O[e];
+        if (lane == 0) {
+            red[warp][D] = Mw;
+            red[warp][D + 1] = Lw;
+        }
+        __syncthreads();
+        if (wsub == 0) {
+            const int w0 = warp;
+            M = -INFINITY;
+            for (int w = 0; w < wpr; ++w) M = fmaxf(M, red[w0 + w][D]);
+            L = 0.f;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) O[e] = 0.f;
+            for (int w = 0; w < wpr; ++w) {
+                const float mw = red[w0 + w][D];
+                const float wt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - M);
+                L = fmaf(red[w0 + w][D + 1], wt, L);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) O[e] = fmaf(red[w0 + w][lane * VEC + e], wt, O[e]);
+            }
+        }
+    }
+    if (skip || wsub != 0) return;
+    // ---- emit: this warp holds the merged row (M log2-domain, L, O[VEC] for dims lane*VEC..) ----
+    if (a.xch_peers) {
+        const int world = a.xch_world, rank = a.xch_rank;
+        const uint32_t epoch = a.xch_epochs[row] + 1u;
+        const int par = epoch & 1u;
+        const size_t stride = D + 2;
+        const size_t data_bytes = xbuf_data_floats_dev(world, nrows, D) * sizeof(float);
+        const size_t slot = ((size_t)(par * world + rank) * nrows + row) * stride;
+        const float m_nat = M * kLn2;
+        for (int p = 0; p < world; ++p) {
+            float* dst = reinterpret_cast<float*>(a.xch_peers[p]) + slot;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) dst[lane * VEC + e] = O[e];
+            if (lane == 0) {
+                dst[D] = m_nat;
+                dst[D + 1] = L;
+            }
+        }
+        __threadfence_system();
+        __syncwarp();
+        float ms = -INFINITY, ls = 0.f;
+        for (int s = lane; s < world; s += 32) {  // world <= 32 in practice; loop keeps it general
+            st_release_sys_u32(reinterpret_cast<uint32_t*>(a.xch_peers[s] + data_bytes) +
+                                   (size_t)(par * world + rank) * nrows + row, epoch);
+        }
+        uint8_t* mine = a.xch_peers[rank];
+        bool ok = true;
+        if (lane < world) {
+            const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + data_bytes) +
+                                (size_t)(par * world + lane) * nrows + row;
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u32(f) != epoch) {
+                if (clock64() - t0 > 4000000000ll) {  // ~2 s: never hang the GPU on a missing peer
+                    ok = false;
+                    break;
+                }
+            }
+            if (!ok && a.xch_status) atomicExch(a.xch_status, 1);
+            const float* src = reinterpret_cast<const float*>(mine) +
+                               ((size_t)(par * world + lane) * nrows + row) * stride;
+            ms = ok ? ld_volatile_f32g(src + D) : -INFINITY;
+            ls = ok ? ld_volatile_f32g(src + D + 1) : 0.f;
+        }
+        __syncwarp();
+        const float Mg = warp_max(ms);
+        const float wl = (ms == -INFINITY) ? 0.f : __expf(ms - Mg);
+        const float Lg = warp_sum(ls * wl);
+        float Og[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) Og[e] = 0.f;
+        for (int sidx = 0; sidx < world; ++sidx) {
+            const float w = __shfl_sync(0xffffffffu, wl, sidx);
+            const float* src = reinterpret_cast<const float*>(mine) +
+                               ((size_t)(par * world + sidx) * nrows + row) * stride;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) Og[e] = fmaf(ld_volatile_f32g(src + lane * VEC + e), w, Og[e]);
+        }
+        const float inv = 1.f / (Lg + 1e-6f);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = Og[e] * inv;
+        if (lane == 0) {
+            if (a.lse_out) a.lse_out[row] = (Lg > 0.f) ? Mg + logf(Lg) : -INFINITY;
+            a.xch_epochs[row] = epoch;
+        }
+        return;
+    }
+    if (a.part_m) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
+        if (lane == 0) {
+            a.part_m[row] = M * kLn2;
+            a.part_l[row] = L;
+        }
+        return;
+    }
+    const float inv = 1.f / (L + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = O[e] * inv;
+    if (lane == 0 && a.lse_out) a.lse_out[row] = (L > 0.f) ? (M + log2f(L)) * kLn2 : -INFINITY;
 }
 
 // Public LSE combine (natural-log m), n_parts x rows layout.
@@ -707,7 +867,7 @@ static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
     const int cu = choose_cu(rows, max_units, sm_count);
     const size_t ov = (size_t)rows * ((max_units + cu - 1) / cu);
     const size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
-    return (ov > dr ? ov : dr) + 64;
+    return (((ov > dr ? ov : dr) + 64) + 3) & ~(size_t)3;  // multiple of 4: ws_o stays 16-byte aligned
 }
 
 static size_t ws_bytes_needed(int B, int H, int D, int num_tiles, int tile_size, int sm_count) {
@@ -761,16 +921,24 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     if (e != cudaSuccess) return (int)e;
     // Rows of a single chunk were finished by the main kernel; everything else is merged here.
     const int nc_uniform = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
-    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1;
+    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1 || a.xch_peers != nullptr;
     if (need_combine) {
-        const int rows_per_cta = 256 / D;
-        int cgrid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-        if (cgrid > G * 8) cgrid = G * 8;
-        combine_chunks_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, cu);
+        const int nc_max = (max_units + cu - 1) / cu;
+        const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
+        const int rpc = 8 / wpr;
+        const int cgrid = (int)((rows + rpc - 1) / rpc);
+        combine_chunks_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, cu, wpr);
         e = cudaGetLastError();
     }
     return e == cudaSuccess ? PA_OK : (int)e;
 }
+
+struct XchgParams {
+    void* const* peers;
+    uint32_t* epochs;
+    int* status;
+    int rank, world;
+};
 
 static int decode_entry(int kv, bool overlap, const float* q, float* out, float* part_m,
                         float* part_l, float* part_o, const void* k_pool, const void* v_pool,
@@ -778,7 +946,7 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
                         int num_beams, int H, int num_tiles, int total_pages,
                         const int32_t* beam_ids, const int32_t* ctx_lens, int B, int T, int D,
                         int tile_size, float temperature, const float* rope, float* lse_out,
-                        void* ws, size_t ws_bytes, pa_stream_t stream) {
+                        void* ws, size_t ws_bytes, pa_stream_t stream, const XchgParams* xch = nullptr) {
     PA_CHECK_ARG(q && k_pool && v_pool && table);
     PA_CHECK_ARG(part_m ? (part_l && part_o) : (out != nullptr));
     PA_CHECK_ARG(num_beams > 0 && H > 0 && num_tiles > 0 && total_pages > 0 && B >= 0 && T >= 0);
@@ -799,6 +967,15 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
     a.num_splits = 1;
     a.evict_first = beam_ids ? 0 : 1;  // shared-prefix pages are re-read by sibling beams: keep them in L2
     a.qscale = kLog2e / temperature;
+    if (xch) {
+        PA_CHECK_ARG(overlap && xch->peers && xch->epochs && xch->world > 0 && xch->world <= 32 &&
+                     xch->rank >= 0 && xch->rank < xch->world && !part_m);
+        a.xch_peers = reinterpret_cast<uint8_t* const*>(xch->peers);
+        a.xch_epochs = xch->epochs;
+        a.xch_status = xch->status;
+        a.xch_rank = xch->rank;
+        a.xch_world = xch->world;
+    }
     cudaStream_t st = as_stream(stream);
     if (kv == 0) {
         return D == 128 ? launch_decode<128, 0>(a, overlap, ws, ws_bytes, st)
@@ -865,6 +1042,16 @@ PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float*
     return decode_entry(0, true, d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
                         nullptr, nullptr, PA_DECODE_COMMON_ARGS, nullptr, d_workspace,
                         workspace_bytes, stream);
+}
+
+PA_API int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_pool,
+                                       const void* d_v_pool, PA_DECODE_COMMON_PARAMS, float* d_lse_out,
+                                       void* d_workspace, size_t workspace_bytes, void* const* d_peer_bufs,
+                                       int rank, int world, uint32_t* d_epochs, int* d_status,
+                                       pa_stream_t stream) {
+    XchgParams x{d_peer_bufs, d_epochs, d_status, rank, world};
+    return decode_entry(0, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
+                        nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream, &x);
 }
 
 PA_API int pa_lse_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,

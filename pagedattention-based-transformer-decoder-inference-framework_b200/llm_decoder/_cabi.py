@@ -36,6 +36,7 @@ _SIGS = {
     "pa_paged_decode_i8": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_i8_overlap": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_partial": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
+    "pa_paged_decode_f16_splitkv": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_lse_combine": ([_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_quantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
     "pa_batch_quantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -54,6 +55,12 @@ _SIGS = {
     "pa_logits_i8": ([_vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),
     "pa_advance_positions": ([_vp, _vp, _i32, _vp], _i32),
+    "pa_splitkv_exchange_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_p2p_alloc": ([_sz, C.POINTER(_vp), C.c_char_p], _i32),
+    "pa_p2p_open": ([C.c_char_p, C.POINTER(_vp)], _i32),
+    "pa_p2p_close": ([_vp], _i32),
+    "pa_p2p_free": ([_vp], _i32),
+    "pa_splitkv_exchange_combine": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
 }
 
 EXPORTS = tuple(_SIGS)

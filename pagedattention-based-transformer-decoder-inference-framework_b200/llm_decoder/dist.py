@@ -53,9 +53,10 @@ def unpack_partials(gathered):
 def gather_partials(msg, group=None):
     """all_gather of every rank's packed partials -> [world, rows, D+2]."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(msg.shape), dtype=msg.dtype, device=msg.device)
-    dist.all_gather_into_tensor(out, msg.contiguous(), group=group)
-    return out
+    msg = msg.contiguous()
+    out = torch.empty((world * msg.shape[0],) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device)
+    dist.all_gather_into_tensor(out, msg, group=group)  # concatenation along dim 0 (gloo and nccl)
+    return out.view((world,) + tuple(msg.shape))
 
 
 def combine_gathered(gathered, combine_fn=None):
@@ -69,12 +70,106 @@ def combine_gathered(gathered, combine_fn=None):
     return _att.lse_combine(pm, pl, po)
 
 
-def split_kv_decode(q, kv_cache, B, T_local, temperature=1.0, beam_ids=None, ctx_lens=None, group=None):
+class PeerExchange:
+    """Exchange buffers of all ranks mapped into this process over CUDA IPC (NVLink P2P), for the
+    fused exchange+combine kernel pa_splitkv_exchange_combine.  One instance per (rows, D) shape."""
+
+    def __init__(self, rows, head_dim, group=None, device=None):
+        import ctypes as C
+
+        from . import _cabi
+        self._cabi, self._C = _cabi, C
+        self.rows, self.D, self.group = rows, head_dim, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _cabi.lib()
+        nbytes = lib.pa_splitkv_exchange_bytes(self.world, rows, head_dim)
+        with torch.cuda.device(self.device):
+            self._own = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            _cabi.check(lib.pa_p2p_alloc(nbytes, C.byref(self._own), handle), "pa_p2p_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._peers, ptrs = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(self._own.value)
+                    continue
+                p = C.c_void_p()
+                _cabi.check(lib.pa_p2p_open(C.create_string_buffer(h, 64), C.byref(p)), "pa_p2p_open")
+                self._peers.append(p)
+                ptrs.append(p.value)
+            self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64).to(self.device)
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.epochs = torch.zeros(rows, dtype=torch.int32, device=self.device)  # advanced by the kernel
+        dist.barrier(group=group)  # every buffer is mapped (and zeroed) before the first kernel runs
+
+    def combine(self, part_m, part_l, part_o, out=None, lse_out=None):
+        """part_m/l [rows], part_o [rows, D] (this rank's partials) -> out [rows, D] on every rank."""
+        _cabi = self._cabi
+        if out is None:
+            out = torch.empty((self.rows, self.D), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().pa_splitkv_exchange_combine(
+                part_m.data_ptr(), part_l.data_ptr(), part_o.data_ptr(), self.peer_ptrs.data_ptr(), self.rank,
+                self.world, self.rows, self.D, self.epochs.data_ptr(), out.data_ptr(), _cabi.ptr(lse_out),
+                self.status.data_ptr(), _cabi.stream()), "pa_splitkv_exchange_combine")
+        return out
+
+    def decode(self, q, kv_cache, B, T_local, temperature=1.0, beam_ids=None, ctx_lens=None, out=None):
+        """pa_paged_decode_f16_splitkv: streaming kernel over this rank's pages + chunk-merge kernel whose
+        epilogue exchanges the row partials with the peers and combines them.  Two launches per call."""
+        _cabi = self._cabi
+        pt = kv_cache.page_table_
+        H, D = pt.num_heads_, kv_cache.head_dim_
+        assert B * H == self.rows and D == self.D
+        if out is None:
+            out = torch.empty((B, H, D), dtype=torch.float32, device=self.device)
+        ws = kv_cache.workspace(B)
+        with torch.cuda.device(self.device):
+            st = _cabi.lib().pa_paged_decode_f16_splitkv(
+                q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
+                pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_,
+                _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T_local, D, kv_cache.tile_size_, float(temperature),
+                None, None, ws.data_ptr(), ws.numel(), self.peer_ptrs.data_ptr(), self.rank, self.world,
+                self.epochs.data_ptr(), self.status.data_ptr(), _cabi.stream())
+        _cabi.check(st, "pa_paged_decode_f16_splitkv")
+        return out
+
+    def check(self):
+        """Raises if a peer ever failed to arrive (synchronises)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("pa_splitkv_exchange_combine: a peer rank did not arrive within the timeout")
+
+    def close(self):
+        lib = self._cabi.lib()
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._peers:
+                lib.pa_p2p_close(p)
+            self._peers = []
+            if self._own is not None:
+                lib.pa_p2p_free(self._own)
+                self._own = None
+
+
+def split_kv_decode(q, kv_cache, B, T_local, temperature=1.0, beam_ids=None, ctx_lens=None, group=None,
+                    exchange=None, fused=False):
     """Decode attention of `B` rows whose KV pages are split across the ranks of `group`.
     `kv_cache` holds THIS rank's pages (table row b = the rank's tile range of sequence b);
-    T_local / ctx_lens are the token counts held locally.  Returns out [B, H, D] on every rank."""
+    T_local / ctx_lens are the token counts held locally.  Returns out [B, H, D] on every rank.
+    exchange=None: NCCL all-gather of the partials followed by pa_lse_combine.
+    exchange=PeerExchange: partial kernel + ONE peer-memory exchange+combine kernel;
+    with fused=True the exchange runs in the epilogue of the decode's own chunk-merge kernel
+    (pa_paged_decode_f16_splitkv; the two exchange forms use the same buffers but must not be mixed
+    within one PeerExchange because they keep separate step counters)."""
+    if exchange is not None and fused:
+        return exchange.decode(q, kv_cache, B, T_local, temperature, beam_ids, ctx_lens)
     pm, pl, po = _att.paged_decode_partial(q, kv_cache, B, T_local, temperature, beam_ids, ctx_lens)
     H, D = po.shape[1], po.shape[2]
+    if exchange is not None:
+        return exchange.combine(pm.reshape(-1), pl.reshape(-1), po.reshape(B * H, D)).reshape(B, H, D)
     msg = pack_partials(pm, pl, po.reshape(B * H, D))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         gathered = gather_partials(msg, group)
