@@ -157,6 +157,24 @@ int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8_t* d_k
                                const float* d_rope, float* d_lse_out, void* d_workspace,
                                size_t workspace_bytes, pa_stream_t stream);
 
+/* Beam-aware shared-prefix decode (north star; the reference's only hook is the
+ * beam_ids[b] -> page-table-row indirection, ...fused.cu:22).  Rows b = g*beam_width ..
+ * g*beam_width + beam_width-1 form beam group g.  Same results as pa_paged_decode_f16, but
+ * a K/V page whose id is the same for several beams of a group (shared prefix /
+ * not-yet-copied copy-on-write page) is read from HBM ONCE per group and applied to all
+ * those beams' queries on the tensor cores (mma.sync m16n8k16, fp16 operands split hi/lo so
+ * scores and outputs keep fp32 accuracy).  Pages that differ are staged per distinct id.
+ * Requires head_dim == 128, beam_width <= 4, B % beam_width == 0, d_ctx_lens == NULL
+ * (beams advance in lock step: every row has T tokens); otherwise PA_ERR_UNSUPPORTED and
+ * the caller uses pa_paged_decode_f16[_overlap]. */
+int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_pool,
+                              const void* d_v_pool, const int32_t* d_table, int num_beams,
+                              int num_heads, int num_tiles, int total_pages,
+                              const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B, int T,
+                              int head_dim, int tile_size, float temperature, const float* d_rope,
+                              int beam_width, float* d_lse_out, void* d_workspace,
+                              size_t workspace_bytes, pa_stream_t stream);
+
 /* Split-KV across GPUs (north-star long-context mode): same computation over
  * this rank's pages only, emitting UN-normalised partials for an LSE combine:
  *   d_part_m[b,h] = max_t s[t] (natural-log units; -inf if no key)

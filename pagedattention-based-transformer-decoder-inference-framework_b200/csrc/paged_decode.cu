@@ -22,6 +22,10 @@
 //     handed out through a global atomic counter (dynamic balance; a static
 //     equal split lost ~4% to SM-to-SM rate differences, profiles/), each chunk
 //     emits an (m, l, O) partial that a small combine kernel merges per row.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "pa_common.cuh"
 
 namespace pa {
@@ -58,6 +62,7 @@ struct DecodeArgs {
     uint32_t* xch_epochs;       // [rows] step counters
     int* xch_status;
     int xch_rank, xch_world;
+    int all_rows_in_ws;  // combine kernel: merge rows of a single chunk too (exchange / group kernels)
 };
 
 template <int D, int KV>
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
         nc = cm.nchunks_of(b);
         s0 = cm.row_start(b, h);
     }
-    const bool skip = !row_ok || (nc == 1 && !a.xch_peers);  // nc == 1: written by the main kernel
+    const bool skip = !row_ok || (nc == 1 && !a.all_rows_in_ws);  // nc == 1: written by the main kernel
     // chunks of this warp: j = wsub + wpr * i, i < n_mine
     const int n_mine = (skip || nc <= wsub) ? 0 : (nc - wsub + wpr - 1) / wpr;
     float mloc = -INFINITY;
@@ -829,6 +834,348 @@ __global__ void lse_combine_kernel(const float* __restrict__ pm, const float* __
     if (threadIdx.x == 0 && lse_out) lse_out[row] = (L > 0.f) ? M + logf(L) : -INFINITY;
 }
 
+// ------------------------------------------------------- beam-group kernel (C3)
+// Beams of a group share the page ids of their common prefix (beam_ids -> table rows,
+// ...fused.cu:22).  Here a GROUP of W <= 4 consecutive rows is the unit of work: for every 16-token
+// unit the W page ids are compared; rows with equal ids share ONE staged copy of the K/V unit
+// (the bytes cross HBM once per group instead of once per beam), private / copy-on-write pages are
+// staged per distinct id.  With W queries per K/V byte the op is a skinny GEMM, so it runs on the
+// tensor cores: mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with
+//     S[16 x 16 tok] = Qs[16 x 128] . K^T      rows 0-3 = fp16 hi part of the W queries,
+//     O[16 x 128]   += P[16 x 16 tok] . V      rows 4-7 = fp16 lo part (q - hi), rows 8-15 unused
+// so hi+lo rows summed give fp32-accurate scores from fp16 tensor-core operands; P is split into
+// hi/lo rows the same way.  K/V units are staged by TMA tensor copies (cp.async.bulk.tensor.2d,
+// SWIZZLE_128B, boxes of 16 tokens x 64 dims) into per-warp rings so ldmatrix is conflict-free.
+// Each chunk writes W (m, l, O) partials into the same workspace slots the overlap kernel uses;
+// combine_chunks_kernel merges them.
+constexpr int kGroupMaxW = 4;
+constexpr int kGroupStageBytes = 8192;  // K lo/hi + V lo/hi boxes of [16][64] fp16
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D += A.B, rows 8-15 of A are zero (a1 = a3 = 0)
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    const uint32_t z = 0u;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+    __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct GroupArgs {
+    int W;        // rows per group
+    int groups;   // B / W
+};
+
+template <int NW, int S>
+__global__ void __launch_bounds__(NW * 32, 1)
+paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                          const DecodeArgs a, const GroupArgs ga, int cu, unsigned int* counter) {
+    constexpr int D = 128;
+    constexpr int QN = 16;
+    extern __shared__ __align__(1024) uint8_t smem_g[];
+    const uint32_t smem_base = (smem_u32(smem_g) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_g + (smem_base - smem_u32(smem_g));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + (size_t)NW * S * kGroupStageBytes);
+    int* meta = reinterpret_cast<int*>(bars + NW * S);
+    int64_t* cq = reinterpret_cast<int64_t*>(meta + NW * S + ((NW * S) & 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g8 = lane >> 2, j4 = lane & 3;
+    const int W = ga.W;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NW * S; ++i) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+    }
+    __syncthreads();
+
+    // chunk space: (group, head, j) with NC chunks of `cu` units per row (uniform context a.T)
+    const int units = units_of_ctx(row_ctx(a, 0));
+    const int NC = (units + cu - 1) / cu;
+    const int64_t total = (int64_t)ga.groups * a.H * NC;
+    const int64_t total_warps = (int64_t)gridDim.x * NW;
+    const int64_t gw = (int64_t)blockIdx.x * NW + warp;
+    const int upt = a.tile_size / kUnitTok;
+    const int ctx = row_ctx(a, 0);
+
+    const uint32_t my_stage0 = smem_base + (uint32_t)warp * S * kGroupStageBytes;
+    const uint32_t my_bar0 = smem_u32(bars + warp * S);
+    int* my_meta = meta + warp * S;
+    int64_t* my_cq = cq + warp * QN;
+
+    // ---------------- producer (warp-uniform state; lanes < W look pages up in parallel) -------
+    bool p_has = false, p_first = true;
+    int p_g = 0, p_h = 0, p_u = 0, p_uend = 0;
+    int p_beam = 0;          // lane w < W: table row of beam w of the current group
+    uint32_t issued = 0, p_chunks = 0;
+    int p_pending_mask = 0;  // beams of the current unit not yet staged
+    int p_page = -1;         // lane w: page of beam w for the current unit
+
+    auto p_next_chunk = [&]() -> bool {
+        int64_t id;
+        if (p_first) {
+            id = gw;
+            p_first = false;
+        } else {
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(counter, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            id = total_warps + (int64_t)t;
+        }
+        if (id >= total) return false;
+        // Chunk order: position-major, LAST chunks first.  The tail of a beam's context is private
+        // (W staged copies per unit) while the prefix is shared (one copy), so the expensive chunks
+        // are dispatched first and the cheap ones fill the end of the run (longest-first balance).
+        const int64_t per_j = (int64_t)ga.groups * a.H;
+        const int j = NC - 1 - (int)(id / per_j);
+        const int rem = (int)(id % per_j);
+        p_g = rem / a.H;
+        p_h = rem - p_g * a.H;
+        p_u = j * cu;
+        p_uend = min(units, p_u + cu);
+        if (lane < W) {
+            const int b = p_g * W + lane;
+            p_beam = a.beam_ids ? a.beam_ids[b] : b;
+        }
+        if (lane == 0) my_cq[p_chunks % QN] = id;
+        ++p_chunks;
+        __syncwarp();
+        return true;
+    };
+    auto p_fetch_unit = [&]() {  // page ids of the W beams for unit p_u
+        p_page = (lane < W) ? lookup_page(a, p_beam, p_h, p_u / upt) : -1;
+        p_pending_mask = (int)(__ballot_sync(0xffffffffu, lane < W && p_page >= 0));
+    };
+    p_has = p_next_chunk();
+    if (p_has) p_fetch_unit();
+
+    // Stage ONE copy: the lowest pending beam's page, shared by every pending beam with the same id.
+    auto produce = [&]() {
+        if (!p_has) return;
+        const uint32_t st = issued % S;
+        const uint32_t bar = my_bar0 + st * 8;
+        int mask = 0, page = -1;
+        if (p_pending_mask) {
+            const int lead = __ffs(p_pending_mask) - 1;
+            page = __shfl_sync(0xffffffffu, p_page, lead);
+            mask = (int)(__ballot_sync(0xffffffffu, lane < W && p_page == page)) & p_pending_mask;
+            p_pending_mask &= ~mask;
+        }
+        const bool last_of_unit = (p_pending_mask == 0);
+        const bool last_of_chunk = last_of_unit && (p_u + 1 >= p_uend);
+        const int nvalid = mask ? min(kUnitTok, ctx - p_u * kUnitTok) : 0;
+        if (lane == 0) {
+            my_meta[st] = nvalid | (mask << 8) | (last_of_chunk ? (1 << 16) : 0);
+            if (nvalid > 0) {
+                const int row0 = page * a.tile_size + (p_u % upt) * kUnitTok;  // token row in the pool
+                const uint32_t dst = my_stage0 + st * kGroupStageBytes;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, kGroupStageBytes);
+                tma_load_2d(dst, &tmK, 0, row0, bar);
+                tma_load_2d(dst + 2048, &tmK, 64, row0, bar);
+                tma_load_2d(dst + 4096, &tmV, 0, row0, bar);
+                tma_load_2d(dst + 6144, &tmV, 64, row0, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+        ++issued;
+        if (last_of_unit) {
+            ++p_u;
+            if (p_u >= p_uend) p_has = p_next_chunk();
+            if (p_has) p_fetch_unit();
+        }
+    };
+
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) produce();
+
+    // ---------------- consumer ---------------------------------------------------------------
+    uint32_t consumed = 0, c_chunks = 0;
+    const int beam_of_lane = g8 & 3;          // MMA row g8: rows 0-3 hi, 4-7 lo of beam g8 & 3
+    const bool lo_half = g8 >= 4;
+    while (c_chunks < p_chunks) {
+        const int64_t id = my_cq[c_chunks % QN];
+        ++c_chunks;
+        const int64_t per_j = (int64_t)ga.groups * a.H;
+        const int cj = NC - 1 - (int)(id / per_j);
+        const int rem = (int)(id % per_j);
+        const int cg = rem / a.H;
+        const int ch = rem - cg * a.H;
+        // Q fragments: row g8 of the 16 x 128 operand, fp16 hi (rows 0-3) / lo (rows 4-7) parts
+        uint32_t qa[8][2];
+        {
+            const bool valid_beam = beam_of_lane < W;
+            const int64_t qrow = ((int64_t)(cg * W + (valid_beam ? beam_of_lane : 0)) * a.H + ch) * D;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int d0 = s * 16 + hh * 8 + j4 * 2;
+                    float x0 = 0.f, x1 = 0.f;
+                    if (valid_beam) {
+                        x0 = a.q[qrow + d0];
+                        x1 = a.q[qrow + d0 + 1];
+                        if (a.rope) {
+                            const float cs = a.rope[d0], sn = a.rope[d0 + 1];
+                            const float r0 = x0 * cs - x1 * sn, r1 = x0 * sn + x1 * cs;
+                            x0 = r0;
+                            x1 = r1;
+                        }
+                        x0 *= a.qscale;
+                        x1 *= a.qscale;
+                    }
+                    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                    if (lo_half) {
+                        x0 -= __half2float(h0);
+                        x1 -= __half2float(h1);
+                        qa[s][hh] = pack_half2(x0, x1);
+                    } else {
+                        __half2 hv = __halves2half2(h0, h1);
+                        qa[s][hh] = *reinterpret_cast<uint32_t*>(&hv);
+                    }
+                }
+            }
+        }
+        float m_run = -INFINITY, l_run = 0.f;  // of beam_of_lane (replicated over the 4 j4 lanes: l is per-lane partial)
+        float o[16][4];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f; }
+
+        bool done = false;
+#pragma unroll 1
+        while (!done) {
+            const uint32_t st = consumed % S;
+            mbar_wait(my_bar0 + st * 8, (consumed / S) & 1);
+            const int mt = my_meta[st];
+            const int nvalid = mt & 0xff, mask = (mt >> 8) & 0xff;
+            done = (mt >> 16) & 1;
+            if (nvalid > 0) {
+                const uint32_t sb = my_stage0 + st * kGroupStageBytes;
+                if (nvalid < kUnitTok) {
+                    // rows past the context end may hold anything (even NaN bit patterns): zero the V rows
+                    for (int i = lane; i < (kUnitTok - nvalid) * 16; i += 32) {
+                        const int r = nvalid + i / 16, c = i % 16;  // 16 chunks of 16 B per 256-byte row (2 boxes)
+                        const uint32_t addr = sb + 4096 + (c >> 3) * 2048 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+                    }
+                    __syncwarp();
+                }
+                // ---- S = Qs . K^T : 2 n-tiles of 8 tokens ----
+                float sacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                {
+                    const int mi = lane >> 3;
+                    const int r = (lane & 7) + (mi >> 1) * 8;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int c = 2 * (s & 3) + (mi & 1);
+                        const uint32_t addr = sb + (s >> 2) * 2048 + r * 128 + ((c ^ (r & 7)) << 4);
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4(addr, b0, b1, b2, b3);
+                        mma_16816(sacc[0], qa[s][0], qa[s][1], b0, b1);
+                        mma_16816(sacc[1], qa[s][0], qa[s][1], b2, b3);
+                    }
+                }
+                // hi + lo rows -> full-precision scores of beam_of_lane for tokens t*8 + j4*2 + {0,1}
+                float sc[4];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float v = sacc[t][e];
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        const int tok = t * 8 + j4 * 2 + e;
+                        const bool ok = tok < nvalid && ((mask >> beam_of_lane) & 1);
+                        sc[t * 2 + e] = ok ? v : -INFINITY;
+                    }
+                }
+                float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const float m_new = fmaxf(m_run, mx);
+                // beams without this unit (mask bit 0) or with no valid key keep their state: corr = 1
+                const float corr = (m_new == -INFINITY) ? 1.f : fast_exp2(m_run - m_new);
+                float p[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) p[i] = (sc[i] == -INFINITY) ? 0.f : fast_exp2(sc[i] - m_new);
+                l_run = fmaf(l_run, corr, (p[0] + p[1]) + (p[2] + p[3]));
+                m_run = m_new;
+                if (__any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) { o[t][0] *= corr; o[t][1] *= corr; }
+                }
+                // P fragments: rows 0-3 hi, rows 4-7 lo
+                uint32_t pa0, pa2;
+                {
+                    const __half2 h01 = __floats2half2_rn(p[0], p[1]), h23 = __floats2half2_rn(p[2], p[3]);
+                    if (lo_half) {
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        pa0 = pack_half2(p[0] - f01.x, p[1] - f01.y);
+                        pa2 = pack_half2(p[2] - f23.x, p[3] - f23.y);
+                    } else {
+                        pa0 = *reinterpret_cast<const uint32_t*>(&h01);
+                        pa2 = *reinterpret_cast<const uint32_t*>(&h23);
+                    }
+                }
+                // ---- O += P . V : 16 n-tiles of 8 dims ----
+                {
+                    const int mi = lane >> 3;
+                    const int r = (lane & 7) + (mi & 1) * 8;
+#pragma unroll
+                    for (int n2 = 0; n2 < 8; ++n2) {
+                        const int c = 2 * (n2 & 3) + (mi >> 1);
+                        const uint32_t addr = sb + 4096 + (n2 >> 2) * 2048 + r * 128 + ((c ^ (r & 7)) << 4);
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4_trans(addr, b0, b1, b2, b3);
+                        mma_16816(o[2 * n2], pa0, pa2, b0, b1);
+                        mma_16816(o[2 * n2 + 1], pa0, pa2, b2, b3);
+                    }
+                }
+            }
+            __syncwarp();
+            ++consumed;
+            produce();
+        }
+        // ---- chunk done: per-beam (m, l, O) partial -> workspace slot ((b*H + h)*NC + j) ----
+        float l_tot = l_run;
+        l_tot += __shfl_xor_sync(0xffffffffu, l_tot, 1);
+        l_tot += __shfl_xor_sync(0xffffffffu, l_tot, 2);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            o[t][0] += __shfl_xor_sync(0xffffffffu, o[t][0], 16);
+            o[t][1] += __shfl_xor_sync(0xffffffffu, o[t][1], 16);
+        }
+        if (!lo_half && beam_of_lane < W) {
+            const int64_t slot = ((int64_t)(cg * W + beam_of_lane) * a.H + ch) * NC + cj;
+            float* dst = a.ws_o + slot * D;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                *reinterpret_cast<float2*>(dst + t * 8 + j4 * 2) = make_float2(o[t][0], o[t][1]);
+            if (j4 == 0) {
+                a.ws_m[slot] = m_run;
+                a.ws_l[slot] = l_tot;
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------- host side
 constexpr int kOvWarps = 8;
 template <int D, int KV>
@@ -867,7 +1214,12 @@ static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
     const int cu = choose_cu(rows, max_units, sm_count);
     const size_t ov = (size_t)rows * ((max_units + cu - 1) / cu);
     const size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
-    return (((ov > dr ? ov : dr) + 64) + 3) & ~(size_t)3;  // multiple of 4: ws_o stays 16-byte aligned
+    // beam-group kernel: chunk size chosen from the number of (group, head) pairs, >= rows / 4
+    const int cug = choose_cu(rows / kGroupMaxW > 0 ? rows / kGroupMaxW : 1, max_units, sm_count);
+    const size_t gr = (size_t)rows * ((max_units + cug - 1) / cug);
+    size_t mx = ov > dr ? ov : dr;
+    if (gr > mx) mx = gr;
+    return ((mx + 64) + 3) & ~(size_t)3;  // multiple of 4: ws_o stays 16-byte aligned
 }
 
 static size_t ws_bytes_needed(int B, int H, int D, int num_tiles, int tile_size, int sm_count) {
@@ -933,6 +1285,74 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     return e == cudaSuccess ? PA_OK : (int)e;
 }
 
+// ---- host: tensor maps for the group kernel ------------------------------------------------
+typedef CUresult (*EncodeTiledFnG)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnG encode_fn_g() {
+    static EncodeTiledFnG fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnG>(p);
+    });
+    return fn;
+}
+// fp16 pool viewed as [total_tokens][128]; box = 16 tokens x 64 dims (128 B), SWIZZLE_128B.
+static bool make_pool_map(CUtensorMap* map, const void* pool, uint64_t total_tokens) {
+    EncodeTiledFnG fn = encode_fn_g();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {128, total_tokens};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 16};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(pool), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
+    constexpr int D = 128, S = 3;
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return PA_ERR_NO_DEVICE;
+    const int64_t rows = (int64_t)a.B * a.H;
+    const int max_units = (int)(((int64_t)a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok);
+    if (!ws || ws_bytes < ws_bytes_needed(a.B, a.H, D, a.num_tiles, a.tile_size, di.sm_count)) return PA_ERR_WORKSPACE;
+    unsigned int* counter = static_cast<unsigned int*>(ws);
+    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+    const size_t nslots = ws_slots(rows, max_units, di.sm_count);
+    a.ws_m = w;
+    a.ws_l = w + nslots;
+    a.ws_o = w + 2 * nslots;
+    a.all_rows_in_ws = 1;
+    GroupArgs ga{W, a.B / W};
+    const int64_t gh = (int64_t)ga.groups * a.H;
+    const int cu = choose_cu(gh, max_units, di.sm_count);
+    CUtensorMap tmK, tmV;
+    const uint64_t total_tokens = (uint64_t)a.total_pages * a.tile_size;
+    if (!make_pool_map(&tmK, a.k_pool, total_tokens) || !make_pool_map(&tmV, a.v_pool, total_tokens))
+        return PA_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)kOvWarps * S * kGroupStageBytes + (size_t)kOvWarps * S * (8 + 4) + 8 +
+                        (size_t)kOvWarps * 16 * sizeof(int64_t) + 1024;
+    auto kern = paged_decode_group_kernel<kOvWarps, S>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<di.sm_count, kOvWarps * 32, smem, st>>>(tmK, tmV, a, ga, cu, counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int nc_max = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
+    const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
+    const int rpc = 8 / wpr;
+    combine_chunks_kernel<D><<<(int)((rows + rpc - 1) / rpc), 256, 0, st>>>(a, cu, wpr);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? PA_OK : (int)e;
+}
+
 struct XchgParams {
     void* const* peers;
     uint32_t* epochs;
@@ -975,6 +1395,7 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
         a.xch_status = xch->status;
         a.xch_rank = xch->rank;
         a.xch_world = xch->world;
+        a.all_rows_in_ws = 1;
     }
     cudaStream_t st = as_stream(stream);
     if (kv == 0) {
@@ -1052,6 +1473,30 @@ PA_API int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const voi
     XchgParams x{d_peer_bufs, d_epochs, d_status, rank, world};
     return decode_entry(0, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
                         nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream, &x);
+}
+
+PA_API int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_pool,
+                                     const void* d_v_pool, PA_DECODE_COMMON_PARAMS, int beam_width,
+                                     float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                                     pa_stream_t stream) {
+    PA_CHECK_ARG(d_q && d_out && d_k_pool && d_v_pool && d_table);
+    PA_CHECK_ARG(num_beams > 0 && num_heads > 0 && num_tiles > 0 && total_pages > 0 && B >= 0 && T >= 0);
+    PA_CHECK_ARG(temperature != 0.f && tile_size > 0 && beam_width >= 1);
+    PA_CHECK_ARG((uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0);
+    if (head_dim != 128 || tile_size % kUnitTok != 0 || beam_width > kGroupMaxW || d_ctx_lens != nullptr)
+        return PA_ERR_UNSUPPORTED;
+    if (B % beam_width != 0) return PA_ERR_INVALID_ARG;
+    if (B == 0) return PA_OK;
+    DecodeArgs a{};
+    a.q = d_q; a.out = d_out; a.lse_out = d_lse_out;
+    a.k_pool = static_cast<const uint8_t*>(d_k_pool);
+    a.v_pool = static_cast<const uint8_t*>(d_v_pool);
+    a.table = d_table; a.beam_ids = d_beam_ids; a.ctx_lens = nullptr; a.rope = d_rope;
+    a.num_beams = num_beams; a.H = num_heads; a.num_tiles = num_tiles; a.total_pages = total_pages;
+    a.B = B; a.T = T; a.tile_size = tile_size;
+    a.num_splits = 1;
+    a.qscale = kLog2e / temperature;
+    return launch_group(a, beam_width, d_workspace, workspace_bytes, as_stream(stream));
 }
 
 PA_API int pa_lse_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,

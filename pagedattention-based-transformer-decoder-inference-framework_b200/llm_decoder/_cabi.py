@@ -37,6 +37,7 @@ _SIGS = {
     "pa_paged_decode_i8_overlap": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_partial": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_splitkv": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pa_paged_decode_f16_group": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_i32, _vp, _vp, _sz, _vp], _i32),
     "pa_lse_combine": ([_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_quantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
     "pa_batch_quantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),

@@ -132,6 +132,25 @@ class AttentionCUDA:
                                             top_p, rerank_scores, debug, ctx_lens)
 
 
+def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam_ids=None, rotary_emb=None,
+                       lse_out=None):
+    """Beam-aware decode (pa_paged_decode_f16_group): rows [g*W, (g+1)*W) are the W beams of group g;
+    pages with equal ids within a group are read once.  q/out [B, H, D] f32 CUDA tensors."""
+    pt = kv_cache.page_table_
+    H, D = pt.num_heads_, kv_cache.head_dim_
+    if kv_cache.dtype != "f16":
+        raise NotImplementedError("paged_decode_group: fp16 KV pages only")
+    ws = kv_cache.workspace(B)
+    with torch.cuda.device(kv_cache.key_buffer_.device):
+        st = _cabi.lib().pa_paged_decode_f16_group(
+            q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
+            pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids),
+            None, B, T, D, kv_cache.tile_size_, float(temperature), _cabi.ptr(rotary_emb), int(beam_width),
+            _cabi.ptr(lse_out), ws.data_ptr(), ws.numel(), _cabi.stream())
+    _cabi.check(st, "pa_paged_decode_f16_group")
+    return out
+
+
 def paged_decode_partial(q, kv_cache, B, T, temperature=1.0, beam_ids=None, ctx_lens=None, rotary_emb=None):
     """Un-normalised (m, l, O) of this rank's pages (multi-GPU split-KV)."""
     pt = kv_cache.page_table_

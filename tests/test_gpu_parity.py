@@ -273,6 +273,80 @@ def test_partial_and_combine_equal_full(ld, oracle):
     np.testing.assert_allclose(out.reshape(-1, 128), exp, rtol=1e-5, atol=1e-6)
 
 
+# ------------------------------------------------------------------ beam-aware group kernel (C3)
+GROUP_CASES = [
+    dict(B=8, H=2, D=128, T=320, beam_width=4, shared_prefix=192),
+    dict(B=8, H=3, D=128, T=333, beam_width=4, shared_prefix=256),                      # ragged last page
+    dict(B=6, H=2, D=128, T=200, beam_width=2, shared_prefix=96),
+    dict(B=6, H=2, D=128, T=160, beam_width=3, shared_prefix=160),                      # fully shared
+    dict(B=8, H=2, D=128, T=256, beam_width=4, shared_prefix=128, unmapped_frac=0.08),  # -1 / OOB pages per beam
+    dict(B=4, H=4, D=128, T=64, beam_width=1),                                          # degenerate: no sharing
+    dict(B=4, H=2, D=128, T=4096, beam_width=4, shared_prefix=3584),                    # long rows, many chunks
+    dict(B=8, H=2, D=128, T=512, beam_width=4, shared_prefix=256, tile_size=32),
+]
+
+
+@pytest.mark.parametrize("ci", range(len(GROUP_CASES)))
+def test_group_decode_matches_oracle(ld, oracle, ci):
+    cfg = dict(GROUP_CASES[ci])
+    case = make_case(seed=40 + ci, **cfg)
+    W = cfg["beam_width"]
+    if ci == 0:
+        # copy-on-write in progress: inside one shared tile beams 0,1 keep the shared page while beams
+        # 2,3 already point at their own copies (3 distinct page ids in one unit)
+        tb = case["table"]
+        rows = case["beam_ids"][:4]
+        tb[rows[2], 0, 3] = tb[rows[2], 0, -1]
+        tb[rows[3], 0, 3] = tb[rows[3], 0, -2]
+    exp, probs, logits = oracle_attention(case, return_probs=True, return_logits=True)
+    kvc = to_device_cache(case)
+    B, H, D = case["q"].shape
+    q = torch.from_numpy(case["q"]).cuda()
+    out = torch.full((B, H, D), float("nan"), device="cuda")
+    lse = torch.empty((B, H), device="cuda")
+    bid = None if case["beam_ids"] is None else torch.from_numpy(case["beam_ids"]).cuda()
+    ld.paged_decode_group(q, out, kvc, B, case["T"], W, case["temperature"], beam_ids=bid, lse_out=lse)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
+    # equals the per-row kernel far inside the tolerance (hi/lo split keeps fp32 accuracy)
+    ref, _ = run_decode(ld, case, True, kvc)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
+    for b in range(B):
+        for h in range(H):
+            sv = logits[b, h, :case["T"]]
+            sv = sv[sv > -1e8]
+            if sv.size:
+                r = np.log(np.exp(sv - sv.max()).sum()) + sv.max()
+                assert abs(lse.cpu().numpy()[b, h] - r) <= 1e-3 * max(1.0, abs(r))
+
+
+def test_group_decode_poisoned_tail_and_unsupported(ld, oracle):
+    """Rows of the last page past the context end hold NaN bit patterns: they must not leak; and
+    the documented unsupported shapes are refused with PAError (caller then uses the per-row kernel)."""
+    case = make_case(B=4, H=2, D=128, T=100, seed=61, beam_width=4, shared_prefix=64)
+    exp = oracle_attention(case)
+    kvc = to_device_cache(case)
+    # poison every token row >= T % 16 of the last tile's pages
+    last = torch.from_numpy(case["table"][:, :, -1].reshape(-1).astype(np.int64)).cuda()
+    kvc.key_buffer_[last, 100 % 16:] = float("nan")
+    kvc.value_buffer_[last, 100 % 16:] = float("nan")
+    q = torch.from_numpy(case["q"]).cuda()
+    out = torch.empty_like(q)
+    bid = torch.from_numpy(case["beam_ids"]).cuda()
+    ld.paged_decode_group(q, out, kvc, 4, 100, 4, case["temperature"], beam_ids=bid)
+    np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
+    from llm_decoder._cabi import PAError
+    with pytest.raises(PAError):
+        ld.paged_decode_group(q, out, kvc, 4, 100, 3, case["temperature"], beam_ids=bid)   # B % W != 0
+    c64 = make_case(B=2, H=2, D=64, T=64, seed=62, beam_width=2, shared_prefix=32)
+    k64 = to_device_cache(c64)
+    q64 = torch.from_numpy(c64["q"]).cuda()
+    with pytest.raises(PAError):
+        ld.paged_decode_group(q64, torch.empty_like(q64), k64, 2, 64, 2, 1.0)             # head_dim 64
+
+
 # ------------------------------------------------------------------ full-size properties (C2 shape)
 def test_c2_full_size_properties(ld, oracle):
     """BASELINE config C2 (B=64, H=32, D=128, T=4096, 16-token pages): too big for the CPU
