@@ -96,6 +96,13 @@ int pa_kv_append_f32_i8(int8_t* d_k_pool, int8_t* d_v_pool, float* d_k_scales, f
                         const float* d_new_v, const int32_t* d_beam_ids,
                         const int32_t* d_positions, int R, pa_stream_t stream);
 
+/* Copy-on-write support for beam search over shared-prefix pages (north star; no
+ * reference implementation): pool[d_dst_pages[i]] := pool[d_src_pages[i]] for the K and V
+ * pools (and the int8 scale rows when given), i < n.  Bit-exact byte mover. */
+int pa_kv_copy_pages(void* d_k_pool, void* d_v_pool, float* d_k_scales, float* d_v_scales,
+                     const int32_t* d_src_pages, const int32_t* d_dst_pages, int n, int total_pages,
+                     int tile_size, int head_dim, int elem_bytes, pa_stream_t stream);
+
 /* ------------------------------------------------ paged decode attention */
 /* Bytes of scratch the decode entry points need for B rows x H heads of head_dim D over a
  * page table of num_tiles tiles of tile_size tokens. */

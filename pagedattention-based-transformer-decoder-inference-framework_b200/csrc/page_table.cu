@@ -188,6 +188,27 @@ __global__ void kv_append_kernel(void* __restrict__ k_pool, void* __restrict__ v
     }
 }
 
+// Copy-on-write page copies: pool[dst[i]] := pool[src[i]] for K, V (and their scale rows).
+// One warp per (copy, pool): 32 lanes x 16 B per iteration.
+__global__ void kv_copy_pages_kernel(uint8_t* __restrict__ k_pool, uint8_t* __restrict__ v_pool,
+                                     float* __restrict__ k_scales, float* __restrict__ v_scales,
+                                     const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int n,
+                                     int total_pages, int64_t page_bytes, int tile_size) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)n * 2) return;
+    const int i = (int)(w >> 1);
+    const int s = src[i], d = dst[i];
+    if (s < 0 || s >= total_pages || d < 0 || d >= total_pages || s == d) return;
+    uint8_t* pool = (w & 1) ? v_pool : k_pool;
+    const uint4* sp = reinterpret_cast<const uint4*>(pool + (int64_t)s * page_bytes);
+    uint4* dp = reinterpret_cast<uint4*>(pool + (int64_t)d * page_bytes);
+    for (int64_t v = lane; v < page_bytes / 16; v += 32) dp[v] = sp[v];
+    float* sc = (w & 1) ? v_scales : k_scales;
+    if (sc)
+        for (int t = lane; t < tile_size; t += 32) sc[(int64_t)d * tile_size + t] = sc[(int64_t)s * tile_size + t];
+}
+
 static int grid_for(int64_t threads_needed, int block, int max_blocks) {
     int64_t b = (threads_needed + block - 1) / block;
     if (b < 1) b = 1;
@@ -326,4 +347,19 @@ PA_API int pa_kv_append_f32_i8(int8_t* d_k_pool, int8_t* d_v_pool, float* d_k_sc
     return launch_append<2>(d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table, num_beams,
                             num_heads, num_tiles, total_pages, tile_size, head_dim, d_new_k,
                             d_new_v, d_beam_ids, d_positions, R, stream);
+}
+
+PA_API int pa_kv_copy_pages(void* d_k_pool, void* d_v_pool, float* d_k_scales, float* d_v_scales,
+                            const int32_t* d_src_pages, const int32_t* d_dst_pages, int n, int total_pages,
+                            int tile_size, int head_dim, int elem_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(d_k_pool && d_v_pool && d_src_pages && d_dst_pages && n >= 0 && total_pages > 0);
+    PA_CHECK_ARG(tile_size > 0 && head_dim > 0 && (elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4));
+    const int64_t page_bytes = (int64_t)tile_size * head_dim * elem_bytes;
+    if (page_bytes % 16 != 0) return PA_ERR_UNSUPPORTED;
+    if (n == 0) return PA_OK;
+    const int64_t threads = (int64_t)n * 2 * 32;
+    kv_copy_pages_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
+        static_cast<uint8_t*>(d_k_pool), static_cast<uint8_t*>(d_v_pool), d_k_scales, d_v_scales, d_src_pages,
+        d_dst_pages, n, total_pages, page_bytes, tile_size);
+    PA_RETURN_LAUNCH_STATUS();
 }

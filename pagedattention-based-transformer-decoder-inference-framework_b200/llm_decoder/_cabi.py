@@ -30,6 +30,7 @@ _SIGS = {
     "pa_kv_append_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_append_f32_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_append_f32_i8": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_kv_copy_pages": ([_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], _i32),
     "pa_decode_workspace_bytes": ([_i32, _i32, _i32, _i32, _i32], _sz),
     "pa_paged_decode_f16": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_overlap": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),

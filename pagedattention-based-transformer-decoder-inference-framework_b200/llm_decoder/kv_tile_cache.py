@@ -108,10 +108,10 @@ class KVTileCache:
             return page
 
     def _evict_if_needed(self):
-        if not self._free:
+        while not self._free and self.tile_to_page_map_:
             last, page = self.tile_to_page_map_.popitem(last=False)  # least recently used
             self.page_table_.remove(*last)
-            self._free.append(page)
+            self._release_page(page)  # a page still shared by another beam is not freed yet
 
     def sync_page_table_to_gpu(self):
         self.page_table_.sync_to_gpu()
@@ -166,6 +166,92 @@ class KVTileCache:
                 assert new_k.dtype == torch.float32
                 st = lib.pa_kv_append_f32_f16(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), *common)
         _cabi.check(st, "pa_kv_append")
+
+    # ---- beam search: shared-prefix pages with copy-on-write (north star; no reference code) ---
+    def _refs(self):
+        if not hasattr(self, "_page_refs"):
+            self._page_refs = {}
+        return self._page_refs
+
+    def fork_beam(self, src_beam, dst_beam, num_tiles=None):
+        """Make table row `dst_beam` share the pages of `src_beam` (first `num_tiles` tiles of every head):
+        the beam-search fork.  No K/V bytes move; the shared pages become copy-on-write."""
+        pt = self.page_table_
+        nt = pt.num_tiles_ if num_tiles is None else int(num_tiles)
+        refs = self._refs()
+        with self.mutex_:
+            for h in range(pt.num_heads_):
+                for t in range(nt):
+                    old = pt.lookup(dst_beam, h, t)
+                    page = pt.lookup(src_beam, h, t)
+                    if old == page:
+                        continue
+                    if old >= 0:
+                        self._release_page(old)
+                    if page >= 0:
+                        refs[page] = refs.get(page, 1) + 1
+                    pt.assign(dst_beam, h, t, page)
+                    key = (int(dst_beam), h, t)
+                    if page >= 0:
+                        self.tile_to_page_map_[key] = page
+                    else:
+                        self.tile_to_page_map_.pop(key, None)
+
+    def _release_page(self, page):
+        refs = self._refs()
+        n = refs.get(page, 1) - 1
+        if n <= 0:
+            refs.pop(page, None)
+            self._free.append(page)
+        else:
+            refs[page] = n
+
+    def page_refcount(self, page):
+        return self._refs().get(int(page), 1)
+
+    def append_cow(self, new_k, new_v, positions, beam_ids=None):
+        """append() for beams that may share pages: before the row write, every (beam, head) whose
+        target page is shared (refcount > 1) gets a private copy -- a fresh page from the free list, one
+        batched device copy (pa_kv_copy_pages), one batched page-table update.  `positions` (and
+        `beam_ids`) are HOST integer sequences: page management is host logic, as in the reference
+        (kv_tile_cache.cpp:65-98)."""
+        pt = self.page_table_
+        pos_h = [int(p) for p in positions]
+        rows = list(range(len(pos_h))) if beam_ids is None else [int(b) for b in beam_ids]
+        refs = self._refs()
+        src, dst = [], []
+        with self.mutex_:
+            for r, pos in zip(rows, pos_h):
+                if pos < 0:
+                    continue
+                t = pos // self.tile_size_
+                for h in range(pt.num_heads_):
+                    page = pt.lookup(r, h, t)
+                    if page >= 0 and refs.get(page, 1) > 1:
+                        if not self._free:
+                            raise RuntimeError("KVTileCache.append_cow: page pool exhausted")
+                        new_page = self._free.pop()
+                        refs[page] -= 1
+                        if refs[page] <= 1:
+                            refs.pop(page)
+                        src.append(page)
+                        dst.append(new_page)
+                        pt.assign(r, h, t, new_page)
+                        self.tile_to_page_map_[(r, h, t)] = new_page
+        dev = self.key_buffer_.device
+        if src:
+            d_src = torch.tensor(src, dtype=torch.int32).to(dev)
+            d_dst = torch.tensor(dst, dtype=torch.int32).to(dev)
+            with torch.cuda.device(dev):
+                _cabi.check(_cabi.lib().pa_kv_copy_pages(
+                    self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), _cabi.ptr(self.k_scales_),
+                    _cabi.ptr(self.v_scales_), d_src.data_ptr(), d_dst.data_ptr(), len(src), self.total_pages_,
+                    self.tile_size_, self.head_dim_, self.key_buffer_.element_size(), _cabi.stream()),
+                    "pa_kv_copy_pages")
+        d_pos = torch.tensor(pos_h, dtype=torch.int32).to(dev)
+        d_beam = None if beam_ids is None else torch.tensor(rows, dtype=torch.int32).to(dev)
+        self.append(new_k, new_v, d_pos, d_beam)
+        return len(src)
 
     # ---- hot path: gather (KVTileCache::get materialised, hpp:21-26) ----------------------
     def gather(self, which="k", beam_ids=None, rows=None, fill_byte=0):

@@ -347,6 +347,67 @@ def test_group_decode_poisoned_tail_and_unsupported(ld, oracle):
         ld.paged_decode_group(q64, torch.empty_like(q64), k64, 2, 64, 2, 1.0)             # head_dim 64
 
 
+def test_beam_fork_copy_on_write(ld, oracle):
+    """Beam search over shared-prefix pages: fork_beam shares page ids (no bytes move), append_cow
+    copies a shared page before the first divergent write; dense per-beam K/V histories gathered
+    through the table must equal a host simulation, and the group kernel must agree with the oracle."""
+    rng = np.random.default_rng(71)
+    W, H, D, ts, nt = 4, 2, 128, 16, 4
+    kvc = ld.KVTileCache("f16")
+    kvc.init(64, ts, D)
+    kvc.configure_table(W, H, nt)
+    hist_k = [[] for _ in range(W)]   # per beam: list of [H, D] fp16 rows
+    hist_v = [[] for _ in range(W)]
+
+    def append(beams, pos, cow):
+        R = len(beams)
+        nk = rng.standard_normal((R, H, D)).astype(np.float16)
+        nv = rng.standard_normal((R, H, D)).astype(np.float16)
+        for i, b in enumerate(beams):
+            hist_k[b].append(nk[i]); hist_v[b].append(nv[i])
+        for b in beams:
+            for h in range(H):
+                if kvc.page_table_.lookup(b, h, pos // ts) < 0:
+                    kvc.register_tile(b, h, pos // ts)
+        args = (torch.from_numpy(nk).cuda(), torch.from_numpy(nv).cuda())
+        if cow:
+            return kvc.append_cow(*args, [pos] * R, beams)
+        kvc.append(*args, torch.full((R,), pos, dtype=torch.int32, device="cuda"),
+                   torch.tensor(beams, dtype=torch.int32, device="cuda"))
+        return 0
+
+    for pos in range(40):                      # beam 0 alone: 2.5 tiles
+        append([0], pos, cow=False)
+    for b in (1, 2, 3):                        # fork: share all of beam 0's pages
+        kvc.fork_beam(0, b)
+        hist_k[b] = list(hist_k[0]); hist_v[b] = list(hist_v[0])
+    tb = kvc.page_table_.device_data().cpu().numpy().reshape(W, H, nt)
+    assert (tb[1:] == tb[0]).all() and kvc.page_refcount(tb[0, 0, 2]) == 4
+    free_before = len(kvc._free)
+    copies = append([0, 1, 2, 3], 40, cow=True)  # divergent write into the shared third tile
+    assert copies == 3 * H                      # the last holder writes in place
+    assert len(kvc._free) == free_before - copies
+    tb = kvc.page_table_.device_data().cpu().numpy().reshape(W, H, nt)
+    assert (tb[1:, :, :2] == tb[0, :, :2]).all()                      # full prefix tiles still shared
+    assert len({int(x) for x in tb[:, 0, 2]}) == 4                    # third tile now private per beam
+    for pos in range(41, 50):                   # keep decoding: tile 3 gets registered privately
+        assert append([0, 1, 2, 3], pos, cow=True) == 0
+    T = 50
+    tb = kvc.page_table_.device_data().cpu().numpy().reshape(W, H, nt)
+    kp, vp = kvc.key_buffer_.cpu().numpy(), kvc.value_buffer_.cpu().numpy()
+    dense_k = oracle.cpu.gather_pages(kp, tb, W, H, nt, ts, D)
+    dense_v = oracle.cpu.gather_pages(vp, tb, W, H, nt, ts, D)
+    for b in range(W):
+        np.testing.assert_array_equal(dense_k[b, :, :T], np.stack(hist_k[b], axis=1))
+        np.testing.assert_array_equal(dense_v[b, :, :T], np.stack(hist_v[b], axis=1))
+    q = rng.standard_normal((W, H, D)).astype(np.float32)
+    exp = oracle.cpu.paged_attention(q, kp.astype(np.float32), vp.astype(np.float32), tb, num_beams=W, num_tiles=nt,
+                                     tile_size=ts, T=T, temperature=float(np.sqrt(D)))
+    out = torch.empty((W, H, D), device="cuda")
+    ld.paged_decode_group(torch.from_numpy(q).cuda(), out, kvc, W, T, W, float(np.sqrt(D)))
+    np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
+
+
 # ------------------------------------------------------------------ full-size properties (C2 shape)
 def test_c2_full_size_properties(ld, oracle):
     """BASELINE config C2 (B=64, H=32, D=128, T=4096, 16-token pages): too big for the CPU
