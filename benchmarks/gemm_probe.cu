@@ -9,23 +9,30 @@ unsigned long long* pa_gemm_probe_buf = nullptr;
 
 int main(int argc, char** argv) {
     int M = argc > 1 ? atoi(argv[1]) : 256, N = argc > 2 ? atoi(argv[2]) : 16384, K = argc > 3 ? atoi(argv[3]) : 4096;
-    int8_t *A, *B, *C;
-    cudaMalloc(&A, (size_t)M * K); cudaMalloc(&B, (size_t)K * N); cudaMalloc(&C, (size_t)M * N);
-    cudaMemset(A, 1, (size_t)M * K); cudaMemset(B, 1, (size_t)K * N);
+    int8_t *A, *B[4], *C;
+    cudaMalloc(&A, (size_t)M * K); cudaMalloc(&C, (size_t)M * N);
+    for (int i = 0; i < 4; ++i) { cudaMalloc(&B[i], (size_t)K * N); cudaMemset(B[i], 1, (size_t)K * N); }
+    cudaMemset(A, 1, (size_t)M * K);
     cudaMalloc(&pa_gemm_probe_buf, 64); cudaMemset(pa_gemm_probe_buf, 0, 64);
-    void* flush; cudaMalloc(&flush, 256 << 20);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9, sum = 0; int iters = 20;
     for (int it = 0; it < iters + 5; ++it) {
-        cudaMemsetAsync(flush, it, 256 << 20, 0);
         cudaEventRecord(e0, 0);
-        int st = pa_gemm_i8(A, B, C, nullptr, 1, M, N, K, 1.f, 1.f, 1.f, nullptr, 0, nullptr);
+        int st = pa_gemm_i8(A, B[it & 3], C, nullptr, 1, M, N, K, 1.f, 1.f, 1.f, nullptr, 0, nullptr);
         cudaEventRecord(e1, 0);
         cudaEventSynchronize(e1);
         if (st) { printf("status %d\n", st); return 1; }
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (it >= 5) { sum += ms; if (ms < best) best = ms; }
     }
+    // back-to-back launches (4 weight copies round-robin, no sync in between): device time per launch
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, 0);
+    for (int it = 0; it < 40; ++it) pa_gemm_i8(A, B[it & 3], C, nullptr, 1, M, N, K, 1.f, 1.f, 1.f, nullptr, 0, nullptr);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms40; cudaEventElapsedTime(&ms40, e0, e1);
+    printf("back-to-back: %.2f us per launch\n", ms40 / 40 * 1e3);
     unsigned long long h[8]; cudaMemcpy(h, pa_gemm_probe_buf, 64, cudaMemcpyDeviceToHost);
     printf("M=%d N=%d K=%d stages=%d: avg %.2f us  min %.2f us | cta5: producer wait %llu / %llu cyc, mma wait %llu / %llu cyc | setup %llu, mainloop(epi view) %llu, epilogue %llu cyc\n",
            M, N, K, pa::gemm::STAGES, sum / iters * 1e3, best * 1e3, h[0], h[2], h[1], h[3], h[4], h[5], h[6]);

@@ -157,6 +157,31 @@ __device__ __forceinline__ int epilogue_one(int acc, float alpha, float bias) {
     return (int)v;
 }
 
+// Same result as epilogue_one for finite inputs, in fewer instructions: cvt.rni.sat.s8.f32 rounds to
+// nearest-even and saturates to [-128, 127] in one step.
+template <int ACT>
+__device__ __forceinline__ uint32_t epilogue_s8(int acc, float alpha, float bias) {
+    float v = __fadd_rn(__fmul_rn(alpha, (float)acc), bias);
+    if (ACT == PA_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (ACT == PA_ACT_GELU) v = gelu_erf(v);
+    uint32_t q;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(v));
+    return q;
+}
+__device__ __forceinline__ uint32_t pack_s8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return (a & 0xffu) | ((b & 0xffu) << 8) | ((c & 0xffu) << 16) | (d << 24);
+}
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
 // EPI: 0 = integer outputs only (raw s32 and/or split-K reduction), 1/2/3 = s8 output with
 // activation none/relu/gelu (plus optional raw s32).
 // CL: thread-block cluster size along N.  The CL CTAs of a cluster work on adjacent B slabs and
@@ -370,6 +395,284 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------- 2-CTA kernel (M > 128)
+// CTA pair (cluster of 2) = one UMMA M=256 x N=256 tile: tcgen05.mma.cta_group::2.kind::i8 issued
+// by the leader reads A rows 0-127 / 128-255 and B columns 0-127 / 128-255 from the two CTAs'
+// shared memories, so per 128-byte K block each SM ingests 16 KB of A + 16 KB of B for
+// 128 x 256 x 128 MACs -- 1.5x less L2->SM traffic per MAC than the single-CTA 2x(128x128) form,
+// which is what bounds this GEMM (measured: the chip-wide L2 output cap, ~43 B/clk/SM, not HBM or
+// the tensor pipe; profiles/r01_gemm_notes.md).  6 stages x 32 KB ring per CTA; both CTAs'
+// TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor.cta_group::2), the
+// leader's tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
+// Epilogue: 8 warps (two per TMEM lane quarter, 128 columns each).
+constexpr int BN2 = 256;                      // columns per CTA pair
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = 2 * TILE_BYTES;  // A half (128 rows) + B half (128 columns)
+constexpr int NTHREADS2 = 320;
+constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                             ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_remote_arrive_expect_tx(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
+gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + STAGES2 * STAGE2_BYTES;  // full[S], empty[S], tmem_full
+    const uint32_t tmem_slot = bar0 + (2 * STAGES2 + 1) * 8;
+    auto full_bar = [&](int s) { return bar0 + s * 8; };
+    auto empty_bar = [&](int s) { return bar0 + (STAGES2 + s) * 8; };
+    const uint32_t tmem_full_bar = bar0 + 2 * STAGES2 * 8;
+
+#ifdef PA_GEMM_PROBE
+    const long long t_entry = clock64();
+    const bool probe_cta = blockIdx.x == 10 && blockIdx.y == 0 && g.probe;
+#endif
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int n0 = (blockIdx.x >> 1) * BN2;
+    const int m_chunk = blockIdx.y / g.ksplit, split = blockIdx.y % g.ksplit;
+    const int m0 = m_chunk * 2 * BM;
+    const int batch = blockIdx.z;
+    const int total_kb = (g.K + BK - 1) / BK;
+    const int kb0 = split * g.kb_per_split;
+    const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 2);   // one arrive.expect_tx from each CTA's producer (leader's copy is used)
+            mbar_init(empty_bar(s), 1);  // the leader's commit, multicast to both CTAs
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB));
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, BN2);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+#ifdef PA_GEMM_PROBE
+    const long long t_setup = clock64();
+    if (threadIdx.x == 0 && probe_cta) g.probe[4] = t_setup - t_entry;
+    long long pw = 0, mw = 0;
+#endif
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES2;
+#ifdef PA_GEMM_PROBE
+                const long long tw0 = clock64();
+#endif
+                mbar_wait(empty_bar(s), ((i / STAGES2) & 1) ^ 1);
+#ifdef PA_GEMM_PROBE
+                pw += clock64() - tw0;
+#endif
+                const uint32_t st = base + s * STAGE2_BYTES;
+                const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                if (crank == 0) mbar_arrive_expect_tx(full_bar(s), STAGE2_BYTES);
+                else mbar_remote_arrive_expect_tx(lead_full, STAGE2_BYTES);
+                const int k0 = (kb0 + i) * BK;
+                tma_load_3d_2cta(st, &tmA, k0, m0 + (int)crank * BM, batch, lead_full);
+                tma_load_3d_2cta(st + TILE_BYTES, &tmB, n0 + (int)crank * BN, k0, batch, lead_full);
+            }
+#ifdef PA_GEMM_PROBE
+            if (probe_cta) { g.probe[0] = pw; g.probe[2] = clock64() - t_setup; }
+#endif
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES2;
+#ifdef PA_GEMM_PROBE
+                const long long tw0 = clock64();
+#endif
+                mbar_wait(full_bar(s), (i / STAGES2) & 1);
+#ifdef PA_GEMM_PROBE
+                mw += clock64() - tw0;
+#endif
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE2_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / UK; ++ks) {
+                    const uint64_t da = make_desc(st + ks * UK, 16, 1024);
+                    const uint64_t db = make_desc(st + TILE_BYTES + ks * UK * BK, TILE_BYTES, 1024);
+                    umma_i8_2cta(tmem_base, da, db, kIdesc2, (i > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit_2cta(empty_bar(s));
+            }
+            umma_commit_2cta(tmem_full_bar);
+#ifdef PA_GEMM_PROBE
+            if (probe_cta) { g.probe[1] = mw; g.probe[3] = clock64() - t_setup; }
+#endif
+        }
+    } else {
+        constexpr int ACT = EPI == 2 ? PA_ACT_RELU : (EPI == 3 ? PA_ACT_GELU : PA_ACT_NONE);
+        const int qtr = warp & 3;             // TMEM lane quarter this warp may read
+        const int chalf = (warp - 2) >> 2;    // which 128 columns of the 256
+        // While the main loop runs: stage this warp's 128 bias values in shared memory (the epilogue
+        // then reads them as broadcasts instead of 8 dependent L2 round trips per chunk).
+        float* bias_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 128 - smem_u32(smem_raw))) + (warp - 2) * 128;  // 16 B aligned
+        if (EPI != 0) {
+            const int c = n0 + chalf * 128 + lane * 4;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias && c < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+            *reinterpret_cast<float4*>(bias_sm + lane * 4) = bv;
+            __syncwarp();
+        }
+        const int row = m0 + (int)crank * BM + qtr * 32 + lane;
+        const bool row_ok = row < g.M;
+        const int64_t out_row = ((int64_t)batch * g.M + row) * g.N;
+        const float alpha = (g.a_qscale && row_ok) ? __fdiv_rn(g.alpha, __ldg(g.a_qscale + (int64_t)batch * g.M + row))
+                                                   : g.alpha;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#ifdef PA_GEMM_PROBE
+        const long long t_epi0 = clock64();
+#endif
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+            // two 32-column chunks per TMEM round trip
+            uint32_t rr[2][32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + chalf * 128 + c2 * 64;
+            tmem_ld_32x32_nowait(taddr, rr[0]);
+            tmem_ld_32x32_nowait(taddr + 32, rr[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            if (g.acc_ws) {
+                // Split-K partial tile: transpose the warp's 32 rows x 64 columns through shared memory
+                // (the ring is idle once the accumulator is complete) so that every store instruction
+                // writes 256 contiguous bytes of 2 rows instead of 16 bytes of 32 rows.
+                uint32_t* tsm = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw))) + (warp - 2) * (32 * 65);
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tsm[lane * 65 + hc * 32 + j] = rr[hc][j];
+                }
+                __syncwarp();
+                const int colbase = n0 + chalf * 128 + c2 * 64;
+                const int rbase = m0 + (int)crank * BM + qtr * 32;
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const int rl = it * 2 + (lane >> 4);
+                    const int cw = (lane & 15) * 4;
+                    const int grow = rbase + rl;
+                    if (grow < g.M && colbase + cw < g.N) {
+                        const uint32_t* sp = tsm + rl * 65 + cw;
+                        int32_t* wp = g.acc_ws + (int64_t)split * g.BATCH_rows * g.N +
+                                      ((int64_t)batch * g.M + grow) * g.N + colbase + cw;
+                        __stcg(reinterpret_cast<int4*>(wp), make_int4((int)sp[0], (int)sp[1], (int)sp[2], (int)sp[3]));
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+                uint32_t(&r)[32] = rr[hc];
+                const int cc = c2 * 2 + hc;
+                const int col0 = n0 + chalf * 128 + cc * 32;
+                if (!row_ok || col0 >= g.N) continue;
+                const bool hi_ok = col0 + 32 <= g.N;
+                if (g.acc_ws) continue;  // split-K partial tiles: coalesced path below
+                if (g.C32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < 16 || hi_ok)
+                            *reinterpret_cast<int4*>(g.C32 + out_row + col0 + j) =
+                                make_int4((int)r[j], (int)r[j + 1], (int)r[j + 2], (int)r[j + 3]);
+                }
+                if (EPI != 0 && g.Cf) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        if (w < 4 || hi_ok) {
+                            const float4 bj = *reinterpret_cast<const float4*>(bias_sm + cc * 32 + 4 * w);
+                            *reinterpret_cast<float4*>(g.Cf + out_row + col0 + 4 * w) =
+                                make_float4(epilogue_f32<ACT>((int)r[4 * w + 0], alpha, bj.x),
+                                            epilogue_f32<ACT>((int)r[4 * w + 1], alpha, bj.y),
+                                            epilogue_f32<ACT>((int)r[4 * w + 2], alpha, bj.z),
+                                            epilogue_f32<ACT>((int)r[4 * w + 3], alpha, bj.w));
+                        }
+                    }
+                } else if (EPI != 0) {
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const float4 bj = *reinterpret_cast<const float4*>(bias_sm + cc * 32 + 4 * w);
+                        packed[w] = pack_s8x4(epilogue_s8<ACT>((int)r[4 * w + 0], alpha, bj.x),
+                                              epilogue_s8<ACT>((int)r[4 * w + 1], alpha, bj.y),
+                                              epilogue_s8<ACT>((int)r[4 * w + 2], alpha, bj.z),
+                                              epilogue_s8<ACT>((int)r[4 * w + 3], alpha, bj.w));
+                    }
+                    *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (hi_ok)
+                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+        }
+#ifdef PA_GEMM_PROBE
+        if (warp == 2 && lane == 0 && probe_cta) {
+            g.probe[5] = t_epi0 - t_setup;
+            g.probe[6] = clock64() - t_epi0;
+        }
+#endif
+    }
+#ifdef PA_GEMM_PROBE
+    if (warp == 2 && lane == 0 && probe_cta) {
+        // (epilogue warps only reach here with t_epi0 defined)
+    }
+#endif
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // the peer may still be reading its accumulators / signalling this CTA's barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, BN2);
+    }
+}
+
 // Split-K second pass: sum the ksplit partial tiles (exact int32), then C32 copy and/or C8 epilogue.
 template <int ACT>
 __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
@@ -466,7 +769,8 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     if (!di.ok) return PA_ERR_NO_DEVICE;
     cudaStream_t st = as_stream(stream);
 
-    const int n_slabs = (N + BN - 1) / BN;
+    const bool two_cta = M > BM && !(getenv("PA_GEMM_2CTA") && atoi(getenv("PA_GEMM_2CTA")) == 0);
+    const int n_slabs = two_cta ? (N + BN2 - 1) / BN2 : (N + BN - 1) / BN;
     const int m_chunks = (M + 2 * BM - 1) / (2 * BM);
     const int m_tiles0 = M > BM ? 2 : 1;
     // Cluster multicast of A needs one M chunk (uniform m_tiles) and n_slabs divisible by CL.
@@ -474,19 +778,20 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     // Measured (profiles/r01_gemm_notes.md): equal speed for CL = 1/2/4 at the C4 shapes -- the
     // loop is bound by B bytes in flight, not by L2 reads -- so default to pairs, which cut the
     // L2 read traffic for A in half and never strand SMs.  PA_GEMM_CLUSTER=1|2|4 overrides.
-    if (m_chunks == 1) {
+    if (m_chunks == 1 && !two_cta) {
         if (n_slabs % 4 == 0) CLs = 4;
         else if (n_slabs % 2 == 0) CLs = 2;
     }
     const int cl_max = CLs;
     if (CLs > 2) CLs = 2;
     const char* cl_env = getenv("PA_GEMM_CLUSTER");
-    if (cl_env) {
+    if (cl_env && !two_cta) {
         const int want = atoi(cl_env);
         if (want == 1 || (want == 2 && cl_max >= 2) || (want == 4 && cl_max == 4)) CLs = want;
     }
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, CLs == 1 ? BM : m_tiles0 * BM / CLs))
+    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH,
+                  (two_cta || CLs == 1) ? BM : m_tiles0 * BM / CLs))
         return PA_ERR_UNSUPPORTED;
     if (!make_map(&tmB, d_B, (uint64_t)N, (uint64_t)K, (uint64_t)BATCH, BK)) return PA_ERR_UNSUPPORTED;
 
@@ -504,7 +809,7 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     g.probe = pa_gemm_probe_buf;
 #endif
     const int total_kb = (K + BK - 1) / BK;
-    const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH;
+    const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH * (two_cta ? 2 : 1);
     int ksplit = (int)(di.sm_count / ctas);
     if (ksplit > total_kb / 8) ksplit = total_kb / 8;  // >= 8 K blocks (1 KiB of K) per split
     if (ksplit < 1) ksplit = 1;
@@ -526,39 +831,58 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         g.acc_ws = sc.p;
     }
     g.BATCH_rows = rows;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
     const int epi = (ksplit > 1 || !(d_C_s8 || d_C_f32)) ? 0 : 1 + act;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
-    static const KernelFn kernels[3][4] = {
-        {gemm_i8_kernel<0, 1>, gemm_i8_kernel<1, 1>, gemm_i8_kernel<2, 1>, gemm_i8_kernel<3, 1>},
-        {gemm_i8_kernel<0, 2>, gemm_i8_kernel<1, 2>, gemm_i8_kernel<2, 2>, gemm_i8_kernel<3, 2>},
-        {gemm_i8_kernel<0, 4>, gemm_i8_kernel<1, 4>, gemm_i8_kernel<2, 4>, gemm_i8_kernel<3, 4>}};
-    const int cli = CLs == 4 ? 2 : (CLs == 2 ? 1 : 0);
-    KernelFn kern = kernels[cli][epi];
-    static bool attr_set[64][3][4] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr_set[dev & 63][cli][epi]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e;
+    if (two_cta) {
+        const size_t smem2 = (size_t)STAGES2 * STAGE2_BYTES + 128 + 8 * 128 * sizeof(float) + 1024;  // ring, barriers, bias, align
+        static const KernelFn kernels2[4] = {gemm_i8_2cta_kernel<0>, gemm_i8_2cta_kernel<1>, gemm_i8_2cta_kernel<2>,
+                                             gemm_i8_2cta_kernel<3>};
+        KernelFn kern = kernels2[epi];
+        static bool attr_set2[64][4] = {};
+        if (!attr_set2[dev & 63][epi]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+            attr_set2[dev & 63][epi] = true;
+        }
+        // cluster dims (2,1,1) are compiled into the kernel (__cluster_dims__)
+        kern<<<dim3((unsigned)(2 * n_slabs), (unsigned)(m_chunks * ksplit), (unsigned)BATCH), NTHREADS2, smem2, st>>>(
+            tmA, tmB, g);
+        e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
-        attr_set[dev & 63][cli][epi] = true;
+    } else {
+        const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+        static const KernelFn kernels[3][4] = {
+            {gemm_i8_kernel<0, 1>, gemm_i8_kernel<1, 1>, gemm_i8_kernel<2, 1>, gemm_i8_kernel<3, 1>},
+            {gemm_i8_kernel<0, 2>, gemm_i8_kernel<1, 2>, gemm_i8_kernel<2, 2>, gemm_i8_kernel<3, 2>},
+            {gemm_i8_kernel<0, 4>, gemm_i8_kernel<1, 4>, gemm_i8_kernel<2, 4>, gemm_i8_kernel<3, 4>}};
+        const int cli = CLs == 4 ? 2 : (CLs == 2 ? 1 : 0);
+        KernelFn kern = kernels[cli][epi];
+        static bool attr_set[64][3][4] = {};
+        if (!attr_set[dev & 63][cli][epi]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[dev & 63][cli][epi] = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)n_slabs, (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CLs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)n_slabs, (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)CLs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
     if (ksplit > 1) {
         const int64_t n4 = rows * N / 4;
         int blocks = (int)((n4 + 255) / 256);
