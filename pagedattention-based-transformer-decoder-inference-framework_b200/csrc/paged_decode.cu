@@ -107,12 +107,19 @@ __device__ __forceinline__ void words_to_float(const uint32_t (&w)[W], float* f)
             f[2 * i + 1] = t.y;
         }
     } else {
+        // int8 -> f32 without the conversion unit (I2F runs at quarter rate and bounded this kernel at
+        // 2.3 TB/s).  Flip the sign bit (u = b + 128 in [0, 255]) and drop the byte into mantissa bits
+        // 8..15 of 2^15 with ONE PRMT: the float is exactly 32768 + u = b + 32896.  The constant is
+        // folded out by the caller: sum_e q_e b_e = sum_e q_e f_e - 32896 sum_e q_e, so the inner loop
+        // is one PRMT + one FFMA per element (costs ~8 mantissa bits of the partial sums; the offset is
+        // removed per 16-token unit so it never accumulates).
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            f[4 * i + 0] = (float)(int8_t)(w[i] & 0xff);
-            f[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xff);
-            f[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xff);
-            f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
+            const uint32_t x = w[i] ^ 0x80808080u;
+            f[4 * i + 0] = __uint_as_float(__byte_perm(x, 0x47000000u, 0x7404));
+            f[4 * i + 1] = __uint_as_float(__byte_perm(x, 0x47000000u, 0x7414));
+            f[4 * i + 2] = __uint_as_float(__byte_perm(x, 0x47000000u, 0x7424));
+            f[4 * i + 3] = __uint_as_float(__byte_perm(x, 0x47000000u, 0x7434));
         }
     }
 }
@@ -124,14 +131,14 @@ template <int D, int KV>
 __device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::W],
                                             uint32_t (&vf)[4][Cfg<D, KV>::W], const float (&ksc)[4],
                                             const float (&vsc)[4], const float (&q)[Cfg<D, KV>::E],
-                                            int nvalid, int g, Acc<D, KV>& a) {
+                                            float qoff, int nvalid, int g, Acc<D, KV>& a) {
     using C = Cfg<D, KV>;
     float s[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         float f[C::E];
         words_to_float<KV, C::W>(kf[p], f);
-        float acc = 0.f;
+        float acc = qoff;  // int8: qoff = -32896 * sum_e q_e (see words_to_float); fp16: 0
 #pragma unroll
         for (int e = 0; e < C::E; ++e) acc = fmaf(q[e], f[e], acc);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -155,14 +162,21 @@ __device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::
         a.m = m_new;
 #pragma unroll
         for (int e = 0; e < C::E; ++e) a.o[e] *= corr;
+        float wsum = 0.f;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             if (4 * p + g >= nvalid) continue;  // never touch bytes past the context end
             float f[C::E];
             words_to_float<KV, C::W>(vf[p], f);
             const float w = (KV == 1) ? pw[p] * vsc[p] : pw[p];
+            if (KV == 1) wsum += w;
 #pragma unroll
             for (int e = 0; e < C::E; ++e) a.o[e] = fmaf(w, f[e], a.o[e]);
+        }
+        if (KV == 1) {  // sum_p w_p b = sum_p w_p f - 32896 sum_p w_p
+            const float off = -32896.f * wsum;
+#pragma unroll
+            for (int e = 0; e < C::E; ++e) a.o[e] += off;
         }
     }
 }
@@ -248,8 +262,8 @@ __device__ __forceinline__ void cta_merge_emit(float* red, Acc<D, KV>& acc, int 
 
 // q row -> registers, pre-scaled; optional pairwise RoPE (cpu_attention_kernel.cpp:13-19).
 template <int D, int KV>
-__device__ __forceinline__ void load_q(const DecodeArgs& a, int64_t row, int c,
-                                       float (&q)[Cfg<D, KV>::E]) {
+__device__ __forceinline__ float load_q(const DecodeArgs& a, int64_t row, int c,
+                                        float (&q)[Cfg<D, KV>::E]) {
     using C = Cfg<D, KV>;
     const float* qr = a.q + row * D;
 #pragma unroll
@@ -265,6 +279,12 @@ __device__ __forceinline__ void load_q(const DecodeArgs& a, int64_t row, int c,
         q[e] = x0 * a.qscale;
         q[e + 1] = x1 * a.qscale;
     }
+    if (KV == 0) return 0.f;
+    // int8 pages: fold the +256 offset of the PRMT conversion (words_to_float) out of the inner loop
+    float qs = 0.f;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) qs += q[e];
+    return -32896.f * qs;
 }
 
 __device__ __forceinline__ int row_ctx(const DecodeArgs& a, int b) {
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeAr
     const int upt = a.tile_size / kUnitTok;
 
     float q[C::E];
-    load_q<D, KV>(a, row, c, q);
+    const float qoff = load_q<D, KV>(a, row, c, q);
     Acc<D, KV> acc;
     acc.reset();
 
@@ -337,7 +357,7 @@ __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeAr
                 vsc[p] = __frcp_rn(__ldg(a.v_scales + tok0 + t));
             }
         }
-        unit_update<D, KV>(kf, vf, ksc, vsc, q, nvalid, g, acc);
+        unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
     }
 
     const bool final_row = (a.num_splits == 1);
@@ -538,7 +558,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         const int64_t row = (int64_t)b * a.H + h;
         const int u0 = j * cu;
         const int u1 = min(units_of_ctx(row_ctx(a, b)), u0 + cu);
-        load_q<D, KV>(a, row, c, q);
+        const float qoff = load_q<D, KV>(a, row, c, q);
         acc.reset();
 #pragma unroll 1
         for (int u = u0; u < u1; ++u) {
@@ -574,7 +594,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
                         vsc[p] = __frcp_rn(vs);
                     }
                 }
-                unit_update<D, KV>(kf, vf, ksc, vsc, q, nvalid, g, acc);
+                unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
             }
             __syncwarp();
             ++consumed;
@@ -1180,7 +1200,14 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 constexpr int kOvWarps = 8;
 template <int D, int KV>
 struct OvCfg {
-    static constexpr int S = (KV == 0 && D == 128) ? 3 : ((KV == 0 || D == 128) ? 6 : 8);
+    // fp16: 8 streaming warps x 3 stages of 8 KB.  int8: twice the math per byte (and the kernel is
+    // issue/latency bound, not HBM bound), so 16 warps x 3 stages of 4 KB: same bytes in flight, twice
+    // the thread-level parallelism.  PA_OV_I8_WARPS overrides at build time for experiments.
+#ifndef PA_OV_I8_WARPS
+#define PA_OV_I8_WARPS 16
+#endif
+    static constexpr int NW = (KV == 1 && D == 128) ? PA_OV_I8_WARPS : 8;
+    static constexpr int S = (D == 128) ? (KV == 0 ? 3 : (NW == 16 ? 3 : 6)) : (KV == 0 ? 6 : 8);
 };
 
 static int units_of_ctx_host(int T, int cap) {
@@ -1260,15 +1287,16 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     const int G = di.sm_count;
     const int cu = choose_cu(rows, max_units, di.sm_count);
     const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
-    const size_t smem = (size_t)kOvWarps * S * C::STAGE_BYTES + (size_t)kOvWarps * S * (8 + 4) + 8 +
-                        (size_t)kOvWarps * 16 * sizeof(int64_t) + prefix_bytes;
+    constexpr int NWk = OvCfg<D, KV>::NW;
+    const size_t smem = (size_t)NWk * S * C::STAGE_BYTES + (size_t)NWk * S * (8 + 4) + 8 +
+                        (size_t)NWk * 16 * sizeof(int64_t) + prefix_bytes;
     if (smem > (size_t)di.max_smem_optin) return PA_ERR_UNSUPPORTED;  // B too large for the prefix table
-    auto kern = paged_decode_overlap_kernel<D, KV, kOvWarps, S>;
+    auto kern = paged_decode_overlap_kernel<D, KV, NWk, S>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
-    kern<<<G, kOvWarps * 32, smem, st>>>(a, cu, counter);
+    kern<<<G, NWk * 32, smem, st>>>(a, cu, counter);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // Rows of a single chunk were finished by the main kernel; everything else is merged here.
