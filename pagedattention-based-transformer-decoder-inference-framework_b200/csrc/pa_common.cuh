@@ -44,6 +44,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// 1/x to ~1 ulp on the MUFU unit without the Newton fix-up of __frcp_rn (dequantisation scales:
+// q * (1/scale) instead of q / scale differs from the oracle's IEEE division by <= 2 ulp).
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -127,11 +127,11 @@ __device__ __forceinline__ void words_to_float(const uint32_t (&w)[W], float* f)
 // One 16-token unit: 4 token rows per lane group.  kf/vf: this lane's words of rows
 // 4p+g.  ksc/vsc: reciprocal scales of those rows (int8 only).  Scores are in log2
 // units (q pre-multiplied by log2(e)/temperature).
-template <int D, int KV>
-__device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::W],
-                                            uint32_t (&vf)[4][Cfg<D, KV>::W], const float (&ksc)[4],
-                                            const float (&vsc)[4], const float (&q)[Cfg<D, KV>::E],
-                                            float qoff, int nvalid, int g, Acc<D, KV>& a) {
+template <int D, int KV, bool FULL>
+__device__ __forceinline__ void unit_update_impl(const uint32_t (&kf)[4][Cfg<D, KV>::W],
+                                                 uint32_t (&vf)[4][Cfg<D, KV>::W], const float (&ksc)[4],
+                                                 const float (&vsc)[4], const float (&q)[Cfg<D, KV>::E],
+                                                 float qoff, int nvalid, int g, Acc<D, KV>& a) {
     using C = Cfg<D, KV>;
     float s[4];
 #pragma unroll
@@ -145,40 +145,53 @@ __device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         if (KV == 1) acc *= ksc[p];
-        s[p] = (4 * p + g < nvalid) ? acc : -INFINITY;
+        s[p] = (FULL || 4 * p + g < nvalid) ? acc : -INFINITY;
     }
     const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-    if (mx > -INFINITY) {
-        const float m_new = fmaxf(a.m, mx);
-        const float corr = fast_exp2(a.m - m_new);  // a.m == -inf -> 0
-        float pw[4];
-        float ps = 0.f;
+    // Partial unit: a lane group whose rows are all past the context end keeps its state (no early
+    // return: the warp votes below).
+    const bool dead = !FULL && !(mx > -INFINITY);
+    const float m_new = dead ? a.m : fmaxf(a.m, mx);
+    const float corr = dead ? 1.f : fast_exp2(a.m - m_new);  // a.m == -inf -> 0
+    float pw[4];
+    float ps = 0.f;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            pw[p] = fast_exp2(s[p] - m_new);  // masked rows -> 0
-            ps += pw[p];
-        }
-        a.l = fmaf(a.l, corr, ps);
-        a.m = m_new;
+    for (int p = 0; p < 4; ++p) {
+        pw[p] = dead ? 0.f : fast_exp2(s[p] - m_new);  // masked rows -> 0
+        ps += pw[p];
+    }
+    a.l = fmaf(a.l, corr, ps);
+    a.m = m_new;
+    if (__any_sync(0xffffffffu, corr != 1.f)) {  // the running max settles after a few units
 #pragma unroll
         for (int e = 0; e < C::E; ++e) a.o[e] *= corr;
-        float wsum = 0.f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            if (4 * p + g >= nvalid) continue;  // never touch bytes past the context end
-            float f[C::E];
-            words_to_float<KV, C::W>(vf[p], f);
-            const float w = (KV == 1) ? pw[p] * vsc[p] : pw[p];
-            if (KV == 1) wsum += w;
-#pragma unroll
-            for (int e = 0; e < C::E; ++e) a.o[e] = fmaf(w, f[e], a.o[e]);
-        }
-        if (KV == 1) {  // sum_p w_p b = sum_p w_p f - 32896 sum_p w_p
-            const float off = -32896.f * wsum;
-#pragma unroll
-            for (int e = 0; e < C::E; ++e) a.o[e] += off;
-        }
     }
+    float wsum = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (!FULL && 4 * p + g >= nvalid) continue;  // never touch bytes past the context end
+        float f[C::E];
+        words_to_float<KV, C::W>(vf[p], f);
+        const float w = (KV == 1) ? pw[p] * vsc[p] : pw[p];
+        if (KV == 1) wsum += w;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) a.o[e] = fmaf(w, f[e], a.o[e]);
+    }
+    if (KV == 1) {  // sum_p w_p b = sum_p w_p f - 32896 sum_p w_p
+        const float off = -32896.f * wsum;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) a.o[e] += off;
+    }
+}
+
+// Full 16-token units (all but possibly the last unit of a row) take the branch-free path.
+template <int D, int KV>
+__device__ __forceinline__ void unit_update(const uint32_t (&kf)[4][Cfg<D, KV>::W],
+                                            uint32_t (&vf)[4][Cfg<D, KV>::W], const float (&ksc)[4],
+                                            const float (&vsc)[4], const float (&q)[Cfg<D, KV>::E],
+                                            float qoff, int nvalid, int g, Acc<D, KV>& a) {
+    if (nvalid == kUnitTok) unit_update_impl<D, KV, true>(kf, vf, ksc, vsc, q, qoff, nvalid, g, a);
+    else unit_update_impl<D, KV, false>(kf, vf, ksc, vsc, q, qoff, nvalid, g, a);
 }
 
 // Merge the 4 lane groups of a warp (xor 8, 16); afterwards every lane holds the
@@ -467,7 +480,14 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
     const int64_t total = cm.total();
     const int64_t total_warps = (int64_t)gridDim.x * NW;
     const int64_t gw = (int64_t)blockIdx.x * NW + warp;
-    const int upt = a.tile_size / kUnitTok;
+    // kernel parameters used per unit, hoisted out of the constant bank
+    const int tile_size = a.tile_size, upt = tile_size / kUnitTok, Hh = a.H, num_tiles = a.num_tiles;
+    const int total_pages = a.total_pages, num_beams = a.num_beams;
+    const uint8_t* const k_pool = a.k_pool;
+    const uint8_t* const v_pool = a.v_pool;
+    const float* const k_scales = a.k_scales;
+    const float* const v_scales = a.v_scales;
+    const bool evict_first = a.evict_first != 0;
     const uint64_t policy = l2_policy_evict_first();
 
     const uint32_t my_stage0 = smem_u32(stage_base + (size_t)warp * S * C::STAGE_BYTES);
@@ -475,11 +495,17 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
     int* my_meta = meta + warp * S;
     int64_t* my_cq = cq + warp * QN;
 
-    // ---- producer state (warp-uniform; lane 0 issues) ----
+    // ---- producer state (warp-uniform; lane 0 issues).  Everything that changes per unit is kept
+    // incrementally (no divisions / 64-bit index math in the steady state). ----
     bool p_has = false, p_first = true;
-    int p_b = 0, p_h = 0, p_u = 0, p_uend = 0, p_ctx = 0, p_beam = 0, p_page = -1;
-    uint32_t issued = 0, p_chunks = 0;
+    const int32_t* p_trow = nullptr;  // page-table row of (beam, head); null when the beam is out of range
+    int p_tile = 0, p_sub = 0, p_rem = 0, p_left = 0, p_page = -1;
+    uint32_t p_st = 0, p_chunks = 0;
 
+    auto p_fetch = [&]() {
+        int page = p_trow ? __ldg(p_trow + p_tile) : -1;  // page_table.hpp:44-49
+        p_page = ((unsigned)page < (unsigned)total_pages) ? page : -1;  // kv_tile_cache.hpp:23
+    };
     auto p_next_chunk = [&]() -> bool {
         int64_t id;
         if (p_first) {
@@ -492,53 +518,58 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
             id = total_warps + (int64_t)t;
         }
         if (id >= total) return false;
-        int j, nc;
-        cm.locate(id, p_b, p_h, j, nc);
-        p_ctx = row_ctx(a, p_b);
-        p_u = j * cu;
-        p_uend = min(units_of_ctx(p_ctx), p_u + cu);
-        p_beam = a.beam_ids ? a.beam_ids[p_b] : p_b;
+        int pb, ph, j, nc;
+        cm.locate(id, pb, ph, j, nc);
+        const int ctx = row_ctx(a, pb);
+        const int u0 = j * cu;
+        p_left = min(units_of_ctx(ctx), u0 + cu) - u0;
+        p_rem = ctx - u0 * kUnitTok;
+        p_tile = u0 / upt;
+        p_sub = u0 - p_tile * upt;
+        const int beam = a.beam_ids ? a.beam_ids[pb] : pb;
+        p_trow = ((unsigned)beam < (unsigned)num_beams) ? a.table + ((int64_t)beam * Hh + ph) * num_tiles : nullptr;
         if (lane == 0) my_cq[p_chunks % QN] = id;
         ++p_chunks;
         __syncwarp();
         return true;
     };
-    auto p_fetch = [&]() { p_page = lookup_page(a, p_beam, p_h, p_u / upt); };
 
     p_has = p_next_chunk();
     if (p_has) p_fetch();
 
     auto produce = [&]() {
         if (!p_has) return;
-        const uint32_t st = issued % S;
         if (lane == 0) {
-            const int nvalid = (p_page >= 0) ? min(kUnitTok, p_ctx - p_u * kUnitTok) : 0;
-            my_meta[st] = nvalid;
-            const uint32_t bar = my_bar0 + st * 8;
+            const int nvalid = (p_page >= 0) ? min(kUnitTok, p_rem) : 0;
+            my_meta[p_st] = nvalid;
+            const uint32_t bar = my_bar0 + p_st * 8;
             if (nvalid > 0) {
-                const int sub = p_u % upt;
-                const int64_t tok0 = (int64_t)p_page * a.tile_size + sub * kUnitTok;
-                const uint32_t dst = my_stage0 + st * C::STAGE_BYTES;
+                const int64_t tok0 = (int64_t)p_page * tile_size + p_sub * kUnitTok;
+                const uint32_t dst = my_stage0 + p_st * C::STAGE_BYTES;
                 fence_proxy_async();
                 mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
-                if (a.evict_first) {
-                    bulk_g2s(dst, a.k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
-                    bulk_g2s(dst + C::UNIT_BYTES, a.v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
+                if (evict_first) {
+                    bulk_g2s(dst, k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
+                    bulk_g2s(dst + C::UNIT_BYTES, v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar, policy);
                 } else {
-                    bulk_g2s_nohint(dst, a.k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
-                    bulk_g2s_nohint(dst + C::UNIT_BYTES, a.v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
+                    bulk_g2s_nohint(dst, k_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
+                    bulk_g2s_nohint(dst + C::UNIT_BYTES, v_pool + tok0 * C::ROWB, C::UNIT_BYTES, bar);
                 }
                 if (KV == 1) {
-                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES, a.k_scales + tok0, C::SCALE_BYTES, bar);
-                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES + C::SCALE_BYTES, a.v_scales + tok0, C::SCALE_BYTES, bar);
+                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES, k_scales + tok0, C::SCALE_BYTES, bar);
+                    bulk_g2s_nohint(dst + 2 * C::UNIT_BYTES + C::SCALE_BYTES, v_scales + tok0, C::SCALE_BYTES, bar);
                 }
             } else {
                 mbar_arrive(bar);
             }
         }
-        ++issued;
-        ++p_u;
-        if (p_u >= p_uend) p_has = p_next_chunk();
+        p_st = (p_st + 1 == S) ? 0u : p_st + 1;
+        p_rem -= kUnitTok;
+        if (++p_sub == upt) {
+            p_sub = 0;
+            ++p_tile;
+        }
+        if (--p_left == 0) p_has = p_next_chunk();
         if (p_has) p_fetch();
     };
 
@@ -546,7 +577,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
     for (int s = 0; s < S; ++s) produce();
 
     // ---- consumer ----
-    uint32_t consumed = 0, c_chunks = 0;
+    uint32_t c_st = 0, c_par = 0, c_chunks = 0;
     Acc<D, KV> acc;
     float q[C::E];
 
@@ -555,18 +586,17 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         ++c_chunks;
         int b, h, j, nc;
         cm.locate(id, b, h, j, nc);
-        const int64_t row = (int64_t)b * a.H + h;
+        const int64_t row = (int64_t)b * Hh + h;
         const int u0 = j * cu;
         const int u1 = min(units_of_ctx(row_ctx(a, b)), u0 + cu);
         const float qoff = load_q<D, KV>(a, row, c, q);
         acc.reset();
 #pragma unroll 1
         for (int u = u0; u < u1; ++u) {
-            const uint32_t st = consumed % S;
-            mbar_wait(my_bar0 + st * 8, (consumed / S) & 1);
-            const int nvalid = my_meta[st];
+            mbar_wait(my_bar0 + c_st * 8, c_par);
+            const int nvalid = my_meta[c_st];
             if (nvalid > 0) {
-                const uint32_t sb = my_stage0 + st * C::STAGE_BYTES;
+                const uint32_t sb = my_stage0 + c_st * C::STAGE_BYTES;
                 uint32_t kf[4][C::W], vf[4][C::W];
                 float ksc[4] = {1.f, 1.f, 1.f, 1.f}, vsc[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
@@ -590,14 +620,17 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
                         float ks, vs;
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ks) : "r"(sb + 2 * C::UNIT_BYTES + t * 4));
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vs) : "r"(sb + 2 * C::UNIT_BYTES + C::SCALE_BYTES + t * 4));
-                        ksc[p] = __frcp_rn(ks);
-                        vsc[p] = __frcp_rn(vs);
+                        ksc[p] = fast_rcp(ks);
+                        vsc[p] = fast_rcp(vs);
                     }
                 }
                 unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
             }
             __syncwarp();
-            ++consumed;
+            if (++c_st == S) {
+                c_st = 0;
+                c_par ^= 1u;
+            }
             produce();  // refill the stage just drained (may pull the next chunk id)
         }
         // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
