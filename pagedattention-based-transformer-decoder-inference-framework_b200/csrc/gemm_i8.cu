@@ -54,6 +54,8 @@ struct Args {
     float alpha;
     int act;
     int M, N, K;
+    int stages;          // 1-CTA kernel: ring depth (runtime: more, smaller stages when M is small)
+    int a_bytes;         // 1-CTA kernel: bytes of A per stage (m_tiles * a_rows * 128)
     int ksplit;          // K splits
     int kb_per_split;    // BK blocks per split
     int64_t BATCH_rows;  // BATCH * M
@@ -187,17 +189,25 @@ __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&
 // CL: thread-block cluster size along N.  The CL CTAs of a cluster work on adjacent B slabs and
 // need the same A tiles: each loads 1/CL of the A rows and TMA-multicasts them to all CL CTAs,
 // which divides the L2 -> SM traffic for A by CL (the main loop is L2-read bound otherwise).
+constexpr int MAXST = 12;                     // 1-CTA kernel: maximum ring depth
+constexpr int RING_BYTES = 4 * 3 * TILE_BYTES;  // 192 KB of shared memory for the ring in every configuration
+
 template <int EPI, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles.
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar0 = base + STAGES * STAGE_BYTES;  // full[S], empty[S], tmem_full
-    const uint32_t tmem_slot = bar0 + (2 * STAGES + 1) * 8;
+    const uint32_t bar0 = base + RING_BYTES;  // full[MAXST], empty[MAXST], tmem_full
+    const uint32_t tmem_slot = bar0 + (2 * MAXST + 1) * 8;
     auto full_bar = [&](int s) { return bar0 + s * 8; };
-    auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
-    const uint32_t tmem_full_bar = bar0 + 2 * STAGES * 8;
+    auto empty_bar = [&](int s) { return bar0 + (MAXST + s) * 8; };
+    const uint32_t tmem_full_bar = bar0 + 2 * MAXST * 8;
+    // Stage = [A: a_bytes][B: 16 KB].  For M <= 128 only ceil(M/8)*8 rows of A are loaded (a_bytes <
+    // 16 KB) and the ring gets deeper: the UMMA still reads 128 rows, the rows past a_bytes are
+    // whatever follows in the ring -- they only feed accumulator rows >= M, which are never stored.
+    const int nst = g.stages;
+    const uint32_t a_bytes = (uint32_t)g.a_bytes, stage_bytes = a_bytes + TILE_BYTES;
 
 #ifdef PA_GEMM_PROBE
     const long long t_entry = clock64();
@@ -214,7 +224,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nkb = kb1 - kb0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), CL);  // every CTA of the cluster must have drained slot s
         }
@@ -243,21 +253,28 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef PA_GEMM_PROBE
             long long pw = 0, t_start = clock64();
 #endif
+            int s = 0;
+            uint32_t ph = 1;  // empty barriers start "free"
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
 #ifdef PA_GEMM_PROBE
                 long long t0 = clock64();
 #endif
-                mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+                mbar_wait(empty_bar(s), ph);
 #ifdef PA_GEMM_PROBE
                 pw += clock64() - t0;
 #endif
-                const uint32_t st = base + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(full_bar(s), (uint32_t)(m_tiles + 1) * TILE_BYTES);
+                const uint32_t st = base + s * stage_bytes;
+                // bytes that will land: the A boxes actually issued for this M chunk + the B tile
+                const uint32_t a_load = (m_tiles == 2) ? 2u * TILE_BYTES : (a_bytes < (uint32_t)TILE_BYTES ? a_bytes : (uint32_t)TILE_BYTES);
+                mbar_arrive_expect_tx(full_bar(s), a_load + TILE_BYTES);
                 const int k0 = (kb0 + i) * BK;
                 if (CL == 1) {
-                    tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));
-                    if (m_tiles == 2) tma_load_3d(st + TILE_BYTES, &tmA, k0, m0 + BM, batch, full_bar(s));
+                    if (m_tiles == 2) {
+                        tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));
+                        tma_load_3d(st + TILE_BYTES, &tmA, k0, m0 + BM, batch, full_bar(s));
+                    } else {
+                        tma_load_3d(st, &tmA, k0, m0, batch, full_bar(s));  // box = a_bytes / 128 rows
+                    }
                 } else {
                     // This CTA's share of the A rows of the stage (tmA's box holds a_rows rows),
                     // delivered to the same offset in every CTA of the cluster.
@@ -265,7 +282,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int r0 = (int)crank * a_rows;
                     tma_load_3d_mc(st + r0 * BK, &tmA, k0, m0 + r0, batch, full_bar(s), kMask);
                 }
-                tma_load_3d(st + 2 * TILE_BYTES, &tmB, n0, k0, batch, full_bar(s));
+                tma_load_3d(st + a_bytes, &tmB, n0, k0, batch, full_bar(s));
+                if (++s == nst) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
 #ifdef PA_GEMM_PROBE
             if (blockIdx.x == 5 && g.probe) { g.probe[0] = pw; g.probe[2] = clock64() - t_start; }
@@ -276,17 +297,18 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef PA_GEMM_PROBE
             long long mw = 0, t_start = clock64();
 #endif
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
 #ifdef PA_GEMM_PROBE
                 long long t0 = clock64();
 #endif
-                mbar_wait(full_bar(s), (i / STAGES) & 1);
+                mbar_wait(full_bar(s), ph);
 #ifdef PA_GEMM_PROBE
                 mw += clock64() - t0;
 #endif
                 tc_fence_after();
-                const uint32_t st = base + s * STAGE_BYTES;
+                const uint32_t st = base + s * stage_bytes;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     if (mt < m_tiles) {
@@ -295,7 +317,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // A: K-major SW128, 8-row groups 1024 B apart; +32 B per K step inside the swizzle row.
                             const uint64_t da = make_desc(st + mt * TILE_BYTES + ks * UK, 16, 1024);
                             // B: MN-major SW128, 8 k-rows per 1024 B group; 32 k-rows = 4096 B per K step.
-                            const uint64_t db = make_desc(st + 2 * TILE_BYTES + ks * UK * BK, TILE_BYTES, 1024);
+                            const uint64_t db = make_desc(st + a_bytes + ks * UK * BK, TILE_BYTES, 1024);
                             umma_i8(tmem_base + mt * BN, da, db, kIdesc, (i > 0 || ks > 0) ? 1u : 0u);
                         }
                     }
@@ -303,6 +325,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // slot reusable once these MMAs have read it (signalled to every CTA of the cluster)
                 if (CL == 1) umma_commit(empty_bar(s));
                 else umma_commit_mc(empty_bar(s), kMask);
+                if (++s == nst) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
             umma_commit(tmem_full_bar);
 #ifdef PA_GEMM_PROBE
@@ -580,7 +606,6 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_ld_32x32_nowait(taddr, rr[0]);
             tmem_ld_32x32_nowait(taddr + 32, rr[1]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
             if (g.acc_ws) {
                 // Split-K partial tile: transpose the warp's 32 rows x 64 columns through shared memory
                 // (the ring is idle once the accumulator is complete) so that every store instruction
@@ -789,9 +814,21 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         const int want = atoi(cl_env);
         if (want == 1 || (want == 2 && cl_max >= 2) || (want == 4 && cl_max == 4)) CLs = want;
     }
+    // 1-CTA kernel ring geometry.  M <= 128: load only ceil(M/8)*8 rows of A per stage and use the
+    // saved shared memory for a deeper ring (more weight bytes in flight: small-M GEMMs are pure weight
+    // streaming); no cluster multicast in that case.
+    int a_rows_box = BM, a_bytes = m_tiles0 * TILE_BYTES, stages = STAGES;
+    if (!two_cta && M <= BM) {
+        CLs = 1;
+        a_rows_box = ((M + 7) / 8) * 8;
+        a_bytes = a_rows_box * BK;
+        stages = RING_BYTES / (a_bytes + TILE_BYTES);
+        if (stages > MAXST) stages = MAXST;
+    } else if (!two_cta && CLs > 1) {
+        a_rows_box = m_tiles0 * BM / CLs;
+    }
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH,
-                  (two_cta || CLs == 1) ? BM : m_tiles0 * BM / CLs))
+    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, two_cta ? BM : a_rows_box))
         return PA_ERR_UNSUPPORTED;
     if (!make_map(&tmB, d_B, (uint64_t)N, (uint64_t)K, (uint64_t)BATCH, BK)) return PA_ERR_UNSUPPORTED;
 
@@ -804,6 +841,8 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     g.alpha = alpha_host;
     g.act = act;
     g.M = M; g.N = N; g.K = K;
+    g.stages = stages;
+    g.a_bytes = a_bytes;
 #ifdef PA_GEMM_PROBE
     extern unsigned long long* pa_gemm_probe_buf;
     g.probe = pa_gemm_probe_buf;
@@ -853,7 +892,7 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     } else {
-        const size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+        const size_t smem = (size_t)RING_BYTES + (2 * MAXST + 1) * 8 + 16 + 1024;
         static const KernelFn kernels[3][4] = {
             {gemm_i8_kernel<0, 1>, gemm_i8_kernel<1, 1>, gemm_i8_kernel<2, 1>, gemm_i8_kernel<3, 1>},
             {gemm_i8_kernel<0, 2>, gemm_i8_kernel<1, 2>, gemm_i8_kernel<2, 2>, gemm_i8_kernel<3, 2>},
