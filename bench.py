@@ -249,10 +249,11 @@ def run_ours(args):
     value = world * B / (ms_step * 1e-3)
 
     # ---- end to end: host buffers through AttentionCUDA.forward -------------------------------
-    q_host = q_dev.cpu().numpy()
+    # host-side I/O buffers live in page-locked memory (the contract's "pinned host memory")
+    q_host = torch.empty((L, B, H, D)).pin_memory().copy_(q_dev.cpu())
     nk_host = torch.empty((L, B, H, D)).pin_memory().copy_(nk_dev.cpu())
     nv_host = torch.empty((L, B, H, D)).pin_memory().copy_(nv_dev.cpu())
-    out_host = np.empty((L, B, H, D), dtype=np.float32)
+    out_host = torch.empty((L, B, H, D)).pin_memory()
     nk_stage = torch.empty((B, H, D), device=dev)
     nv_stage = torch.empty((B, H, D), device=dev)
 
@@ -281,7 +282,7 @@ def run_ours(args):
     e2e_value = world * B / e2e_s
     row_bytes = B * H * D * 4
     # parity guard inside the bench: e2e output of the last layer == device-resident output
-    agree = float(np.abs(out_host[L - 1] - out_dev[L - 1].cpu().numpy()).max())
+    agree = float((out_host[L - 1] - out_dev[L - 1].cpu()).abs().max())
 
     # ---- roofline of the dominant kernel (paged decode) ------------------------------------------
     kv_bytes = B * H * T * D * 2 * 2

@@ -40,12 +40,21 @@ def _is_host(x):
     return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
 
 
+def _is_pinned(x):
+    return isinstance(x, torch.Tensor) and not x.is_cuda and x.is_pinned()
+
+
 def _to_device(x, key, device, dtype):
-    """Host buffer -> device tensor via a pinned staging buffer (async H2D on the current stream)."""
+    """Host buffer -> device tensor (async H2D on the current stream).  Page-locked torch tensors are
+    DMA'd directly; pageable memory (numpy arrays, ordinary CPU tensors) goes through a pinned staging
+    buffer first."""
     src = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
     pinned, dev = _stage.get(key, src.shape, dtype, device)
-    pinned.copy_(src)
-    dev.copy_(pinned, non_blocking=True)
+    if _is_pinned(src) and src.dtype == dtype and src.is_contiguous():
+        dev.copy_(src, non_blocking=True)
+    else:
+        pinned.copy_(src)
+        dev.copy_(pinned, non_blocking=True)
     return dev
 
 
@@ -109,11 +118,15 @@ class AttentionTileLauncher:
             if debug:  # attention_tile_launcher.hpp:84-88
                 torch.cuda.synchronize(dev)
             if host_out:
-                pinned = _stage.get("out", (B, H, D), torch.float32, dev)[0]
-                pinned.copy_(d_out, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                dst = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
-                dst.view(B, H, D).copy_(pinned)
+                if _is_pinned(out) and out.dtype == torch.float32 and out.is_contiguous():
+                    out.view(B, H, D).copy_(d_out, non_blocking=True)  # D2H straight into the caller's buffer
+                    torch.cuda.current_stream().synchronize()
+                else:
+                    pinned = _stage.get("out", (B, H, D), torch.float32, dev)[0]
+                    pinned.copy_(d_out, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    dst = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+                    dst.view(B, H, D).copy_(pinned)
             if host_lse:
                 dst = torch.from_numpy(rerank_scores) if isinstance(rerank_scores, np.ndarray) else rerank_scores
                 dst.view(B, H).copy_(d_lse.cpu())

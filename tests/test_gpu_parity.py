@@ -238,6 +238,11 @@ def test_host_buffers_roundtrip(ld, oracle):
     out = np.zeros_like(case["q"])
     ld.AttentionCUDA.forward(case["q"], out, 3, 4, 128, 256, None, kvc, None, False, True, True, case["temperature"])
     np.testing.assert_allclose(out, oracle_attention(case), rtol=RTOL, atol=ATOL)
+    # page-locked torch tensors: DMA'd directly, no staging copy
+    qp = torch.from_numpy(case["q"]).pin_memory()
+    op = torch.zeros(3, 4, 128).pin_memory()
+    ld.AttentionCUDA.forward(qp, op, 3, 4, 128, 256, None, kvc, None, False, True, False, case["temperature"])
+    np.testing.assert_allclose(op.numpy(), oracle_attention(case), rtol=RTOL, atol=ATOL)
 
 
 def test_topk_rejected(ld):
