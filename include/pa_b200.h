@@ -274,6 +274,26 @@ int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature,
 /* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
 int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
 
+/* ------------------------------------------------ prefill */
+/* The multi-query form the reference's headers promise (q/out [B, H, T, D] and `is_prefill`,
+ * attention/attention_config.hpp:8-9,17; causal rule attention/attention_kernel_utils.cuh:70-79)
+ * but do not implement: query t of row b attends the cached keys [0, ctx_start[b] + t] of
+ * table row (d_beam_ids ? d_beam_ids[b] : b).  d_q, d_out: [B, num_heads, Tq, head_dim] f32.
+ * d_ctx_start: [B] tokens cached BEFORE this chunk (NULL = 0: plain prefill); the Tq new
+ * tokens' K/V must already be appended.  Same softmax semantics as pa_paged_decode_*. */
+size_t pa_prefill_workspace_bytes(int B, int Tq, int num_heads, int head_dim, int num_tiles, int tile_size);
+int pa_paged_prefill_f16(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                         int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B,
+                         int Tq, int head_dim, int tile_size, float temperature, void* d_workspace,
+                         size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_prefill_i8(const float* d_q, float* d_out, const int8_t* d_k_pool, const int8_t* d_v_pool,
+                        const float* d_k_scales, const float* d_v_scales, const int32_t* d_table,
+                        int num_beams, int num_heads, int num_tiles, int total_pages,
+                        const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq,
+                        int head_dim, int tile_size, float temperature, void* d_workspace,
+                        size_t workspace_bytes, pa_stream_t stream);
+
 /* --------------------------------- inter-GPU split-KV exchange over peer memory */
 /* North-star long-context mode (the reference has no multi-device code).
  * pa_p2p_alloc: cudaMalloc'd, zero-filled exchange buffer + its 64-byte CUDA IPC handle;

@@ -74,6 +74,11 @@ class AttentionTileLauncher:
         pt = kv_cache.page_table_
         dev = kv_cache.key_buffer_.device
         assert H == pt.num_heads_ and D == kv_cache.head_dim_
+        if is_prefill and not _is_host(q) and T > 1 and q.numel() == B * H * T * D:
+            # the reference's prefill form: q/out [B, H, T, D], causal self-attention over the T cached tokens
+            if top_k not in (0, None) or top_p < 1.0 or rotary_emb is not None or rerank_scores is not None:
+                raise NotImplementedError("prefill: top-k/top-p, RoPE table and rerank_scores are decode-only here")
+            return paged_prefill(q, out, kv_cache, B, T, temperature, beam_ids)
         host_io = _is_host(q)
         d_q = _to_device(q, "q", dev, torch.float32) if host_io else q
         host_out = _is_host(out)
@@ -143,6 +148,32 @@ class AttentionCUDA:
         return AttentionTileLauncher.launch(q, out, B, H, D, T, beam_ids, kv_cache, rotary_emb,
                                             is_prefill, use_fp16, use_overlap, temperature, top_k,
                                             top_p, rerank_scores, debug, ctx_lens)
+
+
+def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_start=None):
+    """Causal multi-query attention of Tq new tokens per row over the paged cache
+    (pa_paged_prefill_f16/_i8).  q/out: [B, H, Tq, D] f32 CUDA tensors (the reference's prefill layout,
+    attention_config.hpp:8-9); ctx_start: [B] int32 device tensor of tokens cached before this chunk."""
+    pt = kv_cache.page_table_
+    H, D = pt.num_heads_, kv_cache.head_dim_
+    assert q.is_contiguous() and out.is_contiguous() and q.numel() == B * H * Tq * D == out.numel()
+    lib = _cabi.lib()
+    need = lib.pa_prefill_workspace_bytes(B, Tq, H, D, pt.num_tiles_, kv_cache.tile_size_)
+    ws = getattr(kv_cache, "_prefill_ws", None)
+    if ws is None or ws.numel() < need:
+        ws = kv_cache._prefill_ws = torch.empty(need, dtype=torch.uint8, device=kv_cache.key_buffer_.device)
+    common = (pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids),
+              _cabi.ptr(ctx_start), B, Tq, D, kv_cache.tile_size_, float(temperature), ws.data_ptr(), ws.numel())
+    with torch.cuda.device(kv_cache.key_buffer_.device):
+        if kv_cache.dtype == "f16":
+            st = lib.pa_paged_prefill_f16(q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                                          kv_cache.value_buffer_.data_ptr(), *common, _cabi.stream())
+        else:
+            st = lib.pa_paged_prefill_i8(q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                                         kv_cache.value_buffer_.data_ptr(), kv_cache.k_scales_.data_ptr(),
+                                         kv_cache.v_scales_.data_ptr(), *common, _cabi.stream())
+    _cabi.check(st, "pa_paged_prefill")
+    return out
 
 
 def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam_ids=None, rotary_emb=None,

@@ -49,12 +49,29 @@ class _Layer:
     pass
 
 
+class _Bufs:
+    """Activation buffers for R rows (R = batch for a decode step, batch * prompt_len for the prefill)."""
+
+    def __init__(self, R, hid, inter, dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.R = R
+        self.x = torch.zeros((R, hid), **f32)
+        self.n = torch.zeros((R, hid), **f32)
+        self.a = torch.zeros((R, hid), **f32)
+        self.h = torch.zeros((R, inter), **f32)
+        self.xq = torch.zeros((R, hid), dtype=torch.int8, device=dev)
+        self.hq = torch.zeros((R, inter), dtype=torch.int8, device=dev)
+        self.xs = torch.ones(R, **f32)
+        self.hs = torch.ones(R, **f32)
+
+
 class _DecoderBase:
     KV_DTYPE = "f16"
     ARGMAX_DIVIDE = 1  # cuda_decoder.cu:10-13 logits / temperature
 
     def __init__(self, num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len, *, device=None,
-                 tile_size=16, batch_size=1, attn_temperature=1.0, use_overlap=True, use_cuda_graph=True):
+                 tile_size=16, batch_size=1, attn_temperature=1.0, use_overlap=True, use_cuda_graph=True,
+                 use_prefill=True):
         if min(num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len) <= 0:
             raise ValueError("decoder dimensions must be positive")
         if hidden_dim != num_heads * head_dim:
@@ -69,6 +86,7 @@ class _DecoderBase:
         self.attn_temperature = float(attn_temperature)  # AttentionCUDA::forward default (attention_config.hpp:19)
         self.use_overlap = use_overlap
         self.use_cuda_graph = use_cuda_graph
+        self.use_prefill = use_prefill
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._lib = _cabi.lib()  # fails loudly when the CUDA library is missing
         self.eps = 1e-5  # layer_norm.hpp:10
@@ -97,15 +115,8 @@ class _DecoderBase:
         self.ids = torch.zeros(B, dtype=torch.int32, device=dev)
         self.positions = torch.zeros(B, dtype=torch.int32, device=dev)
         self.ctx_lens = torch.ones(B, dtype=torch.int32, device=dev)
-        self.x = torch.zeros((B, hid), **f32)
-        self.n = torch.zeros((B, hid), **f32)
-        self.a = torch.zeros((B, hid), **f32)
-        self.h = torch.zeros((B, self.inter_dim_), **f32)
+        self.bufs = _Bufs(B, hid, self.inter_dim_, dev)
         self.logits = torch.zeros((B, self.vocab_size_), **f32)
-        self.xq = torch.zeros((B, hid), dtype=torch.int8, device=dev)
-        self.hq = torch.zeros((B, self.inter_dim_), dtype=torch.int8, device=dev)
-        self.xs = torch.ones(B, **f32)
-        self.hs = torch.ones(B, **f32)
         self._ws = self.kv_caches[0].workspace(B)
         self._graph = None
 
@@ -118,13 +129,13 @@ class _DecoderBase:
     def _chk(self, st, what):
         _cabi.check(st, what)
 
-    def _attention(self, layer_idx, q, out):
+    def _attention(self, layer_idx, q, out, R, ctx_lens, beam_ids, ws):
         kvc = self.kv_caches[layer_idx]
         pt = kvc.page_table_
-        lib, B = self._lib, self._batch
-        common = (pt.d_table_.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kvc.total_pages_, None,
-                  self.ctx_lens.data_ptr(), B, self.max_seq_len_, self.head_dim_, kvc.tile_size_,
-                  self.attn_temperature, None, None, self._ws.data_ptr(), self._ws.numel(), _cabi.stream())
+        lib = self._lib
+        common = (pt.d_table_.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kvc.total_pages_,
+                  _cabi.ptr(beam_ids), ctx_lens.data_ptr(), R, self.max_seq_len_, self.head_dim_, kvc.tile_size_,
+                  self.attn_temperature, None, None, ws.data_ptr(), ws.numel(), _cabi.stream())
         if kvc.dtype == "f16":
             fn = lib.pa_paged_decode_f16_overlap if self.use_overlap else lib.pa_paged_decode_f16
             st = fn(q.data_ptr(), out.data_ptr(), kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr(), *common)
@@ -134,25 +145,56 @@ class _DecoderBase:
                     kvc.k_scales_.data_ptr(), kvc.v_scales_.data_ptr(), *common)
         self._chk(st, "pa_paged_decode")
 
+    def _layers(self, bf, ids, positions, ctx_lens, beam_ids, ws):
+        """The decoder stack (decoder_block.hpp:41-62) for bf.R rows: row r is token ids[r] at position
+        positions[r] of table row beam_ids[r] (None: r) attending ctx_lens[r] cached tokens (its own K/V
+        included).  Leaves the final hidden states in bf.x."""
+        lib, R, hid, s = self._lib, bf.R, self.hidden_dim_, _cabi.stream()
+        self._embed(bf, ids)
+        for li, L in enumerate(self.layers):
+            self._chk(lib.pa_layer_norm_f32(bf.x.data_ptr(), L.ln1_g.data_ptr(), L.ln1_b.data_ptr(), R, hid,
+                                            self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
+            nview = bf.n.view(R, self.num_heads_, self.head_dim_)
+            self.kv_caches[li].append(nview, nview, positions, beam_ids)  # K = V = LN1 output (see module doc)
+            self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws)
+            self._chk(lib.pa_layer_norm_f32(bf.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), R, hid,
+                                            self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
+            self._mlp(bf, L)
+
+    def _head(self, x_rows):
+        """logits (tied embedding) + greedy sample of the B rows in x_rows -> self.ids."""
+        self._logits(x_rows)
+        self._chk(self._lib.pa_argmax_f32(self.logits.data_ptr(), self._batch, self.vocab_size_, self._temperature,
+                                          self.ARGMAX_DIVIDE, self.ids.data_ptr(), _cabi.stream()), "pa_argmax_f32")
+
     def _step(self):
         """One decode step for the B tokens in self.ids at self.positions; writes the greedy next
-        ids back into self.ids and advances positions.  Device work only."""
-        lib, B, hid, s = self._lib, self._batch, self.hidden_dim_, _cabi.stream()
-        self._embed()
-        for li, L in enumerate(self.layers):
-            self._chk(lib.pa_layer_norm_f32(self.x.data_ptr(), L.ln1_g.data_ptr(), L.ln1_b.data_ptr(), B, hid,
-                                            self.eps, self.n.data_ptr(), s), "pa_layer_norm_f32")
-            nview = self.n.view(B, self.num_heads_, self.head_dim_)
-            self.kv_caches[li].append(nview, nview, self.positions)  # K = V = LN1 output (see module doc)
-            self._attention(li, self.n, self.a)
-            self._chk(lib.pa_layer_norm_f32(self.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), B, hid,
-                                            self.eps, self.n.data_ptr(), s), "pa_layer_norm_f32")
-            self._mlp(L)
-        self._logits()
-        self._chk(lib.pa_argmax_f32(self.logits.data_ptr(), B, self.vocab_size_, self._temperature,
-                                    self.ARGMAX_DIVIDE, self.ids.data_ptr(), s), "pa_argmax_f32")
-        self._chk(lib.pa_advance_positions(self.positions.data_ptr(), self.ctx_lens.data_ptr(), B, s),
-                  "pa_advance_positions")
+        ids back into self.ids and advances positions.  Device work only (CUDA-graph capturable)."""
+        self._layers(self.bufs, self.ids, self.positions, self.ctx_lens, None, self._ws)
+        self._head(self.bufs.x)
+        self._chk(self._lib.pa_advance_positions(self.positions.data_ptr(), self.ctx_lens.data_ptr(), self._batch,
+                                                 _cabi.stream()), "pa_advance_positions")
+
+    def _prefill(self, prompt):
+        """All prompt tokens of all sequences in ONE pass through the stack: row
+        (b, t) appends its K/V at position t of table row b and attends causally (ctx = t + 1) through
+        the beam indirection of the decode kernels; LayerNorm and the MLP GEMMs run on B*n rows.
+        Leaves the first sampled token in self.ids and positions = n."""
+        B, n = prompt.shape
+        dev = self.device
+        R = B * n
+        bf = _Bufs(R, self.hidden_dim_, self.inter_dim_, dev)
+        t = torch.arange(n, dtype=torch.int32, device=dev)
+        positions = t.repeat(B)
+        ctx = positions + 1
+        beam = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(n)
+        ws = torch.empty(self._lib.pa_decode_workspace_bytes(R, self.num_heads_, self.head_dim_, self._num_tiles,
+                                                             self.tile_size_), dtype=torch.uint8, device=dev)
+        self._layers(bf, prompt.reshape(-1).contiguous(), positions, ctx, beam, ws)
+        last = bf.x.view(B, n, self.hidden_dim_)[:, n - 1, :].contiguous()
+        self._head(last)
+        self.positions.fill_(n)
+        self.ctx_lens.fill_(n + 1)
 
     # ------------------------------------------------------------------ generate
     def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None):
@@ -190,9 +232,12 @@ class _DecoderBase:
         with torch.cuda.device(dev):
             prompt = torch.tensor(prompts, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)  # [B, n]
             gen = torch.empty((max_len, B), dtype=torch.int32, device=dev)
-            for t in range(n_prompt):  # prompt tokens one step each (a prefill kernel is a "next" row)
-                self.ids.copy_(prompt[:, t])
-                self._step_or_replay()
+            if self.use_prefill:
+                self._prefill(prompt)
+            else:
+                for t in range(n_prompt):  # prompt tokens one decode step each
+                    self.ids.copy_(prompt[:, t])
+                    self._step_or_replay()
             for i in range(max_len):  # self.ids holds the token sampled by the previous step
                 gen[i].copy_(self.ids)
                 if i + 1 < max_len:
@@ -284,20 +329,19 @@ class CUDADecoder(_DecoderBase):
             L.fc2_w, L.fc2_b = self._dev(fc2.reshape(inter, hid)), self._dev(b2)
         self._graph = None
 
-    def _embed(self):
-        self._chk(self._lib.pa_embedding_f32(self.embedding.data_ptr(), self.ids.data_ptr(), self._batch,
-                                             self.hidden_dim_, self.vocab_size_, self.x.data_ptr(), _cabi.stream()),
-                  "pa_embedding_f32")
+    def _embed(self, bf, ids):
+        self._chk(self._lib.pa_embedding_f32(self.embedding.data_ptr(), ids.data_ptr(), bf.R, self.hidden_dim_,
+                                             self.vocab_size_, bf.x.data_ptr(), _cabi.stream()), "pa_embedding_f32")
 
-    def _mlp(self, L):
-        lib, B, hid, inter, s = self._lib, self._batch, self.hidden_dim_, self.inter_dim_, _cabi.stream()
-        self._chk(lib.pa_linear_f32(self.n.data_ptr(), L.fc1_w.data_ptr(), L.fc1_b.data_ptr(), B, hid, inter,
-                                    _cabi.ACT["relu"], self.h.data_ptr(), s), "pa_linear_f32")
-        self._chk(lib.pa_linear_f32(self.h.data_ptr(), L.fc2_w.data_ptr(), L.fc2_b.data_ptr(), B, inter, hid,
-                                    _cabi.ACT[""], self.x.data_ptr(), s), "pa_linear_f32")
+    def _mlp(self, bf, L):
+        lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        self._chk(lib.pa_linear_f32(bf.n.data_ptr(), L.fc1_w.data_ptr(), L.fc1_b.data_ptr(), R, hid, inter,
+                                    _cabi.ACT["relu"], bf.h.data_ptr(), s), "pa_linear_f32")
+        self._chk(lib.pa_linear_f32(bf.h.data_ptr(), L.fc2_w.data_ptr(), L.fc2_b.data_ptr(), R, inter, hid,
+                                    _cabi.ACT[""], bf.x.data_ptr(), s), "pa_linear_f32")
 
-    def _logits(self):
-        self._chk(self._lib.pa_logits_f32(self.x.data_ptr(), self.embedding.data_ptr(), self._batch,
+    def _logits(self, x_rows):
+        self._chk(self._lib.pa_logits_f32(x_rows.data_ptr(), self.embedding.data_ptr(), self._batch,
                                           self.hidden_dim_, self.vocab_size_, self.logits.data_ptr(), _cabi.stream()),
                   "pa_logits_f32")
 
@@ -389,29 +433,29 @@ class INT8Decoder(_DecoderBase):
             L.fc1_b, L.fc2_b = self._dev(bb[:inter]), self._dev(bb[inter:])
         self._graph = None
 
-    def _embed(self):
-        self._chk(self._lib.pa_embedding_i8(self.embedding.data_ptr(), float(self.emb_qscale), self.ids.data_ptr(),
-                                            self._batch, self.hidden_dim_, self.vocab_size_, self.x.data_ptr(),
-                                            _cabi.stream()), "pa_embedding_i8")
+    def _embed(self, bf, ids):
+        self._chk(self._lib.pa_embedding_i8(self.embedding.data_ptr(), float(self.emb_qscale), ids.data_ptr(), bf.R,
+                                            self.hidden_dim_, self.vocab_size_, bf.x.data_ptr(), _cabi.stream()),
+                  "pa_embedding_i8")
 
-    def _quant_rows(self, x, q, scales, dim):
-        lib, B, s = self._lib, self._batch, _cabi.stream()
-        self._chk(lib.pa_batch_minmax_scale(x.data_ptr(), B, dim, scales.data_ptr(), s), "pa_batch_minmax_scale")
-        self._chk(lib.pa_batch_quantize_i8(x.data_ptr(), scales.data_ptr(), B, dim, q.data_ptr(), s),
+    def _quant_rows(self, x, q, scales, R, dim):
+        lib, s = self._lib, _cabi.stream()
+        self._chk(lib.pa_batch_minmax_scale(x.data_ptr(), R, dim, scales.data_ptr(), s), "pa_batch_minmax_scale")
+        self._chk(lib.pa_batch_quantize_i8(x.data_ptr(), scales.data_ptr(), R, dim, q.data_ptr(), s),
                   "pa_batch_quantize_i8")
 
-    def _mlp(self, L):
-        lib, B, hid, inter, s = self._lib, self._batch, self.hidden_dim_, self.inter_dim_, _cabi.stream()
-        self._quant_rows(self.n, self.xq, self.xs, hid)
-        self._chk(lib.pa_gemm_i8_dequant(self.xq.data_ptr(), L.fc1_w.data_ptr(), self.h.data_ptr(), 1, B, inter, hid,
-                                         self.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(),
+    def _mlp(self, bf, L):
+        lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        self._quant_rows(bf.n, bf.xq, bf.xs, R, hid)
+        self._chk(lib.pa_gemm_i8_dequant(bf.xq.data_ptr(), L.fc1_w.data_ptr(), bf.h.data_ptr(), 1, R, inter, hid,
+                                         bf.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(),
                                          _cabi.ACT["relu"], s), "pa_gemm_i8_dequant")
-        self._quant_rows(self.h, self.hq, self.hs, inter)
-        self._chk(lib.pa_gemm_i8_dequant(self.hq.data_ptr(), L.fc2_w.data_ptr(), self.x.data_ptr(), 1, B, hid, inter,
-                                         self.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], s),
+        self._quant_rows(bf.h, bf.hq, bf.hs, R, inter)
+        self._chk(lib.pa_gemm_i8_dequant(bf.hq.data_ptr(), L.fc2_w.data_ptr(), bf.x.data_ptr(), 1, R, hid, inter,
+                                         bf.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], s),
                   "pa_gemm_i8_dequant")
 
-    def _logits(self):
-        self._chk(self._lib.pa_logits_i8(self.x.data_ptr(), self.embedding.data_ptr(), float(self.emb_qscale),
+    def _logits(self, x_rows):
+        self._chk(self._lib.pa_logits_i8(x_rows.data_ptr(), self.embedding.data_ptr(), float(self.emb_qscale),
                                          self._batch, self.hidden_dim_, self.vocab_size_, self.logits.data_ptr(),
                                          _cabi.stream()), "pa_logits_i8")

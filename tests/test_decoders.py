@@ -186,10 +186,15 @@ def test_cuda_decoder_generate_vs_oracle(oracle, tmp_path, packed_mlp):
     assert out[:4] == prompt and len(out) == 16 and all(0 <= t < V for t in out)
     ref = RefDecoder(w, H, D)
     check_teacher_forced(out, len(prompt), ref, 0.8, 1, None, 1e-4)
-    # CUDA-graph replay == eager
+    # CUDA-graph replay == eager; batched prefill of the prompt == feeding it token by token
     dec2 = ld.CUDADecoder(L, H, D, hid, V, S, use_cuda_graph=False, use_overlap=False)
     dec2.load_weights(str(tmp_path / "w"))
     assert dec2.generate(prompt, 12, 0.8) == out
+    dec3 = ld.CUDADecoder(L, H, D, hid, V, S, use_prefill=False)
+    dec3.load_weights(str(tmp_path / "w"))
+    out3 = dec3.generate(prompt, 12, 0.8)
+    check_teacher_forced(out3, len(prompt), RefDecoder(w, H, D), 0.8, 1, None, 1e-4)
+    assert out3 == out
     # tolerated caller variants (api/router.py:23, cli/chat_cli.py:24)
     lst = []
     assert dec.generate(prompt, lst, 5, 1.0) is lst and lst[:4] == prompt and len(lst) == 9

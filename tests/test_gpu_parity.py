@@ -278,6 +278,44 @@ def test_partial_and_combine_equal_full(ld, oracle):
     np.testing.assert_allclose(out.reshape(-1, 128), exp, rtol=1e-5, atol=1e-6)
 
 
+# ------------------------------------------------------------------ prefill
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_prefill_causal_matches_oracle(ld, oracle, kv):
+    """q/out [B, H, Tq, D]; query t of row b sees keys [0, ctx_start[b] + t] (causal rule of
+    attention_kernel_utils.cuh:70-79), checked against the oracle run once per (b, t)."""
+    B, H, D, Tq = 2, 3, 128, 37
+    start = np.array([0, 23], np.int32)
+    case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv)
+    rng = np.random.default_rng(81)
+    q = rng.standard_normal((B, H, Tq, D)).astype(np.float32)
+    kvc = to_device_cache(case)
+    out = torch.full((B, H, Tq, D), float("nan"), device="cuda")
+    ld.paged_prefill(torch.from_numpy(q).cuda(), out, kvc, B, Tq, case["temperature"],
+                     ctx_start=torch.from_numpy(start).cuda())
+    got = out.cpu().numpy()
+    # oracle: one decode row per (b, t) through the beam indirection, ctx = start + t + 1
+    rows_q = np.ascontiguousarray(q.transpose(0, 2, 1, 3).reshape(B * Tq, H, D))
+    exp_case = dict(case)
+    exp_case["q"] = rows_q
+    exp_case["beam_ids"] = np.repeat(np.arange(B, dtype=np.int32), Tq)
+    exp_case["ctx_lens"] = (start[:, None] + np.arange(Tq, dtype=np.int32)[None, :] + 1).reshape(-1).astype(np.int32)
+    exp = oracle_attention(exp_case).reshape(B, Tq, H, D).transpose(0, 2, 1, 3)
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
+    if kv == "f16":
+        # the reference-facing call: is_prefill=True with q [B, H, T, D] = causal self-attention over T tokens
+        T = 48
+        q2 = rng.standard_normal((B, H, T, D)).astype(np.float32)
+        out2 = torch.empty((B, H, T, D), device="cuda")
+        ld.AttentionCUDA.forward(torch.from_numpy(q2).cuda(), out2, B, H, D, T, None, kvc, None, True, True, False,
+                                 case["temperature"])
+        c2 = dict(case)
+        c2["q"] = np.ascontiguousarray(q2.transpose(0, 2, 1, 3).reshape(B * T, H, D))
+        c2["beam_ids"] = np.repeat(np.arange(B, dtype=np.int32), T)
+        c2["ctx_lens"] = np.tile(np.arange(1, T + 1, dtype=np.int32), B)
+        exp2 = oracle_attention(c2).reshape(B, T, H, D).transpose(0, 2, 1, 3)
+        np.testing.assert_allclose(out2.cpu().numpy(), exp2, rtol=RTOL, atol=ATOL)
+
+
 # ------------------------------------------------------------------ beam-aware group kernel (C3)
 GROUP_CASES = [
     dict(B=8, H=2, D=128, T=320, beam_width=4, shared_prefix=192),
