@@ -274,6 +274,24 @@ int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature,
 /* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
 int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
 
+/* ------------------------------------------------ sampling */
+/* attention_cpu/softmax_lut.cpp:203-231 softmax_lut_vec over vocabulary logits [rows, vocab]:
+ * p = exp((x - max)/temperature) / (sum + 1e-6). */
+int pa_softmax_temperature(const float* d_logits, int rows, int vocab, float temperature, float* d_probs,
+                           pa_stream_t stream);
+/* attention_cpu/softmax_lut.cpp:233-256 apply_topk_topp_filter, in place: rank entries by
+ * (prob, index) descending (ties: larger index first), zero those with rank >= top_k (top_k > 0)
+ * or whose higher-ranked probability mass is >= top_p (top_p < 1), no renormalisation; then the
+ * EOS rule (probs[eos] > eos_thresh zeroes everything else).  Replaces the serial thread-0 top-k of
+ * attention/top_k_top_p_filter.cuh:55-111 by a radix select. */
+int pa_topk_topp_filter(float* d_probs, int rows, int vocab, int top_k, float top_p, int eos_token_id,
+                        float eos_thresh, pa_stream_t stream);
+/* Inverse-CDF sample in index order: first index whose inclusive prefix sum of d_probs exceeds
+ * d_uniform[row] * total (uniform numbers in [0,1) supplied by the caller; the reference calls the
+ * host rand() from device code, top_k_top_p_filter.cuh:109). */
+int pa_sample_from_probs(const float* d_probs, int rows, int vocab, const float* d_uniform,
+                         int32_t* d_out_ids, pa_stream_t stream);
+
 /* ------------------------------------------------ prefill */
 /* The multi-query form the reference's headers promise (q/out [B, H, T, D] and `is_prefill`,
  * attention/attention_config.hpp:8-9,17; causal rule attention/attention_kernel_utils.cuh:70-79)

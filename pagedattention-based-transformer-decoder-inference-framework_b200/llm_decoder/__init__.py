@@ -12,5 +12,6 @@ from .int8_quant import (batch_dequantize, batch_minmax_scale, batch_quantize, c
                          compute_minmax_scale, dequantize_from_int8, dnnl_matmul_int8, quantize_to_int8)
 from .kv_tile_cache import KVTileCache  # noqa: F401
 from .page_table import PageTable  # noqa: F401
+from . import sampling  # noqa: F401
 
 from .decoders import CUDADecoder, INT8Decoder  # noqa: F401

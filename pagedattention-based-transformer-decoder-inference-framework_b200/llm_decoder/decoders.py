@@ -162,10 +162,22 @@ class _DecoderBase:
             self._mlp(bf, L)
 
     def _head(self, x_rows):
-        """logits (tied embedding) + greedy sample of the B rows in x_rows -> self.ids."""
+        """logits (tied embedding) of the B rows in x_rows, then the next ids -> self.ids: the reference's
+        greedy argmax by default; temperature / top-k / top-p / EOS sampling (sampling.py) when requested."""
         self._logits(x_rows)
-        self._chk(self._lib.pa_argmax_f32(self.logits.data_ptr(), self._batch, self.vocab_size_, self._temperature,
-                                          self.ARGMAX_DIVIDE, self.ids.data_ptr(), _cabi.stream()), "pa_argmax_f32")
+        sp = getattr(self, "_sampling", None)
+        if sp is None:
+            self._chk(self._lib.pa_argmax_f32(self.logits.data_ptr(), self._batch, self.vocab_size_,
+                                              self._temperature, self.ARGMAX_DIVIDE, self.ids.data_ptr(),
+                                              _cabi.stream()), "pa_argmax_f32")
+            return
+        from . import sampling
+        # CUDADecoder scales logits by 1/T (cuda_decoder.cu:10-13), INT8Decoder by T (int8_decoder.cpp:100)
+        t_eff = self._temperature if self.ARGMAX_DIVIDE else 1.0 / self._temperature
+        probs = sampling.softmax_temperature(self.logits, t_eff)
+        sampling.apply_topk_topp_filter(probs, sp["top_k"], sp["top_p"], sp["eos_token_id"], sp["eos_thresh"])
+        u = torch.rand(self._batch, device=self.device, generator=sp["generator"])
+        sampling.sample_from_probs(probs, u, out=self.ids)
 
     def _step(self):
         """One decode step for the B tokens in self.ids at self.positions; writes the greedy next
@@ -197,7 +209,7 @@ class _DecoderBase:
         self.ctx_lens.fill_(n + 1)
 
     # ------------------------------------------------------------------ generate
-    def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None):
+    def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None, **sampling_kw):
         """generate(input_ids, max_len, temperature) -> prompt + generated ids (bindings.cpp:8-15).
         Also tolerated (callers in api/, cli/): generate(input_ids, output_ids_list, max_tokens,
         temperature) -- the list is extended in place and returned -- and max_gen_len=."""
@@ -209,14 +221,17 @@ class _DecoderBase:
             max_len = max_gen_len
         if max_len is None:
             raise TypeError("generate() missing max_len")
-        seqs = self.generate_batch([list(input_ids)], int(max_len), float(temperature))
+        seqs = self.generate_batch([list(input_ids)], int(max_len), float(temperature), **sampling_kw)
         if out_list is not None:
             out_list[:] = seqs[0]
             return out_list
         return seqs[0]
 
-    def generate_batch(self, prompts, max_len, temperature=1.0):
-        """Greedy decode of several sequences at once (equal prompt lengths): rows are independent."""
+    def generate_batch(self, prompts, max_len, temperature=1.0, top_k=0, top_p=1.0, eos_token_id=-1,
+                       eos_thresh=0.0, seed=None):
+        """Decode several sequences at once (equal prompt lengths): rows are independent.  Greedy argmax (the
+        reference's sampler) unless top_k > 0 or top_p < 1, which switch to temperature / top-k / top-p / EOS
+        sampling on the device with a torch generator seeded by `seed`."""
         B = len(prompts)
         n_prompt = len(prompts[0])
         if n_prompt == 0 or any(len(p) != n_prompt for p in prompts):
@@ -229,6 +244,12 @@ class _DecoderBase:
         self.reset()
         self._temperature = float(temperature)
         dev = self.device
+        self._sampling = None
+        if top_k > 0 or top_p < 1.0:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(0 if seed is None else int(seed))
+            self._sampling = dict(top_k=int(top_k), top_p=float(top_p), eos_token_id=int(eos_token_id),
+                                  eos_thresh=float(eos_thresh), generator=gen)
         with torch.cuda.device(dev):
             prompt = torch.tensor(prompts, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)  # [B, n]
             gen = torch.empty((max_len, B), dtype=torch.int32, device=dev)
@@ -257,8 +278,8 @@ class _DecoderBase:
         return self.logits
 
     def _step_or_replay(self):
-        if not self.use_cuda_graph:
-            self._step()
+        if not self.use_cuda_graph or getattr(self, "_sampling", None) is not None:
+            self._step()  # the sampling path draws from a torch generator: not captured
         elif self._graph is not None and self._graph_temp == self._temperature:
             self._graph.replay()
         else:

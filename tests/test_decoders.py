@@ -212,6 +212,32 @@ def test_cuda_decoder_generate_vs_oracle(oracle, tmp_path, packed_mlp):
 
 
 @pytest.mark.gpu
+def test_decoder_sampling_options(tmp_path):
+    """generate(..., top_k / top_p / seed): device sampling instead of greedy; top_k=1 == greedy; same seed
+    reproduces; every sampled token lies in the top-k set of the teacher-forced oracle logits."""
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(33)
+    L, H, D, V, S = 1, 2, 64, 157, 40
+    hid = H * D
+    w = make_weights(rng, L, hid, V)
+    write_fp32_tree(w, str(tmp_path / "w"), True)
+    dec = ld.CUDADecoder(L, H, D, hid, V, S)
+    dec.load_weights(str(tmp_path / "w"))
+    prompt = [5, 9, 2]
+    greedy = dec.generate(prompt, 8, 0.9)
+    assert dec.generate(prompt, 8, 0.9, top_k=1) == greedy
+    a = dec.generate(prompt, 8, 0.9, top_k=5, top_p=0.95, seed=7)
+    assert a == dec.generate(prompt, 8, 0.9, top_k=5, top_p=0.95, seed=7)
+    ref = RefDecoder(w, H, D)
+    for t, tok in enumerate(a[:-1]):
+        lg = ref.step(tok)
+        if t + 1 >= len(prompt):
+            top5 = set(np.argsort(-lg, kind="stable")[:6].tolist())   # 6: tolerate a numeric swap at rank 5/6
+            assert a[t + 1] in top5
+
+
+@pytest.mark.gpu
 def test_decoder_errors():
     import llm_decoder as ld
     with pytest.raises(ValueError):
