@@ -143,6 +143,76 @@ class KVTileCache:
                     self.k_scales_.copy_(torch.from_numpy(ks.copy()).view(self.k_scales_.shape))
                     self.v_scales_.copy_(torch.from_numpy(vs.copy()).view(self.v_scales_.shape))
 
+    # ---- GPU <-> CPU tile offload in the reference's CPU tile-store format --------------------
+    # KVTileCacheCPU<T>::save / load (kv_cache/kv_tile_cache_cpu.cpp:89-123): int32 count, then per tile
+    # {TileIndex = 3 x int32 (batch, head, tile), tile_size x T payload}.  The CPU store has no K/V
+    # distinction, so a tile's payload here is its K page followed by its V page (int8
+    # caches append the two f32 scale rows); the file can be loaded by the reference's own
+    # KVTileCacheCPU with tile_size = tile_payload_bytes() / sizeof(T).
+    def tile_payload_bytes(self):
+        page = self.tile_size_ * self.head_dim_ * self.key_buffer_.element_size()
+        return 2 * page + (2 * self.tile_size_ * 4 if self.dtype == "i8" else 0)
+
+    def _payload_of_pages(self, pages):
+        idx = torch.as_tensor(pages, dtype=torch.int64, device=self.key_buffer_.device)
+        n = idx.numel()
+        parts = [self.key_buffer_.index_select(0, idx).view(torch.uint8).reshape(n, -1),
+                 self.value_buffer_.index_select(0, idx).view(torch.uint8).reshape(n, -1)]
+        if self.dtype == "i8":
+            parts += [self.k_scales_.index_select(0, idx).view(torch.uint8).reshape(n, -1),
+                      self.v_scales_.index_select(0, idx).view(torch.uint8).reshape(n, -1)]
+        return torch.cat(parts, dim=1).cpu().numpy()
+
+    def save_tiles_cpu_format(self, path):
+        pt = self.page_table_
+        pt.flush()
+        flat = np.nonzero((pt.host_table_ >= 0) & (pt.host_table_ < self.total_pages_))[0]
+        pages = pt.host_table_[flat]
+        payload = self._payload_of_pages(pages) if flat.size else np.zeros((0, self.tile_payload_bytes()), np.uint8)
+        hn = pt.num_heads_ * pt.num_tiles_
+        rec = np.zeros(flat.size, dtype=np.dtype([("idx", "<i4", 3), ("data", "u1", self.tile_payload_bytes())]))
+        rec["idx"][:, 0] = flat // hn
+        rec["idx"][:, 1] = (flat % hn) // pt.num_tiles_
+        rec["idx"][:, 2] = flat % pt.num_tiles_
+        rec["data"] = payload
+        try:
+            with open(path, "wb") as f:
+                f.write(np.int32(flat.size).tobytes())
+                f.write(rec.tobytes())
+        except OSError:
+            raise RuntimeError(f"Failed to open file for saving: {path}")
+        return int(flat.size)
+
+    def load_tiles_cpu_format(self, path):
+        """Tiles of the file are (re)mapped to pages (fresh pages from the free list for unmapped tiles)
+        and their K/V bytes uploaded in one batched scatter."""
+        nb = self.tile_payload_bytes()
+        try:
+            with open(path, "rb") as f:
+                raw = f.read()
+        except OSError:
+            raise RuntimeError(f"Failed to open file for loading: {path}")
+        count = int(np.frombuffer(raw[:4], dtype="<i4")[0])
+        rec = np.frombuffer(raw, dtype=np.dtype([("idx", "<i4", 3), ("data", "u1", nb)]), count=count, offset=4)
+        pages = [self.register_tile(int(b), int(h), int(t)) for b, h, t in rec["idx"]]
+        if not pages:
+            return 0
+        dev = self.key_buffer_.device
+        idx = torch.tensor(pages, dtype=torch.int64, device=dev)
+        data = torch.from_numpy(np.ascontiguousarray(rec["data"])).to(dev)
+        page = self.tile_size_ * self.head_dim_ * self.key_buffer_.element_size()
+        self.key_buffer_.view(torch.uint8).reshape(self.total_pages_, page).index_copy_(0, idx, data[:, :page].contiguous())
+        self.value_buffer_.view(torch.uint8).reshape(self.total_pages_, page).index_copy_(
+            0, idx, data[:, page:2 * page].contiguous())
+        if self.dtype == "i8":
+            sb = self.tile_size_ * 4
+            self.k_scales_.view(torch.uint8).reshape(self.total_pages_, sb).index_copy_(
+                0, idx, data[:, 2 * page:2 * page + sb].contiguous())
+            self.v_scales_.view(torch.uint8).reshape(self.total_pages_, sb).index_copy_(
+                0, idx, data[:, 2 * page + sb:].contiguous())
+        self.page_table_.flush()
+        return count
+
     # ---- hot path: append (get_write_ptr + row write, hpp:29-34) -------------------------
     def append(self, new_k, new_v, positions, beam_ids=None):
         """new_k/new_v: [R, H, D] device tensors (f16 or f32); positions: [R] int32 device."""

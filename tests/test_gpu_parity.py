@@ -278,6 +278,47 @@ def test_partial_and_combine_equal_full(ld, oracle):
     np.testing.assert_allclose(out.reshape(-1, 128), exp, rtol=1e-5, atol=1e-6)
 
 
+# ------------------------------------------------------------------ page lifecycle
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_tile_offload_in_reference_cpu_format(ld, oracle, kv, tmp_path):
+    """save_tiles_cpu_format writes the layout of KVTileCacheCPU<T>::save (kv_tile_cache_cpu.cpp:89-103):
+    the reference's OWN object loads the file and returns every tile's K|V bytes; a second GPU cache
+    restored from the file attends identically (pages renumbered through its own free list)."""
+    case = make_case(B=3, H=2, D=128, T=80, seed=91, kv=kv, unmapped_frac=0.1)
+    kvc = to_device_cache(case)
+    path = str(tmp_path / "tiles.bin")
+    n = kvc.save_tiles_cpu_format(path)
+    tb = case["table"]
+    mapped = [(b, h, t) for b in range(3) for h in range(2) for t in range(tb.shape[2])
+              if 0 <= tb[b, h, t] < case["total_pages"]]
+    assert n == len(mapped)
+    nb = kvc.tile_payload_bytes()
+    if oracle.ref.available():
+        cpu = oracle.ref.KVTileCacheCPU(max_size=10 * n, tile_size=nb // 4, dtype=np.float32)   # bytes reinterpreted as f32
+        assert cpu.load(path) is not None
+        page = 16 * 128 * case["k_pool"].itemsize
+        for (b, h, t) in mapped:
+            got = cpu.get(b, h, t)
+            assert got is not None
+            raw = got.view(np.uint8)
+            pg = tb[b, h, t]
+            assert raw[:page].tobytes() == case["k_pool"][pg].tobytes()
+            assert raw[page:2 * page].tobytes() == case["v_pool"][pg].tobytes()
+            if kv == "i8":
+                assert raw[2 * page:2 * page + 64].tobytes() == case["k_scales"][pg].tobytes()
+        assert cpu.get(0, 0, 0) is None or (0, 0, 0) in mapped
+    # restore into a fresh cache (different page numbering) and compare attention
+    kvc2 = ld.KVTileCache(kv)
+    kvc2.init(case["total_pages"] + 5, 16, 128)
+    kvc2.configure_table(3, 2, tb.shape[2])
+    assert kvc2.load_tiles_cpu_format(path) == n
+    out1, _ = run_decode(ld, case, True, kvc)
+    out2, _ = run_decode(ld, case, True, kvc2)
+    np.testing.assert_array_equal(out1, out2)
+    with pytest.raises(RuntimeError):
+        kvc2.load_tiles_cpu_format(str(tmp_path / "nope.bin"))
+
+
 # ------------------------------------------------------------------ prefill (SURVEY 8f row 1)
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 def test_prefill_causal_matches_oracle(ld, oracle, kv):
