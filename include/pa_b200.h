@@ -271,6 +271,18 @@ int pa_logits_i8(const float* d_x, const int8_t* d_E, float qscale, int rows, in
  * first maximum wins (std::max_element). */
 int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature, int divide,
                   int32_t* d_out_ids, pa_stream_t stream);
+/* pa_logits_* followed by pa_argmax_f32 in ONE pass over the embedding table: the sampler is folded
+ * into the logits kernel as an atomicMax on an order-preserving 64-bit key (first maximum wins).
+ * d_best: [rows] u64 scratch, zero-initialised once by the caller, reset by every call.
+ * elem_bytes 4: d_E f32; elem_bytes 1: d_E int8 dequantised as q / qscale. */
+int pa_logits_argmax(const float* d_x, const void* d_E, int elem_bytes, float qscale, int rows, int hidden,
+                     int vocab, float temperature, int divide, float* d_logits,
+                     unsigned long long* d_best, int32_t* d_out_ids, pa_stream_t stream);
+/* compute_minmax_scale + batch_quantize of every row of x [rows, dim] in one kernel
+ * (attention_cpu/int8_quant.cpp:59-64, 15-28); bit-identical to pa_batch_minmax_scale followed by
+ * pa_batch_quantize_i8. */
+int pa_row_quantize_dynamic_i8(const float* d_x, int rows, int dim, float* d_scales, int8_t* d_q,
+                               pa_stream_t stream);
 /* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
 int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
 

@@ -32,46 +32,87 @@ __global__ void embedding_kernel(const WT* __restrict__ E, const int32_t* __rest
     }
 }
 
-// ---- LayerNorm: one warp per row, two passes (mean, then biased variance) ----------------
-__global__ void layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, int rows, int hidden, float eps,
-                                  float* __restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const float* xr = x + (int64_t)warp * hidden;
+// ---- LayerNorm: one CTA of 256 threads per row, two passes (mean, then biased variance) -----
+__device__ __forceinline__ float block_sum_256(float v, float* sm) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    float r = (lane < 8) ? sm[lane] : 0.f;
+    r = warp_sum(r);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int rows, int hidden,
+                                                         float eps, float* __restrict__ out) {
+    __shared__ float sm[8];
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * hidden;
     float s = 0.f;
-    for (int j = lane; j < hidden; j += 32) s += xr[j];
-    const float mean = warp_sum(s) / (float)hidden;
+    for (int j = threadIdx.x; j < hidden; j += 256) s += xr[j];
+    const float mean = block_sum_256(s, sm) / (float)hidden;
     float v = 0.f;
-    for (int j = lane; j < hidden; j += 32) {
+    for (int j = threadIdx.x; j < hidden; j += 256) {
         const float d = xr[j] - mean;
         v = fmaf(d, d, v);
     }
-    const float var = warp_sum(v) / (float)hidden;
+    const float var = block_sum_256(v, sm) / (float)hidden;
     const float inv_std = (float)(1.0 / sqrt((double)(var + eps)));  // layer_norm.hpp:33
-    float* o = out + (int64_t)warp * hidden;
-    for (int j = lane; j < hidden; j += 32) o[j] = (xr[j] - mean) * inv_std * gamma[j] + beta[j];
+    float* o = out + (int64_t)row * hidden;
+    for (int j = threadIdx.x; j < hidden; j += 256) o[j] = (xr[j] - mean) * inv_std * gamma[j] + beta[j];
+}
+
+// ---- dynamic per-row activation quantisation in ONE kernel: compute_minmax_scale (int8_quant.cpp:59-64)
+// then batch_quantize (int8_quant.cpp:15-28) of the same row; bit-identical to the two separate kernels. ----
+__global__ void __launch_bounds__(256) row_quantize_dynamic_kernel(const float* __restrict__ x, int rows, int dim,
+                                                                   float* __restrict__ scales, int8_t* __restrict__ q) {
+    __shared__ float sm[8];
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * dim;
+    float m = 0.f;
+    for (int d = threadIdx.x; d < dim; d += 256) m = fmaxf(m, fabsf(xr[d]));
+    m = warp_max(m);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    m = (lane < 8) ? sm[lane] : 0.f;
+    m = warp_max(m);
+    const float scale = __fdiv_rn(127.f, __fadd_rn(m, 1e-6f));
+    if (threadIdx.x == 0) scales[row] = scale;
+    int8_t* qr = q + (int64_t)row * dim;
+    for (int d = threadIdx.x; d < dim; d += 256) {
+        float r = roundf(__fmul_rn(xr[d], scale));  // half away from zero (std::round)
+        r = fminf(127.f, fmaxf(-128.f, r));
+        qr[d] = (int8_t)(int)r;
+    }
 }
 
 // ---- linear, W [K, N] row-major: out[r, n] = act(bias[n] + sum_k x[r,k] W[k,n]) ----------
-// Block = 8 warps x 32 columns: warp w streams rows k = w, w+8, ... of a 128-byte wide column
-// strip (one coalesced line per k), keeps up to kRowChunk accumulators per lane, and the 8
-// warps are summed through shared memory.  grid.x = N/32 strips, grid.y = row chunks.
+// CTA = 8 warps x 32 columns: warp w streams rows k = k0 + w, k0 + w + 8, ... of a 128-byte wide column
+// strip (one coalesced line per k) inside this CTA's K slice, keeps up to kRowChunk accumulators per
+// lane, and the 8 warps are summed through shared memory.  grid = (N/32 strips, row chunks, K slices):
+// with few strips (fc2 of a small model: N = 768 -> 24) the K dimension is sliced across CTAs so the
+// whole chip streams the weights; slice partials go to a scratch buffer and a second tiny kernel adds
+// them in a fixed order (deterministic, unlike float atomics).
 __global__ void __launch_bounds__(256) linear_kn_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                         const float* __restrict__ bias, int rows, int K, int N,
-                                                        int act, float* __restrict__ out) {
+                                                        int act, int kslice, float* __restrict__ out,
+                                                        float* __restrict__ partial) {
     __shared__ float red[8][kRowChunk][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 32 + lane;
     const int r0 = blockIdx.y * kRowChunk;
     const int nr = min(kRowChunk, rows - r0);
+    const int k0 = blockIdx.z * kslice, k1 = min(K, k0 + kslice);
     float acc[kRowChunk];
 #pragma unroll
     for (int r = 0; r < kRowChunk; ++r) acc[r] = 0.f;
     if (n < N) {
         const float* xr = x + (int64_t)r0 * K;
 #pragma unroll 4
-        for (int k = warp; k < K; k += 8) {
+        for (int k = k0 + warp; k < k1; k += 8) {
             const float w = __ldcs(W + (int64_t)k * N + n);  // streamed once
 #pragma unroll
             for (int r = 0; r < kRowChunk; ++r)
@@ -85,40 +126,111 @@ __global__ void __launch_bounds__(256) linear_kn_kernel(const float* __restrict_
     const int rr = threadIdx.x >> 5, cc = threadIdx.x & 31;
     const int nn = blockIdx.x * 32 + cc;
     if (rr < nr && nn < N) {
-        float s = bias ? bias[nn] : 0.f;
+        float s = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += red[w][rr][cc];
-        if (act == PA_ACT_RELU) s = fmaxf(s, 0.f);
-        out[(int64_t)(r0 + rr) * N + nn] = s;
+        if (partial) {
+            partial[((int64_t)blockIdx.z * rows + r0 + rr) * N + nn] = s;
+        } else {
+            s += bias ? bias[nn] : 0.f;
+            if (act == PA_ACT_RELU) s = fmaxf(s, 0.f);
+            out[(int64_t)(r0 + rr) * N + nn] = s;
+        }
     }
 }
 
-// ---- logits against the tied embedding E [vocab, hidden]: one warp per vocab row ----------
+__global__ void linear_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias, int rows, int N,
+                                     int nslices, int act, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * N) return;
+    float s = bias ? bias[i % N] : 0.f;
+    for (int z = 0; z < nslices; ++z) s += partial[(int64_t)z * rows * N + i];
+    if (act == PA_ACT_RELU) s = fmaxf(s, 0.f);
+    out[i] = s;
+}
+
+// ---- logits against the tied embedding E [vocab, hidden]: one warp per vocab row, 16-byte loads.
+// Optionally folds the greedy sampler in: best[r] = max over v of the 64-bit key
+// (order-preserving bits of (logit / T or logit * T) << 32 | ~v), so the maximum key is the FIRST maximum
+// (std::max_element, cuda_decoder.cu:13 / int8_decoder.cpp:103); argmax_decode_kernel turns it into ids. ----
+__device__ __forceinline__ uint32_t orderable_f32(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 template <typename WT>
 __global__ void __launch_bounds__(256) logits_kernel(const float* __restrict__ x, const WT* __restrict__ E, int rows,
-                                                     int hidden, int vocab, float qscale, float* __restrict__ logits) {
+                                                     int hidden, int vocab, float qscale, float* __restrict__ logits,
+                                                     unsigned long long* __restrict__ best, float t, int divide) {
+    constexpr int EPL = 16 / (int)sizeof(WT);  // elements per 16-byte load: 4 (f32) or 16 (int8)
     const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (v >= vocab) return;
     const WT* e = E + (int64_t)v * hidden;
+    const bool vec_ok = (hidden % EPL == 0) && (((uintptr_t)E & 15) == 0);
     for (int r0 = 0; r0 < rows; r0 += kRowChunk) {
         const int nr = min(kRowChunk, rows - r0);
         float acc[kRowChunk];
 #pragma unroll
         for (int r = 0; r < kRowChunk; ++r) acc[r] = 0.f;
-        for (int j = lane; j < hidden; j += 32) {
-            const float w = (float)e[j];
+        if (vec_ok) {
+            for (int j = lane * EPL; j < hidden; j += 32 * EPL) {
+                float w[EPL];
+                const uint4 raw = ldg_stream_128(e + j);
+                if (sizeof(WT) == 4) {
+                    w[0] = __uint_as_float(raw.x); w[1 % EPL] = __uint_as_float(raw.y);
+                    w[2 % EPL] = __uint_as_float(raw.z); w[3 % EPL] = __uint_as_float(raw.w);
+                } else {
+                    const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int r = 0; r < kRowChunk; ++r)
-                if (r < nr) acc[r] = fmaf(__ldg(x + (int64_t)(r0 + r) * hidden + j), w, acc[r]);
+                    for (int i = 0; i < 4; ++i) {  // exact int8 -> f32 through the mantissa of 2^23 (no I2F)
+                        const uint32_t xw = ww[i] ^ 0x80808080u;
+                        w[(4 * i + 0) % EPL] = __uint_as_float(__byte_perm(xw, 0x4B000000u, 0x7440)) - 8388736.f;
+                        w[(4 * i + 1) % EPL] = __uint_as_float(__byte_perm(xw, 0x4B000000u, 0x7441)) - 8388736.f;
+                        w[(4 * i + 2) % EPL] = __uint_as_float(__byte_perm(xw, 0x4B000000u, 0x7442)) - 8388736.f;
+                        w[(4 * i + 3) % EPL] = __uint_as_float(__byte_perm(xw, 0x4B000000u, 0x7443)) - 8388736.f;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRowChunk; ++r) {
+                    if (r < nr) {
+                        const float* xr = x + (int64_t)(r0 + r) * hidden + j;
+#pragma unroll
+                        for (int i = 0; i < EPL; ++i) acc[r] = fmaf(__ldg(xr + i), w[i], acc[r]);
+                    }
+                }
+            }
+        } else {
+            for (int j = lane; j < hidden; j += 32) {
+                const float w = (float)e[j];
+#pragma unroll
+                for (int r = 0; r < kRowChunk; ++r)
+                    if (r < nr) acc[r] = fmaf(__ldg(x + (int64_t)(r0 + r) * hidden + j), w, acc[r]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < kRowChunk; ++r) {
             if (r < nr) {
                 float s = warp_sum(acc[r]);
                 if (sizeof(WT) == 1) s = __fdiv_rn(s, qscale);
-                if (lane == 0) logits[(int64_t)(r0 + r) * vocab + v] = s;
+                if (lane == 0) {
+                    logits[(int64_t)(r0 + r) * vocab + v] = s;
+                    if (best) {
+                        const float sv = divide ? __fdiv_rn(s, t) : __fmul_rn(s, t);
+                        if (sv == sv)  // NaN never wins (std::max_element keeps the first element)
+                            atomicMax(best + r0 + r, ((unsigned long long)orderable_f32(sv) << 32) | (0xffffffffu - (uint32_t)v));
+                    }
+                }
             }
         }
+    }
+}
+
+__global__ void argmax_decode_kernel(unsigned long long* __restrict__ best, int rows, int32_t* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) {
+        const unsigned long long k = best[r];
+        out[r] = (k == 0ull) ? 0 : (int32_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+        best[r] = 0ull;  // ready for the next step
     }
 }
 
@@ -193,10 +305,25 @@ PA_API int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float
                              float eps, float* d_out, pa_stream_t stream) {
     PA_CHECK_ARG(d_x && d_gamma && d_beta && d_out && rows >= 0 && hidden > 0);
     if (rows == 0) return PA_OK;
-    const int wpb = 4;
-    layer_norm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(d_x, d_gamma, d_beta, rows, hidden,
-                                                                                 eps, d_out);
+    layer_norm_kernel<<<rows, 256, 0, as_stream(stream)>>>(d_x, d_gamma, d_beta, rows, hidden, eps, d_out);
     PA_RETURN_LAUNCH_STATUS();
+}
+
+// K-slice partials of pa_linear_f32, one scratch buffer per device, grown on demand (stream-ordered reuse).
+static float* linear_scratch(size_t bytes) {
+    static float* p[64] = {};
+    static size_t cap[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (cap[dev] < bytes) {
+        if (p[dev]) cudaFree(p[dev]);
+        p[dev] = nullptr;
+        cap[dev] = 0;
+        if (cudaMalloc(&p[dev], bytes) != cudaSuccess) return nullptr;
+        cap[dev] = bytes;
+    }
+    return p[dev];
 }
 
 PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
@@ -205,8 +332,29 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     PA_CHECK_ARG(act == PA_ACT_NONE || act == PA_ACT_RELU);
     PA_CHECK_ARG(d_x != d_out);
     if (rows == 0) return PA_OK;
-    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((rows + kRowChunk - 1) / kRowChunk));
-    linear_kn_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, d_out);
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return PA_ERR_NO_DEVICE;
+    const int strips = (N + 31) / 32, chunks = (rows + kRowChunk - 1) / kRowChunk;
+    // slice K until ~2 CTAs per SM stream the weights; every slice keeps >= 64 k-rows (8 per warp)
+    int nslices = (2 * di.sm_count + strips * chunks - 1) / (strips * chunks);
+    if (nslices > K / 64) nslices = K / 64;
+    if (nslices < 1) nslices = 1;
+    const int kslice = (K + nslices - 1) / nslices;
+    nslices = (K + kslice - 1) / kslice;
+    float* partial = nullptr;
+    if (nslices > 1) {
+        partial = linear_scratch((size_t)nslices * rows * N * sizeof(float));
+        if (!partial) return (int)cudaErrorMemoryAllocation;
+    }
+    dim3 grid((unsigned)strips, (unsigned)chunks, (unsigned)nslices);
+    linear_kn_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, kslice, d_out, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (nslices > 1) {
+        const int64_t n = (int64_t)rows * N;
+        linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, d_bias, rows, N,
+                                                                                        nslices, act, d_out);
+    }
     PA_RETURN_LAUNCH_STATUS();
 }
 
@@ -214,7 +362,8 @@ PA_API int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidde
                          pa_stream_t stream) {
     PA_CHECK_ARG(d_x && d_E && d_logits && rows >= 0 && hidden > 0 && vocab > 0);
     if (rows == 0) return PA_OK;
-    logits_kernel<float><<<(vocab + 7) / 8, 256, 0, as_stream(stream)>>>(d_x, d_E, rows, hidden, vocab, 1.f, d_logits);
+    logits_kernel<float><<<(vocab + 7) / 8, 256, 0, as_stream(stream)>>>(d_x, d_E, rows, hidden, vocab, 1.f, d_logits,
+                                                                         nullptr, 1.f, 0);
     PA_RETURN_LAUNCH_STATUS();
 }
 
@@ -223,7 +372,7 @@ PA_API int pa_logits_i8(const float* d_x, const int8_t* d_E, float qscale, int r
     PA_CHECK_ARG(d_x && d_E && d_logits && rows >= 0 && hidden > 0 && vocab > 0 && qscale != 0.f);
     if (rows == 0) return PA_OK;
     logits_kernel<int8_t><<<(vocab + 7) / 8, 256, 0, as_stream(stream)>>>(d_x, d_E, rows, hidden, vocab, qscale,
-                                                                          d_logits);
+                                                                          d_logits, nullptr, 1.f, 0);
     PA_RETURN_LAUNCH_STATUS();
 }
 
@@ -240,5 +389,38 @@ PA_API int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int r
     PA_CHECK_ARG(d_positions && rows >= 0);
     if (rows == 0) return PA_OK;
     advance_kernel<<<(rows + 127) / 128, 128, 0, as_stream(stream)>>>(d_positions, d_ctx_lens, rows);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
+// logits + greedy sample in one pass over the embedding table: d_best [rows] u64 scratch (zero-initialised
+// once; reset by the call), d_out_ids [rows].  d_E is f32 (elem_bytes 4) or int8 (elem_bytes 1, dequantised
+// as q / qscale).  divide: 1 = argmax(logit / T) (cuda_decoder.cu:7-14), 0 = argmax(logit * T)
+// (int8_decoder.cpp:97-104).
+PA_API int pa_logits_argmax(const float* d_x, const void* d_E, int elem_bytes, float qscale, int rows, int hidden,
+                            int vocab, float temperature, int divide, float* d_logits,
+                            unsigned long long* d_best, int32_t* d_out_ids, pa_stream_t stream) {
+    PA_CHECK_ARG(d_x && d_E && d_logits && d_best && d_out_ids && rows >= 0 && hidden > 0 && vocab > 0);
+    PA_CHECK_ARG((elem_bytes == 4) || (elem_bytes == 1 && qscale != 0.f));
+    PA_CHECK_ARG(!divide || temperature != 0.f);
+    if (rows == 0) return PA_OK;
+    cudaStream_t st = as_stream(stream);
+    if (elem_bytes == 4)
+        logits_kernel<float><<<(vocab + 7) / 8, 256, 0, st>>>(d_x, static_cast<const float*>(d_E), rows, hidden, vocab,
+                                                              1.f, d_logits, d_best, temperature, divide);
+    else
+        logits_kernel<int8_t><<<(vocab + 7) / 8, 256, 0, st>>>(d_x, static_cast<const int8_t*>(d_E), rows, hidden,
+                                                               vocab, qscale, d_logits, d_best, temperature, divide);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    argmax_decode_kernel<<<(rows + 127) / 128, 128, 0, st>>>(d_best, rows, d_out_ids);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
+// compute_minmax_scale + batch_quantize of every row in one kernel (int8_quant.cpp:59-64, 15-28).
+PA_API int pa_row_quantize_dynamic_i8(const float* d_x, int rows, int dim, float* d_scales, int8_t* d_q,
+                                      pa_stream_t stream) {
+    PA_CHECK_ARG(d_x && d_scales && d_q && rows >= 0 && dim > 0);
+    if (rows == 0) return PA_OK;
+    row_quantize_dynamic_kernel<<<rows, 256, 0, as_stream(stream)>>>(d_x, rows, dim, d_scales, d_q);
     PA_RETURN_LAUNCH_STATUS();
 }

@@ -117,6 +117,7 @@ class _DecoderBase:
         self.ctx_lens = torch.ones(B, dtype=torch.int32, device=dev)
         self.bufs = _Bufs(B, hid, self.inter_dim_, dev)
         self.logits = torch.zeros((B, self.vocab_size_), **f32)
+        self._best = torch.zeros(B, dtype=torch.int64, device=dev)  # argmax keys of pa_logits_argmax
         self._ws = self.kv_caches[0].workspace(B)
         self._graph = None
 
@@ -164,13 +165,15 @@ class _DecoderBase:
     def _head(self, x_rows):
         """logits (tied embedding) of the B rows in x_rows, then the next ids -> self.ids: the reference's
         greedy argmax by default; temperature / top-k / top-p / EOS sampling (sampling.py) when requested."""
-        self._logits(x_rows)
         sp = getattr(self, "_sampling", None)
-        if sp is None:
-            self._chk(self._lib.pa_argmax_f32(self.logits.data_ptr(), self._batch, self.vocab_size_,
-                                              self._temperature, self.ARGMAX_DIVIDE, self.ids.data_ptr(),
-                                              _cabi.stream()), "pa_argmax_f32")
+        if sp is None:  # logits and the greedy sampler in one pass over the embedding table
+            E, eb, qs = self._embedding_table()
+            self._chk(self._lib.pa_logits_argmax(x_rows.data_ptr(), E.data_ptr(), eb, qs, self._batch,
+                                                 self.hidden_dim_, self.vocab_size_, self._temperature,
+                                                 self.ARGMAX_DIVIDE, self.logits.data_ptr(), self._best.data_ptr(),
+                                                 self.ids.data_ptr(), _cabi.stream()), "pa_logits_argmax")
             return
+        self._logits(x_rows)
         from . import sampling
         # CUDADecoder scales logits by 1/T (cuda_decoder.cu:10-13), INT8Decoder by T (int8_decoder.cpp:100)
         t_eff = self._temperature if self.ARGMAX_DIVIDE else 1.0 / self._temperature
@@ -350,6 +353,9 @@ class CUDADecoder(_DecoderBase):
             L.fc2_w, L.fc2_b = self._dev(fc2.reshape(inter, hid)), self._dev(b2)
         self._graph = None
 
+    def _embedding_table(self):
+        return self.embedding, 4, 1.0
+
     def _embed(self, bf, ids):
         self._chk(self._lib.pa_embedding_f32(self.embedding.data_ptr(), ids.data_ptr(), bf.R, self.hidden_dim_,
                                              self.vocab_size_, bf.x.data_ptr(), _cabi.stream()), "pa_embedding_f32")
@@ -454,16 +460,18 @@ class INT8Decoder(_DecoderBase):
             L.fc1_b, L.fc2_b = self._dev(bb[:inter]), self._dev(bb[inter:])
         self._graph = None
 
+    def _embedding_table(self):
+        return self.embedding, 1, float(self.emb_qscale)
+
     def _embed(self, bf, ids):
         self._chk(self._lib.pa_embedding_i8(self.embedding.data_ptr(), float(self.emb_qscale), ids.data_ptr(), bf.R,
                                             self.hidden_dim_, self.vocab_size_, bf.x.data_ptr(), _cabi.stream()),
                   "pa_embedding_i8")
 
     def _quant_rows(self, x, q, scales, R, dim):
-        lib, s = self._lib, _cabi.stream()
-        self._chk(lib.pa_batch_minmax_scale(x.data_ptr(), R, dim, scales.data_ptr(), s), "pa_batch_minmax_scale")
-        self._chk(lib.pa_batch_quantize_i8(x.data_ptr(), scales.data_ptr(), R, dim, q.data_ptr(), s),
-                  "pa_batch_quantize_i8")
+        """compute_minmax_scale + batch_quantize per row (int8_quant.cpp:59-64, 15-28), one kernel."""
+        self._chk(self._lib.pa_row_quantize_dynamic_i8(x.data_ptr(), R, dim, scales.data_ptr(), q.data_ptr(),
+                                                       _cabi.stream()), "pa_row_quantize_dynamic_i8")
 
     def _mlp(self, bf, L):
         lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()

@@ -126,6 +126,32 @@ def test_decoder_kernels_match_oracle(oracle):
     np.testing.assert_allclose(lg.cpu().numpy(), x.astype(np.float64) @ E.T.astype(np.float64), rtol=1e-4, atol=1e-3)
     _cabi.check(lib.pa_logits_i8(dx.data_ptr(), dEq.data_ptr(), 42.5, rows, hid, V, lg.data_ptr(), s))
     np.testing.assert_allclose(lg.cpu().numpy(), (x.astype(np.float64) @ Eq.T.astype(np.float64)) / 42.5, rtol=1e-4, atol=1e-3)
+    # fused logits + greedy sampler == logits then argmax (first maximum), f32 and int8 tables
+    best = torch.zeros(rows, dtype=torch.int64, device="cuda")
+    ids_f = torch.empty(rows, dtype=torch.int32, device="cuda")
+    for (tab, eb, qs) in ((dE, 4, 1.0), (dEq, 1, 42.5)):
+        for t, divide in ((0.7, 1), (1.3, 0)):
+            _cabi.check(lib.pa_logits_argmax(dx.data_ptr(), tab.data_ptr(), eb, qs, rows, hid, V, t, divide,
+                                             lg.data_ptr(), best.data_ptr(), ids_f.data_ptr(), s))
+            lv = lg.cpu().numpy()
+            v = lv / np.float32(t) if divide else lv * np.float32(t)
+            np.testing.assert_array_equal(ids_f.cpu().numpy(), np.argmax(v, axis=1))
+            assert int(best.abs().sum()) == 0     # scratch reset for the next call
+    # fused per-row dynamic quantise == compute_minmax_scale + batch_quantize (bit-exact)
+    xs = torch.empty(rows, device="cuda")
+    xq = torch.empty((rows, hid), dtype=torch.int8, device="cuda")
+    _cabi.check(lib.pa_row_quantize_dynamic_i8(dx.data_ptr(), rows, hid, xs.data_ptr(), xq.data_ptr(), s))
+    sc = oracle.cpu.batch_minmax_scale(x, hid)
+    np.testing.assert_array_equal(xs.cpu().numpy(), sc)
+    np.testing.assert_array_equal(xq.cpu().numpy(), oracle.cpu.batch_quantize(x, sc, hid).reshape(rows, hid))
+    # split-K path of the fp32 linear layer (few column strips, long K)
+    x3 = rng.standard_normal((3, 4096)).astype(np.float32)
+    W3 = rng.standard_normal((4096, 64)).astype(np.float32)
+    o3 = torch.empty((3, 64), device="cuda")
+    dx3, dW3 = torch.from_numpy(x3).cuda(), torch.from_numpy(W3).cuda()
+    _cabi.check(lib.pa_linear_f32(dx3.data_ptr(), dW3.data_ptr(), None, 3, 4096, 64, 1, o3.data_ptr(), s))
+    np.testing.assert_allclose(o3.cpu().numpy(), np.maximum(x3.astype(np.float64) @ W3.astype(np.float64), 0),
+                               rtol=1e-4, atol=1e-3)
     l2 = rng.standard_normal((rows, V)).astype(np.float32)
     l2[0, 7] = l2[0, 200] = 9.0     # tie -> first index
     l2[1, :] = -np.inf
