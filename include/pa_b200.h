@@ -291,6 +291,11 @@ int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa
  * p = exp((x - max)/temperature) / (sum + 1e-6). */
 int pa_softmax_temperature(const float* d_logits, int rows, int vocab, float temperature, float* d_probs,
                            pa_stream_t stream);
+/* attention_cpu/softmax_lut.cpp:60-100 fused_softmax_lut_inplace / softmax_batch_parallel over int32
+ * logits [rows, n] with the exp table of build_exp_lut (:11-18, d_lut [resolution], max_x = 10):
+ * BIT-EXACT (table index by truncation, sum in the reference's sequential order). */
+int pa_softmax_lut_i32(const int32_t* d_logits, int rows, int n, float scale, const float* d_lut,
+                       int resolution, float* d_probs, pa_stream_t stream);
 /* attention_cpu/softmax_lut.cpp:233-256 apply_topk_topp_filter, in place: rank entries by
  * (prob, index) descending (ties: larger index first), zero those with rank >= top_k (top_k > 0)
  * or whose higher-ranked probability mass is >= top_p (top_p < 1), no renormalisation; then the

@@ -12,6 +12,8 @@
 // "rank < top_k" is "key >= k-th largest key" (MSB-first radix select, 8 bits per pass), and "cumulative
 // probability of all higher-ranked entries < top_p" is "key >= boundary key", found by the same descent
 // over per-bucket probability sums.
+#include <climits>
+
 #include "pa_common.cuh"
 
 namespace pa {
@@ -47,6 +49,46 @@ __global__ void __launch_bounds__(kSampThreads) softmax_temperature_kernel(const
     s = block_reduce(s, sm, false);
     const float inv = __fdiv_rn(1.f, s + 1e-6f);
     for (int i = threadIdx.x; i < V; i += blockDim.x) p[i] *= inv;
+}
+
+// attention_cpu/softmax_lut.cpp:60-82 fused_softmax_lut_inplace (= the row body of softmax_batch_parallel,
+// :85-100): x = ((float)logit - max) * scale clamped to [-10, 10], idx = (int)((x + 10) * (res-1)/20)
+// (truncation), p = lut[idx] / (sum + 1e-6).  BIT-EXACT: the table look-ups run in parallel, the sum is
+// formed by one thread in the reference's sequential order (rows are attention rows, <= a few thousand
+// entries), so `inv` and every product round exactly as on the CPU.
+__global__ void __launch_bounds__(kSampThreads) softmax_lut_kernel(const int32_t* __restrict__ logits, int N, float scale,
+                                                                   const float* __restrict__ lut, int resolution,
+                                                                   float* __restrict__ probs) {
+    __shared__ int smax[32];
+    __shared__ float s_inv;
+    const int32_t* x = logits + (int64_t)blockIdx.x * N;
+    float* p = probs + (int64_t)blockIdx.x * N;
+    int mx = INT_MIN;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = max(mx, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = smax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = max(mx, smax[w]);
+    const float max_x = 10.0f;
+    const float inv_range = __fdiv_rn((float)(resolution - 1), __fmul_rn(2.f, max_x));
+    const float fmx = (float)mx;  // static_cast<float>(logits[i]) - max_val: int32 max promoted to float
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float v = __fmul_rn(__fsub_rn((float)x[i], fmx), scale);
+        v = fmaxf(-max_x, fminf(max_x, v));
+        const int idx = (int)__fmul_rn(__fadd_rn(v, max_x), inv_range);
+        p[i] = lut[idx];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.0f;
+        for (int i = 0; i < N; ++i) sum = __fadd_rn(sum, p[i]);
+        s_inv = __fdiv_rn(1.0f, __fadd_rn(sum, 1e-6f));
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) p[i] = __fmul_rn(p[i], inv);
 }
 
 __device__ __forceinline__ uint64_t key_of(float p, int i) {
@@ -205,6 +247,14 @@ PA_API int pa_softmax_temperature(const float* d_logits, int rows, int vocab, fl
     PA_CHECK_ARG(d_logits && d_probs && rows >= 0 && vocab > 0 && temperature != 0.f);
     if (rows == 0) return PA_OK;
     softmax_temperature_kernel<<<rows, kSampThreads, 0, as_stream(stream)>>>(d_logits, vocab, temperature, d_probs);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
+PA_API int pa_softmax_lut_i32(const int32_t* d_logits, int rows, int n, float scale, const float* d_lut,
+                              int resolution, float* d_probs, pa_stream_t stream) {
+    PA_CHECK_ARG(d_logits && d_lut && d_probs && rows >= 0 && n > 0 && resolution > 1);
+    if (rows == 0) return PA_OK;
+    softmax_lut_kernel<<<rows, kSampThreads, 0, as_stream(stream)>>>(d_logits, n, scale, d_lut, resolution, d_probs);
     PA_RETURN_LAUNCH_STATUS();
 }
 

@@ -6,6 +6,38 @@ import torch
 from . import _cabi
 
 
+def build_exp_lut(resolution=1024, max_x=10.0, device=None):
+    """build_exp_lut (softmax_lut.cpp:11-18): lut[i] = exp(-max_x + 2*max_x*i/(resolution-1)) in float32 with
+    the C library's expf (what std::exp(float) calls), so the table is the reference's bit for bit."""
+    import ctypes
+    import ctypes.util
+
+    import numpy as np
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.expf.restype = ctypes.c_float
+    libm.expf.argtypes = [ctypes.c_float]
+    mx = np.float32(max_x)
+    lut = np.empty(resolution, dtype=np.float32)
+    for i in range(resolution):
+        x = -mx + np.float32(2) * mx * np.float32(i) / np.float32(resolution - 1)
+        lut[i] = libm.expf(float(np.float32(x)))
+    t = torch.from_numpy(lut)
+    return t.to(device) if device is not None else t
+
+
+def softmax_lut(logits_i32, scale, lut, out=None):
+    """fused_softmax_lut_inplace / softmax_batch_parallel (softmax_lut.cpp:60-100) over int32 logits
+    [rows, n] -> f32 probabilities, bit-exact (pa_softmax_lut_i32)."""
+    x = logits_i32.contiguous()
+    assert x.dtype == torch.int32 and lut.dtype == torch.float32 and lut.is_cuda
+    rows, n = x.shape
+    p = torch.empty((rows, n), dtype=torch.float32, device=x.device) if out is None else out
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().pa_softmax_lut_i32(x.data_ptr(), rows, n, float(scale), lut.data_ptr(), lut.numel(),
+                                                   p.data_ptr(), _cabi.stream()), "pa_softmax_lut_i32")
+    return p
+
+
 def softmax_temperature(logits, temperature=1.0, out=None):
     """softmax_lut_vec (softmax_lut.cpp:203-231): exp((x - max)/T) / (sum + 1e-6) per row."""
     x = logits.contiguous()

@@ -14,6 +14,29 @@ def ld(oracle):
     return llm_decoder
 
 
+def test_softmax_lut_bit_exact(ld, oracle):
+    """pa_softmax_lut_i32 against the reference's OWN compiled softmax_batch_parallel / softmax_lut objects
+    (oracle._ref) and the committed golden vectors: bit for bit, including the table built on the host."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+    lut = ld.sampling.build_exp_lut(1024, 10.0)
+    np.testing.assert_array_equal(lut.numpy(), gold["lut"])
+    dl = lut.cuda()
+    for i in range(3):
+        lg, sc = gold[f"sl_logits{i}"], float(gold[f"sl_scale{i}"])
+        got = ld.sampling.softmax_lut(torch.from_numpy(lg[None]).cuda(), sc, dl).cpu().numpy()[0]
+        np.testing.assert_array_equal(got, gold[f"sl_fused{i}"])
+    rng = np.random.default_rng(12)
+    for n, sc in ((8, 0.01), (512, 0.001), (4096, 0.05), (1000, 0.003)):
+        x = rng.integers(-4000, 4000, size=(5, n), dtype=np.int32)
+        got = ld.sampling.softmax_lut(torch.from_numpy(x).cuda(), sc, dl).cpu().numpy()
+        for r in range(5):
+            np.testing.assert_array_equal(got[r], oracle.cpu.fused_softmax_lut(x[r], sc, gold["lut"]))
+        if oracle.ref.available() and n % 8 == 0:
+            exp = oracle.ref.softmax_batch_parallel(x, sc, gold["lut"])
+            np.testing.assert_array_equal(got, np.asarray(exp))
+
+
 @pytest.mark.parametrize("V", [8, 1000, 50257])
 def test_softmax_temperature_matches_oracle(ld, oracle, V):
     rng = np.random.default_rng(V)
