@@ -171,9 +171,11 @@ int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8_t* d_k
  * not-yet-copied copy-on-write page) is read from HBM ONCE per group and applied to all
  * those beams' queries on the tensor cores (mma.sync m16n8k16, fp16 operands split hi/lo so
  * scores and outputs keep fp32 accuracy).  Pages that differ are staged per distinct id.
- * Requires head_dim == 128, beam_width <= 4, B % beam_width == 0, d_ctx_lens == NULL
- * (beams advance in lock step: every row has T tokens); otherwise PA_ERR_UNSUPPORTED and
- * the caller uses pa_paged_decode_f16[_overlap]. */
+ * Requires head_dim == 128, beam_width <= 4, B % beam_width == 0; otherwise
+ * PA_ERR_UNSUPPORTED and the caller uses pa_paged_decode_f16[_overlap].  d_ctx_lens (optional)
+ * gives every row its own context length (tokens at or past it are masked for that row only):
+ * with consecutive query positions as the rows of a group this is causal prefill, 4 queries
+ * per K/V byte. */
 int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_pool,
                               const void* d_v_pool, const int32_t* d_table, int num_beams,
                               int num_heads, int num_tiles, int total_pages,

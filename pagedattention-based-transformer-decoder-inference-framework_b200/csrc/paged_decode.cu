@@ -63,6 +63,8 @@ struct DecodeArgs {
     int* xch_status;
     int xch_rank, xch_world;
     int all_rows_in_ws;  // combine kernel: merge rows of a single chunk too (exchange / group kernels)
+    const int* row_prefix;    // [B+1] chunk prefix per row, precomputed in global memory (group kernel, ragged)
+    const int* group_prefix;  // [groups+1] chunk prefix per beam group (max over its rows)
 };
 
 template <int D, int KV>
@@ -698,7 +700,9 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
     cm.cu = cu;
     cm.NC = (units_of_ctx(row_ctx(a, 0)) + cu - 1) / cu;
     cm.prefix = nullptr;
-    if (a.ctx_lens) {
+    if (a.row_prefix) {
+        cm.prefix = a.row_prefix;
+    } else if (a.ctx_lens) {
         if (threadIdx.x == 0) {
             prefix_sm[0] = 0;
             for (int i = 0; i < a.B; ++i)
@@ -959,14 +963,41 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     }
     __syncthreads();
 
-    // chunk space: (group, head, j) with NC chunks of `cu` units per row (uniform context a.T)
+    // chunk space: (group, head, j).  Uniform context (a.ctx_lens == NULL): NC chunks of `cu` units per row.
+    // Ragged (per-row context lengths, e.g. causal prefill where the W rows of a group are consecutive
+    // query positions): row b has row_prefix[b+1]-row_prefix[b] chunks, group g as many as its longest row.
+    const bool ragged = a.row_prefix != nullptr;
     const int units = units_of_ctx(row_ctx(a, 0));
     const int NC = (units + cu - 1) / cu;
-    const int64_t total = (int64_t)ga.groups * a.H * NC;
+    const int64_t total = ragged ? (int64_t)a.group_prefix[ga.groups] * a.H : (int64_t)ga.groups * a.H * NC;
     const int64_t total_warps = (int64_t)gridDim.x * NW;
     const int64_t gw = (int64_t)blockIdx.x * NW + warp;
     const int upt = a.tile_size / kUnitTok;
-    const int ctx = row_ctx(a, 0);
+    // chunk id -> (group, head, chunk index, chunks of the group)
+    auto locate_group = [&](int64_t id, int& g_, int& h_, int& j_, int& ncg) {
+        if (!ragged) {
+            // position-major, LAST chunks first: the tail of a beam's context is private (W staged copies
+            // per unit) while the prefix is shared (one copy), so the expensive chunks are dispatched first
+            // and the cheap ones fill the end of the run (longest-first balance).
+            const int64_t per_j = (int64_t)ga.groups * a.H;
+            j_ = NC - 1 - (int)(id / per_j);
+            const int rem = (int)(id % per_j);
+            g_ = rem / a.H;
+            h_ = rem - g_ * a.H;
+            ncg = NC;
+        } else {
+            int lo = 0, hi = ga.groups;  // largest g with group_prefix[g] * H <= id
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)a.group_prefix[mid] * a.H <= id) lo = mid; else hi = mid;
+            }
+            g_ = lo;
+            ncg = a.group_prefix[lo + 1] - a.group_prefix[lo];
+            const int64_t rem = id - (int64_t)a.group_prefix[lo] * a.H;
+            h_ = (int)(rem / ncg);
+            j_ = ncg - 1 - (int)(rem - (int64_t)h_ * ncg);
+        }
+    };
 
     const uint32_t my_stage0 = smem_base + (uint32_t)warp * S * kGroupStageBytes;
     const uint32_t my_bar0 = smem_u32(bars + warp * S);
@@ -975,7 +1006,7 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 
     // ---------------- producer (warp-uniform state; lanes < W look pages up in parallel) -------
     bool p_has = false, p_first = true;
-    int p_g = 0, p_h = 0, p_u = 0, p_uend = 0;
+    int p_g = 0, p_h = 0, p_u = 0, p_uend = 0, p_ctx = 0;
     int p_beam = 0;          // lane w < W: table row of beam w of the current group
     uint32_t issued = 0, p_chunks = 0;
     int p_pending_mask = 0;  // beams of the current unit not yet staged
@@ -993,20 +1024,17 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
             id = total_warps + (int64_t)t;
         }
         if (id >= total) return false;
-        // Chunk order: position-major, LAST chunks first.  The tail of a beam's context is private
-        // (W staged copies per unit) while the prefix is shared (one copy), so the expensive chunks
-        // are dispatched first and the cheap ones fill the end of the run (longest-first balance).
-        const int64_t per_j = (int64_t)ga.groups * a.H;
-        const int j = NC - 1 - (int)(id / per_j);
-        const int rem = (int)(id % per_j);
-        p_g = rem / a.H;
-        p_h = rem - p_g * a.H;
-        p_u = j * cu;
-        p_uend = min(units, p_u + cu);
+        int j, ncg;
+        locate_group(id, p_g, p_h, j, ncg);
+        int cw = 0;
         if (lane < W) {
             const int b = p_g * W + lane;
             p_beam = a.beam_ids ? a.beam_ids[b] : b;
+            cw = row_ctx(a, b);
         }
+        p_ctx = (int)warp_max((float)cw);  // the group's longest context (exact: < 2^24 tokens)
+        p_u = j * cu;
+        p_uend = min(units_of_ctx(p_ctx), p_u + cu);
         if (lane == 0) my_cq[p_chunks % QN] = id;
         ++p_chunks;
         __syncwarp();
@@ -1033,9 +1061,11 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         }
         const bool last_of_unit = (p_pending_mask == 0);
         const bool last_of_chunk = last_of_unit && (p_u + 1 >= p_uend);
-        const int nvalid = mask ? min(kUnitTok, ctx - p_u * kUnitTok) : 0;
+        const int nvalid = mask ? min(kUnitTok, p_ctx - p_u * kUnitTok) : 0;
         if (lane == 0) {
-            my_meta[st] = nvalid | (mask << 8) | (last_of_chunk ? (1 << 16) : 0);
+            // meta: [0,5) tokens of the unit inside the group's context, [5,13) beams sharing this copy,
+            // [13] last stage of the chunk, [14,32) unit index (per-beam context limits in ragged mode)
+            my_meta[st] = nvalid | (mask << 5) | (last_of_chunk ? (1 << 13) : 0) | (p_u << 14);
             if (nvalid > 0) {
                 const int row0 = page * a.tile_size + (p_u % upt) * kUnitTok;  // token row in the pool
                 const uint32_t dst = my_stage0 + st * kGroupStageBytes;
@@ -1067,11 +1097,10 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     while (c_chunks < p_chunks) {
         const int64_t id = my_cq[c_chunks % QN];
         ++c_chunks;
-        const int64_t per_j = (int64_t)ga.groups * a.H;
-        const int cj = NC - 1 - (int)(id / per_j);
-        const int rem = (int)(id % per_j);
-        const int cg = rem / a.H;
-        const int ch = rem - cg * a.H;
+        int cg, ch, cj, ncg;
+        locate_group(id, cg, ch, cj, ncg);
+        // context length of this lane's beam (tokens at or past it are masked: causal limit in prefill)
+        const int c_ctx = (beam_of_lane < W) ? row_ctx(a, cg * W + beam_of_lane) : 0;
         // Q fragments: row g8 of the 16 x 128 operand, fp16 hi (rows 0-3) / lo (rows 4-7) parts
         uint32_t qa[8][2];
         {
@@ -1118,8 +1147,9 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
             const uint32_t st = consumed % S;
             mbar_wait(my_bar0 + st * 8, (consumed / S) & 1);
             const int mt = my_meta[st];
-            const int nvalid = mt & 0xff, mask = (mt >> 8) & 0xff;
-            done = (mt >> 16) & 1;
+            const int nvalid = mt & 0x1f, mask = (mt >> 5) & 0xff;
+            done = (mt >> 13) & 1;
+            const int lim = c_ctx - (int)((unsigned)mt >> 14) * kUnitTok;  // tokens of this unit inside MY context
             if (nvalid > 0) {
                 const uint32_t sb = my_stage0 + st * kGroupStageBytes;
                 if (nvalid < kUnitTok) {
@@ -1155,7 +1185,7 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
                         float v = sacc[t][e];
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
                         const int tok = t * 8 + j4 * 2 + e;
-                        const bool ok = tok < nvalid && ((mask >> beam_of_lane) & 1);
+                        const bool ok = tok < nvalid && tok < lim && ((mask >> beam_of_lane) & 1);
                         sc[t * 2 + e] = ok ? v : -INFINITY;
                     }
                 }
@@ -1215,8 +1245,17 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
             o[t][0] += __shfl_xor_sync(0xffffffffu, o[t][0], 16);
             o[t][1] += __shfl_xor_sync(0xffffffffu, o[t][1], 16);
         }
-        if (!lo_half && beam_of_lane < W) {
-            const int64_t slot = ((int64_t)(cg * W + beam_of_lane) * a.H + ch) * NC + cj;
+        // workspace slot of (row b, head, chunk j): rows own consecutive slots (ChunkMap::row_start); in ragged
+        // mode a row shorter than its group simply has no chunk j.
+        const int brow = cg * W + beam_of_lane;
+        int nc_b = NC;
+        int64_t slot0 = ((int64_t)brow * a.H + ch) * NC;
+        if (ragged && beam_of_lane < W) {
+            nc_b = a.row_prefix[brow + 1] - a.row_prefix[brow];
+            slot0 = (int64_t)a.row_prefix[brow] * a.H + (int64_t)ch * nc_b;
+        }
+        if (!lo_half && beam_of_lane < W && cj < nc_b) {
+            const int64_t slot = slot0 + cj;
             float* dst = a.ws_o + slot * D;
 #pragma unroll
             for (int t = 0; t < 16; ++t)
@@ -1226,6 +1265,46 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
                 a.ws_l[slot] = l_tot;
             }
         }
+    }
+}
+
+// Chunk prefixes for the ragged group kernel, computed once per launch into the workspace:
+// row_prefix[b+1] - row_prefix[b] = ceil(units(ctx_b) / cu); group_prefix over max of the W rows of a group.
+__global__ void __launch_bounds__(1024) group_prefix_kernel(const DecodeArgs a, int W, int cu, int* __restrict__ row_prefix,
+                                                            int* __restrict__ group_prefix) {
+    __shared__ int part[1024];
+    const int G = a.B / W;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass == 0 ? a.B : G;
+        int* out = pass == 0 ? row_prefix : group_prefix;
+        const int per = (n + 1023) / 1024;
+        const int i0 = threadIdx.x * per, i1 = min(n, i0 + per);
+        auto count = [&](int i) {
+            if (pass == 0) return (units_of_ctx(row_ctx(a, i)) + cu - 1) / cu;
+            int m = 0;
+            for (int w = 0; w < W; ++w) m = max(m, (units_of_ctx(row_ctx(a, i * W + w)) + cu - 1) / cu);
+            return m;
+        };
+        int s = 0;
+        for (int i = i0; i < i1; ++i) s += count(i);
+        part[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int t = 0; t < 1024; ++t) {
+                const int v = part[t];
+                part[t] = run;
+                run += v;
+            }
+            out[n] = run;
+        }
+        __syncthreads();
+        int run = part[threadIdx.x];
+        for (int i = i0; i < i1; ++i) {
+            out[i] = run;
+            run += count(i);
+        }
+        __syncthreads();
     }
 }
 
@@ -1284,7 +1363,8 @@ static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
 
 static size_t ws_bytes_needed(int B, int H, int D, int num_tiles, int tile_size, int sm_count) {
     const int max_units = (int)(((int64_t)num_tiles * tile_size + kUnitTok - 1) / kUnitTok);
-    return ws_slots((int64_t)B * H, max_units, sm_count) * (size_t)(D + 2) * sizeof(float) + 256;
+    return ws_slots((int64_t)B * H, max_units, sm_count) * (size_t)(D + 2) * sizeof(float) + 256 +
+           2 * ((size_t)B + 2) * sizeof(int);  // + row / group chunk prefixes of the ragged group kernel
 }
 
 template <int D, int KV>
@@ -1396,10 +1476,20 @@ static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStr
     const uint64_t total_tokens = (uint64_t)a.total_pages * a.tile_size;
     if (!make_pool_map(&tmK, a.k_pool, total_tokens) || !make_pool_map(&tmV, a.v_pool, total_tokens))
         return PA_ERR_UNSUPPORTED;
+    cudaError_t e;
+    if (a.ctx_lens) {  // ragged: per-row context lengths -> chunk prefixes in the workspace
+        int* rp = reinterpret_cast<int*>(w + nslots * (size_t)(D + 2));
+        int* gp = rp + a.B + 2;
+        group_prefix_kernel<<<1, 1024, 0, st>>>(a, W, cu, rp, gp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        a.row_prefix = rp;
+        a.group_prefix = gp;
+    }
     const size_t smem = (size_t)kOvWarps * S * kGroupStageBytes + (size_t)kOvWarps * S * (8 + 4) + 8 +
                         (size_t)kOvWarps * 16 * sizeof(int64_t) + 1024;
     auto kern = paged_decode_group_kernel<kOvWarps, S>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
@@ -1544,15 +1634,14 @@ PA_API int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void*
     PA_CHECK_ARG(num_beams > 0 && num_heads > 0 && num_tiles > 0 && total_pages > 0 && B >= 0 && T >= 0);
     PA_CHECK_ARG(temperature != 0.f && tile_size > 0 && beam_width >= 1);
     PA_CHECK_ARG((uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0);
-    if (head_dim != 128 || tile_size % kUnitTok != 0 || beam_width > kGroupMaxW || d_ctx_lens != nullptr)
-        return PA_ERR_UNSUPPORTED;
+    if (head_dim != 128 || tile_size % kUnitTok != 0 || beam_width > kGroupMaxW) return PA_ERR_UNSUPPORTED;
     if (B % beam_width != 0) return PA_ERR_INVALID_ARG;
     if (B == 0) return PA_OK;
     DecodeArgs a{};
     a.q = d_q; a.out = d_out; a.lse_out = d_lse_out;
     a.k_pool = static_cast<const uint8_t*>(d_k_pool);
     a.v_pool = static_cast<const uint8_t*>(d_v_pool);
-    a.table = d_table; a.beam_ids = d_beam_ids; a.ctx_lens = nullptr; a.rope = d_rope;
+    a.table = d_table; a.beam_ids = d_beam_ids; a.ctx_lens = d_ctx_lens; a.rope = d_rope;
     a.num_beams = num_beams; a.H = num_heads; a.num_tiles = num_tiles; a.total_pages = total_pages;
     a.B = B; a.T = T; a.tile_size = tile_size;
     a.num_splits = 1;

@@ -6,9 +6,11 @@
 // Query t of row b attends the cached keys [0, ctx_start[b] + t] of table row beam(b).  Every
 // (b, t) pair is an independent decode row that shares its pages with the other queries of b, so
 // the op is expressed on the decode kernels: a pack kernel transposes q to [B*Tq, H, D] and writes
-// the per-row table-row / context-length arrays (beam indirection + causal limit), the split-KV
-// decode kernel runs over B*Tq rows (the shared pages are served by the 126 MB L2), an unpack
-// kernel transposes the result back.  K/V of the Tq new tokens must already be in the pages
+// the per-row table-row / context-length arrays (beam indirection + causal limit); for fp16 pages with
+// head_dim 128 the tensor-core group kernel then treats 4 consecutive query positions as one group
+// (every K/V unit staged once per 4 queries, mma.sync QK^T and PV), otherwise the split-KV decode kernel
+// runs over B*Tq rows (the shared pages are served by the 126 MB L2); an unpack kernel transposes the
+// result back.  K/V of the Tq new tokens must already be in the pages
 // (pa_kv_append_* with one row per (b, t)).
 #include "pa_common.cuh"
 
@@ -89,7 +91,16 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     if (e != cudaSuccess) return (int)e;
     const int T = num_tiles * tile_size;  // upper bound; the per-row ctx array is the causal limit
     int stt;
-    if (kv == 0)
+    // fp16, head_dim 128: consecutive query positions of a row share every page, so W of them form a
+    // "beam group" of the tensor-core group kernel (each K/V unit is staged once for W queries; the
+    // per-row context length is the causal limit).  Otherwise one decode row per query.
+    const int W = (Tq % 4 == 0) ? 4 : ((Tq % 2 == 0) ? 2 : 1);
+    if (kv == 0 && head_dim == 128 && tile_size % 16 == 0 && ((uintptr_t)d_k_pool % 128 == 0) &&
+        ((uintptr_t)d_v_pool % 128 == 0))
+        stt = pa_paged_decode_f16_group(q_rows, out_rows, d_k_pool, d_v_pool, d_table, num_beams, num_heads,
+                                        num_tiles, total_pages, beam_rows, ctx_rows, R, T, head_dim, tile_size,
+                                        temperature, nullptr, W, nullptr, dws, dws_bytes, stream);
+    else if (kv == 0)
         stt = pa_paged_decode_f16(q_rows, out_rows, d_k_pool, d_v_pool, d_table, num_beams, num_heads, num_tiles,
                                   total_pages, beam_rows, ctx_rows, R, T, head_dim, tile_size, temperature, nullptr,
                                   nullptr, dws, dws_bytes, stream);

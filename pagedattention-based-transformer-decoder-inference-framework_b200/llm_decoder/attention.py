@@ -177,7 +177,7 @@ def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_s
 
 
 def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam_ids=None, rotary_emb=None,
-                       lse_out=None):
+                       lse_out=None, ctx_lens=None):
     """Beam-aware decode (pa_paged_decode_f16_group): rows [g*W, (g+1)*W) are the W beams of group g;
     pages with equal ids within a group are read once.  q/out [B, H, D] f32 CUDA tensors."""
     pt = kv_cache.page_table_
@@ -189,7 +189,7 @@ def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam
         st = _cabi.lib().pa_paged_decode_f16_group(
             q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
             pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids),
-            None, B, T, D, kv_cache.tile_size_, float(temperature), _cabi.ptr(rotary_emb), int(beam_width),
+            _cabi.ptr(ctx_lens), B, T, D, kv_cache.tile_size_, float(temperature), _cabi.ptr(rotary_emb), int(beam_width),
             _cabi.ptr(lse_out), ws.data_ptr(), ws.numel(), _cabi.stream())
     _cabi.check(st, "pa_paged_decode_f16_group")
     return out

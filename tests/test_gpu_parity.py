@@ -324,8 +324,13 @@ def test_tile_offload_in_reference_cpu_format(ld, oracle, kv, tmp_path):
 def test_prefill_causal_matches_oracle(ld, oracle, kv):
     """q/out [B, H, Tq, D]; query t of row b sees keys [0, ctx_start[b] + t] (causal rule of
     attention_kernel_utils.cuh:70-79), checked against the oracle run once per (b, t)."""
-    B, H, D, Tq = 2, 3, 128, 37
-    start = np.array([0, 23], np.int32)
+    _prefill_case(ld, oracle, kv, Tq=37, start=np.array([0, 23], np.int32))    # odd Tq: one row per query
+    _prefill_case(ld, oracle, kv, Tq=40, start=np.array([5, 0], np.int32))     # Tq % 4 == 0: tensor-core groups (fp16)
+    _prefill_case(ld, oracle, kv, Tq=600, start=np.array([0, 0], np.int32), check_forward=False)  # many chunks
+
+
+def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True):
+    B, H, D = 2, 3, 128
     case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv)
     rng = np.random.default_rng(81)
     q = rng.standard_normal((B, H, Tq, D)).astype(np.float32)
@@ -342,7 +347,7 @@ def test_prefill_causal_matches_oracle(ld, oracle, kv):
     exp_case["ctx_lens"] = (start[:, None] + np.arange(Tq, dtype=np.int32)[None, :] + 1).reshape(-1).astype(np.int32)
     exp = oracle_attention(exp_case).reshape(B, Tq, H, D).transpose(0, 2, 1, 3)
     np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
-    if kv == "f16":
+    if kv == "f16" and check_forward:
         # the reference-facing call: is_prefill=True with q [B, H, T, D] = causal self-attention over T tokens
         T = 48
         q2 = rng.standard_normal((B, H, T, D)).astype(np.float32)
@@ -404,6 +409,25 @@ def test_group_decode_matches_oracle(ld, oracle, ci):
             if sv.size:
                 r = np.log(np.exp(sv - sv.max()).sum()) + sv.max()
                 assert abs(lse.cpu().numpy()[b, h] - r) <= 1e-3 * max(1.0, abs(r))
+
+
+@pytest.mark.parametrize("W", [1, 2, 4])
+def test_group_decode_per_row_context(ld, oracle, W):
+    """Ragged mode of the group kernel: every row has its own context length (random, including 0 and
+    lengths that end inside a page), rows of a group share or do not share pages."""
+    case = make_case(B=8, H=3, D=128, T=333, seed=70 + W, beam_width=W if W > 1 else 1,
+                     shared_prefix=160 if W > 1 else 0, ragged=True, unmapped_frac=0.03)
+    exp = oracle_attention(case)
+    kvc = to_device_cache(case)
+    q = torch.from_numpy(case["q"]).cuda()
+    out = torch.full_like(q, float("nan"))
+    bid = None if case["beam_ids"] is None else torch.from_numpy(case["beam_ids"]).cuda()
+    ld.paged_decode_group(q, out, kvc, 8, case["T"], W, case["temperature"], beam_ids=bid,
+                          ctx_lens=torch.from_numpy(case["ctx_lens"]).cuda())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
 
 
 def test_group_decode_poisoned_tail_and_unsupported(ld, oracle):
