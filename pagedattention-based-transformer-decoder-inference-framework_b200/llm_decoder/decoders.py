@@ -459,9 +459,48 @@ class INT8Decoder(_DecoderBase):
             bb = rd("mlp_biases.bin", inter + hid) * np.float32(deq(rel("mlp_biases.bin")))
             L.fc1_b, L.fc2_b = self._dev(bb[:inter]), self._dev(bb[inter:])
         self._graph = None
+        self._emb_T = None
 
     def _embedding_table(self):
         return self.embedding, 1, float(self.emb_qscale)
+
+    GEMM_LOGITS_MIN_ROWS = 9  # more rows than one pass of the GEMV kernel: logits become an int8 GEMM
+
+    def _head(self, x_rows):
+        """Batches of more than 8 rows compute the logits on the tensor cores: rows are quantised like every
+        other activation of this decoder (int8_quant.cpp:59-64, 15-28) and multiplied with the transposed int8
+        embedding table by the tcgen05 GEMM (dequantising epilogue); up to 8 rows keep the exact f32 x int8
+        GEMV with the sampler folded in."""
+        B = self._batch
+        if B < self.GEMM_LOGITS_MIN_ROWS:
+            return super()._head(x_rows)
+        V, hid, dev = self.vocab_size_, self.hidden_dim_, self.device
+        Vp = (V + 15) // 16 * 16
+        if getattr(self, "_emb_T", None) is None or self._emb_T.shape != (hid, Vp):
+            self._emb_T = torch.zeros((hid, Vp), dtype=torch.int8, device=dev)
+            self._emb_T[:, :V] = self.embedding.t()
+            self._pad_bias = torch.zeros(Vp, dtype=torch.float32, device=dev)
+            self._pad_bias[V:] = float("-inf")  # padded columns never win the argmax
+        if getattr(self, "_logits_pad", None) is None or self._logits_pad.shape != (B, Vp):
+            self._logits_pad = torch.empty((B, Vp), dtype=torch.float32, device=dev)
+            self._lq = torch.empty((B, hid), dtype=torch.int8, device=dev)
+            self._ls = torch.empty(B, dtype=torch.float32, device=dev)
+        lib, s = self._lib, _cabi.stream()
+        self._quant_rows(x_rows, self._lq, self._ls, B, hid)
+        self._chk(lib.pa_gemm_i8_dequant(self._lq.data_ptr(), self._emb_T.data_ptr(), self._logits_pad.data_ptr(), 1,
+                                         B, Vp, hid, self._ls.data_ptr(), 1.0 / float(self.emb_qscale),
+                                         self._pad_bias.data_ptr(), _cabi.ACT[""], s), "pa_gemm_i8_dequant")
+        self.logits = self._logits_pad[:, :V]
+        sp = getattr(self, "_sampling", None)
+        if sp is None:
+            self._chk(lib.pa_argmax_f32(self._logits_pad.data_ptr(), B, Vp, self._temperature, self.ARGMAX_DIVIDE,
+                                        self.ids.data_ptr(), s), "pa_argmax_f32")
+            return
+        from . import sampling
+        probs = sampling.softmax_temperature(self.logits.contiguous(), 1.0 / self._temperature)
+        sampling.apply_topk_topp_filter(probs, sp["top_k"], sp["top_p"], sp["eos_token_id"], sp["eos_thresh"])
+        u = torch.rand(B, device=dev, generator=sp["generator"])
+        sampling.sample_from_probs(probs, u, out=self.ids)
 
     def _embed(self, bf, ids):
         self._chk(self._lib.pa_embedding_i8(self.embedding.data_ptr(), float(self.emb_qscale), ids.data_ptr(), bf.R,

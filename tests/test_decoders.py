@@ -324,3 +324,10 @@ def test_int8_decoder_quantize_load_generate(oracle, tmp_path):
         np.testing.assert_allclose(lg, exp, rtol=5e-3, atol=5e-3 * np.abs(exp).max())
     with pytest.raises(RuntimeError):
         dec.load_quantized_weights(str(tmp_path / "missing"))
+    # batches of more than 8 rows take the tensor-core logits path (activations quantised like the MLP inputs):
+    # every row is still the oracle's argmax up to the quantisation noise of its logits
+    prompts = [[int(t) for t in rng.integers(0, V, 3)] for _ in range(11)]
+    outs = dec.generate_batch(prompts, 6, 1.0)
+    assert all(len(o) == 9 and o[:3] == p for o, p in zip(outs, prompts))
+    for o in outs[:4]:
+        check_teacher_forced(o, 3, RefDecoder(wq, H, D, int8=True), 1.0, 0, None, 3e-2)
