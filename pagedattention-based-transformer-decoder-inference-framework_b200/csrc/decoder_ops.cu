@@ -12,7 +12,8 @@
 
 namespace pa {
 
-constexpr int kRowChunk = 8;  // activation rows processed per pass over the weights
+constexpr int kRowChunk = 8;     // rows per pass of the logits GEMV (one warp per vocab row)
+constexpr int kLinRows = 16;     // activation rows per pass over the weights in linear_kn_kernel
 
 // ---- embedding --------------------------------------------------------------------------
 template <typename WT>
@@ -100,41 +101,60 @@ __global__ void __launch_bounds__(256) linear_kn_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, int rows, int K, int N,
                                                         int act, int kslice, float* __restrict__ out,
                                                         float* __restrict__ partial) {
-    __shared__ float red[8][kRowChunk][32];
+    constexpr int KT = 256;                          // k rows staged per tile
+    __shared__ __align__(16) float xs[KT][kLinRows];  // activations of the tile, [k][row]: one k = 4 x LDS.128
+    __shared__ float red[8][kLinRows][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 32 + lane;
-    const int r0 = blockIdx.y * kRowChunk;
-    const int nr = min(kRowChunk, rows - r0);
+    const int r0 = blockIdx.y * kLinRows;
+    const int nr = min(kLinRows, rows - r0);
     const int k0 = blockIdx.z * kslice, k1 = min(K, k0 + kslice);
-    float acc[kRowChunk];
+    float acc[kLinRows];
 #pragma unroll
-    for (int r = 0; r < kRowChunk; ++r) acc[r] = 0.f;
-    if (n < N) {
-        const float* xr = x + (int64_t)r0 * K;
+    for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+    for (int kt = k0; kt < k1; kt += KT) {
+        const int kn = min(KT, k1 - kt);
+        __syncthreads();  // previous tile fully consumed
+        if ((int)threadIdx.x < kn) {
+#pragma unroll
+            for (int r = 0; r < kLinRows; ++r)
+                xs[threadIdx.x][r] = (r < nr) ? x[(int64_t)(r0 + r) * K + kt + threadIdx.x] : 0.f;
+        }
+        __syncthreads();
+        if (n < N) {
 #pragma unroll 4
-        for (int k = k0 + warp; k < k1; k += 8) {
-            const float w = __ldcs(W + (int64_t)k * N + n);  // streamed once
+            for (int kk = warp; kk < kn; kk += 8) {
+                const float w = __ldcs(W + (int64_t)(kt + kk) * N + n);  // streamed once per row chunk
+                const float4* xv = reinterpret_cast<const float4*>(xs[kk]);
 #pragma unroll
-            for (int r = 0; r < kRowChunk; ++r)
-                if (r < nr) acc[r] = fmaf(__ldg(xr + (int64_t)r * K + k), w, acc[r]);
+                for (int r4 = 0; r4 < kLinRows / 4; ++r4) {
+                    const float4 v = xv[r4];
+                    acc[4 * r4 + 0] = fmaf(v.x, w, acc[4 * r4 + 0]);
+                    acc[4 * r4 + 1] = fmaf(v.y, w, acc[4 * r4 + 1]);
+                    acc[4 * r4 + 2] = fmaf(v.z, w, acc[4 * r4 + 2]);
+                    acc[4 * r4 + 3] = fmaf(v.w, w, acc[4 * r4 + 3]);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int r = 0; r < kRowChunk; ++r) red[warp][r][lane] = acc[r];
+    for (int r = 0; r < kLinRows; ++r) red[warp][r][lane] = acc[r];
     __syncthreads();
-    // 256 threads finish kRowChunk x 32 outputs
-    const int rr = threadIdx.x >> 5, cc = threadIdx.x & 31;
+    // 256 threads finish kLinRows x 32 outputs (8 rows per pass)
+    const int cc = threadIdx.x & 31;
     const int nn = blockIdx.x * 32 + cc;
-    if (rr < nr && nn < N) {
-        float s = 0.f;
+    for (int rr = threadIdx.x >> 5; rr < kLinRows; rr += 8) {
+        if (rr < nr && nn < N) {
+            float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][rr][cc];
-        if (partial) {
-            partial[((int64_t)blockIdx.z * rows + r0 + rr) * N + nn] = s;
-        } else {
-            s += bias ? bias[nn] : 0.f;
-            if (act == PA_ACT_RELU) s = fmaxf(s, 0.f);
-            out[(int64_t)(r0 + rr) * N + nn] = s;
+            for (int w = 0; w < 8; ++w) s += red[w][rr][cc];
+            if (partial) {
+                partial[((int64_t)blockIdx.z * rows + r0 + rr) * N + nn] = s;
+            } else {
+                s += bias ? bias[nn] : 0.f;
+                if (act == PA_ACT_RELU) s = fmaxf(s, 0.f);
+                out[(int64_t)(r0 + rr) * N + nn] = s;
+            }
         }
     }
 }
@@ -334,7 +354,7 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     if (rows == 0) return PA_OK;
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
-    const int strips = (N + 31) / 32, chunks = (rows + kRowChunk - 1) / kRowChunk;
+    const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
     // slice K until ~2 CTAs per SM stream the weights; every slice keeps >= 64 k-rows (8 per warp)
     int nslices = (2 * di.sm_count + strips * chunks - 1) / (strips * chunks);
     if (nslices > K / 64) nslices = K / 64;

@@ -352,9 +352,25 @@ class CUDADecoder(_DecoderBase):
             L.fc1_w, L.fc1_b = self._dev(fc1.reshape(hid, inter)), self._dev(b1)
             L.fc2_w, L.fc2_b = self._dev(fc2.reshape(inter, hid)), self._dev(b2)
         self._graph = None
+        self._emb_T = None
 
     def _embedding_table(self):
         return self.embedding, 4, 1.0
+
+    def _head(self, x_rows):
+        """More than 8 rows: logits = x . E^T through the fp32 linear kernel on a transposed copy of the table
+        (weights streamed once per 16 rows) followed by the argmax kernel; up to 8 rows: the GEMV with the
+        sampler folded in."""
+        B = self._batch
+        if B <= 8 or getattr(self, "_sampling", None) is not None:
+            return super()._head(x_rows)
+        if getattr(self, "_emb_T", None) is None or self._emb_T.shape != (self.hidden_dim_, self.vocab_size_):
+            self._emb_T = self.embedding.t().contiguous()
+        lib, s = self._lib, _cabi.stream()
+        self._chk(lib.pa_linear_f32(x_rows.data_ptr(), self._emb_T.data_ptr(), None, B, self.hidden_dim_,
+                                    self.vocab_size_, _cabi.ACT[""], self.logits.data_ptr(), s), "pa_linear_f32")
+        self._chk(lib.pa_argmax_f32(self.logits.data_ptr(), B, self.vocab_size_, self._temperature,
+                                    self.ARGMAX_DIVIDE, self.ids.data_ptr(), s), "pa_argmax_f32")
 
     def _embed(self, bf, ids):
         self._chk(self._lib.pa_embedding_f32(self.embedding.data_ptr(), ids.data_ptr(), bf.R, self.hidden_dim_,
