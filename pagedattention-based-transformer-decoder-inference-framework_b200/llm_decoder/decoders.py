@@ -120,6 +120,7 @@ class _DecoderBase:
         self._best = torch.zeros(B, dtype=torch.int64, device=dev)  # argmax keys of pa_logits_argmax
         self._ws = self.kv_caches[0].workspace(B)
         self._graph = None
+        self._step_warm = 0  # a new batch size gets one eager step before capture (lazy buffers, GEMM scratch)
 
     def reset(self):
         """Forget all cached context (positions back to 0; pages keep their assignment)."""
