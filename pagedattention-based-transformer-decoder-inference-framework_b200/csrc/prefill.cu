@@ -12,6 +12,9 @@
 // runs over B*Tq rows (the shared pages are served by the 126 MB L2); an unpack kernel transposes the
 // result back.  K/V of the Tq new tokens must already be in the pages
 // (pa_kv_append_* with one row per (b, t)).
+#include <cstdlib>
+
+#include "mma_utils.cuh"
 #include "pa_common.cuh"
 
 namespace pa {
@@ -47,6 +50,232 @@ __global__ void prefill_unpack_kernel(const float* __restrict__ out_rows, float*
     }
 }
 
+// ------------------------------------------------------------------ tensor-core prefill kernel
+// Flash-attention forward over the paged cache for fp16 pages, head_dim 128.  One CTA = 64 consecutive
+// query positions of one (row, head): 4 compute warps x 16 queries (mma.sync m16n8k16, fp16 operands,
+// fp32 accumulate: S = Q K^T and O += P V per 16-token unit, online softmax in registers, the S
+// accumulator fragments are re-packed in place as the A operand of P V) + 1 producer warp that walks the
+// page table and stages K/V units with TMA tensor copies (SWIZZLE_128B, conflict-free ldmatrix) into a
+// 4-stage ring shared by the 4 warps.  Causal limit per query; tiles are launched last-first (the last
+// query tile of a row has the longest context).  q/out stay in the reference's [B, H, T, D] layout.
+constexpr int kPfQ = 64;
+constexpr int kPfStages = 4;
+constexpr int kPfStageBytes = 8192;
+
+struct PrefillArgs {
+    const float* q;
+    float* out;
+    const int32_t* table;
+    const int32_t* beam_ids;
+    const int32_t* ctx_start;
+    int num_beams, H, num_tiles, total_pages, B, Tq, tile_size;
+    float qscale;  // log2(e) / temperature
+};
+
+__global__ void __launch_bounds__(160) prefill_fa_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                         const __grid_constant__ CUtensorMap tmV,
+                                                         const PrefillArgs a) {
+    constexpr int D = 128, S = kPfStages;
+    extern __shared__ __align__(1024) uint8_t smem_p[];
+    const uint32_t base = (smem_u32(smem_p) + 1023u) & ~1023u;
+    uint8_t* gen = smem_p + (base - smem_u32(smem_p));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gen + S * kPfStageBytes);  // full[S], empty[S]
+    int* meta = reinterpret_cast<int*>(bars + 2 * S);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(full0 + i * 8, 1);
+            mbar_init(empty0 + i * 8, 4);  // one arrival per compute warp
+        }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+    }
+    __syncthreads();
+
+    const int nqt = (a.Tq + kPfQ - 1) / kPfQ;
+    const int bh_total = a.B * a.H;
+    const int qt = nqt - 1 - (int)(blockIdx.x / bh_total);  // longest tiles first
+    const int bh = (int)(blockIdx.x % bh_total);
+    const int b = bh / a.H, h = bh - b * a.H;
+    const int start = a.ctx_start ? a.ctx_start[b] : 0;
+    const int q_last = min(a.Tq, (qt + 1) * kPfQ) - 1;
+    const int cap = a.num_tiles * a.tile_size;
+    const int kmax = min(cap, start + q_last + 1);  // keys [0, kmax) can be visible to this tile
+    const int n_units = (kmax + 15) >> 4;
+    const int upt = a.tile_size >> 4;
+
+    if (warp == 4) {  // ---------------- producer
+        if (lane == 0) {
+            const int beam = a.beam_ids ? a.beam_ids[b] : b;
+            const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
+                                      ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
+            int s = 0;
+            uint32_t ph = 1;
+            for (int u = 0; u < n_units; ++u) {
+                int page = trow ? __ldg(trow + u / upt) : -1;
+                if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
+                mbar_wait(empty0 + s * 8, ph);
+                meta[s] = page >= 0 ? min(16, kmax - u * 16) : 0;
+                if (page >= 0) {
+                    const int row0 = page * a.tile_size + (u % upt) * 16;
+                    const uint32_t dst = base + s * kPfStageBytes;
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(full0 + s * 8, kPfStageBytes);
+                    tma_load_2d(dst, &tmK, 0, row0, full0 + s * 8);
+                    tma_load_2d(dst + 2048, &tmK, 64, row0, full0 + s * 8);
+                    tma_load_2d(dst + 4096, &tmV, 0, row0, full0 + s * 8);
+                    tma_load_2d(dst + 6144, &tmV, 64, row0, full0 + s * 8);
+                } else {
+                    mbar_arrive(full0 + s * 8);  // unmapped page: skipped (...fused.cu:32)
+                }
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps
+    const int g8 = lane >> 2, j4 = lane & 3;
+    const int t0 = qt * kPfQ + warp * 16 + g8, t1 = t0 + 8;  // this thread's two query rows
+    const int64_t qbase = ((int64_t)b * a.H + h) * a.Tq;
+    uint32_t qa[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int d0 = s * 16 + hh * 8 + j4 * 2;
+            float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
+            if (t0 < a.Tq) x0 = *reinterpret_cast<const float2*>(a.q + (qbase + t0) * D + d0);
+            if (t1 < a.Tq) x1 = *reinterpret_cast<const float2*>(a.q + (qbase + t1) * D + d0);
+            qa[s][hh * 2 + 0] = pack_half2(x0.x * a.qscale, x0.y * a.qscale);
+            qa[s][hh * 2 + 1] = pack_half2(x1.x * a.qscale, x1.y * a.qscale);
+        }
+    }
+    const int qpos0 = (t0 < a.Tq) ? start + t0 : -1, qpos1 = (t1 < a.Tq) ? start + t1 : -1;  // last visible key
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[16][4];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f; }
+
+    int s = 0;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int u = 0; u < n_units; ++u) {
+        mbar_wait(full0 + s * 8, ph);
+        const int nvalid = meta[s];
+        // units entirely above this warp's last query are masked for every row: skip the math
+        const int kp0 = u * 16;
+        if (nvalid > 0 && kp0 <= start + qt * kPfQ + warp * 16 + 15) {  // (warp-uniform condition)
+            const uint32_t sb = base + s * kPfStageBytes;
+            if (nvalid < 16) {  // rows past the context end may hold anything: zero those V rows
+                for (int i = lane; i < (16 - nvalid) * 16; i += 32) {
+                    const int r = nvalid + i / 16, c = i % 16;
+                    const uint32_t addr = sb + 4096 + (c >> 3) * 2048 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+                }
+                __syncwarp();
+            }
+            float sacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            {
+                const int mi = lane >> 3;
+                const int r = (lane & 7) + (mi >> 1) * 8;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int c = 2 * (ks & 3) + (mi & 1);
+                    const uint32_t addr = sb + (ks >> 2) * 2048 + r * 128 + ((c ^ (r & 7)) << 4);
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(addr, b0, b1, b2, b3);
+                    mma_16816_full(sacc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                    mma_16816_full(sacc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                }
+            }
+            // causal mask + online softmax; sacc[nt][0,1] -> row t0, sacc[nt][2,3] -> row t1
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kp = kp0 + nt * 8 + j4 * 2 + e;
+                    const bool in = (nt * 8 + j4 * 2 + e) < nvalid;
+                    sacc[nt][e] = (in && kp <= qpos0) ? sacc[nt][e] : -INFINITY;
+                    sacc[nt][2 + e] = (in && kp <= qpos1) ? sacc[nt][2 + e] : -INFINITY;
+                    mx0 = fmaxf(mx0, sacc[nt][e]);
+                    mx1 = fmaxf(mx1, sacc[nt][2 + e]);
+                }
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
+            const float c0 = (mn0 == -INFINITY) ? 1.f : fast_exp2(m_run[0] - mn0);
+            const float c1 = (mn1 == -INFINITY) ? 1.f : fast_exp2(m_run[1] - mn1);
+            float p[2][4];
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    p[nt][e] = (sacc[nt][e] == -INFINITY) ? 0.f : fast_exp2(sacc[nt][e] - mn0);
+                    p[nt][2 + e] = (sacc[nt][2 + e] == -INFINITY) ? 0.f : fast_exp2(sacc[nt][2 + e] - mn1);
+                    ps0 += p[nt][e];
+                    ps1 += p[nt][2 + e];
+                }
+            }
+            l_run[0] = fmaf(l_run[0], c0, ps0);
+            l_run[1] = fmaf(l_run[1], c1, ps1);
+            m_run[0] = mn0;
+            m_run[1] = mn1;
+            if (__any_sync(0xffffffffu, c0 != 1.f || c1 != 1.f)) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    o[t][0] *= c0; o[t][1] *= c0;
+                    o[t][2] *= c1; o[t][3] *= c1;
+                }
+            }
+            const uint32_t pa0 = pack_half2(p[0][0], p[0][1]), pa1 = pack_half2(p[0][2], p[0][3]);
+            const uint32_t pa2 = pack_half2(p[1][0], p[1][1]), pa3 = pack_half2(p[1][2], p[1][3]);
+            {
+                const int mi = lane >> 3;
+                const int r = (lane & 7) + (mi & 1) * 8;
+#pragma unroll
+                for (int n2 = 0; n2 < 8; ++n2) {
+                    const int c = 2 * (n2 & 3) + (mi >> 1);
+                    const uint32_t addr = sb + 4096 + (n2 >> 2) * 2048 + r * 128 + ((c ^ (r & 7)) << 4);
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(addr, b0, b1, b2, b3);
+                    mma_16816_full(o[2 * n2], pa0, pa1, pa2, pa3, b0, b1);
+                    mma_16816_full(o[2 * n2 + 1], pa0, pa1, pa2, pa3, b2, b3);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + s * 8);
+        if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+    // normalise and store: o[nt][0,1] -> (row t0, dims nt*8 + j4*2 + {0,1}); o[nt][2,3] -> row t1
+    float l0 = l_run[0], l1 = l_run[1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / (l0 + 1e-6f), i1 = 1.f / (l1 + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+        const int d = nt * 8 + j4 * 2;
+        if (t0 < a.Tq) *reinterpret_cast<float2*>(a.out + (qbase + t0) * D + d) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+        if (t1 < a.Tq) *reinterpret_cast<float2*>(a.out + (qbase + t1) * D + d) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace pa
@@ -67,9 +296,35 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
                          const int32_t* d_ctx_start, int B, int Tq, int head_dim, int tile_size, float temperature,
                          void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
-    PA_CHECK_ARG(d_q && d_out && d_k_pool && d_v_pool && d_table && d_workspace);
+    PA_CHECK_ARG(d_q && d_out && d_k_pool && d_v_pool && d_table);
     PA_CHECK_ARG(B >= 0 && Tq > 0 && num_heads > 0 && head_dim > 0 && head_dim % 4 == 0);
+    PA_CHECK_ARG(num_beams > 0 && num_tiles > 0 && total_pages > 0 && tile_size > 0 && temperature != 0.f);
     if (B == 0) return PA_OK;
+    if (kv == 0 && head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 &&
+        (uintptr_t)d_v_pool % 128 == 0 && d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0)) {
+        // tensor-core flash-attention kernel, straight on the [B, H, Tq, D] layout (no workspace)
+        CUtensorMap tmK, tmV;
+        const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
+        if (make_pool_map(&tmK, d_k_pool, total_tokens) && make_pool_map(&tmV, d_v_pool, total_tokens)) {
+            PrefillArgs pa{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles,
+                           total_pages, B, Tq, tile_size, 1.4426950408889634f / temperature};
+            const int nqt = (Tq + kPfQ - 1) / kPfQ;
+            const int64_t ctas = (int64_t)B * num_heads * nqt;
+            PA_CHECK_ARG(ctas <= 0x7fffffff);
+            const size_t smem = (size_t)kPfStages * kPfStageBytes + 2 * kPfStages * 8 + kPfStages * 4 + 1024;
+            static bool attr_done[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!attr_done[dev & 63]) {
+                cudaError_t e0 = cudaFuncSetAttribute(prefill_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e0 != cudaSuccess) return (int)e0;
+                attr_done[dev & 63] = true;
+            }
+            prefill_fa_kernel<<<(unsigned)ctas, 160, smem, as_stream(stream)>>>(tmK, tmV, pa);
+            PA_RETURN_LAUNCH_STATUS();
+        }
+    }
+    PA_CHECK_ARG(d_workspace);
     const int64_t R64 = (int64_t)B * Tq;
     PA_CHECK_ARG(R64 <= 0x7fffffff);
     const int R = (int)R64;

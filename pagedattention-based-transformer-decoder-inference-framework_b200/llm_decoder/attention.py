@@ -13,6 +13,8 @@ q / out may be CUDA tensors (zero copy) or HOST buffers (numpy arrays or CPU ten
 buffers are staged through pinned memory and copied inside the call, which is what the
 end-to-end bench measures.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -158,12 +160,19 @@ def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_s
     H, D = pt.num_heads_, kv_cache.head_dim_
     assert q.is_contiguous() and out.is_contiguous() and q.numel() == B * H * Tq * D == out.numel()
     lib = _cabi.lib()
-    need = lib.pa_prefill_workspace_bytes(B, Tq, H, D, pt.num_tiles_, kv_cache.tile_size_)
-    ws = getattr(kv_cache, "_prefill_ws", None)
-    if ws is None or ws.numel() < need:
-        ws = kv_cache._prefill_ws = torch.empty(need, dtype=torch.uint8, device=kv_cache.key_buffer_.device)
+    # fp16 pages with head_dim 128 take the tensor-core flash-attention kernel, which needs no scratch
+    fa = (kv_cache.dtype == "f16" and D == 128 and kv_cache.tile_size_ % 16 == 0 and
+          kv_cache.key_buffer_.data_ptr() % 128 == 0 and kv_cache.value_buffer_.data_ptr() % 128 == 0 and
+          q.data_ptr() != out.data_ptr() and os.environ.get("PA_PREFILL_FA", "1") != "0")
+    ws_ptr, ws_bytes = None, 0
+    if not fa:
+        need = lib.pa_prefill_workspace_bytes(B, Tq, H, D, pt.num_tiles_, kv_cache.tile_size_)
+        ws = getattr(kv_cache, "_prefill_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = kv_cache._prefill_ws = torch.empty(need, dtype=torch.uint8, device=kv_cache.key_buffer_.device)
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     common = (pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids),
-              _cabi.ptr(ctx_start), B, Tq, D, kv_cache.tile_size_, float(temperature), ws.data_ptr(), ws.numel())
+              _cabi.ptr(ctx_start), B, Tq, D, kv_cache.tile_size_, float(temperature), ws_ptr, ws_bytes)
     with torch.cuda.device(kv_cache.key_buffer_.device):
         if kv_cache.dtype == "f16":
             st = lib.pa_paged_prefill_f16(q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
