@@ -560,6 +560,75 @@ def test_c2_full_size_properties(ld, oracle):
     np.testing.assert_allclose(out.cpu().numpy(), 0.75, rtol=1e-5)
 
 
+def test_c4_full_size_properties_int8(ld, oracle):
+    """BASELINE config C4 attention (B=256, H=32, D=128, T=4096, int8 pages + f32 scales, 8.25 GiB of pools):
+    (1) direct == overlap kernel, (2) constant V/scale => out == that constant, (3) sampled (b,h) rows vs oracle."""
+    B, H, D, T, ts = 256, 32, 128, 4096, 16
+    nt = T // ts
+    P = B * H * nt
+    g = torch.Generator(device="cuda").manual_seed(1238)
+    k = torch.randint(-127, 128, (P, ts, D), generator=g, device="cuda", dtype=torch.int8)
+    v = torch.randint(-127, 128, (P, ts, D), generator=g, device="cuda", dtype=torch.int8)
+    ks = torch.rand((P, ts), generator=g, device="cuda") * 20 + 30
+    vs = torch.rand((P, ts), generator=g, device="cuda") * 20 + 30
+    q = torch.randn((B, H, D), generator=g, device="cuda")
+    table = torch.randperm(P, generator=g, device="cuda").to(torch.int32).reshape(B, H, nt)
+    kvc = ld.KVTileCache("i8")
+    kvc.adopt_buffers(k, v, ks, vs)
+    kvc.configure_table(B, H, nt)
+    kvc.page_table_.load_host_table(table.cpu().numpy())
+    temp = float(np.sqrt(D))
+    outs = []
+    for overlap in (False, True):
+        out = torch.empty((B, H, D), device="cuda")
+        ld.AttentionCUDA.forward(q, out, B, H, D, T, None, kvc, None, False, False, overlap, temp)
+        outs.append(out)
+    torch.cuda.synchronize()
+    # the folded int8 offset costs ~8 mantissa bits of the partial sums (paged_decode.cu words_to_float): the two
+    # kernels chunk the context differently, so they agree to ~1e-4 absolute on |out| ~ 1, not to fp32 rounding
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=1e-3, atol=2e-4)
+    rng = np.random.default_rng(6)
+    tb = table.cpu().numpy()
+    for _ in range(4):
+        b, h = int(rng.integers(B)), int(rng.integers(H))
+        idx = torch.from_numpy(tb[b, h].astype(np.int64)).cuda()
+        exp = oracle.cpu.paged_attention(q[b:b + 1, h:h + 1].cpu().numpy(), k[idx].cpu().numpy(), v[idx].cpu().numpy(),
+                                         np.arange(nt, dtype=np.int32).reshape(1, 1, nt), num_beams=1, num_tiles=nt,
+                                         tile_size=ts, T=T, temperature=temp, k_scales=ks[idx].cpu().numpy(),
+                                         v_scales=vs[idx].cpu().numpy())
+        np.testing.assert_allclose(outs[1][b, h].cpu().numpy(), exp[0, 0], rtol=RTOL, atol=ATOL)
+    v.fill_(64)
+    vs.fill_(32.0)
+    out = torch.empty((B, H, D), device="cuda")
+    ld.AttentionCUDA.forward(q, out, B, H, D, T, None, kvc, None, False, False, True, temp)
+    np.testing.assert_allclose(out.cpu().numpy(), 2.0, rtol=3e-4)  # int8 path: ~1e-4 relative (folded offset, rcp.approx)
+
+
+def test_c3_full_size_group_equals_rows(ld):
+    """BASELINE config C3 (32 groups x 4 beams, 32 heads, D=128, 2K ctx = 1792 shared + 256 private tokens):
+    the group kernel (pages read once per group) equals the per-row kernels on the same table."""
+    groups, W, H, D, T, shared, ts = 32, 4, 32, 128, 2048, 1792, 16
+    B, nt, pt_ = groups * W, T // ts, shared // ts
+    g = torch.Generator(device="cuda").manual_seed(1237)
+    unique = groups * H * pt_ + B * H * (nt - pt_)
+    perm = torch.randperm(unique, generator=g, device="cuda").to(torch.int32)
+    table = torch.empty((B, H, nt), dtype=torch.int32, device="cuda")
+    table[:, :, :pt_] = perm[:groups * H * pt_].reshape(groups, 1, H, pt_).expand(groups, W, H, pt_).reshape(B, H, pt_)
+    table[:, :, pt_:] = perm[groups * H * pt_:].reshape(B, H, nt - pt_)
+    kvc = ld.KVTileCache("f16")
+    kvc.adopt_buffers(torch.randn((unique, ts, D), generator=g, device="cuda", dtype=torch.float16),
+                      torch.randn((unique, ts, D), generator=g, device="cuda", dtype=torch.float16))
+    kvc.configure_table(B, H, nt)
+    kvc.page_table_.load_host_table(table.cpu().numpy())
+    q = torch.randn((B, H, D), generator=g, device="cuda")
+    temp = float(np.sqrt(D))
+    o_rows, o_grp = torch.empty_like(q), torch.empty_like(q)
+    ld.AttentionCUDA.forward(q, o_rows, B, H, D, T, None, kvc, None, False, True, False, temp)
+    ld.paged_decode_group(q, o_grp, kvc, B, T, W, temp)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o_grp.cpu().numpy(), o_rows.cpu().numpy(), rtol=2e-5, atol=2e-6)
+
+
 # ------------------------------------------------------------------ int8 GEMM (tcgen05 kind::i8)
 GEMM_SHAPES = [
     (1, 5, 32, 48),        # BATCH, M, N, K : tiny, ragged M
