@@ -131,23 +131,36 @@ class _DecoderBase:
     def _chk(self, st, what):
         _cabi.check(st, what)
 
-    def _attention(self, layer_idx, q, out, R, ctx_lens, beam_ids, ws):
+    def _attention(self, layer_idx, q, out, R, ctx_lens, beam_ids, ws, prefill_shape=None):
         kvc = self.kv_caches[layer_idx]
         pt = kvc.page_table_
         lib = self._lib
+        if prefill_shape is not None and kvc.dtype == "f16" and self.head_dim_ == 128:
+            # prompt pass on fp16 pages: the tensor-core flash-attention prefill kernel ([B, H, n, D] layout)
+            from .attention import paged_prefill
+            B, n = prefill_shape
+            H, D = self.num_heads_, self.head_dim_
+            qb = q.view(B, n, H, D).permute(0, 2, 1, 3).contiguous()
+            ob = torch.empty_like(qb)
+            paged_prefill(qb, ob, kvc, B, n, self.attn_temperature)
+            out.view(B, n, H, D).copy_(ob.permute(0, 2, 1, 3))
+            return
+        # the persistent kernel keeps a per-row chunk prefix in shared memory: very many rows (long prompts in
+        # the row-per-query prefill) go through the split-KV grid kernel instead
+        use_overlap = self.use_overlap and R <= 2048
         common = (pt.d_table_.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kvc.total_pages_,
                   _cabi.ptr(beam_ids), ctx_lens.data_ptr(), R, self.max_seq_len_, self.head_dim_, kvc.tile_size_,
                   self.attn_temperature, None, None, ws.data_ptr(), ws.numel(), _cabi.stream())
         if kvc.dtype == "f16":
-            fn = lib.pa_paged_decode_f16_overlap if self.use_overlap else lib.pa_paged_decode_f16
+            fn = lib.pa_paged_decode_f16_overlap if use_overlap else lib.pa_paged_decode_f16
             st = fn(q.data_ptr(), out.data_ptr(), kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr(), *common)
         else:
-            fn = lib.pa_paged_decode_i8_overlap if self.use_overlap else lib.pa_paged_decode_i8
+            fn = lib.pa_paged_decode_i8_overlap if use_overlap else lib.pa_paged_decode_i8
             st = fn(q.data_ptr(), out.data_ptr(), kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr(),
                     kvc.k_scales_.data_ptr(), kvc.v_scales_.data_ptr(), *common)
         self._chk(st, "pa_paged_decode")
 
-    def _layers(self, bf, ids, positions, ctx_lens, beam_ids, ws):
+    def _layers(self, bf, ids, positions, ctx_lens, beam_ids, ws, prefill_shape=None):
         """The decoder stack (decoder_block.hpp:41-62) for bf.R rows: row r is token ids[r] at position
         positions[r] of table row beam_ids[r] (None: r) attending ctx_lens[r] cached tokens (its own K/V
         included).  Leaves the final hidden states in bf.x."""
@@ -158,7 +171,7 @@ class _DecoderBase:
                                             self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
             nview = bf.n.view(R, self.num_heads_, self.head_dim_)
             self.kv_caches[li].append(nview, nview, positions, beam_ids)  # K = V = LN1 output (see module doc)
-            self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws)
+            self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws, prefill_shape)
             self._chk(lib.pa_layer_norm_f32(bf.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), R, hid,
                                             self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
             self._mlp(bf, L)
@@ -206,7 +219,7 @@ class _DecoderBase:
         beam = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(n)
         ws = torch.empty(self._lib.pa_decode_workspace_bytes(R, self.num_heads_, self.head_dim_, self._num_tiles,
                                                              self.tile_size_), dtype=torch.uint8, device=dev)
-        self._layers(bf, prompt.reshape(-1).contiguous(), positions, ctx, beam, ws)
+        self._layers(bf, prompt.reshape(-1).contiguous(), positions, ctx, beam, ws, prefill_shape=(B, n))
         last = bf.x.view(B, n, self.hidden_dim_)[:, n - 1, :].contiguous()
         self._head(last)
         self.positions.fill_(n)

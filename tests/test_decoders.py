@@ -238,6 +238,27 @@ def test_cuda_decoder_generate_vs_oracle(oracle, tmp_path, packed_mlp):
 
 
 @pytest.mark.gpu
+def test_cuda_decoder_head_dim_128_prefill_kernel(oracle, tmp_path):
+    """head_dim 128 + fp16 pages: the prompt goes through the tensor-core prefill kernel; tokens must still be
+    the oracle's (teacher forced), and equal the token-by-token path."""
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(35)
+    L, H, D, V, S = 2, 1, 128, 131, 96
+    hid = H * D
+    w = make_weights(rng, L, hid, V)
+    write_fp32_tree(w, str(tmp_path / "w"), True)
+    dec = ld.CUDADecoder(L, H, D, hid, V, S)
+    dec.load_weights(str(tmp_path / "w"))
+    prompt = [int(t) for t in rng.integers(0, V, 70)]          # two 64-query tiles, ragged second tile
+    out = dec.generate(prompt, 8, 0.9)
+    check_teacher_forced(out, len(prompt), RefDecoder(w, H, D), 0.9, 1, None, 2e-3)
+    dec2 = ld.CUDADecoder(L, H, D, hid, V, S, use_prefill=False)
+    dec2.load_weights(str(tmp_path / "w"))
+    assert dec2.generate(prompt, 8, 0.9) == out
+
+
+@pytest.mark.gpu
 def test_decoder_sampling_options(tmp_path):
     """generate(..., top_k / top_p / seed): device sampling instead of greedy; top_k=1 == greedy; same seed
     reproduces; every sampled token lies in the top-k set of the teacher-forced oracle logits."""
