@@ -22,6 +22,8 @@
 //     handed out through a global atomic counter (dynamic balance; a static
 //     equal split lost ~4% to SM-to-SM rate differences, profiles/), each chunk
 //     emits an (m, l, O) partial that a small combine kernel merges per row.
+#include <cstdlib>
+
 #include "mma_utils.cuh"
 #include "pa_common.cuh"
 
@@ -372,27 +374,9 @@ __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeAr
         unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
     }
 
-    const bool final_row = (a.num_splits == 1);
+    const bool final_row = (a.num_splits == 1);  // (the host forces >= 2 splits when the exchange epilogue is on)
     cta_merge_emit<D, KV, NW>(red, acc, warp, lane, a, final_row ? kEmitFinal : kEmitWorkspace, row,
                               row * a.num_splits + split);
-}
-
-// Combine the direct kernel's splits: one CTA of D threads per row.
-template <int D>
-__global__ void combine_splits_kernel(const DecodeArgs a) {
-    const int64_t row = blockIdx.x;
-    const int d = threadIdx.x;
-    const int ns = a.num_splits;
-    float M = -INFINITY;
-    for (int s = 0; s < ns; ++s) M = fmaxf(M, a.ws_m[row * ns + s]);
-    float L = 0.f, O = 0.f;
-    for (int s = 0; s < ns; ++s) {
-        const float ms = a.ws_m[row * ns + s];
-        const float wt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
-        L = fmaf(a.ws_l[row * ns + s], wt, L);
-        O = fmaf(a.ws_o[(row * ns + s) * D + d], wt, O);
-    }
-    emit_row(a, kEmitFinal, row, 0, D, d, M, L, O);
 }
 
 // ---------------------------------------------------------------- overlap (a2)
@@ -697,7 +681,9 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
     cm.cu = cu;
     cm.NC = (units_of_ctx(row_ctx(a, 0)) + cu - 1) / cu;
     cm.prefix = nullptr;
-    if (a.row_prefix) {
+    if (a.num_splits > 1) {
+        cm.NC = a.num_splits;  // split-KV grid kernel: every row owns num_splits slots (empty splits hold m = -inf)
+    } else if (a.row_prefix) {
         cm.prefix = a.row_prefix;
     } else if (a.ctx_lens) {
         if (threadIdx.x == 0) {
@@ -1323,7 +1309,8 @@ static int choose_cu(int64_t rows, int max_units, int sm_count) {
 static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
     const int cu = choose_cu(rows, max_units, sm_count);
     const size_t ov = (size_t)rows * ((max_units + cu - 1) / cu);
-    const size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
+    size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
+    if (dr < (size_t)rows * 2) dr = (size_t)rows * 2;  // exchange mode forces >= 2 splits
     // beam-group kernel: chunk size chosen from the number of (group, head) pairs, >= rows / 4
     const int cug = choose_cu(rows / kGroupMaxW > 0 ? rows / kGroupMaxW : 1, max_units, sm_count);
     const size_t gr = (size_t)rows * ((max_units + cug - 1) / cug);
@@ -1355,12 +1342,18 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     a.ws_o = w + 2 * nslots;
     if (!overlap) {
         a.num_splits = choose_splits(rows, max_units, di.sm_count);
+        if (a.xch_peers && a.num_splits < 2) a.num_splits = 2;  // the exchange lives in the merge kernel's epilogue
         dim3 grid((unsigned)rows, (unsigned)a.num_splits);
         paged_decode_direct_kernel<D, KV><<<grid, 128, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
         if (a.num_splits > 1) {
-            combine_splits_kernel<D><<<(unsigned)rows, D, 0, st>>>(a);
+            // same warp-parallel merge (and optional inter-GPU exchange epilogue) as the streaming kernel's chunks
+            a.all_rows_in_ws = 1;
+            const int ns = a.num_splits;
+            const int wpr = ns >= 64 ? 8 : (ns >= 32 ? 4 : (ns >= 16 ? 2 : 1));
+            const int rpc = 8 / wpr;
+            combine_chunks_kernel<D><<<(int)((rows + rpc - 1) / rpc), 256, 0, st>>>(a, 1, wpr);
             e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
         }
@@ -1481,7 +1474,7 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
     a.evict_first = beam_ids ? 0 : 1;  // shared-prefix pages are re-read by sibling beams: keep them in L2
     a.qscale = kLog2e / temperature;
     if (xch) {
-        PA_CHECK_ARG(overlap && xch->peers && xch->epochs && xch->world > 0 && xch->world <= 32 &&
+        PA_CHECK_ARG(xch->peers && xch->epochs && xch->world > 0 && xch->world <= 32 &&
                      xch->rank >= 0 && xch->rank < xch->world && !part_m);
         a.xch_peers = reinterpret_cast<uint8_t* const*>(xch->peers);
         a.xch_epochs = xch->epochs;
@@ -1553,7 +1546,14 @@ PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float*
                                        PA_DECODE_COMMON_PARAMS, void* d_workspace,
                                        size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
-    return decode_entry(0, true, d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+    // Kernel choice by problem size: below ~0.5 GB of K/V (one GPU's share of a 128K-token sequence is
+    // 268 MB) the split-KV grid kernel is faster than the persistent streaming kernel (56.7 vs 65 us at the
+    // C5 share: the persistent kernel's per-chunk overheads and ramp are not amortised); above it the
+    // streaming kernel wins.  PA_PARTIAL_DIRECT=0|1 overrides.
+    const int64_t total_units = (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok);
+    bool overlap = total_units > 65536;
+    if (const char* env = getenv("PA_PARTIAL_DIRECT")) overlap = atoi(env) != 1;
+    return decode_entry(0, overlap, d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
                         nullptr, nullptr, PA_DECODE_COMMON_ARGS, nullptr, d_workspace,
                         workspace_bytes, stream);
 }
@@ -1564,7 +1564,10 @@ PA_API int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const voi
                                        int rank, int world, uint32_t* d_epochs, int* d_status,
                                        pa_stream_t stream) {
     XchgParams x{d_peer_bufs, d_epochs, d_status, rank, world};
-    return decode_entry(0, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
+    const int64_t total_units = (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok);
+    bool overlap = total_units > 65536;  // same size rule as pa_paged_decode_f16_partial
+    if (const char* env = getenv("PA_PARTIAL_DIRECT")) overlap = atoi(env) != 1;
+    return decode_entry(0, overlap, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
                         nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream, &x);
 }
 
