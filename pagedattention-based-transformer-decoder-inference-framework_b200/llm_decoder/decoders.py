@@ -70,7 +70,7 @@ class _DecoderBase:
     ARGMAX_DIVIDE = 1  # cuda_decoder.cu:10-13 logits / temperature
 
     def __init__(self, num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len, *, device=None,
-                 tile_size=16, batch_size=1, attn_temperature=1.0, use_overlap=True, use_cuda_graph=True,
+                 tile_size=16, batch_size=1, attn_temperature=1.0, use_overlap=None, use_cuda_graph=True,
                  use_prefill=True):
         if min(num_layers, num_heads, head_dim, hidden_dim, vocab_size, max_seq_len) <= 0:
             raise ValueError("decoder dimensions must be positive")
@@ -147,7 +147,12 @@ class _DecoderBase:
             return
         # the persistent kernel keeps a per-row chunk prefix in shared memory: very many rows (long prompts in
         # the row-per-query prefill) go through the split-KV grid kernel instead
-        use_overlap = self.use_overlap and R <= 2048
+        if self.use_overlap is None:
+            # size rule (measured, paged_decode.cu): the persistent streaming kernel pays off above ~0.5 GB of K/V
+            use_overlap = R * self.num_heads_ * ((self.max_seq_len_ + 15) // 16) > 65536
+        else:
+            use_overlap = self.use_overlap
+        use_overlap = use_overlap and R <= 2048
         common = (pt.d_table_.data_ptr(), pt.num_beams_, pt.num_heads_, pt.num_tiles_, kvc.total_pages_,
                   _cabi.ptr(beam_ids), ctx_lens.data_ptr(), R, self.max_seq_len_, self.head_dim_, kvc.tile_size_,
                   self.attn_temperature, None, None, ws.data_ptr(), ws.numel(), _cabi.stream())
