@@ -285,6 +285,12 @@ int pa_logits_argmax(const float* d_x, const void* d_E, int elem_bytes, float qs
  * pa_batch_quantize_i8. */
 int pa_row_quantize_dynamic_i8(const float* d_x, int rows, int dim, float* d_scales, int8_t* d_q,
                                pa_stream_t stream);
+/* attention/attention_kernel_utils.cuh:20-35 apply_rotary_embedding for whole batches: d_q and/or d_k
+ * [rows, num_heads, head_dim] f32 are rotated pairwise in place with the interleaved table
+ * d_rope[token * head_dim + d] = cos, [.. + d + 1] = sin at token = d_positions[row] (apply_on_k = d_k
+ * given).  Rows whose position is outside [0, T) are left untouched.  Bit-exact (same operation order). */
+int pa_apply_rope_f32(float* d_q, float* d_k, const float* d_rope, const int32_t* d_positions, int rows,
+                      int num_heads, int head_dim, int T, pa_stream_t stream);
 /* positions[r] += 1 (and ctx_lens[r] += 1 when given): advances the decode step on the device. */
 int pa_advance_positions(int32_t* d_positions, int32_t* d_ctx_lens, int rows, pa_stream_t stream);
 

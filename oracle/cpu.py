@@ -324,3 +324,15 @@ def quantize_weights_file(w):
     out = np.empty(w.size, dtype=np.int8)
     scale = lib().orc_quantize_weights_file(_p(w, _f32p), C.c_int64(w.size), _p(out, _i8p))
     return out, float(scale)
+
+
+def apply_rotary_embedding(q, k, rotary_emb, positions):
+    """attention_kernel_utils.cuh:20-35 over rows: q, k [rows, H, D] (copies returned), rotary_emb [T, D]."""
+    q, k = _f32(q).copy(), _f32(k).copy()
+    rope = _f32(rotary_emb)
+    rows, H, D = q.shape
+    for r in range(rows):
+        for h in range(H):
+            lib().orc_apply_rotary_embedding(_p(q[r, h], _f32p), _p(k[r, h], _f32p), _p(rope, _f32p), D,
+                                             int(positions[r]), 1)
+    return q, k

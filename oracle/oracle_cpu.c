@@ -587,6 +587,24 @@ ORC_API float orc_quantize_weights_file(const float* w, int64_t n, int8_t* out) 
     return scale;
 }
 
+/* attention/attention_kernel_utils.cuh:20-35 apply_rotary_embedding, float version, one (row, head) vector:
+ * cos = rotary_emb[token*D + d], sin = rotary_emb[token*D + d + 1]. */
+ORC_API void orc_apply_rotary_embedding(float* q, float* k, const float* rotary_emb, int head_dim, int token_idx,
+                                        int apply_on_k) {
+    for (int d = 0; d < head_dim; d += 2) {
+        float c = rotary_emb[(int64_t)token_idx * head_dim + d];
+        float s = rotary_emb[(int64_t)token_idx * head_dim + d + 1];
+        float q0 = q[d], q1 = q[d + 1];
+        q[d] = q0 * c - q1 * s;
+        q[d + 1] = q0 * s + q1 * c;
+        if (apply_on_k) {
+            float k0 = k[d], k1 = k[d + 1];
+            k[d] = k0 * c - k1 * s;
+            k[d + 1] = k0 * s + k1 * c;
+        }
+    }
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -291,6 +291,34 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
     }
 }
 
+// ---- apply_rotary_embedding (attention/attention_kernel_utils.cuh:20-35): pairwise rotation of q and k
+// rows [rows, H, D] with the interleaved table rotary_emb[token * D + d] = cos, [.. + d + 1] = sin, token =
+// positions[row].  One thread per (row, head, pair); same operation order as the reference (two products and
+// one add/sub per output, no FMA contraction) so the result is bit-exact. ----
+__global__ void rope_kernel(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ rope,
+                            const int32_t* __restrict__ positions, int64_t n_pairs, int H, int D, int T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int half = D >> 1;
+    const int64_t rh = i / half;  // row * H + head
+    const int d = (int)(i - rh * half) * 2;
+    const int row = (int)(rh / H);
+    const int tok = positions[row];
+    if (tok < 0 || tok >= T) return;  // outside the table: left unrotated
+    const float c = rope[(int64_t)tok * D + d], s = rope[(int64_t)tok * D + d + 1];
+    const int64_t o = rh * D + d;
+    if (q) {
+        const float x0 = q[o], x1 = q[o + 1];
+        q[o] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+        q[o + 1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+    }
+    if (k) {
+        const float x0 = k[o], x1 = k[o + 1];
+        k[o] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+        k[o + 1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+    }
+}
+
 // positions[r] += 1 and ids := next ids (keeps the decode step free of host work so it can be
 // captured in a CUDA graph)
 __global__ void advance_kernel(int32_t* __restrict__ positions, int32_t* __restrict__ ctx_lens, int rows) {
@@ -442,5 +470,18 @@ PA_API int pa_row_quantize_dynamic_i8(const float* d_x, int rows, int dim, float
     PA_CHECK_ARG(d_x && d_scales && d_q && rows >= 0 && dim > 0);
     if (rows == 0) return PA_OK;
     row_quantize_dynamic_kernel<<<rows, 256, 0, as_stream(stream)>>>(d_x, rows, dim, d_scales, d_q);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
+// attention/attention_kernel_utils.cuh:20-35 apply_rotary_embedding over rows: d_q and/or d_k [rows, H, D] f32
+// rotated in place with d_rope [T, D] (interleaved cos, sin) at token d_positions[row] (apply_on_k = d_k != NULL).
+PA_API int pa_apply_rope_f32(float* d_q, float* d_k, const float* d_rope, const int32_t* d_positions, int rows,
+                             int num_heads, int head_dim, int T, pa_stream_t stream) {
+    PA_CHECK_ARG((d_q || d_k) && d_rope && d_positions && rows >= 0 && num_heads > 0 && head_dim > 0 && T > 0);
+    PA_CHECK_ARG(head_dim % 2 == 0);
+    if (rows == 0) return PA_OK;
+    const int64_t n = (int64_t)rows * num_heads * (head_dim / 2);
+    rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_q, d_k, d_rope, d_positions, n, num_heads,
+                                                                            head_dim, T);
     PA_RETURN_LAUNCH_STATUS();
 }

@@ -6,7 +6,7 @@ C++ signatures: KVTileCache, PageTable, AttentionCUDA, AttentionTileLauncher, in
 functions and dnnl_matmul_int8.
 """
 from . import _cabi  # noqa: F401
-from .attention import (AttentionCUDA, AttentionTileLauncher, lse_combine, paged_decode_group,  # noqa: F401
+from .attention import (AttentionCUDA, AttentionTileLauncher, apply_rotary_embedding, lse_combine, paged_decode_group,  # noqa: F401
                         paged_decode_partial, paged_prefill)
 from .int8_quant import (batch_dequantize, batch_minmax_scale, batch_quantize, compute_absmax,  # noqa: F401
                          compute_minmax_scale, dequantize_from_int8, dnnl_matmul_int8, quantize_to_int8)

@@ -65,6 +65,7 @@ _SIGS = {
     "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),
     "pa_logits_argmax": ([_vp, _vp, _i32, _f32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp], _i32),
     "pa_row_quantize_dynamic_i8": ([_vp, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pa_apply_rope_f32": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], _i32),
     "pa_advance_positions": ([_vp, _vp, _i32, _vp], _i32),
     "pa_splitkv_exchange_bytes": ([_i32, _i32, _i32], _sz),
     "pa_p2p_alloc": ([_sz, C.POINTER(_vp), C.c_char_p], _i32),

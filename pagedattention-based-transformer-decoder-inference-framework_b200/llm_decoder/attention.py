@@ -152,6 +152,17 @@ class AttentionCUDA:
                                             top_p, rerank_scores, debug, ctx_lens)
 
 
+def apply_rotary_embedding(q, k, rotary_emb, positions):
+    """attention/attention_kernel_utils.cuh:20-35 for batches: q and/or k [rows, H, D] f32 CUDA tensors rotated
+    in place with rotary_emb [T, D] (interleaved cos, sin) at token positions[row] (int32 CUDA tensor)."""
+    ref = q if q is not None else k
+    rows, H, D = ref.shape
+    with torch.cuda.device(ref.device):
+        _cabi.check(_cabi.lib().pa_apply_rope_f32(_cabi.ptr(q), _cabi.ptr(k), rotary_emb.data_ptr(), positions.data_ptr(),
+                                                  rows, H, D, rotary_emb.shape[0], _cabi.stream()), "pa_apply_rope_f32")
+    return q, k
+
+
 def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_start=None):
     """Causal multi-query attention of Tq new tokens per row over the paged cache
     (pa_paged_prefill_f16/_i8).  q/out: [B, H, Tq, D] f32 CUDA tensors (the reference's prefill layout,

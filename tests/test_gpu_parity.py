@@ -231,6 +231,26 @@ def test_rope_and_aliasing(ld, oracle):
         np.testing.assert_allclose(q.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
 
 
+def test_apply_rotary_embedding_bit_exact(ld, oracle):
+    """a8: attention_kernel_utils.cuh:20-35 with the [T, D] interleaved cos/sin table, q and k rows at per-row
+    token positions -- bit for bit against the C restatement (compiled with -ffp-contract=off)."""
+    rng = np.random.default_rng(27)
+    rows, H, D, T = 7, 3, 128, 50
+    q = rng.standard_normal((rows, H, D)).astype(np.float32)
+    k = rng.standard_normal((rows, H, D)).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, (T, D // 2))
+    rope = np.stack([np.cos(ang), np.sin(ang)], axis=2).reshape(T, D).astype(np.float32)
+    pos = rng.integers(0, T, rows).astype(np.int32)
+    eq, ek = oracle.cpu.apply_rotary_embedding(q, k, rope, pos)
+    dq, dk = torch.from_numpy(q).cuda(), torch.from_numpy(k).cuda()
+    ld.apply_rotary_embedding(dq, dk, torch.from_numpy(rope).cuda(), torch.from_numpy(pos).cuda())
+    np.testing.assert_array_equal(dq.cpu().numpy(), eq)
+    np.testing.assert_array_equal(dk.cpu().numpy(), ek)
+    dq2 = torch.from_numpy(q).cuda()
+    ld.apply_rotary_embedding(dq2, None, torch.from_numpy(rope).cuda(), torch.from_numpy(pos).cuda())   # apply_on_k = false
+    np.testing.assert_array_equal(dq2.cpu().numpy(), eq)
+
+
 def test_host_buffers_roundtrip(ld, oracle):
     """The reference-facing call with HOST q/out (numpy), as the e2e bench uses it."""
     case = make_case(B=3, H=4, D=128, T=256, seed=22)
