@@ -93,6 +93,21 @@ def main():
         assert len(out) == CTX
         res[name] = {"decode_tok_s": round((gen_tokens - 1) / max(t_all - t_prefill, 1e-9), 1),
                      "prefill_ms": round(t_prefill * 1e3, 2), "generate_64_tokens_ms": round(t_all * 1e3, 2)}
+        # the same model serving 64 sequences at once (rows are independent; the step is latency bound at batch 1)
+        NB = 64
+        prompts = [[int(t) for t in np.random.default_rng(100 + i).integers(0, V, CTX - gen_tokens)] for i in range(NB)]
+        dec.generate_batch(prompts, 8, 1.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dec.generate_batch(prompts, gen_tokens, 1.0)
+        torch.cuda.synchronize()
+        tb_all = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        dec.generate_batch(prompts, 1, 1.0)
+        torch.cuda.synchronize()
+        tb_prefill = time.perf_counter() - t1
+        res[name]["batch64_decode_tok_s"] = round(NB * (gen_tokens - 1) / max(tb_all - tb_prefill, 1e-9), 1)
+        res[name]["batch64_prefill_ms"] = round(tb_prefill * 1e3, 2)
     t_layer, threads = cpu_reference_layer_seconds(CTX)
     res["cpu_reference"] = {"decode_tok_s": round(1.0 / (t_layer * L), 1), "cores": threads, "kind": "port",
                             "sample": f"one layer-step (int8 paged attention over {CTX} tokens + two oneDNN s8 GEMMs), x{L} layers; "
