@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(192) prefill_fa_kernel(const __grid_constant__
 
     const int nqt = (a.Tq + kPfQ - 1) / kPfQ;
     const int bh_total = a.B * a.H;
-    const int qt = nqt - 1 - (int)(blockIdx.x / bh_total);  // longest tiles first
+    // CTA order: tile-major, longest tiles first (measured better than keeping the query tiles of one
+    // (row, head) adjacent for L2 reuse: 0.187 vs 0.231 ms at B = 1, Tq = 2048)
+    const int qt = nqt - 1 - (int)(blockIdx.x / bh_total);
     const int bh = (int)(blockIdx.x % bh_total);
     const int b = bh / a.H, h = bh - b * a.H;
     const int start = a.ctx_start ? a.ctx_start[b] : 0;
@@ -414,6 +416,12 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 using namespace pa;
 
+// prefill_tc.cu: tcgen05 flash-attention prefill (fp16 pages, head_dim 128)
+int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles, int total_pages,
+                         const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq, int tile_size,
+                         float temperature, cudaStream_t st);
+
 PA_API size_t pa_prefill_workspace_bytes(int B, int Tq, int num_heads, int head_dim, int num_tiles, int tile_size) {
     if (B < 0 || Tq <= 0 || num_heads <= 0 || head_dim <= 0 || num_tiles <= 0 || tile_size <= 0) return 0;
     const int64_t R = (int64_t)B * Tq;
@@ -435,6 +443,12 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     if (head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
         d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0) &&
         (kv == 0 || ((uintptr_t)d_k_scales % 16 == 0 && (uintptr_t)d_v_scales % 16 == 0))) {
+        if (kv == 0 && getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 1) {
+            const int stc = pa_prefill_tc_launch(d_q, d_out, d_k_pool, d_v_pool, d_table, num_beams, num_heads, num_tiles,
+                                                 total_pages, d_beam_ids, d_ctx_start, B, Tq, tile_size, temperature,
+                                                 as_stream(stream));
+            if (stc != PA_ERR_UNSUPPORTED) return stc;
+        }
         // tensor-core flash-attention kernel, straight on the [B, H, Tq, D] layout (no workspace)
         CUtensorMap tmK, tmV;
         const uint64_t total_tokens = (uint64_t)total_pages * tile_size;

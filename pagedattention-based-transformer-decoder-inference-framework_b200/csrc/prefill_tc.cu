@@ -1,0 +1,450 @@
+// prefill_tc.cu -- flash-attention prefill over the paged cache on the 5th-generation tensor cores
+// (tcgen05.mma kind::f16, accumulators in TMEM), fp16 pages, head_dim 128.  SURVEY 8(f) row 1.
+//
+// One CTA = 128 consecutive query positions of one (row, head); KV is consumed in tiles of 64 tokens
+// (4 page units of 16 tokens, each located through the page table and staged by TMA tensor copies):
+//   warp 0      : TMA producer (K tile as the K-major B operand of S = Q K^T, V tile as the MN-major B
+//                 operand of O_tile = P V, 3-stage ring)
+//   warp 1      : TMEM allocation + the single thread that issues the UMMAs:
+//                   S[sb]  (128 x 64, fp32, TMEM)  = Q (smem, fp16) . K^T     8 x (M128 N64  K16)
+//                   O_tile (128 x 128, fp32, TMEM) = P (smem, fp16) . V       4 x (M128 N128 K16)
+//   warps 2..5  : one thread per query row (= TMEM lane): tcgen05.ld its 64 scores, causal mask, online
+//                 softmax in registers, P written to shared memory as the next A operand.
+// O accumulates in TMEM across all KV tiles (accumulate flag), scaled by a per-row REFERENCE maximum that
+// is only raised when the tile maximum exceeds it by more than 8 (log2 units): P stays below 2^8 in fp16,
+// l and O use the same reference so O / l is exact, and the row rescale (tcgen05.ld, multiply, tcgen05.st)
+// happens a few times per row instead of once per tile.  S is double-buffered in TMEM so the tensor core
+// computes S(i+1) while the softmax of tile i runs.
+#include <cstdlib>
+#include <cstring>
+
+#include "mma_utils.cuh"
+#include "pa_common.cuh"
+
+namespace pa {
+namespace ptc {
+
+constexpr int QT = 128;               // queries per CTA
+constexpr int KT = 64;                // tokens per KV tile
+constexpr int D = 128;
+constexpr int ST = 3;                 // KV ring stages
+constexpr int Q_BYTES = 2 * QT * 128; // two k-blocks of [128 rows x 128 B]
+constexpr int K_BYTES = 2 * KT * 128; // two k-blocks of [64 rows x 128 B]
+constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
+constexpr int STAGE = K_BYTES + V_BYTES;
+constexpr int P_BYTES = QT * 128;     // [128 rows x 64 halfs]
+constexpr int TMEM_COLS = 256;        // S0 [0,64), S1 [64,128), O_tile [128,256)
+constexpr int NTHREADS = 288;        // warps: 0 producer, 1 UMMA, 2-5 softmax, 6-8 producers
+
+struct Args {
+    const float* q;
+    float* out;
+    const int32_t* table;
+    const int32_t* beam_ids;
+    const int32_t* ctx_start;
+    int num_beams, H, num_tiles, total_pages, B, Tq, tile_size;
+    float qscale;
+    int total_tokens;  // rows of the pool tensor map: a box at this row is all zeros (out-of-bounds fill)
+};
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (same encoding as gemm_i8.cu make_desc)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: c = F32 (1) [4,6), a = b = F16 (0), a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV,
+                                                                 const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_sm = base;
+    const uint32_t kv_sm = q_sm + Q_BYTES;
+    const uint32_t p_sm = kv_sm + ST * STAGE;
+    const uint32_t bar0 = p_sm + P_BYTES;
+    // barriers: kv_full[ST], kv_empty[ST], s_full[2], s_empty[2], p_full, o_full, o_empty, q_ready
+    auto kv_full = [&](int s) { return bar0 + s * 8; };
+    auto kv_empty = [&](int s) { return bar0 + (ST + s) * 8; };
+    auto s_full = [&](int b) { return bar0 + (2 * ST + b) * 8; };
+    auto s_empty = [&](int b) { return bar0 + (2 * ST + 2 + b) * 8; };
+    const uint32_t p_full = bar0 + (2 * ST + 4) * 8, o_full = p_full + 8, o_empty = o_full + 8, q_ready = o_empty + 8;
+    const uint32_t tmem_slot = q_ready + 8;
+    const uint32_t meta_sm = tmem_slot + 8;  // int nvalid[ST]: tokens of the tile inside the context
+    int* meta = reinterpret_cast<int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(s_full(b), 1);
+            mbar_init(s_empty(b), 128);
+        }
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        mbar_init(o_empty, 128);
+        mbar_init(q_ready, 128);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int nqt = (a.Tq + QT - 1) / QT;
+    const int bh_total = a.B * a.H;
+    // CTA order: tile-major, longest tiles first (measured better than keeping the query tiles of one
+    // (row, head) adjacent for L2 reuse: 0.187 vs 0.231 ms at B = 1, Tq = 2048)
+    const int qt = nqt - 1 - (int)(blockIdx.x / bh_total);
+    const int bh = (int)(blockIdx.x % bh_total);
+    const int b = bh / a.H, h = bh - b * a.H;
+    const int start = a.ctx_start ? a.ctx_start[b] : 0;
+    const int q_last = min(a.Tq, (qt + 1) * QT) - 1;
+    const int cap = a.num_tiles * a.tile_size;
+    const int kmax = min(cap, start + q_last + 1);
+    const int n_tiles = (kmax + KT - 1) / KT;
+    const int upt = a.tile_size >> 4;
+
+    if (warp == 0 || warp >= 6) {
+        // ------------------------------------------------------------ TMA producers
+        // FOUR producer warps, one 16-token unit of the tile each (lanes 0-3: K lo, K hi, V lo, V hi): the
+        // TMA operations of one warp are issued one after the other at ~150 cycles apiece, so a single
+        // producer (16 boxes per tile) capped the ring at one tile per ~2400 cycles.
+        const int uu = warp == 0 ? 0 : warp - 5;  // unit of the tile served by this warp
+        const int which = lane & 3;
+        const int beam = a.beam_ids ? a.beam_ids[b] : b;
+        const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
+                                  ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
+        int s = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < n_tiles; ++i) {
+            mbar_wait(kv_empty(s), ph);
+            const uint32_t st = kv_sm + s * STAGE;
+            if (warp == 0 && lane == 0) {
+                meta[s] = min(KT, kmax - i * KT);
+                fence_proxy_async();
+                mbar_arrive_expect_tx(kv_full(s), STAGE);  // the one arrival of the phase; the other warps' bytes
+            }                                              // may complete before or after it
+            if (lane < 4) {
+                const int u = i * 4 + uu;
+                int page = (trow && u * 16 < kmax) ? __ldg(trow + u / upt) : -1;
+                if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
+                // unmapped page / unit past the context: a box outside the tensor is filled with zeros
+                const int row0 = page >= 0 ? page * a.tile_size + (u % upt) * 16 : a.total_tokens;
+                const uint32_t dst = st + (which >> 1) * K_BYTES + (which & 1) * 8192 + uu * 2048;
+                if (warp != 0) fence_proxy_async();
+                tma_load_2d(dst, (which >> 1) ? &tmV : &tmK, (which & 1) * 64, row0, kv_full(s));
+            }
+            if (++s == ST) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ UMMA issuer
+        constexpr uint32_t kIdescS = idesc_f16(QT, KT, 0, 0);  // Q K-major, K K-major
+        constexpr uint32_t kIdescO = idesc_f16(QT, D, 0, 1);   // P K-major, V MN-major
+        mbar_wait(q_ready, 0);
+        tc_fence_after();
+        int s = 0;
+        uint32_t kv_ph = 0;
+        uint32_t se_ph[2] = {1u, 1u};  // S buffers start free
+        uint32_t p_ph = 0;
+        auto issue_S = [&](int i, int stage) {
+            const int sb = i & 1;
+            mbar_wait(s_empty(sb), se_ph[sb]);
+            se_ph[sb] ^= 1u;
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = kv_sm + stage * STAGE;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {  // 8 k-steps of 16 dims: k-block ks>>2, 32 B per step inside it
+                    const uint64_t da = make_desc(q_sm + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
+                    const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
+                    umma_f16(tmem_base + sb * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(s_full(sb));
+            }
+            __syncwarp();
+        };
+        if (n_tiles > 0) {
+            mbar_wait(kv_full(0), 0);
+            tc_fence_after();
+            issue_S(0, 0);
+        }
+        for (int i = 0; i < n_tiles; ++i) {
+            // S(i+1) as soon as its K tile has landed, so it overlaps the softmax of tile i
+            const int s_next = (s + 1 == ST) ? 0 : s + 1;
+            if (i + 1 < n_tiles) {
+                const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
+                mbar_wait(kv_full(s_next), ph_next);
+                tc_fence_after();
+                issue_S(i + 1, s_next);
+            }
+            // O += P(i) . V(i)   (the softmax threads finished any row rescale before arriving on p_full)
+            mbar_wait(p_full, p_ph);
+            p_ph ^= 1u;
+            tc_fence_after();
+            const int nvalid = meta[s];
+            const uint32_t st = kv_sm + s * STAGE;
+            if (nvalid < KT && (nvalid & 15)) {
+                // rows of the last page past the context end may hold anything (0 x NaN = NaN): zero them
+                const int r0 = nvalid;
+                const int r1 = (nvalid + 15) & ~15;
+                for (int idx = lane; idx < (r1 - r0) * 16; idx += 32) {
+                    const int r = r0 + idx / 16, c = idx % 16;
+                    const uint32_t addr = st + K_BYTES + (c >> 3) * 8192 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const int ksteps = (nvalid + 15) >> 4;  // tokens past the context contribute nothing
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t da = make_desc(p_sm + ks * 32, 16, 1024);
+                    const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
+                    umma_f16(tmem_base + 2 * KT, da, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(o_full);
+                umma_commit(kv_empty(s));
+            }
+            __syncwarp();
+            if (++s == ST) {
+                s = 0;
+                kv_ph ^= 1u;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax / accumulate: one thread per query
+        const int qtr = warp & 3;
+        const int row = qtr * 32 + lane;       // TMEM lane = row of the Q tile
+        const int t = qt * QT + row;           // query position within the prompt chunk
+        const bool t_ok = t < a.Tq;
+        const int qpos = t_ok ? start + t : -1;
+        const uint32_t lane_base = (uint32_t)(qtr * 32) << 16;
+        // Q row -> fp16, pre-scaled, into the swizzled K-major A tile
+        {
+            const float* qr = a.q + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
+#pragma unroll 4
+            for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 halfs
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 x = t_ok ? *reinterpret_cast<const float2*>(qr + c * 8 + j * 2) : make_float2(0.f, 0.f);
+                    w[j] = pack_half2(x.x * a.qscale, x.y * a.qscale);
+                }
+                const uint32_t addr = q_sm + (c >> 3) * (QT * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+            }
+            fence_proxy_async();
+            mbar_arrive_cnt(q_ready);
+        }
+        float m_ref = -INFINITY, l_run = 0.f;  // reference maximum of this row (see the header), running sum
+        uint32_t sf_ph[2] = {0u, 0u};
+        const uint32_t o_addr = tmem_base + lane_base + 2 * KT;
+#pragma unroll 1
+        for (int i = 0; i < n_tiles; ++i) {
+            const int sb = i & 1;
+            mbar_wait(s_full(sb), sf_ph[sb]);
+            sf_ph[sb] ^= 1u;
+            tc_fence_after();
+            uint32_t sr[2][32];
+            tmem_ld32(tmem_base + lane_base + sb * KT, sr[0]);
+            tmem_ld32(tmem_base + lane_base + sb * KT + 32, sr[1]);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive_cnt(s_empty(sb));
+            // causal / context mask (only tiles that touch the diagonal or the context end) + tile maximum
+            const int kp0 = i * KT;
+            const bool full_tile = (kp0 + KT - 1 <= qpos) && (kp0 + KT <= kmax);
+            float mx = -INFINITY;
+            if (!full_tile) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int kp = kp0 + hh * 32 + j;
+                        if (!(kp <= qpos && kp < kmax)) sr[hh][j] = 0xff800000u;  // -inf
+                    }
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[hh][j]));
+            }
+            // raise the reference maximum only when this tile exceeds it by more than 2^8
+            const bool raise = mx > m_ref + 8.f || (m_ref == -INFINITY && mx > -INFINITY);
+            const float m_new = raise ? mx : m_ref;
+            const float corr = (raise && m_ref != -INFINITY) ? fast_exp2(m_ref - m_new) : 1.f;
+            // P.V(i-1) must be complete before P is overwritten and before O is rescaled
+            if (i > 0) {
+                mbar_wait(o_full, (uint32_t)((i - 1) & 1));
+                tc_fence_after();
+            }
+            if (__any_sync(0xffffffffu, corr != 1.f)) {  // warp-collective TMEM access; lanes that keep their
+#pragma unroll                                          // reference multiply by 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint32_t orr[32];
+                    tmem_ld32(o_addr + c4 * 32, orr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * corr);
+                    tmem_st32(o_addr + c4 * 32, orr);
+                }
+                tmem_wait_st();
+                l_run *= corr;
+            }
+            m_ref = m_new;
+            float ps = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 tokens
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k0 = c * 8 + j * 2;
+                    const float s0 = __uint_as_float(sr[k0 >> 5][k0 & 31]), s1 = __uint_as_float(sr[(k0 + 1) >> 5][(k0 + 1) & 31]);
+                    const float p0 = fast_exp2(s0 - m_ref);  // -inf - finite = -inf -> 0; a fully masked row has
+                    const float p1 = fast_exp2(s1 - m_ref);  // m_ref = -inf: -inf - -inf = NaN, handled below
+                    ps += p0 + p1;
+                    w[j] = pack_half2(p0, p1);
+                }
+                if (m_ref == -INFINITY) { w[0] = w[1] = w[2] = w[3] = 0u; }
+                const uint32_t addr = p_sm + row * 128 + ((c ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+            }
+            if (m_ref != -INFINITY) l_run += ps;
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive_cnt(p_full);
+        }
+        float inv = 0.f;
+        if (n_tiles > 0) {
+            mbar_wait(o_full, (uint32_t)((n_tiles - 1) & 1));
+            tc_fence_after();
+            inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+        }
+        float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t orr[32];
+            if (n_tiles > 0) {
+                tmem_ld32(o_addr + c4 * 32, orr);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) orr[j] = 0u;
+            }
+            if (t_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(orow + c4 * 32 + j) =
+                        make_float4(__uint_as_float(orr[j]) * inv, __uint_as_float(orr[j + 1]) * inv,
+                                    __uint_as_float(orr[j + 2]) * inv, __uint_as_float(orr[j + 3]) * inv);
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace ptc
+}  // namespace pa
+
+using namespace pa;
+
+// Launch helper used by prefill.cu (returns PA_ERR_UNSUPPORTED when the tensor maps cannot be built).
+int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles, int total_pages,
+                         const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq, int tile_size,
+                         float temperature, cudaStream_t st) {
+    using namespace pa::ptc;
+    CUtensorMap tmK, tmV;
+    const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
+    if (total_tokens >= 0x7fffffffull) return PA_ERR_UNSUPPORTED;
+    if (!make_pool_map(&tmK, d_k_pool, total_tokens) || !make_pool_map(&tmV, d_v_pool, total_tokens))
+        return PA_ERR_UNSUPPORTED;
+    Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
+           1.4426950408889634f / temperature, (int)total_tokens};
+    const int nqt = (Tq + QT - 1) / QT;
+    const int64_t ctas = (int64_t)B * num_heads * nqt;
+    if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
+    const size_t smem = (size_t)Q_BYTES + ST * STAGE + P_BYTES + (2 * ST + 8) * 8 + 8 + ST * 4 + 16 + 1024;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        cudaError_t e0 = cudaFuncSetAttribute(prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e0 != cudaSuccess) return (int)e0;
+        attr_done[dev & 63] = true;
+    }
+    prefill_tc_kernel<<<(unsigned)ctas, NTHREADS, smem, st>>>(tmK, tmV, a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PA_OK : (int)e;
+}
