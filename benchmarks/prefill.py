@@ -20,12 +20,17 @@ def main():
     dev = torch.device("cuda", 0)
     H, D, TILE = 32, 128, 16
     res = []
-    for B, Tq in ((1, 512), (1, 2048), (4, 2048)):
+    shapes = ((1, 512), (1, 2048), (4, 2048), (2, 8192))
+    kvs = ("f16", "i8")
+    if len(sys.argv) > 1:  # prefill.py B,Tq [kv]: one shape (for ncu captures)
+        shapes = (tuple(int(v) for v in sys.argv[1].split(",")),)
+        kvs = (sys.argv[2],) if len(sys.argv) > 2 else kvs
+    for B, Tq in shapes:
         nt = Tq // TILE
         P = B * H * nt
         g = torch.Generator(device=dev).manual_seed(3)
         out_line = {"B": B, "Tq": Tq}
-        for kv in ("f16", "i8"):
+        for kv in kvs:
             kvc = ld.KVTileCache(kv, device=dev)
             if kv == "f16":
                 kvc.adopt_buffers(torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16),
@@ -44,14 +49,16 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            n = 5
+            n = 10
             for _ in range(n):
                 ld.paged_prefill(q, out, kvc, B, Tq, float(np.sqrt(D)))
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
             flops = 4.0 * B * H * D * Tq * (Tq + 1) / 2
-            out_line["flash_mma_f16" if kv == "f16" else "flash_mma_i8"] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
+            tc = kv == "f16" and os.environ.get("PA_PREFILL_TC", "1") != "0"
+            out_line[("tcgen05_f16" if tc else "flash_mma_f16") if kv == "f16" else "flash_mma_i8"] = {
+                "ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
         res.append(out_line)
     print(json.dumps({"workload": "prefill attention, one layer, 32 heads x D=128, causal", "results": res}))
 

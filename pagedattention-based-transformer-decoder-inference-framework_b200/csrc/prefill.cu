@@ -443,7 +443,8 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     if (head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
         d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0) &&
         (kv == 0 || ((uintptr_t)d_k_scales % 16 == 0 && (uintptr_t)d_v_scales % 16 == 0))) {
-        if (kv == 0 && getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 1) {
+        // fp16 pages: tcgen05 kernel (prefill_tc.cu) unless PA_PREFILL_TC=0 asks for the mma.sync kernel below
+        if (kv == 0 && !(getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 0)) {
             const int stc = pa_prefill_tc_launch(d_q, d_out, d_k_pool, d_v_pool, d_table, num_beams, num_heads, num_tiles,
                                                  total_pages, d_beam_ids, d_ctx_start, B, Tq, tile_size, temperature,
                                                  as_stream(stream));

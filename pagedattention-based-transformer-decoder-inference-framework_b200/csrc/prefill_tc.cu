@@ -1,20 +1,24 @@
 // prefill_tc.cu -- flash-attention prefill over the paged cache on the 5th-generation tensor cores
 // (tcgen05.mma kind::f16, accumulators in TMEM), fp16 pages, head_dim 128.  SURVEY 8(f) row 1.
 //
-// One CTA = 128 consecutive query positions of one (row, head); KV is consumed in tiles of 64 tokens
-// (4 page units of 16 tokens, each located through the page table and staged by TMA tensor copies):
-//   warp 0      : TMA producer (K tile as the K-major B operand of S = Q K^T, V tile as the MN-major B
-//                 operand of O_tile = P V, 3-stage ring)
-//   warp 1      : TMEM allocation + the single thread that issues the UMMAs:
-//                   S[sb]  (128 x 64, fp32, TMEM)  = Q (smem, fp16) . K^T     8 x (M128 N64  K16)
-//                   O_tile (128 x 128, fp32, TMEM) = P (smem, fp16) . V       4 x (M128 N128 K16)
-//   warps 2..5  : one thread per query row (= TMEM lane): tcgen05.ld its 64 scores, causal mask, online
-//                 softmax in registers, P written to shared memory as the next A operand.
+// One CTA = 256 consecutive query positions of one (row, head), handled as TWO query tiles of 128 rows
+// (A, B) that share every K/V tile; KV is consumed in tiles of 64 tokens (4 page units of 16 tokens, each
+// located through the page table and staged by TMA tensor copies):
+//   warps 0-3   : softmax group A, warps 4-7: softmax group B.  One thread per query row (= TMEM lane):
+//                 tcgen05.ld its 64 scores, causal mask, online softmax in registers, P written to shared
+//                 memory as the next A operand.  While one group computes exponentials the tensor core
+//                 runs the other group's MMAs, so MUFU and tensor time overlap.
+//   warp 8      : TMEM allocation (all 512 columns) + the single thread that issues the UMMAs:
+//                   S_X[sb] (128 x 64, fp32, TMEM)  = Q_X (smem, fp16) . K^T     8 x (M128 N64  K16)
+//                   O_X     (128 x 128, fp32, TMEM) += P_X (smem, fp16) . V      4 x (M128 N128 K16)
+//   warps 9-11  : TMA producers sharing the 16 boxes of a tile (K tile as the K-major B operand of
+//                 S = Q K^T, V tile as the MN-major B operand of O = P V, 3-stage ring)
 // O accumulates in TMEM across all KV tiles (accumulate flag), scaled by a per-row REFERENCE maximum that
 // is only raised when the tile maximum exceeds it by more than 8 (log2 units): P stays below 2^8 in fp16,
 // l and O use the same reference so O / l is exact, and the row rescale (tcgen05.ld, multiply, tcgen05.st)
-// happens a few times per row instead of once per tile.  S is double-buffered in TMEM so the tensor core
-// computes S(i+1) while the softmax of tile i runs.
+// happens a few times per row instead of once per tile.  S is double-buffered in TMEM so S(i+1) is computed
+// while the softmax of tile i runs; the exponentials of tile i are computed BEFORE waiting for P.V(i-1), so
+// that MMA runs under them as well.
 #include <cstdlib>
 #include <cstring>
 
@@ -24,17 +28,20 @@
 namespace pa {
 namespace ptc {
 
-constexpr int QT = 128;               // queries per CTA
+constexpr int QT = 128;               // queries per query tile (= TMEM lanes)
+constexpr int NQ = 2;                 // query tiles per CTA
 constexpr int KT = 64;                // tokens per KV tile
 constexpr int D = 128;
 constexpr int ST = 3;                 // KV ring stages
-constexpr int Q_BYTES = 2 * QT * 128; // two k-blocks of [128 rows x 128 B]
+constexpr int Q_BYTES = 2 * QT * 128; // per query tile: two k-blocks of [128 rows x 128 B]
 constexpr int K_BYTES = 2 * KT * 128; // two k-blocks of [64 rows x 128 B]
 constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
-constexpr int P_BYTES = QT * 128;     // [128 rows x 64 halfs]
-constexpr int TMEM_COLS = 256;        // S0 [0,64), S1 [64,128), O_tile [128,256)
-constexpr int NTHREADS = 288;        // warps: 0 producer, 1 UMMA, 2-5 softmax, 6-8 producers
+constexpr int P_BYTES = QT * 128;     // per query tile: [128 rows x 64 halfs]
+constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
+constexpr int NTHREADS = 384;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9-11 TMA producers (12 warps:
+                                      // ptxas grants 168 registers per thread; 13 warps would drop it to 128)
+constexpr int NBAR = 2 * ST + 5 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full, o_full, q_ready
 
 struct Args {
     const float* q;
@@ -111,18 +118,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
-    const uint32_t kv_sm = q_sm + Q_BYTES;
+    const uint32_t kv_sm = q_sm + NQ * Q_BYTES;
     const uint32_t p_sm = kv_sm + ST * STAGE;
-    const uint32_t bar0 = p_sm + P_BYTES;
-    // barriers: kv_full[ST], kv_empty[ST], s_full[2], s_empty[2], p_full, o_full, o_empty, q_ready
+    const uint32_t bar0 = p_sm + NQ * P_BYTES;
     auto kv_full = [&](int s) { return bar0 + s * 8; };
     auto kv_empty = [&](int s) { return bar0 + (ST + s) * 8; };
-    auto s_full = [&](int b) { return bar0 + (2 * ST + b) * 8; };
-    auto s_empty = [&](int b) { return bar0 + (2 * ST + 2 + b) * 8; };
-    const uint32_t p_full = bar0 + (2 * ST + 4) * 8, o_full = p_full + 8, o_empty = o_full + 8, q_ready = o_empty + 8;
-    const uint32_t tmem_slot = q_ready + 8;
-    const uint32_t meta_sm = tmem_slot + 8;  // int nvalid[ST]: tokens of the tile inside the context
-    int* meta = reinterpret_cast<int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
+    auto s_full = [&](int x, int sb) { return bar0 + (2 * ST + 5 * x + sb) * 8; };
+    auto p_full = [&](int x) { return bar0 + (2 * ST + 5 * x + 2) * 8; };
+    auto o_full = [&](int x) { return bar0 + (2 * ST + 5 * x + 3) * 8; };
+    auto q_ready = [&](int x) { return bar0 + (2 * ST + 5 * x + 4) * 8; };
+    const uint32_t tmem_slot = bar0 + NBAR * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -130,67 +135,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(s_full(b), 1);
-            mbar_init(s_empty(b), 128);
+        for (int x = 0; x < NQ; ++x) {
+            mbar_init(s_full(x, 0), 1);
+            mbar_init(s_full(x, 1), 1);
+            mbar_init(p_full(x), QT);
+            mbar_init(o_full(x), 1);
+            mbar_init(q_ready(x), QT);
         }
-        mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
-        mbar_init(o_empty, 128);
-        mbar_init(q_ready, 128);
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int nqt = (a.Tq + QT - 1) / QT;
+    constexpr int QC = NQ * QT;  // queries per CTA
+    const int nqt = (a.Tq + QC - 1) / QC;
     const int bh_total = a.B * a.H;
     // CTA order: tile-major, longest tiles first (measured better than keeping the query tiles of one
-    // (row, head) adjacent for L2 reuse: 0.187 vs 0.231 ms at B = 1, Tq = 2048)
+    // (row, head) adjacent for L2 reuse)
     const int qt = nqt - 1 - (int)(blockIdx.x / bh_total);
     const int bh = (int)(blockIdx.x % bh_total);
     const int b = bh / a.H, h = bh - b * a.H;
     const int start = a.ctx_start ? a.ctx_start[b] : 0;
-    const int q_last = min(a.Tq, (qt + 1) * QT) - 1;
     const int cap = a.num_tiles * a.tile_size;
-    const int kmax = min(cap, start + q_last + 1);
-    const int n_tiles = (kmax + KT - 1) / KT;
+    // per query tile X: keys [0, kmax_X) are visible to its last query; n_X KV tiles; an absent tile has n = 0
+    int kmaxs[NQ], nts[NQ];
+#pragma unroll
+    for (int x = 0; x < NQ; ++x) {
+        const int q0 = qt * QC + x * QT;
+        const int q_last = min(a.Tq, q0 + QT) - 1;
+        kmaxs[x] = q0 < a.Tq ? max(0, min(cap, start + q_last + 1)) : 0;
+        nts[x] = (kmaxs[x] + KT - 1) / KT;
+    }
+    const int kmax_c = max(kmaxs[0], kmaxs[1]);  // kmax is monotone in x, an absent tile has 0
+    const int n_tiles = max(nts[0], nts[1]);
     const int upt = a.tile_size >> 4;
+    const int beam = a.beam_ids ? a.beam_ids[b] : b;
+    const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
+                              ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
 
-    if (warp == 0 || warp >= 6) {
+    if (warp >= 9) {
         // ------------------------------------------------------------ TMA producers
-        // FOUR producer warps, one 16-token unit of the tile each (lanes 0-3: K lo, K hi, V lo, V hi): the
-        // TMA operations of one warp are issued one after the other at ~150 cycles apiece, so a single
-        // producer (16 boxes per tile) capped the ring at one tile per ~2400 cycles.
-        const int uu = warp == 0 ? 0 : warp - 5;  // unit of the tile served by this warp
-        const int which = lane & 3;
-        const int beam = a.beam_ids ? a.beam_ids[b] : b;
-        const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
-                                  ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
+        // THREE producer warps share the 16 boxes of a tile round-robin (box = unit * 4 + {K lo, K hi, V lo,
+        // V hi}, one box per lane): the TMA operations of one warp are issued one after the other at ~150
+        // cycles apiece, so a single producer capped the ring at one tile per ~2400 cycles.
+        const int box = (warp - 9) + 3 * lane;  // lanes 0..5
+        const int uu = box >> 2, which = box & 3;
+        const bool mine = lane < 6 && box < 16;
         int s = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_tiles; ++i) {
             mbar_wait(kv_empty(s), ph);
             const uint32_t st = kv_sm + s * STAGE;
-            if (warp == 0 && lane == 0) {
-                meta[s] = min(KT, kmax - i * KT);
-                fence_proxy_async();
+            if (warp == 9 && lane == 0)
                 mbar_arrive_expect_tx(kv_full(s), STAGE);  // the one arrival of the phase; the other warps' bytes
-            }                                              // may complete before or after it
-            if (lane < 4) {
+                                                           // may complete before or after it
+            if (mine) {
                 const int u = i * 4 + uu;
-                int page = (trow && u * 16 < kmax) ? __ldg(trow + u / upt) : -1;
+                int page = (trow && u * 16 < kmax_c) ? __ldg(trow + u / upt) : -1;
                 if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
-                // unmapped page / unit past the context: a box outside the tensor is filled with zeros
+                // unmapped page / unit past the context: a box outside the tensor is filled with zeros (finite
+                // operands; the softmax threads mask the scores of unmapped units themselves)
                 const int row0 = page >= 0 ? page * a.tile_size + (u % upt) * 16 : a.total_tokens;
                 const uint32_t dst = st + (which >> 1) * K_BYTES + (which & 1) * 8192 + uu * 2048;
-                if (warp != 0) fence_proxy_async();
                 tma_load_2d(dst, (which >> 1) ? &tmV : &tmK, (which & 1) * 64, row0, kv_full(s));
             }
             if (++s == ST) {
@@ -198,38 +210,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 ph ^= 1u;
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 8) {
         // ------------------------------------------------------------ UMMA issuer
         constexpr uint32_t kIdescS = idesc_f16(QT, KT, 0, 0);  // Q K-major, K K-major
         constexpr uint32_t kIdescO = idesc_f16(QT, D, 0, 1);   // P K-major, V MN-major
-        mbar_wait(q_ready, 0);
-        tc_fence_after();
-        int s = 0;
-        uint32_t kv_ph = 0;
-        uint32_t se_ph[2] = {1u, 1u};  // S buffers start free
-        uint32_t p_ph = 0;
-        auto issue_S = [&](int i, int stage) {
-            const int sb = i & 1;
-            mbar_wait(s_empty(sb), se_ph[sb]);
-            se_ph[sb] ^= 1u;
-            tc_fence_after();
+        // S_X(i) into buffer i & 1 of tile X.  The buffer was last read (tcgen05.ld) by the softmax of tile
+        // i - 2, and this thread has already waited for p_full_X(i - 2), which every softmax thread signals
+        // after its tcgen05.wait::ld: no separate "S buffer empty" barrier is needed.
+        auto issue_S = [&](int x, int i, int stage) {
             if (lane == 0) {
                 const uint32_t st = kv_sm + stage * STAGE;
+                const uint32_t qx = q_sm + x * Q_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {  // 8 k-steps of 16 dims: k-block ks>>2, 32 B per step inside it
-                    const uint64_t da = make_desc(q_sm + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
+                    const uint64_t da = make_desc(qx + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
                     const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
-                    umma_f16(tmem_base + sb * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
+                    umma_f16(tmem_base + x * 2 * KT + (i & 1) * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
                 }
-                umma_commit(s_full(sb));
+                umma_commit(s_full(x, i & 1));
             }
             __syncwarp();
         };
         if (n_tiles > 0) {
             mbar_wait(kv_full(0), 0);
-            tc_fence_after();
-            issue_S(0, 0);
+#pragma unroll
+            for (int x = 0; x < NQ; ++x) {
+                if (nts[x] > 0) {
+                    mbar_wait(q_ready(x), 0);
+                    tc_fence_after();
+                    issue_S(x, 0, 0);
+                }
+            }
         }
+        int s = 0;
+        uint32_t kv_ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
             // S(i+1) as soon as its K tile has landed, so it overlaps the softmax of tile i
             const int s_next = (s + 1 == ST) ? 0 : s + 1;
@@ -237,18 +251,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
                 mbar_wait(kv_full(s_next), ph_next);
                 tc_fence_after();
-                issue_S(i + 1, s_next);
+#pragma unroll
+                for (int x = 0; x < NQ; ++x)
+                    if (i + 1 < nts[x]) issue_S(x, i + 1, s_next);
             }
-            // O += P(i) . V(i)   (the softmax threads finished any row rescale before arriving on p_full)
-            mbar_wait(p_full, p_ph);
-            p_ph ^= 1u;
-            tc_fence_after();
-            const int nvalid = meta[s];
             const uint32_t st = kv_sm + s * STAGE;
-            if (nvalid < KT && (nvalid & 15)) {
+            const int nvalid_c = min(KT, kmax_c - i * KT);
+            if (nvalid_c < KT && (nvalid_c & 15)) {
                 // rows of the last page past the context end may hold anything (0 x NaN = NaN): zero them
-                const int r0 = nvalid;
-                const int r1 = (nvalid + 15) & ~15;
+                const int r0 = nvalid_c;
+                const int r1 = (nvalid_c + 15) & ~15;
                 for (int idx = lane; idx < (r1 - r0) * 16; idx += 32) {
                     const int r = r0 + idx / 16, c = idx % 16;
                     const uint32_t addr = st + K_BYTES + (c >> 3) * 8192 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
@@ -257,16 +269,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 fence_proxy_async();
                 __syncwarp();
             }
-            if (lane == 0) {
-                const int ksteps = (nvalid + 15) >> 4;  // tokens past the context contribute nothing
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t da = make_desc(p_sm + ks * 32, 16, 1024);
-                    const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
-                    umma_f16(tmem_base + 2 * KT, da, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
+            // O_X += P_X(i) . V(i)   (the softmax threads finished any row rescale before arriving on p_full)
+#pragma unroll
+            for (int x = 0; x < NQ; ++x) {
+                if (i < nts[x]) {
+                    mbar_wait(p_full(x), (uint32_t)(i & 1));
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const int nvalid = min(KT, kmaxs[x] - i * KT);
+                        const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t da = make_desc(p_sm + x * P_BYTES + ks * 32, 16, 1024);
+                            const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
+                            umma_f16(tmem_base + NQ * 2 * KT + x * D, da, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        umma_commit(o_full(x));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(o_full);
-                umma_commit(kv_empty(s));
             }
+            if (lane == 0) umma_commit(kv_empty(s));
             __syncwarp();
             if (++s == ST) {
                 s = 0;
@@ -275,71 +297,107 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         }
     } else {
         // ------------------------------------------------------------ softmax / accumulate: one thread per query
-        const int qtr = warp & 3;
+        const int x = warp >> 2;               // query tile of this warp's group
+        const int qtr = warp & 3;              // TMEM lane quadrant
         const int row = qtr * 32 + lane;       // TMEM lane = row of the Q tile
-        const int t = qt * QT + row;           // query position within the prompt chunk
+        const int q0 = qt * QC + x * QT;
+        const int t = q0 + row;                // query position within the prompt chunk
         const bool t_ok = t < a.Tq;
         const int qpos = t_ok ? start + t : -1;
+        const int kmax = kmaxs[x], nt = nts[x];
         const uint32_t lane_base = (uint32_t)(qtr * 32) << 16;
-        // Q row -> fp16, pre-scaled, into the swizzled K-major A tile
-        {
-            const float* qr = a.q + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
-#pragma unroll 4
-            for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 halfs
-                uint32_t w[4];
+        if (nt > 0) {
+            // Q rows of this warp -> fp16, pre-scaled, into the swizzled K-major A tile.  One row per step, the
+            // whole warp on its 512 bytes (coalesced); 8 rows in flight.
+            const float* qbase = a.q + (((int64_t)b * a.H + h) * a.Tq) * D;
+            const uint32_t qx = q_sm + x * Q_BYTES;
+            const int c = lane >> 1;  // 16-byte chunk (8 halfs) of the row this lane contributes to
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 x = t_ok ? *reinterpret_cast<const float2*>(qr + c * 8 + j * 2) : make_float2(0.f, 0.f);
-                    w[j] = pack_half2(x.x * a.qscale, x.y * a.qscale);
+                for (int j = 0; j < 8; ++j) {
+                    const int tr = q0 + qtr * 32 + r0 + j;
+                    v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * D) + lane)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                const uint32_t addr = q_sm + (c >> 3) * (QT * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                             : "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int rr = qtr * 32 + r0 + j;
+                    const uint32_t w0 = pack_half2(v[j].x * a.qscale, v[j].y * a.qscale);
+                    const uint32_t w1 = pack_half2(v[j].z * a.qscale, v[j].w * a.qscale);
+                    const uint32_t addr = qx + (c >> 3) * (QT * 128) + rr * 128 + (((c & 7) ^ (rr & 7)) << 4) + (lane & 1) * 8;
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(w0), "r"(w1) : "memory");
+                }
             }
             fence_proxy_async();
-            mbar_arrive_cnt(q_ready);
+            mbar_arrive_cnt(q_ready(x));
         }
         float m_ref = -INFINITY, l_run = 0.f;  // reference maximum of this row (see the header), running sum
-        uint32_t sf_ph[2] = {0u, 0u};
-        const uint32_t o_addr = tmem_base + lane_base + 2 * KT;
+        const uint32_t s_addr = tmem_base + lane_base + x * 2 * KT;
+        const uint32_t o_addr = tmem_base + lane_base + NQ * 2 * KT + x * D;
+        const uint32_t p_row = p_sm + x * P_BYTES + row * 128;
 #pragma unroll 1
-        for (int i = 0; i < n_tiles; ++i) {
+        for (int i = 0; i < nt; ++i) {
             const int sb = i & 1;
-            mbar_wait(s_full(sb), sf_ph[sb]);
-            sf_ph[sb] ^= 1u;
+            // which of the tile's 4 units are mapped (an unmapped page is skipped: ...fused.cu:32) -- the table
+            // entries are fetched before the wait so their latency hides behind it
+            int pg[4];
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int u = i * 4 + uu;
+                pg[uu] = (trow && u * 16 < kmax) ? __ldg(trow + u / upt) : -1;
+            }
+            mbar_wait(s_full(x, sb), (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             uint32_t sr[2][32];
-            tmem_ld32(tmem_base + lane_base + sb * KT, sr[0]);
-            tmem_ld32(tmem_base + lane_base + sb * KT + 32, sr[1]);
+            tmem_ld32(s_addr + sb * KT, sr[0]);
+            tmem_ld32(s_addr + sb * KT + 32, sr[1]);
             tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive_cnt(s_empty(sb));
-            // causal / context mask (only tiles that touch the diagonal or the context end) + tile maximum
+            // causal / context / unmapped-page mask (only tiles that need one) + tile maximum
             const int kp0 = i * KT;
-            const bool full_tile = (kp0 + KT - 1 <= qpos) && (kp0 + KT <= kmax);
-            float mx = -INFINITY;
+            bool all_mapped = true;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) all_mapped &= (unsigned)pg[uu] < (unsigned)a.total_pages;
+            const bool full_tile = (kp0 + KT - 1 <= qpos) && (kp0 + KT <= kmax) && all_mapped;
             if (!full_tile) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int kp = kp0 + hh * 32 + j;
-                        if (!(kp <= qpos && kp < kmax)) sr[hh][j] = 0xff800000u;  // -inf
+                        const bool mapped = (unsigned)pg[(hh * 32 + j) >> 4] < (unsigned)a.total_pages;
+                        if (!(kp <= qpos && kp < kmax && mapped)) sr[hh][j] = 0xff800000u;  // -inf
                     }
                 }
             }
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[hh][j]));
+                for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sr[hh][j]));
             }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // raise the reference maximum only when this tile exceeds it by more than 2^8
             const bool raise = mx > m_ref + 8.f || (m_ref == -INFINITY && mx > -INFINITY);
             const float m_new = raise ? mx : m_ref;
             const float corr = (raise && m_ref != -INFINITY) ? fast_exp2(m_ref - m_new) : 1.f;
+            m_ref = m_new;
+            // exponentials in registers (packed fp16) while P.V(i-1) is still running
+            uint32_t w[32];
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int k0 = 2 * k;
+                const float p0 = fast_exp2(__uint_as_float(sr[k0 >> 5][k0 & 31]) - m_ref);  // -inf - finite -> 0; a fully
+                const float p1 = fast_exp2(__uint_as_float(sr[(k0 + 1) >> 5][(k0 + 1) & 31]) - m_ref);  // masked row: NaN, below
+                ps4[k & 3] += p0 + p1;
+                w[k] = pack_half2(p0, p1);
+            }
+            const bool dead = m_ref == -INFINITY;  // nothing visible yet (padding rows of the last query tile)
             // P.V(i-1) must be complete before P is overwritten and before O is rescaled
             if (i > 0) {
-                mbar_wait(o_full, (uint32_t)((i - 1) & 1));
+                mbar_wait(o_full(x), (uint32_t)((i - 1) & 1));
                 tc_fence_after();
             }
             if (__any_sync(0xffffffffu, corr != 1.f)) {  // warp-collective TMEM access; lanes that keep their
@@ -355,60 +413,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 tmem_wait_st();
                 l_run *= corr;
             }
-            m_ref = m_new;
-            float ps = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 tokens
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k0 = c * 8 + j * 2;
-                    const float s0 = __uint_as_float(sr[k0 >> 5][k0 & 31]), s1 = __uint_as_float(sr[(k0 + 1) >> 5][(k0 + 1) & 31]);
-                    const float p0 = fast_exp2(s0 - m_ref);  // -inf - finite = -inf -> 0; a fully masked row has
-                    const float p1 = fast_exp2(s1 - m_ref);  // m_ref = -inf: -inf - -inf = NaN, handled below
-                    ps += p0 + p1;
-                    w[j] = pack_half2(p0, p1);
+                const uint32_t addr = p_row + ((c ^ (row & 7)) << 4);
+                if (dead) {
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+                } else {
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
                 }
-                if (m_ref == -INFINITY) { w[0] = w[1] = w[2] = w[3] = 0u; }
-                const uint32_t addr = p_sm + row * 128 + ((c ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                             : "memory");
             }
-            if (m_ref != -INFINITY) l_run += ps;
+            if (!dead) l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive_cnt(p_full);
+            mbar_arrive_cnt(p_full(x));
         }
-        float inv = 0.f;
-        if (n_tiles > 0) {
-            mbar_wait(o_full, (uint32_t)((n_tiles - 1) & 1));
+        if (nt > 0) {
+            mbar_wait(o_full(x), (uint32_t)((nt - 1) & 1));
             tc_fence_after();
-            inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
-        }
-        float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
+            const float inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+            float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t orr[32];
-            if (n_tiles > 0) {
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t orr[32];
                 tmem_ld32(o_addr + c4 * 32, orr);
                 tmem_wait_ld();
-            } else {
+                if (t_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) orr[j] = 0u;
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(orow + c4 * 32 + j) =
+                            make_float4(__uint_as_float(orr[j]) * inv, __uint_as_float(orr[j + 1]) * inv,
+                                        __uint_as_float(orr[j + 2]) * inv, __uint_as_float(orr[j + 3]) * inv);
+                }
             }
-            if (t_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(orow + c4 * 32 + j) =
-                        make_float4(__uint_as_float(orr[j]) * inv, __uint_as_float(orr[j + 1]) * inv,
-                                    __uint_as_float(orr[j + 2]) * inv, __uint_as_float(orr[j + 3]) * inv);
-            }
+        } else if (t_ok) {
+            // no visible key at all (zero-capacity table): the reference's 0 / (0 + eps) = 0
+            float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + t) * D;
+            for (int j = 0; j < D; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -432,10 +479,10 @@ int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, c
         return PA_ERR_UNSUPPORTED;
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
            1.4426950408889634f / temperature, (int)total_tokens};
-    const int nqt = (Tq + QT - 1) / QT;
+    const int nqt = (Tq + NQ * QT - 1) / (NQ * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
-    const size_t smem = (size_t)Q_BYTES + ST * STAGE + P_BYTES + (2 * ST + 8) * 8 + 8 + ST * 4 + 16 + 1024;
+    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + NQ * P_BYTES + NBAR * 8 + 16 + 1024;
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -349,12 +349,24 @@ def test_prefill_causal_matches_oracle(ld, oracle, kv):
     _prefill_case(ld, oracle, kv, Tq=600, start=np.array([0, 0], np.int32), check_forward=False)  # many chunks
 
 
-def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True):
+def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=False, **case_kw):
     B, H, D = 2, 3, 128
-    case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv)
+    case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv, **case_kw)
     rng = np.random.default_rng(81)
     q = rng.standard_normal((B, H, Tq, D)).astype(np.float32)
     kvc = to_device_cache(case)
+    if poison_tail:
+        # token rows past each row's context end (inside its last page, and every later page) hold NaN
+        ts = case["tile_size"]
+        for b in range(B):
+            end = int(start[b]) + Tq
+            for h in range(H):
+                for tile in range(end // ts, case["num_tiles"]):
+                    pg = int(case["table"][b, h, tile])
+                    if 0 <= pg < case["total_pages"]:
+                        r0 = end - tile * ts if tile == end // ts else 0
+                        kvc.key_buffer_[pg, r0:] = float("nan")
+                        kvc.value_buffer_[pg, r0:] = float("nan")
     out = torch.full((B, H, Tq, D), float("nan"), device="cuda")
     ld.paged_prefill(torch.from_numpy(q).cuda(), out, kvc, B, Tq, case["temperature"],
                      ctx_start=torch.from_numpy(start).cuda())
@@ -380,6 +392,70 @@ def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True):
         c2["ctx_lens"] = np.tile(np.arange(1, T + 1, dtype=np.int32), B)
         exp2 = oracle_attention(c2).reshape(B, T, H, D).transpose(0, 2, 1, 3)
         np.testing.assert_allclose(out2.cpu().numpy(), exp2, rtol=RTOL, atol=ATOL)
+
+
+PREFILL_TC_CASES = [
+    # Tq, ctx_start per row, extra make_case arguments
+    dict(Tq=128, start=[0, 0]),                                  # exactly one query tile
+    dict(Tq=129, start=[0, 7]),                                  # second query tile holds one row
+    dict(Tq=256, start=[64, 0]),                                 # both query tiles full, chunked prefill offset
+    dict(Tq=300, start=[23, 100]),                               # two CTAs per (row, head), ragged everything
+    dict(Tq=520, start=[0, 0], unmapped_frac=0.05),              # unmapped pages read as zeros
+    dict(Tq=200, start=[40, 8], tile_size=32),                   # 32-token pages (two units per page)
+    dict(Tq=70, start=[500, 3]),                                 # long history, short chunk
+]
+
+
+@pytest.mark.parametrize("ci", range(len(PREFILL_TC_CASES)))
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, monkeypatch):
+    """Both head_dim-128 fp16 prefill kernels (tcgen05 with two query tiles per CTA, PA_PREFILL_TC=1, and the
+    mma.sync kernel, =0) against the oracle at every query position: tile boundaries, ctx_start offsets,
+    unmapped pages, 32-token pages, NaN-poisoned tail of the last page."""
+    cfg = dict(PREFILL_TC_CASES[ci])
+    monkeypatch.setenv("PA_PREFILL_TC", tc)
+    Tq = cfg.pop("Tq")
+    start = np.array(cfg.pop("start"), np.int32)
+    _prefill_case(ld, oracle, "f16", Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
+
+
+def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch):
+    """Llama-7B head shape, Tq = 2048 (the benchmark's size): the tcgen05 kernel and the mma.sync kernel are
+    independent implementations; their outputs must agree within the attention tolerance, rows of a constant-V
+    cache must reproduce the constant (softmax weights sum to 1), and the last row must equal the decode kernel."""
+    B, H, D, Tq, TILE = 1, 32, 128, 2048, 16
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    nt = Tq // TILE
+    P = B * H * nt
+    kvc = ld.KVTileCache("f16", device=dev)
+    k = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+    v = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+    kvc.adopt_buffers(k, v)
+    kvc.configure_table(B, H, nt)
+    kvc.page_table_.load_host_table(torch.randperm(P, generator=g, device=dev).to(torch.int32).cpu().numpy().reshape(B, H, nt))
+    q = torch.randn((B, H, Tq, D), generator=g, device=dev)
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("PA_PREFILL_TC", tc)
+        o = torch.full_like(q, float("nan"))
+        ld.paged_prefill(q, o, kvc, B, Tq, float(np.sqrt(D)))
+        torch.cuda.synchronize()
+        outs[tc] = o.cpu().numpy()
+    np.testing.assert_allclose(outs["1"], outs["0"], rtol=RTOL, atol=ATOL)
+    # last query == one decode row over the full context
+    qd = q[:, :, -1, :].contiguous()
+    od = torch.empty_like(qd)
+    ld.AttentionCUDA.forward(qd, od, B, H, D, Tq, None, kvc, None, False, True, True, float(np.sqrt(D)))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(outs["1"][:, :, -1, :], od.cpu().numpy(), rtol=RTOL, atol=ATOL)
+    # constant V: every output element equals the constant (up to the 1e-6 epsilon of the normaliser)
+    v.fill_(0.75)
+    monkeypatch.setenv("PA_PREFILL_TC", "1")
+    o = torch.empty_like(q)
+    ld.paged_prefill(q, o, kvc, B, Tq, float(np.sqrt(D)))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o.cpu().numpy(), 0.75, rtol=1e-3, atol=0)
 
 
 # ------------------------------------------------------------------ beam-aware group kernel (C3)
