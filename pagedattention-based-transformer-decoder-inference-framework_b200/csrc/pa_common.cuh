@@ -117,6 +117,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// One lane of a converged warp.  ptxas recognises elect.sync: code under `if (elect_one())` keeps its
+// warp-uniform operands in uniform registers, so consecutive tcgen05.mma / TMA instructions are issued back
+// to back.  Under `if (lane == 0)` every such instruction is wrapped in an R2UR + ELECT + BRA.U.ANY
+// "uniformisation" loop (~100 cycles per instruction, measured with clock64 probes in prefill_tc.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -11,7 +11,7 @@
 //   warp 8      : TMEM allocation (all 512 columns) + the single thread that issues the UMMAs:
 //                   S_X[sb] (128 x 64, fp32, TMEM)  = Q_X (smem, fp16) . K^T     8 x (M128 N64  K16)
 //                   O_X     (128 x 128, fp32, TMEM) += P_X (smem, fp16) . V      4 x (M128 N128 K16)
-//   warps 9-11  : TMA producers sharing the 16 boxes of a tile (K tile as the K-major B operand of
+//   warp 9      : TMA producer, one elected thread issues the 16 boxes of a tile (K tile as the K-major B operand of
 //                 S = Q K^T, V tile as the MN-major B operand of O = P V, 3-stage ring)
 // O accumulates in TMEM across all KV tiles (accumulate flag), scaled by a per-row REFERENCE maximum that
 // is only raised when the tile maximum exceeds it by more than 8 (log2 units): P stays below 2^8 in fp16,
@@ -39,8 +39,7 @@ constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
 constexpr int P_BYTES = QT * 128;     // per query tile: [128 rows x 64 halfs]
 constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
-constexpr int NTHREADS = 384;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9-11 TMA producers (12 warps:
-                                      // ptxas grants 168 registers per thread; 13 warps would drop it to 128)
+constexpr int NTHREADS = 320;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 TMA producer
 constexpr int NBAR = 2 * ST + 5 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full, o_full, q_ready
 
 struct Args {
@@ -51,6 +50,7 @@ struct Args {
     const int32_t* ctx_start;
     int num_beams, H, num_tiles, total_pages, B, Tq, tile_size;
     float qscale;
+    int upt_shift;     // log2(16-token units per page)
     int total_tokens;  // rows of the pool tensor map: a box at this row is all zeros (out-of-bounds fill)
 };
 
@@ -174,40 +174,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     }
     const int kmax_c = max(kmaxs[0], kmaxs[1]);  // kmax is monotone in x, an absent tile has 0
     const int n_tiles = max(nts[0], nts[1]);
-    const int upt = a.tile_size >> 4;
+    const int upt_mask = (1 << a.upt_shift) - 1;  // 16-token units per page - 1 (page sizes are 16 << k)
     const int beam = a.beam_ids ? a.beam_ids[b] : b;
     const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
                               ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
 
-    if (warp >= 9) {
-        // ------------------------------------------------------------ TMA producers
-        // THREE producer warps share the 16 boxes of a tile round-robin (box = unit * 4 + {K lo, K hi, V lo,
-        // V hi}, one box per lane): the TMA operations of one warp are issued one after the other at ~150
-        // cycles apiece, so a single producer capped the ring at one tile per ~2400 cycles.
-        const int box = (warp - 9) + 3 * lane;  // lanes 0..5
-        const int uu = box >> 2, which = box & 3;
-        const bool mine = lane < 6 && box < 16;
-        int s = 0;
-        uint32_t ph = 1;
-        for (int i = 0; i < n_tiles; ++i) {
-            mbar_wait(kv_empty(s), ph);
-            const uint32_t st = kv_sm + s * STAGE;
-            if (warp == 9 && lane == 0)
-                mbar_arrive_expect_tx(kv_full(s), STAGE);  // the one arrival of the phase; the other warps' bytes
-                                                           // may complete before or after it
-            if (mine) {
-                const int u = i * 4 + uu;
-                int page = (trow && u * 16 < kmax_c) ? __ldg(trow + u / upt) : -1;
-                if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
-                // unmapped page / unit past the context: a box outside the tensor is filled with zeros (finite
-                // operands; the softmax threads mask the scores of unmapped units themselves)
-                const int row0 = page >= 0 ? page * a.tile_size + (u % upt) * 16 : a.total_tokens;
-                const uint32_t dst = st + (which >> 1) * K_BYTES + (which & 1) * 8192 + uu * 2048;
-                tma_load_2d(dst, (which >> 1) ? &tmV : &tmK, (which & 1) * 64, row0, kv_full(s));
-            }
-            if (++s == ST) {
-                s = 0;
-                ph ^= 1u;
+    if (warp == 9) {
+        // ------------------------------------------------------------ TMA producer
+        // ONE elected thread issues the 16 boxes of a tile (unit uu x {K lo, K hi, V lo, V hi}).  Everything
+        // under elect_one() stays in uniform registers, so the 16 UTMALDG go out back to back; page ids are
+        // fetched one tile ahead.
+        if (elect_one()) {
+            int pgn[4];
+            auto load_pages = [&](int tile) {
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int u = tile * 4 + uu;
+                    int page = (trow && u * 16 < kmax_c) ? __ldg(trow + (u >> a.upt_shift)) : -1;
+                    if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
+                    // unmapped page / unit past the context: a box outside the tensor is filled with zeros (finite
+                    // operands; the softmax threads mask the scores of unmapped units themselves)
+                    pgn[uu] = page >= 0 ? page * a.tile_size + (u & upt_mask) * 16 : a.total_tokens;
+                }
+            };
+            load_pages(0);
+            int s = 0;
+            uint32_t ph = 1;
+            for (int i = 0; i < n_tiles; ++i) {
+                int row0[4];
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) row0[uu] = pgn[uu];
+                if (i + 1 < n_tiles) load_pages(i + 1);
+                mbar_wait(kv_empty(s), ph);
+                const uint32_t st = kv_sm + s * STAGE;
+                mbar_arrive_expect_tx(kv_full(s), STAGE);
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    tma_load_2d(st + uu * 2048, &tmK, 0, row0[uu], kv_full(s));
+                    tma_load_2d(st + 8192 + uu * 2048, &tmK, 64, row0[uu], kv_full(s));
+                }
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    tma_load_2d(st + K_BYTES + uu * 2048, &tmV, 0, row0[uu], kv_full(s));
+                    tma_load_2d(st + K_BYTES + 8192 + uu * 2048, &tmV, 64, row0[uu], kv_full(s));
+                }
+                if (++s == ST) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else if (warp == 8) {
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         // i - 2, and this thread has already waited for p_full_X(i - 2), which every softmax thread signals
         // after its tcgen05.wait::ld: no separate "S buffer empty" barrier is needed.
         auto issue_S = [&](int x, int i, int stage) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t st = kv_sm + stage * STAGE;
                 const uint32_t qx = q_sm + x * Q_BYTES;
 #pragma unroll
@@ -269,13 +283,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 fence_proxy_async();
                 __syncwarp();
             }
-            // O_X += P_X(i) . V(i)   (the softmax threads finished any row rescale before arriving on p_full)
+            // O_X += P_X(i) . V(i), in the order the two groups deliver P (the softmax threads finished any row
+            // rescale before arriving on p_full)
+            uint32_t pend = (i < nts[0] ? 1u : 0u) | (i < nts[1] ? 2u : 0u);
+            while (pend) {
 #pragma unroll
-            for (int x = 0; x < NQ; ++x) {
-                if (i < nts[x]) {
-                    mbar_wait(p_full(x), (uint32_t)(i & 1));
+                for (int x = 0; x < NQ; ++x) {
+                    if (!((pend >> x) & 1u)) continue;
+                    if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x), (uint32_t)(i & 1)))) continue;
+                    pend &= ~(1u << x);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const int nvalid = min(KT, kmaxs[x] - i * KT);
                         const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
                         for (int ks = 0; ks < ksteps; ++ks) {
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                     __syncwarp();
                 }
             }
-            if (lane == 0) umma_commit(kv_empty(s));
+            if (elect_one()) umma_commit(kv_empty(s));
             __syncwarp();
             if (++s == ST) {
                 s = 0;
@@ -308,21 +326,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         const uint32_t lane_base = (uint32_t)(qtr * 32) << 16;
         if (nt > 0) {
             // Q rows of this warp -> fp16, pre-scaled, into the swizzled K-major A tile.  One row per step, the
-            // whole warp on its 512 bytes (coalesced); 8 rows in flight.
+            // whole warp on its 512 bytes (coalesced); 16 rows in flight.
             const float* qbase = a.q + (((int64_t)b * a.H + h) * a.Tq) * D;
             const uint32_t qx = q_sm + x * Q_BYTES;
             const int c = lane >> 1;  // 16-byte chunk (8 halfs) of the row this lane contributes to
 #pragma unroll 1
-            for (int r0 = 0; r0 < 32; r0 += 8) {
-                float4 v[8];
+            for (int r0 = 0; r0 < 32; r0 += 16) {
+                float4 v[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const int tr = q0 + qtr * 32 + r0 + j;
                     v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * D) + lane)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const int rr = qtr * 32 + r0 + j;
                     const uint32_t w0 = pack_half2(v[j].x * a.qscale, v[j].y * a.qscale);
                     const uint32_t w1 = pack_half2(v[j].z * a.qscale, v[j].w * a.qscale);
@@ -337,17 +355,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         const uint32_t s_addr = tmem_base + lane_base + x * 2 * KT;
         const uint32_t o_addr = tmem_base + lane_base + NQ * 2 * KT + x * D;
         const uint32_t p_row = p_sm + x * P_BYTES + row * 128;
+        int pgn[4];  // page ids of the next tile's 4 units
+        auto load_pages = [&](int tile) {
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int u = tile * 4 + uu;
+                pgn[uu] = (trow && u * 16 < kmax) ? __ldg(trow + (u >> a.upt_shift)) : -1;
+            }
+        };
+        load_pages(0);
 #pragma unroll 1
         for (int i = 0; i < nt; ++i) {
             const int sb = i & 1;
-            // which of the tile's 4 units are mapped (an unmapped page is skipped: ...fused.cu:32) -- the table
-            // entries are fetched before the wait so their latency hides behind it
+            // which of the tile's 4 units are mapped (an unmapped page is skipped: ...fused.cu:32); the table
+            // entries were fetched one tile ahead, so their latency is never waited for
             int pg[4];
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-                const int u = i * 4 + uu;
-                pg[uu] = (trow && u * 16 < kmax) ? __ldg(trow + u / upt) : -1;
-            }
+            for (int uu = 0; uu < 4; ++uu) pg[uu] = pgn[uu];
+            load_pages(i + 1);
             mbar_wait(s_full(x, sb), (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             uint32_t sr[2][32];
@@ -477,8 +502,12 @@ int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, c
     if (total_tokens >= 0x7fffffffull) return PA_ERR_UNSUPPORTED;
     if (!make_pool_map(&tmK, d_k_pool, total_tokens) || !make_pool_map(&tmV, d_v_pool, total_tokens))
         return PA_ERR_UNSUPPORTED;
+    const int upt = tile_size >> 4;
+    if (tile_size % 16 != 0 || (upt & (upt - 1)) != 0) return PA_ERR_UNSUPPORTED;  // pages of 16 << k tokens only
+    int upt_shift = 0;
+    while ((1 << upt_shift) < upt) ++upt_shift;
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
-           1.4426950408889634f / temperature, (int)total_tokens};
+           1.4426950408889634f / temperature, upt_shift, (int)total_tokens};
     const int nqt = (Tq + NQ * QT - 1) / (NQ * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
