@@ -249,7 +249,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {  // elect.sync, not lane == 0: operands stay in uniform registers (pa_common.cuh)
 #ifdef PA_GEMM_PROBE
             long long pw = 0, t_start = clock64();
 #endif
@@ -293,7 +293,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
 #ifdef PA_GEMM_PROBE
             long long mw = 0, t_start = clock64();
 #endif
@@ -526,7 +526,7 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES2;
 #ifdef PA_GEMM_PROBE
@@ -549,7 +549,7 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
         }
     } else if (warp == 1) {
-        if (lane == 0 && crank == 0) {
+        if (crank == 0 && elect_one()) {
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES2;
 #ifdef PA_GEMM_PROBE

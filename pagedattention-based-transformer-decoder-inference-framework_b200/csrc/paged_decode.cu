@@ -1019,7 +1019,7 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         const bool last_of_unit = (p_pending_mask == 0);
         const bool last_of_chunk = last_of_unit && (p_u + 1 >= p_uend);
         const int nvalid = mask ? min(kUnitTok, p_ctx - p_u * kUnitTok) : 0;
-        if (lane == 0) {
+        if (elect_one()) {
             // meta: [0,5) tokens of the unit inside the group's context, [5,13) beams sharing this copy,
             // [13] last stage of the chunk, [14,32) unit index (per-beam context limits in ragged mode)
             my_meta[st] = nvalid | (mask << 5) | (last_of_chunk ? (1 << 13) : 0) | (p_u << 14);

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(192) prefill_fa_kernel(const __grid_constant__
     const int upt = a.tile_size >> 4;
 
     if (warp == 4) {  // ---------------- producer
-        if (lane == 0) {
+        if (elect_one()) {
             const int beam = a.beam_ids ? a.beam_ids[b] : b;
             const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
                                       ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
