@@ -37,7 +37,6 @@ constexpr int Q_BYTES = 2 * QT * 128; // per query tile: two k-blocks of [128 ro
 constexpr int K_BYTES = 2 * KT * 128; // two k-blocks of [64 rows x 128 B]
 constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
-constexpr int P_BYTES = QT * 128;     // per query tile: [128 rows x 64 halfs]
 constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
 constexpr int NTHREADS = 320;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 TMA producer
 constexpr int NBAR = 2 * ST + 5 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full, o_full, q_ready
@@ -70,6 +69,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in TMEM: row m of A = TMEM lane m, 32-bit column j = (A[m][2j], A[m][2j+1]) as packed fp16
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -112,6 +121,19 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// -DPA_PTC_PROBE: clock64 stamps of one softmax warp per group and of the UMMA warp for 64 steady-state KV
+// tiles of CTA 5, read back with pa_debug_ptc_probe (benchmarks/prefill_probe.py).  Off in the product build.
+#ifdef PA_PTC_PROBE
+__device__ long long g_probe[3 * 64 * 8];
+#define PROBE(role, it, k)                                                                          \
+    do {                                                                                            \
+        if (blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (it) >= 16 && (it) < 80)                  \
+            g_probe[((role) * 64 + (it) - 16) * 8 + (k)] = clock64();                               \
+    } while (0)
+#else
+#define PROBE(role, it, k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
@@ -119,8 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
     const uint32_t kv_sm = q_sm + NQ * Q_BYTES;
-    const uint32_t p_sm = kv_sm + ST * STAGE;
-    const uint32_t bar0 = p_sm + NQ * P_BYTES;
+    const uint32_t bar0 = kv_sm + ST * STAGE;
     auto kv_full = [&](int s) { return bar0 + s * 8; };
     auto kv_empty = [&](int s) { return bar0 + (ST + s) * 8; };
     auto s_full = [&](int x, int sb) { return bar0 + (2 * ST + 5 * x + sb) * 8; };
@@ -261,6 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         for (int i = 0; i < n_tiles; ++i) {
             // S(i+1) as soon as its K tile has landed, so it overlaps the softmax of tile i
             const int s_next = (s + 1 == ST) ? 0 : s + 1;
+            PROBE(2, i, 0);
             if (i + 1 < n_tiles) {
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
                 mbar_wait(kv_full(s_next), ph_next);
@@ -269,6 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 for (int x = 0; x < NQ; ++x)
                     if (i + 1 < nts[x]) issue_S(x, i + 1, s_next);
             }
+            PROBE(2, i, 1);
             const uint32_t st = kv_sm + s * STAGE;
             const int nvalid_c = min(KT, kmax_c - i * KT);
             if (nvalid_c < KT && (nvalid_c & 15)) {
@@ -292,18 +315,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                     if (!((pend >> x) & 1u)) continue;
                     if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x), (uint32_t)(i & 1)))) continue;
                     pend &= ~(1u << x);
+                    PROBE(2, i, 2 + 2 * x);
                     tc_fence_after();
                     if (elect_one()) {
                         const int nvalid = min(KT, kmaxs[x] - i * KT);
                         const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t da = make_desc(p_sm + x * P_BYTES + ks * 32, 16, 1024);
+                            // P(i) sits in the first 32 columns of the S buffer it was computed from
+                            const uint32_t ta = tmem_base + x * 2 * KT + (i & 1) * KT + ks * 8;
                             const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
-                            umma_f16(tmem_base + NQ * 2 * KT + x * D, da, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
+                            umma_f16_ts(tmem_base + NQ * 2 * KT + x * D, ta, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
                         }
                         umma_commit(o_full(x));
                     }
                     __syncwarp();
+                    PROBE(2, i, 3 + 2 * x);
                 }
             }
             if (elect_one()) umma_commit(kv_empty(s));
@@ -354,7 +380,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         float m_ref = -INFINITY, l_run = 0.f;  // reference maximum of this row (see the header), running sum
         const uint32_t s_addr = tmem_base + lane_base + x * 2 * KT;
         const uint32_t o_addr = tmem_base + lane_base + NQ * 2 * KT + x * D;
-        const uint32_t p_row = p_sm + x * P_BYTES + row * 128;
         int pgn[4];  // page ids of the next tile's 4 units
         auto load_pages = [&](int tile) {
 #pragma unroll
@@ -373,12 +398,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) pg[uu] = pgn[uu];
             load_pages(i + 1);
+            if (qtr == 0) PROBE(x, i, 0);
             mbar_wait(s_full(x, sb), (uint32_t)((i >> 1) & 1));
             tc_fence_after();
+            if (qtr == 0) PROBE(x, i, 1);
             uint32_t sr[2][32];
             tmem_ld32(s_addr + sb * KT, sr[0]);
             tmem_ld32(s_addr + sb * KT + 32, sr[1]);
             tmem_wait_ld();
+            if (qtr == 0) PROBE(x, i, 2);
             // causal / context / unmapped-page mask (only tiles that need one) + tile maximum
             const int kp0 = i * KT;
             bool all_mapped = true;
@@ -419,14 +447,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                 ps4[k & 3] += p0 + p1;
                 w[k] = pack_half2(p0, p1);
             }
+            if (qtr == 0) PROBE(x, i, 3);
             const bool dead = m_ref == -INFINITY;  // nothing visible yet (padding rows of the last query tile)
-            // P.V(i-1) must be complete before P is overwritten and before O is rescaled
-            if (i > 0) {
-                mbar_wait(o_full(x), (uint32_t)((i - 1) & 1));
-                tc_fence_after();
-            }
+            if (qtr == 0) PROBE(x, i, 4);
             if (__any_sync(0xffffffffu, corr != 1.f)) {  // warp-collective TMEM access; lanes that keep their
-#pragma unroll                                          // reference multiply by 1
+                // reference multiply by 1.  P.V(i-1) must be complete before O is rescaled.  (Skipping this wait
+                // on other tiles is safe: the barrier cannot run more than one phase ahead of this thread,
+                // because P.V(i) is only issued after the thread's own arrival on p_full(i).)
+                if (i > 0) {
+                    mbar_wait(o_full(x), (uint32_t)((i - 1) & 1));
+                    tc_fence_after();
+                }
+#pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     uint32_t orr[32];
                     tmem_ld32(o_addr + c4 * 32, orr);
@@ -435,25 +467,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                     for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * corr);
                     tmem_st32(o_addr + c4 * 32, orr);
                 }
-                tmem_wait_st();
                 l_run *= corr;
             }
+            // P(i) as packed fp16 over the first 32 columns of this tile's S buffer (every score of the row is
+            // already in registers); it is the TMEM A operand of P.V(i).  The buffer's previous user, P.V(i-2),
+            // completed before S(i) was written (same issuing thread, in order).
+            if (dead) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 tokens
-                const uint32_t addr = p_row + ((c ^ (row & 7)) << 4);
-                if (dead) {
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
-                } else {
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
-                                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
-                }
+                for (int k = 0; k < 32; ++k) w[k] = 0u;
             }
+            tmem_st32(s_addr + sb * KT, w);
+            tmem_wait_st();
             if (!dead) l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-            fence_proxy_async();
+            if (qtr == 0) PROBE(x, i, 5);
             tc_fence_before();
             mbar_arrive_cnt(p_full(x));
+            if (qtr == 0) PROBE(x, i, 6);
         }
         if (nt > 0) {
+            // The per-tile waits on o_full are skipped unless a rescale needs them, so the barrier may still be
+            // in phase nt - 2 here (S(nt-1), which this thread has read, was issued before P.V(nt-2)): wait for
+            // that phase first, a parity wait is only unambiguous one phase at a time.
+            if (nt > 1) mbar_wait(o_full(x), (uint32_t)((nt - 2) & 1));
             mbar_wait(o_full(x), (uint32_t)((nt - 1) & 1));
             tc_fence_after();
             const float inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
@@ -491,6 +526,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
 
 using namespace pa;
 
+#ifdef PA_PTC_PROBE
+extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, pa::ptc::g_probe, sizeof(long long) * 3 * 64 * 8);
+}
+#endif
+
 // Launch helper used by prefill.cu (returns PA_ERR_UNSUPPORTED when the tensor maps cannot be built).
 int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                          const int32_t* d_table, int num_beams, int num_heads, int num_tiles, int total_pages,
@@ -511,7 +552,7 @@ int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, c
     const int nqt = (Tq + NQ * QT - 1) / (NQ * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
-    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + NQ * P_BYTES + NBAR * 8 + 16 + 1024;
+    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + NBAR * 8 + 16 + 1024;
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
