@@ -6,8 +6,8 @@
 
 clock64 stamps of warp 0 (softmax group A), warp 4 (group B) and the UMMA warp over 64 steady-state KV tiles
 of CTA 5.  Softmax segments: wait S | tcgen05.ld | mask + max + exp2 + pack | wait P.V(i-1) | rescale + P
-stores | fences + arrive.  UMMA warp: wait K/V(i+1) + issue S(i+1) x2 | wait first P | issue P.V | wait
-second P | issue P.V.  The product library is not touched."""
+store to TMEM | fence + arrive.  UMMA warp, per tile t: A's P(t) seen | A's P.V(t) issued | B's P(t) seen | B's
+P.V(t) issued (differences between consecutive stamps).  The product library is not touched."""
 import ctypes
 import glob
 import os
@@ -65,7 +65,12 @@ def main():
     fn.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     assert fn(buf) == 0
     a = np.array(buf[:]).reshape(3, 64, 8)
-    for role, name, nseg in ((0, "softmax A", 6), (1, "softmax B", 6), (2, "umma", 5)):
+    if "--raw" in sys.argv:  # stamps of 8 consecutive tiles relative to the first
+        t0 = a[:, 20, :].min()
+        for role, name in ((0, "softmax A"), (1, "softmax B"), (2, "umma")):
+            for it in range(20, 28):
+                print(name, "tile", it + 16, (a[role, it, :7] - t0).tolist())
+    for role, name, nseg in ((0, "softmax A", 6), (1, "softmax B", 6), (2, "umma", 3)):
         r = a[role]
         per = np.diff(r[:, 0])
         seg = np.median(np.diff(r[:, :nseg + 1], axis=1), axis=0)

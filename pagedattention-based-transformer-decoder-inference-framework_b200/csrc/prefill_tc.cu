@@ -39,7 +39,7 @@ constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
 constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
 constexpr int NTHREADS = 320;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 TMA producer
-constexpr int NBAR = 2 * ST + 5 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full, o_full, q_ready
+constexpr int NBAR = 2 * ST + 7 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full[2], o_full[2], q_ready
 
 struct Args {
     const float* q;
@@ -117,6 +117,14 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
     return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+// Every wait of this kernel is bounded: a protocol error becomes a trap (CUDA error at the next
+// synchronisation) after ~1 s instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > (1u << 26)) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -144,10 +152,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     const uint32_t bar0 = kv_sm + ST * STAGE;
     auto kv_full = [&](int s) { return bar0 + s * 8; };
     auto kv_empty = [&](int s) { return bar0 + (ST + s) * 8; };
-    auto s_full = [&](int x, int sb) { return bar0 + (2 * ST + 5 * x + sb) * 8; };
-    auto p_full = [&](int x) { return bar0 + (2 * ST + 5 * x + 2) * 8; };
-    auto o_full = [&](int x) { return bar0 + (2 * ST + 5 * x + 3) * 8; };
-    auto q_ready = [&](int x) { return bar0 + (2 * ST + 5 * x + 4) * 8; };
+    // s_full, p_full and o_full alternate between two barriers (tile i -> barrier i & 1, phase i >> 1): a parity
+    // wait is only unambiguous while the barrier is at most ONE phase ahead of the waiter, and with S computed
+    // one tile ahead the softmax threads and the UMMA thread can be a tile apart in either direction.
+    auto s_full = [&](int x, int sb) { return bar0 + (2 * ST + 7 * x + sb) * 8; };
+    auto p_full = [&](int x, int par) { return bar0 + (2 * ST + 7 * x + 2 + par) * 8; };
+    auto o_full = [&](int x, int par) { return bar0 + (2 * ST + 7 * x + 4 + par) * 8; };
+    auto q_ready = [&](int x) { return bar0 + (2 * ST + 7 * x + 6) * 8; };
     const uint32_t tmem_slot = bar0 + NBAR * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,8 +170,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         for (int x = 0; x < NQ; ++x) {
             mbar_init(s_full(x, 0), 1);
             mbar_init(s_full(x, 1), 1);
-            mbar_init(p_full(x), QT);
-            mbar_init(o_full(x), 1);
+            mbar_init(p_full(x, 0), QT);
+            mbar_init(p_full(x, 1), QT);
+            mbar_init(o_full(x, 0), 1);
+            mbar_init(o_full(x, 1), 1);
             mbar_init(q_ready(x), QT);
         }
         mbar_fence_init();
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) row0[uu] = pgn[uu];
                 if (i + 1 < n_tiles) load_pages(i + 1);
-                mbar_wait(kv_empty(s), ph);
+                mbar_wait_wd(kv_empty(s), ph);
                 const uint32_t st = kv_sm + s * STAGE;
                 mbar_arrive_expect_tx(kv_full(s), STAGE);
 #pragma unroll
@@ -267,11 +280,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             __syncwarp();
         };
         if (n_tiles > 0) {
-            mbar_wait(kv_full(0), 0);
+            mbar_wait_wd(kv_full(0), 0);
 #pragma unroll
             for (int x = 0; x < NQ; ++x) {
                 if (nts[x] > 0) {
-                    mbar_wait(q_ready(x), 0);
+                    mbar_wait_wd(q_ready(x), 0);
                     tc_fence_after();
                     issue_S(x, 0, 0);
                 }
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             PROBE(2, i, 0);
             if (i + 1 < n_tiles) {
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
-                mbar_wait(kv_full(s_next), ph_next);
+                mbar_wait_wd(kv_full(s_next), ph_next);
                 tc_fence_after();
 #pragma unroll
                 for (int x = 0; x < NQ; ++x)
@@ -309,11 +322,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             // O_X += P_X(i) . V(i), in the order the two groups deliver P (the softmax threads finished any row
             // rescale before arriving on p_full)
             uint32_t pend = (i < nts[0] ? 1u : 0u) | (i < nts[1] ? 2u : 0u);
+            uint32_t idle = 0;
             while (pend) {
+                if (++idle > (1u << 26)) __trap();
 #pragma unroll
                 for (int x = 0; x < NQ; ++x) {
                     if (!((pend >> x) & 1u)) continue;
-                    if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x), (uint32_t)(i & 1)))) continue;
+                    if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x, i & 1), (uint32_t)((i >> 1) & 1)))) continue;
                     pend &= ~(1u << x);
                     PROBE(2, i, 2 + 2 * x);
                     tc_fence_after();
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
                             const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
                             umma_f16_ts(tmem_base + NQ * 2 * KT + x * D, ta, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
                         }
-                        umma_commit(o_full(x));
+                        umma_commit(o_full(x, i & 1));
                     }
                     __syncwarp();
                     PROBE(2, i, 3 + 2 * x);
@@ -380,6 +395,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
         float m_ref = -INFINITY, l_run = 0.f;  // reference maximum of this row (see the header), running sum
         const uint32_t s_addr = tmem_base + lane_base + x * 2 * KT;
         const uint32_t o_addr = tmem_base + lane_base + NQ * 2 * KT + x * D;
+        // P.V(t') completion: tile t' -> barrier t' & 1, phase t' >> 1.  Every thread consumes the phases of each
+        // barrier in order and at the latest two tiles late (P.V(t') can only be issued after this thread's own
+        // arrival on p_full(t'), so the barrier is never more than one phase ahead of what is waited for).
+        int oc[2] = {0, 0};
+        auto ensure_pv = [&](int tp) {
+            const int bsel = tp & 1, k = tp >> 1;
+            if (oc[bsel] <= k) {
+                mbar_wait_wd(o_full(x, bsel), (uint32_t)(k & 1));
+                oc[bsel] = k + 1;
+            }
+        };
         int pgn[4];  // page ids of the next tile's 4 units
         auto load_pages = [&](int tile) {
 #pragma unroll
@@ -399,7 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             for (int uu = 0; uu < 4; ++uu) pg[uu] = pgn[uu];
             load_pages(i + 1);
             if (qtr == 0) PROBE(x, i, 0);
-            mbar_wait(s_full(x, sb), (uint32_t)((i >> 1) & 1));
+            mbar_wait_wd(s_full(x, sb), (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             if (qtr == 0) PROBE(x, i, 1);
             uint32_t sr[2][32];
@@ -450,14 +476,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             if (qtr == 0) PROBE(x, i, 3);
             const bool dead = m_ref == -INFINITY;  // nothing visible yet (padding rows of the last query tile)
             if (qtr == 0) PROBE(x, i, 4);
+            if (i >= 2) ensure_pv(i - 2);  // complete since S(i) was written: keeps the phase bookkeeping tight
             if (__any_sync(0xffffffffu, corr != 1.f)) {  // warp-collective TMEM access; lanes that keep their
-                // reference multiply by 1.  P.V(i-1) must be complete before O is rescaled.  (Skipping this wait
-                // on other tiles is safe: the barrier cannot run more than one phase ahead of this thread,
-                // because P.V(i) is only issued after the thread's own arrival on p_full(i).)
-                if (i > 0) {
-                    mbar_wait(o_full(x), (uint32_t)((i - 1) & 1));
-                    tc_fence_after();
-                }
+                // reference multiply by 1.  P.V(i-1) must be complete before O is rescaled.
+                if (i > 0) ensure_pv(i - 1);
+                tc_fence_after();
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     uint32_t orr[32];
@@ -481,15 +504,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             if (!dead) l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             if (qtr == 0) PROBE(x, i, 5);
             tc_fence_before();
-            mbar_arrive_cnt(p_full(x));
+            mbar_arrive_cnt(p_full(x, sb));
             if (qtr == 0) PROBE(x, i, 6);
         }
         if (nt > 0) {
-            // The per-tile waits on o_full are skipped unless a rescale needs them, so the barrier may still be
-            // in phase nt - 2 here (S(nt-1), which this thread has read, was issued before P.V(nt-2)): wait for
-            // that phase first, a parity wait is only unambiguous one phase at a time.
-            if (nt > 1) mbar_wait(o_full(x), (uint32_t)((nt - 2) & 1));
-            mbar_wait(o_full(x), (uint32_t)((nt - 1) & 1));
+            if (nt > 1) ensure_pv(nt - 2);
+            ensure_pv(nt - 1);
             tc_fence_after();
             const float inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
             float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
