@@ -56,8 +56,8 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
             flops = 4.0 * B * H * D * Tq * (Tq + 1) / 2
-            tc = kv == "f16" and os.environ.get("PA_PREFILL_TC", "1") != "0"
-            out_line[("tcgen05_f16" if tc else "flash_mma_f16") if kv == "f16" else "flash_mma_i8"] = {
+            tc = os.environ.get("PA_PREFILL_TC", "1") != "0"
+            out_line[("tcgen05_" if tc else "flash_mma_") + kv] = {
                 "ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
         res.append(out_line)
     print(json.dumps({"workload": "prefill attention, one layer, 32 heads x D=128, causal", "results": res}))

@@ -417,10 +417,10 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 using namespace pa;
 
 // prefill_tc.cu: tcgen05 flash-attention prefill (fp16 pages, head_dim 128)
-int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
-                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles, int total_pages,
-                         const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq, int tile_size,
-                         float temperature, cudaStream_t st);
+int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                         const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
+                         int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
+                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st);
 
 PA_API size_t pa_prefill_workspace_bytes(int B, int Tq, int num_heads, int head_dim, int num_tiles, int tile_size) {
     if (B < 0 || Tq <= 0 || num_heads <= 0 || head_dim <= 0 || num_tiles <= 0 || tile_size <= 0) return 0;
@@ -443,11 +443,11 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     if (head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
         d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0) &&
         (kv == 0 || ((uintptr_t)d_k_scales % 16 == 0 && (uintptr_t)d_v_scales % 16 == 0))) {
-        // fp16 pages: tcgen05 kernel (prefill_tc.cu) unless PA_PREFILL_TC=0 asks for the mma.sync kernel below
-        if (kv == 0 && !(getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 0)) {
-            const int stc = pa_prefill_tc_launch(d_q, d_out, d_k_pool, d_v_pool, d_table, num_beams, num_heads, num_tiles,
-                                                 total_pages, d_beam_ids, d_ctx_start, B, Tq, tile_size, temperature,
-                                                 as_stream(stream));
+        // tcgen05 kernel (prefill_tc.cu, fp16 and int8 pages) unless PA_PREFILL_TC=0 asks for the mma.sync kernel below
+        if (!(getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 0)) {
+            const int stc = pa_prefill_tc_launch(kv, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table,
+                                                 num_beams, num_heads, num_tiles, total_pages, d_beam_ids, d_ctx_start, B,
+                                                 Tq, tile_size, temperature, as_stream(stream));
             if (stc != PA_ERR_UNSUPPORTED) return stc;
         }
         // tensor-core flash-attention kernel, straight on the [B, H, Tq, D] layout (no workspace)

@@ -39,6 +39,15 @@ constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
 constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
 constexpr int NTHREADS = 320;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 TMA producer
+// int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
+// into a raw ring, two converter warps (10, 11) rewrite them as the same swizzled fp16 stage the fp16 path gets
+// from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
+// the K scale to the score columns and fold the V scale into P (int8_quant.cpp:46-57: x = q / scale).
+constexpr int NTHREADS_I8 = 384;      // 12 warps still get 168 registers per thread
+constexpr int RS = 3;                 // raw ring stages (one 64-token tile each)
+constexpr int RAW_UNIT = 2048 + 2048 + 64 + 64;
+constexpr int RAW_STAGE = 4 * RAW_UNIT;
+constexpr int SCALE_BYTES = 2 * KT * 4;  // per fp16 stage: 1/k_scale[64], 1/v_scale[64]
 constexpr int NBAR = 2 * ST + 7 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full[2], o_full[2], q_ready
 
 struct Args {
@@ -49,6 +58,10 @@ struct Args {
     const int32_t* ctx_start;
     int num_beams, H, num_tiles, total_pages, B, Tq, tile_size;
     float qscale;
+    const int8_t* k8;      // int8 pools and their per-(page, token) scales (KV = 1)
+    const int8_t* v8;
+    const float* k_scales;
+    const float* v_scales;
     int upt_shift;     // log2(16-token units per page)
     int total_tokens;  // rows of the pool tensor map: a box at this row is all zeros (out-of-bounds fill)
 };
@@ -142,14 +155,17 @@ __device__ long long g_probe[3 * 64 * 8];
 #define PROBE(role, it, k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
+template <int KV>
+__global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
     const uint32_t kv_sm = q_sm + NQ * Q_BYTES;
-    const uint32_t bar0 = kv_sm + ST * STAGE;
+    const uint32_t raw_sm = kv_sm + ST * STAGE;                       // KV = 1 only
+    const uint32_t scale_sm = raw_sm + (KV ? RS * RAW_STAGE : 0);     // KV = 1 only
+    const uint32_t bar0 = scale_sm + (KV ? ST * SCALE_BYTES : 0);
     auto kv_full = [&](int s) { return bar0 + s * 8; };
     auto kv_empty = [&](int s) { return bar0 + (ST + s) * 8; };
     // s_full, p_full and o_full alternate between two barriers (tile i -> barrier i & 1, phase i >> 1): a parity
@@ -159,13 +175,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     auto p_full = [&](int x, int par) { return bar0 + (2 * ST + 7 * x + 2 + par) * 8; };
     auto o_full = [&](int x, int par) { return bar0 + (2 * ST + 7 * x + 4 + par) * 8; };
     auto q_ready = [&](int x) { return bar0 + (2 * ST + 7 * x + 6) * 8; };
-    const uint32_t tmem_slot = bar0 + NBAR * 8;
+    auto raw_full = [&](int s) { return bar0 + (NBAR + s) * 8; };
+    auto raw_empty = [&](int s) { return bar0 + (NBAR + RS + s) * 8; };
+    const uint32_t tmem_slot = bar0 + (NBAR + 2 * RS) * 8;
+    const uint32_t meta_sm = tmem_slot + 8;  // KV = 1: per raw stage, bit u = unit u of the tile was copied
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; ++s) {
-            mbar_init(kv_full(s), 1);
+            mbar_init(kv_full(s), KV ? 2 : 1);  // KV = 1: one arrival per converter warp
             mbar_init(kv_empty(s), 1);
+        }
+        if (KV) {
+            for (int s = 0; s < RS; ++s) {
+                mbar_init(raw_full(s), 1);
+                mbar_init(raw_empty(s), 2);
+            }
         }
         for (int x = 0; x < NQ; ++x) {
             mbar_init(s_full(x, 0), 1);
@@ -213,7 +238,122 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
     const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
                               ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
 
-    if (warp == 9) {
+    if (KV == 1 && warp == 9) {
+        // ------------------------------------------------------------ producer, int8 pages: raw units by bulk copy
+        if (elect_one()) {
+            int* meta = reinterpret_cast<int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
+            int rs = 0;
+            uint32_t ph = 1;
+            for (int i = 0; i < n_tiles; ++i) {
+                int64_t row0[4];
+                uint32_t mask = 0;
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int u = i * 4 + uu;
+                    int page = (trow && u * 16 < kmax_c) ? __ldg(trow + (u >> a.upt_shift)) : -1;
+                    if ((unsigned)page >= (unsigned)a.total_pages) page = -1;
+                    row0[uu] = (int64_t)page * a.tile_size + (u & upt_mask) * 16;  // token row in the pools
+                    if (page >= 0) mask |= 1u << uu;
+                }
+                mbar_wait_wd(raw_empty(rs), ph);
+                meta[rs] = (int)mask;
+                mbar_arrive_expect_tx(raw_full(rs), (uint32_t)__popc(mask) * RAW_UNIT);
+                const uint32_t dst = raw_sm + rs * RAW_STAGE;
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    if ((mask >> uu) & 1u) {
+                        const uint32_t d = dst + uu * RAW_UNIT;
+                        bulk_g2s_nohint(d, a.k8 + row0[uu] * D, 2048, raw_full(rs));
+                        bulk_g2s_nohint(d + 2048, a.v8 + row0[uu] * D, 2048, raw_full(rs));
+                        bulk_g2s_nohint(d + 4096, a.k_scales + row0[uu], 64, raw_full(rs));
+                        bulk_g2s_nohint(d + 4160, a.v_scales + row0[uu], 64, raw_full(rs));
+                    }
+                }
+                if (++rs == RS) {
+                    rs = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (KV == 1 && warp >= 10) {
+        // ------------------------------------------------------------ converters: raw int8 units -> fp16 stage
+        // warp cw rewrites units 2 cw and 2 cw + 1 of every tile; lane = (token row, 64-dim half).  K and V have
+        // the same shared-memory image ([64-dim half][token row of 128 B], SWIZZLE_128B); only the UMMA
+        // descriptors read them differently.
+        const int* meta = reinterpret_cast<const int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
+        const int cw = warp - 10;
+        const int tr = lane >> 1, hf = lane & 1;
+        const __half2 off = __floats2half2_rn(1152.f, 1152.f);
+        int rs = 0, fs = 0;
+        uint32_t rph = 0, fph = 1;
+        for (int i = 0; i < n_tiles; ++i) {
+            mbar_wait_wd(raw_full(rs), rph);
+            mbar_wait_wd(kv_empty(fs), fph);
+            const uint32_t mask = (uint32_t)meta[rs];
+            const uint32_t dst = kv_sm + fs * STAGE;
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const int uu = 2 * cw + k2;
+                const uint32_t src = raw_sm + rs * RAW_STAGE + uu * RAW_UNIT;
+                const bool have = (mask >> uu) & 1u;
+                const int r = uu * 16 + tr;  // token row inside the tile
+#pragma unroll
+                for (int kvsel = 0; kvsel < 2; ++kvsel) {
+                    const uint32_t boxrow = dst + kvsel * K_BYTES + hf * 8192 + r * 128;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {  // 16 int8 -> two 16-byte chunks of 8 halfs
+                        uint32_t hv[8];
+                        if (have) {
+                            const uint4 w = lds_128(src + kvsel * 2048 + tr * 128 + hf * 64 + c4 * 16);
+                            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t xb = ww[e] ^ 0x80808080u;  // u = b + 128
+                                uint32_t p01 = __byte_perm(xb, 0x64646464u, 0x4140);  // halfs (1024 + u0, 1024 + u1)
+                                uint32_t p23 = __byte_perm(xb, 0x64646464u, 0x4342);
+                                __half2 a01 = __hsub2(*reinterpret_cast<__half2*>(&p01), off);
+                                __half2 a23 = __hsub2(*reinterpret_cast<__half2*>(&p23), off);
+                                hv[2 * e] = *reinterpret_cast<uint32_t*>(&a01);
+                                hv[2 * e + 1] = *reinterpret_cast<uint32_t*>(&a23);
+                            }
+                        } else {  // unmapped page / unit past the context: finite zeros (its scores are masked)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) hv[e] = 0u;
+                        }
+                        const int c = 2 * c4;
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c) ^ (r & 7)) << 4)),
+                                     "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c + 1) ^ (r & 7)) << 4)),
+                                     "r"(hv[4]), "r"(hv[5]), "r"(hv[6]), "r"(hv[7]) : "memory");
+                    }
+                }
+                // 1 / scale per token: lanes 0-15 the unit's K rows, 16-31 its V rows.  Tokens past the context
+                // get 0 (their P is 0, and 0 x a garbage scale must not become NaN).
+                float sc = 0.f;
+                const int tok = i * KT + uu * 16 + (lane & 15);
+                if (have && tok < kmax_c) {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(src + 4096 + lane * 4));
+                    sc = fast_rcp(sc);
+                }
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(scale_sm + fs * SCALE_BYTES + (lane >> 4) * (KT * 4) +
+                                                              (uu * 16 + (lane & 15)) * 4), "f"(sc) : "memory");
+            }
+            fence_proxy_async();  // the UMMA reads the stage through the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(kv_full(fs));
+                mbar_arrive(raw_empty(rs));
+            }
+            if (++rs == RS) {
+                rs = 0;
+                rph ^= 1u;
+            }
+            if (++fs == ST) {
+                fs = 0;
+                fph ^= 1u;
+            }
+        }
+    } else if (warp == 9) {
         // ------------------------------------------------------------ TMA producer
         // ONE elected thread issues the 16 boxes of a tile (unit uu x {K lo, K hi, V lo, V hi}).  Everything
         // under elect_one() stays in uniform registers, so the 16 UTMALDG go out back to back; page ids are
@@ -307,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             PROBE(2, i, 1);
             const uint32_t st = kv_sm + s * STAGE;
             const int nvalid_c = min(KT, kmax_c - i * KT);
-            if (nvalid_c < KT && (nvalid_c & 15)) {
+            if (KV == 0 && nvalid_c < KT && (nvalid_c & 15)) {
                 // rows of the last page past the context end may hold anything (0 x NaN = NaN): zero them
                 const int r0 = nvalid_c;
                 const int r1 = (nvalid_c + 15) & ~15;
@@ -415,6 +555,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             }
         };
         load_pages(0);
+        int sfs = 0;          // KV = 1: fp16 stage of tile i and the parity of its kv_full phase
+        uint32_t sfph = 0;
 #pragma unroll 1
         for (int i = 0; i < nt; ++i) {
             const int sb = i & 1;
@@ -432,6 +574,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             tmem_ld32(s_addr + sb * KT, sr[0]);
             tmem_ld32(s_addr + sb * KT + 32, sr[1]);
             tmem_wait_ld();
+            if (KV == 1) {
+                // int8 pages: score column k is (q . k_q[k]) / k_scale[k].  Waiting on the stage's own barrier
+                // (long complete) makes the converter's scale writes visible to this thread.
+                mbar_wait_wd(kv_full(sfs), sfph);
+                const uint32_t ksc = scale_sm + sfs * SCALE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const uint4 f = lds_128(ksc + c * 16);
+                    const int k0 = 4 * c;
+                    sr[k0 >> 5][k0 & 31] = __float_as_uint(__uint_as_float(sr[k0 >> 5][k0 & 31]) * __uint_as_float(f.x));
+                    sr[k0 >> 5][(k0 + 1) & 31] = __float_as_uint(__uint_as_float(sr[k0 >> 5][(k0 + 1) & 31]) * __uint_as_float(f.y));
+                    sr[k0 >> 5][(k0 + 2) & 31] = __float_as_uint(__uint_as_float(sr[k0 >> 5][(k0 + 2) & 31]) * __uint_as_float(f.z));
+                    sr[k0 >> 5][(k0 + 3) & 31] = __float_as_uint(__uint_as_float(sr[k0 >> 5][(k0 + 3) & 31]) * __uint_as_float(f.w));
+                }
+            }
             if (qtr == 0) PROBE(x, i, 2);
             // causal / context / unmapped-page mask (only tiles that need one) + tile maximum
             const int kp0 = i * KT;
@@ -466,12 +623,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             uint32_t w[32];
             float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int k0 = 2 * k;
-                const float p0 = fast_exp2(__uint_as_float(sr[k0 >> 5][k0 & 31]) - m_ref);  // -inf - finite -> 0; a fully
-                const float p1 = fast_exp2(__uint_as_float(sr[(k0 + 1) >> 5][(k0 + 1) & 31]) - m_ref);  // masked row: NaN, below
-                ps4[k & 3] += p0 + p1;
-                w[k] = pack_half2(p0, p1);
+            for (int k = 0; k < 32; k += 2) {
+                float pv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k0 = 2 * k + e;  // -inf - finite -> 0; a fully masked row gives NaN, handled below
+                    pv[e] = fast_exp2(__uint_as_float(sr[k0 >> 5][k0 & 31]) - m_ref);
+                }
+                ps4[(k >> 1) & 3] += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+                if (KV == 1) {  // the V scale of each token folded into its P column (the row sum stays unscaled)
+                    const uint4 f = lds_128(scale_sm + sfs * SCALE_BYTES + KT * 4 + k * 8);
+                    pv[0] *= __uint_as_float(f.x);
+                    pv[1] *= __uint_as_float(f.y);
+                    pv[2] *= __uint_as_float(f.z);
+                    pv[3] *= __uint_as_float(f.w);
+                }
+                w[k] = pack_half2(pv[0], pv[1]);
+                w[k + 1] = pack_half2(pv[2], pv[3]);
             }
             if (qtr == 0) PROBE(x, i, 3);
             const bool dead = m_ref == -INFINITY;  // nothing visible yet (padding rows of the last query tile)
@@ -506,6 +674,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) prefill_tc_kernel(const __grid_co
             tc_fence_before();
             mbar_arrive_cnt(p_full(x, sb));
             if (qtr == 0) PROBE(x, i, 6);
+            if (++sfs == ST) {
+                sfs = 0;
+                sfph ^= 1u;
+            }
         }
         if (nt > 0) {
             if (nt > 1) ensure_pv(nt - 2);
@@ -553,35 +725,43 @@ extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe(long lo
 #endif
 
 // Launch helper used by prefill.cu (returns PA_ERR_UNSUPPORTED when the tensor maps cannot be built).
-int pa_prefill_tc_launch(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
-                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles, int total_pages,
-                         const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq, int tile_size,
-                         float temperature, cudaStream_t st) {
+int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                         const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
+                         int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
+                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st) {
     using namespace pa::ptc;
     CUtensorMap tmK, tmV;
     const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
     if (total_tokens >= 0x7fffffffull) return PA_ERR_UNSUPPORTED;
-    if (!make_pool_map(&tmK, d_k_pool, total_tokens) || !make_pool_map(&tmV, d_v_pool, total_tokens))
-        return PA_ERR_UNSUPPORTED;
+    if (kv == 0) {
+        if (!make_pool_map(&tmK, d_k_pool, total_tokens) || !make_pool_map(&tmV, d_v_pool, total_tokens))
+            return PA_ERR_UNSUPPORTED;
+    } else {  // the int8 variant stages raw units with plain bulk copies
+        memset(&tmK, 0, sizeof(tmK));
+        memset(&tmV, 0, sizeof(tmV));
+    }
     const int upt = tile_size >> 4;
     if (tile_size % 16 != 0 || (upt & (upt - 1)) != 0) return PA_ERR_UNSUPPORTED;  // pages of 16 << k tokens only
     int upt_shift = 0;
     while ((1 << upt_shift) < upt) ++upt_shift;
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
-           1.4426950408889634f / temperature, upt_shift, (int)total_tokens};
+           1.4426950408889634f / temperature, static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool),
+           d_k_scales, d_v_scales, upt_shift, (int)total_tokens};
     const int nqt = (Tq + NQ * QT - 1) / (NQ * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
-    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + NBAR * 8 + 16 + 1024;
-    static bool attr_done[64] = {};
+    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + (kv ? RS * RAW_STAGE + ST * SCALE_BYTES : 0) +
+                        (NBAR + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
+    static bool attr_done[64][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr_done[dev & 63]) {
-        cudaError_t e0 = cudaFuncSetAttribute(prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = kv == 0 ? prefill_tc_kernel<0> : prefill_tc_kernel<1>;
+    if (!attr_done[dev & 63][kv]) {
+        cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e0 != cudaSuccess) return (int)e0;
-        attr_done[dev & 63] = true;
+        attr_done[dev & 63][kv] = true;
     }
-    prefill_tc_kernel<<<(unsigned)ctas, NTHREADS, smem, st>>>(tmK, tmV, a);
+    kern<<<(unsigned)ctas, kv == 0 ? NTHREADS : NTHREADS_I8, smem, st>>>(tmK, tmV, a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? PA_OK : (int)e;
 }

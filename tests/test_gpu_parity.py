@@ -365,8 +365,12 @@ def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=Fal
                     pg = int(case["table"][b, h, tile])
                     if 0 <= pg < case["total_pages"]:
                         r0 = end - tile * ts if tile == end // ts else 0
-                        kvc.key_buffer_[pg, r0:] = float("nan")
-                        kvc.value_buffer_[pg, r0:] = float("nan")
+                        if kv == "f16":
+                            kvc.key_buffer_[pg, r0:] = float("nan")
+                            kvc.value_buffer_[pg, r0:] = float("nan")
+                        else:   # int8 bytes are always finite; the per-token scales are what can be garbage
+                            kvc.k_scales_[pg, r0:] = float("nan")
+                            kvc.v_scales_[pg, r0:] = 0.0
     out = torch.full((B, H, Tq, D), float("nan"), device="cuda")
     ld.paged_prefill(torch.from_numpy(q).cuda(), out, kvc, B, Tq, case["temperature"],
                      ctx_start=torch.from_numpy(start).cuda())
@@ -408,18 +412,21 @@ PREFILL_TC_CASES = [
 
 @pytest.mark.parametrize("ci", range(len(PREFILL_TC_CASES)))
 @pytest.mark.parametrize("tc", ["1", "0"])
-def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, monkeypatch):
-    """Both head_dim-128 fp16 prefill kernels (tcgen05 with two query tiles per CTA, PA_PREFILL_TC=1, and the
-    mma.sync kernel, =0) against the oracle at every query position: tile boundaries, ctx_start offsets,
-    unmapped pages, 32-token pages, NaN-poisoned tail of the last page."""
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, kv, monkeypatch):
+    """Both head_dim-128 prefill kernels (tcgen05 with two query tiles per CTA, PA_PREFILL_TC=1, and the
+    mma.sync kernel, =0), fp16 and int8 pages, against the oracle at every query position: tile boundaries,
+    ctx_start offsets, unmapped pages, 32-token pages, poisoned tail of the last page (NaN K/V for fp16, NaN / zero
+    scales for int8)."""
     cfg = dict(PREFILL_TC_CASES[ci])
     monkeypatch.setenv("PA_PREFILL_TC", tc)
     Tq = cfg.pop("Tq")
     start = np.array(cfg.pop("start"), np.int32)
-    _prefill_case(ld, oracle, "f16", Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
+    _prefill_case(ld, oracle, kv, Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
 
 
-def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch):
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch, kv):
     """Llama-7B head shape, Tq = 2048 (the benchmark's size): the tcgen05 kernel and the mma.sync kernel are
     independent implementations; their outputs must agree within the attention tolerance, rows of a constant-V
     cache must reproduce the constant (softmax weights sum to 1), and the last row must equal the decode kernel."""
@@ -428,10 +435,16 @@ def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch):
     g = torch.Generator(device=dev).manual_seed(5)
     nt = Tq // TILE
     P = B * H * nt
-    kvc = ld.KVTileCache("f16", device=dev)
-    k = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
-    v = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
-    kvc.adopt_buffers(k, v)
+    kvc = ld.KVTileCache(kv, device=dev)
+    if kv == "f16":
+        k = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        v = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        kvc.adopt_buffers(k, v)
+    else:
+        k = torch.randint(-127, 128, (P, TILE, D), generator=g, device=dev, dtype=torch.int8)
+        v = torch.randint(-127, 128, (P, TILE, D), generator=g, device=dev, dtype=torch.int8)
+        vs = torch.rand((P, TILE), generator=g, device=dev) * 20 + 30
+        kvc.adopt_buffers(k, v, torch.rand((P, TILE), generator=g, device=dev) * 20 + 30, vs)
     kvc.configure_table(B, H, nt)
     kvc.page_table_.load_host_table(torch.randperm(P, generator=g, device=dev).to(torch.int32).cpu().numpy().reshape(B, H, nt))
     q = torch.randn((B, H, Tq, D), generator=g, device=dev)
@@ -446,11 +459,15 @@ def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch):
     # last query == one decode row over the full context
     qd = q[:, :, -1, :].contiguous()
     od = torch.empty_like(qd)
-    ld.AttentionCUDA.forward(qd, od, B, H, D, Tq, None, kvc, None, False, True, True, float(np.sqrt(D)))
+    ld.AttentionCUDA.forward(qd, od, B, H, D, Tq, None, kvc, None, False, kv == "f16", True, float(np.sqrt(D)))
     torch.cuda.synchronize()
     np.testing.assert_allclose(outs["1"][:, :, -1, :], od.cpu().numpy(), rtol=RTOL, atol=ATOL)
     # constant V: every output element equals the constant (up to the 1e-6 epsilon of the normaliser)
-    v.fill_(0.75)
+    if kv == "f16":
+        v.fill_(0.75)
+    else:
+        v.fill_(96)
+        vs.fill_(128.0)   # x = q / scale = 0.75
     monkeypatch.setenv("PA_PREFILL_TC", "1")
     o = torch.empty_like(q)
     ld.paged_prefill(q, o, kvc, B, Tq, float(np.sqrt(D)))
