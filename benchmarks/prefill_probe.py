@@ -65,6 +65,7 @@ def main():
     fn.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     assert fn(buf) == 0
     a = np.array(buf[:]).reshape(3, 64, 8)
+    cta_life(_cabi)
     if "--raw" in sys.argv:  # stamps of 8 consecutive tiles relative to the first
         t0 = a[:, 20, :].min()
         for role, name in ((0, "softmax A"), (1, "softmax B"), (2, "umma")):
@@ -76,6 +77,16 @@ def main():
         seg = np.median(np.diff(r[:, :nseg + 1], axis=1), axis=0)
         print(f"{name}: period median {np.median(per):.0f} cycles (min {per.min()}, max {per.max()}); "
               f"segment medians {[int(v) for v in seg]}")
+
+
+def cta_life(_cabi):
+    buf = (ctypes.c_longlong * 8)()
+    fn = _cabi.lib().pa_debug_ptc_probe_cta
+    fn.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+    assert fn(buf) == 0
+    v = np.array(buf[:])
+    names = ["setup (barriers, TMEM alloc, sync)", "Q staged", "first S seen", "KV loop", "last P.V seen", "O stored", "exit sync"]
+    print("CTA 5 life (cycles):", {n: int(d) for n, d in zip(names, np.diff(v))}, "total", int(v[7] - v[0]))
 
 
 if __name__ == "__main__":

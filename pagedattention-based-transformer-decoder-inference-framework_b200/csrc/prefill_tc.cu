@@ -151,8 +151,16 @@ __device__ long long g_probe[3 * 64 * 8];
         if (blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (it) >= 16 && (it) < 80)                  \
             g_probe[((role) * 64 + (it) - 16) * 8 + (k)] = clock64();                               \
     } while (0)
+// life of CTA 5 seen from warp 0: entry | setup done | Q staged | first S seen | KV loop done | last P.V seen |
+// O stored | exit
+__device__ long long g_probe_cta[8];
+#define PROBE_CTA(k)                                                                                \
+    do {                                                                                            \
+        if (blockIdx.x == 5 && threadIdx.x == 0) g_probe_cta[k] = clock64();                        \
+    } while (0)
 #else
 #define PROBE(role, it, k) do { } while (0)
+#define PROBE_CTA(k) do { } while (0)
 #endif
 
 template <int KV>
@@ -160,6 +168,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    PROBE_CTA(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
     const uint32_t kv_sm = q_sm + NQ * Q_BYTES;
@@ -211,6 +220,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PROBE_CTA(1);
 
     constexpr int QC = NQ * QT;  // queries per CTA
     const int nqt = (a.Tq + QC - 1) / QC;
@@ -419,6 +429,26 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
             }
             __syncwarp();
         };
+        // Both query tiles at once, k-steps interleaved (A0 B0 A1 B1 ...): consecutive MMAs accumulate into
+        // different TMEM tiles and share the K operand descriptor.  Measured gain is small (16 MMAs: 1202 -> 1107
+        // cycles, clock64 probes): these N = 64 instructions cost ~70 cycles each whatever their order.
+        auto issue_S2 = [&](int i, int stage) {
+            if (elect_one()) {
+                const uint32_t st = kv_sm + stage * STAGE;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) {
+                        const uint64_t da = make_desc(q_sm + x * Q_BYTES + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
+                        umma_f16(tmem_base + x * 2 * KT + (i & 1) * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(s_full(0, i & 1));
+                umma_commit(s_full(1, i & 1));
+            }
+            __syncwarp();
+        };
         if (n_tiles > 0) {
             mbar_wait_wd(kv_full(0), 0);
 #pragma unroll
@@ -440,9 +470,13 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
                 mbar_wait_wd(kv_full(s_next), ph_next);
                 tc_fence_after();
+                if (i + 1 < nts[0] && i + 1 < nts[1]) {
+                    issue_S2(i + 1, s_next);
+                } else {
 #pragma unroll
-                for (int x = 0; x < NQ; ++x)
-                    if (i + 1 < nts[x]) issue_S(x, i + 1, s_next);
+                    for (int x = 0; x < NQ; ++x)
+                        if (i + 1 < nts[x]) issue_S(x, i + 1, s_next);
+                }
             }
             PROBE(2, i, 1);
             const uint32_t st = kv_sm + s * STAGE;
@@ -531,6 +565,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
             }
             fence_proxy_async();
             mbar_arrive_cnt(q_ready(x));
+            PROBE_CTA(2);
         }
         float m_ref = -INFINITY, l_run = 0.f;  // reference maximum of this row (see the header), running sum
         const uint32_t s_addr = tmem_base + lane_base + x * 2 * KT;
@@ -570,6 +605,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
             mbar_wait_wd(s_full(x, sb), (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             if (qtr == 0) PROBE(x, i, 1);
+            if (i == 0) PROBE_CTA(3);
             uint32_t sr[2][32];
             tmem_ld32(s_addr + sb * KT, sr[0]);
             tmem_ld32(s_addr + sb * KT + 32, sr[1]);
@@ -679,9 +715,11 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 sfph ^= 1u;
             }
         }
+        PROBE_CTA(4);
         if (nt > 0) {
             if (nt > 1) ensure_pv(nt - 2);
             ensure_pv(nt - 1);
+            PROBE_CTA(5);
             tc_fence_after();
             const float inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
             float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
@@ -703,10 +741,12 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
             float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + t) * D;
             for (int j = 0; j < D; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        PROBE_CTA(6);
         tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();
+    PROBE_CTA(7);
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -721,6 +761,9 @@ using namespace pa;
 #ifdef PA_PTC_PROBE
 extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, pa::ptc::g_probe, sizeof(long long) * 3 * 64 * 8);
+}
+extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe_cta(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, pa::ptc::g_probe_cta, sizeof(long long) * 8);
 }
 #endif
 
