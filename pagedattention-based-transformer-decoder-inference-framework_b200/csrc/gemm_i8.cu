@@ -476,16 +476,20 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
+// OCC = 2 (used when the grid has more CTA pairs than one wave): two CTAs per SM with a 3-stage ring each (same
+// bytes in flight per SM, 2 x 256 TMEM columns), so the epilogue, set-up and pipeline fill of one tile run under
+// the main loop of the other CTA's tile.
+template <int EPI, int OCC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, OCC)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int NST = OCC == 2 ? 3 : STAGES2;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar0 = base + STAGES2 * STAGE2_BYTES;  // full[S], empty[S], tmem_full
-    const uint32_t tmem_slot = bar0 + (2 * STAGES2 + 1) * 8;
+    const uint32_t bar0 = base + NST * STAGE2_BYTES;  // full[S], empty[S], tmem_full
+    const uint32_t tmem_slot = bar0 + (2 * NST + 1) * 8;
     auto full_bar = [&](int s) { return bar0 + s * 8; };
-    auto empty_bar = [&](int s) { return bar0 + (STAGES2 + s) * 8; };
-    const uint32_t tmem_full_bar = bar0 + 2 * STAGES2 * 8;
+    auto empty_bar = [&](int s) { return bar0 + (NST + s) * 8; };
+    const uint32_t tmem_full_bar = bar0 + 2 * NST * 8;
 
 #ifdef PA_GEMM_PROBE
     const long long t_entry = clock64();
@@ -503,7 +507,7 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int nkb = kb1 - kb0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES2; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(full_bar(s), 2);   // one arrive.expect_tx from each CTA's producer (leader's copy is used)
             mbar_init(empty_bar(s), 1);  // the leader's commit, multicast to both CTAs
         }
@@ -528,11 +532,11 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         if (elect_one()) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES2;
+                const int s = i % NST;
 #ifdef PA_GEMM_PROBE
                 const long long tw0 = clock64();
 #endif
-                mbar_wait(empty_bar(s), ((i / STAGES2) & 1) ^ 1);
+                mbar_wait(empty_bar(s), ((i / NST) & 1) ^ 1);
 #ifdef PA_GEMM_PROBE
                 pw += clock64() - tw0;
 #endif
@@ -551,11 +555,11 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         if (crank == 0 && elect_one()) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES2;
+                const int s = i % NST;
 #ifdef PA_GEMM_PROBE
                 const long long tw0 = clock64();
 #endif
-                mbar_wait(full_bar(s), (i / STAGES2) & 1);
+                mbar_wait(full_bar(s), (i / NST) & 1);
 #ifdef PA_GEMM_PROBE
                 mw += clock64() - tw0;
 #endif
@@ -876,15 +880,19 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     cudaGetDevice(&dev);
     cudaError_t e;
     if (two_cta) {
-        const size_t smem2 = (size_t)STAGES2 * STAGE2_BYTES + 128 + 8 * 128 * sizeof(float) + 1024;  // ring, barriers, bias, align
-        static const KernelFn kernels2[4] = {gemm_i8_2cta_kernel<0>, gemm_i8_2cta_kernel<1>, gemm_i8_2cta_kernel<2>,
-                                             gemm_i8_2cta_kernel<3>};
-        KernelFn kern = kernels2[epi];
-        static bool attr_set2[64][4] = {};
-        if (!attr_set2[dev & 63][epi]) {
+        // more CTA pairs than one wave (148 SMs = 74 pairs): two CTAs per SM, see the kernel's header
+        const int64_t pairs = (int64_t)n_slabs * m_chunks * ksplit * BATCH;
+        const int occ2 = (pairs > di.sm_count / 2 && !(getenv("PA_GEMM_OCC2") && atoi(getenv("PA_GEMM_OCC2")) == 0)) ? 1 : 0;
+        const size_t smem2 = (size_t)(occ2 ? 3 : STAGES2) * STAGE2_BYTES + 128 + 8 * 128 * sizeof(float) + 1024;  // ring, barriers, bias, align
+        static const KernelFn kernels2[2][4] = {
+            {gemm_i8_2cta_kernel<0, 1>, gemm_i8_2cta_kernel<1, 1>, gemm_i8_2cta_kernel<2, 1>, gemm_i8_2cta_kernel<3, 1>},
+            {gemm_i8_2cta_kernel<0, 2>, gemm_i8_2cta_kernel<1, 2>, gemm_i8_2cta_kernel<2, 2>, gemm_i8_2cta_kernel<3, 2>}};
+        KernelFn kern = kernels2[occ2][epi];
+        static bool attr_set2[64][2][4] = {};
+        if (!attr_set2[dev & 63][occ2][epi]) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
-            attr_set2[dev & 63][epi] = true;
+            attr_set2[dev & 63][occ2][epi] = true;
         }
         // cluster dims (2,1,1) are compiled into the kernel (__cluster_dims__)
         kern<<<dim3((unsigned)(2 * n_slabs), (unsigned)(m_chunks * ksplit), (unsigned)BATCH), NTHREADS2, smem2, st>>>(

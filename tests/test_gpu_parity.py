@@ -752,6 +752,8 @@ GEMM_SHAPES = [
     (1, 300, 256, 512),    # M > 256: two M chunks
     (1, 64, 128, 8192),    # one slab -> split-K path
     (3, 17, 16, 16),       # minimum N, K
+    (1, 640, 8192, 512),   # 96 CTA pairs > one wave: the two-CTAs-per-SM variant (3-stage ring), ragged M chunk
+    (2, 1030, 2048, 384),  # the same variant, batched, 5 M chunks (last one 6 rows), K tail inside a block
 ]
 
 
