@@ -471,16 +471,31 @@ __device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint64_t a_desc, u
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// cta_group::2 load delivered to every CTA of `mask` at the same offset; each copy's bytes complete on the full
+// barrier of the destination's PAIR LEADER (the barrier address names the even CTA of the issuer's pair).
+__device__ __forceinline__ void tma_load_3d_2cta_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                    uint32_t bar_cluster_addr, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
 }
 
 // OCC = 2 (used when the grid has more CTA pairs than one wave): two CTAs per SM with a 3-stage ring each (same
 // bytes in flight per SM, 2 x 256 TMEM columns), so the epilogue, set-up and pipeline fill of one tile run under
 // the main loop of the other CTA's tile.
-template <int EPI, int OCC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, OCC)
+// CLP = 2: a cluster of FOUR CTAs = two pairs on adjacent column slabs of the same rows.  Both pairs need the
+// same A tile, so every CTA fetches 64 of its 128 A rows and multicasts them to its counterpart in the other
+// pair: A crosses the L2 -> SM fabric once per cluster instead of once per pair (at M = 256 the whole GEMM is
+// bound by that fabric, profiles/r01_gemm_notes.md).  A ring slot is then reusable only when BOTH pairs have
+// consumed it (empty barrier count 2, each leader's commit multicast to all four CTAs).
+template <int EPI, int OCC, int CLP>
+__global__ void __launch_bounds__(NTHREADS2, OCC)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int NST = OCC == 2 ? 3 : STAGES2;
@@ -496,7 +511,12 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool probe_cta = blockIdx.x == 10 && blockIdx.y == 0 && g.probe;
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();
+    const uint32_t cluster_rank = cluster_ctarank();
+    const uint32_t crank = cluster_rank & 1u;   // rank inside the CTA pair (0 = leader)
+    const uint32_t cpair = cluster_rank >> 1;   // pair inside the cluster (CLP = 2)
+    const uint32_t lead_rank = cluster_rank & ~1u;
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * cpair));
+    const uint16_t all_mask = (uint16_t)((1u << (2 * CLP)) - 1u);
     const int n0 = (blockIdx.x >> 1) * BN2;
     const int m_chunk = blockIdx.y / g.ksplit, split = blockIdx.y % g.ksplit;
     const int m0 = m_chunk * 2 * BM;
@@ -509,7 +529,7 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(full_bar(s), 2);   // one arrive.expect_tx from each CTA's producer (leader's copy is used)
-            mbar_init(empty_bar(s), 1);  // the leader's commit, multicast to both CTAs
+            mbar_init(empty_bar(s), CLP);  // each pair leader's commit, multicast to every CTA of the cluster
         }
         mbar_init(tmem_full_bar, 1);
         mbar_fence_init();
@@ -541,11 +561,16 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 pw += clock64() - tw0;
 #endif
                 const uint32_t st = base + s * STAGE2_BYTES;
-                const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                const uint32_t lead_full = mapa_shared(full_bar(s), lead_rank);
                 if (crank == 0) mbar_arrive_expect_tx(full_bar(s), STAGE2_BYTES);
                 else mbar_remote_arrive_expect_tx(lead_full, STAGE2_BYTES);
                 const int k0 = (kb0 + i) * BK;
-                tma_load_3d_2cta(st, &tmA, k0, m0 + (int)crank * BM, batch, lead_full);
+                if (CLP == 1) {
+                    tma_load_3d_2cta(st, &tmA, k0, m0 + (int)crank * BM, batch, lead_full);
+                } else {  // tmA's box holds 64 rows: this CTA's share of the A half both pairs need
+                    tma_load_3d_2cta_mc(st + cpair * (TILE_BYTES / 2), &tmA, k0, m0 + (int)crank * BM + (int)cpair * (BM / 2),
+                                        batch, lead_full, (uint16_t)((1u << crank) | (1u << (2 + crank))));
+                }
                 tma_load_3d_2cta(st + TILE_BYTES, &tmB, n0 + (int)crank * BN, k0, batch, lead_full);
             }
 #ifdef PA_GEMM_PROBE
@@ -571,9 +596,9 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t db = make_desc(st + TILE_BYTES + ks * UK * BK, TILE_BYTES, 1024);
                     umma_i8_2cta(tmem_base, da, db, kIdesc2, (i > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit_2cta(empty_bar(s));
+                umma_commit_2cta(empty_bar(s), all_mask);
             }
-            umma_commit_2cta(tmem_full_bar);
+            umma_commit_2cta(tmem_full_bar, pair_mask);
 #ifdef PA_GEMM_PROBE
             if (probe_cta) { g.probe[1] = mw; g.probe[3] = clock64() - t_setup; }
 #endif
@@ -832,7 +857,8 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         a_rows_box = m_tiles0 * BM / CLs;
     }
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, two_cta ? BM : a_rows_box))
+    const bool mc_pairs = two_cta && n_slabs % 2 == 0 && !(getenv("PA_GEMM_MC") && atoi(getenv("PA_GEMM_MC")) == 0);
+    if (!make_map(&tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, two_cta ? (mc_pairs ? BM / 2 : BM) : a_rows_box))
         return PA_ERR_UNSUPPORTED;
     if (!make_map(&tmB, d_B, (uint64_t)N, (uint64_t)K, (uint64_t)BATCH, BK)) return PA_ERR_UNSUPPORTED;
 
@@ -884,19 +910,34 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         const int64_t pairs = (int64_t)n_slabs * m_chunks * ksplit * BATCH;
         const int occ2 = (pairs > di.sm_count / 2 && !(getenv("PA_GEMM_OCC2") && atoi(getenv("PA_GEMM_OCC2")) == 0)) ? 1 : 0;
         const size_t smem2 = (size_t)(occ2 ? 3 : STAGES2) * STAGE2_BYTES + 128 + 8 * 128 * sizeof(float) + 1024;  // ring, barriers, bias, align
-        static const KernelFn kernels2[2][4] = {
-            {gemm_i8_2cta_kernel<0, 1>, gemm_i8_2cta_kernel<1, 1>, gemm_i8_2cta_kernel<2, 1>, gemm_i8_2cta_kernel<3, 1>},
-            {gemm_i8_2cta_kernel<0, 2>, gemm_i8_2cta_kernel<1, 2>, gemm_i8_2cta_kernel<2, 2>, gemm_i8_2cta_kernel<3, 2>}};
-        KernelFn kern = kernels2[occ2][epi];
-        static bool attr_set2[64][2][4] = {};
-        if (!attr_set2[dev & 63][occ2][epi]) {
+        // cluster of two pairs sharing A by multicast when the slabs pair up (PA_GEMM_MC=0 turns it off)
+        const int clp2 = mc_pairs ? 1 : 0;
+        static const KernelFn kernels2[2][2][4] = {
+            {{gemm_i8_2cta_kernel<0, 1, 1>, gemm_i8_2cta_kernel<1, 1, 1>, gemm_i8_2cta_kernel<2, 1, 1>, gemm_i8_2cta_kernel<3, 1, 1>},
+             {gemm_i8_2cta_kernel<0, 2, 1>, gemm_i8_2cta_kernel<1, 2, 1>, gemm_i8_2cta_kernel<2, 2, 1>, gemm_i8_2cta_kernel<3, 2, 1>}},
+            {{gemm_i8_2cta_kernel<0, 1, 2>, gemm_i8_2cta_kernel<1, 1, 2>, gemm_i8_2cta_kernel<2, 1, 2>, gemm_i8_2cta_kernel<3, 1, 2>},
+             {gemm_i8_2cta_kernel<0, 2, 2>, gemm_i8_2cta_kernel<1, 2, 2>, gemm_i8_2cta_kernel<2, 2, 2>, gemm_i8_2cta_kernel<3, 2, 2>}}};
+        KernelFn kern = kernels2[clp2][occ2][epi];
+        static bool attr_set2[64][2][2][4] = {};
+        if (!attr_set2[dev & 63][clp2][occ2][epi]) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
-            attr_set2[dev & 63][occ2][epi] = true;
+            attr_set2[dev & 63][clp2][occ2][epi] = true;
         }
-        // cluster dims (2,1,1) are compiled into the kernel (__cluster_dims__)
-        kern<<<dim3((unsigned)(2 * n_slabs), (unsigned)(m_chunks * ksplit), (unsigned)BATCH), NTHREADS2, smem2, st>>>(
-            tmA, tmB, g);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * n_slabs), (unsigned)(m_chunks * ksplit), (unsigned)BATCH);
+        cfg.blockDim = dim3(NTHREADS2);
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = clp2 ? 4u : 2u;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
+        if (e != cudaSuccess) return (int)e;
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     } else {
