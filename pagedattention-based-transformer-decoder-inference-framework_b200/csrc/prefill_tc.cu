@@ -29,26 +29,29 @@ namespace pa {
 namespace ptc {
 
 constexpr int QT = 128;               // queries per query tile (= TMEM lanes)
-constexpr int NQ = 2;                 // query tiles per CTA
 constexpr int KT = 64;                // tokens per KV tile
 constexpr int D = 128;
-constexpr int ST = 3;                 // KV ring stages
 constexpr int Q_BYTES = 2 * QT * 128; // per query tile: two k-blocks of [128 rows x 128 B]
 constexpr int K_BYTES = 2 * KT * 128; // two k-blocks of [64 rows x 128 B]
 constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
 constexpr int STAGE = K_BYTES + V_BYTES;
-constexpr int TMEM_COLS = 512;        // tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)
-constexpr int NTHREADS = 320;         // warps: 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 TMA producer
+// NQ = query tiles per CTA.  NQ = 2 (default): warps 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 producer, 3-stage ring,
+// all 512 TMEM columns (tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)), one CTA per SM.
+// NQ = 1 (fp16 pages only): warps 0-3 softmax, 4 UMMA, 5 producer, 2-stage ring, 256 TMEM columns, TWO CTAs per
+// SM -- K/V bytes are staged once per 128 queries instead of 256, but the prologue / epilogue of one CTA runs
+// under the main loop of the other.
+__host__ __device__ constexpr int stages_for(int nq) { return nq == 2 ? 3 : 2; }
+// barriers: kv_full/kv_empty[ST]; per query tile s_full[2], p_full[2], o_full[2], q_ready
+__host__ __device__ constexpr int nbar_for(int nq) { return 2 * stages_for(nq) + 7 * nq; }
+__host__ __device__ constexpr int threads_for(int kv, int nq) { return (4 * nq + 2 + 2 * kv) * 32; }
 // int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
-// into a raw ring, two converter warps (10, 11) rewrite them as the same swizzled fp16 stage the fp16 path gets
+// into a raw ring, two converter warps (10, 11; 12 warps still get 168 registers) rewrite them as the same swizzled fp16 stage the fp16 path gets
 // from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
 // the K scale to the score columns and fold the V scale into P (int8_quant.cpp:46-57: x = q / scale).
-constexpr int NTHREADS_I8 = 384;      // 12 warps still get 168 registers per thread
 constexpr int RS = 3;                 // raw ring stages (one 64-token tile each)
 constexpr int RAW_UNIT = 2048 + 2048 + 64 + 64;
 constexpr int RAW_STAGE = 4 * RAW_UNIT;
 constexpr int SCALE_BYTES = 2 * KT * 4;  // per fp16 stage: 1/k_scale[64], 1/v_scale[64]
-constexpr int NBAR = 2 * ST + 7 * NQ; // kv_full/kv_empty[ST]; per tile: s_full[2], p_full[2], o_full[2], q_ready
 
 struct Args {
     const float* q;
@@ -163,11 +166,13 @@ __device__ long long g_probe_cta[8];
 #define PROBE_CTA(k) do { } while (0)
 #endif
 
-template <int KV>
-__global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
+template <int KV, int NQ>
+__global__ void __launch_bounds__(threads_for(KV, NQ), NQ == 1 ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int ST = stages_for(NQ), NBAR = nbar_for(NQ), TMEM_COLS = NQ * 256;
+    constexpr int W_MMA = 4 * NQ, W_PROD = 4 * NQ + 1, W_CONV = 4 * NQ + 2;  // warp roles after the softmax groups
     PROBE_CTA(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
     }
-    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -241,14 +246,14 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
         kmaxs[x] = q0 < a.Tq ? max(0, min(cap, start + q_last + 1)) : 0;
         nts[x] = (kmaxs[x] + KT - 1) / KT;
     }
-    const int kmax_c = max(kmaxs[0], kmaxs[1]);  // kmax is monotone in x, an absent tile has 0
-    const int n_tiles = max(nts[0], nts[1]);
+    const int kmax_c = max(kmaxs[0], kmaxs[NQ - 1]);  // kmax is monotone in x, an absent tile has 0
+    const int n_tiles = max(nts[0], nts[NQ - 1]);
     const int upt_mask = (1 << a.upt_shift) - 1;  // 16-token units per page - 1 (page sizes are 16 << k)
     const int beam = a.beam_ids ? a.beam_ids[b] : b;
     const int32_t* trow = ((unsigned)beam < (unsigned)a.num_beams)
                               ? a.table + ((int64_t)beam * a.H + h) * a.num_tiles : nullptr;
 
-    if (KV == 1 && warp == 9) {
+    if (KV == 1 && warp == W_PROD) {
         // ------------------------------------------------------------ producer, int8 pages: raw units by bulk copy
         if (elect_one()) {
             int* meta = reinterpret_cast<int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
@@ -285,13 +290,13 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 }
             }
         }
-    } else if (KV == 1 && warp >= 10) {
+    } else if (KV == 1 && warp >= W_CONV) {
         // ------------------------------------------------------------ converters: raw int8 units -> fp16 stage
         // warp cw rewrites units 2 cw and 2 cw + 1 of every tile; lane = (token row, 64-dim half).  K and V have
         // the same shared-memory image ([64-dim half][token row of 128 B], SWIZZLE_128B); only the UMMA
         // descriptors read them differently.
         const int* meta = reinterpret_cast<const int*>(smem_raw + (meta_sm - smem_u32(smem_raw)));
-        const int cw = warp - 10;
+        const int cw = warp - W_CONV;
         const int tr = lane >> 1, hf = lane & 1;
         const __half2 off = __floats2half2_rn(1152.f, 1152.f);
         int rs = 0, fs = 0;
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 fph ^= 1u;
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == W_PROD) {
         // ------------------------------------------------------------ TMA producer
         // ONE elected thread issues the 16 boxes of a tile (unit uu x {K lo, K hi, V lo, V hi}).  Everything
         // under elect_one() stays in uniform registers, so the 16 UTMALDG go out back to back; page ids are
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------ UMMA issuer
         constexpr uint32_t kIdescS = idesc_f16(QT, KT, 0, 0);  // Q K-major, K K-major
         constexpr uint32_t kIdescO = idesc_f16(QT, D, 0, 1);   // P K-major, V MN-major
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                     }
                 }
                 umma_commit(s_full(0, i & 1));
-                umma_commit(s_full(1, i & 1));
+                umma_commit(s_full(NQ - 1, i & 1));
             }
             __syncwarp();
         };
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
                 mbar_wait_wd(kv_full(s_next), ph_next);
                 tc_fence_after();
-                if (i + 1 < nts[0] && i + 1 < nts[1]) {
+                if (NQ == 2 && i + 1 < nts[0] && i + 1 < nts[NQ - 1]) {
                     issue_S2(i + 1, s_next);
                 } else {
 #pragma unroll
@@ -495,7 +500,9 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
             }
             // O_X += P_X(i) . V(i), in the order the two groups deliver P (the softmax threads finished any row
             // rescale before arriving on p_full)
-            uint32_t pend = (i < nts[0] ? 1u : 0u) | (i < nts[1] ? 2u : 0u);
+            uint32_t pend = 0;
+#pragma unroll
+            for (int x = 0; x < NQ; ++x) pend |= (i < nts[x] ? 1u : 0u) << x;
             uint32_t idle = 0;
             while (pend) {
                 if (++idle > (1u << 26)) __trap();
@@ -747,7 +754,7 @@ __global__ void __launch_bounds__(KV ? NTHREADS_I8 : NTHREADS, 1) prefill_tc_ker
     tc_fence_before();
     __syncthreads();
     PROBE_CTA(7);
-    if (warp == 8) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -790,21 +797,25 @@ int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
            1.4426950408889634f / temperature, static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool),
            d_k_scales, d_v_scales, upt_shift, (int)total_tokens};
-    const int nqt = (Tq + NQ * QT - 1) / (NQ * QT);
+    // fp16 pages: NQ = 1 (two CTAs per SM) or NQ = 2 (one CTA per SM, K/V shared by 256 queries)
+    int nq = 2;
+    if (kv == 0 && getenv("PA_PREFILL_NQ")) nq = atoi(getenv("PA_PREFILL_NQ")) == 1 ? 1 : 2;
+    const int nqt = (Tq + nq * QT - 1) / (nq * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
-    const size_t smem = (size_t)NQ * Q_BYTES + ST * STAGE + (kv ? RS * RAW_STAGE + ST * SCALE_BYTES : 0) +
-                        (NBAR + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
-    static bool attr_done[64][2] = {};
+    const size_t smem = (size_t)nq * Q_BYTES + stages_for(nq) * STAGE + (kv ? RS * RAW_STAGE + stages_for(nq) * SCALE_BYTES : 0) +
+                        (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
+    static bool attr_done[64][3] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    auto kern = kv == 0 ? prefill_tc_kernel<0> : prefill_tc_kernel<1>;
-    if (!attr_done[dev & 63][kv]) {
+    const int ki = kv == 1 ? 2 : (nq == 1 ? 1 : 0);
+    auto kern = ki == 2 ? prefill_tc_kernel<1, 2> : (ki == 1 ? prefill_tc_kernel<0, 1> : prefill_tc_kernel<0, 2>);
+    if (!attr_done[dev & 63][ki]) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e0 != cudaSuccess) return (int)e0;
-        attr_done[dev & 63][kv] = true;
+        attr_done[dev & 63][ki] = true;
     }
-    kern<<<(unsigned)ctas, kv == 0 ? NTHREADS : NTHREADS_I8, smem, st>>>(tmK, tmV, a);
+    kern<<<(unsigned)ctas, threads_for(kv, nq), smem, st>>>(tmK, tmV, a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? PA_OK : (int)e;
 }
