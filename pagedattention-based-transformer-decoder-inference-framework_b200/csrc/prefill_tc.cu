@@ -65,6 +65,7 @@ struct Args {
     const int8_t* v8;
     const float* k_scales;
     const float* v_scales;
+    int stagger;       // UMMA issue order, see the UMMA warp
     int upt_shift;     // log2(16-token units per page)
     int total_tokens;  // rows of the pool tensor map: a box at this row is all zeros (out-of-bounds fill)
 };
@@ -475,7 +476,9 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), NQ == 1 ? 2 : 1) prefill_
                 const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
                 mbar_wait_wd(kv_full(s_next), ph_next);
                 tc_fence_after();
-                if (NQ == 2 && i + 1 < nts[0] && i + 1 < nts[NQ - 1]) {
+                if (NQ == 2 && a.stagger) {
+                    if (i + 1 < nts[0]) issue_S(0, i + 1, s_next);  // S_B(i+1) follows P.V_A(i), below
+                } else if (NQ == 2 && i + 1 < nts[0] && i + 1 < nts[NQ - 1]) {
                     issue_S2(i + 1, s_next);
                 } else {
 #pragma unroll
@@ -498,34 +501,53 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), NQ == 1 ? 2 : 1) prefill_
                 fence_proxy_async();
                 __syncwarp();
             }
-            // O_X += P_X(i) . V(i), in the order the two groups deliver P (the softmax threads finished any row
-            // rescale before arriving on p_full)
-            uint32_t pend = 0;
-#pragma unroll
-            for (int x = 0; x < NQ; ++x) pend |= (i < nts[x] ? 1u : 0u) << x;
-            uint32_t idle = 0;
-            while (pend) {
-                if (++idle > (1u << 26)) __trap();
-#pragma unroll
-                for (int x = 0; x < NQ; ++x) {
-                    if (!((pend >> x) & 1u)) continue;
-                    if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x, i & 1), (uint32_t)((i >> 1) & 1)))) continue;
-                    pend &= ~(1u << x);
-                    PROBE(2, i, 2 + 2 * x);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const int nvalid = min(KT, kmaxs[x] - i * KT);
-                        const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            // P(i) sits in the first 32 columns of the S buffer it was computed from
-                            const uint32_t ta = tmem_base + x * 2 * KT + (i & 1) * KT + ks * 8;
-                            const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
-                            umma_f16_ts(tmem_base + NQ * 2 * KT + x * D, ta, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
-                        }
-                        umma_commit(o_full(x, i & 1));
+            // O_X += P_X(i) . V(i)   (the softmax threads finished any row rescale before arriving on p_full)
+            auto issue_PV = [&](int x) {
+                PROBE(2, i, 2 + 2 * x);
+                tc_fence_after();
+                if (elect_one()) {
+                    const int nvalid = min(KT, kmaxs[x] - i * KT);
+                    const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        // P(i) sits in the first 32 columns of the S buffer it was computed from
+                        const uint32_t ta = tmem_base + x * 2 * KT + (i & 1) * KT + ks * 8;
+                        const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
+                        umma_f16_ts(tmem_base + NQ * 2 * KT + x * D, ta, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
                     }
-                    __syncwarp();
-                    PROBE(2, i, 3 + 2 * x);
+                    umma_commit(o_full(x, i & 1));
+                }
+                __syncwarp();
+                PROBE(2, i, 3 + 2 * x);
+            };
+            if (NQ == 2 && a.stagger) {
+                // Staggered order: S_A(i+1) | P.V_A(i) | S_B(i+1) | P.V_B(i).  Group B's scores arrive half an
+                // iteration after group A's, so the two groups are in their exponentials (MUFU-bound) at different
+                // times instead of in lock-step, and each has a whole iteration of tensor work between "S ready"
+                // and "P needed".
+                if (i < nts[0]) {
+                    mbar_wait_wd(p_full(0, i & 1), (uint32_t)((i >> 1) & 1));
+                    issue_PV(0);
+                }
+                if (i + 1 < nts[1]) issue_S(1, i + 1, s_next);
+                if (i < nts[1]) {
+                    mbar_wait_wd(p_full(1, i & 1), (uint32_t)((i >> 1) & 1));
+                    issue_PV(1);
+                }
+            } else {
+                // in the order the groups deliver P
+                uint32_t pend = 0;
+#pragma unroll
+                for (int x = 0; x < NQ; ++x) pend |= (i < nts[x] ? 1u : 0u) << x;
+                uint32_t idle = 0;
+                while (pend) {
+                    if (++idle > (1u << 26)) __trap();
+#pragma unroll
+                    for (int x = 0; x < NQ; ++x) {
+                        if (!((pend >> x) & 1u)) continue;
+                        if (!__all_sync(0xffffffffu, mbar_try_wait(p_full(x, i & 1), (uint32_t)((i >> 1) & 1)))) continue;
+                        pend &= ~(1u << x);
+                        issue_PV(x);
+                    }
                 }
             }
             if (elect_one()) umma_commit(kv_empty(s));
@@ -796,7 +818,8 @@ int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k
     while ((1 << upt_shift) < upt) ++upt_shift;
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
            1.4426950408889634f / temperature, static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool),
-           d_k_scales, d_v_scales, upt_shift, (int)total_tokens};
+           d_k_scales, d_v_scales, (getenv("PA_PTC_STAGGER") && atoi(getenv("PA_PTC_STAGGER")) == 0) ? 0 : 1, upt_shift,
+           (int)total_tokens};
     // fp16 pages: NQ = 1 (two CTAs per SM) or NQ = 2 (one CTA per SM, K/V shared by 256 queries)
     int nq = 2;
     if (kv == 0 && getenv("PA_PREFILL_NQ")) nq = atoi(getenv("PA_PREFILL_NQ")) == 1 ? 1 : 2;
