@@ -1,24 +1,26 @@
 // prefill_tc.cu -- flash-attention prefill over the paged cache on the 5th-generation tensor cores
-// (tcgen05.mma kind::f16, accumulators in TMEM), fp16 pages, head_dim 128.  SURVEY 8(f) row 1.
+// (tcgen05.mma kind::f16, accumulators in TMEM), fp16 and int8 pages, head_dim 128.  SURVEY 8(f) row 1.
 //
 // One CTA = 256 consecutive query positions of one (row, head), handled as TWO query tiles of 128 rows
 // (A, B) that share every K/V tile; KV is consumed in tiles of 64 tokens (4 page units of 16 tokens, each
-// located through the page table and staged by TMA tensor copies):
+// located through the page table):
 //   warps 0-3   : softmax group A, warps 4-7: softmax group B.  One thread per query row (= TMEM lane):
-//                 tcgen05.ld its 64 scores, causal mask, online softmax in registers, P written to shared
-//                 memory as the next A operand.  While one group computes exponentials the tensor core
-//                 runs the other group's MMAs, so MUFU and tensor time overlap.
-//   warp 8      : TMEM allocation (all 512 columns) + the single thread that issues the UMMAs:
-//                   S_X[sb] (128 x 64, fp32, TMEM)  = Q_X (smem, fp16) . K^T     8 x (M128 N64  K16)
-//                   O_X     (128 x 128, fp32, TMEM) += P_X (smem, fp16) . V      4 x (M128 N128 K16)
-//   warp 9      : TMA producer, one elected thread issues the 16 boxes of a tile (K tile as the K-major B operand of
-//                 S = Q K^T, V tile as the MN-major B operand of O = P V, 3-stage ring)
+//                 tcgen05.ld its 64 scores, causal / context / unmapped-page mask, online softmax in registers,
+//                 P written back to TMEM (packed fp16 over the first 32 columns of the scores it came from).
+//   warp 8      : TMEM allocation (all 512 columns) + one elected thread that issues the UMMAs:
+//                   S_X[sb] (128 x 64, fp32, TMEM)  = Q_X (smem, fp16) . K^T        8 x (M128 N64  K16)
+//                   O_X     (128 x 128, fp32, TMEM) += P_X (TMEM, fp16) . V (smem)   4 x (M128 N128 K16)
+//                 in the staggered order S_A(i+1) | P.V_A(i) | S_B(i+1) | P.V_B(i).
+//   warp 9      : producer, one elected thread: fp16 pages = 16 TMA tensor boxes per tile (K tile as the K-major B
+//                 operand of S, V tile as the MN-major B operand of P.V, 3-stage ring); int8 pages = bulk copies
+//                 of raw units into a raw ring.
+//   warps 10-11 : (int8 pages) converters: raw units -> the same swizzled fp16 stage, 1/scale per token beside it.
 // O accumulates in TMEM across all KV tiles (accumulate flag), scaled by a per-row REFERENCE maximum that
 // is only raised when the tile maximum exceeds it by more than 8 (log2 units): P stays below 2^8 in fp16,
 // l and O use the same reference so O / l is exact, and the row rescale (tcgen05.ld, multiply, tcgen05.st)
 // happens a few times per row instead of once per tile.  S is double-buffered in TMEM so S(i+1) is computed
-// while the softmax of tile i runs; the exponentials of tile i are computed BEFORE waiting for P.V(i-1), so
-// that MMA runs under them as well.
+// while the softmax of tile i runs; P.V(i-1) is only waited for when a row rescale needs O.
+// Design history, the experiments behind each choice and the rejected variants: profiles/r01_prefill_tc_notes.md.
 #include <cstdlib>
 #include <cstring>
 
