@@ -170,7 +170,7 @@ __device__ long long g_probe_cta[8];
 #endif
 
 template <int KV, int NQ>
-__global__ void __launch_bounds__(threads_for(KV, NQ), NQ == 1 ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -822,19 +822,25 @@ int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k
            1.4426950408889634f / temperature, static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool),
            d_k_scales, d_v_scales, (getenv("PA_PTC_STAGGER") && atoi(getenv("PA_PTC_STAGGER")) == 0) ? 0 : 1, upt_shift,
            (int)total_tokens};
-    // fp16 pages: NQ = 1 (two CTAs per SM) or NQ = 2 (one CTA per SM, K/V shared by 256 queries)
-    int nq = 2;
-    if (kv == 0 && getenv("PA_PREFILL_NQ")) nq = atoi(getenv("PA_PREFILL_NQ")) == 1 ? 1 : 2;
+    // NQ = 2 (256 queries per CTA share every staged K/V byte) unless that leaves SMs without a CTA: small
+    // prompts then take NQ = 1 (twice the CTAs).  PA_PREFILL_NQ forces either.
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int sm_count[64] = {};
+    if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    int nq = ((int64_t)B * num_heads * ((Tq + 2 * QT - 1) / (2 * QT)) < sm_count[dev & 63]) ? 1 : 2;
+    if (getenv("PA_PREFILL_NQ")) nq = atoi(getenv("PA_PREFILL_NQ")) == 1 ? 1 : 2;
     const int nqt = (Tq + nq * QT - 1) / (nq * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
     const size_t smem = (size_t)nq * Q_BYTES + stages_for(nq) * STAGE + (kv ? RS * RAW_STAGE + stages_for(nq) * SCALE_BYTES : 0) +
                         (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
-    static bool attr_done[64][3] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int ki = kv == 1 ? 2 : (nq == 1 ? 1 : 0);
-    auto kern = ki == 2 ? prefill_tc_kernel<1, 2> : (ki == 1 ? prefill_tc_kernel<0, 1> : prefill_tc_kernel<0, 2>);
+    static bool attr_done[64][4] = {};
+    const int ki = kv * 2 + (nq == 1 ? 1 : 0);
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
+    static const KernelFn kernels[4] = {prefill_tc_kernel<0, 2>, prefill_tc_kernel<0, 1>, prefill_tc_kernel<1, 2>,
+                                        prefill_tc_kernel<1, 1>};
+    KernelFn kern = kernels[ki];
     if (!attr_done[dev & 63][ki]) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e0 != cudaSuccess) return (int)e0;

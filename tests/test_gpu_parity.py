@@ -411,15 +411,17 @@ PREFILL_TC_CASES = [
 
 
 @pytest.mark.parametrize("ci", range(len(PREFILL_TC_CASES)))
-@pytest.mark.parametrize("tc", ["1", "0"])
+@pytest.mark.parametrize("tc", ["tc-nq2", "tc-nq1", "mma"])
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, kv, monkeypatch):
-    """Both head_dim-128 prefill kernels (tcgen05 with two query tiles per CTA, PA_PREFILL_TC=1, and the
-    mma.sync kernel, =0), fp16 and int8 pages, against the oracle at every query position: tile boundaries,
+    """Both head_dim-128 prefill kernels (tcgen05 with two or one query tiles per CTA, and the mma.sync kernel,
+    PA_PREFILL_TC=0), fp16 and int8 pages, against the oracle at every query position: tile boundaries,
     ctx_start offsets, unmapped pages, 32-token pages, poisoned tail of the last page (NaN K/V for fp16, NaN / zero
     scales for int8)."""
     cfg = dict(PREFILL_TC_CASES[ci])
-    monkeypatch.setenv("PA_PREFILL_TC", tc)
+    monkeypatch.setenv("PA_PREFILL_TC", "0" if tc == "mma" else "1")
+    if tc != "mma":   # both CTA shapes of the tcgen05 kernel (the launcher would pick one by grid size)
+        monkeypatch.setenv("PA_PREFILL_NQ", tc[-1])
     Tq = cfg.pop("Tq")
     start = np.array(cfg.pop("start"), np.int32)
     _prefill_case(ld, oracle, kv, Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
