@@ -38,6 +38,94 @@ class _HostStage:
 _stage = _HostStage()
 
 
+class HostPipe:
+    """Page-locked host buffers <-> device, off the compute stream.
+
+    One H2D stream and one D2H stream per device (the two copy engines) and small rings of device staging
+    buffers, so that the upload of call n+1 and the download of call n run under the kernels of calls n / n+1
+    instead of in line with them.  Ordering is by events only: the compute stream waits for an upload, a
+    staging buffer is reused once the kernel that read it (or the download that drained it) has completed."""
+    SLOTS = 4
+    _pipes = {}
+
+    @classmethod
+    def get(cls, device):
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in cls._pipes:
+            cls._pipes[key] = cls(torch.device("cuda", key[1]))
+        return cls._pipes[key]
+
+    def __init__(self, device):
+        self.device = device
+        self.h2d = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+        self.rings = {}
+        self.pending = []   # completion events of downloads not yet waited for
+
+    def _ring(self, key, shape, dtype):
+        k = (key, tuple(shape), dtype)
+        r = self.rings.get(k)
+        if r is None:
+            r = self.rings[k] = {"bufs": [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(self.SLOTS)],
+                                 "free": [None] * self.SLOTS, "idx": 0}
+        i = r["idx"]
+        r["idx"] = (i + 1) % self.SLOTS
+        return r, i
+
+    def upload(self, src, key):
+        """Async H2D of a pinned tensor.  Returns (device tensor, release): call release() once the kernel that
+        reads the tensor has been enqueued on the current stream."""
+        r, i = self._ring(key, src.shape, src.dtype)
+        buf = r["bufs"][i]
+        main = torch.cuda.current_stream(self.device)
+        if r["free"][i] is not None:
+            self.h2d.wait_event(r["free"][i])
+        with torch.cuda.stream(self.h2d):
+            buf.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d)
+        main.wait_event(ev)
+
+        def release():
+            e = torch.cuda.Event()
+            e.record(torch.cuda.current_stream(self.device))
+            r["free"][i] = e
+        return buf, release
+
+    def out_slot(self, key, shape, dtype):
+        """Device buffer a kernel on the current stream may write (its previous download has been ordered first)."""
+        r, i = self._ring(key, shape, dtype)
+        if r["free"][i] is not None:
+            torch.cuda.current_stream(self.device).wait_event(r["free"][i])
+        return r["bufs"][i], (r, i)
+
+    def download(self, buf, slot, dst, sync=True):
+        """D2H of `buf` (written on the current stream) into the pinned tensor `dst` on the download stream."""
+        r, i = slot
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.d2h.wait_event(ev)
+        with torch.cuda.stream(self.d2h):
+            dst.copy_(buf, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.d2h)
+        r["free"][i] = done
+        if sync:
+            done.synchronize()
+        else:
+            self.pending.append(done)
+            if len(self.pending) > 4 * self.SLOTS:
+                self.pending.pop(0).synchronize()
+        return done
+
+    def synchronize(self):
+        """Host results of every sync=False call are valid after this."""
+        for ev in self.pending:
+            ev.synchronize()
+        self.pending.clear()
+
+
 def _is_host(x):
     return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
 
@@ -66,7 +154,9 @@ class AttentionTileLauncher:
     @staticmethod
     def launch(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
                use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
-               rerank_scores=None, debug=False, ctx_lens=None):
+               rerank_scores=None, debug=False, ctx_lens=None, sync=True):
+        """sync=False (page-locked host q / out only): return once the work is enqueued; `out` is valid after
+        AttentionCUDA.synchronize().  Copies then overlap the kernels of neighbouring calls (HostPipe)."""
         if kv_cache is None:
             raise ValueError("AttentionTileLauncher.launch: kv_cache is required (paged path only)")
         if top_k not in (0, None) or top_p < 1.0:
@@ -82,9 +172,22 @@ class AttentionTileLauncher:
                 raise NotImplementedError("prefill: top-k/top-p, RoPE table and rerank_scores are decode-only here")
             return paged_prefill(q, out, kv_cache, B, T, temperature, beam_ids)
         host_io = _is_host(q)
-        d_q = _to_device(q, "q", dev, torch.float32) if host_io else q
         host_out = _is_host(out)
-        d_out = _stage.get("out", (B, H, D), torch.float32, dev)[1] if host_out else out
+        # page-locked host tensors take the copy-engine pipeline, anything else the in-line staging path
+        pipe_q = host_io and _is_pinned(q) and q.dtype == torch.float32 and q.is_contiguous()
+        pipe_out = host_out and _is_pinned(out) and out.dtype == torch.float32 and out.is_contiguous()
+        pipe = HostPipe.get(dev) if (pipe_q or pipe_out) else None
+        release_q = out_slot = None
+        if pipe_q:
+            with torch.cuda.device(dev):
+                d_q, release_q = pipe.upload(q.view(B, H, D), "q")
+        else:
+            d_q = _to_device(q, "q", dev, torch.float32) if host_io else q
+        if pipe_out:
+            with torch.cuda.device(dev):
+                d_out, out_slot = pipe.out_slot("out", (B, H, D), torch.float32)
+        else:
+            d_out = _stage.get("out", (B, H, D), torch.float32, dev)[1] if host_out else out
         assert d_q.dtype == torch.float32 and d_q.is_contiguous() and d_q.numel() == B * H * D
         assert d_out.dtype == torch.float32 and d_out.is_contiguous() and d_out.numel() == B * H * D
         d_beam = None
@@ -124,10 +227,11 @@ class AttentionTileLauncher:
             _cabi.check(st, "pa_paged_decode")
             if debug:  # attention_tile_launcher.hpp:84-88
                 torch.cuda.synchronize(dev)
+            if release_q is not None:
+                release_q()
             if host_out:
-                if _is_pinned(out) and out.dtype == torch.float32 and out.is_contiguous():
-                    out.view(B, H, D).copy_(d_out, non_blocking=True)  # D2H straight into the caller's buffer
-                    torch.cuda.current_stream().synchronize()
+                if pipe_out:
+                    pipe.download(d_out, out_slot, out.view(B, H, D), sync=sync)  # D2H straight into the caller's buffer
                 else:
                     pinned = _stage.get("out", (B, H, D), torch.float32, dev)[0]
                     pinned.copy_(d_out, non_blocking=True)
@@ -146,10 +250,17 @@ class AttentionCUDA:
     @staticmethod
     def forward(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
                 use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
-                rerank_scores=None, debug=False, ctx_lens=None):
+                rerank_scores=None, debug=False, ctx_lens=None, sync=True):
         return AttentionTileLauncher.launch(q, out, B, H, D, T, beam_ids, kv_cache, rotary_emb,
                                             is_prefill, use_fp16, use_overlap, temperature, top_k,
-                                            top_p, rerank_scores, debug, ctx_lens)
+                                            top_p, rerank_scores, debug, ctx_lens, sync)
+
+    @staticmethod
+    def synchronize(device=None):
+        """Completes every forward(..., sync=False) issued on `device` (default: the current one)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        HostPipe.get(dev).synchronize()
+        torch.cuda.current_stream(dev).synchronize()
 
 
 def apply_rotary_embedding(q, k, rotary_emb, positions):

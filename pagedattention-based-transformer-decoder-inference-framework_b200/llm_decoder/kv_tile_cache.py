@@ -215,9 +215,19 @@ class KVTileCache:
 
     # ---- hot path: append (get_write_ptr + row write, hpp:29-34) -------------------------
     def append(self, new_k, new_v, positions, beam_ids=None):
-        """new_k/new_v: [R, H, D] device tensors (f16 or f32); positions: [R] int32 device."""
+        """new_k/new_v: [R, H, D] device tensors (f16 or f32), or page-locked host tensors (uploaded on the copy
+        stream, attention.HostPipe); positions: [R] int32 device."""
         pt = self.page_table_
         table = pt.device_data()
+        releases = []
+        if not new_k.is_cuda:
+            from .attention import HostPipe
+            assert new_k.is_pinned() and new_v.is_pinned(), "host new_k/new_v must be page-locked"
+            pipe = HostPipe.get(table.device)
+            with torch.cuda.device(table.device):
+                new_k, rk = pipe.upload(new_k, "new_k")
+                new_v, rv = pipe.upload(new_v, "new_v")
+            releases = [rk, rv]
         R = new_k.shape[0]
         assert new_k.is_contiguous() and new_v.is_contiguous() and new_k.shape == new_v.shape
         assert new_k.shape[1] == pt.num_heads_ and new_k.shape[2] == self.head_dim_
@@ -236,6 +246,9 @@ class KVTileCache:
                 assert new_k.dtype == torch.float32
                 st = lib.pa_kv_append_f32_f16(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), *common)
         _cabi.check(st, "pa_kv_append")
+        with torch.cuda.device(table.device):
+            for rel in releases:
+                rel()
 
     # ---- beam search: shared-prefix pages with copy-on-write (north star; no reference code) ---
     def _refs(self):

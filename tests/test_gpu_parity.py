@@ -298,6 +298,38 @@ def test_partial_and_combine_equal_full(ld, oracle):
     np.testing.assert_allclose(out.reshape(-1, 128), exp, rtol=1e-5, atol=1e-6)
 
 
+def test_host_pipe_async_forward_matches_device(ld, oracle):
+    """Page-locked host q / out with sync=False (copies on the two copy engines, HostPipe): eight back-to-back
+    calls reuse every staging slot twice; after AttentionCUDA.synchronize() each host output equals the
+    device-resident call bit for bit, and page-locked host K/V rows appended through the same pipeline land in
+    the pages exactly like device rows."""
+    case = make_case(B=3, H=4, D=128, T=256, seed=77)
+    kvc = to_device_cache(case)
+    rng = np.random.default_rng(7)
+    n = 8
+    qs = torch.from_numpy(rng.standard_normal((n, 3, 4, 128)).astype(np.float32)).pin_memory()
+    outs = torch.full((n, 3, 4, 128), float("nan")).pin_memory()
+    for i in range(n):
+        ld.AttentionCUDA.forward(qs[i], outs[i], 3, 4, 128, 256, None, kvc, None, False, True, bool(i & 1),
+                                 case["temperature"], sync=False)
+    ld.AttentionCUDA.synchronize()
+    for i in range(n):
+        d_out = torch.empty((3, 4, 128), device="cuda")
+        ld.AttentionCUDA.forward(qs[i].cuda(), d_out, 3, 4, 128, 256, None, kvc, None, False, True, bool(i & 1),
+                                 case["temperature"])
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(outs[i].numpy(), d_out.cpu().numpy())
+    # host rows through KVTileCache.append
+    kvc2 = to_device_cache(case)
+    nk = torch.from_numpy(rng.standard_normal((3, 4, 128)).astype(np.float32))
+    nv = torch.from_numpy(rng.standard_normal((3, 4, 128)).astype(np.float32))
+    pos = torch.tensor([5, 100, 255], dtype=torch.int32, device="cuda")
+    kvc.append(nk.pin_memory(), nv.pin_memory(), pos)
+    kvc2.append(nk.cuda(), nv.cuda(), pos)
+    torch.cuda.synchronize()
+    assert torch.equal(kvc.key_buffer_, kvc2.key_buffer_) and torch.equal(kvc.value_buffer_, kvc2.value_buffer_)
+
+
 # ------------------------------------------------------------------ page lifecycle (SURVEY 8f row 2)
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 def test_tile_offload_in_reference_cpu_format(ld, oracle, kv, tmp_path):
