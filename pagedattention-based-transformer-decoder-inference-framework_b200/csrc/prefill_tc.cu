@@ -753,19 +753,34 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
             PROBE_CTA(5);
             tc_fence_after();
             const float inv = 1.f / (l_run + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
-            float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + (t_ok ? t : 0)) * D;
-#pragma unroll
+            // O rows leave through shared memory so that every global store instruction writes whole 128-byte
+            // row segments (a thread-per-row store scatters 16 bytes to each of 32 rows).  Staging area: this
+            // warp's quarter of its tile's Q buffer, idle since the tile's last S MMA (which completed before
+            // the P.V just waited for); 32 rows x 128 B per round, 16-byte chunks XOR-swizzled by row.
+            const uint32_t ebuf = q_sm + x * Q_BYTES + qtr * 8192;
+            float* out_tile = a.out + (((int64_t)b * a.H + h) * a.Tq + q0 + qtr * 32) * D;
+            const int rows_ok = a.Tq - (q0 + qtr * 32);  // rows of this warp inside the prompt chunk
+#pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
                 uint32_t orr[32];
                 tmem_ld32(o_addr + c4 * 32, orr);
                 tmem_wait_ld();
-                if (t_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(orow + c4 * 32 + j) =
-                            make_float4(__uint_as_float(orr[j]) * inv, __uint_as_float(orr[j + 1]) * inv,
-                                        __uint_as_float(orr[j + 2]) * inv, __uint_as_float(orr[j + 3]) * inv);
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t addr = ebuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr),
+                                 "f"(__uint_as_float(orr[4 * j]) * inv), "f"(__uint_as_float(orr[4 * j + 1]) * inv),
+                                 "f"(__uint_as_float(orr[4 * j + 2]) * inv), "f"(__uint_as_float(orr[4 * j + 3]) * inv)
+                                 : "memory");
                 }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3), j = lane & 7;
+                    const uint4 v = lds_128(ebuf + r * 128 + ((j ^ (r & 7)) << 4));
+                    if (r < rows_ok) *reinterpret_cast<uint4*>(out_tile + (int64_t)r * D + c4 * 32 + j * 4) = v;
+                }
+                __syncwarp();
             }
         } else if (t_ok) {
             // no visible key at all (zero-capacity table): the reference's 0 / (0 + eps) = 0
