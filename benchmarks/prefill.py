@@ -18,7 +18,7 @@ for p in (ROOT, os.path.join(ROOT, "pagedattention-based-transformer-decoder-inf
 def main():
     import llm_decoder as ld
     dev = torch.device("cuda", 0)
-    H, D, TILE = 32, 128, 16
+    H, D, TILE = 32, int(os.environ.get("HEAD_DIM", "128")), 16   # HEAD_DIM=64: GPT-2-style heads
     res = []
     shapes = ((1, 512), (1, 2048), (4, 2048), (2, 8192))
     kvs = ("f16", "i8")
@@ -60,7 +60,7 @@ def main():
             out_line[("tcgen05_" if tc else "flash_mma_") + kv] = {
                 "ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}
         res.append(out_line)
-    print(json.dumps({"workload": "prefill attention, one layer, 32 heads x D=128, causal", "results": res}))
+    print(json.dumps({"workload": f"prefill attention, one layer, 32 heads x D={D}, causal", "results": res}))
 
 
 if __name__ == "__main__":

@@ -60,12 +60,12 @@ static inline EncodeTiledFnG encode_fn_g() {
     });
     return fn;
 }
-// fp16 pool viewed as [total_tokens][128]; box = 16 tokens x 64 dims (128 B), SWIZZLE_128B.
-static inline bool make_pool_map(CUtensorMap* map, const void* pool, uint64_t total_tokens) {
+// fp16 pool viewed as [total_tokens][head_dim]; box = 16 tokens x 64 dims (128 B), SWIZZLE_128B.
+static inline bool make_pool_map(CUtensorMap* map, const void* pool, uint64_t total_tokens, int head_dim = 128) {
     EncodeTiledFnG fn = encode_fn_g();
     if (!fn) return false;
-    cuuint64_t dims[2] = {128, total_tokens};
-    cuuint64_t strides[1] = {256};
+    cuuint64_t dims[2] = {(cuuint64_t)head_dim, total_tokens};
+    cuuint64_t strides[1] = {(cuuint64_t)head_dim * 2};
     cuuint32_t box[2] = {64, 16};
     cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(pool), dims, strides, box, estr,

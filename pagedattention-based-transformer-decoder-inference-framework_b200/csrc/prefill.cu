@@ -417,7 +417,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 using namespace pa;
 
 // prefill_tc.cu: tcgen05 flash-attention prefill (fp16 pages, head_dim 128)
-int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                          const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
                          const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st);
@@ -440,21 +440,21 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
     PA_CHECK_ARG(B >= 0 && Tq > 0 && num_heads > 0 && head_dim > 0 && head_dim % 4 == 0);
     PA_CHECK_ARG(num_beams > 0 && num_tiles > 0 && total_pages > 0 && tile_size > 0 && temperature != 0.f);
     if (B == 0) return PA_OK;
-    if (head_dim == 128 && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
+    if ((head_dim == 128 || head_dim == 64) && tile_size % 16 == 0 && (uintptr_t)d_k_pool % 128 == 0 && (uintptr_t)d_v_pool % 128 == 0 &&
         d_q != d_out && !(getenv("PA_PREFILL_FA") && atoi(getenv("PA_PREFILL_FA")) == 0) &&
         (kv == 0 || ((uintptr_t)d_k_scales % 16 == 0 && (uintptr_t)d_v_scales % 16 == 0))) {
         // tcgen05 kernel (prefill_tc.cu, fp16 and int8 pages) unless PA_PREFILL_TC=0 asks for the mma.sync kernel below
         if (!(getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 0)) {
-            const int stc = pa_prefill_tc_launch(kv, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table,
+            const int stc = pa_prefill_tc_launch(kv, head_dim, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table,
                                                  num_beams, num_heads, num_tiles, total_pages, d_beam_ids, d_ctx_start, B,
                                                  Tq, tile_size, temperature, as_stream(stream));
             if (stc != PA_ERR_UNSUPPORTED) return stc;
         }
-        // tensor-core flash-attention kernel, straight on the [B, H, Tq, D] layout (no workspace)
+        // mma.sync flash-attention kernel (head_dim 128), straight on the [B, H, Tq, D] layout (no workspace)
         CUtensorMap tmK, tmV;
         const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
-        bool maps_ok = true;
-        if (kv == 0) maps_ok = make_pool_map(&tmK, d_k_pool, total_tokens) && make_pool_map(&tmV, d_v_pool, total_tokens);
+        bool maps_ok = head_dim == 128;
+        if (kv == 0 && maps_ok) maps_ok = make_pool_map(&tmK, d_k_pool, total_tokens) && make_pool_map(&tmV, d_v_pool, total_tokens);
         else memset(&tmK, 0, sizeof(tmK)), memset(&tmV, 0, sizeof(tmV));  // unused by the int8 variant
         if (maps_ok) {
             PrefillArgs pa{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles,

@@ -32,11 +32,11 @@ namespace ptc {
 
 constexpr int QT = 128;               // queries per query tile (= TMEM lanes)
 constexpr int KT = 64;                // tokens per KV tile
-constexpr int D = 128;
-constexpr int Q_BYTES = 2 * QT * 128; // per query tile: two k-blocks of [128 rows x 128 B]
-constexpr int K_BYTES = 2 * KT * 128; // two k-blocks of [64 rows x 128 B]
-constexpr int V_BYTES = 2 * KT * 128; // two n-blocks of [64 k-rows x 128 B]
-constexpr int STAGE = K_BYTES + V_BYTES;
+// HD = head_dim (64 or 128) = HD / 64 blocks of 64 dims (128 B of fp16 per row, the SWIZZLE_128B span):
+__host__ __device__ constexpr int q_bytes(int hd) { return (hd / 64) * QT * 128; }  // per query tile: k-blocks of [128 rows x 128 B]
+__host__ __device__ constexpr int k_bytes(int hd) { return (hd / 64) * KT * 128; }  // K: k-blocks of [64 token rows x 128 B];
+                                                                                    // V: n-blocks of the same shape
+__host__ __device__ constexpr int stage_bytes(int hd) { return 2 * k_bytes(hd); }
 // NQ = query tiles per CTA.  NQ = 2 (default): warps 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 producer, 3-stage ring,
 // all 512 TMEM columns (tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)), one CTA per SM.
 // NQ = 1 (fp16 pages only): warps 0-3 softmax, 4 UMMA, 5 producer, 2-stage ring, 256 TMEM columns, TWO CTAs per
@@ -51,8 +51,7 @@ __host__ __device__ constexpr int threads_for(int kv, int nq) { return (4 * nq +
 // from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
 // the K scale to the score columns and fold the V scale into P (int8_quant.cpp:46-57: x = q / scale).
 constexpr int RS = 3;                 // raw ring stages (one 64-token tile each)
-constexpr int RAW_UNIT = 2048 + 2048 + 64 + 64;
-constexpr int RAW_STAGE = 4 * RAW_UNIT;
+__host__ __device__ constexpr int raw_unit(int hd) { return 2 * 16 * hd + 64 + 64; }  // K rows, V rows, k scales, v scales
 constexpr int SCALE_BYTES = 2 * KT * 4;  // per fp16 stage: 1/k_scale[64], 1/v_scale[64]
 
 struct Args {
@@ -169,12 +168,15 @@ __device__ long long g_probe_cta[8];
 #define PROBE_CTA(k) do { } while (0)
 #endif
 
-template <int KV, int NQ>
+template <int KV, int NQ, int HD>
 __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int ST = stages_for(NQ), NBAR = nbar_for(NQ), TMEM_COLS = NQ * 256;
+    constexpr int ST = stages_for(NQ), NBAR = nbar_for(NQ), TMEM_COLS = NQ * 256;  // (HD = 64 leaves columns unused)
+    constexpr int D = HD, KB = HD / 64;
+    constexpr int Q_BYTES = q_bytes(HD), K_BYTES = k_bytes(HD), STAGE = stage_bytes(HD);
+    constexpr int RAW_UNIT = raw_unit(HD), RAW_STAGE = 4 * RAW_UNIT;
     constexpr int W_MMA = 4 * NQ, W_PROD = 4 * NQ + 1, W_CONV = 4 * NQ + 2;  // warp roles after the softmax groups
     PROBE_CTA(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -281,10 +283,10 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 for (int uu = 0; uu < 4; ++uu) {
                     if ((mask >> uu) & 1u) {
                         const uint32_t d = dst + uu * RAW_UNIT;
-                        bulk_g2s_nohint(d, a.k8 + row0[uu] * D, 2048, raw_full(rs));
-                        bulk_g2s_nohint(d + 2048, a.v8 + row0[uu] * D, 2048, raw_full(rs));
-                        bulk_g2s_nohint(d + 4096, a.k_scales + row0[uu], 64, raw_full(rs));
-                        bulk_g2s_nohint(d + 4160, a.v_scales + row0[uu], 64, raw_full(rs));
+                        bulk_g2s_nohint(d, a.k8 + row0[uu] * D, 16 * D, raw_full(rs));
+                        bulk_g2s_nohint(d + 16 * D, a.v8 + row0[uu] * D, 16 * D, raw_full(rs));
+                        bulk_g2s_nohint(d + 32 * D, a.k_scales + row0[uu], 64, raw_full(rs));
+                        bulk_g2s_nohint(d + 32 * D + 64, a.v_scales + row0[uu], 64, raw_full(rs));
                     }
                 }
                 if (++rs == RS) {
@@ -317,12 +319,12 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 const int r = uu * 16 + tr;  // token row inside the tile
 #pragma unroll
                 for (int kvsel = 0; kvsel < 2; ++kvsel) {
-                    const uint32_t boxrow = dst + kvsel * K_BYTES + hf * 8192 + r * 128;
+                    const uint32_t rowbase = dst + kvsel * K_BYTES + r * 128;
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {  // 16 int8 -> two 16-byte chunks of 8 halfs
+                    for (int c4 = 0; c4 < D / 32; ++c4) {  // 16 int8 -> two 16-byte chunks of 8 halfs
                         uint32_t hv[8];
                         if (have) {
-                            const uint4 w = lds_128(src + kvsel * 2048 + tr * 128 + hf * 64 + c4 * 16);
+                            const uint4 w = lds_128(src + kvsel * (16 * D) + tr * D + hf * (D / 2) + c4 * 16);
                             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -338,10 +340,11 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
 #pragma unroll
                             for (int e = 0; e < 8; ++e) hv[e] = 0u;
                         }
-                        const int c = 2 * c4;
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c) ^ (r & 7)) << 4)),
+                        const int c = hf * (D / 16) + 2 * c4;  // 16-byte chunk of the fp16 row; 8 chunks per 64-dim block
+                        const uint32_t boxrow = rowbase + (c >> 3) * 8192;
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + ((((c) & 7) ^ (r & 7)) << 4)),
                                      "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + (((c + 1) ^ (r & 7)) << 4)),
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(boxrow + ((((c + 1) & 7) ^ (r & 7)) << 4)),
                                      "r"(hv[4]), "r"(hv[5]), "r"(hv[6]), "r"(hv[7]) : "memory");
                     }
                 }
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 float sc = 0.f;
                 const int tok = i * KT + uu * 16 + (lane & 15);
                 if (have && tok < kmax_c) {
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(src + 4096 + lane * 4));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(src + 32 * D + lane * 4));
                     sc = fast_rcp(sc);
                 }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(scale_sm + fs * SCALE_BYTES + (lane >> 4) * (KT * 4) +
@@ -402,13 +405,14 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 mbar_arrive_expect_tx(kv_full(s), STAGE);
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
-                    tma_load_2d(st + uu * 2048, &tmK, 0, row0[uu], kv_full(s));
-                    tma_load_2d(st + 8192 + uu * 2048, &tmK, 64, row0[uu], kv_full(s));
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * 8192 + uu * 2048, &tmK, kb * 64, row0[uu], kv_full(s));
                 }
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
-                    tma_load_2d(st + K_BYTES + uu * 2048, &tmV, 0, row0[uu], kv_full(s));
-                    tma_load_2d(st + K_BYTES + 8192 + uu * 2048, &tmV, 64, row0[uu], kv_full(s));
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_2d(st + K_BYTES + kb * 8192 + uu * 2048, &tmV, kb * 64, row0[uu], kv_full(s));
                 }
                 if (++s == ST) {
                     s = 0;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 const uint32_t st = kv_sm + stage * STAGE;
                 const uint32_t qx = q_sm + x * Q_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {  // 8 k-steps of 16 dims: k-block ks>>2, 32 B per step inside it
+                for (int ks = 0; ks < D / 16; ++ks) {  // k-steps of 16 dims: k-block ks>>2, 32 B per step inside it
                     const uint64_t da = make_desc(qx + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
                     const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
                     umma_f16(tmem_base + x * 2 * KT + (i & 1) * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
             if (elect_one()) {
                 const uint32_t st = kv_sm + stage * STAGE;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < D / 16; ++ks) {
                     const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
 #pragma unroll
                     for (int x = 0; x < NQ; ++x) {
@@ -495,8 +499,8 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 // rows of the last page past the context end may hold anything (0 x NaN = NaN): zero them
                 const int r0 = nvalid_c;
                 const int r1 = (nvalid_c + 15) & ~15;
-                for (int idx = lane; idx < (r1 - r0) * 16; idx += 32) {
-                    const int r = r0 + idx / 16, c = idx % 16;
+                for (int idx = lane; idx < (r1 - r0) * (D / 8); idx += 32) {
+                    const int r = r0 + idx / (D / 8), c = idx % (D / 8);
                     const uint32_t addr = st + K_BYTES + (c >> 3) * 8192 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
                     asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
                 }
@@ -575,19 +579,22 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
             // whole warp on its 512 bytes (coalesced); 16 rows in flight.
             const float* qbase = a.q + (((int64_t)b * a.H + h) * a.Tq) * D;
             const uint32_t qx = q_sm + x * Q_BYTES;
-            const int c = lane >> 1;  // 16-byte chunk (8 halfs) of the row this lane contributes to
+            constexpr int LPR = D / 4;    // lanes per row (one float4 each); 128 / D rows per load instruction
+            constexpr int RPI = 32 / LPR;
+            const int lr = lane % LPR, rsub = lane / LPR;
+            const int c = lr >> 1;  // 16-byte chunk (8 halfs) of the row this lane contributes to
 #pragma unroll 1
-            for (int r0 = 0; r0 < 32; r0 += 16) {
+            for (int r0 = 0; r0 < 32; r0 += 16 * RPI) {
                 float4 v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int tr = q0 + qtr * 32 + r0 + j;
-                    v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * D) + lane)
+                    const int tr = q0 + qtr * 32 + r0 + j * RPI + rsub;
+                    v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * D) + lr)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int rr = qtr * 32 + r0 + j;
+                    const int rr = qtr * 32 + r0 + j * RPI + rsub;
                     const uint32_t w0 = pack_half2(v[j].x * a.qscale, v[j].y * a.qscale);
                     const uint32_t w1 = pack_half2(v[j].z * a.qscale, v[j].w * a.qscale);
                     const uint32_t addr = qx + (c >> 3) * (QT * 128) + rr * 128 + (((c & 7) ^ (rr & 7)) << 4) + (lane & 1) * 8;
@@ -717,7 +724,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                 if (i > 0) ensure_pv(i - 1);
                 tc_fence_after();
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
+                for (int c4 = 0; c4 < D / 32; ++c4) {
                     uint32_t orr[32];
                     tmem_ld32(o_addr + c4 * 32, orr);
                     tmem_wait_ld();
@@ -757,11 +764,11 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
             // row segments (a thread-per-row store scatters 16 bytes to each of 32 rows).  Staging area: this
             // warp's quarter of its tile's Q buffer, idle since the tile's last S MMA (which completed before
             // the P.V just waited for); 32 rows x 128 B per round, 16-byte chunks XOR-swizzled by row.
-            const uint32_t ebuf = q_sm + x * Q_BYTES + qtr * 8192;
+            const uint32_t ebuf = q_sm + x * Q_BYTES + qtr * (Q_BYTES / 4);
             float* out_tile = a.out + (((int64_t)b * a.H + h) * a.Tq + q0 + qtr * 32) * D;
             const int rows_ok = a.Tq - (q0 + qtr * 32);  // rows of this warp inside the prompt chunk
 #pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c4 = 0; c4 < D / 32; ++c4) {
                 uint32_t orr[32];
                 tmem_ld32(o_addr + c4 * 32, orr);
                 tmem_wait_ld();
@@ -814,7 +821,7 @@ extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe_cta(lon
 #endif
 
 // Launch helper used by prefill.cu (returns PA_ERR_UNSUPPORTED when the tensor maps cannot be built).
-int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                          const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
                          const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st) {
@@ -823,13 +830,14 @@ int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k
     const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
     if (total_tokens >= 0x7fffffffull) return PA_ERR_UNSUPPORTED;
     if (kv == 0) {
-        if (!make_pool_map(&tmK, d_k_pool, total_tokens) || !make_pool_map(&tmV, d_v_pool, total_tokens))
+        if (!make_pool_map(&tmK, d_k_pool, total_tokens, head_dim) || !make_pool_map(&tmV, d_v_pool, total_tokens, head_dim))
             return PA_ERR_UNSUPPORTED;
     } else {  // the int8 variant stages raw units with plain bulk copies
         memset(&tmK, 0, sizeof(tmK));
         memset(&tmV, 0, sizeof(tmV));
     }
     const int upt = tile_size >> 4;
+    if (head_dim != 64 && head_dim != 128) return PA_ERR_UNSUPPORTED;
     if (tile_size % 16 != 0 || (upt & (upt - 1)) != 0) return PA_ERR_UNSUPPORTED;  // pages of 16 << k tokens only
     int upt_shift = 0;
     while ((1 << upt_shift) < upt) ++upt_shift;
@@ -848,13 +856,15 @@ int pa_prefill_tc_launch(int kv, const float* d_q, float* d_out, const void* d_k
     const int nqt = (Tq + nq * QT - 1) / (nq * QT);
     const int64_t ctas = (int64_t)B * num_heads * nqt;
     if (ctas > 0x7fffffff) return PA_ERR_INVALID_ARG;
-    const size_t smem = (size_t)nq * Q_BYTES + stages_for(nq) * STAGE + (kv ? RS * RAW_STAGE + stages_for(nq) * SCALE_BYTES : 0) +
+    const size_t smem = (size_t)nq * q_bytes(head_dim) + stages_for(nq) * stage_bytes(head_dim) +
+                        (kv ? RS * 4 * raw_unit(head_dim) + stages_for(nq) * SCALE_BYTES : 0) +
                         (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
-    static bool attr_done[64][4] = {};
-    const int ki = kv * 2 + (nq == 1 ? 1 : 0);
+    static bool attr_done[64][8] = {};
+    const int ki = (head_dim == 64 ? 4 : 0) + kv * 2 + (nq == 1 ? 1 : 0);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
-    static const KernelFn kernels[4] = {prefill_tc_kernel<0, 2>, prefill_tc_kernel<0, 1>, prefill_tc_kernel<1, 2>,
-                                        prefill_tc_kernel<1, 1>};
+    static const KernelFn kernels[8] = {prefill_tc_kernel<0, 2, 128>, prefill_tc_kernel<0, 1, 128>, prefill_tc_kernel<1, 2, 128>,
+                                        prefill_tc_kernel<1, 1, 128>, prefill_tc_kernel<0, 2, 64>,  prefill_tc_kernel<0, 1, 64>,
+                                        prefill_tc_kernel<1, 2, 64>,  prefill_tc_kernel<1, 1, 64>};
     KernelFn kern = kernels[ki];
     if (!attr_done[dev & 63][ki]) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

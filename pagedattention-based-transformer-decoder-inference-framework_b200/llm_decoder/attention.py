@@ -282,7 +282,8 @@ def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_s
     H, D = pt.num_heads_, kv_cache.head_dim_
     assert q.is_contiguous() and out.is_contiguous() and q.numel() == B * H * Tq * D == out.numel()
     lib = _cabi.lib()
-    # head_dim 128 takes the tensor-core flash-attention kernel (fp16 or int8 pages), which needs no scratch
+    # head_dim 128 takes a tensor-core flash-attention kernel (fp16 or int8 pages), which needs no scratch; head_dim 64
+    # takes the tcgen05 kernel too but keeps the scratch for the row-per-query fallback (odd page sizes)
     fa = (D == 128 and kv_cache.tile_size_ % 16 == 0 and
           kv_cache.key_buffer_.data_ptr() % 128 == 0 and kv_cache.value_buffer_.data_ptr() % 128 == 0 and
           q.data_ptr() != out.data_ptr() and os.environ.get("PA_PREFILL_FA", "1") != "0")

@@ -135,8 +135,8 @@ class _DecoderBase:
         kvc = self.kv_caches[layer_idx]
         pt = kvc.page_table_
         lib = self._lib
-        if prefill_shape is not None and self.head_dim_ == 128:
-            # prompt pass: the tensor-core flash-attention prefill kernel ([B, H, n, D] layout)
+        if prefill_shape is not None and self.head_dim_ in (64, 128):
+            # prompt pass: the tcgen05 flash-attention prefill kernel ([B, H, n, D] layout)
             from .attention import paged_prefill
             B, n = prefill_shape
             H, D = self.num_heads_, self.head_dim_

@@ -381,8 +381,8 @@ def test_prefill_causal_matches_oracle(ld, oracle, kv):
     _prefill_case(ld, oracle, kv, Tq=600, start=np.array([0, 0], np.int32), check_forward=False)  # many chunks
 
 
-def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=False, **case_kw):
-    B, H, D = 2, 3, 128
+def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=False, D=128, **case_kw):
+    B, H = 2, 3
     case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv, **case_kw)
     rng = np.random.default_rng(81)
     q = rng.standard_normal((B, H, Tq, D)).astype(np.float32)
@@ -457,6 +457,18 @@ def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, kv, monkey
     Tq = cfg.pop("Tq")
     start = np.array(cfg.pop("start"), np.int32)
     _prefill_case(ld, oracle, kv, Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
+
+
+@pytest.mark.parametrize("nq", ["1", "2"])
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_prefill_head_dim_64_on_tcgen05(ld, oracle, kv, nq, monkeypatch):
+    """head_dim 64 (GPT-2-small heads, BASELINE config C1) takes the same tcgen05 kernel (one 64-dim block per
+    row instead of two): tile boundaries, ctx_start, unmapped pages and poisoned tails against the oracle."""
+    monkeypatch.setenv("PA_PREFILL_NQ", nq)
+    _prefill_case(ld, oracle, kv, Tq=129, start=np.array([0, 7], np.int32), check_forward=False, poison_tail=True, D=64)
+    _prefill_case(ld, oracle, kv, Tq=300, start=np.array([23, 100], np.int32), check_forward=False, poison_tail=True,
+                  D=64, unmapped_frac=0.05)
+    _prefill_case(ld, oracle, kv, Tq=200, start=np.array([40, 8], np.int32), check_forward=False, D=64, tile_size=32)
 
 
 @pytest.mark.parametrize("kv", ["f16", "i8"])
