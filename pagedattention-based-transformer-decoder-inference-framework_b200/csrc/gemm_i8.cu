@@ -40,7 +40,6 @@ constexpr int UK = 32;       // K per tcgen05.mma kind::i8
 #endif
 constexpr int STAGES = PA_GEMM_STAGES;
 constexpr int TILE_BYTES = BM * BK;          // 16 KiB: one A tile or one B tile
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;  // A0, A1, B
 constexpr int TMEM_COLS = 2 * BN;            // two accumulators
 constexpr int NTHREADS = 192;
 

@@ -381,7 +381,7 @@ def test_prefill_causal_matches_oracle(ld, oracle, kv):
     _prefill_case(ld, oracle, kv, Tq=600, start=np.array([0, 0], np.int32), check_forward=False)  # many chunks
 
 
-def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=False, D=128, **case_kw):
+def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=False, D=128, swap_beams=False, **case_kw):
     B, H = 2, 3
     case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=81, kv=kv, **case_kw)
     rng = np.random.default_rng(81)
@@ -404,14 +404,16 @@ def _prefill_case(ld, oracle, kv, Tq, start, check_forward=True, poison_tail=Fal
                             kvc.k_scales_[pg, r0:] = float("nan")
                             kvc.v_scales_[pg, r0:] = 0.0
     out = torch.full((B, H, Tq, D), float("nan"), device="cuda")
+    rows = np.array([1, 0], np.int32) if swap_beams else np.arange(B, dtype=np.int32)   # row b reads table row rows[b]
     ld.paged_prefill(torch.from_numpy(q).cuda(), out, kvc, B, Tq, case["temperature"],
+                     beam_ids=torch.from_numpy(rows).cuda() if swap_beams else None,
                      ctx_start=torch.from_numpy(start).cuda())
     got = out.cpu().numpy()
     # oracle: one decode row per (b, t) through the beam indirection, ctx = start + t + 1
     rows_q = np.ascontiguousarray(q.transpose(0, 2, 1, 3).reshape(B * Tq, H, D))
     exp_case = dict(case)
     exp_case["q"] = rows_q
-    exp_case["beam_ids"] = np.repeat(np.arange(B, dtype=np.int32), Tq)
+    exp_case["beam_ids"] = np.repeat(rows, Tq)
     exp_case["ctx_lens"] = (start[:, None] + np.arange(Tq, dtype=np.int32)[None, :] + 1).reshape(-1).astype(np.int32)
     exp = oracle_attention(exp_case).reshape(B, Tq, H, D).transpose(0, 2, 1, 3)
     np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
@@ -439,6 +441,7 @@ PREFILL_TC_CASES = [
     dict(Tq=520, start=[0, 0], unmapped_frac=0.05),              # unmapped pages read as zeros
     dict(Tq=200, start=[40, 8], tile_size=32),                   # 32-token pages (two units per page)
     dict(Tq=70, start=[500, 3]),                                 # long history, short chunk
+    dict(Tq=260, start=[9, 9], swap_beams=True),                 # beam indirection: row b reads table row 1 - b
 ]
 
 
