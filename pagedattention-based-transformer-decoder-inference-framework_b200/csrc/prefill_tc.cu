@@ -45,7 +45,7 @@ __host__ __device__ constexpr int stage_bytes(int hd) { return 2 * k_bytes(hd); 
 __host__ __device__ constexpr int stages_for(int nq) { return nq == 2 ? 3 : 2; }
 // barriers: kv_full/kv_empty[ST]; per query tile s_full[2], p_full[2], o_full[2], q_ready
 __host__ __device__ constexpr int nbar_for(int nq) { return 2 * stages_for(nq) + 7 * nq; }
-__host__ __device__ constexpr int threads_for(int kv, int nq) { return (4 * nq + 2 + 2 * kv) * 32; }
+__host__ __device__ constexpr int threads_for(int kv, int nq, int mw = 1) { return (4 * nq + mw + 1 + 2 * kv) * 32; }
 // int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
 // into a raw ring, two converter warps (10, 11; 12 warps still get 168 registers) rewrite them as the same swizzled fp16 stage the fp16 path gets
 // from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
@@ -168,8 +168,12 @@ __device__ long long g_probe_cta[8];
 #define PROBE_CTA(k) do { } while (0)
 #endif
 
-template <int KV, int NQ, int HD>
-__global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
+// MW = UMMA-issuing warps.  MW = 2 (fp16 pages, two query tiles): one issuing warp per query tile.  A thread's
+// mbarrier waits queue behind its own tcgen05.commit, so a single issuer sees every "P ready?" wait only after the
+// MMAs it has just issued have drained (~250 cycles of idle tensor pipe per wait, clock64 probes); with one issuer
+// per tile those waits run under the other tile's MMAs.
+template <int KV, int NQ, int HD, int MW = 1>
+__global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) ? 2 : 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
     constexpr int D = HD, KB = HD / 64;
     constexpr int Q_BYTES = q_bytes(HD), K_BYTES = k_bytes(HD), STAGE = stage_bytes(HD);
     constexpr int RAW_UNIT = raw_unit(HD), RAW_STAGE = 4 * RAW_UNIT;
-    constexpr int W_MMA = 4 * NQ, W_PROD = 4 * NQ + 1, W_CONV = 4 * NQ + 2;  // warp roles after the softmax groups
+    constexpr int W_MMA = 4 * NQ, W_PROD = 4 * NQ + MW, W_CONV = 4 * NQ + MW + 1;  // warp roles after the softmax groups
     PROBE_CTA(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_sm = base;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; ++s) {
             mbar_init(kv_full(s), KV ? 2 : 1);  // KV = 1: one arrival per converter warp
-            mbar_init(kv_empty(s), 1);
+            mbar_init(kv_empty(s), MW);
         }
         if (KV) {
             for (int s = 0; s < RS; ++s) {
@@ -418,6 +422,83 @@ __global__ void __launch_bounds__(threads_for(KV, NQ), (NQ == 1 && KV == 0) ? 2 
                     s = 0;
                     ph ^= 1u;
                 }
+            }
+        }
+    } else if (MW == 2 && (warp == W_MMA || warp == W_MMA + 1)) {
+        // ------------------------------------------------------------ UMMA issuers, one per query tile
+        constexpr uint32_t kIdescS = idesc_f16(QT, KT, 0, 0);  // Q K-major, K K-major
+        constexpr uint32_t kIdescO = idesc_f16(QT, D, 0, 1);   // P (TMEM), V MN-major
+        const int x = warp - W_MMA;
+        const int ntx = nts[x];
+        auto issue_S = [&](int i, int stage) {  // S_x(i) into buffer i & 1 (see the single-issuer branch below)
+            if (elect_one()) {
+                const uint32_t st = kv_sm + stage * STAGE;
+                const uint32_t qx = q_sm + x * Q_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    const uint64_t da = make_desc(qx + (ks >> 2) * (QT * 128) + (ks & 3) * 32, 16, 1024);
+                    const uint64_t db = make_desc(st + (ks >> 2) * (KT * 128) + (ks & 3) * 32, 16, 1024);
+                    umma_f16(tmem_base + x * 2 * KT + (i & 1) * KT, da, db, kIdescS, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(s_full(x, i & 1));
+            }
+            __syncwarp();
+        };
+        if (n_tiles > 0) {
+            mbar_wait_wd(kv_full(0), 0);
+            if (ntx > 0) {
+                mbar_wait_wd(q_ready(x), 0);
+                tc_fence_after();
+                issue_S(0, 0);
+            }
+        }
+        int s = 0;
+        uint32_t kv_ph = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s_next = (s + 1 == ST) ? 0 : s + 1;
+            if (i + 1 < n_tiles) {
+                // every stage is waited for by both issuers, also the ones a finished tile no longer reads: its
+                // arrival on kv_empty below must fall into the phase of THIS use of the stage
+                const uint32_t ph_next = (s + 1 == ST) ? (kv_ph ^ 1u) : kv_ph;
+                mbar_wait_wd(kv_full(s_next), ph_next);
+                tc_fence_after();
+                if (i + 1 < ntx) issue_S(i + 1, s_next);  // runs under the softmax of tile i
+            }
+            if (i < ntx) {
+                const uint32_t st = kv_sm + s * STAGE;
+                const int nvalid_c = min(KT, kmax_c - i * KT);
+                if (KV == 0 && nvalid_c < KT && (nvalid_c & 15)) {
+                    // rows of the last page past the context end may hold anything (0 x NaN = NaN): zero them
+                    // (both issuers may do this for the same tile: same zeros)
+                    const int r0 = nvalid_c;
+                    const int r1 = (nvalid_c + 15) & ~15;
+                    for (int idx = lane; idx < (r1 - r0) * (D / 8); idx += 32) {
+                        const int r = r0 + idx / (D / 8), c = idx % (D / 8);
+                        const uint32_t addr = st + K_BYTES + (c >> 3) * 8192 + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                }
+                mbar_wait_wd(p_full(x, i & 1), (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                if (elect_one()) {
+                    const int nvalid = min(KT, kmaxs[x] - i * KT);
+                    const int ksteps = (nvalid + 15) >> 4;  // tokens past the causal limit contribute nothing
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t ta = tmem_base + x * 2 * KT + (i & 1) * KT + ks * 8;  // P(i), packed fp16
+                        const uint64_t db = make_desc(st + K_BYTES + ks * 2048, 8192, 1024);
+                        umma_f16_ts(tmem_base + NQ * 2 * KT + x * D, ta, db, kIdescO, (i > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(o_full(x, i & 1));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(kv_empty(s));  // arrives once this issuer's reads of the stage (if any) are done
+            __syncwarp();
+            if (++s == ST) {
+                s = 0;
+                kv_ph ^= 1u;
             }
         }
     } else if (warp == W_MMA) {
@@ -859,19 +940,22 @@ int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, c
     const size_t smem = (size_t)nq * q_bytes(head_dim) + stages_for(nq) * stage_bytes(head_dim) +
                         (kv ? RS * 4 * raw_unit(head_dim) + stages_for(nq) * SCALE_BYTES : 0) +
                         (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
-    static bool attr_done[64][8] = {};
-    const int ki = (head_dim == 64 ? 4 : 0) + kv * 2 + (nq == 1 ? 1 : 0);
+    // one UMMA issuer per query tile for fp16 pages (PA_PREFILL_MW=1: single issuer)
+    const bool mw2 = kv == 0 && nq == 2 && !(getenv("PA_PREFILL_MW") && atoi(getenv("PA_PREFILL_MW")) == 1);
+    static bool attr_done[64][10] = {};
+    const int ki = mw2 ? (head_dim == 64 ? 9 : 8) : (head_dim == 64 ? 4 : 0) + kv * 2 + (nq == 1 ? 1 : 0);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
-    static const KernelFn kernels[8] = {prefill_tc_kernel<0, 2, 128>, prefill_tc_kernel<0, 1, 128>, prefill_tc_kernel<1, 2, 128>,
-                                        prefill_tc_kernel<1, 1, 128>, prefill_tc_kernel<0, 2, 64>,  prefill_tc_kernel<0, 1, 64>,
-                                        prefill_tc_kernel<1, 2, 64>,  prefill_tc_kernel<1, 1, 64>};
+    static const KernelFn kernels[10] = {prefill_tc_kernel<0, 2, 128>,    prefill_tc_kernel<0, 1, 128>, prefill_tc_kernel<1, 2, 128>,
+                                         prefill_tc_kernel<1, 1, 128>,    prefill_tc_kernel<0, 2, 64>,  prefill_tc_kernel<0, 1, 64>,
+                                         prefill_tc_kernel<1, 2, 64>,     prefill_tc_kernel<1, 1, 64>,  prefill_tc_kernel<0, 2, 128, 2>,
+                                         prefill_tc_kernel<0, 2, 64, 2>};
     KernelFn kern = kernels[ki];
     if (!attr_done[dev & 63][ki]) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e0 != cudaSuccess) return (int)e0;
         attr_done[dev & 63][ki] = true;
     }
-    kern<<<(unsigned)ctas, threads_for(kv, nq), smem, st>>>(tmK, tmV, a);
+    kern<<<(unsigned)ctas, threads_for(kv, nq, mw2 ? 2 : 1), smem, st>>>(tmK, tmV, a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? PA_OK : (int)e;
 }
