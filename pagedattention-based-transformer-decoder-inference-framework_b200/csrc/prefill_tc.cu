@@ -45,7 +45,9 @@ __host__ __device__ constexpr int stage_bytes(int hd) { return 2 * k_bytes(hd); 
 __host__ __device__ constexpr int stages_for(int nq) { return nq == 2 ? 3 : 2; }
 // barriers: kv_full/kv_empty[ST]; per query tile s_full[2], p_full[2], o_full[2], q_ready
 __host__ __device__ constexpr int nbar_for(int nq) { return 2 * stages_for(nq) + 7 * nq; }
-__host__ __device__ constexpr int threads_for(int kv, int nq, int mw = 1) { return (4 * nq + mw + 1 + 2 * kv) * 32; }
+// int8 pages: two converter warps with one UMMA issuer, one with two (12 warps keep 168 registers per thread)
+__host__ __device__ constexpr int conv_warps(int kv, int mw) { return kv ? (mw == 2 ? 1 : 2) : 0; }
+__host__ __device__ constexpr int threads_for(int kv, int nq, int mw = 1) { return (4 * nq + mw + 1 + conv_warps(kv, mw)) * 32; }
 // int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
 // into a raw ring, two converter warps (10, 11; 12 warps still get 168 registers) rewrite them as the same swizzled fp16 stage the fp16 path gets
 // from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
@@ -206,13 +208,13 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; ++s) {
-            mbar_init(kv_full(s), KV ? 2 : 1);  // KV = 1: one arrival per converter warp
+            mbar_init(kv_full(s), KV ? conv_warps(KV, MW) : 1);  // KV = 1: one arrival per converter warp
             mbar_init(kv_empty(s), MW);
         }
         if (KV) {
             for (int s = 0; s < RS; ++s) {
                 mbar_init(raw_full(s), 1);
-                mbar_init(raw_empty(s), 2);
+                mbar_init(raw_empty(s), conv_warps(KV, MW));
             }
         }
         for (int x = 0; x < NQ; ++x) {
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
             const uint32_t mask = (uint32_t)meta[rs];
             const uint32_t dst = kv_sm + fs * STAGE;
 #pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-                const int uu = 2 * cw + k2;
+            for (int k2 = 0; k2 < 4 / conv_warps(1, MW); ++k2) {
+                const int uu = (4 / conv_warps(1, MW)) * cw + k2;
                 const uint32_t src = raw_sm + rs * RAW_STAGE + uu * RAW_UNIT;
                 const bool have = (mask >> uu) & 1u;
                 const int r = uu * 16 + tr;  // token row inside the tile
@@ -940,15 +942,18 @@ int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, c
     const size_t smem = (size_t)nq * q_bytes(head_dim) + stages_for(nq) * stage_bytes(head_dim) +
                         (kv ? RS * 4 * raw_unit(head_dim) + stages_for(nq) * SCALE_BYTES : 0) +
                         (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
-    // one UMMA issuer per query tile for fp16 pages (PA_PREFILL_MW=1: single issuer)
-    const bool mw2 = kv == 0 && nq == 2 && !(getenv("PA_PREFILL_MW") && atoi(getenv("PA_PREFILL_MW")) == 1);
-    static bool attr_done[64][10] = {};
-    const int ki = mw2 ? (head_dim == 64 ? 9 : 8) : (head_dim == 64 ? 4 : 0) + kv * 2 + (nq == 1 ? 1 : 0);
+    // one UMMA issuer per query tile for fp16 pages (PA_PREFILL_MW=1: single issuer, =2: two issuers)
+    // (int8 pages: a second issuer leaves room for only one converter warp inside the 12-warp register budget, and
+    //  one converter cannot keep up -- 292 vs 452 TFLOP/s at 4 x 2048 -- so they stay on MW = 1 unless PA_PREFILL_MW=2)
+    const char* mw_env = getenv("PA_PREFILL_MW");
+    const bool mw2 = nq == 2 && (mw_env ? atoi(mw_env) == 2 : kv == 0);
+    static bool attr_done[64][12] = {};
+    const int ki = mw2 ? 8 + kv * 2 + (head_dim == 64 ? 1 : 0) : (head_dim == 64 ? 4 : 0) + kv * 2 + (nq == 1 ? 1 : 0);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
-    static const KernelFn kernels[10] = {prefill_tc_kernel<0, 2, 128>,    prefill_tc_kernel<0, 1, 128>, prefill_tc_kernel<1, 2, 128>,
+    static const KernelFn kernels[12] = {prefill_tc_kernel<0, 2, 128>,    prefill_tc_kernel<0, 1, 128>, prefill_tc_kernel<1, 2, 128>,
                                          prefill_tc_kernel<1, 1, 128>,    prefill_tc_kernel<0, 2, 64>,  prefill_tc_kernel<0, 1, 64>,
                                          prefill_tc_kernel<1, 2, 64>,     prefill_tc_kernel<1, 1, 64>,  prefill_tc_kernel<0, 2, 128, 2>,
-                                         prefill_tc_kernel<0, 2, 64, 2>};
+                                         prefill_tc_kernel<0, 2, 64, 2>,  prefill_tc_kernel<1, 2, 128, 2>, prefill_tc_kernel<1, 2, 64, 2>};
     KernelFn kern = kernels[ki];
     if (!attr_done[dev & 63][ki]) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

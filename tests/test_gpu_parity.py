@@ -457,6 +457,8 @@ def test_prefill_tensor_core_kernels_match_oracle(ld, oracle, ci, tc, kv, monkey
     monkeypatch.setenv("PA_PREFILL_TC", "0" if tc == "mma" else "1")
     if tc != "mma":   # both CTA shapes of the tcgen05 kernel (the launcher would pick one by grid size)
         monkeypatch.setenv("PA_PREFILL_NQ", tc[-1])
+        if ci % 2:    # and both UMMA-issuer layouts of the two-tile shape (default: two for fp16, one for int8)
+            monkeypatch.setenv("PA_PREFILL_MW", "1" if kv == "f16" else "2")
     Tq = cfg.pop("Tq")
     start = np.array(cfg.pop("start"), np.int32)
     _prefill_case(ld, oracle, kv, Tq=Tq, start=start, check_forward=False, poison_tail=True, **cfg)
