@@ -1,5 +1,5 @@
 // prefill_tc.cu -- flash-attention prefill over the paged cache on the 5th-generation tensor cores
-// (tcgen05.mma kind::f16, accumulators in TMEM), fp16 and int8 pages, head_dim 128.  SURVEY 8(f) row 1.
+// (tcgen05.mma kind::f16, accumulators in TMEM), fp16 and int8 pages, head_dim 64 / 128.  SURVEY 8(f) row 1.
 //
 // One CTA = 256 consecutive query positions of one (row, head), handled as TWO query tiles of 128 rows
 // (A, B) that share every K/V tile; KV is consumed in tiles of 64 tokens (4 page units of 16 tokens, each
@@ -7,14 +7,16 @@
 //   warps 0-3   : softmax group A, warps 4-7: softmax group B.  One thread per query row (= TMEM lane):
 //                 tcgen05.ld its 64 scores, causal / context / unmapped-page mask, online softmax in registers,
 //                 P written back to TMEM (packed fp16 over the first 32 columns of the scores it came from).
-//   warp 8      : TMEM allocation (all 512 columns) + one elected thread that issues the UMMAs:
+//   warp 8 (+9) : TMEM allocation (all 512 columns) + the elected thread(s) that issue the UMMAs:
 //                   S_X[sb] (128 x 64, fp32, TMEM)  = Q_X (smem, fp16) . K^T        8 x (M128 N64  K16)
 //                   O_X     (128 x 128, fp32, TMEM) += P_X (TMEM, fp16) . V (smem)   4 x (M128 N128 K16)
-//                 in the staggered order S_A(i+1) | P.V_A(i) | S_B(i+1) | P.V_B(i).
-//   warp 9      : producer, one elected thread: fp16 pages = 16 TMA tensor boxes per tile (K tile as the K-major B
+//                 fp16 pages: one issuing warp PER QUERY TILE (MW = 2; a thread's mbarrier waits queue behind its own
+//                 tcgen05.commit, so a single issuer idles the pipe at every P hand-off); int8 pages: one issuer,
+//                 staggered order S_A(i+1) | P.V_A(i) | S_B(i+1) | P.V_B(i).
+//   next warp   : producer, one elected thread: fp16 pages = 16 TMA tensor boxes per tile (K tile as the K-major B
 //                 operand of S, V tile as the MN-major B operand of P.V, 3-stage ring); int8 pages = bulk copies
 //                 of raw units into a raw ring.
-//   warps 10-11 : (int8 pages) converters: raw units -> the same swizzled fp16 stage, 1/scale per token beside it.
+//   last 2 warps: (int8 pages) converters: raw units -> the same swizzled fp16 stage, 1/scale per token beside it.
 // O accumulates in TMEM across all KV tiles (accumulate flag), scaled by a per-row REFERENCE maximum that
 // is only raised when the tile maximum exceeds it by more than 8 (log2 units): P stays below 2^8 in fp16,
 // l and O use the same reference so O / l is exact, and the row rescale (tcgen05.ld, multiply, tcgen05.st)
@@ -37,7 +39,7 @@ __host__ __device__ constexpr int q_bytes(int hd) { return (hd / 64) * QT * 128;
 __host__ __device__ constexpr int k_bytes(int hd) { return (hd / 64) * KT * 128; }  // K: k-blocks of [64 token rows x 128 B];
                                                                                     // V: n-blocks of the same shape
 __host__ __device__ constexpr int stage_bytes(int hd) { return 2 * k_bytes(hd); }
-// NQ = query tiles per CTA.  NQ = 2 (default): warps 0-3 softmax A, 4-7 softmax B, 8 UMMA, 9 producer, 3-stage ring,
+// NQ = query tiles per CTA.  NQ = 2 (default): warps 0-3 softmax A, 4-7 softmax B, then UMMA issuer(s), producer, 3-stage ring,
 // all 512 TMEM columns (tile X: S0 [128X, +64), S1 [128X+64, +64); O_X [256 + 128X, +128)), one CTA per SM.
 // NQ = 1 (fp16 pages only): warps 0-3 softmax, 4 UMMA, 5 producer, 2-stage ring, 256 TMEM columns, TWO CTAs per
 // SM -- K/V bytes are staged once per 128 queries instead of 256, but the prologue / epilogue of one CTA runs
@@ -49,8 +51,8 @@ __host__ __device__ constexpr int nbar_for(int nq) { return 2 * stages_for(nq) +
 __host__ __device__ constexpr int conv_warps(int kv, int mw) { return kv ? (mw == 2 ? 1 : 2) : 0; }
 __host__ __device__ constexpr int threads_for(int kv, int nq, int mw = 1) { return (4 * nq + mw + 1 + conv_warps(kv, mw)) * 32; }
 // int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
-// into a raw ring, two converter warps (10, 11; 12 warps still get 168 registers) rewrite them as the same swizzled fp16 stage the fp16 path gets
-// from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
+// into a raw ring, the converter warps (12 warps in all still get 168 registers) rewrite them as the same swizzled
+// fp16 stage the fp16 path gets from TMA (exact: PRMT to 1024 + u, HSUB2) and leave 1/scale per token next to it; the softmax threads apply
 // the K scale to the score columns and fold the V scale into P (int8_quant.cpp:46-57: x = q / scale).
 constexpr int RS = 3;                 // raw ring stages (one 64-token tile each)
 __host__ __device__ constexpr int raw_unit(int hd) { return 2 * 16 * hd + 64 + 64; }  // K rows, V rows, k scales, v scales
