@@ -47,8 +47,9 @@ __host__ __device__ constexpr int stage_bytes(int hd) { return 2 * k_bytes(hd); 
 __host__ __device__ constexpr int stages_for(int nq) { return nq == 2 ? 3 : 2; }
 // barriers: kv_full/kv_empty[ST]; per query tile s_full[2], p_full[2], o_full[2], q_ready
 __host__ __device__ constexpr int nbar_for(int nq) { return 2 * stages_for(nq) + 7 * nq; }
-// int8 pages: two converter warps with one UMMA issuer, one with two (12 warps keep 168 registers per thread)
-__host__ __device__ constexpr int conv_warps(int kv, int mw) { return kv ? (mw == 2 ? 1 : 2) : 0; }
+// int8 pages: two converter warps (with two UMMA issuers that makes 13 warps = 128 registers per thread, a few
+// spilled words; measured no faster than one issuer, so int8 defaults to MW = 1)
+__host__ __device__ constexpr int conv_warps(int kv, int mw) { return kv ? 2 : 0; }
 __host__ __device__ constexpr int threads_for(int kv, int nq, int mw = 1) { return (4 * nq + mw + 1 + conv_warps(kv, mw)) * 32; }
 // int8 pages (KV = 1): the producer bulk-copies RAW units (16 tokens: 2 KB of K, 2 KB of V, 16 + 16 f32 scales)
 // into a raw ring, the converter warps (12 warps in all still get 168 registers) rewrite them as the same swizzled
@@ -945,8 +946,8 @@ int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, c
                         (kv ? RS * 4 * raw_unit(head_dim) + stages_for(nq) * SCALE_BYTES : 0) +
                         (nbar_for(nq) + 2 * RS) * 8 + 8 + RS * 4 + 16 + 1024;
     // one UMMA issuer per query tile for fp16 pages (PA_PREFILL_MW=1: single issuer, =2: two issuers)
-    // (int8 pages: a second issuer leaves room for only one converter warp inside the 12-warp register budget, and
-    //  one converter cannot keep up -- 292 vs 452 TFLOP/s at 4 x 2048 -- so they stay on MW = 1 unless PA_PREFILL_MW=2)
+    // (int8 pages: 440 / 585 TFLOP/s with two issuers against 453 / 606 with one -- their limit is elsewhere -- so they
+    //  stay on MW = 1 unless PA_PREFILL_MW=2)
     const char* mw_env = getenv("PA_PREFILL_MW");
     const bool mw2 = nq == 2 && (mw_env ? atoi(mw_env) == 2 : kv == 0);
     static bool attr_done[64][12] = {};
