@@ -17,6 +17,7 @@ python benchmarks/gemm_i8.py 2>/dev/null | tail -1 > $OUT/gemm_m256.json
 M=2048 python benchmarks/gemm_i8.py 2>/dev/null | tail -1 > $OUT/gemm_m2048.json
 M=32 python benchmarks/gemm_i8.py 2>/dev/null | tail -1 > $OUT/gemm_m32.json
 python benchmarks/prefill.py 2>/dev/null | tail -1 > $OUT/prefill.json
+HEAD_DIM=64 python benchmarks/prefill.py 2>/dev/null | tail -1 > $OUT/prefill_d64.json
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29533 \
     benchmarks/splitkv_c5.py --ctx 16384 --iters 40 2>/dev/null | tail -1 > $OUT/c5_share_1gpu.json
 ls -la $OUT
