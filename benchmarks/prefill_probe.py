@@ -6,8 +6,10 @@
 
 clock64 stamps of warp 0 (softmax group A), warp 4 (group B) and the UMMA warp over 64 steady-state KV tiles
 of CTA 5.  Softmax segments: wait S | tcgen05.ld | mask + max + exp2 + pack | wait P.V(i-1) | rescale + P
-store to TMEM | fence + arrive.  UMMA warp, per tile t: A's P(t) seen | A's P.V(t) issued | B's P(t) seen | B's
-P.V(t) issued (differences between consecutive stamps).  The product library is not touched."""
+store to TMEM | fence + arrive.  UMMA issuer of tile A (default two-issuer kernel): wait K/V(i+1) + issue S(i+1) |
+wait P(i) | issue P.V(i).  With PA_PREFILL_MW=1 (single issuer) the stamps are: loop top | S issued | A's P seen |
+A's P.V issued | B's P seen | B's P.V issued.  The product library is not touched (the probes compile to nothing
+there: identical SASS)."""
 import ctypes
 import glob
 import os

@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
         uint32_t kv_ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
             const int s_next = (s + 1 == ST) ? 0 : s + 1;
+            if (x == 0) PROBE(2, i, 0);  // issuer of tile A: loop top | S(i+1) issued | P(i) seen | P.V(i) issued
             if (i + 1 < n_tiles) {
                 // every stage is waited for by both issuers, also the ones a finished tile no longer reads: its
                 // arrival on kv_empty below must fall into the phase of THIS use of the stage
@@ -469,6 +470,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
                 tc_fence_after();
                 if (i + 1 < ntx) issue_S(i + 1, s_next);  // runs under the softmax of tile i
             }
+            if (x == 0) PROBE(2, i, 1);
             if (i < ntx) {
                 const uint32_t st = kv_sm + s * STAGE;
                 const int nvalid_c = min(KT, kmax_c - i * KT);
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
                     __syncwarp();
                 }
                 mbar_wait_wd(p_full(x, i & 1), (uint32_t)((i >> 1) & 1));
+                if (x == 0) PROBE(2, i, 2);
                 tc_fence_after();
                 if (elect_one()) {
                     const int nvalid = min(KT, kmaxs[x] - i * KT);
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
                     umma_commit(o_full(x, i & 1));
                 }
                 __syncwarp();
+                if (x == 0) PROBE(2, i, 3);
             }
             if (elect_one()) umma_commit(kv_empty(s));  // arrives once this issuer's reads of the stage (if any) are done
             __syncwarp();
