@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- numpy wrappers over oracle/liboracle_cpu.so (oracle_cpu.c).
 
 Parity status: int8_quant / softmax_lut / filter functions are pinned bit-exact against
-the reference's own objects (tests/test_oracle_pinning.py).  `paged_attention` restates
-attention_cpu/cpu_attention_kernel.cpp:36-129, which does not compile as shipped, so its
-loop structure is a restatement; the stages it calls are pinned.  The oneDNN epilogue
-(`dnnl_matmul_int8`) is PARITY UNPINNED beyond its int32 accumulators.
+the reference's own objects; `paged_attention` (attention_cpu/cpu_attention_kernel.cpp:36-129) is
+pinned bit-exact -- output, attention weights and logits -- against the reference's own
+cpu_paged_attention_forward<float>, built by oracle/build_ref_attention.py from a temporary copy
+with identifier-level fixes only (the TU does not compile as shipped); `layer_norm` / `mlp_f32`
+are pinned bit-exact against decoder/layer_norm.hpp / mlp.hpp compiled unmodified
+(tests/test_oracle_pinning.py, tests/golden/ref_attention_vectors.npz).  The oneDNN epilogue
+(`dnnl_matmul_int8`) is PARITY UNPINNED beyond its int32 accumulators (oneDNN < 3 is absent).
 """
 import ctypes as C
 import os
@@ -29,6 +32,10 @@ def build(force=False):
     ref_so = os.path.join(_HERE, "_ref", "libref_cpu.so")
     if os.path.isdir("/root/reference") and (force or not os.path.exists(ref_so)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference"):
+        # the reference's own cpu_paged_attention_forward<float> + decoder headers (oracle/_ref/libref_attn.so)
+        from . import build_ref_attention
+        build_ref_attention.build(force=force)
 
 
 def lib():

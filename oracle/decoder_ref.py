@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the decoder layer loop, built from the oracle's
-pinned pieces.  PARITY UNPINNED as a whole: the reference's decoders do not compile and do not
-append K/V; this restates the SAME decisions llm_decoder/decoders.py
-documents, step by step, so the GPU `generate` can be checked against an independent CPU path.
+pinned pieces.  Every STAGE is pinned bit-exact against the reference's own compiled code
+(embedding lookup, LayerNorm<float>, MLP<float>, cpu_paged_attention_forward<float>, int8_quant:
+tests/test_oracle_pinning.py); the WIRING between them is not: decoder_block.hpp / cuda_decoder.cu /
+int8_decoder.cpp do not compile and never append K/V, so this file restates the
+decisions llm_decoder/decoders.py documents, step by step, as an independent CPU path.
 
   decoder/token_embedding.hpp:19-26  embedding lookup
   decoder/decoder_block.hpp:41-62    LN1 -> attention(q = LN1 out) -> LN2 -> MLP, no residuals

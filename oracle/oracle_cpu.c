@@ -548,7 +548,10 @@ ORC_API void orc_layer_norm(const float* in, float* out, const float* gamma, con
         float var = 0;
         for (int j = 0; j < hidden; ++j) var += (x[j] - mean) * (x[j] - mean);
         var /= hidden;
-        float inv_std = (float)(1.0 / sqrt((double)(var + eps))); /* T inv_std = 1.0 / std::sqrt(var+eps) */
+        /* `T inv_std = 1.0 / std::sqrt(var + epsilon_)` with T = float: std::sqrt picks the FLOAT overload (the
+         * root is rounded to f32 first), the division by the double literal 1.0 is done in double, the quotient
+         * is rounded to f32 (pinned bit-exact against the compiled header, tests/test_oracle_pinning.py) */
+        float inv_std = (float)(1.0 / (double)sqrtf(var + eps));
         for (int j = 0; j < hidden; ++j) y[j] = (x[j] - mean) * inv_std * gamma[j] + beta[j];
     }
 }

@@ -171,3 +171,100 @@ class KVTileCacheCPU:
     def load(self, path):
         assert self._sfx == "f32"
         return lib().ref_kvcpu_f32_load(self._h, path.encode())
+
+
+# ---- oracle/_ref/libref_attn.so: the reference's OWN cpu_paged_attention_forward<float> and the
+# decoder's header-only LayerNorm / MLP / TokenEmbedding (oracle/build_ref_attention.py) -------------
+_ATTN_PATH = os.path.join(_HERE, "_ref", "libref_attn.so")
+_attn = None
+
+
+def attn_available():
+    return os.path.exists(_ATTN_PATH)
+
+
+def attn_lib():
+    global _attn
+    if _attn is None:
+        _attn = C.CDLL(_ATTN_PATH)
+    return _attn
+
+
+def cpu_paged_attention_forward(q, k_pool, v_pool, table, *, tile_size, T, beam_ids=None, temperature=1.0,
+                                rope=None, top_k=0, top_p=1.0, causal=False, return_probs=False,
+                                return_logits=False):
+    """attention_cpu/cpu_attention_kernel.cpp:36-129, float instantiation, run on the reference's own tile
+    store.  q [B,H,D]; pools [total_pages, tile_size, D] f32; table int32 [num_beams, H, num_tiles]."""
+    q, k_pool, v_pool = _f32(q), _f32(k_pool), _f32(v_pool)
+    table = np.ascontiguousarray(table, dtype=np.int32)
+    B, H, D = q.shape
+    num_beams, _, num_tiles = table.shape
+    out = np.zeros((B, H, D), dtype=np.float32)
+    probs = np.zeros((B, H, T), dtype=np.float32) if return_probs else None
+    logits = np.zeros((B, H, T), dtype=np.float32) if return_logits else None
+    beam_ids = None if beam_ids is None else np.ascontiguousarray(beam_ids, dtype=np.int32)
+    rope = None if rope is None else _f32(rope)
+    st = attn_lib().ref_cpu_paged_attention_f32(
+        _p(q, _f32p), _p(out, _f32p), _p(k_pool, _f32p), _p(v_pool, _f32p), _p(table, _i32p), num_beams, num_tiles,
+        k_pool.shape[0], _p(beam_ids, _i32p), B, H, T, D, tile_size, C.c_float(temperature), _p(rope, _f32p),
+        top_k, C.c_float(top_p), 1 if causal else 0, _p(probs, _f32p), _p(logits, _f32p))
+    assert st == 0, "reference cpu_paged_attention_forward threw"
+    res = (out,)
+    if return_probs:
+        res += (probs,)
+    if return_logits:
+        res += (logits,)
+    return res[0] if len(res) == 1 else res
+
+
+def _tmp_weights(arrays):
+    import tempfile
+    f = tempfile.NamedTemporaryFile(suffix=".bin", delete=False)
+    for a in arrays:
+        f.write(_f32(a).tobytes())
+    f.close()
+    return f.name
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    """decoder/layer_norm.hpp:20-37 (weights through its own load_weights, :13-18)."""
+    x = _f32(x)
+    rows, hidden = x.shape
+    out = np.empty_like(x)
+    path = _tmp_weights([gamma, beta])
+    try:
+        st = attn_lib().ref_layer_norm_f32(path.encode(), hidden, C.c_float(eps), _p(x, _f32p), _p(out, _f32p), rows)
+    finally:
+        os.unlink(path)
+    assert st == 0
+    return out
+
+
+def mlp_f32(x, fc1_w, fc1_b, fc2_w, fc2_b):
+    """decoder/mlp.hpp:23-41 (weights through its own load_weights, :14-21)."""
+    x = _f32(x)
+    rows, hidden = x.shape
+    inter = np.asarray(fc1_b).size
+    out = np.empty_like(x)
+    path = _tmp_weights([fc1_w, fc1_b, fc2_w, fc2_b])
+    try:
+        st = attn_lib().ref_mlp_f32(path.encode(), hidden, inter, _p(x, _f32p), _p(out, _f32p), rows)
+    finally:
+        os.unlink(path)
+    assert st == 0
+    return out
+
+
+def token_embedding(table, ids):
+    """decoder/token_embedding.hpp:19-26."""
+    table = _f32(table)
+    vocab, hidden = table.shape
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    out = np.empty((ids.size, hidden), dtype=np.float32)
+    path = _tmp_weights([table])
+    try:
+        st = attn_lib().ref_token_embedding_f32(path.encode(), vocab, hidden, _p(ids, _i32p), ids.size, _p(out, _f32p))
+    finally:
+        os.unlink(path)
+    assert st == 0
+    return out

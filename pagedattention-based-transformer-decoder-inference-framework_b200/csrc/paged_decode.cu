@@ -522,7 +522,9 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
 
     auto produce = [&]() {
         if (!p_has) return;
-        if (lane == 0) {
+        // elect.sync, not `lane == 0`: the bulk copies keep their operands in uniform registers and are issued
+        // back to back (under lane == 0 ptxas wraps every UBLKCP in an R2UR + BRA.U.ANY loop; tests/test_sass.py)
+        if (elect_one()) {
             const int nvalid = (p_page >= 0) ? min(kUnitTok, p_rem) : 0;
             my_meta[p_st] = nvalid;
             const uint32_t bar = my_bar0 + p_st * 8;
