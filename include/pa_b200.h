@@ -27,6 +27,7 @@ extern "C" {
 #define PA_ERR_UNSUPPORTED (-2)  /* head_dim / tile_size / activation outside the built set */
 #define PA_ERR_WORKSPACE (-3)    /* workspace too small; see pa_decode_workspace_bytes */
 #define PA_ERR_NO_DEVICE (-4)    /* no sm_100 device is current */
+#define PA_ERR_NCCL (-5)         /* an NCCL call failed (pa_nccl_*) */
 
 #define PA_ACT_NONE 0
 #define PA_ACT_RELU 1
@@ -85,6 +86,11 @@ int pa_kv_append_f16(void* d_k_pool, void* d_v_pool, const int32_t* d_table, int
                      int num_heads, int num_tiles, int total_pages, int tile_size, int head_dim,
                      const void* d_new_k, const void* d_new_v, const int32_t* d_beam_ids,
                      const int32_t* d_positions, int R, pa_stream_t stream);
+/* fp32 rows into an fp32 pool (KVTileCache<float>): raw copy. */
+int pa_kv_append_f32(float* d_k_pool, float* d_v_pool, const int32_t* d_table, int num_beams,
+                     int num_heads, int num_tiles, int total_pages, int tile_size, int head_dim,
+                     const float* d_new_k, const float* d_new_v, const int32_t* d_beam_ids,
+                     const int32_t* d_positions, int R, pa_stream_t stream);
 int pa_kv_append_f32_f16(void* d_k_pool, void* d_v_pool, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, int tile_size,
                          int head_dim, const float* d_new_k, const float* d_new_v,
@@ -134,6 +140,9 @@ size_t pa_decode_workspace_bytes(int B, int num_heads, int head_dim, int num_til
  *       loads and math overlap.
  * _i8 / _i8_overlap: int8 K/V pages with per-(page,row) f32 scales, dequantised
  *       in the kernel as q/scale (int8_quant.cpp:46-57).
+ * _f32 / _f32_overlap: fp32 K/V pages -- KVTileCache<float>, the instantiation
+ *       AttentionCUDA::forward takes (attention_config.hpp:15, kv_tile_cache.cpp:127);
+ *       the same kernels on 4-byte elements.
  */
 int pa_paged_decode_f16(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
@@ -164,6 +173,20 @@ int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8_t* d_k
                                const float* d_rope, float* d_lse_out, void* d_workspace,
                                size_t workspace_bytes, pa_stream_t stream);
 
+int pa_paged_decode_f32(const float* d_q, float* d_out, const float* d_k_pool, const float* d_v_pool,
+                        const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                        int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_lens,
+                        int B, int T, int head_dim, int tile_size, float temperature,
+                        const float* d_rope, float* d_lse_out, void* d_workspace,
+                        size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_decode_f32_overlap(const float* d_q, float* d_out, const float* d_k_pool,
+                                const float* d_v_pool, const int32_t* d_table, int num_beams,
+                                int num_heads, int num_tiles, int total_pages,
+                                const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B,
+                                int T, int head_dim, int tile_size, float temperature,
+                                const float* d_rope, float* d_lse_out, void* d_workspace,
+                                size_t workspace_bytes, pa_stream_t stream);
+
 /* Beam-aware shared-prefix decode (north star; the reference's only hook is the
  * beam_ids[b] -> page-table-row indirection, ...fused.cu:22).  Rows b = g*beam_width ..
  * g*beam_width + beam_width-1 form beam group g.  Same results as pa_paged_decode_f16, but
@@ -188,7 +211,9 @@ int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_po
  * this rank's pages only, emitting UN-normalised partials for an LSE combine:
  *   d_part_m[b,h] = max_t s[t] (natural-log units; -inf if no key)
  *   d_part_l[b,h] = sum_t exp(s[t]-m),  d_part_o[b,h,:] = sum_t exp(s[t]-m) V[t,:]
- * `token_offset` is unused by the math (no positional terms) and reserved. */
+ * (no positional term enters the math, so a rank needs no token offset: its page-table rows simply hold
+ * its own tile range).  One launch: the streaming kernel merges each row when its last chunk finishes.
+ * _i8: int8 pages with per-(page,row) scales. */
 int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
                                 float* d_part_o, const void* d_k_pool, const void* d_v_pool,
                                 const int32_t* d_table, int num_beams, int num_heads,
@@ -196,6 +221,13 @@ int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part
                                 const int32_t* d_ctx_lens, int B, int T, int head_dim,
                                 int tile_size, float temperature, const float* d_rope,
                                 void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+int pa_paged_decode_i8_partial(const float* d_q, float* d_part_m, float* d_part_l, float* d_part_o,
+                               const int8_t* d_k_pool, const int8_t* d_v_pool, const float* d_k_scales,
+                               const float* d_v_scales, const int32_t* d_table, int num_beams,
+                               int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
+                               const int32_t* d_ctx_lens, int B, int T, int head_dim, int tile_size,
+                               float temperature, const float* d_rope, void* d_workspace,
+                               size_t workspace_bytes, pa_stream_t stream);
 
 /* LSE combine of n_parts partials (layout [n_parts][rows] for m/l and
  * [n_parts][rows][D] for o, as gathered from n_parts ranks):
@@ -229,10 +261,15 @@ int pa_batch_dequantize_i8(const int8_t* d_q, const float* d_scales, int rows, i
  * A [BATCH,M,K], B [BATCH,K,N], C [BATCH,M,N] row-major (format_tag::abc).
  * d_C_s8 and/or d_C_s32 may be NULL (at least one must be given); d_C_s32
  * receives the raw int32 accumulators (the bit-exact parity target).
- * tcgen05 kind::i8 tensor-core kernel; K % 16 == 0 and N % 16 == 0 required. */
+ * tcgen05 kind::i8 tensor-core kernel; K % 16 == 0 and N % 16 == 0 required.
+ * d_workspace: caller-owned scratch for split-K partial tiles, at least
+ * pa_gemm_i8_workspace_bytes(BATCH, M, N, K) bytes (0 = this shape never splits), 16-byte aligned.  The
+ * library owns no growable scratch (a pointer captured in a CUDA graph must stay valid; streams must not share
+ * it): NULL or too small a workspace makes the GEMM run unsplit -- same result, fewer CTAs. */
+size_t pa_gemm_i8_workspace_bytes(int BATCH, int M, int N, int K);
 int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH,
                int M, int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias,
-               int act, pa_stream_t stream);
+               int act, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
 
 /* Dynamic-quantisation form of the same GEMM, used by the INT8 decoder MLP ("int8_quant ->
  * dnnl_matmul_int8 -> dequant", attention_cpu/README.md:80-86):
@@ -244,6 +281,7 @@ int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_
  * pa_batch_minmax_scale feed this call directly. */
 int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f32, int BATCH, int M, int N,
                        int K, const float* d_a_qscales, float b_dequant, const float* d_bias, int act,
+                       void* d_workspace, size_t workspace_bytes,
                        pa_stream_t stream);
 
 /* ------------------------------------------------- decoder glue (row a14) */
@@ -259,9 +297,12 @@ int pa_embedding_i8(const int8_t* d_E, float qscale, const int32_t* d_ids, int r
 int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float* d_beta, int rows,
                       int hidden, float eps, float* d_out, pa_stream_t stream);
 /* decoder/mlp.hpp:23-41, one layer of the float MLP: out[r,n] = act(bias[n] + sum_k x[r,k]*W[k*N+n]),
- * act in {PA_ACT_NONE, PA_ACT_RELU}.  d_out must not alias d_x. */
+ * act in {PA_ACT_NONE, PA_ACT_RELU}.  d_out must not alias d_x.  d_workspace: caller-owned scratch for the
+ * K-slice partials, >= pa_linear_workspace_bytes(rows, K, N) bytes (NULL / too small: unsliced, same result
+ * up to the summation order). */
+size_t pa_linear_workspace_bytes(int rows, int K, int N);
 int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N,
-                  int act, float* d_out, pa_stream_t stream);
+                  int act, float* d_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
 /* logits[r,v] = dot(x[r,:], E[v,:]) against the (tied) embedding table E [vocab, hidden]
  * (the reference reads logits out of the hidden state, cuda_decoder.cu:58). */
 int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidden, int vocab,
@@ -338,7 +379,8 @@ int pa_paged_prefill_i8(const float* d_q, float* d_out, const int8_t* d_k_pool, 
                         size_t workspace_bytes, pa_stream_t stream);
 
 /* --------------------------------- inter-GPU split-KV exchange over peer memory */
-/* North-star long-context mode (the reference has no multi-device code).
+/* Exchange buffers: one per rank, pa_splitkv_exchange_bytes(world, rows, head_dim) bytes
+ * (uint4 [2 parity][world][rows][head_dim/2 + 1] flag-in-data packets, csrc/xchg.cuh).
  * pa_p2p_alloc: cudaMalloc'd, zero-filled exchange buffer + its 64-byte CUDA IPC handle;
  * pa_p2p_open: map a peer process's buffer (NVLink P2P); pa_p2p_close / pa_p2p_free. */
 size_t pa_splitkv_exchange_bytes(int world, int rows, int head_dim);
@@ -346,20 +388,15 @@ int pa_p2p_alloc(size_t bytes, void** d_ptr, unsigned char* handle64);
 int pa_p2p_open(const unsigned char* handle64, void** d_peer_ptr);
 int pa_p2p_close(void* d_peer_ptr);
 int pa_p2p_free(void* d_ptr);
-/* ONE kernel = exchange + combine: stores this rank's partial rows (as produced by
- * pa_paged_decode_f16_partial) into slot `rank` of every peer's exchange buffer
- * (d_peer_bufs: DEVICE array of `world` buffer base pointers, own buffer at [rank]),
- * publishes them with release.sys flags, waits for all ranks' rows and LSE-combines
- * them (same math as pa_lse_combine).  d_epochs: [rows] uint32 step counters in device
- * memory, zero-initialised once and advanced by the kernel itself (all ranks must call
- * in lock step; keeping the counter on the device makes the launch CUDA-graph
- * replayable).  *d_status (optional) is set to 1 if a peer did not arrive
- * within ~2 s (outputs are then undefined; the kernel never hangs the GPU). */
-/* Decode + exchange in TWO launches: pa_paged_decode_f16_overlap's streaming kernel over this
- * rank's pages, then the chunk-merge kernel whose epilogue performs the exchange above for
- * each (row, head) directly from registers (no partial round trip through HBM, no separate
- * collective).  d_out [B,H,D] holds the attention over ALL ranks' pages on every rank.  The
- * exchange buffers must have been sized for rows = B*num_heads. */
+/* Decode + row merge + exchange + combine in ONE launch: the streaming kernel over this rank's
+ * pages; the warp that finishes the last chunk of a row merges it and stores it into slot `rank`
+ * of every peer's exchange buffer (d_peer_bufs: device array [world] of mapped buffer pointers,
+ * this rank's own buffer at index `rank`) as 16-byte packets that carry their own epoch flag --
+ * sending never blocks; at the end of the same kernel every row's `world` partials are received
+ * from the local buffer and LSE-combined into d_out [B, H, D] (identical on every rank).
+ * d_epochs [B*H] u32: per-row step counters in device memory, zero-initialised once (the launch is
+ * CUDA-graph replayable); *d_status is set to 1, the row written as NaN and its epoch NOT advanced if a
+ * peer does not arrive within ~2 s.  Exchange buffers must be sized for rows = B*num_heads. */
 int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_pool,
                                 const void* d_v_pool, const int32_t* d_table, int num_beams,
                                 int num_heads, int num_tiles, int total_pages,
@@ -368,10 +405,35 @@ int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_
                                 float* d_lse_out, void* d_workspace, size_t workspace_bytes,
                                 void* const* d_peer_bufs, int rank, int world, uint32_t* d_epochs,
                                 int* d_status, pa_stream_t stream);
+int pa_paged_decode_i8_splitkv(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                               const int8_t* d_v_pool, const float* d_k_scales, const float* d_v_scales,
+                               const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                               int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_lens,
+                               int B, int T, int head_dim, int tile_size, float temperature,
+                               const float* d_rope, float* d_lse_out, void* d_workspace,
+                               size_t workspace_bytes, void* const* d_peer_bufs, int rank, int world,
+                               uint32_t* d_epochs, int* d_status, pa_stream_t stream);
+/* The same packet exchange as a stand-alone kernel after pa_paged_decode_*_partial: phase 1 sends
+ * every row (never blocks), phase 2 receives and combines.  head_dim in {64, 128}, world <= 32. */
 int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
                                 void* const* d_peer_bufs, int rank, int world, int rows,
                                 int head_dim, uint32_t* d_epochs, float* d_out, float* d_lse_out,
                                 int* d_status, pa_stream_t stream);
+
+/* --------------------------------- NCCL form of the exchange (the north star's baseline) */
+/* NCCL is loaded at run time (dlopen "libnccl.so.2"); PA_ERR_UNSUPPORTED when it is absent.
+ * pa_nccl_unique_id: rank 0 creates the 128-byte ncclUniqueId, the application distributes it;
+ * pa_nccl_init: ncclCommInitRank on the current device; pa_nccl_destroy.
+ * pa_nccl_allgather_combine: ncclAllGather of this rank's (m [rows], l [rows], O [rows, D]) into
+ * d_gather_ws (>= pa_nccl_gather_bytes) in the [n_parts][rows] layout of pa_lse_combine, then the
+ * combine kernel, all on `stream`. */
+int pa_nccl_unique_id(unsigned char* id128);
+int pa_nccl_init(const unsigned char* id128, int rank, int world, void** comm);
+int pa_nccl_destroy(void* comm);
+size_t pa_nccl_gather_bytes(int world, int rows, int head_dim);
+int pa_nccl_allgather_combine(void* comm, int world, const float* d_part_m, const float* d_part_l,
+                              const float* d_part_o, int rows, int head_dim, void* d_gather_ws,
+                              size_t gather_bytes, float* d_out, float* d_lse_out, pa_stream_t stream);
 
 #ifdef __cplusplus
 }

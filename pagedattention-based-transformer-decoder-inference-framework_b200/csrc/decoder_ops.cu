@@ -357,25 +357,29 @@ PA_API int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float
     PA_RETURN_LAUNCH_STATUS();
 }
 
-// K-slice partials of pa_linear_f32, one scratch buffer per device, grown on demand (stream-ordered reuse).
-static float* linear_scratch(size_t bytes) {
-    static float* p[64] = {};
-    static size_t cap[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (cap[dev] < bytes) {
-        if (p[dev]) cudaFree(p[dev]);
-        p[dev] = nullptr;
-        cap[dev] = 0;
-        if (cudaMalloc(&p[dev], bytes) != cudaSuccess) return nullptr;
-        cap[dev] = bytes;
-    }
-    return p[dev];
+// K-slice geometry of pa_linear_f32 (shared with pa_linear_workspace_bytes).
+static int linear_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
+    const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
+    // slice K until ~2 CTAs per SM stream the weights; every slice keeps >= 64 k-rows (8 per warp)
+    int nslices = (2 * sm_count + strips * chunks - 1) / (strips * chunks);
+    if (nslices > K / 64) nslices = K / 64;
+    if (nslices < 1) nslices = 1;
+    const int kslice = (K + nslices - 1) / nslices;
+    if (kslice_out) *kslice_out = kslice;
+    return (K + kslice - 1) / kslice;
 }
 
+PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
+    if (rows <= 0 || K <= 0 || N <= 0) return 0;
+    const DeviceInfo& di = device_info();
+    const int nslices = linear_slices(rows, K, N, di.ok ? di.sm_count : 148, nullptr);
+    return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
+}
+
+// The K-slice partials live in the CALLER's workspace (no library-owned scratch: a pointer captured in a CUDA
+// graph stays valid, streams never share it).  Without a large enough workspace the layer runs unsliced.
 PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
-                         float* d_out, pa_stream_t stream) {
+                         float* d_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_x && d_W && d_out && rows >= 0 && K > 0 && N > 0);
     PA_CHECK_ARG(act == PA_ACT_NONE || act == PA_ACT_RELU);
     PA_CHECK_ARG(d_x != d_out);
@@ -383,16 +387,16 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
     const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
-    // slice K until ~2 CTAs per SM stream the weights; every slice keeps >= 64 k-rows (8 per warp)
-    int nslices = (2 * di.sm_count + strips * chunks - 1) / (strips * chunks);
-    if (nslices > K / 64) nslices = K / 64;
-    if (nslices < 1) nslices = 1;
-    const int kslice = (K + nslices - 1) / nslices;
-    nslices = (K + kslice - 1) / kslice;
+    int kslice = K;
+    int nslices = linear_slices(rows, K, N, di.sm_count, &kslice);
     float* partial = nullptr;
     if (nslices > 1) {
-        partial = linear_scratch((size_t)nslices * rows * N * sizeof(float));
-        if (!partial) return (int)cudaErrorMemoryAllocation;
+        if (d_workspace && workspace_bytes >= (size_t)nslices * rows * N * sizeof(float)) {
+            partial = static_cast<float*>(d_workspace);
+        } else {
+            nslices = 1;
+            kslice = K;
+        }
     }
     dim3 grid((unsigned)strips, (unsigned)chunks, (unsigned)nslices);
     linear_kn_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, kslice, d_out, partial);

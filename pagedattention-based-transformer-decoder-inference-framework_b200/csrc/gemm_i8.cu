@@ -788,17 +788,24 @@ static bool make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Split-K partial-tile scratch, one per device, grown on demand (stream-ordered reuse: all
-// pa_gemm_i8 calls of a process are expected on one stream per device).
-struct Scratch {
-    int32_t* p = nullptr;
-    size_t bytes = 0;
+// Tile / split-K geometry shared by the launcher and pa_gemm_i8_workspace_bytes.
+struct Plan {
+    bool two_cta;
+    int n_slabs, m_chunks, ksplit, kb_per_split;
 };
-static Scratch& scratch_for_device() {
-    static Scratch s[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    return s[dev & 63];
+static Plan make_plan(int BATCH, int M, int N, int K, int sm_count) {
+    Plan p;
+    p.two_cta = M > BM && !(getenv("PA_GEMM_2CTA") && atoi(getenv("PA_GEMM_2CTA")) == 0);
+    p.n_slabs = p.two_cta ? (N + BN2 - 1) / BN2 : (N + BN - 1) / BN;
+    p.m_chunks = (M + 2 * BM - 1) / (2 * BM);
+    const int total_kb = (K + BK - 1) / BK;
+    const int64_t ctas = (int64_t)p.n_slabs * p.m_chunks * BATCH * (p.two_cta ? 2 : 1);
+    int ksplit = (int)(sm_count / ctas);
+    if (ksplit > total_kb / 8) ksplit = total_kb / 8;  // >= 8 K blocks (1 KiB of K) per split
+    if (ksplit < 1) ksplit = 1;
+    p.kb_per_split = (total_kb + ksplit - 1) / ksplit;
+    p.ksplit = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    return p;
 }
 
 }  // namespace gemm
@@ -809,7 +816,8 @@ using namespace pa::gemm;
 
 static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, float* d_C_f32, int32_t* d_C_s32,
                           int BATCH, int M, int N, int K, float alpha_host, const float* d_a_qscale,
-                          const float* d_bias, int act, pa_stream_t stream) {
+                          const float* d_bias, int act, void* d_workspace, size_t workspace_bytes,
+                          pa_stream_t stream) {
     PA_CHECK_ARG(d_A && d_B && (d_C_s8 || d_C_s32 || d_C_f32));
     PA_CHECK_ARG(BATCH > 0 && M > 0 && N > 0 && K > 0);
     PA_CHECK_ARG(!d_C_f32 || (uintptr_t)d_C_f32 % 16 == 0);
@@ -822,9 +830,9 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     if (!di.ok) return PA_ERR_NO_DEVICE;
     cudaStream_t st = as_stream(stream);
 
-    const bool two_cta = M > BM && !(getenv("PA_GEMM_2CTA") && atoi(getenv("PA_GEMM_2CTA")) == 0);
-    const int n_slabs = two_cta ? (N + BN2 - 1) / BN2 : (N + BN - 1) / BN;
-    const int m_chunks = (M + 2 * BM - 1) / (2 * BM);
+    const Plan plan = make_plan(BATCH, M, N, K, di.sm_count);
+    const bool two_cta = plan.two_cta;
+    const int n_slabs = plan.n_slabs, m_chunks = plan.m_chunks;
     const int m_tiles0 = M > BM ? 2 : 1;
     // Cluster multicast of A needs one M chunk (uniform m_tiles) and n_slabs divisible by CL.
     int CLs = 1;
@@ -876,28 +884,22 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     extern unsigned long long* pa_gemm_probe_buf;
     g.probe = pa_gemm_probe_buf;
 #endif
-    const int total_kb = (K + BK - 1) / BK;
-    const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH * (two_cta ? 2 : 1);
-    int ksplit = (int)(di.sm_count / ctas);
-    if (ksplit > total_kb / 8) ksplit = total_kb / 8;  // >= 8 K blocks (1 KiB of K) per split
-    if (ksplit < 1) ksplit = 1;
-    g.kb_per_split = (total_kb + ksplit - 1) / ksplit;
-    ksplit = (total_kb + g.kb_per_split - 1) / g.kb_per_split;
-    g.ksplit = ksplit;
+    // Split-K partial tiles live in the CALLER's workspace (pa_gemm_i8_workspace_bytes): the library owns no
+    // growable scratch, so pointers baked into a captured CUDA graph stay valid and streams never share it.
+    // Without a (large enough) workspace the GEMM runs unsplit: same result, fewer CTAs.
     const int64_t rows = (int64_t)BATCH * M;
+    int ksplit = plan.ksplit;
+    g.kb_per_split = plan.kb_per_split;
     if (ksplit > 1) {
-        Scratch& sc = scratch_for_device();
         const size_t need = (size_t)ksplit * rows * N * sizeof(int32_t);
-        if (sc.bytes < need) {
-            if (sc.p) cudaFree(sc.p);
-            sc.p = nullptr;
-            sc.bytes = 0;
-            cudaError_t e = cudaMalloc(&sc.p, need);
-            if (e != cudaSuccess) return (int)e;
-            sc.bytes = need;
+        if (d_workspace && workspace_bytes >= need && (uintptr_t)d_workspace % 16 == 0) {
+            g.acc_ws = static_cast<int32_t*>(d_workspace);
+        } else {
+            ksplit = 1;
+            g.kb_per_split = (K + BK - 1) / BK;
         }
-        g.acc_ws = sc.p;
     }
+    g.ksplit = ksplit;
     g.BATCH_rows = rows;
     const int epi = (ksplit > 1 || !(d_C_s8 || d_C_f32)) ? 0 : 1 + act;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
@@ -983,20 +985,27 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     return PA_OK;
 }
 
+PA_API size_t pa_gemm_i8_workspace_bytes(int BATCH, int M, int N, int K) {
+    if (BATCH <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
+    const DeviceInfo& di = device_info();
+    const Plan p = make_plan(BATCH, M, N, K, di.ok ? di.sm_count : 148);
+    return p.ksplit > 1 ? (size_t)p.ksplit * BATCH * M * N * sizeof(int32_t) : 0;
+}
+
 PA_API int pa_gemm_i8(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, int32_t* d_C_s32, int BATCH, int M,
                       int N, int K, float scaleA, float scaleB, float scaleC, const float* d_bias, int act,
-                      pa_stream_t stream) {
+                      void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_C_s8 || d_C_s32);
     PA_CHECK_ARG(scaleC != 0.f);
     // dnnl_matmul_int8.cpp:40, fp32, left to right
     return gemm_i8_launch(d_A, d_B, d_C_s8, nullptr, d_C_s32, BATCH, M, N, K, scaleA * scaleB / scaleC, nullptr,
-                          d_bias, act, stream);
+                          d_bias, act, d_workspace, workspace_bytes, stream);
 }
 
 PA_API int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f32, int BATCH, int M, int N, int K,
                               const float* d_a_qscale, float b_dequant, const float* d_bias, int act,
-                              pa_stream_t stream) {
+                              void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_C_f32 && d_a_qscale);
     return gemm_i8_launch(d_A, d_B, nullptr, d_C_f32, nullptr, BATCH, M, N, K, b_dequant, d_a_qscale, d_bias, act,
-                          stream);
+                          d_workspace, workspace_bytes, stream);
 }

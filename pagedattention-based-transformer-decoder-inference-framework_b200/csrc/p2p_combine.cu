@@ -1,117 +1,79 @@
-// p2p_combine.cu -- inter-GPU split-KV combine over NVLink peer memory (north-star long-context
-// mode).  The reference has no multi-device code; the exchange step is new.
+// p2p_combine.cu -- inter-GPU split-KV combine (north-star long-context mode).  The reference has
+// no multi-device code; the exchange step is new.
 //
-// Each rank holds a contiguous page range of ONE sequence and produces un-normalised partials
-// (m, l, O) per (row, head) with pa_paged_decode_f16_partial.  The message is tiny (D+2 floats per
-// row-head, 16.6 KB per rank at the Llama-7B shape), so the exchange is latency-bound: instead of
-// an NCCL all-gather followed by a combine kernel, ONE kernel
-//   1. stores this rank's partial row straight into slot `rank` of every peer's exchange buffer
-//      (plain st.global to the peer's NVLink-mapped address),
-//   2. publishes it with a release.sys flag per (src rank, row),
-//   3. acquires the flags of all source ranks for its row, and
-//   4. LSE-combines the `world` partials locally.
-// Rows are independent, so there is no grid-wide barrier: CTA `row` on every rank only waits for
-// CTA `row` of the other ranks.  Buffers are double-buffered by epoch parity (a rank can be at
-// most one step ahead of its slowest peer because step e+1's wait needs every peer's e+1 data,
-// which a peer only sends after its step-e kernel finished).
+// Each rank holds a contiguous page range of ONE sequence and produces un-normalised partials (m, l, O) per
+// (row, head).  The message is tiny (D+2 floats per row-head, 16.6 KB per rank at the Llama-7B shape), so the
+// exchange is latency-bound.  Three forms, all with the same result:
+//   * pa_paged_decode_{f16,i8}_splitkv (paged_decode.cu): decode, row merge, send and receive+combine in ONE
+//     launch -- the warp that finishes a row's last chunk stores it into every peer's buffer as flag-in-data
+//     packets (xchg.cuh), rows are received at the end of the same kernel;
+//   * pa_splitkv_exchange_combine (here): the same packet exchange as a stand-alone kernel after
+//     pa_paged_decode_*_partial -- phase 1 sends all rows (never blocks), phase 2 receives and combines;
+//   * pa_nccl_allgather_combine (here): the north star's baseline -- ncclAllGather of (m, l, O) over NVLink /
+//     NVSwitch followed by pa_lse_combine's kernel.  NCCL is loaded at run time (dlopen "libnccl.so.2": inside
+//     a PyTorch process that is the library torch already loaded), so libpa_b200.so has no link-time dependency.
+#include <dlfcn.h>
+
 #include <cstring>
 
 #include "pa_common.cuh"
+#include "xchg.cuh"
 
 namespace pa {
 
-// Exchange buffer layout (per rank, identical on all ranks):
-//   data  : [2 parity][world src][rows][D + 2] float   (O[0..D), m, l)
-//   flags : [2 parity][world src][rows] uint32 (epoch of the data in the slot)
-__host__ __device__ inline size_t xbuf_data_floats(int world, int rows, int D) {
-    return (size_t)2 * world * rows * (D + 2);
-}
-__host__ __device__ inline size_t xbuf_bytes(int world, int rows, int D) {
-    return xbuf_data_floats(world, rows, D) * sizeof(float) + (size_t)2 * world * rows * sizeof(uint32_t);
+// grid-stride over rows, one warp per row: all sends first, then all receives (a send never waits, so no
+// ordering between ranks or CTAs is assumed and any number of rows fits any grid).
+template <int D>
+__global__ void __launch_bounds__(256) splitkv_exchange_combine_kernel(
+    const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
+    uint8_t* const* __restrict__ peers, int rank, int world, int rows, uint32_t* __restrict__ epochs,
+    float* __restrict__ out, float* __restrict__ lse_out, int* __restrict__ status) {
+    constexpr int VEC = D / 32;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int row = gw; row < rows; row += nw) {
+        float O[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) O[e] = po[(size_t)row * D + lane * VEC + e];
+        xchg::send_row<D>(peers, epochs, rank, world, rows, row, O, pm[row], pl[row], lane);
+    }
+    for (int row = gw; row < rows; row += nw)
+        xchg::recv_row<D>(peers, epochs, rank, world, rows, row, out, lse_out, status, lane);
 }
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_volatile_f32(const float* p) {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void splitkv_exchange_combine_kernel(const float* __restrict__ pm, const float* __restrict__ pl,
-                                                const float* __restrict__ po, uint8_t* const* __restrict__ peers,
-                                                int rank, int world, int rows, int D, uint32_t* __restrict__ epochs,
-                                                long long timeout_cycles, float* __restrict__ out,
-                                                float* __restrict__ lse_out, int* __restrict__ status) {
-    extern __shared__ float sm[];  // [world] m, [world] l
-    const int row = blockIdx.x;
-    // Per-row epoch counter in device memory (so the launch is CUDA-graph replayable): CTA `row` is
-    // the only reader/writer of epochs[row] on this rank; all ranks advance in lock step.
-    const uint32_t epoch = epochs[row] + 1u;
-    const int par = epoch & 1u;
-    const size_t row_stride = D + 2;
-    const size_t slot = ((size_t)(par * world + rank) * rows + row) * row_stride;
-    const size_t flag_idx = (size_t)(par * world + rank) * rows + row;
-    const size_t data_bytes = xbuf_data_floats(world, rows, D) * sizeof(float);
-
-    // 1. scatter my partial row to every rank (self included)
-    const float m_mine = pm[row], l_mine = pl[row];
-    for (int p = 0; p < world; ++p) {
-        float* dst = reinterpret_cast<float*>(peers[p]) + slot;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = po[(size_t)row * D + d];
-        if (threadIdx.x == 0) {
-            dst[D] = m_mine;
-            dst[D + 1] = l_mine;
+// ---- NCCL through dlopen -------------------------------------------------------------------------------
+struct NcclId128 {  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+    char b[128];
+};
+struct NcclApi {
+    // ncclResult_t is an int enum (0 = success); ncclFloat = 7.
+    int (*GetUniqueId)(void*);
+    int (*CommInitRank)(void**, int, NcclId128, int);
+    int (*CommDestroy)(void*);
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    bool ok = false;
+};
+static NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+            api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+            api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GroupStart &&
+                     api.GroupEnd;
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish
-    if (threadIdx.x < world) {
-        uint32_t* f = reinterpret_cast<uint32_t*>(peers[threadIdx.x] + data_bytes) + flag_idx;
-        st_release_sys(f, epoch);
-    }
-    // 3. wait for every source rank's row
-    uint8_t* mine = peers[rank];
-    bool ok = true;
-    if (threadIdx.x < world) {
-        const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + data_bytes) +
-                            (size_t)(par * world + threadIdx.x) * rows + row;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) != epoch) {
-            if (clock64() - t0 > timeout_cycles) {
-                ok = false;
-                break;
-            }
-        }
-        if (!ok && status) atomicExch(status, 1);
-        const float* src = reinterpret_cast<const float*>(mine) + ((size_t)(par * world + threadIdx.x) * rows + row) * row_stride;
-        sm[threadIdx.x] = ok ? ld_volatile_f32(src + D) : -INFINITY;
-        sm[world + threadIdx.x] = ok ? ld_volatile_f32(src + D + 1) : 0.f;
-    }
-    __syncthreads();
-    // 4. combine (same math as lse_combine_kernel / oracle orc_lse_combine)
-    float M = -INFINITY;
-    for (int s = 0; s < world; ++s) M = fmaxf(M, sm[s]);
-    float L = 0.f;
-    for (int s = 0; s < world; ++s) L += (sm[s] == -INFINITY) ? 0.f : sm[world + s] * __expf(sm[s] - M);
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float O = 0.f;
-        for (int s = 0; s < world; ++s) {
-            const float w = (sm[s] == -INFINITY) ? 0.f : __expf(sm[s] - M);
-            const float* src = reinterpret_cast<const float*>(mine) + ((size_t)(par * world + s) * rows + row) * row_stride;
-            O = fmaf(ld_volatile_f32(src + d), w, O);
-        }
-        out[(size_t)row * D + d] = O / (L + 1e-6f);
-    }
-    if (threadIdx.x == 0 && lse_out) lse_out[row] = (L > 0.f) ? M + logf(L) : -INFINITY;
-    if (threadIdx.x == 0) epochs[row] = epoch;
+    return api;
 }
 
 }  // namespace pa
@@ -120,9 +82,8 @@ using namespace pa;
 
 PA_API size_t pa_splitkv_exchange_bytes(int world, int rows, int head_dim) {
     if (world <= 0 || rows <= 0 || head_dim <= 0) return 0;
-    return xbuf_bytes(world, rows, head_dim);
+    return xchg::buffer_bytes(world, rows, head_dim);
 }
-
 // cudaMalloc'd (IPC-exportable), zero-filled buffer + its 64-byte IPC handle.
 PA_API int pa_p2p_alloc(size_t bytes, void** d_ptr, unsigned char* handle64) {
     PA_CHECK_ARG(bytes > 0 && d_ptr && handle64);
@@ -168,13 +129,71 @@ PA_API int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_par
                                        uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
                                        pa_stream_t stream) {
     PA_CHECK_ARG(d_part_m && d_part_l && d_part_o && d_peer_bufs && d_out && d_epochs);
-    PA_CHECK_ARG(world > 0 && world <= 64 && rank >= 0 && rank < world && rows >= 0 && head_dim > 0);
+    PA_CHECK_ARG(world > 0 && world <= 32 && rank >= 0 && rank < world && rows >= 0);
+    if (head_dim != 64 && head_dim != 128) return PA_ERR_UNSUPPORTED;
     if (rows == 0) return PA_OK;
-    int threads = head_dim < 64 ? 64 : (head_dim > 256 ? 256 : head_dim);
-    if (threads < world) threads = 64;
-    const long long timeout_cycles = 4000000000ll;  // ~2 s: a missing peer must not hang the GPU
-    splitkv_exchange_combine_kernel<<<rows, threads, 2 * world * sizeof(float), as_stream(stream)>>>(
-        d_part_m, d_part_l, d_part_o, reinterpret_cast<uint8_t* const*>(d_peer_bufs), rank, world, rows, head_dim,
-        d_epochs, timeout_cycles, d_out, d_lse_out, d_status);
+    const DeviceInfo& di = device_info();
+    int blocks = (rows + 7) / 8;
+    if (di.ok && blocks > di.sm_count * 8) blocks = di.sm_count * 8;  // every CTA resident; rows are grid-strided
+    uint8_t* const* peers = reinterpret_cast<uint8_t* const*>(d_peer_bufs);
+    if (head_dim == 128)
+        splitkv_exchange_combine_kernel<128><<<blocks, 256, 0, as_stream(stream)>>>(
+            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status);
+    else
+        splitkv_exchange_combine_kernel<64><<<blocks, 256, 0, as_stream(stream)>>>(
+            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status);
     PA_RETURN_LAUNCH_STATUS();
+}
+
+// ---- NCCL form (SURVEY 8b "pa_nccl_* init / allgather-combine", 8e) ---------------------------------------
+PA_API int pa_nccl_unique_id(unsigned char* id128) {
+    PA_CHECK_ARG(id128);
+    NcclApi& n = nccl();
+    if (!n.ok) return PA_ERR_UNSUPPORTED;
+    return n.GetUniqueId(id128) == 0 ? PA_OK : PA_ERR_NCCL;
+}
+
+PA_API int pa_nccl_init(const unsigned char* id128, int rank, int world, void** comm) {
+    PA_CHECK_ARG(id128 && comm && world > 0 && rank >= 0 && rank < world);
+    NcclApi& n = nccl();
+    if (!n.ok) return PA_ERR_UNSUPPORTED;
+    NcclId128 id;
+    memcpy(id.b, id128, 128);
+    return n.CommInitRank(comm, world, id, rank) == 0 ? PA_OK : PA_ERR_NCCL;
+}
+
+PA_API int pa_nccl_destroy(void* comm) {
+    PA_CHECK_ARG(comm);
+    NcclApi& n = nccl();
+    if (!n.ok) return PA_ERR_UNSUPPORTED;
+    return n.CommDestroy(comm) == 0 ? PA_OK : PA_ERR_NCCL;
+}
+
+PA_API size_t pa_nccl_gather_bytes(int world, int rows, int head_dim) {
+    if (world <= 0 || rows <= 0 || head_dim <= 0) return 0;
+    return (size_t)world * rows * (head_dim + 2) * sizeof(float);
+}
+
+// Three all-gathers in one NCCL group straight into the [n_parts][rows] / [n_parts][rows][D] layout of
+// pa_lse_combine (no pack / unpack passes), then the combine kernel, all on `stream`.
+PA_API int pa_nccl_allgather_combine(void* comm, int world, const float* d_part_m, const float* d_part_l,
+                                     const float* d_part_o, int rows, int head_dim, void* d_gather_ws,
+                                     size_t gather_bytes, float* d_out, float* d_lse_out, pa_stream_t stream) {
+    PA_CHECK_ARG(comm && d_part_m && d_part_l && d_part_o && d_gather_ws && d_out && world > 0 && rows >= 0 && head_dim > 0);
+    PA_CHECK_ARG(gather_bytes >= pa_nccl_gather_bytes(world, rows, head_dim));
+    if (rows == 0) return PA_OK;
+    NcclApi& n = nccl();
+    if (!n.ok) return PA_ERR_UNSUPPORTED;
+    float* gm = static_cast<float*>(d_gather_ws);
+    float* gl = gm + (size_t)world * rows;
+    float* go = gl + (size_t)world * rows;
+    cudaStream_t st = as_stream(stream);
+    constexpr int kNcclFloat = 7;
+    int rc = n.GroupStart();
+    rc |= n.AllGather(d_part_m, gm, (size_t)rows, kNcclFloat, comm, st);
+    rc |= n.AllGather(d_part_l, gl, (size_t)rows, kNcclFloat, comm, st);
+    rc |= n.AllGather(d_part_o, go, (size_t)rows * head_dim, kNcclFloat, comm, st);
+    rc |= n.GroupEnd();
+    if (rc != 0) return PA_ERR_NCCL;
+    return pa_lse_combine(gm, gl, go, world, rows, head_dim, d_out, d_lse_out, stream);
 }

@@ -109,7 +109,8 @@ __global__ void kv_gather_kernel(const uint8_t* __restrict__ pool, uint8_t* __re
 
 // Append.  One warp per (row r, head h).  MODE 0: raw copy of elem_bytes rows
 // (fp16 in, fp16 pool); MODE 1: f32 -> f16 round-to-nearest-even; MODE 2: f32 -> int8
-// with the per-row minmax scale (int8_quant.cpp:59-64 then :15-28).
+// with the per-row minmax scale (int8_quant.cpp:59-64 then :15-28); MODE 3: raw copy of f32 rows into an
+// fp32 pool (KVTileCache<float>, kv_tile_cache.cpp:127).
 template <int MODE>
 __global__ void kv_append_kernel(void* __restrict__ k_pool, void* __restrict__ v_pool,
                                  float* __restrict__ k_scales, float* __restrict__ v_scales,
@@ -133,7 +134,16 @@ __global__ void kv_append_kernel(void* __restrict__ k_pool, void* __restrict__ v
     const int64_t dst_el = ((int64_t)page * tile_size + row) * head_dim;
     const int64_t src_el = ((int64_t)r * num_heads + h) * head_dim;
 
-    if (MODE == 0) {
+    if (MODE == 3) {
+        const float* sk = static_cast<const float*>(new_k) + src_el;
+        const float* sv = static_cast<const float*>(new_v) + src_el;
+        float* dk = static_cast<float*>(k_pool) + dst_el;
+        float* dv = static_cast<float*>(v_pool) + dst_el;
+        for (int d = lane * 4; d < head_dim; d += 128) {
+            *reinterpret_cast<uint4*>(dk + d) = *reinterpret_cast<const uint4*>(sk + d);
+            *reinterpret_cast<uint4*>(dv + d) = *reinterpret_cast<const uint4*>(sv + d);
+        }
+    } else if (MODE == 0) {
         const __half* sk = static_cast<const __half*>(new_k) + src_el;
         const __half* sv = static_cast<const __half*>(new_v) + src_el;
         __half* dk = static_cast<__half*>(k_pool) + dst_el;
@@ -229,6 +239,7 @@ PA_API const char* pa_error_string(int status) {
         case PA_ERR_UNSUPPORTED: return "pa_b200: unsupported shape (head_dim in {64,128}, tile_size % 16 == 0)";
         case PA_ERR_WORKSPACE: return "pa_b200: workspace too small";
         case PA_ERR_NO_DEVICE: return "pa_b200: no sm_100 CUDA device is current";
+        case PA_ERR_NCCL: return "pa_b200: an NCCL call failed";
         default: break;
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -324,6 +335,15 @@ PA_API int pa_kv_append_f16(void* d_k_pool, void* d_v_pool, const int32_t* d_tab
                             const int32_t* d_beam_ids, const int32_t* d_positions, int R,
                             pa_stream_t stream) {
     return launch_append<0>(d_k_pool, d_v_pool, nullptr, nullptr, d_table, num_beams, num_heads,
+                            num_tiles, total_pages, tile_size, head_dim, d_new_k, d_new_v,
+                            d_beam_ids, d_positions, R, stream);
+}
+
+PA_API int pa_kv_append_f32(float* d_k_pool, float* d_v_pool, const int32_t* d_table, int num_beams,
+                            int num_heads, int num_tiles, int total_pages, int tile_size, int head_dim,
+                            const float* d_new_k, const float* d_new_v, const int32_t* d_beam_ids,
+                            const int32_t* d_positions, int R, pa_stream_t stream) {
+    return launch_append<3>(d_k_pool, d_v_pool, nullptr, nullptr, d_table, num_beams, num_heads,
                             num_tiles, total_pages, tile_size, head_dim, d_new_k, d_new_v,
                             d_beam_ids, d_positions, R, stream);
 }

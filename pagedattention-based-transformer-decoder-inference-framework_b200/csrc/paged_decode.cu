@@ -26,6 +26,7 @@
 
 #include "mma_utils.cuh"
 #include "pa_common.cuh"
+#include "xchg.cuh"
 
 namespace pa {
 
@@ -61,14 +62,15 @@ struct DecodeArgs {
     uint32_t* xch_epochs;       // [rows] step counters
     int* xch_status;
     int xch_rank, xch_world;
-    int all_rows_in_ws;  // combine kernel: merge rows of a single chunk too (exchange / group kernels)
+    int all_rows_in_ws;  // combine kernel: merge rows of a single chunk too (group kernel)
+    unsigned int* row_done;  // streaming kernel: per-row count of finished chunks (the last one merges the row)
     const int* row_prefix;    // [B+1] chunk prefix per row, precomputed in global memory (group kernel, ragged)
     const int* group_prefix;  // [groups+1] chunk prefix per beam group (max over its rows)
 };
 
 template <int D, int KV>
 struct Cfg {
-    static constexpr int ES = KV == 0 ? 2 : 1;                 // bytes per element
+    static constexpr int ES = KV == 0 ? 2 : (KV == 1 ? 1 : 4);  // bytes per element: fp16, int8, fp32 pools
     static constexpr int ROWB = D * ES;                        // bytes per token row
     static constexpr int VB = (ROWB / 8 >= 16) ? 16 : ROWB / 8;  // bytes per lane vector
     static constexpr int NV = ROWB / (8 * VB);                 // vectors per lane per row
@@ -77,7 +79,7 @@ struct Cfg {
     static constexpr int WPV = VB / 4;
     static constexpr int W = NV * WPV;                         // 32-bit words per lane per row
     static constexpr int UNIT_BYTES = kUnitTok * ROWB;         // one K (or V) unit
-    static constexpr int SCALE_BYTES = KV == 0 ? 0 : kUnitTok * 4;
+    static constexpr int SCALE_BYTES = KV == 1 ? kUnitTok * 4 : 0;
     static constexpr int STAGE_BYTES = 2 * UNIT_BYTES + 2 * SCALE_BYTES;
     // head dim owned by (chunk lane c, element e)
     __device__ static __forceinline__ int dim_of(int c, int e) {
@@ -100,7 +102,10 @@ struct Acc {
 
 template <int KV, int W>
 __device__ __forceinline__ void words_to_float(const uint32_t (&w)[W], float* f) {
-    if (KV == 0) {
+    if (KV == 2) {  // fp32 pools (KVTileCache<float>, kv_tile_cache.cpp:127): the words are the values
+#pragma unroll
+        for (int i = 0; i < W; ++i) f[i] = __uint_as_float(w[i]);
+    } else if (KV == 0) {
 #pragma unroll
         for (int i = 0; i < W; ++i) {
             float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
@@ -293,7 +298,7 @@ __device__ __forceinline__ float load_q(const DecodeArgs& a, int64_t row, int c,
         q[e] = x0 * a.qscale;
         q[e + 1] = x1 * a.qscale;
     }
-    if (KV == 0) return 0.f;
+    if (KV != 1) return 0.f;
     // int8 pages: fold the +256 offset of the PRMT conversion (words_to_float) out of the inner loop
     float qs = 0.f;
 #pragma unroll
@@ -374,9 +379,77 @@ __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeAr
         unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
     }
 
-    const bool final_row = (a.num_splits == 1);  // (the host forces >= 2 splits when the exchange epilogue is on)
+    const bool final_row = (a.num_splits == 1);
     cta_merge_emit<D, KV, NW>(red, acc, warp, lane, a, final_row ? kEmitFinal : kEmitWorkspace, row,
                               row * a.num_splits + split);
+}
+
+// ---- row merge by ONE warp (streaming kernel: the warp that finishes the LAST chunk of a row merges it) ----
+// Reads the row's `nc` chunk partials (slots s0 .. s0+nc, log2-domain m) straight from L2 (ld.global.cg: they
+// were written by other SMs), lane l ends up with O for dims l*VEC .. l*VEC+VEC and the row's (M, L).
+__device__ __forceinline__ float ldcg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int D>
+__device__ __forceinline__ void merge_row_warp(const DecodeArgs& a, int64_t s0, int nc, int lane, float& M, float& L,
+                                               float (&O)[D / 32]) {
+    constexpr int VEC = D / 32;
+    float mloc = -INFINITY;
+    for (int i = lane; i < nc; i += 32) mloc = fmaxf(mloc, ldcg_f32(a.ws_m + s0 + i));
+    M = warp_max(mloc);
+    float Lw = 0.f;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) O[e] = 0.f;
+    for (int base = 0; base < nc; base += 32) {
+        const int i = base + lane;
+        float wt = 0.f;
+        if (i < nc) {
+            const float mj = ldcg_f32(a.ws_m + s0 + i);
+            wt = (mj == -INFINITY) ? 0.f : fast_exp2(mj - M);
+            Lw = fmaf(ldcg_f32(a.ws_l + s0 + i), wt, Lw);
+        }
+        const int cnt = min(32, nc - base);
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const float w = __shfl_sync(0xffffffffu, wt, t);
+            const float* src = a.ws_o + (s0 + base + t) * D + lane * VEC;
+            if (VEC == 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
+                O[2 % VEC] = fmaf(v.z, w, O[2 % VEC]); O[3 % VEC] = fmaf(v.w, w, O[3 % VEC]);
+            } else {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
+            }
+        }
+    }
+    L = warp_sum(Lw);
+}
+
+// Final / partial / exchange emit of a merged row held as above (M in log2 units).
+template <int D>
+__device__ __forceinline__ void emit_merged_row(const DecodeArgs& a, int64_t row, int lane, float M, float L,
+                                                const float (&O)[D / 32]) {
+    constexpr int VEC = D / 32;
+    if (a.xch_peers) {  // send only (never blocks); the row is received and combined at the end of the kernel
+        xchg::send_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, (int64_t)a.B * a.H, row, O, M * kLn2, L, lane);
+        return;
+    }
+    if (a.part_m) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
+        if (lane == 0) {
+            a.part_m[row] = M * kLn2;  // natural-log units at the API
+            a.part_l[row] = L;
+        }
+        return;
+    }
+    const float inv = 1.f / (L + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = O[e] * inv;
+    if (lane == 0 && a.lse_out) a.lse_out[row] = (L > 0.f) ? (M + log2f(L)) * kLn2 : -INFINITY;
 }
 
 // ---------------------------------------------------------------- overlap (a2)
@@ -620,49 +693,69 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         }
         // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
         warp_merge<D, KV>(acc);
+        const bool final_row = (nc == 1) && !a.xch_peers;
+        if (final_row) {
+            if (lane < 8) {
+                if (!a.part_m) {
+                    const float inv = 1.f / (acc.l + 1e-6f);
+#pragma unroll
+                    for (int e = 0; e < C::E; ++e) a.out[row * D + C::dim_of(lane, e)] = acc.o[e] * inv;
+                    if (lane == 0 && a.lse_out)
+                        a.lse_out[row] = (acc.l > 0.f) ? (acc.m + log2f(acc.l)) * kLn2 : -INFINITY;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < C::E; ++e) a.part_o[row * D + C::dim_of(lane, e)] = acc.o[e];
+                    if (lane == 0) {
+                        a.part_m[row] = acc.m * kLn2;
+                        a.part_l[row] = acc.l;
+                    }
+                }
+            }
+            continue;
+        }
         if (lane < 8) {
-            const bool final_row = (nc == 1) && !a.xch_peers;
-            if (final_row && !a.part_m) {
-                const float inv = 1.f / (acc.l + 1e-6f);
 #pragma unroll
-                for (int e = 0; e < C::E; ++e) a.out[row * D + C::dim_of(lane, e)] = acc.o[e] * inv;
-                if (lane == 0 && a.lse_out)
-                    a.lse_out[row] = (acc.l > 0.f) ? (acc.m + log2f(acc.l)) * kLn2 : -INFINITY;
-            } else if (final_row) {
-#pragma unroll
-                for (int e = 0; e < C::E; ++e) a.part_o[row * D + C::dim_of(lane, e)] = acc.o[e];
-                if (lane == 0) {
-                    a.part_m[row] = acc.m * kLn2;
-                    a.part_l[row] = acc.l;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < C::E; ++e) a.ws_o[id * D + C::dim_of(lane, e)] = acc.o[e];
-                if (lane == 0) {
-                    a.ws_m[id] = acc.m;
-                    a.ws_l[id] = acc.l;
-                }
+            for (int e = 0; e < C::E; ++e) a.ws_o[id * D + C::dim_of(lane, e)] = acc.o[e];
+            if (lane == 0) {
+                a.ws_m[id] = acc.m;
+                a.ws_l[id] = acc.l;
+            }
+        }
+        if (a.row_done) {
+            // The warp that completes the LAST chunk of a row merges the row here (no second launch): partial
+            // visible device-wide -> count -> the last arrival reads all nc partials back from L2.
+            __threadfence();
+            __syncwarp();
+            unsigned int prev = 0;
+            if (lane == 0) prev = atomicAdd(a.row_done + row, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev + 1u == (unsigned)nc) {
+                __threadfence();
+                float M, L, O[D / 32];
+                merge_row_warp<D>(a, id - j, nc, lane, M, L, O);
+                emit_merged_row<D>(a, row, lane, M, L, O);
             }
         }
     }
-}
-
-// Exchange-buffer layout shared with p2p_combine.cu.
-__device__ __forceinline__ size_t xbuf_data_floats_dev(int world, int64_t rows, int D) {
-    return (size_t)2 * world * rows * (D + 2);
-}
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_volatile_f32g(const float* p) {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
+    // Rows without a single chunk (context length 0) are emitted as "no keys": out = 0, lse = -inf.
+    if (a.row_done && (cm.prefix || cm.NC == 0)) {
+        const int64_t nrows0 = (int64_t)a.B * Hh;
+        for (int64_t row = gw; row < nrows0; row += total_warps) {
+            if (cm.nchunks_of((int)(row / Hh)) != 0) continue;
+            float O[D / 32];
+#pragma unroll
+            for (int e = 0; e < D / 32; ++e) O[e] = 0.f;
+            emit_merged_row<D>(a, row, lane, -INFINITY, 0.f, O);
+        }
+    }
+    // ---- split-KV across GPUs: receive + combine.  Every row's partial has been (or will be) SENT by the warp
+    // that merged it, on this rank and on the peers; sends never block, so polling here cannot deadlock. ----
+    if (a.xch_peers) {
+        const int64_t nrows = (int64_t)a.B * Hh;
+        for (int64_t row = gw; row < nrows; row += total_warps)
+            xchg::recv_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, a.out, a.lse_out,
+                              a.xch_status, lane);
+    }
 }
 
 // Merge the per-chunk partials of every row (rows of a single chunk were finished by the main
@@ -670,8 +763,8 @@ __device__ __forceinline__ float ld_volatile_f32g(const float* p) {
 // 8 / WPR rows: WPR warps share a row's chunks (strided), each lane owns D/32 output dims, chunk
 // weights are computed by lanes in parallel and broadcast with shuffles, so a row of 256 chunks
 // (C5: 16K tokens per GPU) costs ~32 dependent 512-byte loads per warp instead of 512 serial
-// scalar loads per thread.  With xch_peers set, the warp that owns the merged row also performs the
-// inter-GPU exchange (store to peers, release flag, acquire all ranks' flags, LSE combine).
+// scalar loads per thread.  Used by the split-KV grid kernel and the beam-group kernel; the streaming kernel
+// merges its rows itself (merge_row_warp).
 template <int D>
 __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a, int cu, int wpr) {
     constexpr int VEC = D / 32;
@@ -772,71 +865,6 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
     }
     if (skip || wsub != 0) return;
     // ---- emit: this warp holds the merged row (M log2-domain, L, O[VEC] for dims lane*VEC..) ----
-    if (a.xch_peers) {
-        const int world = a.xch_world, rank = a.xch_rank;
-        const uint32_t epoch = a.xch_epochs[row] + 1u;
-        const int par = epoch & 1u;
-        const size_t stride = D + 2;
-        const size_t data_bytes = xbuf_data_floats_dev(world, nrows, D) * sizeof(float);
-        const size_t slot = ((size_t)(par * world + rank) * nrows + row) * stride;
-        const float m_nat = M * kLn2;
-        for (int p = 0; p < world; ++p) {
-            float* dst = reinterpret_cast<float*>(a.xch_peers[p]) + slot;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) dst[lane * VEC + e] = O[e];
-            if (lane == 0) {
-                dst[D] = m_nat;
-                dst[D + 1] = L;
-            }
-        }
-        __threadfence_system();
-        __syncwarp();
-        float ms = -INFINITY, ls = 0.f;
-        for (int s = lane; s < world; s += 32) {  // world <= 32 in practice; loop keeps it general
-            st_release_sys_u32(reinterpret_cast<uint32_t*>(a.xch_peers[s] + data_bytes) +
-                                   (size_t)(par * world + rank) * nrows + row, epoch);
-        }
-        uint8_t* mine = a.xch_peers[rank];
-        bool ok = true;
-        if (lane < world) {
-            const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + data_bytes) +
-                                (size_t)(par * world + lane) * nrows + row;
-            const long long t0 = clock64();
-            while (ld_acquire_sys_u32(f) != epoch) {
-                if (clock64() - t0 > 4000000000ll) {  // ~2 s: never hang the GPU on a missing peer
-                    ok = false;
-                    break;
-                }
-            }
-            if (!ok && a.xch_status) atomicExch(a.xch_status, 1);
-            const float* src = reinterpret_cast<const float*>(mine) +
-                               ((size_t)(par * world + lane) * nrows + row) * stride;
-            ms = ok ? ld_volatile_f32g(src + D) : -INFINITY;
-            ls = ok ? ld_volatile_f32g(src + D + 1) : 0.f;
-        }
-        __syncwarp();
-        const float Mg = warp_max(ms);
-        const float wl = (ms == -INFINITY) ? 0.f : __expf(ms - Mg);
-        const float Lg = warp_sum(ls * wl);
-        float Og[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) Og[e] = 0.f;
-        for (int sidx = 0; sidx < world; ++sidx) {
-            const float w = __shfl_sync(0xffffffffu, wl, sidx);
-            const float* src = reinterpret_cast<const float*>(mine) +
-                               ((size_t)(par * world + sidx) * nrows + row) * stride;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) Og[e] = fmaf(ld_volatile_f32g(src + lane * VEC + e), w, Og[e]);
-        }
-        const float inv = 1.f / (Lg + 1e-6f);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = Og[e] * inv;
-        if (lane == 0) {
-            if (a.lse_out) a.lse_out[row] = (Lg > 0.f) ? Mg + logf(Lg) : -INFINITY;
-            a.xch_epochs[row] = epoch;
-        }
-        return;
-    }
     if (a.part_m) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
@@ -1277,8 +1305,9 @@ struct OvCfg {
 #ifndef PA_OV_I8_WARPS
 #define PA_OV_I8_WARPS 16
 #endif
-    static constexpr int NW = (KV == 1 && D == 128) ? PA_OV_I8_WARPS : 8;
-    static constexpr int S = (D == 128) ? (KV == 0 ? 3 : (NW == 16 ? 3 : 6)) : (KV == 0 ? 6 : 8);
+    // fp32 pools (KV == 2): 16 KB (D = 128) / 8 KB (D = 64) per stage -> 4 / 8 warps x 3 stages = 192 KB.
+    static constexpr int NW = KV == 2 ? (D == 128 ? 4 : 8) : ((KV == 1 && D == 128) ? PA_OV_I8_WARPS : 8);
+    static constexpr int S = KV == 2 ? 3 : ((D == 128) ? (KV == 0 ? 3 : (NW == 16 ? 3 : 6)) : (KV == 0 ? 6 : 8));
 };
 
 static int units_of_ctx_host(int T, int cap) {
@@ -1296,11 +1325,22 @@ static int choose_splits(int64_t rows, int max_units, int sm_count) {
     return (int)ns;
 }
 
-// Units per chunk of the overlap kernel: 16 (128 KiB of fp16 K+V at D=128) when that still
-// yields >= 4 chunks per resident warp, fewer for small problems so every warp gets work.
-static int choose_cu(int64_t rows, int max_units, int sm_count) {
-    const int64_t warps = (int64_t)sm_count * kOvWarps;
-    int64_t cu = (rows * max_units) / (4 * warps);
+// Units per chunk of the overlap kernel (nw = streaming warps per CTA of the instance that will run).
+//  * short jobs with few rows (one GPU's share of a long sequence, C5: 32 rows x 1024 units): ONE chunk per
+//    warp, handed out statically (the first chunk of a warp is its global warp index) -- no atomics, no
+//    per-chunk overheads, every warp streams the same number of units and the row merge happens in-kernel;
+//  * otherwise 16 units (128 KiB of fp16 K+V at D=128) when that still yields >= 4 chunks per resident warp,
+//    fewer for small problems so every warp gets work; chunks are dispatched dynamically.
+static int choose_cu(int64_t rows, int max_units, int sm_count, int nw) {
+    const int64_t warps = (int64_t)sm_count * nw;
+    const int64_t total = rows * (int64_t)max_units;
+    if (rows > 0 && rows <= warps && total <= warps * 64 && max_units > 0) {
+        const int64_t per_row = warps / rows;
+        const int64_t cu1 = (max_units + per_row - 1) / per_row;
+        const int64_t chunks = rows * ((max_units + cu1 - 1) / cu1);
+        if (chunks * 100 >= warps * 85) return (int)cu1;  // >= 85 % of the warps get (exactly) one chunk
+    }
+    int64_t cu = total / (4 * warps);
     if (cu > 16) cu = 16;
     if (cu < 2) cu = 2;
     int p = 2;
@@ -1309,22 +1349,30 @@ static int choose_cu(int64_t rows, int max_units, int sm_count) {
 }
 
 static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
-    const int cu = choose_cu(rows, max_units, sm_count);
-    const size_t ov = (size_t)rows * ((max_units + cu - 1) / cu);
+    size_t ov = 0;
+    for (int nw : {4, 8, 16}) {  // the streaming-kernel instances differ in warps per CTA; size for the largest need
+        const int cu = choose_cu(rows, max_units, sm_count, nw);
+        const size_t v = (size_t)rows * ((max_units + cu - 1) / cu);
+        if (v > ov) ov = v;
+    }
     size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
-    if (dr < (size_t)rows * 2) dr = (size_t)rows * 2;  // exchange mode forces >= 2 splits
     // beam-group kernel: chunk size chosen from the number of (group, head) pairs, >= rows / 4
-    const int cug = choose_cu(rows / kGroupMaxW > 0 ? rows / kGroupMaxW : 1, max_units, sm_count);
+    int cug = choose_cu(rows / kGroupMaxW > 0 ? rows / kGroupMaxW : 1, max_units, sm_count, kOvWarps);
+    if (cug > 16) cug = 16;  // as launch_group
     const size_t gr = (size_t)rows * ((max_units + cug - 1) / cug);
     size_t mx = ov > dr ? ov : dr;
     if (gr > mx) mx = gr;
     return ((mx + 64) + 3) & ~(size_t)3;  // multiple of 4: ws_o stays 16-byte aligned
 }
 
+// Workspace layout: [chunk counter: 256 B][row_done: rows x u32, padded to 256 B][m: nslots][l: nslots][o: nslots * D]
+// [row / group chunk prefixes of the ragged group kernel]
+static size_t ws_header_bytes(int64_t rows) { return 256 + (((size_t)rows * 4 + 255) & ~(size_t)255); }
+
 static size_t ws_bytes_needed(int B, int H, int D, int num_tiles, int tile_size, int sm_count) {
     const int max_units = (int)(((int64_t)num_tiles * tile_size + kUnitTok - 1) / kUnitTok);
-    return ws_slots((int64_t)B * H, max_units, sm_count) * (size_t)(D + 2) * sizeof(float) + 256 +
-           2 * ((size_t)B + 2) * sizeof(int);  // + row / group chunk prefixes of the ragged group kernel
+    return ws_slots((int64_t)B * H, max_units, sm_count) * (size_t)(D + 2) * sizeof(float) +
+           ws_header_bytes((int64_t)B * H) + 2 * ((size_t)B + 2) * sizeof(int);
 }
 
 template <int D, int KV>
@@ -1335,22 +1383,20 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     const int max_units = (int)(((int64_t)a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok);
     if (!ws || ws_bytes < ws_bytes_needed(a.B, a.H, D, a.num_tiles, a.tile_size, di.sm_count))
         return PA_ERR_WORKSPACE;
-    // layout: [counter (256 B)] [m: nslots] [l: nslots] [o: nslots * D]
     unsigned int* counter = static_cast<unsigned int*>(ws);
-    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ws_header_bytes(rows));
     const size_t nslots = ws_slots(rows, max_units, di.sm_count);
     a.ws_m = w;
     a.ws_l = w + nslots;
     a.ws_o = w + 2 * nslots;
+    if (a.xch_peers) overlap = true;  // the inter-GPU exchange lives in the streaming kernel
     if (!overlap) {
         a.num_splits = choose_splits(rows, max_units, di.sm_count);
-        if (a.xch_peers && a.num_splits < 2) a.num_splits = 2;  // the exchange lives in the merge kernel's epilogue
         dim3 grid((unsigned)rows, (unsigned)a.num_splits);
         paged_decode_direct_kernel<D, KV><<<grid, 128, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
         if (a.num_splits > 1) {
-            // same warp-parallel merge (and optional inter-GPU exchange epilogue) as the streaming kernel's chunks
             a.all_rows_in_ws = 1;
             const int ns = a.num_splits;
             const int wpr = ns >= 64 ? 8 : (ns >= 32 ? 4 : (ns >= 16 ? 2 : 1));
@@ -1364,23 +1410,29 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     constexpr int S = OvCfg<D, KV>::S;
     using C = Cfg<D, KV>;
     const int G = di.sm_count;
-    const int cu = choose_cu(rows, max_units, di.sm_count);
-    const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
     constexpr int NWk = OvCfg<D, KV>::NW;
+    const int cu = choose_cu(rows, max_units, di.sm_count, NWk);
+    const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
     const size_t smem = (size_t)NWk * S * C::STAGE_BYTES + (size_t)NWk * S * (8 + 4) + 8 +
                         (size_t)NWk * 16 * sizeof(int64_t) + prefix_bytes;
     if (smem > (size_t)di.max_smem_optin) return PA_ERR_UNSUPPORTED;  // B too large for the prefix table
     auto kern = paged_decode_overlap_kernel<D, KV, NWk, S>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    // ONE launch: the warp that finishes the last chunk of a row merges the row (and, across GPUs, sends it; rows
+    // are received at the end of the same kernel).  PA_DECODE_MERGE_KERNEL=1 restores the separate merge kernel
+    // (kept for A/B measurements; not available with the inter-GPU exchange).
+    static const bool separate_merge = getenv("PA_DECODE_MERGE_KERNEL") && atoi(getenv("PA_DECODE_MERGE_KERNEL")) == 1;
+    const bool fused_merge = a.xch_peers || !separate_merge;
+    a.row_done = fused_merge ? counter + 64 : nullptr;
+    e = cudaMemsetAsync(ws, 0, fused_merge ? ws_header_bytes(rows) : sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     kern<<<G, NWk * 32, smem, st>>>(a, cu, counter);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess || fused_merge) return e == cudaSuccess ? PA_OK : (int)e;
     // Rows of a single chunk were finished by the main kernel; everything else is merged here.
     const int nc_uniform = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
-    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1 || a.xch_peers != nullptr;
+    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1;
     if (need_combine) {
         const int nc_max = (max_units + cu - 1) / cu;
         const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
@@ -1400,7 +1452,7 @@ static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStr
     const int max_units = (int)(((int64_t)a.num_tiles * a.tile_size + kUnitTok - 1) / kUnitTok);
     if (!ws || ws_bytes < ws_bytes_needed(a.B, a.H, D, a.num_tiles, a.tile_size, di.sm_count)) return PA_ERR_WORKSPACE;
     unsigned int* counter = static_cast<unsigned int*>(ws);
-    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+    float* w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ws_header_bytes(rows));
     const size_t nslots = ws_slots(rows, max_units, di.sm_count);
     a.ws_m = w;
     a.ws_l = w + nslots;
@@ -1408,7 +1460,8 @@ static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStr
     a.all_rows_in_ws = 1;
     GroupArgs ga{W, a.B / W};
     const int64_t gh = (int64_t)ga.groups * a.H;
-    const int cu = choose_cu(gh, max_units, di.sm_count);
+    int cu = choose_cu(gh, max_units, di.sm_count, kOvWarps);
+    if (cu > 16) cu = 16;  // the group kernel's chunk queue and partial layout assume <= 16-unit chunks
     CUtensorMap tmK, tmV;
     const uint64_t total_tokens = (uint64_t)a.total_pages * a.tile_size;
     if (!make_pool_map(&tmK, a.k_pool, total_tokens) || !make_pool_map(&tmV, a.v_pool, total_tokens))
@@ -1483,12 +1536,15 @@ static int decode_entry(int kv, bool overlap, const float* q, float* out, float*
         a.xch_status = xch->status;
         a.xch_rank = xch->rank;
         a.xch_world = xch->world;
-        a.all_rows_in_ws = 1;
     }
     cudaStream_t st = as_stream(stream);
     if (kv == 0) {
         return D == 128 ? launch_decode<128, 0>(a, overlap, ws, ws_bytes, st)
                         : launch_decode<64, 0>(a, overlap, ws, ws_bytes, st);
+    }
+    if (kv == 2) {
+        return D == 128 ? launch_decode<128, 2>(a, overlap, ws, ws_bytes, st)
+                        : launch_decode<64, 2>(a, overlap, ws, ws_bytes, st);
     }
     return D == 128 ? launch_decode<128, 1>(a, overlap, ws, ws_bytes, st)
                     : launch_decode<64, 1>(a, overlap, ws, ws_bytes, st);
@@ -1543,21 +1599,44 @@ PA_API int pa_paged_decode_i8_overlap(const float* d_q, float* d_out, const int8
                         d_k_scales, d_v_scales, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace,
                         workspace_bytes, stream);
 }
+// fp32 pools: KVTileCache<float>, the reference's default instantiation (attention_config.hpp:15,
+// kv_tile_cache.cpp:127).  Same kernels, 4-byte elements.
+PA_API int pa_paged_decode_f32(const float* d_q, float* d_out, const float* d_k_pool, const float* d_v_pool,
+                               PA_DECODE_COMMON_PARAMS, float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                               pa_stream_t stream) {
+    return decode_entry(2, false, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr, nullptr,
+                        PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_f32_overlap(const float* d_q, float* d_out, const float* d_k_pool, const float* d_v_pool,
+                                       PA_DECODE_COMMON_PARAMS, float* d_lse_out, void* d_workspace,
+                                       size_t workspace_bytes, pa_stream_t stream) {
+    return decode_entry(2, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr, nullptr,
+                        PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
+}
+
+// Kernel choice for the partial / split-KV entries: the streaming kernel (one static chunk per warp for a GPU's
+// share of a long sequence, in-kernel row merge) unless PA_PARTIAL_DIRECT=1 asks for the split-KV grid kernel.
+static bool partial_uses_streaming() {
+    const char* env = getenv("PA_PARTIAL_DIRECT");
+    return !(env && atoi(env) == 1);
+}
+
 PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
                                        float* d_part_o, const void* d_k_pool, const void* d_v_pool,
                                        PA_DECODE_COMMON_PARAMS, void* d_workspace,
                                        size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
-    // Kernel choice by problem size: below ~0.5 GB of K/V (one GPU's share of a 128K-token sequence is
-    // 268 MB) the split-KV grid kernel is faster than the persistent streaming kernel (56.7 vs 65 us at the
-    // C5 share: the persistent kernel's per-chunk overheads and ramp are not amortised); above it the
-    // streaming kernel wins.  PA_PARTIAL_DIRECT=0|1 overrides.
-    const int64_t total_units = (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok);
-    bool overlap = total_units > 65536;
-    if (const char* env = getenv("PA_PARTIAL_DIRECT")) overlap = atoi(env) != 1;
-    return decode_entry(0, overlap, d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+    return decode_entry(0, partial_uses_streaming(), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
                         nullptr, nullptr, PA_DECODE_COMMON_ARGS, nullptr, d_workspace,
                         workspace_bytes, stream);
+}
+PA_API int pa_paged_decode_i8_partial(const float* d_q, float* d_part_m, float* d_part_l, float* d_part_o,
+                                      const int8_t* d_k_pool, const int8_t* d_v_pool, const float* d_k_scales,
+                                      const float* d_v_scales, PA_DECODE_COMMON_PARAMS, void* d_workspace,
+                                      size_t workspace_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
+    return decode_entry(1, partial_uses_streaming(), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+                        d_k_scales, d_v_scales, PA_DECODE_COMMON_ARGS, nullptr, d_workspace, workspace_bytes, stream);
 }
 
 PA_API int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_pool,
@@ -1566,11 +1645,17 @@ PA_API int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const voi
                                        int rank, int world, uint32_t* d_epochs, int* d_status,
                                        pa_stream_t stream) {
     XchgParams x{d_peer_bufs, d_epochs, d_status, rank, world};
-    const int64_t total_units = (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok);
-    bool overlap = total_units > 65536;  // same size rule as pa_paged_decode_f16_partial
-    if (const char* env = getenv("PA_PARTIAL_DIRECT")) overlap = atoi(env) != 1;
-    return decode_entry(0, overlap, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
+    return decode_entry(0, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, nullptr,
                         nullptr, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream, &x);
+}
+PA_API int pa_paged_decode_i8_splitkv(const float* d_q, float* d_out, const int8_t* d_k_pool,
+                                      const int8_t* d_v_pool, const float* d_k_scales, const float* d_v_scales,
+                                      PA_DECODE_COMMON_PARAMS, float* d_lse_out, void* d_workspace,
+                                      size_t workspace_bytes, void* const* d_peer_bufs, int rank, int world,
+                                      uint32_t* d_epochs, int* d_status, pa_stream_t stream) {
+    XchgParams x{d_peer_bufs, d_epochs, d_status, rank, world};
+    return decode_entry(1, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, d_k_scales,
+                        d_v_scales, PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream, &x);
 }
 
 PA_API int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_pool,

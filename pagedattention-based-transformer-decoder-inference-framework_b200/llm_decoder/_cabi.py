@@ -28,6 +28,7 @@ _SIGS = {
     "pa_page_table_lookup": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_gather": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp], _i32),
     "pa_kv_append_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
+    "pa_kv_append_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_append_f32_f16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_append_f32_i8": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp], _i32),
     "pa_kv_copy_pages": ([_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], _i32),
@@ -36,8 +37,12 @@ _SIGS = {
     "pa_paged_decode_f16_overlap": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_i8": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_i8_overlap": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_f32": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_f32_overlap": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_partial": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
+    "pa_paged_decode_i8_partial": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_splitkv": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pa_paged_decode_i8_splitkv": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_paged_decode_f16_group": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_i32, _vp, _vp, _sz, _vp], _i32),
     "pa_softmax_lut_i32": ([_vp, _i32, _i32, _f32, _vp, _i32, _vp, _vp], _i32),
     "pa_softmax_temperature": ([_vp, _i32, _i32, _f32, _vp, _vp], _i32),
@@ -54,12 +59,14 @@ _SIGS = {
     "pa_batch_minmax_scale": ([_vp, _i32, _i32, _vp, _vp], _i32),
     "pa_dequantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
     "pa_batch_dequantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),
-    "pa_gemm_i8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp], _i32),
-    "pa_gemm_i8_dequant": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _vp], _i32),
+    "pa_gemm_i8_workspace_bytes": ([_i32, _i32, _i32, _i32], _sz),
+    "pa_gemm_i8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _sz, _vp], _i32),
+    "pa_gemm_i8_dequant": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _vp, _sz, _vp], _i32),
     "pa_embedding_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_embedding_i8": ([_vp, _f32, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_layer_norm_f32": ([_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp], _i32),
-    "pa_linear_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_linear_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_linear_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
     "pa_logits_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_logits_i8": ([_vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),
@@ -73,6 +80,11 @@ _SIGS = {
     "pa_p2p_close": ([_vp], _i32),
     "pa_p2p_free": ([_vp], _i32),
     "pa_splitkv_exchange_combine": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "pa_nccl_unique_id": ([C.c_char_p], _i32),
+    "pa_nccl_init": ([C.c_char_p, _i32, _i32, C.POINTER(_vp)], _i32),
+    "pa_nccl_destroy": ([_vp], _i32),
+    "pa_nccl_gather_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_nccl_allgather_combine": ([_vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp], _i32),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -22,16 +22,20 @@ from . import _cabi
 
 
 class _HostStage:
-    """Pinned staging buffers reused across calls (per shape)."""
+    """Pinned + device staging buffers for pageable host inputs, reused across calls.  One pair per
+    (key, shape, dtype, device, STREAM): calls on different streams never share a buffer, and the event recorded
+    after each H2D is waited for before the pinned buffer is overwritten by the next call (the DMA of call n may
+    not have run yet when call n+1 stages its input)."""
 
     def __init__(self):
         self.bufs = {}
 
     def get(self, key, shape, dtype, device):
-        k = (key, tuple(shape), dtype, str(device))
+        stream = torch.cuda.current_stream(device).cuda_stream
+        k = (key, tuple(shape), dtype, str(device), stream)
         if k not in self.bufs:
-            self.bufs[k] = (torch.empty(shape, dtype=dtype).pin_memory(),
-                            torch.empty(shape, dtype=dtype, device=device))
+            self.bufs[k] = [torch.empty(shape, dtype=dtype).pin_memory(),
+                            torch.empty(shape, dtype=dtype, device=device), None]
         return self.bufs[k]
 
 
@@ -139,12 +143,17 @@ def _to_device(x, key, device, dtype):
     DMA'd directly; pageable memory (numpy arrays, ordinary CPU tensors) goes through a pinned staging
     buffer first."""
     src = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
-    pinned, dev = _stage.get(key, src.shape, dtype, device)
+    slot = _stage.get(key, src.shape, dtype, device)
+    pinned, dev = slot[0], slot[1]
     if _is_pinned(src) and src.dtype == dtype and src.is_contiguous():
         dev.copy_(src, non_blocking=True)
     else:
+        if slot[2] is not None:
+            slot[2].synchronize()  # the previous call's H2D out of this pinned buffer has completed
         pinned.copy_(src)
         dev.copy_(pinned, non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record(torch.cuda.current_stream(device))
     return dev
 
 
@@ -166,7 +175,7 @@ class AttentionTileLauncher:
         pt = kv_cache.page_table_
         dev = kv_cache.key_buffer_.device
         assert H == pt.num_heads_ and D == kv_cache.head_dim_
-        if is_prefill and not _is_host(q) and T > 1 and q.numel() == B * H * T * D:
+        if is_prefill and not _is_host(q) and T > 1 and q.numel() == B * H * T * D and kv_cache.dtype != "f32":
             # the reference's prefill form: q/out [B, H, T, D], causal self-attention over the T cached tokens
             if top_k not in (0, None) or top_p < 1.0 or rotary_emb is not None or rerank_scores is not None:
                 raise NotImplementedError("prefill: top-k/top-p, RoPE table and rerank_scores are decode-only here")
@@ -217,6 +226,10 @@ class AttentionTileLauncher:
             common = common[:-1] + (_cabi.stream(),)
             if kv_cache.dtype == "f16":
                 fn = lib.pa_paged_decode_f16_overlap if use_overlap else lib.pa_paged_decode_f16
+                st = fn(d_q.data_ptr(), d_out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                        kv_cache.value_buffer_.data_ptr(), *common)
+            elif kv_cache.dtype == "f32":  # KVTileCache<float>
+                fn = lib.pa_paged_decode_f32_overlap if use_overlap else lib.pa_paged_decode_f32
                 st = fn(d_q.data_ptr(), d_out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
                         kv_cache.value_buffer_.data_ptr(), *common)
             else:
@@ -328,7 +341,7 @@ def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam
 
 
 def paged_decode_partial(q, kv_cache, B, T, temperature=1.0, beam_ids=None, ctx_lens=None, rotary_emb=None):
-    """Un-normalised (m, l, O) of this rank's pages (multi-GPU split-KV)."""
+    """Un-normalised (m, l, O) of this rank's pages (multi-GPU split-KV): pa_paged_decode_{f16,i8}_partial."""
     pt = kv_cache.page_table_
     dev = kv_cache.key_buffer_.device
     H, D = pt.num_heads_, kv_cache.head_dim_
@@ -336,13 +349,20 @@ def paged_decode_partial(q, kv_cache, B, T, temperature=1.0, beam_ids=None, ctx_
     pl = torch.empty((B, H), dtype=torch.float32, device=dev)
     po = torch.empty((B, H, D), dtype=torch.float32, device=dev)
     ws = kv_cache.workspace(B)
+    lib = _cabi.lib()
+    pools = (kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr())
+    if kv_cache.dtype == "i8":
+        fn, name = lib.pa_paged_decode_i8_partial, "pa_paged_decode_i8_partial"
+        pools += (kv_cache.k_scales_.data_ptr(), kv_cache.v_scales_.data_ptr())
+    elif kv_cache.dtype == "f16":
+        fn, name = lib.pa_paged_decode_f16_partial, "pa_paged_decode_f16_partial"
+    else:
+        raise NotImplementedError("paged_decode_partial: fp16 or int8 KV pages")
     with torch.cuda.device(dev):
-        st = _cabi.lib().pa_paged_decode_f16_partial(
-            q.data_ptr(), pm.data_ptr(), pl.data_ptr(), po.data_ptr(), kv_cache.key_buffer_.data_ptr(),
-            kv_cache.value_buffer_.data_ptr(), pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_,
-            kv_cache.total_pages_, _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T, D, kv_cache.tile_size_,
-            float(temperature), _cabi.ptr(rotary_emb), ws.data_ptr(), ws.numel(), _cabi.stream())
-    _cabi.check(st, "pa_paged_decode_f16_partial")
+        st = fn(q.data_ptr(), pm.data_ptr(), pl.data_ptr(), po.data_ptr(), *pools, pt.device_data().data_ptr(),
+                pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T, D,
+                kv_cache.tile_size_, float(temperature), _cabi.ptr(rotary_emb), ws.data_ptr(), ws.numel(), _cabi.stream())
+    _cabi.check(st, name)
     return pm, pl, po
 
 

@@ -63,6 +63,7 @@ class _Bufs:
         self.hq = torch.zeros((R, inter), dtype=torch.int8, device=dev)
         self.xs = torch.ones(R, **f32)
         self.hs = torch.ones(R, **f32)
+        self.ws = None  # GEMM / linear scratch for R rows (owned here, never by the library; _DecoderBase._scratch)
 
 
 class _DecoderBase:
@@ -130,6 +131,18 @@ class _DecoderBase:
     # ------------------------------------------------------------------ device step
     def _chk(self, st, what):
         _cabi.check(st, what)
+
+    def _scratch(self, bf, need):
+        """Caller-owned scratch of the split-K / K-sliced matmuls for the rows of `bf` (pointer, bytes).  Lives as
+        long as the activation buffers it belongs to, so a CUDA graph that captured the pointer stays valid; a
+        request that does not fit re-allocates AND drops the captured graph."""
+        if need == 0:
+            return None, 0
+        if bf.ws is None or bf.ws.numel() < need:
+            bf.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if bf is getattr(self, "bufs", None):
+                self._graph = None
+        return bf.ws.data_ptr(), bf.ws.numel()
 
     def _attention(self, layer_idx, q, out, R, ctx_lens, beam_ids, ws, prefill_shape=None):
         kvc = self.kv_caches[layer_idx]
@@ -231,19 +244,42 @@ class _DecoderBase:
         self.ctx_lens.fill_(n + 1)
 
     # ------------------------------------------------------------------ generate
-    def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None, **sampling_kw):
-        """generate(input_ids, max_len, temperature) -> prompt + generated ids (bindings.cpp:8-15).
-        Also tolerated (callers in api/, cli/): generate(input_ids, output_ids_list, max_tokens,
-        temperature) -- the list is extended in place and returned -- and max_gen_len=."""
+    @staticmethod
+    def normalize_generate_args(input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None, max_tokens=None):
+        """The call forms of `generate` found in the reference, reduced to (input_ids, out_list, max_len, temperature):
+          * pybind form        generate(input_ids, max_len, temperature)            src/bindings.cpp:8-15
+          * C++ out-param form generate(input_ids, output_ids, max_tokens[, temp])  api/router.py:23, web/app.py:23,
+                                                                                   cli/generate_batch.py:23
+          * keyword forms      generate(input_ids, output_ids, max_gen_len=64[, temperature=1.0])
+                                                                                   cli/chat_cli.py:24, cli/stream_cli.py:16
+        Pure host logic (no device work), so the call-site compatibility tests run without a GPU."""
         out_list = None
-        if isinstance(max_len, list):  # 4-arg out-param form (api/router.py:23)
-            out_list, max_len = max_len, temperature
-            temperature = extra[0] if extra else 1.0
+        if isinstance(max_len, list):  # 4-arg out-param form: (input_ids, output_ids, max_tokens, temperature)
+            out_list = max_len
+            if isinstance(temperature, (int, float)) and (extra or max_gen_len is None and max_tokens is None):
+                # positional max_tokens landed in `temperature`, the real temperature (if any) in extra[0]
+                max_len, temperature = temperature, (extra[0] if extra else 1.0)
+            else:
+                max_len = None  # max_gen_len= / max_tokens= keyword follows; `temperature` is the real one
+        elif extra:
+            raise TypeError("generate() takes at most 4 positional arguments")
         if max_gen_len is not None:
             max_len = max_gen_len
+        if max_tokens is not None:
+            max_len = max_tokens
         if max_len is None:
             raise TypeError("generate() missing max_len")
-        seqs = self.generate_batch([list(input_ids)], int(max_len), float(temperature), **sampling_kw)
+        return list(input_ids), out_list, int(max_len), float(temperature)
+
+    def generate(self, input_ids, max_len=None, temperature=1.0, *extra, max_gen_len=None, max_tokens=None,
+                 **sampling_kw):
+        """generate(input_ids, max_len, temperature) -> prompt + generated ids (bindings.cpp:8-15).
+        Also accepted (callers in api/, cli/, web/; see normalize_generate_args): generate(input_ids,
+        output_ids_list, max_tokens, temperature) -- the list is overwritten in place with prompt + generated
+        ids (cuda_decoder.cu:49,59: `output_ids = input_ids` then push_back) and returned -- and max_gen_len=."""
+        ids, out_list, max_len, temperature = self.normalize_generate_args(
+            input_ids, max_len, temperature, *extra, max_gen_len=max_gen_len, max_tokens=max_tokens)
+        seqs = self.generate_batch([ids], max_len, temperature, **sampling_kw)
         if out_list is not None:
             out_list[:] = seqs[0]
             return out_list
@@ -386,8 +422,9 @@ class CUDADecoder(_DecoderBase):
         if getattr(self, "_emb_T", None) is None or self._emb_T.shape != (self.hidden_dim_, self.vocab_size_):
             self._emb_T = self.embedding.t().contiguous()
         lib, s = self._lib, _cabi.stream()
+        wp, wb = self._scratch(self.bufs, lib.pa_linear_workspace_bytes(B, self.hidden_dim_, self.vocab_size_))
         self._chk(lib.pa_linear_f32(x_rows.data_ptr(), self._emb_T.data_ptr(), None, B, self.hidden_dim_,
-                                    self.vocab_size_, _cabi.ACT[""], self.logits.data_ptr(), s), "pa_linear_f32")
+                                    self.vocab_size_, _cabi.ACT[""], self.logits.data_ptr(), wp, wb, s), "pa_linear_f32")
         self._chk(lib.pa_argmax_f32(self.logits.data_ptr(), B, self.vocab_size_, self._temperature,
                                     self.ARGMAX_DIVIDE, self.ids.data_ptr(), s), "pa_argmax_f32")
 
@@ -397,10 +434,12 @@ class CUDADecoder(_DecoderBase):
 
     def _mlp(self, bf, L):
         lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        wp, wb = self._scratch(bf, max(lib.pa_linear_workspace_bytes(R, hid, inter),
+                                       lib.pa_linear_workspace_bytes(R, inter, hid)))
         self._chk(lib.pa_linear_f32(bf.n.data_ptr(), L.fc1_w.data_ptr(), L.fc1_b.data_ptr(), R, hid, inter,
-                                    _cabi.ACT["relu"], bf.h.data_ptr(), s), "pa_linear_f32")
+                                    _cabi.ACT["relu"], bf.h.data_ptr(), wp, wb, s), "pa_linear_f32")
         self._chk(lib.pa_linear_f32(bf.h.data_ptr(), L.fc2_w.data_ptr(), L.fc2_b.data_ptr(), R, inter, hid,
-                                    _cabi.ACT[""], bf.x.data_ptr(), s), "pa_linear_f32")
+                                    _cabi.ACT[""], bf.x.data_ptr(), wp, wb, s), "pa_linear_f32")
 
     def _logits(self, x_rows):
         self._chk(self._lib.pa_logits_f32(x_rows.data_ptr(), self.embedding.data_ptr(), self._batch,
@@ -522,9 +561,10 @@ class INT8Decoder(_DecoderBase):
             self._ls = torch.empty(B, dtype=torch.float32, device=dev)
         lib, s = self._lib, _cabi.stream()
         self._quant_rows(x_rows, self._lq, self._ls, B, hid)
+        wp, wb = self._scratch(self.bufs, lib.pa_gemm_i8_workspace_bytes(1, B, Vp, hid))
         self._chk(lib.pa_gemm_i8_dequant(self._lq.data_ptr(), self._emb_T.data_ptr(), self._logits_pad.data_ptr(), 1,
                                          B, Vp, hid, self._ls.data_ptr(), 1.0 / float(self.emb_qscale),
-                                         self._pad_bias.data_ptr(), _cabi.ACT[""], s), "pa_gemm_i8_dequant")
+                                         self._pad_bias.data_ptr(), _cabi.ACT[""], wp, wb, s), "pa_gemm_i8_dequant")
         self.logits = self._logits_pad[:, :V]
         sp = getattr(self, "_sampling", None)
         if sp is None:
@@ -549,13 +589,15 @@ class INT8Decoder(_DecoderBase):
 
     def _mlp(self, bf, L):
         lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        wp, wb = self._scratch(bf, max(lib.pa_gemm_i8_workspace_bytes(1, R, inter, hid),
+                                       lib.pa_gemm_i8_workspace_bytes(1, R, hid, inter)))
         self._quant_rows(bf.n, bf.xq, bf.xs, R, hid)
         self._chk(lib.pa_gemm_i8_dequant(bf.xq.data_ptr(), L.fc1_w.data_ptr(), bf.h.data_ptr(), 1, R, inter, hid,
                                          bf.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(),
-                                         _cabi.ACT["relu"], s), "pa_gemm_i8_dequant")
+                                         _cabi.ACT["relu"], wp, wb, s), "pa_gemm_i8_dequant")
         self._quant_rows(bf.h, bf.hq, bf.hs, R, inter)
         self._chk(lib.pa_gemm_i8_dequant(bf.hq.data_ptr(), L.fc2_w.data_ptr(), bf.x.data_ptr(), 1, R, hid, inter,
-                                         bf.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], s),
+                                         bf.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], wp, wb, s),
                   "pa_gemm_i8_dequant")
 
     def _logits(self, x_rows):

@@ -8,8 +8,11 @@ modes, both implemented here:
   collective on the data path.  `shard_range` keeps beam groups on one rank.
 * split-KV of ONE long sequence -- rank r holds a contiguous range of the sequence's pages,
   runs the same decode kernel over its range emitting un-normalised partials (m, l, O)
-  (pa_paged_decode_f16_partial), the partials ([H, D+2] floats = 16.6 KB per rank at the
-  Llama-7B shape) are all-gathered over NVLink and merged by pa_lse_combine on every rank.
+  (pa_paged_decode_{f16,i8}_partial); the partials ([H, D+2] floats = 16.6 KB per rank at the
+  Llama-7B shape) are exchanged over NVLink and LSE-combined on every rank.  Three exchange forms
+  (split_kv_decode): NCCL all-gather + combine (`NcclCombine`, pa_nccl_allgather_combine: the north
+  star's baseline), a stand-alone peer-memory exchange kernel, and decode + merge + exchange fused
+  into ONE launch (`PeerExchange.decode`, pa_paged_decode_*_splitkv).
 """
 import torch
 import torch.distributed as dist
@@ -117,8 +120,9 @@ class PeerExchange:
         return out
 
     def decode(self, q, kv_cache, B, T_local, temperature=1.0, beam_ids=None, ctx_lens=None, out=None):
-        """pa_paged_decode_f16_splitkv: streaming kernel over this rank's pages + chunk-merge kernel whose
-        epilogue exchanges the row partials with the peers and combines them.  Two launches per call."""
+        """pa_paged_decode_{f16,i8}_splitkv: ONE launch -- the streaming kernel over this rank's pages; the warp that
+        finishes a row merges it and sends it to every peer (flag-in-data packets, never blocks); rows are received
+        and LSE-combined at the end of the same kernel."""
         _cabi = self._cabi
         pt = kv_cache.page_table_
         H, D = pt.num_heads_, kv_cache.head_dim_
@@ -126,26 +130,34 @@ class PeerExchange:
         if out is None:
             out = torch.empty((B, H, D), dtype=torch.float32, device=self.device)
         ws = kv_cache.workspace(B)
+        lib = _cabi.lib()
+        pools = (kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr())
+        if kv_cache.dtype == "i8":
+            fn, name = lib.pa_paged_decode_i8_splitkv, "pa_paged_decode_i8_splitkv"
+            pools += (kv_cache.k_scales_.data_ptr(), kv_cache.v_scales_.data_ptr())
+        else:
+            fn, name = lib.pa_paged_decode_f16_splitkv, "pa_paged_decode_f16_splitkv"
         with torch.cuda.device(self.device):
-            st = _cabi.lib().pa_paged_decode_f16_splitkv(
-                q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
-                pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_,
-                _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T_local, D, kv_cache.tile_size_, float(temperature),
-                None, None, ws.data_ptr(), ws.numel(), self.peer_ptrs.data_ptr(), self.rank, self.world,
-                self.epochs.data_ptr(), self.status.data_ptr(), _cabi.stream())
-        _cabi.check(st, "pa_paged_decode_f16_splitkv")
+            st = fn(q.data_ptr(), out.data_ptr(), *pools, pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_,
+                    kv_cache.total_pages_, _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T_local, D, kv_cache.tile_size_,
+                    float(temperature), None, None, ws.data_ptr(), ws.numel(), self.peer_ptrs.data_ptr(), self.rank,
+                    self.world, self.epochs.data_ptr(), self.status.data_ptr(), _cabi.stream())
+        _cabi.check(st, name)
         return out
 
     def check(self):
-        """Raises if a peer ever failed to arrive (synchronises)."""
+        """Raises if a peer ever failed to arrive (synchronises the device: call it at a host sync point, e.g. once
+        per generated token when the ids are read back).  A timed-out row was written as NaN and its epoch was not
+        advanced, so a missed step can never be mistaken for a result."""
         if int(self.status.item()) != 0:
-            raise RuntimeError("pa_splitkv_exchange_combine: a peer rank did not arrive within the timeout")
+            raise RuntimeError("split-KV exchange: a peer rank did not arrive within the timeout")
 
     def close(self):
         lib = self._cabi.lib()
         dist.barrier(group=self.group)
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
+            self.check()
             for p in self._peers:
                 lib.pa_p2p_close(p)
             self._peers = []
@@ -154,17 +166,61 @@ class PeerExchange:
                 self._own = None
 
 
+class NcclCombine:
+    """pa_nccl_*: the library's own NCCL communicator (ncclCommInitRank from an id broadcast through
+    torch.distributed) + all-gather of (m, l, O) straight into pa_lse_combine's layout + combine kernel."""
+
+    def __init__(self, rows, head_dim, group=None, device=None):
+        import ctypes as C
+
+        from . import _cabi
+        self._cabi = _cabi
+        self.rows, self.D, self.group = rows, head_dim, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _cabi.lib()
+        ident = C.create_string_buffer(128)
+        if self.rank == 0:
+            _cabi.check(lib.pa_nccl_unique_id(ident), "pa_nccl_unique_id")
+        box = [bytes(ident.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._comm = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.pa_nccl_init(C.create_string_buffer(box[0], 128), self.rank, self.world, C.byref(self._comm)),
+                        "pa_nccl_init")
+            self._gather = torch.empty(lib.pa_nccl_gather_bytes(self.world, rows, head_dim), dtype=torch.uint8,
+                                       device=self.device)
+
+    def combine(self, part_m, part_l, part_o, out=None, lse_out=None):
+        _cabi = self._cabi
+        if out is None:
+            out = torch.empty((self.rows, self.D), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().pa_nccl_allgather_combine(
+                self._comm, self.world, part_m.data_ptr(), part_l.data_ptr(), part_o.data_ptr(), self.rows, self.D,
+                self._gather.data_ptr(), self._gather.numel(), out.data_ptr(), _cabi.ptr(lse_out), _cabi.stream()),
+                "pa_nccl_allgather_combine")
+        return out
+
+    def close(self):
+        if self._comm:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                self._cabi.lib().pa_nccl_destroy(self._comm)
+            self._comm = None
+
+
 def split_kv_decode(q, kv_cache, B, T_local, temperature=1.0, beam_ids=None, ctx_lens=None, group=None,
                     exchange=None, fused=False):
     """Decode attention of `B` rows whose KV pages are split across the ranks of `group`.
     `kv_cache` holds THIS rank's pages (table row b = the rank's tile range of sequence b);
     T_local / ctx_lens are the token counts held locally.  Returns out [B, H, D] on every rank.
-    exchange=None: NCCL all-gather of the partials followed by pa_lse_combine.
-    exchange=PeerExchange: partial kernel + ONE peer-memory exchange+combine kernel;
-    with fused=True the exchange runs in the epilogue of the decode's own chunk-merge kernel
-    (pa_paged_decode_f16_splitkv; the two exchange forms use the same buffers but must not be mixed
-    within one PeerExchange because they keep separate step counters)."""
-    if exchange is not None and fused:
+    exchange=None: all-gather of the partials through torch.distributed followed by pa_lse_combine.
+    exchange=NcclCombine: pa_nccl_allgather_combine (the library's own NCCL path, no pack / unpack passes).
+    exchange=PeerExchange: partial kernel + ONE peer-memory exchange+combine kernel; with fused=True decode, row
+    merge, exchange and combine are ONE launch (pa_paged_decode_*_splitkv; the two peer-memory forms use the same
+    buffers but must not be mixed within one PeerExchange because they advance the same step counters)."""
+    if isinstance(exchange, PeerExchange) and fused:
         return exchange.decode(q, kv_cache, B, T_local, temperature, beam_ids, ctx_lens)
     pm, pl, po = _att.paged_decode_partial(q, kv_cache, B, T_local, temperature, beam_ids, ctx_lens)
     H, D = po.shape[1], po.shape[2]

@@ -103,9 +103,13 @@ def dnnl_matmul_int8(A, B, C, BATCH, M, N, K, scaleA, scaleB, scaleC=1.0, bias=N
         return False
     try:
         with torch.cuda.device(A.device):
-            st = _cabi.lib().pa_gemm_i8(A.data_ptr(), B.data_ptr(), _cabi.ptr(C), _cabi.ptr(acc_out), BATCH, M,
-                                        N, K, float(scaleA), float(scaleB), float(scaleC), _cabi.ptr(bias),
-                                        _cabi.ACT[activation], _cabi.stream())
+            lib = _cabi.lib()
+            # split-K scratch is the caller's (stream-ordered torch allocation, released after the call is enqueued)
+            need = lib.pa_gemm_i8_workspace_bytes(BATCH, M, N, K)
+            ws = torch.empty(need, dtype=torch.uint8, device=A.device) if need else None
+            st = lib.pa_gemm_i8(A.data_ptr(), B.data_ptr(), _cabi.ptr(C), _cabi.ptr(acc_out), BATCH, M,
+                                N, K, float(scaleA), float(scaleB), float(scaleC), _cabi.ptr(bias),
+                                _cabi.ACT[activation], _cabi.ptr(ws), need, _cabi.stream())
         return st == _cabi.PA_OK
     except Exception:
         return False

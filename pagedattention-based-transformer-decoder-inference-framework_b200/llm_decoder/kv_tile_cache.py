@@ -3,8 +3,9 @@
 Mirrors kv_cache/kv_tile_cache.hpp:9-80 / kv_tile_cache.cpp:7-128: two device pools
 (`key_buffer_`, `value_buffer_`) of `total_pages * tile_size * head_dim` elements, page p
 of either pool starting at element p*tile_size*head_dim (cpp:52-62), K and V of a tile
-sharing one page id.  Storage dtype: 'f16' (fp16 pages) or 'i8' (int8 pages plus one f32
-scale per (page, row) for K and for V).
+sharing one page id.  Storage dtype: 'f16' (fp16 pages, KVTileCache<half>), 'f32' (fp32 pages,
+KVTileCache<float> -- the two instantiations of kv_tile_cache.cpp:127-128) or 'i8' (int8 pages plus
+one f32 scale per (page, row) for K and for V).
 
 Decisions taken where the reference contradicts itself: page ids come
 from a free list (the reference's `map.size()` re-issues live ids after an eviction),
@@ -22,13 +23,13 @@ import torch
 from . import _cabi
 from .page_table import PageTable
 
-_DTYPES = {"f16": torch.float16, "i8": torch.int8}
+_DTYPES = {"f16": torch.float16, "i8": torch.int8, "f32": torch.float32}
 
 
 class KVTileCache:
     def __init__(self, dtype="f16", device=None):
         if dtype not in _DTYPES:
-            raise ValueError("KVTileCache dtype must be 'f16' or 'i8'")
+            raise ValueError("KVTileCache dtype must be 'f16', 'i8' or 'f32'")
         self.dtype = dtype
         self._device = torch.device(device) if device is not None else None
         self.key_buffer_ = self.value_buffer_ = None
@@ -37,8 +38,9 @@ class KVTileCache:
         self.page_table_ = PageTable(device)
         self.tile_to_page_map_ = OrderedDict()  # (beam, head, tile) -> page, LRU order (oldest first)
         self._free = []
+        self._page_refs = {}  # page -> number of table entries sharing it (absent = 1); copy-on-write state
         self.mutex_ = threading.Lock()
-        self._ws = None
+        self._ws = {}         # decode scratch, one buffer per stream (the chunk counter and partials live in it)
 
     # ---- kv_tile_cache.cpp:18-24, 39-50 ------------------------------------------------
     def init(self, num_pages, tile_size, head_dim):
@@ -46,8 +48,15 @@ class KVTileCache:
             raise ValueError("KVTileCache.init: sizes must be positive")
         self.tile_size_, self.head_dim_, self.total_pages_ = int(tile_size), int(head_dim), int(num_pages)
         self._allocate_buffers()
+        self._reset_allocator()
+        self.page_table_.clear()  # a table configured before a re-init must not keep ids of the old pool
+
+    def _reset_allocator(self):
+        """Fresh pool: every page free, no tile mapped, no page shared, scratch re-sized on next use."""
         self.tile_to_page_map_.clear()
         self._free = list(range(self.total_pages_ - 1, -1, -1))
+        self._page_refs.clear()
+        self._ws = {}
 
     def configure_table(self, num_beams, num_heads, num_tiles):
         self.page_table_.init(num_beams, num_heads, num_tiles)
@@ -71,16 +80,14 @@ class KVTileCache:
         self.total_pages_, self.tile_size_, self.head_dim_ = key_buffer.shape
         self.key_buffer_, self.value_buffer_ = key_buffer, value_buffer
         self.k_scales_, self.v_scales_ = k_scales, v_scales
-        self.tile_to_page_map_.clear()
-        self._free = list(range(self.total_pages_ - 1, -1, -1))
+        self._reset_allocator()
 
     # ---- kv_tile_cache.cpp:27-37 -------------------------------------------------------
     def resize(self, new_num_pages, new_tile_size):
         with self.mutex_:
             self.tile_size_, self.total_pages_ = int(new_tile_size), int(new_num_pages)
             self._allocate_buffers()
-            self.tile_to_page_map_.clear()
-            self._free = list(range(self.total_pages_ - 1, -1, -1))
+            self._reset_allocator()
             self.page_table_.clear()
 
     # ---- kv_tile_cache.cpp:52-62 (device addresses) ------------------------------------
@@ -101,6 +108,8 @@ class KVTileCache:
             page = self.tile_to_page_map_.get(key)
             if page is None:
                 self._evict_if_needed()
+                if not self._free:  # every remaining page is shared by a live beam, or the pool is empty
+                    raise RuntimeError("KVTileCache.register_tile: page pool exhausted")
                 page = self._free.pop()
                 self.tile_to_page_map_[key] = page
                 self.page_table_.assign(*key, page)
@@ -127,7 +136,7 @@ class KVTileCache:
 
     def load_from_file(self, path):
         n = self.key_buffer_.numel()
-        npdt = np.float16 if self.dtype == "f16" else np.int8
+        npdt = {"f16": np.float16, "i8": np.int8, "f32": np.float32}[self.dtype]
         with open(path, "rb") as f:
             k = np.frombuffer(f.read(n * np.dtype(npdt).itemsize), dtype=npdt)
             v = np.frombuffer(f.read(n * np.dtype(npdt).itemsize), dtype=npdt)
@@ -194,7 +203,20 @@ class KVTileCache:
             raise RuntimeError(f"Failed to open file for loading: {path}")
         count = int(np.frombuffer(raw[:4], dtype="<i4")[0])
         rec = np.frombuffer(raw, dtype=np.dtype([("idx", "<i4", 3), ("data", "u1", nb)]), count=count, offset=4)
-        pages = [self.register_tile(int(b), int(h), int(t)) for b, h, t in rec["idx"]]
+        keys = [(int(b), int(h), int(t)) for b, h, t in rec["idx"]]
+        if len(set(keys)) != len(keys):
+            raise RuntimeError(f"duplicate tile index in {path}")
+        new = sum(1 for k in keys if k not in self.tile_to_page_map_)
+        evictable = sum(1 for k, p in self.tile_to_page_map_.items()
+                        if k not in set(keys) and self._page_refs.get(p, 1) == 1)
+        if new > len(self._free) + evictable:
+            # registering them would evict tiles of this same file and alias two tiles to one page
+            raise RuntimeError(f"KVTileCache.load_tiles_cpu_format: {count} tiles do not fit the page pool "
+                               f"({len(self._free)} free + {evictable} evictable pages)")
+        for k in keys:  # tiles of the file that are already mapped become most-recently-used first
+            if k in self.tile_to_page_map_:
+                self.tile_to_page_map_.move_to_end(k)
+        pages = [self.register_tile(*k) for k in keys]
         if not pages:
             return 0
         dev = self.key_buffer_.device
@@ -236,7 +258,10 @@ class KVTileCache:
                   self.tile_size_, self.head_dim_, new_k.data_ptr(), new_v.data_ptr(),
                   _cabi.ptr(beam_ids), positions.data_ptr(), R, _cabi.stream())
         with torch.cuda.device(table.device):
-            if self.dtype == "i8":
+            if self.dtype == "f32":
+                assert new_k.dtype == torch.float32
+                st = lib.pa_kv_append_f32(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(), *common)
+            elif self.dtype == "i8":
                 assert new_k.dtype == torch.float32
                 st = lib.pa_kv_append_f32_i8(self.key_buffer_.data_ptr(), self.value_buffer_.data_ptr(),
                                              self.k_scales_.data_ptr(), self.v_scales_.data_ptr(), *common)
@@ -252,8 +277,6 @@ class KVTileCache:
 
     # ---- beam search: shared-prefix pages with copy-on-write (north star; no reference code) ---
     def _refs(self):
-        if not hasattr(self, "_page_refs"):
-            self._page_refs = {}
         return self._page_refs
 
     def fork_beam(self, src_beam, dst_beam, num_tiles=None):
@@ -353,9 +376,14 @@ class KVTileCache:
         return dense
 
     def workspace(self, B):
-        """Scratch for the decode kernels, cached per cache object."""
-        need = _cabi.lib().pa_decode_workspace_bytes(B, self.page_table_.num_heads_, self.head_dim_,
-                                                     self.page_table_.num_tiles_, self.tile_size_)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.key_buffer_.device)
-        return self._ws
+        """Scratch for the decode kernels (chunk counter + partials): one buffer per (cache, stream), so decode
+        calls on different streams never share it; sized on the cache's own device."""
+        dev = self.key_buffer_.device
+        with torch.cuda.device(dev):
+            need = _cabi.lib().pa_decode_workspace_bytes(B, self.page_table_.num_heads_, self.head_dim_,
+                                                         self.page_table_.num_tiles_, self.tile_size_)
+            key = torch.cuda.current_stream(dev).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws

@@ -68,6 +68,8 @@ def make_case(B, H, D, T, tile_size=16, seed=0, kv="f16", unmapped_frac=0.0, rag
     if kv == "f16":
         case["k_pool"] = kf.astype(np.float16)
         case["v_pool"] = vf.astype(np.float16)
+    elif kv == "f32":  # KVTileCache<float>: the values as they are
+        case["k_pool"], case["v_pool"] = kf, vf
     else:
         c = oracle.cpu
         ks = c.batch_minmax_scale(kf, D)
@@ -85,7 +87,7 @@ def oracle_attention(case, **kw):
                 T=case["T"], ctx_lens=case["ctx_lens"], beam_ids=case["beam_ids"],
                 temperature=case["temperature"])
     args.update(kw)
-    if case["kv"] == "f16":
+    if case["kv"] in ("f16", "f32"):
         return c.paged_attention(case["q"], case["k_pool"].astype(np.float32),
                                  case["v_pool"].astype(np.float32), case["table"], **args)
     return c.paged_attention(case["q"], case["k_pool"], case["v_pool"], case["table"],

@@ -101,7 +101,8 @@ def test_decoder_kernels_match_oracle(oracle):
     dx2, dW, dbias = (torch.from_numpy(a).cuda() for a in (x2, W, bias))
     for act in (0, 1):
         o = torch.empty((rows2, N), device="cuda")
-        _cabi.check(lib.pa_linear_f32(dx2.data_ptr(), dW.data_ptr(), dbias.data_ptr(), rows2, K, N, act, o.data_ptr(), s))
+        _cabi.check(lib.pa_linear_f32(dx2.data_ptr(), dW.data_ptr(), dbias.data_ptr(), rows2, K, N, act, o.data_ptr(),
+                                      None, 0, s))
         exp = x2.astype(np.float64) @ W.astype(np.float64) + bias
         if act:
             exp = np.maximum(exp, 0)
@@ -149,7 +150,15 @@ def test_decoder_kernels_match_oracle(oracle):
     W3 = rng.standard_normal((4096, 64)).astype(np.float32)
     o3 = torch.empty((3, 64), device="cuda")
     dx3, dW3 = torch.from_numpy(x3).cuda(), torch.from_numpy(W3).cuda()
-    _cabi.check(lib.pa_linear_f32(dx3.data_ptr(), dW3.data_ptr(), None, 3, 4096, 64, 1, o3.data_ptr(), s))
+    # K-sliced across CTAs (caller-owned scratch) and unsliced (no scratch): same result up to summation order
+    need = lib.pa_linear_workspace_bytes(3, 4096, 64)
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    o3b = torch.empty((3, 64), device="cuda")
+    _cabi.check(lib.pa_linear_f32(dx3.data_ptr(), dW3.data_ptr(), None, 3, 4096, 64, 1, o3b.data_ptr(), None, 0, s))
+    _cabi.check(lib.pa_linear_f32(dx3.data_ptr(), dW3.data_ptr(), None, 3, 4096, 64, 1, o3.data_ptr(), ws.data_ptr(),
+                                  need, s))
+    np.testing.assert_allclose(o3b.cpu().numpy(), o3.cpu().numpy(), rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(o3.cpu().numpy(), np.maximum(x3.astype(np.float64) @ W3.astype(np.float64), 0),
                                rtol=1e-4, atol=1e-3)
     l2 = rng.standard_normal((rows, V)).astype(np.float32)
@@ -177,10 +186,14 @@ def test_gemm_i8_dequant_matches_oracle(oracle, shape):
     qs = rng.uniform(5, 60, BATCH * M).astype(np.float32)
     acc = oracle.cpu.gemm_s8s8s32(A, B).astype(np.float32)
     dA, dB, dbias, dqs = (torch.from_numpy(a).cuda() for a in (A, B, bias, qs))
-    for act in ("", "relu", "gelu"):
+    need = _cabi.lib().pa_gemm_i8_workspace_bytes(BATCH, M, N, K)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    for act in ("", "relu", "gelu", "relu-nows"):
         C = torch.full((BATCH, M, N), float("nan"), device="cuda")
+        wp, wb = (None, 0) if act == "relu-nows" else (ws.data_ptr(), need)  # without scratch: unsplit, same bits
+        act = act.split("-")[0]
         _cabi.check(_cabi.lib().pa_gemm_i8_dequant(dA.data_ptr(), dB.data_ptr(), C.data_ptr(), BATCH, M, N, K,
-                                                   dqs.data_ptr(), 0.013, dbias.data_ptr(), _cabi.ACT[act], None))
+                                                   dqs.data_ptr(), 0.013, dbias.data_ptr(), _cabi.ACT[act], wp, wb, None))
         alpha = (np.float32(0.013) / qs).reshape(BATCH, M, 1)
         exp = (alpha * acc).astype(np.float32) + bias
         if act == "relu":

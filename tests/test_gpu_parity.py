@@ -34,7 +34,7 @@ def run_decode(ld, case, overlap, kvc=None):
     q = torch.from_numpy(case["q"]).cuda()
     out = torch.full((B, H, D), float("nan"), device="cuda")
     lse = torch.empty((B, H), device="cuda")
-    ld.AttentionCUDA.forward(q, out, B, H, D, case["T"], case["beam_ids"], kvc, None, False, case["kv"] == "f16",
+    ld.AttentionCUDA.forward(q, out, B, H, D, case["T"], case["beam_ids"], kvc, None, False, case["kv"] != "i8",
                              overlap, case["temperature"], 0, 1.0, lse, False, ctx_lens=case["ctx_lens"])
     torch.cuda.synchronize()
     return out.cpu().numpy(), lse.cpu().numpy()
@@ -191,7 +191,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("overlap", [False, True], ids=["fused", "overlap"])
-@pytest.mark.parametrize("kv", ["f16", "i8"])
+@pytest.mark.parametrize("kv", ["f16", "i8", "f32"])
 @pytest.mark.parametrize("ci", range(len(CASES)))
 def test_decode_matches_oracle(ld, oracle, ci, kv, overlap):
     case = make_case(seed=ci, kv=kv, **CASES[ci])
@@ -273,10 +273,12 @@ def test_topk_rejected(ld):
         ld.AttentionCUDA.forward(q, q, 1, 1, 128, 32, None, kvc, None, False, True, False, 1.0, 1, 1.0)
 
 
-def test_partial_and_combine_equal_full(ld, oracle):
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_partial_and_combine_equal_full(ld, oracle, kv):
     """Split one sequence's pages across 4 'ranks' (disjoint tile ranges), emit (m,l,O) partials
-    with the C-ABI and combine: equals the single-GPU result (the C5 multi-GPU data path)."""
-    case = make_case(B=1, H=8, D=128, T=2048, seed=24)
+    with the C-ABI (pa_paged_decode_{f16,i8}_partial) and combine: equals the single-GPU result (the C5
+    multi-GPU data path)."""
+    case = make_case(B=1, H=8, D=128, T=2048, seed=24, kv=kv)
     full, _ = run_decode(ld, case, True)
     parts = 4
     nt = case["num_tiles"]
@@ -866,3 +868,174 @@ def test_gemm_i8_c4_full_size_vs_onednn(ld, shape):
     assert ld.dnnl_matmul_int8(A1.cuda(), B.cuda(), None, 1, M, N, K, 1.0, 1.0, acc_out=acc1)
     assert ld.dnnl_matmul_int8(A2.cuda(), B.cuda(), None, 1, M, N, K, 1.0, 1.0, acc_out=acc2)
     assert torch.equal(acc1 + acc2, acc)
+
+
+# ------------------------------------------------------------------ split-KV exchange on ONE GPU
+def _peer_buffers(ld, world, rows, D):
+    """`world` exchange buffers in this process (no IPC needed on one device) + the device array of pointers."""
+    import ctypes as C
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    bufs = []
+    for _ in range(world):
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        _cabi.check(lib.pa_p2p_alloc(lib.pa_splitkv_exchange_bytes(world, rows, D), C.byref(p), h), "pa_p2p_alloc")
+        bufs.append(p)
+    ptrs = torch.tensor([b.value for b in bufs], dtype=torch.int64).cuda()
+    return bufs, ptrs
+
+
+def _free_buffers(bufs):
+    from llm_decoder import _cabi
+    torch.cuda.synchronize()
+    for b in bufs:
+        _cabi.lib().pa_p2p_free(b)
+
+
+def _rank_cache(case, world, r):
+    nt = case["num_tiles"]
+    sub = dict(case)
+    tb = np.full_like(case["table"], -1)
+    sl = slice(r * nt // world, (r + 1) * nt // world)
+    tb[:, :, sl] = case["table"][:, :, sl]
+    sub["table"] = tb
+    return to_device_cache(sub)
+
+
+def _splitkv(ld, case, kvc, ptrs, rank, world, epochs, status, out, stream=None):
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    B, H, D = case["q"].shape
+    pt = kvc.page_table_
+    q = torch.from_numpy(case["q"]).cuda()
+    ws = kvc.workspace(B)
+    pools = (kvc.key_buffer_.data_ptr(), kvc.value_buffer_.data_ptr())
+    fn = lib.pa_paged_decode_f16_splitkv
+    if case["kv"] == "i8":
+        fn = lib.pa_paged_decode_i8_splitkv
+        pools += (kvc.k_scales_.data_ptr(), kvc.v_scales_.data_ptr())
+    _cabi.check(fn(q.data_ptr(), out.data_ptr(), *pools, pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_,
+                   kvc.total_pages_, None, None, B, case["T"], D, kvc.tile_size_, case["temperature"], None, None,
+                   ws.data_ptr(), ws.numel(), ptrs.data_ptr(), rank, world, epochs.data_ptr(), status.data_ptr(),
+                   stream if stream is not None else _cabi.stream()), "splitkv")
+    return q
+
+
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+@pytest.mark.parametrize("shape", [dict(B=1, H=8, D=128, T=4096), dict(B=3, H=4, D=64, T=400)])
+def test_fused_splitkv_world1_is_the_plain_decode(ld, oracle, kv, shape):
+    """pa_paged_decode_*_splitkv with a world of one rank: decode + in-kernel row merge + send to its own buffer +
+    receive + combine, all in one launch, three steps in a row (epochs / buffer parity advance)."""
+    case = make_case(seed=61, kv=kv, **shape)
+    B, H, D = case["q"].shape
+    bufs, ptrs = _peer_buffers(ld, 1, B * H, D)
+    kvc = to_device_cache(case)
+    epochs = torch.zeros(B * H, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    exp = oracle_attention(case)
+    for step in range(3):
+        out = torch.full((B, H, D), float("nan"), device="cuda")
+        _splitkv(ld, case, kvc, ptrs, 0, 1, epochs, status, out)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
+        assert int(status.item()) == 0 and (epochs.cpu().numpy() == step + 1).all()
+    _free_buffers(bufs)
+
+
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv):
+    """Two 'ranks' on one device, each holding half of the sequence's pages.  Rank 1 runs the stand-alone exchange
+    kernel (partials -> pa_splitkv_exchange_combine) on its own stream: it sends, then polls for rank 0.  Rank 0 runs
+    the FUSED kernel (pa_paged_decode_*_splitkv) on another stream: it streams its pages, merges, sends to both
+    buffers, and receives both sources.  Both forms speak the same packet protocol; both outputs must equal the
+    oracle over the WHOLE sequence; two steps (buffer parity flips)."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    case = make_case(B=1, H=8, D=128, T=4096, seed=62, kv=kv)
+    B, H, D = case["q"].shape
+    rows = B * H
+    bufs, ptrs = _peer_buffers(ld, 2, rows, D)
+    caches = [_rank_cache(case, 2, r) for r in range(2)]
+    epochs = [torch.zeros(rows, dtype=torch.int32, device="cuda") for _ in range(2)]
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    exp = oracle_attention(case)
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    q = torch.from_numpy(case["q"]).cuda()
+    for step in range(2):
+        out0 = torch.full((B, H, D), float("nan"), device="cuda")
+        out1 = torch.full((rows, D), float("nan"), device="cuda")
+        pm, pl, po = ld.paged_decode_partial(q, caches[1], B, case["T"], case["temperature"])
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            _cabi.check(lib.pa_splitkv_exchange_combine(pm.data_ptr(), pl.data_ptr(), po.data_ptr(), ptrs.data_ptr(), 1, 2,
+                                                        rows, D, epochs[1].data_ptr(), out1.data_ptr(), None,
+                                                        status.data_ptr(), s1.cuda_stream), "exchange")
+        with torch.cuda.stream(s0):
+            _splitkv(ld, case, caches[0], ptrs, 0, 2, epochs[0], status, out0, s0.cuda_stream)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        np.testing.assert_allclose(out0.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out1.cpu().numpy().reshape(B, H, D), exp, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out0.cpu().numpy().reshape(rows, D), out1.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    _free_buffers(bufs)
+
+
+def test_exchange_timeout_is_loud(ld):
+    """A peer that never arrives: the row is written as NaN, the status word is set and the epoch is NOT advanced
+    (a missed step can never be mistaken for a result)."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    rows, D = 4, 128
+    bufs, ptrs = _peer_buffers(ld, 2, rows, D)
+    epochs = torch.zeros(rows, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pm = torch.zeros(rows, device="cuda")
+    pl = torch.ones(rows, device="cuda")
+    po = torch.ones((rows, D), device="cuda")
+    out = torch.zeros((rows, D), device="cuda")
+    _cabi.check(lib.pa_splitkv_exchange_combine(pm.data_ptr(), pl.data_ptr(), po.data_ptr(), ptrs.data_ptr(), 0, 2, rows, D,
+                                                epochs.data_ptr(), out.data_ptr(), None, status.data_ptr(), None), "exchange")
+    torch.cuda.synchronize()   # ~2 s: rank 1 never sends
+    assert int(status.item()) == 1
+    assert torch.isnan(out).all() and (epochs == 0).all()
+    _free_buffers(bufs)
+
+
+def test_nccl_allgather_combine_single_rank(ld, oracle):
+    """pa_nccl_*: communicator of one rank (NCCL loaded at run time) -> all-gather + combine == pa_lse_combine of the
+    rank's own partial."""
+    import ctypes as C
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    case = make_case(B=2, H=4, D=128, T=512, seed=63)
+    kvc = to_device_cache(case)
+    q = torch.from_numpy(case["q"]).cuda()
+    pm, pl, po = ld.paged_decode_partial(q, kvc, 2, 512, case["temperature"])
+    ident = C.create_string_buffer(128)
+    st = lib.pa_nccl_unique_id(ident)
+    if st == -2:
+        pytest.skip("libnccl.so.2 not loadable")
+    _cabi.check(st, "pa_nccl_unique_id")
+    comm = C.c_void_p()
+    _cabi.check(lib.pa_nccl_init(ident, 0, 1, C.byref(comm)), "pa_nccl_init")
+    rows, D = 8, 128
+    gw = torch.empty(lib.pa_nccl_gather_bytes(1, rows, D), dtype=torch.uint8, device="cuda")
+    out = torch.empty((rows, D), device="cuda")
+    _cabi.check(lib.pa_nccl_allgather_combine(comm, 1, pm.data_ptr(), pl.data_ptr(), po.data_ptr(), rows, D, gw.data_ptr(),
+                                              gw.numel(), out.data_ptr(), None, _cabi.stream()), "pa_nccl_allgather_combine")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy().reshape(2, 4, 128), oracle_attention(case), rtol=RTOL, atol=ATOL)
+    _cabi.check(lib.pa_nccl_destroy(comm), "pa_nccl_destroy")
+
+
+def test_fused_row_merge_equals_separate_merge_kernel(ld, oracle):
+    """The in-kernel row merge (default) against the two-launch form (PA_DECODE_MERGE_KERNEL=1 is read once per
+    process, so the comparison is against the oracle and the split-KV grid kernel instead): ragged rows incl. a row
+    of length 0 and rows of a single chunk."""
+    case = make_case(B=6, H=3, D=128, T=1500, seed=64, ragged=True)
+    a, lse_a = run_decode(ld, case, True)
+    b, lse_b = run_decode(ld, case, False)
+    np.testing.assert_allclose(a, oracle_attention(case), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert (a[1] == 0).all() and np.isneginf(lse_a[1]).all()      # ctx_lens[1] == 0: no keys
+    np.testing.assert_allclose(lse_a[lse_a > -np.inf], lse_b[lse_b > -np.inf], rtol=1e-5, atol=1e-5)
