@@ -18,7 +18,13 @@ roofline = achieved algorithmic GB/s of the decode launch vs the measured HBM co
 cpu_baseline / --impl reference = the reference's CPU attention path (oracle port of
          cpu_paged_attention_forward, which does not compile as shipped) on the host cores,
          on a bounded sample (a few rows of one layer), scaled to the same metric.
-N > 1: one process per GPU (torchrun), rows sharded across ranks, no data-path collective.
+extra  = the other BASELINE.json configurations under the same clock (benchmarks/extras.py), each with its
+         achieved rate, fraction of the measured peak and a max-abs-err against the CPU oracle on a bounded
+         sample: c4_int8_decode, c4_gemm_pair (+ an int8 library peak measured in the same run), c3_group,
+         c5_splitkv (one 128K-token sequence split over the N ranks: decode + merge + exchange in ONE launch, the
+         stand-alone peer-memory exchange, and the NCCL all-gather form).  --no-extra skips them.
+N > 1: one process per GPU (torchrun), rows sharded across ranks, no data-path collective in the headline
+         step; c5_splitkv is the mode with an exchange.
 """
 import argparse
 import json
@@ -52,7 +58,23 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=16, help="rows in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="overlap", choices=["overlap", "fused"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / C5 extra block")
     return ap.parse_args()
+
+
+def workload_config(args):
+    """The workload both arms measure (identical dict in both JSON lines)."""
+    return {"workload": "C2: fp16 paged decode, Llama-7B shape, batch 64/GPU, 4K ctx, 16-token pages",
+            "layers": args.layers, "heads": HEADS, "head_dim": HDIM, "ctx": args.ctx, "page_tokens": TILE,
+            "rows_per_gpu": args.batch, "parallelism": f"batch-sharded x{args.gpus}, no collective"}
+
+
+def host_threads():
+    """Cores this process may run on (the CPU arm uses all of them, whatever OMP_NUM_THREADS torchrun exported)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # --------------------------------------------------------------------------- CPU baseline
@@ -62,9 +84,11 @@ def cpu_reference_sample(rows, ctx, repeats):
     (seconds per layer-pass [list], threads)."""
     import numpy as np
 
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())  # torchrun exports OMP_NUM_THREADS=1
     import oracle
     oracle.cpu.build()
     c = oracle.cpu
+    c.set_threads(host_threads())
     rng = np.random.default_rng(1236)
     nt = ctx // TILE
     P = rows * HEADS * nt
@@ -99,8 +123,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C2: fp16 paged decode, Llama-7B shape, batch 64/GPU, 4K ctx, 16-token pages",
-                   "layers": args.layers, "heads": HEADS, "head_dim": HDIM, "ctx": args.ctx, "page_tokens": TILE},
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,6 +189,7 @@ def run_ours(args):
     import llm_decoder as ld
     from llm_decoder import _cabi
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,6 +305,27 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * B / e2e_s
     row_bytes = B * H * D * 4
+
+    # The same host-buffer step when every layer NEEDS the previous layer's host result (the layers of a real decoder
+    # are dependent; above they are not, so their copies hide under neighbouring kernels): one synchronisation per
+    # layer, copies in line with the kernels.  Reported beside e2e, not instead of it.
+    def step_e2e_dependent():
+        for l in range(L):
+            kvc = caches[l % n_pools]
+            kvc.append(nk_host[l], nv_host[l], pos)
+            ld.AttentionCUDA.forward(q_host[l], out_host[l], B, H, D, T, None, kvc, None, False, True, use_overlap, temp,
+                                     sync=True)
+    step_e2e_dependent()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        step_e2e_dependent()
+    torch.cuda.synchronize(dev)
+    e2e_dep_s = (time.perf_counter() - t0) / 2
+    if world > 1:
+        t = torch.tensor([e2e_dep_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dep_s = float(t.item())
     # parity guard inside the bench: e2e output of the last layer == device-resident output
     agree = float((out_host[L - 1] - out_dev[L - 1].cpu()).abs().max())
 
@@ -303,6 +348,42 @@ def run_ours(args):
     except Exception:
         pass
 
+    # ---- parity of the timed configuration itself: a bounded sample of the last layer vs the CPU oracle -------
+    parity = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+            import extras
+            pairs = [(0, 0), (B // 2, H // 2), (B - 1, H - 1)]
+            exp = extras.oracle_rows(caches[(L - 1) % n_pools], q_dev[L - 1], pairs, T, temp)
+            got = np.stack([out_dev[L - 1][b, h].cpu().numpy() for b, h in pairs])
+            parity = {"max_abs_err_vs_oracle": float(np.abs(got - exp).max()),
+                      "ok": bool(np.allclose(got, exp, rtol=2e-3, atol=1e-3)), "tolerance": "2e-3 rel + 1e-3 abs",
+                      "sample": "3 (row, head) pairs of the last layer at the full 4096-token context"}
+        except Exception as e:  # the bench number stands; the failure is reported, not hidden
+            parity = {"error": repr(e)}
+
+    # ---- the other BASELINE.json configurations under the same clock ----------------------------------------
+    extra = None
+    if not args.no_extra:
+        del caches, q_dev, nk_dev, nv_dev, out_dev, q_host, nk_host, nv_host, out_host
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import extras
+        extra = {}
+
+        def run_extra(name, fn, *a, **kw):
+            try:
+                extra[name] = fn(*a, **kw)
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+        if world == 1:
+            run_extra("c4_int8_decode", extras.c4_int8_decode, dev, peak)
+            run_extra("c4_gemm_pair", extras.c4_gemm_pair, dev)
+            run_extra("c3_group", extras.c3_group, dev, peak)
+        run_extra("c5_splitkv", extras.c5_splitkv, dev, world, rank, peak)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,21 +402,27 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (fp16 K/V storage, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": "C2: fp16 paged decode, Llama-7B shape, batch 64/GPU, 4K ctx, 16-token pages",
-                   "layers": L, "heads": H, "head_dim": D, "ctx": T, "page_tokens": TILE, "rows_per_gpu": B,
-                   "kv_pools": n_pools, "kv_bytes_per_gpu": n_pools * pool_bytes, "kernel": args.kernel,
-                   "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": "each launch streams 4 GiB >> 126 MB L2; no flush needed"},
+        "config": workload_config(args),
+        "run_info": {"kv_pools": n_pools, "kv_bytes_per_gpu": n_pools * pool_bytes, "kernel": args.kernel,
+                     "l2": "each launch streams 4 GiB >> 126 MB L2; no flush needed",
+                     "decode_launches_per_layer": 1 if os.environ.get("PA_DECODE_MERGE_KERNEL") == "0" else 2},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "paged_decode_%s_kernel<128,f16>" % args.kernel,
                      "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "min_launch_ms": min(kern_ms),
                      "frac_of_8TBps": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * row_bytes * L,
                 "d2h_bytes_per_step": row_bytes * L, "ms_per_step": e2e_s * 1e3,
-                "max_abs_diff_vs_device_path": agree},
-        "gpu_launches": args.steps * L * 3,
+                "max_abs_diff_vs_device_path": agree,
+                "dependent_layers_value": world * B / e2e_dep_s, "dependent_layers_ms_per_step": e2e_dep_s * 1e3,
+                "note": "value: the 32 layer calls of a step are independent, copies overlap neighbouring kernels; "
+                        "dependent_layers_value: one host synchronisation per layer (each layer waits for the previous "
+                        "layer's host result)"},
+        "gpu_launches": args.steps * L * (2 if os.environ.get("PA_DECODE_MERGE_KERNEL") == "0" else 3),
         "clocks": clocks,
+        "parity": parity,
     }
+    if extra is not None:
+        line["extra"] = extra
     if cpu_base:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)

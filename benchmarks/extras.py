@@ -1,0 +1,366 @@
+"""Secondary configurations of BASELINE.json measured under the bench's own clock (bench.py `extra`).
+
+Each function builds its synthetic workload on `dev`, times the hot kernel(s) as CUDA-graph replays over rotating
+data sets (CUDA events; max over ranks when world > 1), checks a bounded sample of the output against the CPU
+oracle, frees its memory and returns one dict:  {"us": ..., "achieved": ..., "unit": ..., "frac": ...,
+"max_abs_err_vs_oracle": ..., ...}.
+
+  c4_int8_decode  C4 attention: int8 KV pages + f32 scales, 256 rows x 32 heads x 4096 ctx (8.86 GB per launch)
+  c4_gemm_pair    C4 MLP: [256 x 4096] . [4096 x 16384] (relu) -> [256 x 16384] . [16384 x 4096], s8 in / s8 out,
+                  plus the activation quantisation around it; denominators: nominal 4.5 POP/s AND the int8 rate a
+                  large cuBLASLt GEMM (torch._int_mm, 8192^3) reaches on this box in the same run
+  c3_group        C3: 32 beam groups x 4 beams, 2048 ctx = 1792 shared + 256 private tokens, achieved on UNIQUE bytes
+  c5_splitkv      C5: one sequence of 131072 tokens, pages split over the ranks; three exchange forms
+The oracle is used as the checker only (never timed here).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "pagedattention-based-transformer-decoder-inference-framework_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H, D, TILE = 32, 128, 16
+
+
+def graph_time(fns, iters, dev, world=1, per=None):
+    """fns: callables (one per data set) captured round-robin into ONE graph of `per` calls; returns the median
+    (max over ranks per replay) microseconds per call."""
+    per = per or 2 * len(fns)
+    for i in range(per):
+        fns[i % len(fns)]()
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(per):
+            fns[i % len(fns)]()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(iters):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ts.append(e0.elapsed_time(e1) / per)
+    t = torch.tensor(ts, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del g
+    return float(t.median().item()) * 1e3, float(t.min().item()) * 1e3
+
+
+def oracle_rows(kvc, q, pairs, T, temp, beam_ids=None):
+    """CPU oracle for a few (row, head) pairs of a device cache: the pair's pages are gathered to the host in tile
+    order and attended by oracle.cpu.paged_attention (B = H = 1 each).  Returns [len(pairs), D]."""
+    import oracle
+    oracle.cpu.build()
+    pt = kvc.page_table_
+    nt = (T + kvc.tile_size_ - 1) // kvc.tile_size_
+    table = pt.device_data().view(pt.num_beams_, pt.num_heads_, pt.num_tiles_)
+    outs = []
+    for (b, h) in pairs:
+        beam = b if beam_ids is None else int(beam_ids[b])
+        pages = table[beam, h, :nt].to(torch.int64)
+        k = kvc.key_buffer_.index_select(0, pages).cpu().numpy()
+        v = kvc.value_buffer_.index_select(0, pages).cpu().numpy()
+        tb = np.arange(nt, dtype=np.int32).reshape(1, 1, nt)
+        qq = q[b, h].reshape(1, 1, -1).cpu().numpy()
+        kw = dict(num_beams=1, num_tiles=nt, tile_size=kvc.tile_size_, T=T, temperature=temp)
+        if kvc.dtype == "i8":
+            ks = kvc.k_scales_.index_select(0, pages).cpu().numpy()
+            vs = kvc.v_scales_.index_select(0, pages).cpu().numpy()
+            o = oracle.cpu.paged_attention(qq, k, v, tb, k_scales=ks, v_scales=vs, **kw)
+        else:
+            o = oracle.cpu.paged_attention(qq, k.astype(np.float32), v.astype(np.float32), tb, **kw)
+        outs.append(o.reshape(-1))
+    return np.stack(outs)
+
+
+def _err(out, kvc, q, pairs, T, temp, beam_ids=None):
+    exp = oracle_rows(kvc, q, pairs, T, temp, beam_ids)
+    got = np.stack([out[b, h].cpu().numpy() for b, h in pairs])
+    ok = bool(np.allclose(got, exp, rtol=2e-3, atol=1e-3))
+    return float(np.abs(got - exp).max()), ok
+
+
+def c4_int8_decode(dev, hbm_peak, B=256, T=4096, iters=6):
+    import llm_decoder as ld
+    nt = T // TILE
+    P = B * H * nt
+    g = torch.Generator(device=dev).manual_seed(1238)
+    caches = []
+    for _ in range(2):  # one set streams 8.86 GB >> 126 MB L2; two sets alternate anyway
+        k = torch.randint(-127, 128, (P, TILE, D), generator=g, device=dev, dtype=torch.int8)
+        v = torch.randint(-127, 128, (P, TILE, D), generator=g, device=dev, dtype=torch.int8)
+        ks = torch.rand((P, TILE), generator=g, device=dev) * 20 + 30
+        vs = torch.rand((P, TILE), generator=g, device=dev) * 20 + 30
+        kvc = ld.KVTileCache("i8", device=dev)
+        kvc.adopt_buffers(k, v, ks, vs)
+        kvc.configure_table(B, H, nt)
+        kvc.page_table_.load_host_table(torch.randperm(P, generator=g, device=dev).to(torch.int32).cpu().numpy().reshape(B, H, nt))
+        caches.append(kvc)
+    q = torch.randn((B, H, D), generator=g, device=dev)
+    out = torch.empty_like(q)
+    temp = float(np.sqrt(D))
+    us, us_min = graph_time([lambda c=c: ld.AttentionCUDA.forward(q, out, B, H, D, T, None, c, None, False, False, True, temp)
+                             for c in caches], iters, dev)
+    ld.AttentionCUDA.forward(q, out, B, H, D, T, None, caches[0], None, False, False, True, temp)
+    torch.cuda.synchronize(dev)
+    err, ok = _err(out, caches[0], q, [(0, 0), (B // 2, 7), (B - 1, H - 1)], T, temp)
+    alg = B * H * T * D * 2 + B * H * T * 2 * 4 + 2 * B * H * D * 4 + B * H * nt * 4
+    ach = alg / us / 1e3
+    res = {"workload": f"C4 attention: int8 KV + f32 scales, {B} rows x {H} heads x {T} ctx, D=128, 16-token pages",
+           "kernel": "paged_decode_overlap_kernel<128,i8,16,3>", "us": round(us, 2), "us_min": round(us_min, 2),
+           "alg_bytes_per_launch": alg, "achieved": round(ach, 1), "unit": "GB/s", "peak": hbm_peak,
+           "frac": round(ach / hbm_peak, 4), "frac_of_8TBps": round(ach / 8000.0, 4),
+           "max_abs_err_vs_oracle": err, "parity_ok": ok, "oracle_sample": "3 (row, head) pairs at full context"}
+    del caches, q, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def measured_int8_peak(dev, n=8192, iters=5):
+    """What a LIBRARY int8 GEMM (cuBLASLt through torch._int_mm) reaches on this box at a large square shape: the
+    measured denominator beside the nominal 4.5 POP/s."""
+    a = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
+    b = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
+    for _ in range(2):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def c4_gemm_pair(dev, M=256, iters=10):
+    import llm_decoder as ld
+    import oracle
+    from llm_decoder import _cabi
+    HID, INTER = 4096, 16384
+    g = torch.Generator(device=dev).manual_seed(1239)
+    nw = 4  # 4 x 128 MiB of weights used round-robin (> L2)
+    W1 = [torch.randint(-127, 128, (1, HID, INTER), generator=g, device=dev, dtype=torch.int8) for _ in range(nw)]
+    W2 = [torch.randint(-127, 128, (1, INTER, HID), generator=g, device=dev, dtype=torch.int8) for _ in range(nw)]
+    b1, b2 = torch.randn(INTER, generator=g, device=dev), torch.randn(HID, generator=g, device=dev)
+    x = torch.randn((M, HID), generator=g, device=dev)
+    xq = torch.empty((1, M, HID), dtype=torch.int8, device=dev)
+    xs = torch.empty(M, device=dev)
+    h8 = torch.empty((1, M, INTER), dtype=torch.int8, device=dev)
+    y8 = torch.empty((1, M, HID), dtype=torch.int8, device=dev)
+    lib = _cabi.lib()
+
+    def quant():
+        _cabi.check(lib.pa_row_quantize_dynamic_i8(x.data_ptr(), M, HID, xs.data_ptr(), xq.data_ptr(), _cabi.stream()))
+
+    def fc1(i):
+        assert ld.dnnl_matmul_int8(xq, W1[i], h8, 1, M, INTER, HID, 1 / 16, 1 / 16, 8.0, b1, "relu")
+
+    def fc2(i):
+        assert ld.dnnl_matmul_int8(h8, W2[i], y8, 1, M, HID, INTER, 1 / 16, 1 / 16, 32.0, b2, "")
+
+    quant()
+    us_q, _ = graph_time([quant], iters, dev)
+    us_1, _ = graph_time([lambda i=i: fc1(i) for i in range(nw)], iters, dev)
+    us_2, _ = graph_time([lambda i=i: fc2(i) for i in range(nw)], iters, dev)
+    us_pair, us_pair_min = graph_time([lambda i=i: (fc1(i), fc2(i)) for i in range(nw)], iters, dev)
+    # library baseline at the same shapes (cuBLASLt int8 through torch._int_mm; s32 output, no epilogue)
+    a2, h2 = xq[0], h8[0]
+    us_lib1, _ = graph_time([lambda i=i: torch._int_mm(a2, W1[i][0]) for i in range(nw)], iters, dev)
+    us_lib2, _ = graph_time([lambda i=i: torch._int_mm(h2, W2[i][0]) for i in range(nw)], iters, dev)
+    # parity: s8 outputs of a few rows against the oracle's exact accumulators + restated epilogue
+    fc1(0)
+    fc2(0)
+    torch.cuda.synchronize(dev)
+    oracle.cpu.build()
+    rows = [0, M // 2, M - 1]
+    A = xq[0][rows].cpu().numpy()
+    e1 = oracle.cpu.dnnl_matmul_int8(A[None], W1[0].cpu().numpy(), 1 / 16, 1 / 16, 8.0, b1.cpu().numpy(), "relu")[0]
+    d1 = int(np.abs(e1.astype(np.int32) - h8[0][rows].cpu().numpy().astype(np.int32)).max())
+    Hm = h8[0][rows].cpu().numpy()
+    e2 = oracle.cpu.dnnl_matmul_int8(Hm[None], W2[0].cpu().numpy(), 1 / 16, 1 / 16, 32.0, b2.cpu().numpy(), "")[0]
+    d2 = int(np.abs(e2.astype(np.int32) - y8[0][rows].cpu().numpy().astype(np.int32)).max())
+    peak_lib = measured_int8_peak(dev)
+    ops1 = 2.0 * M * HID * INTER
+    tops = lambda us, n=1: n * ops1 / us / 1e6  # noqa: E731
+    res = {"workload": f"C4 MLP GEMMs: [{M} x 4096].[4096 x 16384] relu -> [{M} x 16384].[16384 x 4096], s8 x s8 -> s32 -> s8",
+           "kernel": "gemm_i8_2cta_kernel (tcgen05 kind::i8, cta_group::2)",
+           "us": round(us_pair, 2), "us_min": round(us_pair_min, 2), "fc1_us": round(us_1, 2), "fc2_us": round(us_2, 2),
+           "act_quant_us": round(us_q, 2), "pair_plus_quant_us": round(us_pair + 2 * us_q, 2),
+           "achieved": round(tops(us_pair, 2), 1), "unit": "TOP/s", "peak": 4500.0, "frac": round(tops(us_pair, 2) / 4500.0, 4),
+           "fc1_tops": round(tops(us_1), 1), "fc2_tops": round(tops(us_2), 1),
+           "measured_int8_peak_tops": round(peak_lib * 1e0, 1),
+           "measured_int8_peak_how": "torch._int_mm (cuBLASLt) 8192^3, best of 5, same run",
+           "frac_of_measured_int8_peak": round(tops(us_pair, 2) / peak_lib, 4),
+           "cublaslt_same_shapes_us": [round(us_lib1, 2), round(us_lib2, 2)],
+           "weight_stream_floor_us": round(2 * HID * INTER / 6547.2e3, 2),
+           "max_abs_err_vs_oracle": max(d1, d2), "parity_ok": max(d1, d2) <= 1,
+           "oracle_sample": "3 rows of each GEMM, s8 outputs in LSB vs exact int32 accumulators + restated epilogue"}
+    del W1, W2
+    torch.cuda.empty_cache()
+    return res
+
+
+def c3_group(dev, hbm_peak, iters=10, sets=3):
+    import llm_decoder as ld
+    groups, W, T, shared = 32, 4, 2048, 1792
+    B = groups * W
+    nt, pt = T // TILE, shared // TILE
+    temp = float(np.sqrt(D))
+    caches = []
+    for i in range(sets):
+        g = torch.Generator(device=dev).manual_seed(1237 + i)
+        unique = groups * H * pt + B * H * (nt - pt)
+        perm = torch.randperm(unique, generator=g, device=dev).to(torch.int32)
+        table = torch.empty((B, H, nt), dtype=torch.int32, device=dev)
+        table[:, :, :pt] = perm[:groups * H * pt].reshape(groups, 1, H, pt).expand(groups, W, H, pt).reshape(B, H, pt)
+        table[:, :, pt:] = perm[groups * H * pt:].reshape(B, H, nt - pt)
+        k = torch.randn((unique, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        v = torch.randn((unique, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        kvc = ld.KVTileCache("f16", device=dev)
+        kvc.adopt_buffers(k, v)
+        kvc.configure_table(B, H, nt)
+        kvc.page_table_.load_host_table(table.cpu().numpy())
+        caches.append(kvc)
+    q = torch.randn((B, H, D), device=dev)
+    out = torch.empty_like(q)
+    beam_ids = torch.arange(B, dtype=torch.int32, device=dev)
+    unique_bytes = unique * TILE * D * 2 * 2 + 2 * B * H * D * 4 + B * H * nt * 4
+    logical_bytes = B * H * T * D * 2 * 2 + 2 * B * H * D * 4 + B * H * nt * 4
+    us, us_min = graph_time([lambda c=c: ld.paged_decode_group(q, out, c, B, T, W, temp, beam_ids=beam_ids) for c in caches],
+                            iters, dev)
+    us_row, _ = graph_time([lambda c=c: ld.AttentionCUDA.forward(q, out, B, H, D, T, beam_ids, c, None, False, True, False, temp)
+                            for c in caches], iters, dev)
+    ld.paged_decode_group(q, out, caches[0], B, T, W, temp, beam_ids=beam_ids)
+    torch.cuda.synchronize(dev)
+    err, ok = _err(out, caches[0], q, [(0, 0), (1, 3), (B - 1, H - 1)], T, temp, beam_ids.cpu().numpy())
+    ach = unique_bytes / us / 1e3
+    res = {"workload": "C3: 32 groups x 4 beams x 32 heads, ctx 2048 = 1792 shared (copy-on-write) + 256 private tokens, fp16",
+           "kernel": "paged_decode_group_kernel", "us": round(us, 2), "us_min": round(us_min, 2),
+           "alg_bytes_per_launch": unique_bytes, "logical_bytes": logical_bytes, "achieved": round(ach, 1), "unit": "GB/s",
+           "peak": hbm_peak, "frac": round(ach / hbm_peak, 4), "frac_of_8TBps": round(ach / 8000.0, 4),
+           "effective_gbs_on_logical_bytes": round(logical_bytes / us / 1e3, 1),
+           "per_row_kernel_us": round(us_row, 2), "max_abs_err_vs_oracle": err, "parity_ok": ok,
+           "oracle_sample": "3 (row, head) pairs at full context"}
+    del caches, q, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def c5_splitkv(dev, world, rank, hbm_peak, ctx=131072, iters=30):
+    """One sequence of `ctx` tokens, pages split over the ranks.  Parity first (small shape, EVERY rank's output of
+    every exchange form against the CPU oracle over the whole sequence), then timing at full size."""
+    import llm_decoder as ld
+    from llm_decoder import dist as pd
+    tests = os.path.join(ROOT, "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    from synth import make_case, oracle_attention
+    temp = float(np.sqrt(D))
+    multi = world > 1
+    # ---- parity at the check shape (4 heads x 2048 tokens; f16 and int8 pages) ----
+    errs = {}
+    for kv in ("f16", "i8"):
+        case = make_case(B=1, H=4, D=D, T=2048, seed=55, kv=kv)      # identical on every rank (seeded)
+        exp = oracle_attention(case)
+        nt = case["num_tiles"]
+        t0, t1 = pd.page_range(nt, world, rank)
+        kvc = ld.KVTileCache(kv, device=dev)
+        args = [torch.from_numpy(case["k_pool"]).to(dev), torch.from_numpy(case["v_pool"]).to(dev)]
+        if kv == "i8":
+            args += [torch.from_numpy(case["k_scales"]).to(dev), torch.from_numpy(case["v_scales"]).to(dev)]
+        kvc.adopt_buffers(*args)
+        kvc.configure_table(1, 4, t1 - t0)
+        kvc.page_table_.load_host_table(np.ascontiguousarray(case["table"][:, :, t0:t1]))
+        q = torch.from_numpy(case["q"]).to(dev)
+        forms = {"fused": pd.PeerExchange(4, D), "p2p": pd.PeerExchange(4, D)}
+        if multi:
+            forms["nccl"] = pd.NcclCombine(4, D)
+        for name, ex in forms.items():
+            e = 0.0
+            for _ in range(3):  # three steps: epochs and buffer parity advance
+                o = pd.split_kv_decode(q, kvc, 1, (t1 - t0) * TILE, temp, exchange=ex, fused=(name == "fused"))
+                torch.cuda.synchronize(dev)
+                e = max(e, float(np.abs(o.cpu().numpy() - exp).max()))
+                assert np.allclose(o.cpu().numpy(), exp, rtol=2e-3, atol=1e-3), (kv, name, rank, e)
+            t = torch.tensor([e], device=dev, dtype=torch.float64)
+            if multi:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)   # worst rank
+            errs[f"{kv}_{name}"] = float(t.item())
+        for ex in forms.values():
+            ex.close()
+        del kvc
+    # ---- timing at full size ----
+    nt = ctx // TILE
+    t0, t1 = pd.page_range(nt, world, rank)
+    nt_loc = t1 - t0
+    P = H * nt_loc
+    kv_bytes_rank = H * nt_loc * TILE * D * 2 * 2
+    nsets = max(2, -(-(3 * 126 << 20) // kv_bytes_rank))
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    caches = []
+    for _ in range(nsets):
+        k = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        v = torch.randn((P, TILE, D), generator=g, device=dev, dtype=torch.float16)
+        kvc = ld.KVTileCache("f16", device=dev)
+        kvc.adopt_buffers(k, v)
+        kvc.configure_table(1, H, nt_loc)
+        kvc.page_table_.load_host_table(torch.randperm(P, generator=g, device=dev).to(torch.int32).cpu().numpy().reshape(1, H, nt_loc))
+        caches.append(kvc)
+    q = torch.randn((1, H, D), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    Tl = nt_loc * TILE
+    fused, p2p = pd.PeerExchange(H, D), pd.PeerExchange(H, D)
+    res_us = {}
+    res_us["partial_only"] = graph_time([lambda c=c: ld.paged_decode_partial(q, c, 1, Tl, temp) for c in caches], iters, dev, world,
+                                        per=nsets)
+    res_us["fused_one_launch"] = graph_time([lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=fused, fused=True)
+                                             for c in caches], iters, dev, world, per=nsets)
+    res_us["partial_plus_p2p_kernel"] = graph_time([lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=p2p)
+                                                    for c in caches], iters, dev, world, per=nsets)
+    outs = {"fused": pd.split_kv_decode(q, caches[0], 1, Tl, temp, exchange=fused, fused=True).clone(),
+            "p2p": pd.split_kv_decode(q, caches[0], 1, Tl, temp, exchange=p2p).clone()}
+    if multi:
+        nc = pd.NcclCombine(H, D)
+        res_us["partial_plus_nccl_allgather_combine"] = graph_time(
+            [lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=nc) for c in caches], iters, dev, world, per=nsets)
+        outs["nccl"] = pd.split_kv_decode(q, caches[0], 1, Tl, temp, exchange=nc).clone()
+    torch.cuda.synchronize(dev)
+    fused.check()
+    p2p.check()
+    agree = max(float((outs["fused"] - o).abs().max().item()) for o in outs.values())
+    us = res_us["fused_one_launch"][0]
+    ach = kv_bytes_rank / us / 1e3
+    res = {"workload": f"C5: 1 sequence x {ctx} ctx, {H} heads, D=128, fp16 KV pages split over {world} GPU(s)",
+           "kernel": "paged_decode_overlap_kernel<128,f16,8,3> (one static chunk per warp, in-kernel merge + exchange)",
+           "n_gpus": world, "kv_bytes_per_gpu": kv_bytes_rank, "payload_bytes_per_rank": H * (D + 2) * 4,
+           "us": round(us, 2), "us_min": round(res_us["fused_one_launch"][1], 2),
+           "us_by_form": {k: round(v[0], 2) for k, v in res_us.items()},
+           "exchange_overhead_us": round(us - res_us["partial_only"][0], 2),
+           "achieved": round(ach, 1), "unit": "GB/s per GPU", "peak": hbm_peak, "frac": round(ach / hbm_peak, 4),
+           "frac_of_8TBps": round(ach / 8000.0, 4), "roofline_us_at_8TBps": round(kv_bytes_rank / 8e6, 2),
+           "max_abs_err_vs_oracle": max(errs.values()), "parity_by_form_worst_rank": errs,
+           "parity_ok": True, "oracle_sample": "check shape (4 heads x 2048 ctx, f16 and int8 pages), every rank, every form, 3 steps",
+           "forms_agree_full_size_max_abs_diff": agree,
+           "l2": f"{nsets} page sets used round-robin (> 3x L2)"}
+    if multi:
+        nc.close()
+    fused.close()
+    p2p.close()
+    del caches
+    torch.cuda.empty_cache()
+    return res

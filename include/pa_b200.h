@@ -394,8 +394,8 @@ int pa_p2p_free(void* d_ptr);
  * this rank's own buffer at index `rank`) as 16-byte packets that carry their own epoch flag --
  * sending never blocks; at the end of the same kernel every row's `world` partials are received
  * from the local buffer and LSE-combined into d_out [B, H, D] (identical on every rank).
- * d_epochs [B*H] u32: per-row step counters in device memory, zero-initialised once (the launch is
- * CUDA-graph replayable); *d_status is set to 1, the row written as NaN and its epoch NOT advanced if a
+ * d_epochs [2*B*H] u32: per-row step counters (first half) and self-resetting row-completion counters (second
+ * half) in device memory, zero-initialised ONCE by the caller (the launch is CUDA-graph replayable); *d_status is set to 1, the row written as NaN and its epoch NOT advanced if a
  * peer does not arrive within ~2 s.  Exchange buffers must be sized for rows = B*num_heads. */
 int pa_paged_decode_f16_splitkv(const float* d_q, float* d_out, const void* d_k_pool,
                                 const void* d_v_pool, const int32_t* d_table, int num_beams,

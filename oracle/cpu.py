@@ -68,6 +68,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_threads(n):
+    """omp_set_num_threads for the oracle's loops (explicit, so OMP_NUM_THREADS=1 from torchrun does not apply)."""
+    lib().orc_set_threads(int(n))
+    return num_threads()
+
+
 # ---- page table / pool addressing -------------------------------------------------
 def pt_index(beam, head, tile, num_heads, num_tiles):
     return int(lib().orc_pt_index(int(beam), int(head), int(tile), int(num_heads), int(num_tiles)))

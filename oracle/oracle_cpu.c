@@ -608,6 +608,16 @@ ORC_API void orc_apply_rotary_embedding(float* q, float* k, const float* rotary_
     }
 }
 
+/* Thread count of the OpenMP loops (bench.py sets it to the box's core count: under torchrun the environment
+ * carries OMP_NUM_THREADS=1, which would otherwise make the CPU baseline single-threaded). */
+ORC_API void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -320,12 +320,123 @@ __device__ __forceinline__ int lookup_page(const DecodeArgs& a, int beam, int h,
     return (page < 0 || page >= a.total_pages) ? -1 : page;
 }
 
+// ---- row merge by ONE warp -------------------------------------------------------------------------------------
+// Reads `nc` partials (slots s0 .. s0+nc, log2-domain m) straight from L2 (ld.global.cg: they were written by other
+// SMs); lane l ends up with O for dims l*VEC .. l*VEC+VEC and the (M, L) of the merged range.
+__device__ __forceinline__ float ldcg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int D>
+__device__ __forceinline__ void merge_row_warp(const DecodeArgs& a, int64_t s0, int nc, int lane, float& M, float& L,
+                                               float (&O)[D / 32]) {
+    // Online merge in groups of G partials: all loads of a group (the G partial rows of 512 B, and m / l of the
+    // group on lanes < G) are issued together, so a group costs ONE L2 round trip; the running maximum is raised
+    // per group and the accumulator rescaled (a row of 37 chunks -- one GPU's share of a 128K-token sequence --
+    // merges in 3 round trips instead of 37 dependent ones).
+    constexpr int VEC = D / 32, G = 16;
+    M = -INFINITY;
+    float Lw = 0.f;  // lane-partial sum of l (lanes < G)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) O[e] = 0.f;
+    for (int base = 0; base < nc; base += G) {
+        const int cnt = min(G, nc - base);
+        float v[G][VEC];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            if (t < cnt) {
+                const float* src = a.ws_o + (s0 + base + t) * D + lane * VEC;
+                if (VEC == 4) {
+                    const float4 x = __ldcg(reinterpret_cast<const float4*>(src));
+                    v[t][0] = x.x; v[t][1] = x.y; v[t][2 % VEC] = x.z; v[t][3 % VEC] = x.w;
+                } else {
+                    const float2 x = __ldcg(reinterpret_cast<const float2*>(src));
+                    v[t][0] = x.x; v[t][1] = x.y;
+                }
+            }
+        }
+        float mj = -INFINITY, lj = 0.f;
+        if (lane < cnt) {
+            mj = ldcg_f32(a.ws_m + s0 + base + lane);
+            lj = ldcg_f32(a.ws_l + s0 + base + lane);
+        }
+        const float Mn = fmaxf(M, warp_max(mj));
+        const float corr = (M == -INFINITY) ? 0.f : fast_exp2(M - Mn);  // Mn == -inf only if everything so far is empty
+        const float wt = (mj == -INFINITY) ? 0.f : fast_exp2(mj - Mn);
+        Lw = fmaf(Lw, corr, lj * wt);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) O[e] *= corr;
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            if (t < cnt) {
+                const float w = __shfl_sync(0xffffffffu, wt, t);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) O[e] = fmaf(v[t][e], w, O[e]);
+            }
+        }
+        M = Mn;
+    }
+    L = warp_sum(Lw);
+}
+
+// Final / partial / exchange emit of a merged row held as above (M in log2 units).
+template <int D>
+__device__ __forceinline__ void emit_merged_row(const DecodeArgs& a, int64_t row, int lane, float M, float L,
+                                                const float (&O)[D / 32]) {
+    constexpr int VEC = D / 32;
+    if (a.xch_peers) {  // send only (never blocks); the row is received and combined at the end of the kernel
+        xchg::send_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, (int64_t)a.B * a.H, row, O, M * kLn2, L, lane);
+        return;
+    }
+    if (a.part_m) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
+        if (lane == 0) {
+            a.part_m[row] = M * kLn2;  // natural-log units at the API
+            a.part_l[row] = L;
+        }
+        return;
+    }
+    const float inv = 1.f / (L + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = O[e] * inv;
+    if (lane == 0 && a.lse_out) a.lse_out[row] = (L > 0.f) ? (M + log2f(L)) * kLn2 : -INFINITY;
+}
+
+// Cold tails of the streaming kernel, kept OUT of line (and only in its TAIL instance): inlined -- or merely present
+// as calls -- their registers cost the 16-warp int8 instance (128-register cap) its allocation in the hot loop
+// (1.49 -> 2.6 ms at C4).
+template <int D>
+__device__ __noinline__ void tail_merge_row(const DecodeArgs& a, int64_t s0, int nc, int64_t row, int lane) {
+    float M, L, O[D / 32];
+    merge_row_warp<D>(a, s0, nc, lane, M, L, O);
+    emit_merged_row<D>(a, row, lane, M, L, O);
+}
+template <int D>
+__device__ __noinline__ void tail_empty_row(const DecodeArgs& a, int64_t row, int lane) {
+    float O[D / 32];
+#pragma unroll
+    for (int e = 0; e < D / 32; ++e) O[e] = 0.f;
+    emit_merged_row<D>(a, row, lane, -INFINITY, 0.f, O);
+}
+template <int D>
+__device__ __noinline__ void tail_recv_rows(const DecodeArgs& a, int64_t first, int64_t stride, int lane) {
+    const int64_t nrows = (int64_t)a.B * a.H;
+    for (int64_t row = first; row < nrows; row += stride)
+        xchg::recv_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, a.out, a.lse_out, a.xch_status,
+                          lane);
+}
+
 // ------------------------------------------------------------------ direct (a1)
 template <int D, int KV>
 __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeArgs a) {
     using C = Cfg<D, KV>;
     constexpr int NW = 4;
     __shared__ float red[NW * (D + 2)];
+    // A grid launched with programmatic stream serialisation after this one (splitkv_merge_exchange_kernel) may
+    // become resident as soon as every CTA here has started; it waits for this grid's completion itself.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t row = blockIdx.x;
     const int split = blockIdx.y;
     const int b = (int)(row / a.H), h = (int)(row % a.H);
@@ -379,77 +490,9 @@ __global__ void __launch_bounds__(128) paged_decode_direct_kernel(const DecodeAr
         unit_update<D, KV>(kf, vf, ksc, vsc, q, qoff, nvalid, g, acc);
     }
 
-    const bool final_row = (a.num_splits == 1);
+    const bool final_row = (a.num_splits == 1) && !a.xch_peers;  // across GPUs the row always goes through the workspace
     cta_merge_emit<D, KV, NW>(red, acc, warp, lane, a, final_row ? kEmitFinal : kEmitWorkspace, row,
                               row * a.num_splits + split);
-}
-
-// ---- row merge by ONE warp (streaming kernel: the warp that finishes the LAST chunk of a row merges it) ----
-// Reads the row's `nc` chunk partials (slots s0 .. s0+nc, log2-domain m) straight from L2 (ld.global.cg: they
-// were written by other SMs), lane l ends up with O for dims l*VEC .. l*VEC+VEC and the row's (M, L).
-__device__ __forceinline__ float ldcg_f32(const float* p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-template <int D>
-__device__ __forceinline__ void merge_row_warp(const DecodeArgs& a, int64_t s0, int nc, int lane, float& M, float& L,
-                                               float (&O)[D / 32]) {
-    constexpr int VEC = D / 32;
-    float mloc = -INFINITY;
-    for (int i = lane; i < nc; i += 32) mloc = fmaxf(mloc, ldcg_f32(a.ws_m + s0 + i));
-    M = warp_max(mloc);
-    float Lw = 0.f;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) O[e] = 0.f;
-    for (int base = 0; base < nc; base += 32) {
-        const int i = base + lane;
-        float wt = 0.f;
-        if (i < nc) {
-            const float mj = ldcg_f32(a.ws_m + s0 + i);
-            wt = (mj == -INFINITY) ? 0.f : fast_exp2(mj - M);
-            Lw = fmaf(ldcg_f32(a.ws_l + s0 + i), wt, Lw);
-        }
-        const int cnt = min(32, nc - base);
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            const float w = __shfl_sync(0xffffffffu, wt, t);
-            const float* src = a.ws_o + (s0 + base + t) * D + lane * VEC;
-            if (VEC == 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
-                O[2 % VEC] = fmaf(v.z, w, O[2 % VEC]); O[3 % VEC] = fmaf(v.w, w, O[3 % VEC]);
-            } else {
-                const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
-                O[0] = fmaf(v.x, w, O[0]); O[1] = fmaf(v.y, w, O[1]);
-            }
-        }
-    }
-    L = warp_sum(Lw);
-}
-
-// Final / partial / exchange emit of a merged row held as above (M in log2 units).
-template <int D>
-__device__ __forceinline__ void emit_merged_row(const DecodeArgs& a, int64_t row, int lane, float M, float L,
-                                                const float (&O)[D / 32]) {
-    constexpr int VEC = D / 32;
-    if (a.xch_peers) {  // send only (never blocks); the row is received and combined at the end of the kernel
-        xchg::send_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, (int64_t)a.B * a.H, row, O, M * kLn2, L, lane);
-        return;
-    }
-    if (a.part_m) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
-        if (lane == 0) {
-            a.part_m[row] = M * kLn2;  // natural-log units at the API
-            a.part_l[row] = L;
-        }
-        return;
-    }
-    const float inv = 1.f / (L + 1e-6f);  // softmax_lut.cpp:224 epsilon (App. A D4)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) a.out[row * D + lane * VEC + e] = O[e] * inv;
-    if (lane == 0 && a.lse_out) a.lse_out[row] = (L > 0.f) ? (M + log2f(L)) * kLn2 : -INFINITY;
 }
 
 // ---------------------------------------------------------------- overlap (a2)
@@ -496,7 +539,9 @@ struct ChunkMap {
 
 __device__ __forceinline__ int units_of_ctx(int ctx) { return (ctx + kUnitTok - 1) / kUnitTok; }
 
-template <int D, int KV, int NW, int S>
+// TAIL: the instance that can merge rows in-kernel / exchange them across GPUs (a.row_done != null).  The plain
+// instance carries none of that code (see the note at tail_merge_row).
+template <int D, int KV, int NW, int S, bool TAIL>
 __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const DecodeArgs a, int cu,
                                                                           unsigned int* counter) {
     using C = Cfg<D, KV>;
@@ -568,6 +613,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
             id = gw;  // first chunk is static: no atomic on the critical path of the prologue
             p_first = false;
         } else {
+            if (total <= total_warps) return false;  // one static chunk per warp: nothing to fetch
             unsigned int t = 0;
             if (lane == 0) t = atomicAdd(counter, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
@@ -693,7 +739,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         }
         // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
         warp_merge<D, KV>(acc);
-        const bool final_row = (nc == 1) && !a.xch_peers;
+        const bool final_row = (nc == 1) && !(TAIL && a.xch_peers);
         if (final_row) {
             if (lane < 8) {
                 if (!a.part_m) {
@@ -721,7 +767,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
                 a.ws_l[id] = acc.l;
             }
         }
-        if (a.row_done) {
+        if (TAIL && a.row_done) {
             // The warp that completes the LAST chunk of a row merges the row here (no second launch): partial
             // visible device-wide -> count -> the last arrival reads all nc partials back from L2.
             __threadfence();
@@ -731,31 +777,64 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
             prev = __shfl_sync(0xffffffffu, prev, 0);
             if (prev + 1u == (unsigned)nc) {
                 __threadfence();
-                float M, L, O[D / 32];
-                merge_row_warp<D>(a, id - j, nc, lane, M, L, O);
-                emit_merged_row<D>(a, row, lane, M, L, O);
+                if (lane == 0) a.row_done[row] = 0u;  // self-resetting: counters handed over zeroed stay zeroed
+                tail_merge_row<D>(a, id - j, nc, row, lane);
             }
         }
     }
     // Rows without a single chunk (context length 0) are emitted as "no keys": out = 0, lse = -inf.
-    if (a.row_done && (cm.prefix || cm.NC == 0)) {
+    if (TAIL && a.row_done && (cm.prefix || cm.NC == 0)) {
         const int64_t nrows0 = (int64_t)a.B * Hh;
         for (int64_t row = gw; row < nrows0; row += total_warps) {
-            if (cm.nchunks_of((int)(row / Hh)) != 0) continue;
-            float O[D / 32];
-#pragma unroll
-            for (int e = 0; e < D / 32; ++e) O[e] = 0.f;
-            emit_merged_row<D>(a, row, lane, -INFINITY, 0.f, O);
+            if (cm.nchunks_of((int)(row / Hh)) == 0) tail_empty_row<D>(a, row, lane);
         }
     }
     // ---- split-KV across GPUs: receive + combine.  Every row's partial has been (or will be) SENT by the warp
     // that merged it, on this rank and on the peers; sends never block, so polling here cannot deadlock. ----
-    if (a.xch_peers) {
-        const int64_t nrows = (int64_t)a.B * Hh;
-        for (int64_t row = gw; row < nrows; row += total_warps)
-            xchg::recv_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, a.out, a.lse_out,
-                              a.xch_status, lane);
+    if (TAIL && a.xch_peers) tail_recv_rows<D>(a, gw, total_warps, lane);
+}
+
+// ---- split-KV grid kernel across GPUs: merge + exchange as a PROGRAMMATICALLY DEPENDENT launch ----------------------
+// One CTA per row, launched with programmatic stream serialisation right behind paged_decode_direct_kernel: its CTAs
+// are resident before the decode grid has finished (the launch latency and ramp of a second kernel disappear) and
+// block in griddepcontrol.wait until the split partials are complete and visible.  Warp w merges splits
+// [16w, 16w + 16) (two L2 round trips), the four results meet in shared memory, warp 0 sends the row to every peer
+// and receives / combines the peers' rows.
+template <int D>
+__global__ void __launch_bounds__(128) splitkv_merge_exchange_kernel(const DecodeArgs a) {
+    constexpr int VEC = D / 32;
+    __shared__ float red[4 * (D + 2)];
+    const int64_t row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int s_lo = warp * 16, n_mine = max(0, min(16, a.num_splits - s_lo));
+    float M, L, O[VEC];
+    merge_row_warp<D>(a, row * a.num_splits + s_lo, n_mine, lane, M, L, O);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) red[warp * (D + 2) + lane * VEC + e] = O[e];
+    if (lane == 0) {
+        red[warp * (D + 2) + D] = M;
+        red[warp * (D + 2) + D + 1] = L;
     }
+    __syncthreads();
+    if (warp != 0) return;
+    float Mg = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) Mg = fmaxf(Mg, red[w * (D + 2) + D]);
+    float Lg = 0.f;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) O[e] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const float mw = red[w * (D + 2) + D];
+        const float wt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - Mg);
+        Lg = fmaf(red[w * (D + 2) + D + 1], wt, Lg);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) O[e] = fmaf(red[w * (D + 2) + lane * VEC + e], wt, O[e]);
+    }
+    const int64_t nrows = (int64_t)a.B * a.H;
+    xchg::send_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, O, Mg * kLn2, Lg, lane);
+    xchg::recv_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, a.out, a.lse_out, a.xch_status, lane);
 }
 
 // Merge the per-chunk partials of every row (rows of a single chunk were finished by the main
@@ -1331,10 +1410,15 @@ static int choose_splits(int64_t rows, int max_units, int sm_count) {
 //    per-chunk overheads, every warp streams the same number of units and the row merge happens in-kernel;
 //  * otherwise 16 units (128 KiB of fp16 K+V at D=128) when that still yields >= 4 chunks per resident warp,
 //    fewer for small problems so every warp gets work; chunks are dispatched dynamically.
-static int choose_cu(int64_t rows, int max_units, int sm_count, int nw) {
+static int choose_cu(int64_t rows, int max_units, int sm_count, int nw, bool prefer_static = false) {
     const int64_t warps = (int64_t)sm_count * nw;
     const int64_t total = rows * (int64_t)max_units;
-    if (rows > 0 && rows <= warps && total <= warps * 64 && max_units > 0) {
+    // prefer_static (inter-GPU exchange: rows are merged in-kernel, which costs a device-wide fence per finished
+    // chunk): one chunk per warp whatever the size -- a static split loses some % to SM-to-SM rate differences on long
+    // jobs (measured 5 % at 1 GB), less than ~14 fences + a 512-chunk row merge per warp would (25 %).
+    const char* st_env = getenv("PA_DECODE_STATIC");  // experiments: 0 = never one static chunk per warp, 1 = whenever possible
+    if (st_env) prefer_static = atoi(st_env) == 1;
+    if (rows > 0 && rows <= warps && !(st_env && atoi(st_env) == 0) && (prefer_static || total <= warps * 64) && max_units > 0) {
         const int64_t per_row = warps / rows;
         const int64_t cu1 = (max_units + per_row - 1) / per_row;
         const int64_t chunks = rows * ((max_units + cu1 - 1) / cu1);
@@ -1351,9 +1435,11 @@ static int choose_cu(int64_t rows, int max_units, int sm_count, int nw) {
 static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
     size_t ov = 0;
     for (int nw : {4, 8, 16}) {  // the streaming-kernel instances differ in warps per CTA; size for the largest need
-        const int cu = choose_cu(rows, max_units, sm_count, nw);
-        const size_t v = (size_t)rows * ((max_units + cu - 1) / cu);
-        if (v > ov) ov = v;
+        for (int st = 0; st < 2; ++st) {
+            const int cu = choose_cu(rows, max_units, sm_count, nw, st == 1);
+            const size_t v = (size_t)rows * ((max_units + cu - 1) / cu);
+            if (v > ov) ov = v;
+        }
     }
     size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
     // beam-group kernel: chunk size chosen from the number of (group, head) pairs, >= rows / 4
@@ -1389,7 +1475,33 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     a.ws_m = w;
     a.ws_l = w + nslots;
     a.ws_o = w + 2 * nslots;
-    if (a.xch_peers) overlap = true;  // the inter-GPU exchange lives in the streaming kernel
+    if (a.xch_peers) {
+        // Inter-GPU exchange.  Up to ~0.5 GB of K/V per GPU (C5: 268 MB) the split-KV grid kernel streams fastest
+        // (one GPU's C5 share: 46 us vs 56 us for the streaming kernel, whose static split waits for the slowest SM),
+        // so: grid kernel -> row partials in the workspace -> merge + exchange kernel chained by PROGRAMMATIC
+        // DEPENDENT LAUNCH (resident before the decode grid ends, no launch gap).  Above that size: the streaming
+        // kernel, ONE launch.  PA_PARTIAL_DIRECT=0 / 1 forces either.
+        const char* env = getenv("PA_PARTIAL_DIRECT");
+        overlap = env ? atoi(env) != 1 : !(rows * (int64_t)max_units <= 65536 && rows <= 1024);
+        if (!overlap) {
+            a.num_splits = choose_splits(rows, max_units, di.sm_count);  // <= 64 = 4 warps x 16 in the merge kernel
+            dim3 grid((unsigned)rows, (unsigned)a.num_splits);
+            paged_decode_direct_kernel<D, KV><<<grid, 128, 0, st>>>(a);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)rows);
+            cfg.blockDim = dim3(128);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, splitkv_merge_exchange_kernel<D>, a);
+            return e == cudaSuccess ? PA_OK : (int)e;
+        }
+    }
     if (!overlap) {
         a.num_splits = choose_splits(rows, max_units, di.sm_count);
         dim3 grid((unsigned)rows, (unsigned)a.num_splits);
@@ -1411,21 +1523,30 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     using C = Cfg<D, KV>;
     const int G = di.sm_count;
     constexpr int NWk = OvCfg<D, KV>::NW;
-    const int cu = choose_cu(rows, max_units, di.sm_count, NWk);
+    const int cu = choose_cu(rows, max_units, di.sm_count, NWk, a.xch_peers != nullptr);
     const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
     const size_t smem = (size_t)NWk * S * C::STAGE_BYTES + (size_t)NWk * S * (8 + 4) + 8 +
                         (size_t)NWk * 16 * sizeof(int64_t) + prefix_bytes;
     if (smem > (size_t)di.max_smem_optin) return PA_ERR_UNSUPPORTED;  // B too large for the prefix table
-    auto kern = paged_decode_overlap_kernel<D, KV, NWk, S>;
+    // Rows are merged IN-KERNEL (the warp that finishes a row's last chunk merges it) only where that pays.  Measured
+    // at C2 (27.7 chunks per warp): the device-wide fence + counter per finished chunk stall a streaming warp ~1.5 us
+    // each = 5 % of the launch, more than the second launch costs (9 us of 640).  So: in-kernel where a warp
+    // finishes ONE chunk (static mode: a GPU's share of a long sequence, where the second launch is ~10 % of the
+    // step) and across GPUs (the exchange needs it); the separate merge kernel otherwise.
+    // PA_DECODE_MERGE_KERNEL=0 / 1 forces in-kernel / separate merging where both are possible.
+    const bool static_chunks = rows * (int64_t)((max_units + cu - 1) / cu) <= (int64_t)G * NWk;
+    const char* merge_env = getenv("PA_DECODE_MERGE_KERNEL");
+    const bool fused_merge = a.xch_peers || (merge_env ? atoi(merge_env) == 0 : static_chunks);
+    a.row_done = fused_merge ? counter + 64 : nullptr;
+    // Across GPUs with one static chunk per warp nothing in the workspace header is needed: the chunk counter is not
+    // used and the row counters live behind the caller's zero-initialised, self-resetting epoch array (d_epochs
+    // [2 * rows]) -- no memset node in front of the kernel (~2 us of a ~50 us step).
+    const bool no_memset = a.xch_peers && static_chunks;
+    if (no_memset) a.row_done = a.xch_epochs + rows;
+    auto kern = fused_merge ? paged_decode_overlap_kernel<D, KV, NWk, S, true> : paged_decode_overlap_kernel<D, KV, NWk, S, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    // ONE launch: the warp that finishes the last chunk of a row merges the row (and, across GPUs, sends it; rows
-    // are received at the end of the same kernel).  PA_DECODE_MERGE_KERNEL=1 restores the separate merge kernel
-    // (kept for A/B measurements; not available with the inter-GPU exchange).
-    static const bool separate_merge = getenv("PA_DECODE_MERGE_KERNEL") && atoi(getenv("PA_DECODE_MERGE_KERNEL")) == 1;
-    const bool fused_merge = a.xch_peers || !separate_merge;
-    a.row_done = fused_merge ? counter + 64 : nullptr;
-    e = cudaMemsetAsync(ws, 0, fused_merge ? ws_header_bytes(rows) : sizeof(unsigned int), st);
+    if (!no_memset) e = cudaMemsetAsync(ws, 0, fused_merge ? ws_header_bytes(rows) : sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     kern<<<G, NWk * 32, smem, st>>>(a, cu, counter);
     e = cudaGetLastError();

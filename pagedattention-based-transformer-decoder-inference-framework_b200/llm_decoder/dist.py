@@ -83,7 +83,8 @@ class PeerExchange:
         from . import _cabi
         self._cabi, self._C = _cabi, C
         self.rows, self.D, self.group = rows, head_dim, group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._dist = dist.is_available() and dist.is_initialized()   # a single process is a world of one rank
+        self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if self._dist else (1, 0)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         lib = _cabi.lib()
         nbytes = lib.pa_splitkv_exchange_bytes(self.world, rows, head_dim)
@@ -91,8 +92,10 @@ class PeerExchange:
             self._own = C.c_void_p()
             handle = C.create_string_buffer(64)
             _cabi.check(lib.pa_p2p_alloc(nbytes, C.byref(self._own), handle), "pa_p2p_alloc")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            handles = [bytes(handle.raw)]
+            if self._dist:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
             self._peers, ptrs = [], []
             for r, h in enumerate(handles):
                 if r == self.rank:
@@ -104,8 +107,10 @@ class PeerExchange:
                 ptrs.append(p.value)
             self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64).to(self.device)
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self.epochs = torch.zeros(rows, dtype=torch.int32, device=self.device)  # advanced by the kernel
-        dist.barrier(group=group)  # every buffer is mapped (and zeroed) before the first kernel runs
+            # [rows] step counters advanced by the kernels + [rows] self-resetting row-completion counters
+            self.epochs = torch.zeros(2 * rows, dtype=torch.int32, device=self.device)
+        if self._dist:
+            dist.barrier(group=group)  # every buffer is mapped (and zeroed) before the first kernel runs
 
     def combine(self, part_m, part_l, part_o, out=None, lse_out=None):
         """part_m/l [rows], part_o [rows, D] (this rank's partials) -> out [rows, D] on every rank."""
@@ -154,7 +159,8 @@ class PeerExchange:
 
     def close(self):
         lib = self._cabi.lib()
-        dist.barrier(group=self.group)
+        if self._dist:
+            dist.barrier(group=self.group)
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             self.check()

@@ -921,16 +921,20 @@ def _splitkv(ld, case, kvc, ptrs, rank, world, epochs, status, out, stream=None)
     return q
 
 
+@pytest.mark.parametrize("path", ["grid", "streaming"])
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 @pytest.mark.parametrize("shape", [dict(B=1, H=8, D=128, T=4096), dict(B=3, H=4, D=64, T=400)])
-def test_fused_splitkv_world1_is_the_plain_decode(ld, oracle, kv, shape):
+def test_fused_splitkv_world1_is_the_plain_decode(ld, oracle, kv, shape, path, monkeypatch):
     """pa_paged_decode_*_splitkv with a world of one rank: decode + in-kernel row merge + send to its own buffer +
-    receive + combine, all in one launch, three steps in a row (epochs / buffer parity advance)."""
+    receive + combine, all in one launch, three steps in a row (epochs / buffer parity advance).  Both single-launch
+    kernels: the split-KV grid kernel (exchange in the tail of each row's last CTA; default below ~0.5 GB of K/V)
+    and the streaming kernel (PA_PARTIAL_DIRECT=0)."""
+    monkeypatch.setenv("PA_PARTIAL_DIRECT", "1" if path == "grid" else "0")
     case = make_case(seed=61, kv=kv, **shape)
     B, H, D = case["q"].shape
     bufs, ptrs = _peer_buffers(ld, 1, B * H, D)
     kvc = to_device_cache(case)
-    epochs = torch.zeros(B * H, dtype=torch.int32, device="cuda")
+    epochs = torch.zeros(2 * B * H, dtype=torch.int32, device="cuda")   # step counters + row-completion counters
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     exp = oracle_attention(case)
     for step in range(3):
@@ -938,12 +942,14 @@ def test_fused_splitkv_world1_is_the_plain_decode(ld, oracle, kv, shape):
         _splitkv(ld, case, kvc, ptrs, 0, 1, epochs, status, out)
         torch.cuda.synchronize()
         np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
-        assert int(status.item()) == 0 and (epochs.cpu().numpy() == step + 1).all()
+        ep = epochs.cpu().numpy()
+        assert int(status.item()) == 0 and (ep[:B * H] == step + 1).all() and (ep[B * H:] == 0).all()
     _free_buffers(bufs)
 
 
+@pytest.mark.parametrize("path", ["grid", "streaming"])
 @pytest.mark.parametrize("kv", ["f16", "i8"])
-def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv):
+def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv, path, monkeypatch):
     """Two 'ranks' on one device, each holding half of the sequence's pages.  Rank 1 runs the stand-alone exchange
     kernel (partials -> pa_splitkv_exchange_combine) on its own stream: it sends, then polls for rank 0.  Rank 0 runs
     the FUSED kernel (pa_paged_decode_*_splitkv) on another stream: it streams its pages, merges, sends to both
@@ -951,12 +957,13 @@ def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv):
     oracle over the WHOLE sequence; two steps (buffer parity flips)."""
     from llm_decoder import _cabi
     lib = _cabi.lib()
+    monkeypatch.setenv("PA_PARTIAL_DIRECT", "1" if path == "grid" else "0")
     case = make_case(B=1, H=8, D=128, T=4096, seed=62, kv=kv)
     B, H, D = case["q"].shape
     rows = B * H
     bufs, ptrs = _peer_buffers(ld, 2, rows, D)
     caches = [_rank_cache(case, 2, r) for r in range(2)]
-    epochs = [torch.zeros(rows, dtype=torch.int32, device="cuda") for _ in range(2)]
+    epochs = [torch.zeros(2 * rows, dtype=torch.int32, device="cuda") for _ in range(2)]
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     exp = oracle_attention(case)
     s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -1028,14 +1035,24 @@ def test_nccl_allgather_combine_single_rank(ld, oracle):
     _cabi.check(lib.pa_nccl_destroy(comm), "pa_nccl_destroy")
 
 
-def test_fused_row_merge_equals_separate_merge_kernel(ld, oracle):
-    """The in-kernel row merge (default) against the two-launch form (PA_DECODE_MERGE_KERNEL=1 is read once per
-    process, so the comparison is against the oracle and the split-KV grid kernel instead): ragged rows incl. a row
-    of length 0 and rows of a single chunk."""
-    case = make_case(B=6, H=3, D=128, T=1500, seed=64, ragged=True)
-    a, lse_a = run_decode(ld, case, True)
-    b, lse_b = run_decode(ld, case, False)
-    np.testing.assert_allclose(a, oracle_attention(case), rtol=RTOL, atol=ATOL)
-    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
-    assert (a[1] == 0).all() and np.isneginf(lse_a[1]).all()      # ctx_lens[1] == 0: no keys
-    np.testing.assert_allclose(lse_a[lse_a > -np.inf], lse_b[lse_b > -np.inf], rtol=1e-5, atol=1e-5)
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_in_kernel_row_merge_equals_separate_merge_kernel(ld, oracle, kv, monkeypatch):
+    """The streaming kernel merges a row in-kernel (last-arriving warp; default for one-chunk-per-warp jobs and for
+    the inter-GPU exchange) or leaves it to the merge kernel (default otherwise).  PA_DECODE_MERGE_KERNEL=0 / 1
+    forces either: same results on ragged rows incl. a row of length 0 and rows of a single chunk."""
+    case = make_case(B=6, H=3, D=128, T=1500, seed=64, ragged=True, kv=kv)
+    exp = oracle_attention(case)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PA_DECODE_MERGE_KERNEL", mode)
+        res[mode] = run_decode(ld, case, True)
+        np.testing.assert_allclose(res[mode][0], exp, rtol=RTOL, atol=ATOL)
+        assert (res[mode][0][1] == 0).all() and np.isneginf(res[mode][1][1]).all()      # ctx_lens[1] == 0: no keys
+    monkeypatch.delenv("PA_DECODE_MERGE_KERNEL")
+    np.testing.assert_allclose(res["0"][0], res["1"][0], rtol=1e-5, atol=1e-6)
+    fin = res["0"][1] > -np.inf
+    np.testing.assert_allclose(res["0"][1][fin], res["1"][1][fin], rtol=1e-5, atol=1e-5)
+    # one static chunk per warp (a long row on few heads): in-kernel merge by default
+    long_case = make_case(B=1, H=4, D=128, T=16384, seed=65, kv=kv)
+    got, _ = run_decode(ld, long_case, True)
+    np.testing.assert_allclose(got, oracle_attention(long_case), rtol=RTOL, atol=ATOL)
