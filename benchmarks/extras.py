@@ -174,11 +174,56 @@ def c4_gemm_pair(dev, M=256, iters=10):
     def fc2(i):
         assert ld.dnnl_matmul_int8(h8, W2[i], y8, 1, M, HID, INTER, 1 / 16, 1 / 16, 32.0, b2, "")
 
+    ops1 = 2.0 * M * HID * INTER
+    tops = lambda us, n=1: n * ops1 / us / 1e6  # noqa: E731
     quant()
     us_q, _ = graph_time([quant], iters, dev)
     us_1, _ = graph_time([lambda i=i: fc1(i) for i in range(nw)], iters, dev)
     us_2, _ = graph_time([lambda i=i: fc2(i) for i in range(nw)], iters, dev)
     us_pair, us_pair_min = graph_time([lambda i=i: (fc1(i), fc2(i)) for i in range(nw)], iters, dev)
+    # The MLP as the INT8 decoder runs it (decoders.py): LN2 -> quantise -> fc1 (relu) -> quantise -> fc2 (f32 out),
+    # unfused (5 kernels, f32 fc1 output written and re-read) and fused (LN+quantise; fc1 with the quantisation in its
+    # epilogue, accumulators waiting in TMEM for the row maxima; fc2) -- bit-identical results.
+    a_in = torch.randn((M, HID), generator=g, device=dev)
+    gam, bet = torch.ones(HID, device=dev), torch.zeros(HID, device=dev)
+    nbuf = torch.empty((M, HID), device=dev)
+    hf = torch.empty((M, INTER), device=dev)
+    hs = torch.empty(M, device=dev)
+    yf = torch.empty((M, HID), device=dev)
+    need = max(lib.pa_gemm_i8_workspace_bytes(1, M, INTER, HID), lib.pa_gemm_i8_workspace_bytes(1, M, HID, INTER), 16)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    dq_ws = torch.zeros(lib.pa_gemm_i8_dynquant_workspace_bytes(1, M, INTER), dtype=torch.uint8, device=dev)
+    relu, none = _cabi.ACT["relu"], _cabi.ACT[""]
+
+    def mlp_unfused(i):
+        st = _cabi.stream()
+        _cabi.check(lib.pa_layer_norm_f32(a_in.data_ptr(), gam.data_ptr(), bet.data_ptr(), M, HID, 1e-5, nbuf.data_ptr(), st))
+        _cabi.check(lib.pa_row_quantize_dynamic_i8(nbuf.data_ptr(), M, HID, xs.data_ptr(), xq.data_ptr(), st))
+        _cabi.check(lib.pa_gemm_i8_dequant(xq.data_ptr(), W1[i].data_ptr(), hf.data_ptr(), 1, M, INTER, HID, xs.data_ptr(), 1e-3,
+                                           b1.data_ptr(), relu, ws.data_ptr(), need, st))
+        _cabi.check(lib.pa_row_quantize_dynamic_i8(hf.data_ptr(), M, INTER, hs.data_ptr(), h8.data_ptr(), st))
+        _cabi.check(lib.pa_gemm_i8_dequant(h8.data_ptr(), W2[i].data_ptr(), yf.data_ptr(), 1, M, HID, INTER, hs.data_ptr(), 1e-3,
+                                           b2.data_ptr(), none, ws.data_ptr(), need, st))
+
+    def mlp_fused(i):
+        st = _cabi.stream()
+        _cabi.check(lib.pa_layer_norm_quantize_i8(a_in.data_ptr(), gam.data_ptr(), bet.data_ptr(), M, HID, 1e-5, None,
+                                                  xs.data_ptr(), xq.data_ptr(), st))
+        _cabi.check(lib.pa_gemm_i8_dynquant(xq.data_ptr(), W1[i].data_ptr(), h8.data_ptr(), hs.data_ptr(), 1, M, INTER, HID,
+                                            xs.data_ptr(), 1e-3, b1.data_ptr(), relu, dq_ws.data_ptr(), dq_ws.numel(), st))
+        _cabi.check(lib.pa_gemm_i8_dequant(h8.data_ptr(), W2[i].data_ptr(), yf.data_ptr(), 1, M, HID, INTER, hs.data_ptr(), 1e-3,
+                                           b2.data_ptr(), none, ws.data_ptr(), need, st))
+
+    mlp_unfused(0)
+    y_ref = yf.clone()
+    mlp_fused(0)
+    torch.cuda.synchronize(dev)
+    fused_equal = bool(torch.equal(y_ref, yf))
+    us_unf, _ = graph_time([lambda i=i: mlp_unfused(i) for i in range(nw)], iters, dev)
+    us_fus, _ = graph_time([lambda i=i: mlp_fused(i) for i in range(nw)], iters, dev)
+    us_dq, _ = graph_time([lambda i=i: _cabi.check(lib.pa_gemm_i8_dynquant(
+        xq.data_ptr(), W1[i].data_ptr(), h8.data_ptr(), hs.data_ptr(), 1, M, INTER, HID, xs.data_ptr(), 1e-3, b1.data_ptr(), relu,
+        dq_ws.data_ptr(), dq_ws.numel(), _cabi.stream())) for i in range(nw)], iters, dev)
     # library baseline at the same shapes (cuBLASLt int8 through torch._int_mm; s32 output, no epilogue)
     a2, h2 = xq[0], h8[0]
     us_lib1, _ = graph_time([lambda i=i: torch._int_mm(a2, W1[i][0]) for i in range(nw)], iters, dev)
@@ -196,12 +241,15 @@ def c4_gemm_pair(dev, M=256, iters=10):
     e2 = oracle.cpu.dnnl_matmul_int8(Hm[None], W2[0].cpu().numpy(), 1 / 16, 1 / 16, 32.0, b2.cpu().numpy(), "")[0]
     d2 = int(np.abs(e2.astype(np.int32) - y8[0][rows].cpu().numpy().astype(np.int32)).max())
     peak_lib = measured_int8_peak(dev)
-    ops1 = 2.0 * M * HID * INTER
-    tops = lambda us, n=1: n * ops1 / us / 1e6  # noqa: E731
     res = {"workload": f"C4 MLP GEMMs: [{M} x 4096].[4096 x 16384] relu -> [{M} x 16384].[16384 x 4096], s8 x s8 -> s32 -> s8",
            "kernel": "gemm_i8_2cta_kernel (tcgen05 kind::i8, cta_group::2)",
            "us": round(us_pair, 2), "us_min": round(us_pair_min, 2), "fc1_us": round(us_1, 2), "fc2_us": round(us_2, 2),
-           "act_quant_us": round(us_q, 2), "pair_plus_quant_us": round(us_pair + 2 * us_q, 2),
+           "act_quant_us": round(us_q, 2),
+           "mlp_layer_unfused_us": round(us_unf, 2), "mlp_layer_fused_us": round(us_fus, 2),
+           "mlp_layer_note": "LN2 -> quantise -> fc1(relu) -> quantise -> fc2(f32) as INT8Decoder runs it; fused = "
+                             "pa_layer_norm_quantize_i8 + pa_gemm_i8_dynquant + pa_gemm_i8_dequant, bit-identical output",
+           "fc1_dynquant_us": round(us_dq, 2), "fused_equals_unfused": fused_equal,
+           "mlp_layer_fused_tops": round(2 * ops1 / us_fus / 1e6, 1),
            "achieved": round(tops(us_pair, 2), 1), "unit": "TOP/s", "peak": 4500.0, "frac": round(tops(us_pair, 2) / 4500.0, 4),
            "fc1_tops": round(tops(us_1), 1), "fc2_tops": round(tops(us_2), 1),
            "measured_int8_peak_tops": round(peak_lib * 1e0, 1),
@@ -328,7 +376,7 @@ def c5_splitkv(dev, world, rank, hbm_peak, ctx=131072, iters=30):
     res_us = {}
     res_us["partial_only"] = graph_time([lambda c=c: ld.paged_decode_partial(q, c, 1, Tl, temp) for c in caches], iters, dev, world,
                                         per=nsets)
-    res_us["fused_one_launch"] = graph_time([lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=fused, fused=True)
+    res_us["fused"] = graph_time([lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=fused, fused=True)
                                              for c in caches], iters, dev, world, per=nsets)
     res_us["partial_plus_p2p_kernel"] = graph_time([lambda c=c: pd.split_kv_decode(q, c, 1, Tl, temp, exchange=p2p)
                                                     for c in caches], iters, dev, world, per=nsets)
@@ -343,12 +391,13 @@ def c5_splitkv(dev, world, rank, hbm_peak, ctx=131072, iters=30):
     fused.check()
     p2p.check()
     agree = max(float((outs["fused"] - o).abs().max().item()) for o in outs.values())
-    us = res_us["fused_one_launch"][0]
+    us = res_us["fused"][0]
     ach = kv_bytes_rank / us / 1e3
     res = {"workload": f"C5: 1 sequence x {ctx} ctx, {H} heads, D=128, fp16 KV pages split over {world} GPU(s)",
-           "kernel": "paged_decode_overlap_kernel<128,f16,8,3> (one static chunk per warp, in-kernel merge + exchange)",
+           "kernel": "paged_decode_direct_kernel<128,f16> + splitkv_merge_exchange_kernel chained by programmatic dependent "
+                     "launch (<= 0.5 GB of K/V per GPU); paged_decode_overlap_kernel<...,TAIL> in one launch above that",
            "n_gpus": world, "kv_bytes_per_gpu": kv_bytes_rank, "payload_bytes_per_rank": H * (D + 2) * 4,
-           "us": round(us, 2), "us_min": round(res_us["fused_one_launch"][1], 2),
+           "us": round(us, 2), "us_min": round(res_us["fused"][1], 2),
            "us_by_form": {k: round(v[0], 2) for k, v in res_us.items()},
            "exchange_overhead_us": round(us - res_us["partial_only"][0], 2),
            "achieved": round(ach, 1), "unit": "GB/s per GPU", "peak": hbm_peak, "frac": round(ach / hbm_peak, 4),

@@ -284,6 +284,22 @@ int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f32, int
                        void* d_workspace, size_t workspace_bytes,
                        pa_stream_t stream);
 
+/* The same GEMM with the DYNAMIC ROW QUANTISATION of its output fused into the epilogue -- the
+ * "fc1 -> int8_quant -> fc2" hand-off of the INT8 decoder MLP (attention_cpu/README.md:80-86) in one kernel:
+ *   v[b,m,n]       = act(alpha_row*acc + bias[n])                  (as pa_gemm_i8_dequant; act none / relu)
+ *   d_c_qscale[bm] = 127 / (max_n |v| + 1e-6)                      (compute_minmax_scale, int8_quant.cpp:59-64)
+ *   C_s8[b,m,n]    = clamp(round_half_away(v * d_c_qscale[bm]))    (batch_quantize, int8_quant.cpp:15-28)
+ * bit-identical to pa_gemm_i8_dequant followed by pa_row_quantize_dynamic_i8, without the f32 round trip (the
+ * accumulators wait in TMEM while the row maxima cross the grid).  Needs the whole grid resident at once:
+ * PA_ERR_UNSUPPORTED for M <= 128, for more CTA pairs than SMs / 2, for shapes that would split K, and for gelu --
+ * callers then use the two separate calls.  d_workspace: >= pa_gemm_i8_dynquant_workspace_bytes(BATCH, M, N) bytes,
+ * 16-byte aligned, DEDICATED to this function and ZERO-FILLED ONCE by the caller (its first 16 bytes are the
+ * self-resetting counters of the grid barrier; one stream at a time per workspace). */
+size_t pa_gemm_i8_dynquant_workspace_bytes(int BATCH, int M, int N);
+int pa_gemm_i8_dynquant(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, float* d_c_qscale, int BATCH,
+                        int M, int N, int K, const float* d_a_qscale, float b_dequant, const float* d_bias,
+                        int act, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+
 /* ------------------------------------------------- decoder glue (row a14) */
 /* decoder/token_embedding.hpp:19-26: d_out[r,:] = E[d_ids[r],:] (ids outside [0,vocab) give
  * zeros; the reference reads out of bounds).  _i8: int8 table dequantised as q/qscale
@@ -321,6 +337,12 @@ int pa_argmax_f32(const float* d_logits, int rows, int vocab, float temperature,
 int pa_logits_argmax(const float* d_x, const void* d_E, int elem_bytes, float qscale, int rows, int hidden,
                      int vocab, float temperature, int divide, float* d_logits,
                      unsigned long long* d_best, int32_t* d_out_ids, pa_stream_t stream);
+/* LayerNorm (decoder/layer_norm.hpp:20-37) fused with the dynamic row quantisation that follows it in the INT8
+ * decoder (compute_minmax_scale + batch_quantize per row, int8_quant.cpp:59-64, 15-28): d_scales[row], d_q [rows,
+ * hidden]; d_out_f32 (optional) also receives the normalised f32 rows.  Bit-identical to pa_layer_norm_f32 followed
+ * by pa_row_quantize_dynamic_i8. */
+int pa_layer_norm_quantize_i8(const float* d_x, const float* d_gamma, const float* d_beta, int rows, int hidden,
+                              float eps, float* d_out_f32, float* d_scales, int8_t* d_q, pa_stream_t stream);
 /* compute_minmax_scale + batch_quantize of every row of x [rows, dim] in one kernel
  * (attention_cpu/int8_quant.cpp:59-64, 15-28); bit-identical to pa_batch_minmax_scale followed by
  * pa_batch_quantize_i8. */

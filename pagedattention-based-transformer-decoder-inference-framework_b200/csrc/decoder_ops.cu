@@ -60,9 +60,53 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
         v = fmaf(d, d, v);
     }
     const float var = block_sum_256(v, sm) / (float)hidden;
-    const float inv_std = (float)(1.0 / sqrt((double)(var + eps)));  // layer_norm.hpp:33
+    // layer_norm.hpp:33 `T inv_std = 1.0 / std::sqrt(var + epsilon_)`, T = float: float square root, double division
+    const float inv_std = (float)(1.0 / (double)sqrtf(var + eps));
     float* o = out + (int64_t)row * hidden;
     for (int j = threadIdx.x; j < hidden; j += 256) o[j] = (xr[j] - mean) * inv_std * gamma[j] + beta[j];
+}
+
+// ---- LayerNorm + dynamic row quantisation fused (the INT8 decoder's LN2 -> int8_quant -> fc1 hand-off): the
+// normalised row never goes to memory as f32 unless `out` is given; scale and int8 values are bit-identical to
+// layer_norm_kernel followed by row_quantize_dynamic_kernel (same expressions, same order). ----
+__global__ void __launch_bounds__(256) layer_norm_quantize_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int rows, int hidden,
+                                                                  float eps, float* __restrict__ out,
+                                                                  float* __restrict__ scales, int8_t* __restrict__ q) {
+    __shared__ float sm[8];
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * hidden;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < hidden; j += 256) s += xr[j];
+    const float mean = block_sum_256(s, sm) / (float)hidden;
+    float v = 0.f;
+    for (int j = threadIdx.x; j < hidden; j += 256) {
+        const float d = xr[j] - mean;
+        v = fmaf(d, d, v);
+    }
+    const float var = block_sum_256(v, sm) / (float)hidden;
+    const float inv_std = (float)(1.0 / (double)sqrtf(var + eps));
+    float m = 0.f;
+    for (int j = threadIdx.x; j < hidden; j += 256) {
+        const float y = (xr[j] - mean) * inv_std * gamma[j] + beta[j];
+        if (out) out[(int64_t)row * hidden + j] = y;
+        m = fmaxf(m, fabsf(y));
+    }
+    m = warp_max(m);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    m = (lane < 8) ? sm[lane] : 0.f;
+    m = warp_max(m);
+    const float scale = __fdiv_rn(127.f, __fadd_rn(m, 1e-6f));
+    if (threadIdx.x == 0) scales[row] = scale;
+    int8_t* qr = q + (int64_t)row * hidden;
+    for (int j = threadIdx.x; j < hidden; j += 256) {
+        const float y = (xr[j] - mean) * inv_std * gamma[j] + beta[j];
+        float r = roundf(__fmul_rn(y, scale));
+        r = fminf(127.f, fmaxf(-128.f, r));
+        qr[j] = (int8_t)(int)r;
+    }
 }
 
 // ---- dynamic per-row activation quantisation in ONE kernel: compute_minmax_scale (int8_quant.cpp:59-64)
@@ -469,6 +513,16 @@ PA_API int pa_logits_argmax(const float* d_x, const void* d_E, int elem_bytes, f
 }
 
 // compute_minmax_scale + batch_quantize of every row in one kernel (int8_quant.cpp:59-64, 15-28).
+PA_API int pa_layer_norm_quantize_i8(const float* d_x, const float* d_gamma, const float* d_beta, int rows, int hidden,
+                                     float eps, float* d_out_f32, float* d_scales, int8_t* d_q, pa_stream_t stream) {
+    PA_CHECK_ARG(d_x && d_gamma && d_beta && d_scales && d_q && rows >= 0 && hidden > 0);
+    PA_CHECK_ARG((const void*)d_x != (const void*)d_q && d_x != d_out_f32);  // the row is read three times
+    if (rows == 0) return PA_OK;
+    layer_norm_quantize_kernel<<<rows, 256, 0, as_stream(stream)>>>(d_x, d_gamma, d_beta, rows, hidden, eps, d_out_f32,
+                                                                     d_scales, d_q);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
 PA_API int pa_row_quantize_dynamic_i8(const float* d_x, int rows, int dim, float* d_scales, int8_t* d_q,
                                       pa_stream_t stream) {
     PA_CHECK_ARG(d_x && d_scales && d_q && rows >= 0 && dim > 0);

@@ -58,6 +58,13 @@ struct Args {
     int ksplit;          // K splits
     int kb_per_split;    // BK blocks per split
     int64_t BATCH_rows;  // BATCH * M
+    // dynamic row quantisation of the OUTPUT fused into the epilogue (DQ instances)
+    unsigned int* dq_rowmax;   // [BATCH*M] bit patterns of max_n |act(alpha*acc + bias)| (non-negative floats order as uints)
+    unsigned int* dq_barrier;  // [2] arrive / done counters of the grid barrier
+    float* dq_scales;          // [BATCH*M] out: 127 / (rowmax + 1e-6)   (compute_minmax_scale)
+    unsigned int dq_expected;  // CTAs in the grid
+    // dq_rowmax and dq_barrier are zero ONCE (caller) and left zero by every launch: the last CTA to have read its
+    // rows' maxima clears them (no memset node in front of the kernel).
 #ifdef PA_GEMM_PROBE
     unsigned long long* probe;  // [0] producer wait cycles, [1] mma wait cycles, [2] total cycles (CTA 0)
 #endif
@@ -167,6 +174,17 @@ __device__ __forceinline__ uint32_t epilogue_s8(int acc, float alpha, float bias
     else if (ACT == PA_ACT_GELU) v = gelu_erf(v);
     uint32_t q;
     asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(v));
+    return q;
+}
+// clamp(std::round(y)) to int8 in four instructions (int8_quant.cpp:8-9: round half AWAY from zero, saturate):
+// floor(|y| + 0.5) with the sign put back.  The addition is done round-TOWARD-ZERO, which makes it exact where it
+// matters: RZ(|y| + 0.5) >= n exactly when |y| + 0.5 >= n for every integer n (n is representable), so truncating it
+// gives floor(|y| + 0.5) -- e.g. 0.49999997 + 0.5 stays below 1 (round-to-nearest would give 1.0 and the wrong answer;
+// SURVEY App. B has that value).  cvt.rzi.sat truncates and saturates to [-128, 127] in one instruction.
+__device__ __forceinline__ uint32_t quantize_half_away_s8(float y) {
+    const float half = __uint_as_float((__float_as_uint(y) & 0x80000000u) | 0x3f000000u);  // copysign(0.5, y)
+    uint32_t q;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fadd_rz(y, half)));
     return q;
 }
 __device__ __forceinline__ uint32_t pack_s8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -493,7 +511,15 @@ __device__ __forceinline__ void tma_load_3d_2cta_mc(uint32_t dst, const CUtensor
 // pair: A crosses the L2 -> SM fabric once per cluster instead of once per pair (at M = 256 the whole GEMM is
 // bound by that fabric, profiles/r01_gemm_notes.md).  A ring slot is then reusable only when BOTH pairs have
 // consumed it (empty barrier count 2, each leader's commit multicast to all four CTAs).
-template <int EPI, int OCC, int CLP>
+// DQ = true: the s8 output is the dynamically quantised row (compute_minmax_scale + batch_quantize,
+// int8_quant.cpp:59-64, 15-28) of act(alpha_row * acc + bias) -- the "fc1 -> int8_quant -> fc2" hand-off of the INT8
+// decoder MLP without the f32 round trip through memory (16 MiB written and re-read per layer at M = 256).  A row's
+// scale needs its maximum over ALL N columns, which are spread over every CTA pair of the grid, so the epilogue runs in
+// two passes over accumulators that simply STAY IN TMEM: pass 1 computes the f32 values and folds the row maxima into
+// global memory (atomicMax on the bit patterns), a grid-wide barrier follows (every CTA is resident: the host only
+// uses this instance when the grid fits one wave), pass 2 re-reads TMEM, quantises with the final scale and stores
+// s8.  Values, scale and rounding are bit-identical to the unfused kernels.
+template <int EPI, int OCC, int CLP, bool DQ = false>
 __global__ void __launch_bounds__(NTHREADS2, OCC)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -626,6 +652,90 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef PA_GEMM_PROBE
         const long long t_epi0 = clock64();
 #endif
+        if (DQ) {
+            const int64_t grow = (int64_t)batch * g.M + row;
+            const int cbase = n0 + chalf * 128;
+            // ---- pass 1: row maxima of |act(alpha * acc + bias)| over this thread's 128 columns ----
+            float vmax = 0.f;
+#pragma unroll 1
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t rr[2][32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + chalf * 128 + c2 * 64;
+                tmem_ld_32x32_nowait(taddr, rr[0]);
+                tmem_ld_32x32_nowait(taddr + 32, rr[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int cl = c2 * 64 + hc * 32 + j;
+                        const float v = epilogue_f32<ACT>((int)rr[hc][j], alpha, bias_sm[cl]);
+                        if (cbase + cl < g.N) vmax = fmaxf(vmax, fabsf(v));
+                    }
+                }
+            }
+            // CTA-level maximum first (the two column halves of a row meet in shared memory; the ring is idle by now),
+            // then ONE atomicMax per row and CTA
+            float* rowmax_sm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+            if (chalf == 1) rowmax_sm[qtr * 32 + lane] = vmax;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (chalf == 0 && row_ok) atomicMax(g.dq_rowmax + grow, __float_as_uint(fmaxf(vmax, rowmax_sm[qtr * 32 + lane])));
+            // ---- grid barrier over the epilogue threads of every CTA ----
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                atomicAdd(g.dq_barrier, 1u);
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.dq_barrier) : "memory");
+                } while (seen < g.dq_expected);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- pass 2: quantise with the row's final scale ----
+            float scale = 1.f;
+            if (row_ok) {
+                const float m = __uint_as_float(__ldcg(g.dq_rowmax + grow));
+                scale = __fdiv_rn(127.f, __fadd_rn(m, 1e-6f));          // compute_minmax_scale
+                if (n0 == 0 && chalf == 0) g.dq_scales[grow] = scale;
+            }
+            // every thread of this CTA holds its scale: the last CTA of the grid to get here clears the words
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                if (atomicAdd(g.dq_barrier + 1, 1u) + 1u == g.dq_expected) {
+                    for (int64_t i = 0; i < g.BATCH_rows; ++i) g.dq_rowmax[i] = 0u;
+                    g.dq_barrier[0] = 0u;
+                    g.dq_barrier[1] = 0u;
+                }
+            }
+#pragma unroll 1
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t rr[2][32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + chalf * 128 + c2 * 64;
+                tmem_ld_32x32_nowait(taddr, rr[0]);
+                tmem_ld_32x32_nowait(taddr + 32, rr[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    const int col0 = cbase + c2 * 64 + hc * 32;
+                    if (!row_ok || col0 >= g.N) continue;
+                    const bool hi_ok = col0 + 32 <= g.N;
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        uint32_t b4[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float v = epilogue_f32<ACT>((int)rr[hc][4 * w + t], alpha, bias_sm[c2 * 64 + hc * 32 + 4 * w + t]);
+                            b4[t] = quantize_half_away_s8(__fmul_rn(v, scale));   // batch_quantize
+                        }
+                        packed[w] = pack_s8x4(b4[0], b4[1], b4[2], b4[3]);
+                    }
+                    *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (hi_ok)
+                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+        } else
 #pragma unroll 1
         for (int c2 = 0; c2 < 2; ++c2) {
             // two 32-column chunks per TMEM round trip
@@ -817,7 +927,7 @@ using namespace pa::gemm;
 static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, float* d_C_f32, int32_t* d_C_s32,
                           int BATCH, int M, int N, int K, float alpha_host, const float* d_a_qscale,
                           const float* d_bias, int act, void* d_workspace, size_t workspace_bytes,
-                          pa_stream_t stream) {
+                          pa_stream_t stream, float* d_dq_scales = nullptr) {
     PA_CHECK_ARG(d_A && d_B && (d_C_s8 || d_C_s32 || d_C_f32));
     PA_CHECK_ARG(BATCH > 0 && M > 0 && N > 0 && K > 0);
     PA_CHECK_ARG(!d_C_f32 || (uintptr_t)d_C_f32 % 16 == 0);
@@ -900,6 +1010,18 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         }
     }
     g.ksplit = ksplit;
+    const bool dq = d_dq_scales != nullptr;
+    if (dq) {
+        // fused output quantisation: one wave of CTA pairs, no split-K, activation none / relu (see the DQ instance)
+        const int64_t ctas = (int64_t)n_slabs * m_chunks * BATCH * 2;
+        if (!two_cta || plan.ksplit != 1 || ctas > di.sm_count || act == PA_ACT_GELU) return PA_ERR_UNSUPPORTED;
+        const size_t need = 16 + (size_t)rows * sizeof(unsigned int);
+        if (!d_workspace || workspace_bytes < need || (uintptr_t)d_workspace % 16 != 0) return PA_ERR_WORKSPACE;
+        g.dq_barrier = static_cast<unsigned int*>(d_workspace);  // zero once (caller); every launch leaves it zero
+        g.dq_rowmax = g.dq_barrier + 4;
+        g.dq_scales = d_dq_scales;
+        g.dq_expected = (unsigned int)ctas;
+    }
     g.BATCH_rows = rows;
     const int epi = (ksplit > 1 || !(d_C_s8 || d_C_f32)) ? 0 : 1 + act;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args);
@@ -919,8 +1041,16 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
             {{gemm_i8_2cta_kernel<0, 1, 2>, gemm_i8_2cta_kernel<1, 1, 2>, gemm_i8_2cta_kernel<2, 1, 2>, gemm_i8_2cta_kernel<3, 1, 2>},
              {gemm_i8_2cta_kernel<0, 2, 2>, gemm_i8_2cta_kernel<1, 2, 2>, gemm_i8_2cta_kernel<2, 2, 2>, gemm_i8_2cta_kernel<3, 2, 2>}}};
         KernelFn kern = kernels2[clp2][occ2][epi];
+        if (dq) {
+            static const KernelFn kernels_dq[2][2] = {
+                {gemm_i8_2cta_kernel<1, 1, 1, true>, gemm_i8_2cta_kernel<2, 1, 1, true>},
+                {gemm_i8_2cta_kernel<1, 1, 2, true>, gemm_i8_2cta_kernel<2, 1, 2, true>}};
+            kern = kernels_dq[clp2][act == PA_ACT_RELU ? 1 : 0];
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+        }
         static bool attr_set2[64][2][2][4] = {};
-        if (!attr_set2[dev & 63][clp2][occ2][epi]) {
+        if (!dq && !attr_set2[dev & 63][clp2][occ2][epi]) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
             attr_set2[dev & 63][clp2][occ2][epi] = true;
@@ -1008,4 +1138,21 @@ PA_API int pa_gemm_i8_dequant(const int8_t* d_A, const int8_t* d_B, float* d_C_f
     PA_CHECK_ARG(d_C_f32 && d_a_qscale);
     return gemm_i8_launch(d_A, d_B, nullptr, d_C_f32, nullptr, BATCH, M, N, K, b_dequant, d_a_qscale, d_bias, act,
                           d_workspace, workspace_bytes, stream);
+}
+
+PA_API size_t pa_gemm_i8_dynquant_workspace_bytes(int BATCH, int M, int N) {
+    (void)N;
+    if (BATCH <= 0 || M <= 0) return 0;
+    return 16 + (size_t)BATCH * M * sizeof(unsigned int);
+}
+
+// "fc1 -> int8_quant" in one kernel (see the DQ instance of gemm_i8_2cta_kernel).  PA_ERR_UNSUPPORTED when the shape
+// does not fit one wave of CTA pairs (M <= 128, more pairs than SMs / 2, split-K shapes, gelu): the caller then
+// uses pa_gemm_i8_dequant + pa_row_quantize_dynamic_i8, which give the same bits.
+PA_API int pa_gemm_i8_dynquant(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, float* d_c_qscale, int BATCH, int M,
+                               int N, int K, const float* d_a_qscale, float b_dequant, const float* d_bias, int act,
+                               void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(d_C_s8 && d_c_qscale && d_a_qscale);
+    return gemm_i8_launch(d_A, d_B, d_C_s8, nullptr, nullptr, BATCH, M, N, K, b_dequant, d_a_qscale, d_bias, act,
+                          d_workspace, workspace_bytes, stream, d_c_qscale);
 }

@@ -1735,11 +1735,14 @@ PA_API int pa_paged_decode_f32_overlap(const float* d_q, float* d_out, const flo
                         PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
 }
 
-// Kernel choice for the partial / split-KV entries: the streaming kernel (one static chunk per warp for a GPU's
-// share of a long sequence, in-kernel row merge) unless PA_PARTIAL_DIRECT=1 asks for the split-KV grid kernel.
-static bool partial_uses_streaming() {
+// Kernel choice for the partial entries, by problem size: below ~0.5 GB of K/V (one GPU's share of a 128K-token
+// sequence is 268 MB) the split-KV grid kernel is faster than the persistent streaming kernel (measured on that share:
+// 50 us incl. the merge launch vs 57 us -- the streaming kernel's static split waits for its slowest SM); above it the
+// streaming kernel wins.  PA_PARTIAL_DIRECT=0 / 1 overrides.
+static bool partial_uses_streaming(int B, int num_heads, int T) {
     const char* env = getenv("PA_PARTIAL_DIRECT");
-    return !(env && atoi(env) == 1);
+    if (env) return atoi(env) != 1;
+    return (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok) > 65536;
 }
 
 PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
@@ -1747,7 +1750,7 @@ PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float*
                                        PA_DECODE_COMMON_PARAMS, void* d_workspace,
                                        size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
-    return decode_entry(0, partial_uses_streaming(), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+    return decode_entry(0, partial_uses_streaming(B, num_heads, T), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
                         nullptr, nullptr, PA_DECODE_COMMON_ARGS, nullptr, d_workspace,
                         workspace_bytes, stream);
 }
@@ -1756,7 +1759,7 @@ PA_API int pa_paged_decode_i8_partial(const float* d_q, float* d_part_m, float* 
                                       const float* d_v_scales, PA_DECODE_COMMON_PARAMS, void* d_workspace,
                                       size_t workspace_bytes, pa_stream_t stream) {
     PA_CHECK_ARG(d_part_m && d_part_l && d_part_o);
-    return decode_entry(1, partial_uses_streaming(), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
+    return decode_entry(1, partial_uses_streaming(B, num_heads, T), d_q, nullptr, d_part_m, d_part_l, d_part_o, d_k_pool, d_v_pool,
                         d_k_scales, d_v_scales, PA_DECODE_COMMON_ARGS, nullptr, d_workspace, workspace_bytes, stream);
 }
 

@@ -62,6 +62,8 @@ _SIGS = {
     "pa_gemm_i8_workspace_bytes": ([_i32, _i32, _i32, _i32], _sz),
     "pa_gemm_i8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _sz, _vp], _i32),
     "pa_gemm_i8_dequant": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _vp, _sz, _vp], _i32),
+    "pa_gemm_i8_dynquant_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_gemm_i8_dynquant": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _vp, _sz, _vp], _i32),
     "pa_embedding_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_embedding_i8": ([_vp, _f32, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_layer_norm_f32": ([_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp], _i32),
@@ -71,6 +73,7 @@ _SIGS = {
     "pa_logits_i8": ([_vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),
     "pa_logits_argmax": ([_vp, _vp, _i32, _f32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp], _i32),
+    "pa_layer_norm_quantize_i8": ([_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp], _i32),
     "pa_row_quantize_dynamic_i8": ([_vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_apply_rope_f32": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], _i32),
     "pa_advance_positions": ([_vp, _vp, _i32, _vp], _i32),

@@ -190,9 +190,14 @@ class _DecoderBase:
             nview = bf.n.view(R, self.num_heads_, self.head_dim_)
             self.kv_caches[li].append(nview, nview, positions, beam_ids)  # K = V = LN1 output (see module doc)
             self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws, prefill_shape)
-            self._chk(lib.pa_layer_norm_f32(bf.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), R, hid,
-                                            self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
-            self._mlp(bf, L)
+            self._ln2_mlp(bf, L)
+
+    def _ln2_mlp(self, bf, L):
+        """LN2 -> MLP (decoder_block.hpp:55-60): bf.a -> bf.x."""
+        self._chk(self._lib.pa_layer_norm_f32(bf.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), bf.R,
+                                              self.hidden_dim_, self.eps, bf.n.data_ptr(), _cabi.stream()),
+                  "pa_layer_norm_f32")
+        self._mlp(bf, L)
 
     def _head(self, x_rows):
         """logits (tied embedding) of the B rows in x_rows, then the next ids -> self.ids: the reference's
@@ -586,6 +591,37 @@ class INT8Decoder(_DecoderBase):
         """compute_minmax_scale + batch_quantize per row (int8_quant.cpp:59-64, 15-28), one kernel."""
         self._chk(self._lib.pa_row_quantize_dynamic_i8(x.data_ptr(), R, dim, scales.data_ptr(), q.data_ptr(),
                                                        _cabi.stream()), "pa_row_quantize_dynamic_i8")
+
+    def _ln2_mlp(self, bf, L):
+        """LN2 -> int8_quant -> fc1 (relu) -> int8_quant -> fc2 with both quantisations fused into their producers:
+        pa_layer_norm_quantize_i8 (the normalised row never goes to memory as f32) and pa_gemm_i8_dynquant (fc1's
+        accumulators wait in TMEM while the row maxima cross the grid; no 4 x inter bytes per row written and re-read).
+        Same bits as the unfused kernels, which remain the path for shapes the fused GEMM does not take (few rows, more
+        than one wave of tiles)."""
+        lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
+        if getattr(bf, "dq_ok", None) is None:  # decided once per buffer set (before any graph capture: warm-up step)
+            bf.dq_ok = os.environ.get("PA_MLP_FUSED_QUANT", "1") != "0" and R > 128
+        if not bf.dq_ok:
+            return super()._ln2_mlp(bf, L)
+        wp, wb = self._scratch(bf, max(lib.pa_gemm_i8_workspace_bytes(1, R, hid, inter), lib.pa_gemm_i8_workspace_bytes(1, R, inter, hid)))
+        if getattr(bf, "dq_ws", None) is None:  # dedicated, zeroed once: the grid barrier's self-resetting counters live here
+            bf.dq_ws = torch.zeros(lib.pa_gemm_i8_dynquant_workspace_bytes(1, R, inter), dtype=torch.uint8, device=self.device)
+        self._chk(lib.pa_layer_norm_quantize_i8(bf.a.data_ptr(), L.ln2_g.data_ptr(), L.ln2_b.data_ptr(), R, hid, self.eps,
+                                                None, bf.xs.data_ptr(), bf.xq.data_ptr(), s), "pa_layer_norm_quantize_i8")
+        st = lib.pa_gemm_i8_dynquant(bf.xq.data_ptr(), L.fc1_w.data_ptr(), bf.hq.data_ptr(), bf.hs.data_ptr(), 1, R, inter,
+                                     hid, bf.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(), _cabi.ACT["relu"],
+                                     bf.dq_ws.data_ptr(), bf.dq_ws.numel(), s)
+        if st == -2:  # PA_ERR_UNSUPPORTED: this shape does not fit one wave -> unfused fc1 + quantise, same bits
+            bf.dq_ok = False
+            self._chk(lib.pa_gemm_i8_dequant(bf.xq.data_ptr(), L.fc1_w.data_ptr(), bf.h.data_ptr(), 1, R, inter, hid,
+                                             bf.xs.data_ptr(), float(L.fc1_deq), L.fc1_b.data_ptr(), _cabi.ACT["relu"],
+                                             wp, wb, s), "pa_gemm_i8_dequant")
+            self._quant_rows(bf.h, bf.hq, bf.hs, R, inter)
+        else:
+            self._chk(st, "pa_gemm_i8_dynquant")
+        self._chk(lib.pa_gemm_i8_dequant(bf.hq.data_ptr(), L.fc2_w.data_ptr(), bf.x.data_ptr(), 1, R, hid, inter,
+                                         bf.hs.data_ptr(), float(L.fc2_deq), L.fc2_b.data_ptr(), _cabi.ACT[""], wp, wb, s),
+                  "pa_gemm_i8_dequant")
 
     def _mlp(self, bf, L):
         lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()

@@ -393,3 +393,120 @@ def test_int8_decoder_quantize_load_generate(oracle, tmp_path):
     assert all(len(o) == 9 and o[:3] == p for o, p in zip(outs, prompts))
     for o in outs[:4]:
         check_teacher_forced(o, 3, RefDecoder(wq, H, D, int8=True), 1.0, 0, None, 3e-2)
+
+
+# ------------------------------------------------------------------ GPU: fused quantisation around the INT8 MLP
+@pytest.mark.gpu
+def test_layer_norm_quantize_is_bit_identical_to_the_two_kernels(oracle):
+    from llm_decoder import _cabi
+    lib, s = _cabi.lib(), None
+    rng = np.random.default_rng(51)
+    for rows, hid in ((7, 192), (256, 4096), (3, 1000)):
+        x = torch.from_numpy((rng.standard_normal((rows, hid)) * 3 + 0.3).astype(np.float32)).cuda()
+        g = torch.from_numpy((1 + 0.1 * rng.standard_normal(hid)).astype(np.float32)).cuda()
+        b = torch.from_numpy((0.1 * rng.standard_normal(hid)).astype(np.float32)).cuda()
+        n = torch.empty_like(x)
+        q0 = torch.empty((rows, hid), dtype=torch.int8, device="cuda")
+        s0 = torch.empty(rows, device="cuda")
+        _cabi.check(lib.pa_layer_norm_f32(x.data_ptr(), g.data_ptr(), b.data_ptr(), rows, hid, 1e-5, n.data_ptr(), s))
+        _cabi.check(lib.pa_row_quantize_dynamic_i8(n.data_ptr(), rows, hid, s0.data_ptr(), q0.data_ptr(), s))
+        n1 = torch.empty_like(x)
+        q1, s1 = torch.empty_like(q0), torch.empty_like(s0)
+        _cabi.check(lib.pa_layer_norm_quantize_i8(x.data_ptr(), g.data_ptr(), b.data_ptr(), rows, hid, 1e-5, n1.data_ptr(),
+                                                  s1.data_ptr(), q1.data_ptr(), s))
+        assert torch.equal(q0, q1) and torch.equal(s0, s1) and torch.equal(n, n1)
+        q2, s2 = torch.empty_like(q0), torch.empty_like(s0)
+        _cabi.check(lib.pa_layer_norm_quantize_i8(x.data_ptr(), g.data_ptr(), b.data_ptr(), rows, hid, 1e-5, None,
+                                                  s2.data_ptr(), q2.data_ptr(), s))            # no f32 output
+        assert torch.equal(q0, q2) and torch.equal(s0, s2)
+        # and the pair is the oracle's: layer_norm (pinned to decoder/layer_norm.hpp) -> minmax scale -> batch_quantize
+        ln = oracle.cpu.layer_norm(x.cpu().numpy(), g.cpu().numpy(), b.cpu().numpy(), 1e-5)
+        np.testing.assert_allclose(n.cpu().numpy(), ln, rtol=2e-5, atol=2e-5)
+        sc = oracle.cpu.batch_minmax_scale(n.cpu().numpy(), hid)
+        np.testing.assert_array_equal(s0.cpu().numpy(), sc)
+        np.testing.assert_array_equal(q0.cpu().numpy(), oracle.cpu.batch_quantize(n.cpu().numpy(), sc, hid))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(256, 512, 256), (160, 1024, 128), (256, 16384, 4096), (200, 272, 64)])
+@pytest.mark.parametrize("act", ["relu", ""])
+def test_gemm_dynquant_is_bit_identical_to_dequant_then_quantize(oracle, shape, act):
+    """pa_gemm_i8_dynquant (row maxima cross the grid while the accumulators wait in TMEM) == pa_gemm_i8_dequant +
+    pa_row_quantize_dynamic_i8, bit for bit: s8 values and per-row scales; and both follow the oracle's chain
+    exact int32 accumulators -> alpha_row*acc + bias -> act -> compute_minmax_scale -> batch_quantize."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    M, N, K = shape
+    rng = np.random.default_rng(52)
+    A = rng.integers(-127, 128, (1, M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, (1, K, N), dtype=np.int8)
+    bias = rng.standard_normal(N).astype(np.float32)
+    qs = rng.uniform(5, 60, M).astype(np.float32)
+    dA, dB, dbias, dqs = (torch.from_numpy(a).cuda() for a in (A, B, bias, qs))
+    need = max(lib.pa_gemm_i8_workspace_bytes(1, M, N, K), 16)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    dq_ws = torch.zeros(lib.pa_gemm_i8_dynquant_workspace_bytes(1, M, N), dtype=torch.uint8, device="cuda")  # zeroed ONCE
+    Cf = torch.empty((1, M, N), device="cuda")
+    _cabi.check(lib.pa_gemm_i8_dequant(dA.data_ptr(), dB.data_ptr(), Cf.data_ptr(), 1, M, N, K, dqs.data_ptr(), 0.011,
+                                       dbias.data_ptr(), _cabi.ACT[act], ws.data_ptr(), need, None))
+    q0 = torch.empty((M, N), dtype=torch.int8, device="cuda")
+    s0 = torch.empty(M, device="cuda")
+    _cabi.check(lib.pa_row_quantize_dynamic_i8(Cf.data_ptr(), M, N, s0.data_ptr(), q0.data_ptr(), None))
+    for _ in range(3):   # three times on the same workspace: the barrier counters reset themselves
+        q1 = torch.full((1, M, N), 99, dtype=torch.int8, device="cuda")
+        s1 = torch.zeros(M, device="cuda")
+        _cabi.check(lib.pa_gemm_i8_dynquant(dA.data_ptr(), dB.data_ptr(), q1.data_ptr(), s1.data_ptr(), 1, M, N, K,
+                                            dqs.data_ptr(), 0.011, dbias.data_ptr(), _cabi.ACT[act], dq_ws.data_ptr(),
+                                            dq_ws.numel(), None))
+        torch.cuda.synchronize()
+        assert torch.equal(s0, s1)
+        assert torch.equal(q0, q1[0])
+    acc = oracle.cpu.gemm_s8s8s32(A, B)[0].astype(np.float32)
+    v = ((np.float32(0.011) / qs)[:, None] * acc).astype(np.float32) + bias
+    if act == "relu":
+        v = np.maximum(v, 0)
+    sc = oracle.cpu.batch_minmax_scale(v, N)
+    np.testing.assert_array_equal(s0.cpu().numpy(), sc)
+    np.testing.assert_array_equal(q0.cpu().numpy(), oracle.cpu.batch_quantize(v, sc, N))
+
+
+@pytest.mark.gpu
+def test_gemm_dynquant_rejects_shapes_that_do_not_fit_one_wave():
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    ws = torch.zeros(1 << 22, dtype=torch.uint8, device="cuda")
+    for (M, N, K) in ((64, 512, 256),          # M <= 128: single-CTA kernel
+                      (2048, 16384, 256)):      # 8 x 64 tiles: more CTA pairs than one wave
+        A = torch.zeros((1, M, K), dtype=torch.int8, device="cuda")
+        B = torch.zeros((1, K, N), dtype=torch.int8, device="cuda")
+        q = torch.empty((1, M, N), dtype=torch.int8, device="cuda")
+        sc = torch.empty(M, device="cuda")
+        qs = torch.ones(M, device="cuda")
+        st = lib.pa_gemm_i8_dynquant(A.data_ptr(), B.data_ptr(), q.data_ptr(), sc.data_ptr(), 1, M, N, K, qs.data_ptr(), 1.0,
+                                     None, 0, ws.data_ptr(), ws.numel(), None)
+        assert st == -2, (M, N, K, st)
+
+
+@pytest.mark.gpu
+def test_int8_decoder_fused_quantisation_same_tokens(monkeypatch):
+    """INT8Decoder with > 128 rows: LN2 + quantise and fc1 + quantise fused into their producers give the SAME tokens
+    and logits as the unfused kernels (the arithmetic is bit-identical)."""
+    import llm_decoder as ld
+    L, H, D, V, S = 2, 2, 64, 131, 24
+    hid = H * D
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("PA_MLP_FUSED_QUANT", fused)
+        dec = ld.INT8Decoder(L, H, D, hid, V, S)
+        g = torch.Generator(device="cuda").manual_seed(53)
+        dec.embedding.copy_(torch.randint(-127, 128, dec.embedding.shape, generator=g, device="cuda", dtype=torch.int8))
+        for Ly in dec.layers:
+            Ly.fc1_w.copy_(torch.randint(-127, 128, Ly.fc1_w.shape, generator=g, device="cuda", dtype=torch.int8))
+            Ly.fc2_w.copy_(torch.randint(-127, 128, Ly.fc2_w.shape, generator=g, device="cuda", dtype=torch.int8))
+            Ly.fc1_deq = Ly.fc2_deq = 0.05 / 127
+        prompts = [[(7 * i + j) % V for j in range(3)] for i in range(160)]
+        seqs = dec.generate_batch(prompts, 5, 1.0)
+        outs.append((seqs, dec.logits.clone(), getattr(dec.bufs, "dq_ok", None)))
+    assert outs[0][2] is True and outs[1][2] is False
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -50,3 +50,6 @@ def test_decode_kernels_stream_pages_with_bulk_copies():
     assert _count(sass, "UBLKCP") > 0                        # cp.async.bulk page units (overlap kernel)
     assert _count(sass, "UTMALDG") > 0                       # TMA tensor boxes (beam-group kernel)
     assert _count(sass, "HMMA.16816") > 0                    # mma.sync m16n8k16 (beam-group kernel)
+    # the producers issue their copies under elect.sync: no R2UR + BRA.U.ANY uniformisation loop around any UBLKCP /
+    # UTMALDG (r01 had 40 of them in this object: every bulk copy of the streaming kernels)
+    assert _count(sass, "BRA.U.ANY") == 0
