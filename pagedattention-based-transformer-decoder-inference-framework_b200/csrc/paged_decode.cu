@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
                                                                           unsigned int* counter) {
     using C = Cfg<D, KV>;
     constexpr int QN = 16;  // per-warp chunk-id ring (producer runs <= S chunks ahead)
+    asm volatile("griddepcontrol.launch_dependents;");  // the merge kernel may become resident (it waits for this grid)
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)NW * S * C::STAGE_BYTES);
@@ -849,6 +850,9 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
     constexpr int VEC = D / 32;
     extern __shared__ int prefix_sm[];
     __shared__ float red[8][D + 2];
+    // launched with programmatic stream serialisation behind the kernel that writes the partials: resident early,
+    // blocks here until that grid has completed and its writes are visible (a no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     ChunkMap cm;
     cm.B = a.B;
     cm.H = a.H;
@@ -1011,6 +1015,7 @@ paged_decode_group_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
                           const DecodeArgs a, const GroupArgs ga, int cu, unsigned int* counter) {
     constexpr int D = 128;
     constexpr int QN = 16;
+    asm volatile("griddepcontrol.launch_dependents;");  // the merge kernel may become resident (it waits for this grid)
     extern __shared__ __align__(1024) uint8_t smem_g[];
     const uint32_t smem_base = (smem_u32(smem_g) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_g + (smem_base - smem_u32(smem_g));
@@ -1389,6 +1394,23 @@ struct OvCfg {
     static constexpr int S = KV == 2 ? 3 : ((D == 128) ? (KV == 0 ? 3 : (NW == 16 ? 3 : 6)) : (KV == 0 ? 6 : 8));
 };
 
+// combine_chunks_kernel as a programmatically dependent launch: its launch latency and ramp hide under the tail of the
+// producer grid (which executes griddepcontrol.launch_dependents as its first instruction).
+template <int D>
+static cudaError_t launch_combine_pdl(const DecodeArgs& a, int cu, int wpr, int grid, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, combine_chunks_kernel<D>, a, cu, wpr);
+}
+
 static int units_of_ctx_host(int T, int cap) {
     int ctx = T < 0 ? 0 : (T > cap ? cap : T);
     return (ctx + kUnitTok - 1) / kUnitTok;
@@ -1432,6 +1454,28 @@ static int choose_cu(int64_t rows, int max_units, int sm_count, int nw, bool pre
     return p;
 }
 
+// Units per chunk of the beam-group kernel.  A chunk is expensive to start and finish there (W query fragments in
+// fp16 hi / lo, W partial rows written and merged later), so few large chunks win: measured at C3 (1024 (group, head)
+// pairs of 128 units, 1184 resident warps) 8-unit chunks 307 us, 16: 272, 32: 260, 64: 249, 128 (ONE chunk per pair,
+// a single wave on 86 % of the warps): 243 us.  Rule: split a pair into the largest power-of-two number of chunks
+// that still fits ONE wave of warps; with more pairs than warps, the fewest chunks that give >= 3 waves to balance.
+static int choose_group_cu(int64_t group_heads, int max_units, int sm_count) {
+    const int64_t warps = (int64_t)sm_count * kOvWarps;
+    if (group_heads <= 0 || max_units <= 0) return 2;
+    int nc = 1;
+    if (group_heads <= warps) {
+        while ((int64_t)group_heads * nc * 2 <= warps && nc * 2 <= max_units) nc *= 2;
+    } else {
+        while ((int64_t)group_heads * nc < 3 * warps && nc * 2 <= max_units) nc *= 2;
+    }
+    int cu = (max_units + nc - 1) / nc;
+    if (const char* env = getenv("PA_GROUP_CU")) {
+        const int v = atoi(env);
+        if (v >= 2) cu = v;
+    }
+    return cu < 2 ? 2 : cu;
+}
+
 static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
     size_t ov = 0;
     for (int nw : {4, 8, 16}) {  // the streaming-kernel instances differ in warps per CTA; size for the largest need
@@ -1442,10 +1486,14 @@ static size_t ws_slots(int64_t rows, int max_units, int sm_count) {
         }
     }
     size_t dr = (size_t)rows * choose_splits(rows, max_units, sm_count);
-    // beam-group kernel: chunk size chosen from the number of (group, head) pairs, >= rows / 4
-    int cug = choose_cu(rows / kGroupMaxW > 0 ? rows / kGroupMaxW : 1, max_units, sm_count, kOvWarps);
-    if (cug > 16) cug = 16;  // as launch_group
-    const size_t gr = (size_t)rows * ((max_units + cug - 1) / cug);
+    // beam-group kernel: its chunk size depends on the number of (group, head) pairs = rows / beam width (1..4)
+    size_t gr = 0;
+    for (int w = 1; w <= kGroupMaxW; ++w) {
+        int cug = choose_group_cu(rows / w > 0 ? rows / w : 1, max_units, sm_count);
+        if (getenv("PA_GROUP_CU")) cug = 2;  // experiments may lower the chunk size down to 2 units: size for that
+        const size_t v = (size_t)rows * ((max_units + cug - 1) / cug);
+        if (v > gr) gr = v;
+    }
     size_t mx = ov > dr ? ov : dr;
     if (gr > mx) mx = gr;
     return ((mx + 64) + 3) & ~(size_t)3;  // multiple of 4: ws_o stays 16-byte aligned
@@ -1513,8 +1561,7 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
             const int ns = a.num_splits;
             const int wpr = ns >= 64 ? 8 : (ns >= 32 ? 4 : (ns >= 16 ? 2 : 1));
             const int rpc = 8 / wpr;
-            combine_chunks_kernel<D><<<(int)((rows + rpc - 1) / rpc), 256, 0, st>>>(a, 1, wpr);
-            e = cudaGetLastError();
+            e = launch_combine_pdl<D>(a, 1, wpr, (int)((rows + rpc - 1) / rpc), 0, st);
             if (e != cudaSuccess) return (int)e;
         }
         return PA_OK;
@@ -1559,8 +1606,7 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
         const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
         const int rpc = 8 / wpr;
         const int cgrid = (int)((rows + rpc - 1) / rpc);
-        combine_chunks_kernel<D><<<cgrid, 256, prefix_bytes, st>>>(a, cu, wpr);
-        e = cudaGetLastError();
+        e = launch_combine_pdl<D>(a, cu, wpr, cgrid, prefix_bytes, st);
     }
     return e == cudaSuccess ? PA_OK : (int)e;
 }
@@ -1581,8 +1627,7 @@ static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStr
     a.all_rows_in_ws = 1;
     GroupArgs ga{W, a.B / W};
     const int64_t gh = (int64_t)ga.groups * a.H;
-    int cu = choose_cu(gh, max_units, di.sm_count, kOvWarps);
-    if (cu > 16) cu = 16;  // the group kernel's chunk queue and partial layout assume <= 16-unit chunks
+    const int cu = choose_group_cu(gh, max_units, di.sm_count);
     CUtensorMap tmK, tmV;
     const uint64_t total_tokens = (uint64_t)a.total_pages * a.tile_size;
     if (!make_pool_map(&tmK, a.k_pool, total_tokens) || !make_pool_map(&tmV, a.v_pool, total_tokens))
@@ -1610,8 +1655,7 @@ static int launch_group(DecodeArgs& a, int W, void* ws, size_t ws_bytes, cudaStr
     const int nc_max = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
     const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
     const int rpc = 8 / wpr;
-    combine_chunks_kernel<D><<<(int)((rows + rpc - 1) / rpc), 256, 0, st>>>(a, cu, wpr);
-    e = cudaGetLastError();
+    e = launch_combine_pdl<D>(a, cu, wpr, (int)((rows + rpc - 1) / rpc), 0, st);
     return e == cudaSuccess ? PA_OK : (int)e;
 }
 
