@@ -187,6 +187,26 @@ int pa_paged_decode_f32_overlap(const float* d_q, float* d_out, const float* d_k
                                 const float* d_rope, float* d_lse_out, void* d_workspace,
                                 size_t workspace_bytes, pa_stream_t stream);
 
+/* Decode attention WITH the reference's in-attention top-k / top-p filter and its optional side outputs: the CPU
+ * kernel's algorithm stage by stage (attention_cpu/cpu_attention_kernel.cpp:61-126) -- K pass, softmax over all T
+ * scores (softmax_lut.cpp:203-231), apply_topk_topp_filter (rank-based zeroing, no renormalisation,
+ * softmax_lut.cpp:233-256), V pass.  The filter needs a row's every probability before any is used, so this is
+ * the explicit three-stage form, not the one-pass kernels above; callers use it only when top_k > 0, top_p < 1
+ * or a side output is wanted (cpu_attention_kernel.hpp:20-21 defaults keep the hot path).
+ *   kv_kind: 0 fp16 pages, 1 int8 pages + scales, 2 fp32 pages.
+ *   d_logits_out  (optional) [B,H,T]: pre-softmax scores, -1e9 for unmapped tiles (CPUAttentionOutput::logits),
+ *                 -inf past a row's context;  d_weights_out (optional) [B,H,T]: post-filter probabilities
+ *                 (CPUAttentionOutput::attention_weights).  Whichever is NULL lives in d_workspace
+ *                 (>= pa_attention_filtered_workspace_bytes(B, num_heads, T)).  Temperature applied once (D3). */
+size_t pa_attention_filtered_workspace_bytes(int B, int num_heads, int T);
+int pa_paged_attention_filtered(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                                const float* d_k_scales, const float* d_v_scales, int kv_kind,
+                                const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                                int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B,
+                                int T, int head_dim, int tile_size, float temperature, const float* d_rope,
+                                int top_k, float top_p, float* d_logits_out, float* d_weights_out,
+                                void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+
 /* Beam-aware shared-prefix decode (north star; the reference's only hook is the
  * beam_ids[b] -> page-table-row indirection, ...fused.cu:22).  Rows b = g*beam_width ..
  * g*beam_width + beam_width-1 form beam group g.  Same results as pa_paged_decode_f16, but

@@ -6,8 +6,8 @@ C++ signatures: KVTileCache, PageTable, AttentionCUDA, AttentionTileLauncher, in
 functions and dnnl_matmul_int8.
 """
 from . import _cabi  # noqa: F401
-from .attention import (AttentionCUDA, AttentionTileLauncher, apply_rotary_embedding, lse_combine, paged_decode_group,  # noqa: F401
-                        paged_decode_partial, paged_prefill)
+from .attention import (AttentionCUDA, AttentionTileLauncher, apply_rotary_embedding, lse_combine,  # noqa: F401
+                        paged_attention_filtered, paged_decode_group, paged_decode_partial, paged_prefill)
 from .int8_quant import (batch_dequantize, batch_minmax_scale, batch_quantize, compute_absmax,  # noqa: F401
                          compute_minmax_scale, dequantize_from_int8, dnnl_matmul_int8, quantize_to_int8)
 from .kv_tile_cache import KVTileCache  # noqa: F401

@@ -39,6 +39,8 @@ _SIGS = {
     "pa_paged_decode_i8_overlap": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f32": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f32_overlap": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp], _i32),
+    "pa_attention_filtered_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "pa_paged_attention_filtered": ([_vp, _vp, _vp, _vp, _vp, _vp, _i32] + _DECODE_COMMON + [_i32, _f32, _vp, _vp, _vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_partial": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
     "pa_paged_decode_i8_partial": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _sz, _vp], _i32),
     "pa_paged_decode_f16_splitkv": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),

@@ -163,15 +163,19 @@ class AttentionTileLauncher:
     @staticmethod
     def launch(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
                use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
-               rerank_scores=None, debug=False, ctx_lens=None, sync=True):
+               rerank_scores=None, debug=False, ctx_lens=None, sync=True, logits=None, attention_weights=None):
         """sync=False (page-locked host q / out only): return once the work is enqueued; `out` is valid after
-        AttentionCUDA.synchronize().  Copies then overlap the kernels of neighbouring calls (HostPipe)."""
+        AttentionCUDA.synchronize().  Copies then overlap the kernels of neighbouring calls (HostPipe).
+        top_k > 0 / top_p < 1 (the reference's in-attention filter, softmax_lut.cpp:233-256) or the side outputs
+        `logits` / `attention_weights` ([B, H, T] f32 CUDA tensors, cpu_attention_kernel.hpp:34-39) take the explicit
+        three-stage kernels (pa_paged_attention_filtered); everything else the one-pass hot path."""
         if kv_cache is None:
             raise ValueError("AttentionTileLauncher.launch: kv_cache is required (paged path only)")
-        if top_k not in (0, None) or top_p < 1.0:
-            raise NotImplementedError(
-                "in-attention top-k/top-p filtering is not on the GPU path (SURVEY App. A D6); "
-                "pass top_k=0, top_p=1.0")
+        if top_k not in (0, None) or top_p < 1.0 or logits is not None or attention_weights is not None:
+            if _is_host(q) or _is_host(out) or rerank_scores is not None:
+                raise NotImplementedError("filtered attention: device q / out only, no rerank_scores")
+            return paged_attention_filtered(q, out, kv_cache, B, T, temperature, int(top_k or 0), float(top_p), beam_ids,
+                                            ctx_lens, rotary_emb, logits, attention_weights)
         pt = kv_cache.page_table_
         dev = kv_cache.key_buffer_.device
         assert H == pt.num_heads_ and D == kv_cache.head_dim_
@@ -263,10 +267,10 @@ class AttentionCUDA:
     @staticmethod
     def forward(q, out, B, H, D, T, beam_ids=None, kv_cache=None, rotary_emb=None, is_prefill=True,
                 use_fp16=False, use_overlap=False, temperature=1.0, top_k=0, top_p=1.0,
-                rerank_scores=None, debug=False, ctx_lens=None, sync=True):
+                rerank_scores=None, debug=False, ctx_lens=None, sync=True, logits=None, attention_weights=None):
         return AttentionTileLauncher.launch(q, out, B, H, D, T, beam_ids, kv_cache, rotary_emb,
                                             is_prefill, use_fp16, use_overlap, temperature, top_k,
-                                            top_p, rerank_scores, debug, ctx_lens, sync)
+                                            top_p, rerank_scores, debug, ctx_lens, sync, logits, attention_weights)
 
     @staticmethod
     def synchronize(device=None):
@@ -318,6 +322,41 @@ def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_s
                                          kv_cache.value_buffer_.data_ptr(), kv_cache.k_scales_.data_ptr(),
                                          kv_cache.v_scales_.data_ptr(), *common, _cabi.stream())
     _cabi.check(st, "pa_paged_prefill")
+    return out
+
+
+def _dev_i32(x, dev):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        return x
+    return torch.as_tensor(np.asarray(x), dtype=torch.int32).to(dev)
+
+
+def paged_attention_filtered(q, out, kv_cache, B, T, temperature=1.0, top_k=0, top_p=1.0, beam_ids=None, ctx_lens=None,
+                             rotary_emb=None, logits=None, attention_weights=None):
+    """pa_paged_attention_filtered: the CPU kernel's K pass -> softmax -> top-k / top-p filter -> V pass
+    (cpu_attention_kernel.cpp:61-126) with the optional side outputs logits / attention_weights [B, H, T]."""
+    pt = kv_cache.page_table_
+    dev = kv_cache.key_buffer_.device
+    H, D = pt.num_heads_, kv_cache.head_dim_
+    lib = _cabi.lib()
+    kind = {"f16": 0, "i8": 1, "f32": 2}[kv_cache.dtype]
+    need = lib.pa_attention_filtered_workspace_bytes(B, H, T)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    d_beam, d_ctx = _dev_i32(beam_ids, dev), _dev_i32(ctx_lens, dev)
+    d_rope = None if rotary_emb is None else (rotary_emb if (isinstance(rotary_emb, torch.Tensor) and rotary_emb.is_cuda)
+                                              else torch.as_tensor(np.asarray(rotary_emb), dtype=torch.float32).to(dev))
+    for t in (logits, attention_weights):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == B * H * T)
+    with torch.cuda.device(dev):
+        st = lib.pa_paged_attention_filtered(
+            q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
+            _cabi.ptr(kv_cache.k_scales_), _cabi.ptr(kv_cache.v_scales_), kind, pt.device_data().data_ptr(), pt.num_beams_, H,
+            pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(d_beam), _cabi.ptr(d_ctx), B, T, D, kv_cache.tile_size_,
+            float(temperature), _cabi.ptr(d_rope), int(top_k), float(top_p), _cabi.ptr(logits), _cabi.ptr(attention_weights),
+            ws.data_ptr(), ws.numel(), _cabi.stream())
+    _cabi.check(st, "pa_paged_attention_filtered")
     return out
 
 

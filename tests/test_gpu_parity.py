@@ -265,12 +265,52 @@ def test_host_buffers_roundtrip(ld, oracle):
     np.testing.assert_allclose(op.numpy(), oracle_attention(case), rtol=RTOL, atol=ATOL)
 
 
-def test_topk_rejected(ld):
-    case = make_case(B=1, H=1, D=128, T=32, seed=23)
+@pytest.mark.parametrize("kv", ["f16", "i8", "f32"])
+@pytest.mark.parametrize("filt", [(0, 1.0), (5, 1.0), (0, 0.7), (7, 0.9), (1, 1.0)])
+def test_in_attention_topk_topp_and_side_outputs(ld, oracle, kv, filt):
+    """AttentionCUDA.forward with the reference's in-attention filter (top_k / top_p; cpu_attention_kernel.cpp:93-97,
+    apply_topk_topp_filter softmax_lut.cpp:233-256: rank-based zeroing, no renormalisation) and the side outputs
+    logits / attention_weights (cpu_attention_kernel.hpp:34-39): output, weights and logits against the oracle,
+    ragged rows, unmapped pages, beam_ids."""
+    top_k, top_p = filt
+    case = make_case(B=4, H=3, D=128 if kv != "i8" else 64, T=200, seed=71, kv=kv, ragged=True, unmapped_frac=0.05)
+    B, H, D = case["q"].shape
+    T = case["T"]
+    exp, probs, logits = oracle_attention(case, top_k=top_k, top_p=top_p, return_probs=True, return_logits=True)
     kvc = to_device_cache(case)
     q = torch.from_numpy(case["q"]).cuda()
+    out = torch.full((B, H, D), float("nan"), device="cuda")
+    lg = torch.empty((B, H, T), device="cuda")
+    aw = torch.empty((B, H, T), device="cuda")
+    ld.AttentionCUDA.forward(q, out, B, H, D, T, None, kvc, None, False, kv != "i8", True, case["temperature"], top_k, top_p,
+                             None, False, ctx_lens=case["ctx_lens"], logits=lg, attention_weights=aw)
+    torch.cuda.synchronize()
+    got, gl, gw = out.cpu().numpy(), lg.cpu().numpy(), aw.cpu().numpy()
+    for b in range(B):
+        ctx = int(case["ctx_lens"][b])
+        # pre-softmax scores (incl. the -1e9 of unmapped tiles), then the filtered probabilities
+        np.testing.assert_allclose(gl[b, :, :ctx], logits[b, :, :ctx], rtol=1e-5, atol=1e-5)
+        assert np.isneginf(gl[b, :, ctx:]).all()
+        if ctx == 0:
+            continue
+        w, e = gw[b, :, :ctx], probs[b, :, :ctx]
+        # rank-based zeroing: the same entries survive (ties at the cut are measure-zero with random data)
+        assert ((w == 0) == (e == 0)).mean() > 0.999
+        np.testing.assert_allclose(w, e, rtol=1e-4, atol=1e-6)
+        assert (gw[b, :, ctx:] == 0).all()
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
+    if top_k == 0 and top_p >= 1.0:  # no filter: the three-stage form equals the one-pass hot path
+        hot, _ = run_decode(ld, case, True)
+        tol = dict(rtol=RTOL, atol=ATOL) if kv == "i8" else dict(rtol=1e-4, atol=1e-5)  # int8 hot path: rcp.approx scales
+        np.testing.assert_allclose(got, hot, **tol)
+
+
+def test_in_attention_filter_host_buffers_rejected(ld):
+    case = make_case(B=1, H=1, D=128, T=32, seed=23)
+    kvc = to_device_cache(case)
     with pytest.raises(NotImplementedError):
-        ld.AttentionCUDA.forward(q, q, 1, 1, 128, 32, None, kvc, None, False, True, False, 1.0, 1, 1.0)
+        ld.AttentionCUDA.forward(case["q"], np.zeros_like(case["q"]), 1, 1, 128, 32, None, kvc, None, False, True, False, 1.0,
+                                 1, 1.0)
 
 
 @pytest.mark.parametrize("kv", ["f16", "i8"])
