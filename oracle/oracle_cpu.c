@@ -103,6 +103,10 @@ ORC_API void orc_kv_append(uint8_t* k_pool, uint8_t* v_pool, const int32_t* tabl
     for (int r = 0; r < R; ++r) {
         int beam = beam_ids ? beam_ids[r] : r;
         int pos = positions[r];
+        /* deliberate deviation (SURVEY App. A D14 family): a position past the table's capacity, or a beam outside
+         * it, writes nothing; the reference's flat-index bound (page_table.hpp:44-49) would alias into another
+         * head's / beam's entry and overwrite its page. */
+        if (pos < 0 || pos / tile_size >= num_tiles || beam < 0 || beam >= num_beams) continue;
         for (int h = 0; h < num_heads; ++h) {
             int64_t off = orc_kv_page_offset(table, total_entries, beam, h, pos / tile_size,
                                              num_heads, num_tiles, total_pages, tile_size, head_dim);

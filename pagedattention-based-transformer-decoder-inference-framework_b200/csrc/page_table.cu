@@ -126,7 +126,11 @@ __global__ void kv_append_kernel(void* __restrict__ k_pool, void* __restrict__ v
     const int r = (int)(w / num_heads);
     const int beam = beam_ids ? beam_ids[r] : r;
     const int pos = positions[r];
-    if (pos < 0) return;
+    // A position past the table's capacity writes NOTHING.  The reference's lookup only bounds the FLAT index
+    // (page_table.hpp:44-49), so tile_id >= num_tiles aliases into the next head's / beam's entries and
+    // get_write_ptr (kv_tile_cache.hpp:29-34) would hand out somebody else's page -- silent corruption of another
+    // sequence's cache (found by tests/test_bounds_guards.py).  Reads keep the reference's flat-index rule.
+    if (pos < 0 || pos / tile_size >= num_tiles || (unsigned)beam >= (unsigned)num_beams) return;
     const int page = pt_lookup(table, (int64_t)num_beams * num_heads * num_tiles, beam, h,
                                pos / tile_size, num_heads, num_tiles);
     if (page < 0 || page >= total_pages) return;  // get_write_ptr -> nullptr
