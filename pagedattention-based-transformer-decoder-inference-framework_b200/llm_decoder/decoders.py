@@ -20,6 +20,13 @@ the host with aliased buffers is meaningless:
     dnnl_matmul_int8 -> dequant" pipeline of attention_cpu/README.md:80-86 instead of
     MLP<int8_t>'s overflowing int8 accumulators (mlp.hpp:28).
 
+Optional attention projections (weights/README.md:31-34): when a layer directory holds
+attn_wq.bin / attn_wk.bin / attn_wv.bin / attn_wo.bin (each [hidden, hidden] row-major, column block h = head h's
+[hidden, head_dim] matrix of the README), q = n.Wq, k = n.Wk, v = n.Wv feed the paged cache / attention and the
+attention output is multiplied by Wo before LN2.  CUDADecoder: fp32 (pa_linear_f32); INT8Decoder: int8 weights on the
+tcgen05 GEMM (pa_gemm_i8_dequant) with the LN1 output quantised per row.  Files absent = the reference block (q = k = v
+= LN1 output, no output projection).
+
 Every step runs on the device through libpa_b200.so (no host math, no per-step
 synchronisation); the steady-state step is captured in a CUDA graph.
 """
@@ -33,6 +40,7 @@ from . import _cabi
 from .kv_tile_cache import KVTileCache
 
 _LAYER_FILES = ("ln1.bin", "ln2.bin", "mlp_fc1.bin", "mlp_fc2.bin", "mlp_biases.bin")  # int8_decoder.cpp:66-70
+_ATTN_FILES = ("attn_wq.bin", "attn_wk.bin", "attn_wv.bin", "attn_wo.bin")               # weights/README.md:31-34
 
 
 def _read_bin(path, dtype, count, what):
@@ -64,6 +72,7 @@ class _Bufs:
         self.xs = torch.ones(R, **f32)
         self.hs = torch.ones(R, **f32)
         self.ws = None  # GEMM / linear scratch for R rows (owned here, never by the library; _DecoderBase._scratch)
+        self.qp = self.kp = self.vp = None  # q / k / v projections [R, hid] f32, allocated when a layer has them
 
 
 class _DecoderBase:
@@ -187,9 +196,18 @@ class _DecoderBase:
         for li, L in enumerate(self.layers):
             self._chk(lib.pa_layer_norm_f32(bf.x.data_ptr(), L.ln1_g.data_ptr(), L.ln1_b.data_ptr(), R, hid,
                                             self.eps, bf.n.data_ptr(), s), "pa_layer_norm_f32")
-            nview = bf.n.view(R, self.num_heads_, self.head_dim_)
-            self.kv_caches[li].append(nview, nview, positions, beam_ids)  # K = V = LN1 output (see module doc)
-            self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws, prefill_shape)
+            H, D = self.num_heads_, self.head_dim_
+            if getattr(L, "wq", None) is None:
+                nview = bf.n.view(R, H, D)
+                self.kv_caches[li].append(nview, nview, positions, beam_ids)  # K = V = LN1 output (see module doc)
+                self._attention(li, bf.n, bf.a, R, ctx_lens, beam_ids, ws, prefill_shape)
+            else:
+                if bf.qp is None:
+                    bf.qp, bf.kp, bf.vp = (torch.empty((R, hid), dtype=torch.float32, device=self.device) for _ in range(3))
+                self._qkv_proj(bf, L)                                   # bf.n -> bf.qp, bf.kp, bf.vp
+                self.kv_caches[li].append(bf.kp.view(R, H, D), bf.vp.view(R, H, D), positions, beam_ids)
+                self._attention(li, bf.qp, bf.kp, R, ctx_lens, beam_ids, ws, prefill_shape)   # kp reused as the output
+                self._o_proj(bf, L, bf.kp, bf.a)                        # attention output . Wo -> bf.a
             self._ln2_mlp(bf, L)
 
     def _ln2_mlp(self, bf, L):
@@ -378,6 +396,7 @@ class CUDADecoder(_DecoderBase):
             L.ln1_g, L.ln1_b = torch.ones(hid, device=dev), z(hid)  # layer_norm.hpp:11 gamma=1, beta=0
             L.ln2_g, L.ln2_b = torch.ones(hid, device=dev), z(hid)
             L.fc1_w, L.fc1_b, L.fc2_w, L.fc2_b = z(hid, inter), z(inter), z(inter, hid), z(hid)
+            L.wq = L.wk = L.wv = L.wo = None
 
     def load_weights(self, path):
         """cuda_decoder.cu:35-45: <path>/embedding.bin, <path>/layer_<i>/{ln1.bin, ln2.bin} (gamma then
@@ -411,11 +430,30 @@ class CUDADecoder(_DecoderBase):
                 raise RuntimeError("Cannot open MLP weights file")  # mlp.hpp:16
             L.fc1_w, L.fc1_b = self._dev(fc1.reshape(hid, inter)), self._dev(b1)
             L.fc2_w, L.fc2_b = self._dev(fc2.reshape(inter, hid)), self._dev(b2)
+            L.wq = L.wk = L.wv = L.wo = None
+            if os.path.isfile(os.path.join(lp, "attn_wq.bin")):  # weights/README.md:31-34 (optional)
+                for nm in ("wq", "wk", "wv", "wo"):
+                    setattr(L, nm, self._dev(_read_bin(os.path.join(lp, f"attn_{nm}.bin"), np.float32, hid * hid,
+                                                       f"attn_{nm}").reshape(hid, hid)))
         self._graph = None
         self._emb_T = None
 
     def _embedding_table(self):
         return self.embedding, 4, 1.0
+
+    def _lin(self, bf, x, W, out):
+        lib, R, hid = self._lib, bf.R, self.hidden_dim_
+        wp, wb = self._scratch(bf, lib.pa_linear_workspace_bytes(R, hid, hid))
+        self._chk(lib.pa_linear_f32(x.data_ptr(), W.data_ptr(), None, R, hid, hid, _cabi.ACT[""], out.data_ptr(), wp, wb,
+                                    _cabi.stream()), "pa_linear_f32")
+
+    def _qkv_proj(self, bf, L):
+        self._lin(bf, bf.n, L.wq, bf.qp)
+        self._lin(bf, bf.n, L.wk, bf.kp)
+        self._lin(bf, bf.n, L.wv, bf.vp)
+
+    def _o_proj(self, bf, L, x, out):
+        self._lin(bf, x, L.wo, out)
 
     def _head(self, x_rows):
         """More than 8 rows: logits = x . E^T through the fp32 linear kernel on a transposed copy of the table
@@ -484,6 +522,7 @@ class INT8Decoder(_DecoderBase):
             L.fc1_w, L.fc2_w = zi(hid, inter), zi(inter, hid)
             L.fc1_deq = L.fc2_deq = 1.0 / 127.0
             L.fc1_b, L.fc2_b = z(inter), z(hid)
+            L.wq = L.wk = L.wv = L.wo = None
 
     def quantize_weights(self, path_fp32, path_int8):
         """int8_decoder.cpp:43-89: embedding.bin and, per layer, ln1/ln2/mlp_fc1/mlp_fc2/mlp_biases .bin are
@@ -506,6 +545,9 @@ class INT8Decoder(_DecoderBase):
             os.makedirs(os.path.join(path_int8, f"layer_{i}"), exist_ok=True)
             for fname in _LAYER_FILES:
                 one(f"layer_{i}/{fname}")
+            for fname in _ATTN_FILES:  # optional projections (weights/README.md:31-34): quantised like every other file
+                if os.path.isfile(os.path.join(path_fp32, f"layer_{i}", fname)):
+                    one(f"layer_{i}/{fname}")
         with open(os.path.join(path_int8, self.SCALES_FILE), "w") as f:
             json.dump(scales, f, indent=1)
         print(f"[INT8Decoder] Quantized weights saved to {path_int8}")  # int8_decoder.cpp:88
@@ -537,8 +579,32 @@ class INT8Decoder(_DecoderBase):
             L.fc1_deq, L.fc2_deq = deq(rel("mlp_fc1.bin")), deq(rel("mlp_fc2.bin"))
             bb = rd("mlp_biases.bin", inter + hid) * np.float32(deq(rel("mlp_biases.bin")))
             L.fc1_b, L.fc2_b = self._dev(bb[:inter]), self._dev(bb[inter:])
+            L.wq = L.wk = L.wv = L.wo = None
+            if os.path.isfile(os.path.join(path_int8, rel("attn_wq.bin"))):
+                for nm in ("wq", "wk", "wv", "wo"):
+                    f = f"attn_{nm}.bin"
+                    setattr(L, nm, self._dev(_read_bin(os.path.join(path_int8, rel(f)), np.int8, hid * hid, f).reshape(hid, hid),
+                                             torch.int8))
+                    setattr(L, nm + "_deq", deq(rel(f)))
         self._graph = None
         self._emb_T = None
+
+    def _gemm_deq(self, bf, xq, xs, W, w_deq, out):
+        lib, R, hid = self._lib, bf.R, self.hidden_dim_
+        wp, wb = self._scratch(bf, lib.pa_gemm_i8_workspace_bytes(1, R, hid, hid))
+        self._chk(lib.pa_gemm_i8_dequant(xq.data_ptr(), W.data_ptr(), out.data_ptr(), 1, R, hid, hid, xs.data_ptr(),
+                                         float(w_deq), None, _cabi.ACT[""], wp, wb, _cabi.stream()), "pa_gemm_i8_dequant")
+
+    def _qkv_proj(self, bf, L):
+        """int8_quant -> three tcgen05 GEMMs with the dequantising epilogue (the LN1 output is quantised once)."""
+        self._quant_rows(bf.n, bf.xq, bf.xs, bf.R, self.hidden_dim_)
+        self._gemm_deq(bf, bf.xq, bf.xs, L.wq, L.wq_deq, bf.qp)
+        self._gemm_deq(bf, bf.xq, bf.xs, L.wk, L.wk_deq, bf.kp)
+        self._gemm_deq(bf, bf.xq, bf.xs, L.wv, L.wv_deq, bf.vp)
+
+    def _o_proj(self, bf, L, x, out):
+        self._quant_rows(x, bf.xq, bf.xs, bf.R, self.hidden_dim_)
+        self._gemm_deq(bf, bf.xq, bf.xs, L.wo, L.wo_deq, out)
 
     def _embedding_table(self):
         return self.embedding, 1, float(self.emb_qscale)

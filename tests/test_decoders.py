@@ -31,11 +31,15 @@ def test_quantize_weights_arithmetic_matches_restatement(oracle):
 
 
 # ------------------------------------------------------------------ helpers
-def make_weights(rng, L, hid, V, scale=1.0):
+def make_weights(rng, L, hid, V, scale=1.0, attn=False):
     inter = 4 * hid
     w = {"embedding": (rng.standard_normal((V, hid)) * scale).astype(np.float32), "layers": []}
     for _ in range(L):
+        extra = {}
+        if attn:  # optional attention projections (weights/README.md:31-34)
+            extra = {n: (rng.standard_normal((hid, hid)) / np.sqrt(hid)).astype(np.float32) for n in ("wq", "wk", "wv", "wo")}
         w["layers"].append(dict(
+            **extra,
             ln1_g=(1 + 0.1 * rng.standard_normal(hid)).astype(np.float32),
             ln1_b=(0.1 * rng.standard_normal(hid)).astype(np.float32),
             ln2_g=(1 + 0.1 * rng.standard_normal(hid)).astype(np.float32),
@@ -55,6 +59,9 @@ def write_fp32_tree(w, path, packed_mlp):
         os.makedirs(lp, exist_ok=True)
         np.concatenate([L["ln1_g"], L["ln1_b"]]).tofile(os.path.join(lp, "ln1.bin"))
         np.concatenate([L["ln2_g"], L["ln2_b"]]).tofile(os.path.join(lp, "ln2.bin"))
+        for n in ("wq", "wk", "wv", "wo"):
+            if n in L:
+                L[n].tofile(os.path.join(lp, f"attn_{n}.bin"))
         if packed_mlp:   # the order MLP::load_weights reads (mlp.hpp:17-20)
             np.concatenate([L["fc1_w"].ravel(), L["fc1_b"], L["fc2_w"].ravel(), L["fc2_b"]]).tofile(
                 os.path.join(lp, "mlp.bin"))
@@ -510,3 +517,79 @@ def test_int8_decoder_fused_quantisation_same_tokens(monkeypatch):
     assert outs[0][2] is True and outs[1][2] is False
     assert outs[0][0] == outs[1][0]
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+# ------------------------------------------------------------------ GPU: optional Q/K/V/O projections (8f row 1)
+@pytest.mark.gpu
+def test_cuda_decoder_with_attention_projections(oracle, tmp_path):
+    """attn_wq / wk / wv / wo present in the layer directories (weights/README.md:31-34): q, k, v are projected before
+    the cache append / attention and the attention output goes through Wo -- tokens and logits against the oracle."""
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(37)
+    L, H, D, V, S = 2, 2, 64, 151, 40
+    hid = H * D
+    w = make_weights(rng, L, hid, V, attn=True)
+    write_fp32_tree(w, str(tmp_path / "w"), True)
+    dec = ld.CUDADecoder(L, H, D, hid, V, S)
+    dec.load_weights(str(tmp_path / "w"))
+    assert dec.layers[0].wq is not None
+    prompt = [3, 17, 101, 5, 9]
+    out = dec.generate(prompt, 10, 0.8)
+    check_teacher_forced(out, len(prompt), RefDecoder(w, H, D), 0.8, 1, None, 1e-4)
+    dec2 = ld.CUDADecoder(L, H, D, hid, V, S, use_prefill=False, use_cuda_graph=False)
+    dec2.load_weights(str(tmp_path / "w"))
+    assert dec2.generate(prompt, 10, 0.8) == out
+    dec.reset()
+    ref = RefDecoder(w, H, D)
+    for tok in prompt:
+        np.testing.assert_allclose(dec.forward_tokens([tok]).cpu().numpy()[0], ref.step(tok), rtol=2e-3, atol=2e-3)
+    # a tree WITHOUT the files keeps the reference block (q = k = v = LN1 output)
+    w0 = {"embedding": w["embedding"], "layers": [{k: v for k, v in Ly.items() if not k.startswith("w")} for Ly in w["layers"]]}
+    write_fp32_tree(w0, str(tmp_path / "w0"), True)
+    dec3 = ld.CUDADecoder(L, H, D, hid, V, S)
+    dec3.load_weights(str(tmp_path / "w0"))
+    assert dec3.layers[0].wq is None
+    check_teacher_forced(dec3.generate(prompt, 6, 0.8), len(prompt), RefDecoder(w0, H, D), 0.8, 1, None, 1e-4)
+
+
+@pytest.mark.gpu
+def test_int8_decoder_with_attention_projections(oracle, tmp_path):
+    """The same through quantize_weights / load_quantized_weights: the four projection files are quantised like every
+    other file and run on the tcgen05 int8 GEMM (int8_quant -> GEMM -> dequant)."""
+    import json
+    import llm_decoder as ld
+    from oracle.decoder_ref import RefDecoder
+    rng = np.random.default_rng(38)
+    L, H, D, V, S = 2, 2, 64, 149, 40
+    hid, inter = H * D, 4 * H * D
+    w = make_weights(rng, L, hid, V, attn=True)
+    fp32, int8 = str(tmp_path / "fp32"), str(tmp_path / "int8")
+    write_fp32_tree(w, fp32, packed_mlp=False)
+    dec = ld.INT8Decoder(L, H, D, hid, V, S)
+    dec.quantize_weights(fp32, int8)
+    for i in range(L):
+        for n in ("wq", "wk", "wv", "wo"):
+            exp, _ = oracle.cpu.quantize_weights_file(np.fromfile(os.path.join(fp32, f"layer_{i}/attn_{n}.bin"), np.float32))
+            assert np.fromfile(os.path.join(int8, f"layer_{i}/attn_{n}.bin"), np.int8).tobytes() == exp.tobytes()
+    dec.load_quantized_weights(int8)
+    assert dec.layers[0].wq is not None and dec.layers[0].wq.dtype == torch.int8
+    out = dec.generate([1, 2, 3], 8, 1.0)
+    scales = json.load(open(os.path.join(int8, "quant_scales.json")))
+    deq = lambda rel: np.float32(scales[rel] / 127.0)   # noqa: E731
+    rd = lambda rel: np.fromfile(os.path.join(int8, rel), np.int8)  # noqa: E731
+    wq = {"embedding": rd("embedding.bin").reshape(V, hid), "emb_qscale": 1.0 / (scales["embedding.bin"] / 127.0), "layers": []}
+    for i in range(L):
+        r = lambda f: f"layer_{i}/{f}"  # noqa: E731
+        ln1 = rd(r("ln1.bin")).astype(np.float32) * deq(r("ln1.bin"))
+        ln2 = rd(r("ln2.bin")).astype(np.float32) * deq(r("ln2.bin"))
+        bb = rd(r("mlp_biases.bin")).astype(np.float32) * deq(r("mlp_biases.bin"))
+        Ly = dict(ln1_g=ln1[:hid], ln1_b=ln1[hid:], ln2_g=ln2[:hid], ln2_b=ln2[hid:],
+                  fc1_w=rd(r("mlp_fc1.bin")).reshape(hid, inter), fc1_deq=float(deq(r("mlp_fc1.bin"))),
+                  fc2_w=rd(r("mlp_fc2.bin")).reshape(inter, hid), fc2_deq=float(deq(r("mlp_fc2.bin"))),
+                  fc1_b=bb[:inter], fc2_b=bb[inter:])
+        for n in ("wq", "wk", "wv", "wo"):
+            Ly[n] = rd(r(f"attn_{n}.bin")).reshape(hid, hid)
+            Ly[n + "_deq"] = float(deq(r(f"attn_{n}.bin")))
+        wq["layers"].append(Ly)
+    check_teacher_forced(out, 3, RefDecoder(wq, H, D, int8=True), 1.0, 0, None, 5e-3)
