@@ -462,6 +462,16 @@ int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_part_l, co
                                 int head_dim, uint32_t* d_epochs, float* d_out, float* d_lse_out,
                                 int* d_status, pa_stream_t stream);
 
+/* The two halves of pa_splitkv_exchange_combine on their own: _send stores this rank's rows into every peer's
+ * buffer and never waits; _recv polls until every rank's packets of the current step are in this rank's buffer,
+ * combines and advances the epochs. */
+int pa_splitkv_exchange_send(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                             void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                             const uint32_t* d_epochs, pa_stream_t stream);
+int pa_splitkv_exchange_recv(void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                             uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
+                             pa_stream_t stream);
+
 /* --------------------------------- NCCL form of the exchange (the north star's baseline) */
 /* NCCL is loaded at run time (dlopen "libnccl.so.2"); PA_ERR_UNSUPPORTED when it is absent.
  * pa_nccl_unique_id: rank 0 creates the 128-byte ncclUniqueId, the application distributes it;

@@ -1060,13 +1060,20 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         cfg.blockDim = dim3(NTHREADS2);
         cfg.dynamicSmemBytes = smem2;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = clp2 ? 4u : 2u;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (dq) {
+            // the epilogue contains a grid-wide barrier: a COOPERATIVE launch makes the driver guarantee (or refuse)
+            // that every CTA is resident at once instead of leaving it to the grid-size check above
+            attr[1].id = cudaLaunchAttributeCooperative;
+            attr[1].val.cooperative = 1;
+            cfg.numAttrs = 2;
+        }
         e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
         if (e != cudaSuccess) return (int)e;
         e = cudaGetLastError();

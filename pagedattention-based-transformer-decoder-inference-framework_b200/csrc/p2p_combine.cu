@@ -23,22 +23,27 @@ namespace pa {
 
 // grid-stride over rows, one warp per row: all sends first, then all receives (a send never waits, so no
 // ordering between ranks or CTAs is assumed and any number of rows fits any grid).
+// phases: 1 = send, 2 = receive + combine, 3 = both (the normal call)
 template <int D>
 __global__ void __launch_bounds__(256) splitkv_exchange_combine_kernel(
     const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
     uint8_t* const* __restrict__ peers, int rank, int world, int rows, uint32_t* __restrict__ epochs,
-    float* __restrict__ out, float* __restrict__ lse_out, int* __restrict__ status) {
+    float* __restrict__ out, float* __restrict__ lse_out, int* __restrict__ status, int phases) {
     constexpr int VEC = D / 32;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int row = gw; row < rows; row += nw) {
-        float O[VEC];
+    if (phases & 1) {
+        for (int row = gw; row < rows; row += nw) {
+            float O[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) O[e] = po[(size_t)row * D + lane * VEC + e];
-        xchg::send_row<D>(peers, epochs, rank, world, rows, row, O, pm[row], pl[row], lane);
+            for (int e = 0; e < VEC; ++e) O[e] = po[(size_t)row * D + lane * VEC + e];
+            xchg::send_row<D>(peers, epochs, rank, world, rows, row, O, pm[row], pl[row], lane);
+        }
     }
-    for (int row = gw; row < rows; row += nw)
-        xchg::recv_row<D>(peers, epochs, rank, world, rows, row, out, lse_out, status, lane);
+    if (phases & 2) {
+        for (int row = gw; row < rows; row += nw)
+            xchg::recv_row<D>(peers, epochs, rank, world, rows, row, out, lse_out, status, lane);
+    }
 }
 
 // ---- NCCL through dlopen -------------------------------------------------------------------------------
@@ -124,11 +129,13 @@ PA_API int pa_p2p_free(void* d_ptr) {
     return e == cudaSuccess ? PA_OK : (int)e;
 }
 
-PA_API int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
-                                       void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
-                                       uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
-                                       pa_stream_t stream) {
-    PA_CHECK_ARG(d_part_m && d_part_l && d_part_o && d_peer_bufs && d_out && d_epochs);
+static int exchange_launch(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                           void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                           uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
+                           pa_stream_t stream, int phases) {
+    PA_CHECK_ARG(d_peer_bufs && d_epochs);
+    PA_CHECK_ARG(!(phases & 1) || (d_part_m && d_part_l && d_part_o));
+    PA_CHECK_ARG(!(phases & 2) || d_out);
     PA_CHECK_ARG(world > 0 && world <= 32 && rank >= 0 && rank < world && rows >= 0);
     if (head_dim != 64 && head_dim != 128) return PA_ERR_UNSUPPORTED;
     if (rows == 0) return PA_OK;
@@ -138,11 +145,35 @@ PA_API int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_par
     uint8_t* const* peers = reinterpret_cast<uint8_t* const*>(d_peer_bufs);
     if (head_dim == 128)
         splitkv_exchange_combine_kernel<128><<<blocks, 256, 0, as_stream(stream)>>>(
-            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status);
+            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status, phases);
     else
         splitkv_exchange_combine_kernel<64><<<blocks, 256, 0, as_stream(stream)>>>(
-            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status);
+            d_part_m, d_part_l, d_part_o, peers, rank, world, rows, d_epochs, d_out, d_lse_out, d_status, phases);
     PA_RETURN_LAUNCH_STATUS();
+}
+
+PA_API int pa_splitkv_exchange_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                                       void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                                       uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
+                                       pa_stream_t stream) {
+    return exchange_launch(d_part_m, d_part_l, d_part_o, d_peer_bufs, rank, world, rows, head_dim, d_epochs, d_out,
+                           d_lse_out, d_status, stream, 3);
+}
+
+// The two halves on their own.  SEND never waits for anybody; RECV polls until every rank's packets of the current
+// step are in this rank's buffer.  (Several ranks emulated on ONE device must use them in this order -- all sends,
+// then the receives -- so that no kernel ever waits for another kernel on the same GPU.)
+PA_API int pa_splitkv_exchange_send(const float* d_part_m, const float* d_part_l, const float* d_part_o,
+                                    void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                                    const uint32_t* d_epochs, pa_stream_t stream) {
+    return exchange_launch(d_part_m, d_part_l, d_part_o, d_peer_bufs, rank, world, rows, head_dim,
+                           const_cast<uint32_t*>(d_epochs), nullptr, nullptr, nullptr, stream, 1);
+}
+PA_API int pa_splitkv_exchange_recv(void* const* d_peer_bufs, int rank, int world, int rows, int head_dim,
+                                    uint32_t* d_epochs, float* d_out, float* d_lse_out, int* d_status,
+                                    pa_stream_t stream) {
+    return exchange_launch(nullptr, nullptr, nullptr, d_peer_bufs, rank, world, rows, head_dim, d_epochs, d_out, d_lse_out,
+                           d_status, stream, 2);
 }
 
 // ---- NCCL form (SURVEY 8b "pa_nccl_* init / allgather-combine", 8e) ---------------------------------------

@@ -85,6 +85,8 @@ _SIGS = {
     "pa_p2p_close": ([_vp], _i32),
     "pa_p2p_free": ([_vp], _i32),
     "pa_splitkv_exchange_combine": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "pa_splitkv_exchange_send": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pa_splitkv_exchange_recv": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "pa_nccl_unique_id": ([C.c_char_p], _i32),
     "pa_nccl_init": ([C.c_char_p, _i32, _i32, C.POINTER(_vp)], _i32),
     "pa_nccl_destroy": ([_vp], _i32),

@@ -990,11 +990,12 @@ def test_fused_splitkv_world1_is_the_plain_decode(ld, oracle, kv, shape, path, m
 @pytest.mark.parametrize("path", ["grid", "streaming"])
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv, path, monkeypatch):
-    """Two 'ranks' on one device, each holding half of the sequence's pages.  Rank 1 runs the stand-alone exchange
-    kernel (partials -> pa_splitkv_exchange_combine) on its own stream: it sends, then polls for rank 0.  Rank 0 runs
-    the FUSED kernel (pa_paged_decode_*_splitkv) on another stream: it streams its pages, merges, sends to both
-    buffers, and receives both sources.  Both forms speak the same packet protocol; both outputs must equal the
-    oracle over the WHOLE sequence; two steps (buffer parity flips)."""
+    """Two 'ranks' on one device, each holding half of the sequence's pages, run strictly ONE KERNEL AFTER THE OTHER on
+    one stream so that no kernel ever waits for another kernel on the same GPU: rank 1 computes its partials and only
+    SENDS them (pa_splitkv_exchange_send: stores into both buffers, never waits); rank 0 runs the FUSED path
+    (pa_paged_decode_*_splitkv: streams its pages, merges, sends, receives -- rank 1's packets are already there);
+    rank 1 then RECEIVES (pa_splitkv_exchange_recv: rank 0's packets are there).  All forms speak the same packet
+    protocol; both outputs must equal the oracle over the WHOLE sequence; two steps (buffer parity flips)."""
     from llm_decoder import _cabi
     lib = _cabi.lib()
     monkeypatch.setenv("PA_PARTIAL_DIRECT", "1" if path == "grid" else "0")
@@ -1006,24 +1007,22 @@ def test_splitkv_two_ranks_on_one_gpu(ld, oracle, kv, path, monkeypatch):
     epochs = [torch.zeros(2 * rows, dtype=torch.int32, device="cuda") for _ in range(2)]
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     exp = oracle_attention(case)
-    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
     q = torch.from_numpy(case["q"]).cuda()
     for step in range(2):
         out0 = torch.full((B, H, D), float("nan"), device="cuda")
         out1 = torch.full((rows, D), float("nan"), device="cuda")
         pm, pl, po = ld.paged_decode_partial(q, caches[1], B, case["T"], case["temperature"])
-        torch.cuda.synchronize()
-        with torch.cuda.stream(s1):
-            _cabi.check(lib.pa_splitkv_exchange_combine(pm.data_ptr(), pl.data_ptr(), po.data_ptr(), ptrs.data_ptr(), 1, 2,
-                                                        rows, D, epochs[1].data_ptr(), out1.data_ptr(), None,
-                                                        status.data_ptr(), s1.cuda_stream), "exchange")
-        with torch.cuda.stream(s0):
-            _splitkv(ld, case, caches[0], ptrs, 0, 2, epochs[0], status, out0, s0.cuda_stream)
+        _cabi.check(lib.pa_splitkv_exchange_send(pm.data_ptr(), pl.data_ptr(), po.data_ptr(), ptrs.data_ptr(), 1, 2, rows, D,
+                                                 epochs[1].data_ptr(), None), "send")
+        _splitkv(ld, case, caches[0], ptrs, 0, 2, epochs[0], status, out0)
+        _cabi.check(lib.pa_splitkv_exchange_recv(ptrs.data_ptr(), 1, 2, rows, D, epochs[1].data_ptr(), out1.data_ptr(), None,
+                                                 status.data_ptr(), None), "recv")
         torch.cuda.synchronize()
         assert int(status.item()) == 0
         np.testing.assert_allclose(out0.cpu().numpy(), exp, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(out1.cpu().numpy().reshape(B, H, D), exp, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(out0.cpu().numpy().reshape(rows, D), out1.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        assert (epochs[0][:rows] == step + 1).all() and (epochs[1][:rows] == step + 1).all()
     _free_buffers(bufs)
 
 
