@@ -836,6 +836,206 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------- persistent 2-CTA kernel (more tiles than one wave)
+// One CTA pair per two SMs (74 pairs), each looping over 256 x 256 tiles; TMEM holds TWO accumulators (2 x 256 of
+// the 512 columns) so the 8 epilogue warps drain tile j while the UMMA thread already fills tile j+1, and the TMA
+// ring simply keeps running across tile boundaries.  Against one tile per CTA (two CTAs per SM, OCC = 2) this removes
+// the wave quantisation: fc1 at M = 2048 is 512 tiles = 3.46 waves of 148 resident pairs (the last wave 46 % full),
+// here 6.92 rounds of 74 pairs at full per-pair speed.  Tiles are numbered m-chunk fastest, so the pairs running at
+// the same time share B slabs (weights cross HBM once, the re-reads hit L2).
+// Barriers: full / empty per ring stage as above; tmem_full[2] (UMMA commit -> both CTAs' epilogue warps);
+// tmem_empty[2] on the LEADER (16 arrivals: 8 epilogue warps of each CTA, the peer's by remote arrive).
+// Every wait is bounded: a protocol error becomes a trap, not a hung GPU.
+__device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > (1u << 27)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS2, 1)
+gemm_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g,
+                       int n_slabs, int m_chunks, int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int NST = STAGES2;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + NST * STAGE2_BYTES;  // full[NST], empty[NST], tmem_full[2], tmem_empty[2]
+    auto full_bar = [&](int s) { return bar0 + s * 8; };
+    auto empty_bar = [&](int s) { return bar0 + (NST + s) * 8; };
+    auto tfull_bar = [&](int b) { return bar0 + (2 * NST + b) * 8; };
+    auto tempty_bar = [&](int b) { return bar0 + (2 * NST + 2 + b) * 8; };
+    const uint32_t tmem_slot = bar0 + (2 * NST + 4) * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank() & 1u;
+    const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int total_kb = (g.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(full_bar(s), 2);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 16);
+        }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB));
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN2);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    auto tile_coords = [&](int t, int& n0, int& m0, int& batch) {
+        const int per_batch = n_slabs * m_chunks;
+        batch = t / per_batch;
+        const int rem = t - batch * per_batch;
+        n0 = (rem / m_chunks) * BN2;
+        m0 = (rem % m_chunks) * 2 * BM;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int t = pid; t < total_tiles; t += npairs) {
+                int n0, m0, batch;
+                tile_coords(t, n0, m0, batch);
+                for (int i = 0; i < total_kb; ++i, ++it) {
+                    const int s = it % NST;
+                    mbar_wait_trap(empty_bar(s), ((it / NST) & 1) ^ 1);
+                    const uint32_t st = base + s * STAGE2_BYTES;
+                    const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                    if (crank == 0) mbar_arrive_expect_tx(full_bar(s), STAGE2_BYTES);
+                    else mbar_remote_arrive_expect_tx(lead_full, STAGE2_BYTES);
+                    const int k0 = i * BK;
+                    tma_load_3d_2cta(st, &tmA, k0, m0 + (int)crank * BM, batch, lead_full);
+                    tma_load_3d_2cta(st + TILE_BYTES, &tmB, n0 + (int)crank * BN, k0, batch, lead_full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (crank == 0 && elect_one()) {
+            uint32_t it = 0, j = 0;
+            for (int t = pid; t < total_tiles; t += npairs, ++j) {
+                const uint32_t buf = j & 1u;
+                mbar_wait_trap(tempty_bar(buf), ((j >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (int i = 0; i < total_kb; ++i, ++it) {
+                    const int s = it % NST;
+                    mbar_wait_trap(full_bar(s), (it / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t st = base + s * STAGE2_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UK; ++ks) {
+                        const uint64_t da = make_desc(st + ks * UK, 16, 1024);
+                        const uint64_t db = make_desc(st + TILE_BYTES + ks * UK * BK, TILE_BYTES, 1024);
+                        umma_i8_2cta(tmem_base + buf * BN2, da, db, kIdesc2, (i > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2cta(empty_bar(s), 3);
+                }
+                umma_commit_2cta(tfull_bar(buf), 3);
+            }
+        }
+    } else {
+        constexpr int ACT = EPI == 2 ? PA_ACT_RELU : (EPI == 3 ? PA_ACT_GELU : PA_ACT_NONE);
+        const int qtr = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        float* bias_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 256 - smem_u32(smem_raw))) + (warp - 2) * 128;  // past the barriers + TMEM slot
+        const uint32_t lead_tempty0 = mapa_shared(tempty_bar(0), 0);
+        uint32_t j = 0;
+        for (int t = pid; t < total_tiles; t += npairs, ++j) {
+            int n0, m0, batch;
+            tile_coords(t, n0, m0, batch);
+            const uint32_t buf = j & 1u;
+            if (EPI != 0) {
+                const int c = n0 + chalf * 128 + lane * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias && c < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+                __syncwarp();
+                *reinterpret_cast<float4*>(bias_sm + lane * 4) = bv;
+                __syncwarp();
+            }
+            const int row = m0 + (int)crank * BM + qtr * 32 + lane;
+            const bool row_ok = row < g.M;
+            const int64_t out_row = ((int64_t)batch * g.M + row) * g.N;
+            const float alpha = (g.a_qscale && row_ok) ? __fdiv_rn(g.alpha, __ldg(g.a_qscale + (int64_t)batch * g.M + row))
+                                                       : g.alpha;
+            mbar_wait_trap(tfull_bar(buf), (j >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t rr[2][32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + buf * BN2 + chalf * 128 + c2 * 64;
+                tmem_ld_32x32_nowait(taddr, rr[0]);
+                tmem_ld_32x32_nowait(taddr + 32, rr[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint32_t(&r)[32] = rr[hc];
+                    const int cc = c2 * 2 + hc;
+                    const int col0 = n0 + chalf * 128 + cc * 32;
+                    if (!row_ok || col0 >= g.N) continue;
+                    const bool hi_ok = col0 + 32 <= g.N;
+                    if (g.C32) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj += 4)
+                            if (jj < 16 || hi_ok)
+                                *reinterpret_cast<int4*>(g.C32 + out_row + col0 + jj) =
+                                    make_int4((int)r[jj], (int)r[jj + 1], (int)r[jj + 2], (int)r[jj + 3]);
+                    }
+                    if (EPI != 0 && g.Cf) {
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            if (w < 4 || hi_ok) {
+                                const float4 bj = *reinterpret_cast<const float4*>(bias_sm + cc * 32 + 4 * w);
+                                *reinterpret_cast<float4*>(g.Cf + out_row + col0 + 4 * w) =
+                                    make_float4(epilogue_f32<ACT>((int)r[4 * w + 0], alpha, bj.x),
+                                                epilogue_f32<ACT>((int)r[4 * w + 1], alpha, bj.y),
+                                                epilogue_f32<ACT>((int)r[4 * w + 2], alpha, bj.z),
+                                                epilogue_f32<ACT>((int)r[4 * w + 3], alpha, bj.w));
+                            }
+                        }
+                    } else if (EPI != 0) {
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const float4 bj = *reinterpret_cast<const float4*>(bias_sm + cc * 32 + 4 * w);
+                            packed[w] = pack_s8x4(epilogue_s8<ACT>((int)r[4 * w + 0], alpha, bj.x),
+                                                  epilogue_s8<ACT>((int)r[4 * w + 1], alpha, bj.y),
+                                                  epilogue_s8<ACT>((int)r[4 * w + 2], alpha, bj.z),
+                                                  epilogue_s8<ACT>((int)r[4 * w + 3], alpha, bj.w));
+                        }
+                        *reinterpret_cast<uint4*>(g.C8 + out_row + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (hi_ok)
+                            *reinterpret_cast<uint4*>(g.C8 + out_row + col0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+            }
+            // this warp has read its part of accumulator `buf`: tell the leader's UMMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_remote_arrive(lead_tempty0 + buf * 8);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 2 * BN2);
+    }
+}
+
 // Split-K second pass: sum the ksplit partial tiles (exact int32), then C32 copy and/or C8 epilogue.
 template <int ACT>
 __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
@@ -1028,6 +1228,38 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaError_t e;
+    const int64_t tiles2 = (int64_t)n_slabs * m_chunks * BATCH;
+    const bool persist = two_cta && !dq && ksplit == 1 && tiles2 > di.sm_count / 2 && tiles2 < (1ll << 30) &&
+                         !(getenv("PA_GEMM_PERSIST") && atoi(getenv("PA_GEMM_PERSIST")) == 0);
+    if (persist) {
+        // more tiles than one wave of CTA pairs: persistent pairs with double-buffered TMEM accumulators
+        CUtensorMap tmA2;
+        if (!make_map(&tmA2, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)BATCH, BM)) return PA_ERR_UNSUPPORTED;
+        using PKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Args, int, int, int);
+        static const PKernelFn pk[4] = {gemm_i8_persist_kernel<0>, gemm_i8_persist_kernel<1>, gemm_i8_persist_kernel<2>,
+                                        gemm_i8_persist_kernel<3>};
+        PKernelFn kern = pk[epi];
+        const size_t smemp = (size_t)STAGES2 * STAGE2_BYTES + 256 + 8 * 128 * sizeof(float) + 1024;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);
+        if (e != cudaSuccess) return (int)e;
+        const int npairs = (int)(tiles2 < di.sm_count / 2 ? tiles2 : di.sm_count / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * npairs));
+        cfg.blockDim = dim3(NTHREADS2);
+        cfg.dynamicSmemBytes = smemp;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA2, tmB, g, n_slabs, m_chunks, (int)tiles2);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaGetLastError();
+        return e == cudaSuccess ? PA_OK : (int)e;
+    }
     if (two_cta) {
         // more CTA pairs than one wave (148 SMs = 74 pairs): two CTAs per SM, see the kernel's header
         const int64_t pairs = (int64_t)n_slabs * m_chunks * ksplit * BATCH;

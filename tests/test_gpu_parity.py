@@ -845,9 +845,25 @@ GEMM_SHAPES = [
     (1, 300, 256, 512),    # M > 256: two M chunks
     (1, 64, 128, 8192),    # one slab -> split-K path
     (3, 17, 16, 16),       # minimum N, K
-    (1, 640, 8192, 512),   # 96 CTA pairs > one wave: the two-CTAs-per-SM variant (3-stage ring), ragged M chunk
-    (2, 1030, 2048, 384),  # the same variant, batched, 5 M chunks (last one 6 rows), K tail inside a block
+    (1, 640, 8192, 512),   # 96 tiles > one wave of CTA pairs: the PERSISTENT kernel (double-buffered TMEM), ragged M chunk
+    (2, 1030, 2048, 384),  # the same, batched, 5 M chunks (last one 6 rows), K tail inside a block
+    (1, 1024, 4880, 256),  # 80 tiles, N tail inside the last slab
 ]
+
+
+@pytest.mark.parametrize("shape", [(1, 640, 8192, 512), (2, 1030, 2048, 384)], ids=lambda s: "x".join(map(str, s)))
+def test_gemm_i8_one_tile_per_cta_variant_still_exact(ld, oracle, shape, monkeypatch):
+    """PA_GEMM_PERSIST=0: the two-CTAs-per-SM, one-tile-per-CTA variant (3-stage rings) the persistent kernel replaced
+    by default -- kept for A/B measurements, so kept exact."""
+    monkeypatch.setenv("PA_GEMM_PERSIST", "0")
+    BATCH, M, N, K = shape
+    rng = np.random.default_rng(sum(shape))
+    A = rng.integers(-127, 128, size=(BATCH, M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, size=(BATCH, K, N), dtype=np.int8)
+    acc = torch.empty((BATCH, M, N), dtype=torch.int32, device="cuda")
+    assert ld.dnnl_matmul_int8(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), None, BATCH, M, N, K, 1.0, 1.0, acc_out=acc)
+    np.testing.assert_array_equal(acc.cpu().numpy(), oracle.cpu.gemm_s8s8s32(A, B))
+
 
 
 @pytest.mark.parametrize("shape", GEMM_SHAPES, ids=lambda s: "x".join(map(str, s)))
