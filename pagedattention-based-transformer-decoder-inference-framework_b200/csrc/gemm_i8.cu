@@ -213,6 +213,7 @@ template <int EPI, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;");  // a split-K reduction launched behind this grid may become resident
     // 1024-byte alignment for the 128B-swizzled tiles.
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + RING_BYTES;  // full[MAXST], empty[MAXST], tmem_full
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(NTHREADS2, OCC)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int NST = OCC == 2 ? 3 : STAGES2;
+    asm volatile("griddepcontrol.launch_dependents;");  // a split-K reduction launched behind this grid may become resident
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + NST * STAGE2_BYTES;  // full[S], empty[S], tmem_full
     const uint32_t tmem_slot = bar0 + (2 * NST + 1) * 8;
@@ -1039,6 +1041,9 @@ gemm_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // Split-K second pass: sum the ksplit partial tiles (exact int32), then C32 copy and/or C8 epilogue.
 template <int ACT>
 __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
+    // launched with programmatic stream serialisation behind the GEMM: resident early, blocks here until the partial
+    // tiles are complete and visible (a no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t n4 = rows * g.N / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         int4 a = __ldcs(reinterpret_cast<const int4*>(g.acc_ws) + i);
@@ -1345,10 +1350,18 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         const int64_t n4 = rows * N / 4;
         int blocks = (int)((n4 + 255) / 256);
         if (blocks > di.sm_count * 8) blocks = di.sm_count * 8;
-        if (act == PA_ACT_RELU) gemm_i8_splitk_epilogue_kernel<PA_ACT_RELU><<<blocks, 256, 0, st>>>(g, rows);
-        else if (act == PA_ACT_GELU) gemm_i8_splitk_epilogue_kernel<PA_ACT_GELU><<<blocks, 256, 0, st>>>(g, rows);
-        else gemm_i8_splitk_epilogue_kernel<PA_ACT_NONE><<<blocks, 256, 0, st>>>(g, rows);
-        e = cudaGetLastError();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)blocks);
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see the kernel: it waits for the GEMM itself
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (act == PA_ACT_RELU) e = cudaLaunchKernelEx(&cfg, gemm_i8_splitk_epilogue_kernel<PA_ACT_RELU>, g, rows);
+        else if (act == PA_ACT_GELU) e = cudaLaunchKernelEx(&cfg, gemm_i8_splitk_epilogue_kernel<PA_ACT_GELU>, g, rows);
+        else e = cudaLaunchKernelEx(&cfg, gemm_i8_splitk_epilogue_kernel<PA_ACT_NONE>, g, rows);
         if (e != cudaSuccess) return (int)e;
     }
     return PA_OK;
