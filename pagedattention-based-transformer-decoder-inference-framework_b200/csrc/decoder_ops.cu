@@ -8,6 +8,8 @@
 //   decoder/layer_norm.hpp:20-37        -> layer_norm_kernel
 //   decoder/mlp.hpp:23-41 (float)       -> linear_kn_kernel (W [K,N] row-major, j*N+i)
 //   decoder/cuda_decoder.cu:7-14, decoder/int8_decoder.cpp:97-104 -> argmax_kernel
+#include <cstdlib>
+
 #include "pa_common.cuh"
 
 namespace pa {
@@ -401,14 +403,132 @@ PA_API int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float
     PA_RETURN_LAUNCH_STATUS();
 }
 
+// ---- linear for MANY rows (batched decode / prefill): register-tiled fp32 GEMM -----------------------------------
+// The strip kernel above re-streams the weights once per 16 rows and spends one shared-memory read per four FMAs
+// (measured ~17 TFLOP/s: two thirds of a CUDADecoder step at the C2 shape).  Here a CTA of 256 threads owns a 64-row x
+// 128-column tile: thread (warp w, lane l) keeps an 8 x 4 accumulator block (rows 8w..8w+7, columns 4l..4l+3), the K
+// loop stages W [32][128] and x [64][32] tiles with cp.async (3 stages, 16-byte copies; the W rows are whole 512-byte
+// runs of the reference's [K, N] layout) and per 4 k-steps issues 4 + 8 LDS.128 for 128 FMAs, so the FMA pipe, not
+// shared memory, bounds it.  fp32 throughout (the reference's CUDADecoder<float> arithmetic; only the summation order
+// differs).  Needs N % 4 == 0 and K % 4 == 0 (16-byte alignment of the rows); other shapes keep the strip kernel.
+constexpr int kGemmBM = 64, kGemmBN = 128, kGemmKT = 32, kGemmStages = 3;
+constexpr int kGemmXStride = kGemmKT + 4;  // floats; keeps every x row 16-byte aligned, staggers banks for the copies
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(256) linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, int rows, int K, int N, int act,
+                                                          int kslice, float* __restrict__ out, float* __restrict__ partial) {
+    extern __shared__ __align__(16) float gsm[];
+    float* ws = gsm;                                             // [stages][KT][BN]
+    float* xs = gsm + kGemmStages * kGemmKT * kGemmBN;           // [stages][BM][XStride]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kGemmBN, r0 = blockIdx.y * kGemmBM;
+    const int k0 = blockIdx.z * kslice, k1 = min(K, k0 + kslice);
+    const int ntiles = (k1 - k0 + kGemmKT - 1) / kGemmKT;
+
+    auto load_tile = [&](int t, int st) {
+        const int kt = k0 + t * kGemmKT;
+        // W tile: 32 rows x 128 floats = 1024 16-byte pieces, 4 per thread
+        float* wd = ws + st * kGemmKT * kGemmBN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = threadIdx.x + i * 256;
+            const int kr = p >> 5, c4 = (p & 31) * 4;
+            const bool ok = (kt + kr < k1) && (n0 + c4 < N);
+            cp_async16(smem_u32(wd + kr * kGemmBN + c4), W + (int64_t)(ok ? kt + kr : 0) * N + (ok ? n0 + c4 : 0), ok);
+        }
+        // x tile: 64 rows x 32 floats = 512 pieces, 2 per thread
+        float* xd = xs + st * kGemmBM * kGemmXStride;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int p = threadIdx.x + i * 256;
+            const int r = p >> 3, c4 = (p & 7) * 4;
+            const bool ok = (r0 + r < rows) && (kt + c4 < k1);
+            cp_async16(smem_u32(xd + r * kGemmXStride + c4), x + (int64_t)(ok ? r0 + r : 0) * K + (ok ? kt + c4 : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+
+    for (int s = 0; s < kGemmStages - 1; ++s) {
+        if (s < ntiles) load_tile(s, s);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kGemmStages - 2) : "memory");
+        __syncthreads();  // tile t has landed for everyone; tile t-1's buffer is free
+        if (t + kGemmStages - 1 < ntiles) load_tile(t + kGemmStages - 1, (t + kGemmStages - 1) % kGemmStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const float* wt = ws + (t % kGemmStages) * kGemmKT * kGemmBN + lane * 4;
+        const float* xt = xs + (t % kGemmStages) * kGemmBM * kGemmXStride + warp * 8 * kGemmXStride;
+#pragma unroll
+        for (int kk = 0; kk < kGemmKT; kk += 4) {
+            float4 wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(wt + (kk + j) * kGemmBN);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(xt + r * kGemmXStride + kk);  // broadcast
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[r][0] = fmaf(xa[j], wv[j].x, acc[r][0]);
+                    acc[r][1] = fmaf(xa[j], wv[j].y, acc[r][1]);
+                    acc[r][2] = fmaf(xa[j], wv[j].z, acc[r][2]);
+                    acc[r][3] = fmaf(xa[j], wv[j].w, acc[r][3]);
+                }
+            }
+        }
+    }
+    const int n = n0 + lane * 4;
+    if (n >= N) return;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!partial && bias) b4 = *reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = r0 + warp * 8 + r;
+        if (row >= rows) continue;
+        float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (partial) {
+            *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.z * rows + row) * N + n) = v;
+        } else {
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (act == PA_ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(out + (int64_t)row * N + n) = v;
+        }
+    }
+}
+
 // K-slice geometry of pa_linear_f32 (shared with pa_linear_workspace_bytes).
-static int linear_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
-    const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
-    // slice K until ~2 CTAs per SM stream the weights; every slice keeps >= 64 k-rows (8 per warp)
-    int nslices = (2 * sm_count + strips * chunks - 1) / (strips * chunks);
-    if (nslices > K / 64) nslices = K / 64;
+static bool linear_uses_gemm(const void* x, const void* W, const void* out, const void* bias, int rows, int K, int N) {
+    // the register-tiled kernel needs 16-byte aligned rows; few rows stay on the strip kernel (weights streamed once
+    // either way, and its K slicing covers the chip better for tiny problems)
+    if (getenv("PA_LINEAR_GEMM") && atoi(getenv("PA_LINEAR_GEMM")) == 0) return false;
+    return rows >= 16 && N % 4 == 0 && K % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)W % 16 == 0 &&
+           (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
+}
+
+static int linear_slices(int rows, int K, int N, int sm_count, int* kslice_out, bool gemm) {
+    const int strips = gemm ? (N + kGemmBN - 1) / kGemmBN : (N + 31) / 32;
+    const int chunks = gemm ? (rows + kGemmBM - 1) / kGemmBM : (rows + kLinRows - 1) / kLinRows;
+    // slice K until ~2 CTAs (strip kernel) / ~1 CTA (tile kernel) per SM stream the weights; every slice keeps
+    // >= 64 k-rows (8 per warp) / >= 128 (4 K tiles)
+    const int want = gemm ? sm_count : 2 * sm_count;
+    int nslices = (want + strips * chunks - 1) / (strips * chunks);
+    const int min_k = gemm ? 128 : 64;
+    if (nslices > K / min_k) nslices = K / min_k;
     if (nslices < 1) nslices = 1;
-    const int kslice = (K + nslices - 1) / nslices;
+    int kslice = (K + nslices - 1) / nslices;
+    if (gemm) kslice = (kslice + kGemmKT - 1) / kGemmKT * kGemmKT;  // whole K tiles per slice (16-byte aligned starts)
     if (kslice_out) *kslice_out = kslice;
     return (K + kslice - 1) / kslice;
 }
@@ -416,7 +536,11 @@ static int linear_slices(int rows, int K, int N, int sm_count, int* kslice_out) 
 PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
     if (rows <= 0 || K <= 0 || N <= 0) return 0;
     const DeviceInfo& di = device_info();
-    const int nslices = linear_slices(rows, K, N, di.ok ? di.sm_count : 148, nullptr);
+    const int sm = di.ok ? di.sm_count : 148;
+    // either kernel may run (the choice also depends on pointer alignment): size for the larger need
+    const int a = linear_slices(rows, K, N, sm, nullptr, false);
+    const int b = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? linear_slices(rows, K, N, sm, nullptr, true) : 1;
+    const int nslices = a > b ? a : b;
     return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
 }
 
@@ -430,21 +554,37 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     if (rows == 0) return PA_OK;
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
-    const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
+    const bool gemm = linear_uses_gemm(d_x, d_W, d_out, d_bias, rows, K, N);
     int kslice = K;
-    int nslices = linear_slices(rows, K, N, di.sm_count, &kslice);
+    int nslices = linear_slices(rows, K, N, di.sm_count, &kslice, gemm);
     float* partial = nullptr;
     if (nslices > 1) {
-        if (d_workspace && workspace_bytes >= (size_t)nslices * rows * N * sizeof(float)) {
+        if (d_workspace && workspace_bytes >= (size_t)nslices * rows * N * sizeof(float) && (uintptr_t)d_workspace % 16 == 0) {
             partial = static_cast<float*>(d_workspace);
         } else {
             nslices = 1;
             kslice = K;
         }
     }
-    dim3 grid((unsigned)strips, (unsigned)chunks, (unsigned)nslices);
-    linear_kn_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, kslice, d_out, partial);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (gemm) {
+        const size_t smem = (size_t)kGemmStages * (kGemmKT * kGemmBN + kGemmBM * kGemmXStride) * sizeof(float);
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            e = cudaFuncSetAttribute(linear_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[dev & 63] = true;
+        }
+        dim3 grid((unsigned)((N + kGemmBN - 1) / kGemmBN), (unsigned)((rows + kGemmBM - 1) / kGemmBM), (unsigned)nslices);
+        linear_gemm_kernel<<<grid, 256, smem, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, kslice, d_out, partial);
+    } else {
+        const int strips = (N + 31) / 32, chunks = (rows + kLinRows - 1) / kLinRows;
+        dim3 grid((unsigned)strips, (unsigned)chunks, (unsigned)nslices);
+        linear_kn_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_W, d_bias, rows, K, N, act, kslice, d_out, partial);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (nslices > 1) {
         const int64_t n = (int64_t)rows * N;

@@ -593,3 +593,36 @@ def test_int8_decoder_with_attention_projections(oracle, tmp_path):
             Ly[n + "_deq"] = float(deq(r(f"attn_{n}.bin")))
         wq["layers"].append(Ly)
     check_teacher_forced(out, 3, RefDecoder(wq, H, D, int8=True), 1.0, 0, None, 5e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 4096, 1024), (100, 192, 100), (16, 256, 128), (300, 520, 388), (65, 36, 12)])
+def test_linear_register_tiled_gemm_matches_fp64(shape, monkeypatch):
+    """pa_linear_f32 with >= 16 rows and 16-byte aligned rows runs the register-tiled fp32 GEMM (cp.async tiles, 8 x 4
+    accumulators per thread): against a float64 product, K-sliced and unsliced, with bias / relu, ragged M / N / K tiles;
+    and it equals the strip kernel (PA_LINEAR_GEMM=0) to fp32 summation-order noise."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    rows, K, N = shape
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal((rows, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dx, dW, db = (torch.from_numpy(a).cuda() for a in (x, W, b))
+    exp = x.astype(np.float64) @ W.astype(np.float64) + b
+    need = lib.pa_linear_workspace_bytes(rows, K, N)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    outs = {}
+    for mode in ("gemm", "gemm-nows", "strip"):
+        monkeypatch.setenv("PA_LINEAR_GEMM", "0" if mode == "strip" else "1")
+        for act in (0, 1):
+            o = torch.full((rows, N), float("nan"), device="cuda")
+            wp, wb = (None, 0) if mode == "gemm-nows" else (ws.data_ptr(), need)
+            _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), db.data_ptr(), rows, K, N, act, o.data_ptr(), wp, wb, None))
+            e = np.maximum(exp, 0) if act else exp
+            np.testing.assert_allclose(o.cpu().numpy(), e, rtol=1e-4, atol=2e-4)
+            outs[(mode, act)] = o.cpu().numpy()
+    np.testing.assert_allclose(outs[("gemm", 0)], outs[("strip", 0)], rtol=1e-5, atol=1e-5)
+    o = torch.empty((rows, N), device="cuda")
+    _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), None, rows, K, N, 0, o.data_ptr(), ws.data_ptr(), need, None))
+    np.testing.assert_allclose(o.cpu().numpy(), exp - b, rtol=1e-4, atol=2e-4)
