@@ -512,7 +512,13 @@ __global__ void __launch_bounds__(256) linear_gemm_kernel(const float* __restric
 static bool linear_uses_gemm(const void* x, const void* W, const void* out, const void* bias, int rows, int K, int N) {
     // the register-tiled kernel needs 16-byte aligned rows; few rows stay on the strip kernel (weights streamed once
     // either way, and its K slicing covers the chip better for tiny problems)
-    if (getenv("PA_LINEAR_GEMM") && atoi(getenv("PA_LINEAR_GEMM")) == 0) return false;
+    if (const char* env = getenv("PA_LINEAR_GEMM")) {
+        if (atoi(env) == 0) return false;
+    } else if ((int64_t)rows * K * N < 500000000ll) {
+        // small layers (GPT-2-small MLP at batch 64: 0.15 GMAC, weights L2-resident): too few 128-column tiles to fill
+        // the chip without heavy K slicing; the strip kernel measured 14 % faster there
+        return false;
+    }
     return rows >= 16 && N % 4 == 0 && K % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)W % 16 == 0 &&
            (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
 }
@@ -539,7 +545,7 @@ PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
     const int sm = di.ok ? di.sm_count : 148;
     // either kernel may run (the choice also depends on pointer alignment): size for the larger need
     const int a = linear_slices(rows, K, N, sm, nullptr, false);
-    const int b = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? linear_slices(rows, K, N, sm, nullptr, true) : 1;
+    const int b = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? linear_slices(rows, K, N, sm, nullptr, true) : 1;  // (env may force it)
     const int nslices = a > b ? a : b;
     return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
 }
