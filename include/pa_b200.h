@@ -227,6 +227,16 @@ int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void* d_k_po
                               int beam_width, float* d_lse_out, void* d_workspace,
                               size_t workspace_bytes, pa_stream_t stream);
 
+/* Beam groups over INT8 pages: the per-row streaming kernel through the beam_ids indirection (the tensor-core group
+ * kernel is fp16-only).  Same results as pa_paged_decode_i8_overlap; shared-prefix pages are served from L2 after
+ * their first read (evict_first is off when d_beam_ids is given), so HBM sees roughly the unique bytes. */
+int pa_paged_decode_i8_group(const float* d_q, float* d_out, const int8_t* d_k_pool, const int8_t* d_v_pool,
+                             const float* d_k_scales, const float* d_v_scales, const int32_t* d_table,
+                             int num_beams, int num_heads, int num_tiles, int total_pages,
+                             const int32_t* d_beam_ids, const int32_t* d_ctx_lens, int B, int T, int head_dim,
+                             int tile_size, float temperature, const float* d_rope, int beam_width,
+                             float* d_lse_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+
 /* Split-KV across GPUs (north-star long-context mode): same computation over
  * this rank's pages only, emitting UN-normalised partials for an LSE combine:
  *   d_part_m[b,h] = max_t s[t] (natural-log units; -inf if no key)

@@ -1849,6 +1849,21 @@ PA_API int pa_paged_decode_f16_group(const float* d_q, float* d_out, const void*
     return launch_group(a, beam_width, d_workspace, workspace_bytes, as_stream(stream));
 }
 
+// int8 pages for beam groups.  The tensor-core group kernel stages fp16 boxes for ldmatrix; int8 pages take the
+// per-row streaming kernel through the beam_ids indirection instead: same results, and the shared-prefix pages of a
+// group are served from L2 after their first read (L2::evict_first is off whenever beam_ids are given; sibling beams
+// are adjacent rows, i.e. adjacent chunk ids, so they stream the same pages at about the same time) -- HBM sees the
+// unique bytes roughly once, the SMs ingest the logical bytes.  beam_width only validates the grouping.
+PA_API int pa_paged_decode_i8_group(const float* d_q, float* d_out, const int8_t* d_k_pool, const int8_t* d_v_pool,
+                                    const float* d_k_scales, const float* d_v_scales, PA_DECODE_COMMON_PARAMS,
+                                    int beam_width, float* d_lse_out, void* d_workspace, size_t workspace_bytes,
+                                    pa_stream_t stream) {
+    PA_CHECK_ARG(beam_width >= 1 && B >= 0);
+    if (B % beam_width != 0) return PA_ERR_INVALID_ARG;
+    return decode_entry(1, true, d_q, d_out, nullptr, nullptr, nullptr, d_k_pool, d_v_pool, d_k_scales, d_v_scales,
+                        PA_DECODE_COMMON_ARGS, d_lse_out, d_workspace, workspace_bytes, stream);
+}
+
 PA_API int pa_lse_combine(const float* d_part_m, const float* d_part_l, const float* d_part_o,
                           int n_parts, int rows, int head_dim, float* d_out, float* d_lse_out,
                           pa_stream_t stream) {

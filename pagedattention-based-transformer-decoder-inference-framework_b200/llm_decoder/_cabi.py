@@ -46,6 +46,7 @@ _SIGS = {
     "pa_paged_decode_f16_splitkv": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_paged_decode_i8_splitkv": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_vp, _vp, _sz, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_paged_decode_f16_group": ([_vp, _vp, _vp, _vp] + _DECODE_COMMON + [_i32, _vp, _vp, _sz, _vp], _i32),
+    "pa_paged_decode_i8_group": ([_vp, _vp, _vp, _vp, _vp, _vp] + _DECODE_COMMON + [_i32, _vp, _vp, _sz, _vp], _i32),
     "pa_softmax_lut_i32": ([_vp, _i32, _i32, _f32, _vp, _i32, _vp, _vp], _i32),
     "pa_softmax_temperature": ([_vp, _i32, _i32, _f32, _vp, _vp], _i32),
     "pa_topk_topp_filter": ([_vp, _i32, _i32, _i32, _f32, _i32, _f32, _vp], _i32),

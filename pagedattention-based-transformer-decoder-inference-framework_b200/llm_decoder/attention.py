@@ -366,8 +366,19 @@ def paged_decode_group(q, out, kv_cache, B, T, beam_width, temperature=1.0, beam
     pages with equal ids within a group are read once.  q/out [B, H, D] f32 CUDA tensors."""
     pt = kv_cache.page_table_
     H, D = pt.num_heads_, kv_cache.head_dim_
+    if kv_cache.dtype == "i8":  # per-row streaming kernel through the beam indirection; shared pages served from L2
+        ws = kv_cache.workspace(B)
+        with torch.cuda.device(kv_cache.key_buffer_.device):
+            st = _cabi.lib().pa_paged_decode_i8_group(
+                q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(), kv_cache.value_buffer_.data_ptr(),
+                kv_cache.k_scales_.data_ptr(), kv_cache.v_scales_.data_ptr(), pt.device_data().data_ptr(), pt.num_beams_, H,
+                pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids), _cabi.ptr(ctx_lens), B, T, D, kv_cache.tile_size_,
+                float(temperature), _cabi.ptr(rotary_emb), int(beam_width), _cabi.ptr(lse_out), ws.data_ptr(), ws.numel(),
+                _cabi.stream())
+        _cabi.check(st, "pa_paged_decode_i8_group")
+        return out
     if kv_cache.dtype != "f16":
-        raise NotImplementedError("paged_decode_group: fp16 KV pages only")
+        raise NotImplementedError("paged_decode_group: fp16 or int8 KV pages")
     ws = kv_cache.workspace(B)
     with torch.cuda.device(kv_cache.key_buffer_.device):
         st = _cabi.lib().pa_paged_decode_f16_group(

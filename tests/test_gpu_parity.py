@@ -617,6 +617,22 @@ def test_group_decode_matches_oracle(ld, oracle, ci):
                 assert abs(lse.cpu().numpy()[b, h] - r) <= 1e-3 * max(1.0, abs(r))
 
 
+@pytest.mark.parametrize("ci", [0, 1, 4, 6])
+def test_group_decode_int8_pages_matches_oracle(ld, oracle, ci):
+    """pa_paged_decode_i8_group: beam groups over INT8 pages (shared-prefix pages, copy-on-write tails, unmapped pages)
+    through the streaming kernel + beam indirection -- results against the oracle fed the same int8 pages."""
+    cfg = dict(GROUP_CASES[ci])
+    case = make_case(seed=40 + ci, kv="i8", **cfg)
+    kvc = to_device_cache(case)
+    B, H, D = case["q"].shape
+    q = torch.from_numpy(case["q"]).cuda()
+    out = torch.full((B, H, D), float("nan"), device="cuda")
+    bid = torch.from_numpy(case["beam_ids"]).cuda()
+    ld.paged_decode_group(q, out, kvc, B, case["T"], cfg["beam_width"], case["temperature"], beam_ids=bid)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), oracle_attention(case), rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("W", [1, 2, 4])
 def test_group_decode_per_row_context(ld, oracle, W):
     """Ragged mode of the group kernel: every row has its own context length (random, including 0 and
