@@ -430,6 +430,23 @@ int pa_paged_prefill_i8(const float* d_q, float* d_out, const int8_t* d_k_pool, 
                         int head_dim, int tile_size, float temperature, void* d_workspace,
                         size_t workspace_bytes, pa_stream_t stream);
 
+/* Token-major prefill: d_q, d_out are [B, Tq, num_heads, head_dim] f32 -- the layout the decoders' QKV
+ * projection leaves the activations in (CUDADecoder.py:75-80 reshapes [B, n, hidden] into heads), so the
+ * caller needs no permute + copy either side of the attention.  The strides are folded into the tcgen05
+ * kernel's Q loads and O stores; everything else as pa_paged_prefill_f16/_i8.  No workspace.  Returns
+ * PA_ERR_UNSUPPORTED where that kernel does not apply (head_dim other than 64 / 128, pages that are not
+ * 16 << k tokens, pools not 128-byte aligned, d_q == d_out): permute and call the [B, H, Tq, D] entry then. */
+int pa_paged_prefill_f16_tokmajor(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                                  const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                                  int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_start,
+                                  int B, int Tq, int head_dim, int tile_size, float temperature,
+                                  pa_stream_t stream);
+int pa_paged_prefill_i8_tokmajor(const float* d_q, float* d_out, const int8_t* d_k_pool, const int8_t* d_v_pool,
+                                 const float* d_k_scales, const float* d_v_scales, const int32_t* d_table,
+                                 int num_beams, int num_heads, int num_tiles, int total_pages,
+                                 const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq,
+                                 int head_dim, int tile_size, float temperature, pa_stream_t stream);
+
 /* --------------------------------- inter-GPU split-KV exchange over peer memory */
 /* Exchange buffers: one per rank, pa_splitkv_exchange_bytes(world, rows, head_dim) bytes
  * (uint4 [2 parity][world][rows][head_dim/2 + 1] flag-in-data packets, csrc/xchg.cuh).

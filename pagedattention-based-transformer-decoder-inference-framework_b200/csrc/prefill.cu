@@ -420,7 +420,8 @@ using namespace pa;
 int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                          const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
-                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st);
+                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, int token_major,
+                         cudaStream_t st);
 
 PA_API size_t pa_prefill_workspace_bytes(int B, int Tq, int num_heads, int head_dim, int num_tiles, int tile_size) {
     if (B < 0 || Tq <= 0 || num_heads <= 0 || head_dim <= 0 || num_tiles <= 0 || tile_size <= 0) return 0;
@@ -435,7 +436,7 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
                          const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
                          const int32_t* d_ctx_start, int B, int Tq, int head_dim, int tile_size, float temperature,
-                         void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
+                         void* d_workspace, size_t workspace_bytes, pa_stream_t stream, int token_major = 0) {
     PA_CHECK_ARG(d_q && d_out && d_k_pool && d_v_pool && d_table);
     PA_CHECK_ARG(B >= 0 && Tq > 0 && num_heads > 0 && head_dim > 0 && head_dim % 4 == 0);
     PA_CHECK_ARG(num_beams > 0 && num_tiles > 0 && total_pages > 0 && tile_size > 0 && temperature != 0.f);
@@ -447,9 +448,10 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
         if (!(getenv("PA_PREFILL_TC") && atoi(getenv("PA_PREFILL_TC")) == 0)) {
             const int stc = pa_prefill_tc_launch(kv, head_dim, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table,
                                                  num_beams, num_heads, num_tiles, total_pages, d_beam_ids, d_ctx_start, B,
-                                                 Tq, tile_size, temperature, as_stream(stream));
+                                                 Tq, tile_size, temperature, token_major, as_stream(stream));
             if (stc != PA_ERR_UNSUPPORTED) return stc;
         }
+        if (token_major) return PA_ERR_UNSUPPORTED;  // only the tcgen05 kernel reads strided rows
         // mma.sync flash-attention kernel (head_dim 128), straight on the [B, H, Tq, D] layout (no workspace)
         CUtensorMap tmK, tmV;
         const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
@@ -479,6 +481,7 @@ static int prefill_entry(int kv, const float* d_q, float* d_out, const void* d_k
             PA_RETURN_LAUNCH_STATUS();
         }
     }
+    if (token_major) return PA_ERR_UNSUPPORTED;
     PA_CHECK_ARG(d_workspace);
     const int64_t R64 = (int64_t)B * Tq;
     PA_CHECK_ARG(R64 <= 0x7fffffff);
@@ -543,4 +546,28 @@ PA_API int pa_paged_prefill_i8(const float* d_q, float* d_out, const int8_t* d_k
     return prefill_entry(1, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table, num_beams, num_heads,
                          num_tiles, total_pages, d_beam_ids, d_ctx_start, B, Tq, head_dim, tile_size, temperature,
                          d_workspace, workspace_bytes, stream);
+}
+
+// Token-major variants: q/out are [B, Tq, H, D] (the decoders' activation layout after the QKV projection, so no
+// permute + copy either side of the attention).  Served by the tcgen05 kernel only; PA_ERR_UNSUPPORTED where
+// that kernel does not apply (head_dim other than 64/128, pages that are not 16 << k tokens, misaligned pools) --
+// the caller then permutes and takes pa_paged_prefill_f16/_i8.
+PA_API int pa_paged_prefill_f16_tokmajor(const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
+                                         const int32_t* d_table, int num_beams, int num_heads, int num_tiles,
+                                         int total_pages, const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B,
+                                         int Tq, int head_dim, int tile_size, float temperature, pa_stream_t stream) {
+    return prefill_entry(0, d_q, d_out, d_k_pool, d_v_pool, nullptr, nullptr, d_table, num_beams, num_heads, num_tiles,
+                         total_pages, d_beam_ids, d_ctx_start, B, Tq, head_dim, tile_size, temperature, nullptr, 0,
+                         stream, 1);
+}
+
+PA_API int pa_paged_prefill_i8_tokmajor(const float* d_q, float* d_out, const int8_t* d_k_pool, const int8_t* d_v_pool,
+                                        const float* d_k_scales, const float* d_v_scales, const int32_t* d_table,
+                                        int num_beams, int num_heads, int num_tiles, int total_pages,
+                                        const int32_t* d_beam_ids, const int32_t* d_ctx_start, int B, int Tq,
+                                        int head_dim, int tile_size, float temperature, pa_stream_t stream) {
+    PA_CHECK_ARG(d_k_scales && d_v_scales);
+    return prefill_entry(1, d_q, d_out, d_k_pool, d_v_pool, d_k_scales, d_v_scales, d_table, num_beams, num_heads,
+                         num_tiles, total_pages, d_beam_ids, d_ctx_start, B, Tq, head_dim, tile_size, temperature,
+                         nullptr, 0, stream, 1);
 }

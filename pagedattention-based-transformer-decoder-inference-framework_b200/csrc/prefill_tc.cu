@@ -74,6 +74,9 @@ struct Args {
     int stagger;       // UMMA issue order, see the UMMA warp
     int upt_shift;     // log2(16-token units per page)
     int total_tokens;  // rows of the pool tensor map: a box at this row is all zeros (out-of-bounds fill)
+    // element strides of q and out (same layout for both): batch, head, query position.  [B, H, Tq, D] is
+    // (H*Tq*D, Tq*D, D); the decoders' token-major activations [B, Tq, H, D] are (Tq*H*D, D, H*D).
+    int64_t sb, sh, st;
 };
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -667,7 +670,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
         if (nt > 0) {
             // Q rows of this warp -> fp16, pre-scaled, into the swizzled K-major A tile.  One row per step, the
             // whole warp on its 512 bytes (coalesced); 16 rows in flight.
-            const float* qbase = a.q + (((int64_t)b * a.H + h) * a.Tq) * D;
+            const float* qbase = a.q + (int64_t)b * a.sb + (int64_t)h * a.sh;
             const uint32_t qx = q_sm + x * Q_BYTES;
             constexpr int LPR = D / 4;    // lanes per row (one float4 each); 128 / D rows per load instruction
             constexpr int RPI = 32 / LPR;
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int tr = q0 + qtr * 32 + r0 + j * RPI + rsub;
-                    v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * D) + lr)
+                    v[j] = tr < a.Tq ? __ldg(reinterpret_cast<const float4*>(qbase + (int64_t)tr * a.st) + lr)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
             // warp's quarter of its tile's Q buffer, idle since the tile's last S MMA (which completed before
             // the P.V just waited for); 32 rows x 128 B per round, 16-byte chunks XOR-swizzled by row.
             const uint32_t ebuf = q_sm + x * Q_BYTES + qtr * (Q_BYTES / 4);
-            float* out_tile = a.out + (((int64_t)b * a.H + h) * a.Tq + q0 + qtr * 32) * D;
+            float* out_tile = a.out + (int64_t)b * a.sb + (int64_t)h * a.sh + (int64_t)(q0 + qtr * 32) * a.st;
             const int rows_ok = a.Tq - (q0 + qtr * 32);  // rows of this warp inside the prompt chunk
 #pragma unroll 1
             for (int c4 = 0; c4 < D / 32; ++c4) {
@@ -875,13 +878,13 @@ __global__ void __launch_bounds__(threads_for(KV, NQ, MW), (NQ == 1 && KV == 0) 
                 for (int it = 0; it < 8; ++it) {
                     const int r = it * 4 + (lane >> 3), j = lane & 7;
                     const uint4 v = lds_128(ebuf + r * 128 + ((j ^ (r & 7)) << 4));
-                    if (r < rows_ok) *reinterpret_cast<uint4*>(out_tile + (int64_t)r * D + c4 * 32 + j * 4) = v;
+                    if (r < rows_ok) *reinterpret_cast<uint4*>(out_tile + (int64_t)r * a.st + c4 * 32 + j * 4) = v;
                 }
                 __syncwarp();
             }
         } else if (t_ok) {
             // no visible key at all (zero-capacity table): the reference's 0 / (0 + eps) = 0
-            float* orow = a.out + (((int64_t)b * a.H + h) * a.Tq + t) * D;
+            float* orow = a.out + (int64_t)b * a.sb + (int64_t)h * a.sh + (int64_t)t * a.st;
             for (int j = 0; j < D; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         PROBE_CTA(6);
@@ -914,7 +917,8 @@ extern "C" __attribute__((visibility("default"))) int pa_debug_ptc_probe_cta(lon
 int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, const void* d_k_pool, const void* d_v_pool,
                          const float* d_k_scales, const float* d_v_scales, const int32_t* d_table, int num_beams,
                          int num_heads, int num_tiles, int total_pages, const int32_t* d_beam_ids,
-                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, cudaStream_t st) {
+                         const int32_t* d_ctx_start, int B, int Tq, int tile_size, float temperature, int token_major,
+                         cudaStream_t st) {
     using namespace pa::ptc;
     CUtensorMap tmK, tmV;
     const uint64_t total_tokens = (uint64_t)total_pages * tile_size;
@@ -934,7 +938,10 @@ int pa_prefill_tc_launch(int kv, int head_dim, const float* d_q, float* d_out, c
     Args a{d_q, d_out, d_table, d_beam_ids, d_ctx_start, num_beams, num_heads, num_tiles, total_pages, B, Tq, tile_size,
            1.4426950408889634f / temperature, static_cast<const int8_t*>(d_k_pool), static_cast<const int8_t*>(d_v_pool),
            d_k_scales, d_v_scales, (getenv("PA_PTC_STAGGER") && atoi(getenv("PA_PTC_STAGGER")) == 0) ? 0 : 1, upt_shift,
-           (int)total_tokens};
+           (int)total_tokens,
+           token_major ? (int64_t)Tq * num_heads * head_dim : (int64_t)num_heads * Tq * head_dim,
+           token_major ? (int64_t)head_dim : (int64_t)Tq * head_dim,
+           token_major ? (int64_t)num_heads * head_dim : (int64_t)head_dim};
     // NQ = 2 (256 queries per CTA share every staged K/V byte) unless that leaves SMs without a CTA: small
     // prompts then take NQ = 1 (twice the CTAs).  PA_PREFILL_NQ forces either.
     int dev = 0;

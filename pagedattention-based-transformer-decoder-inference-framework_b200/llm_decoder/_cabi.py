@@ -11,6 +11,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "libpa_b200.so")
 
 PA_OK = 0
+PA_ERR_UNSUPPORTED = -2
 ACT = {"": 0, None: 0, "none": 0, "relu": 1, "gelu": 2}
 
 _lib = None
@@ -54,6 +55,8 @@ _SIGS = {
     "pa_prefill_workspace_bytes": ([_i32, _i32, _i32, _i32, _i32, _i32], _sz),
     "pa_paged_prefill_f16": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp], _i32),
     "pa_paged_prefill_i8": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp], _i32),
+    "pa_paged_prefill_f16_tokmajor": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp], _i32),
+    "pa_paged_prefill_i8_tokmajor": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp], _i32),
     "pa_lse_combine": ([_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pa_quantize_i8": ([_vp, _i64, _f32, _vp, _vp], _i32),
     "pa_batch_quantize_i8": ([_vp, _vp, _i32, _i32, _vp, _vp], _i32),

@@ -291,14 +291,34 @@ def apply_rotary_embedding(q, k, rotary_emb, positions):
     return q, k
 
 
-def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_start=None):
+def paged_prefill(q, out, kv_cache, B, Tq, temperature=1.0, beam_ids=None, ctx_start=None, token_major=False):
     """Causal multi-query attention of Tq new tokens per row over the paged cache
     (pa_paged_prefill_f16/_i8).  q/out: [B, H, Tq, D] f32 CUDA tensors (the reference's prefill layout,
-    attention_config.hpp:8-9); ctx_start: [B] int32 device tensor of tokens cached before this chunk."""
+    attention_config.hpp:8-9); ctx_start: [B] int32 device tensor of tokens cached before this chunk.
+    token_major=True: q/out are [B, Tq, H, D] (the decoders' activation layout) and the strides are folded
+    into the tcgen05 kernel (pa_paged_prefill_*_tokmajor); returns None instead of out where that kernel does
+    not apply, and the caller permutes."""
     pt = kv_cache.page_table_
     H, D = pt.num_heads_, kv_cache.head_dim_
     assert q.is_contiguous() and out.is_contiguous() and q.numel() == B * H * Tq * D == out.numel()
     lib = _cabi.lib()
+    if token_major:
+        common = (pt.device_data().data_ptr(), pt.num_beams_, H, pt.num_tiles_, kv_cache.total_pages_, _cabi.ptr(beam_ids),
+                  _cabi.ptr(ctx_start), B, Tq, D, kv_cache.tile_size_, float(temperature))
+        with torch.cuda.device(kv_cache.key_buffer_.device):
+            if kv_cache.dtype == "f16":
+                st = lib.pa_paged_prefill_f16_tokmajor(q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                                                       kv_cache.value_buffer_.data_ptr(), *common, _cabi.stream())
+            elif kv_cache.dtype == "i8":
+                st = lib.pa_paged_prefill_i8_tokmajor(q.data_ptr(), out.data_ptr(), kv_cache.key_buffer_.data_ptr(),
+                                                      kv_cache.value_buffer_.data_ptr(), kv_cache.k_scales_.data_ptr(),
+                                                      kv_cache.v_scales_.data_ptr(), *common, _cabi.stream())
+            else:
+                return None
+        if st == _cabi.PA_ERR_UNSUPPORTED:
+            return None
+        _cabi.check(st, "pa_paged_prefill_tokmajor")
+        return out
     # head_dim 128 takes a tensor-core flash-attention kernel (fp16 or int8 pages), which needs no scratch; head_dim 64
     # takes the tcgen05 kernel too but keeps the scratch for the row-per-query fallback (odd page sizes)
     fa = (D == 128 and kv_cache.tile_size_ % 16 == 0 and

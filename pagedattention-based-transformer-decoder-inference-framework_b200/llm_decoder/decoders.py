@@ -162,6 +162,10 @@ class _DecoderBase:
             from .attention import paged_prefill
             B, n = prefill_shape
             H, D = self.num_heads_, self.head_dim_
+            # q/out are [B, n, H, D] as the projection left them: the kernel takes the strides (no permute + copy)
+            if q.data_ptr() != out.data_ptr() and \
+                    paged_prefill(q, out, kvc, B, n, self.attn_temperature, token_major=True) is not None:
+                return
             qb = q.view(B, n, H, D).permute(0, 2, 1, 3).contiguous()
             ob = torch.empty_like(qb)
             paged_prefill(qb, ob, kvc, B, n, self.attn_temperature)

@@ -518,6 +518,45 @@ def test_prefill_head_dim_64_on_tcgen05(ld, oracle, kv, nq, monkeypatch):
     _prefill_case(ld, oracle, kv, Tq=200, start=np.array([40, 8], np.int32), check_forward=False, D=64, tile_size=32)
 
 
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("nq", ["1", "2"])
+@pytest.mark.parametrize("kv", ["f16", "i8"])
+def test_prefill_token_major_layout_is_bit_identical(ld, oracle, kv, nq, D, monkeypatch):
+    """pa_paged_prefill_*_tokmajor ([B, Tq, H, D] activations, strides folded into the tcgen05 kernel's Q loads and
+    O stores) against the [B, H, Tq, D] entry: the same arithmetic on the same rows, so the bits must match (the
+    [B, H, Tq, D] entry is what the oracle tests above pin); rows past Tq and the canaries either side of the output
+    stay untouched."""
+    monkeypatch.setenv("PA_PREFILL_NQ", nq)
+    B, H = 2, 3
+    for Tq, start, kw in ((129, [0, 7], {}), (300, [23, 100], dict(unmapped_frac=0.05)), (200, [40, 8], dict(tile_size=32))):
+        start = np.array(start, np.int32)
+        case = make_case(B=B, H=H, D=D, T=int(start.max()) + Tq, seed=83, kv=kv, **kw)
+        kvc = to_device_cache(case)
+        q = torch.randn((B, H, Tq, D), device="cuda", generator=torch.Generator(device="cuda").manual_seed(Tq))
+        ref = torch.full((B, H, Tq, D), float("nan"), device="cuda")
+        cs = torch.from_numpy(start).cuda()
+        ld.paged_prefill(q, ref, kvc, B, Tq, case["temperature"], ctx_start=cs)
+        q_tm = q.permute(0, 2, 1, 3).contiguous()
+        guard = 1024
+        buf = torch.full((B * Tq * H * D + 2 * guard,), -77.0, device="cuda")
+        out_tm = buf[guard:guard + B * Tq * H * D].view(B, Tq, H, D)
+        got = ld.paged_prefill(q_tm, out_tm, kvc, B, Tq, case["temperature"], ctx_start=cs, token_major=True)
+        assert got is not None, "the tcgen05 kernel serves head_dim 64 / 128 with 16 << k token pages"
+        torch.cuda.synchronize()
+        assert torch.equal(out_tm.permute(0, 2, 1, 3), ref)
+        assert bool((buf[:guard] == -77.0).all()) and bool((buf[-guard:] == -77.0).all())
+
+
+def test_prefill_token_major_reports_unsupported(ld, oracle):
+    """Shapes the tcgen05 kernel does not serve (head_dim 32) answer None (PA_ERR_UNSUPPORTED at the C-ABI): the caller
+    permutes and uses the [B, H, Tq, D] entry."""
+    case = make_case(B=1, H=2, D=32, T=40, seed=84, kv="f16")
+    kvc = to_device_cache(case)
+    q = torch.randn((1, 24, 2, 32), device="cuda")
+    out = torch.empty_like(q)
+    assert ld.paged_prefill(q, out, kvc, 1, 24, 1.0, token_major=True) is None
+
+
 @pytest.mark.parametrize("kv", ["f16", "i8"])
 def test_prefill_tc_full_size_agrees_with_mma_kernel(ld, monkeypatch, kv):
     """Llama-7B head shape, Tq = 2048 (the benchmark's size): the tcgen05 kernel and the mma.sync kernel are
