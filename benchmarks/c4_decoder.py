@@ -64,7 +64,7 @@ def main():
     dt = (time.perf_counter() - t0) / args.steps
     tok = start + args.steps // 2
     kv_bytes = B * H * tok * D * 2 + B * H * tok * 8 if args.decoder == "int8" else B * H * tok * D * 2 * 2
-    name = "C4 via INT8Decoder" if args.decoder == "int8" else "C2 shape via CUDADecoder (fp32 SIMT MLP)"
+    name = "C4 via INT8Decoder" if args.decoder == "int8" else "C2 shape via CUDADecoder (fp32 weights, 3xTF32 tcgen05 MLP)"
     print(json.dumps({"workload": f"{name}: {L} layers, batch {B}, ctx ~{args.ctx}",
                       "ms_per_step": round(dt * 1e3, 3), "decode_tok_s": round(B / dt, 1),
                       "attention_kv_gbs_lower_bound": round(L * kv_bytes / dt / 1e9, 1),

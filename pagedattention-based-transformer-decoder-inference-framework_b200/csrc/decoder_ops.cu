@@ -523,6 +523,24 @@ static bool linear_uses_gemm(const void* x, const void* W, const void* out, cons
            (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
 }
 
+// linear_tf32x3.cu: 3xTF32 tcgen05 kernel over the same [rows, K] x [K, N] operands
+int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out);
+int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
+                        float* d_out, float* d_partial, int nslices, int kslice, cudaStream_t st);
+
+// The tensor-core kernel serves what the register-tiled kernel serves (>= 16 rows, 16-byte aligned rows of x, W, out)
+// wherever the layer is large enough for the tile kernels at all; PA_LINEAR_TC=0 keeps the fp32 SIMT kernels
+// (bit-level fp32 arithmetic), PA_LINEAR_TC=1 forces it for every eligible shape.
+static bool linear_uses_tc(const void* x, const void* W, const void* out, const void* bias, int rows, int K, int N) {
+    if (const char* env = getenv("PA_LINEAR_TC")) {
+        if (atoi(env) == 0) return false;
+    } else if ((int64_t)rows * K * N < 500000000ll) {
+        return false;
+    }
+    return rows >= 16 && N % 4 == 0 && K % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)W % 16 == 0 &&
+           (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
+}
+
 static int linear_slices(int rows, int K, int N, int sm_count, int* kslice_out, bool gemm) {
     const int strips = gemm ? (N + kGemmBN - 1) / kGemmBN : (N + 31) / 32;
     const int chunks = gemm ? (rows + kGemmBM - 1) / kGemmBM : (rows + kLinRows - 1) / kLinRows;
@@ -546,7 +564,9 @@ PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
     // either kernel may run (the choice also depends on pointer alignment): size for the larger need
     const int a = linear_slices(rows, K, N, sm, nullptr, false);
     const int b = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? linear_slices(rows, K, N, sm, nullptr, true) : 1;  // (env may force it)
-    const int nslices = a > b ? a : b;
+    const int c = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? pa_linear_tc_slices(rows, K, N, sm, nullptr) : 1;
+    int nslices = a > b ? a : b;
+    if (c > nslices) nslices = c;
     return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
 }
 
@@ -560,9 +580,11 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     if (rows == 0) return PA_OK;
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
-    const bool gemm = linear_uses_gemm(d_x, d_W, d_out, d_bias, rows, K, N);
+    const bool tc = linear_uses_tc(d_x, d_W, d_out, d_bias, rows, K, N);
+    const bool gemm = !tc && linear_uses_gemm(d_x, d_W, d_out, d_bias, rows, K, N);
     int kslice = K;
-    int nslices = linear_slices(rows, K, N, di.sm_count, &kslice, gemm);
+    int nslices = tc ? pa_linear_tc_slices(rows, K, N, di.sm_count, &kslice)
+                     : linear_slices(rows, K, N, di.sm_count, &kslice, gemm);
     float* partial = nullptr;
     if (nslices > 1) {
         if (d_workspace && workspace_bytes >= (size_t)nslices * rows * N * sizeof(float) && (uintptr_t)d_workspace % 16 == 0) {
@@ -573,7 +595,11 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
         }
     }
     cudaError_t e;
-    if (gemm) {
+    if (tc) {
+        const int stc = pa_linear_tc_launch(d_x, d_W, d_bias, rows, K, N, act, d_out, partial, nslices, kslice,
+                                            as_stream(stream));
+        if (stc != PA_OK) return stc;
+    } else if (gemm) {
         const size_t smem = (size_t)kGemmStages * (kGemmKT * kGemmBN + kGemmBM * kGemmXStride) * sizeof(float);
         static bool attr_set[64] = {};
         int dev = 0;

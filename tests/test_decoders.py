@@ -613,6 +613,7 @@ def test_linear_register_tiled_gemm_matches_fp64(shape, monkeypatch):
     need = lib.pa_linear_workspace_bytes(rows, K, N)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
     outs = {}
+    monkeypatch.setenv("PA_LINEAR_TC", "0")   # the SIMT kernels are the subject here
     for mode in ("gemm", "gemm-nows", "strip"):
         monkeypatch.setenv("PA_LINEAR_GEMM", "0" if mode == "strip" else "1")
         for act in (0, 1):
@@ -626,3 +627,46 @@ def test_linear_register_tiled_gemm_matches_fp64(shape, monkeypatch):
     o = torch.empty((rows, N), device="cuda")
     _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), None, rows, K, N, 0, o.data_ptr(), ws.data_ptr(), need, None))
     np.testing.assert_allclose(o.cpu().numpy(), exp - b, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 4096, 1024), (100, 192, 100), (16, 256, 128), (300, 520, 388), (65, 36, 12),
+                                   (128, 64, 260), (257, 2048, 128)])
+def test_linear_tf32x3_tensor_core_kernel_matches_fp64(shape, monkeypatch):
+    """pa_linear_f32 on tcgen05 kind::tf32 with the 3-term operand split (linear_tf32x3.cu, PA_LINEAR_TC=1 forces it
+    for small shapes): against a float64 product with the stated bound 1e-5 * sum_k |x||W| + 4 fp32 ulps of the
+    result (measured <= 3e-6: operand split 2^-21, plus the tensor core's truncating fp32 accumulation over K) -- K-sliced and unsliced, bias / relu, ragged M / N / K tiles (TMA zero fill), rows past the tile untouched;
+    and within the same bound of the fp32 SIMT kernel (PA_LINEAR_TC=0)."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    rows, K, N = shape
+    rng = np.random.default_rng(sum(shape) + 1)
+    x = (rng.standard_normal((rows, K)) * np.exp(rng.uniform(-3, 3, (rows, 1)))).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dx, dW, db = (torch.from_numpy(a).cuda() for a in (x, W, b))
+    exp = x.astype(np.float64) @ W.astype(np.float64) + b
+    bound = 1e-5 * (np.abs(x).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)) + 4 * np.spacing(np.abs(exp).astype(np.float32))
+    need = lib.pa_linear_workspace_bytes(rows, K, N)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    outs = {}
+    for mode in ("tc", "tc-nows", "simt"):
+        monkeypatch.setenv("PA_LINEAR_TC", "0" if mode == "simt" else "1")
+        for act in (0, 1):
+            guard = 512
+            buf = torch.full((rows * N + 2 * guard,), float("nan"), device="cuda")
+            o = buf[guard:guard + rows * N].view(rows, N)
+            wp, wb = (None, 0) if mode == "tc-nows" else (ws.data_ptr(), need)
+            _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), db.data_ptr(), rows, K, N, act, o.data_ptr(), wp, wb, None))
+            torch.cuda.synchronize()
+            got = o.cpu().numpy().astype(np.float64)
+            e = np.maximum(exp, 0) if act else exp
+            assert np.all(np.abs(got - e) <= bound), float(np.max(np.abs(got - e) / bound))
+            assert bool(torch.isnan(buf[:guard]).all()) and bool(torch.isnan(buf[-guard:]).all())
+            outs[(mode, act)] = got
+    assert np.all(np.abs(outs[("tc", 0)] - outs[("simt", 0)]) <= 2 * bound)
+    # no bias
+    o = torch.empty((rows, N), device="cuda")
+    monkeypatch.setenv("PA_LINEAR_TC", "1")
+    _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), None, rows, K, N, 0, o.data_ptr(), ws.data_ptr(), need, None))
+    assert np.all(np.abs(o.cpu().numpy() - (exp - b)) <= bound)
