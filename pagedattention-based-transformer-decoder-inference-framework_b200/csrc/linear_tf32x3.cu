@@ -4,25 +4,31 @@
 // tcgen05.mma kind::tf32 reads 32-bit containers and uses sign, 8 exponent and the top 10 mantissa bits.  Each
 // operand is therefore split exactly into  v = hi + lo,  hi = v with the low 13 mantissa bits cleared (what the
 // tensor core sees of v itself), lo = v - hi (exact in fp32, 13 significant bits of which the core keeps 11), and
-//     x . W  ~=  x_lo . W_hi + x_hi . W_lo + x_hi . W_hi                     ("3xTF32")
-// accumulated in fp32 in TMEM.  Dropped: lo.lo (2^-22 relative) and the tail of each lo (2^-21): per-product error
-// <= ~1e-6 of |x||W|, the same order as fp32 summation-order noise of the SIMT kernels it replaces (tests state
-// 2e-6 * sum_k |x||W| + fp32 eps of the result).  x and W are consumed where they lie: x [rows, K] is the K-major A
-// operand, W [K, N] (the reference's layout) the MN-major B operand -- no transposed or pre-split copy of the
-// weights, which stream from HBM exactly once per 128-row tile of x.
+//     x . W  ~=  x_hi . W_lo + x_lo . W_hi + x_hi . W_hi                     ("3xTF32")
+// accumulated in fp32 in TMEM.  Dropped: lo.lo (2^-22 relative) and the tail of each lo (2^-21); the tensor core's
+// fp32 accumulation truncates, which adds ~K/8 * 2^-24 of the running sum.  Measured <= 3e-6 of sum_k |x||W|
+// (K = 11008, unsliced); the tests state 1e-5 * sum_k |x||W| + 4 ulp.  The fp32 SIMT kernels (PA_LINEAR_TC=0) stay
+// for callers that need fp32 arithmetic proper.
 //
-// One CTA = one 128 x 128 output tile over one K slice; 192 threads:
-//   warp 0    TMA producer: per 32-float K block the x tile [128 rows][128 B] and four W boxes [32 k][32 n]
-//             (128-byte swizzle -- 32-byte atoms for W --, out-of-range rows / columns / k zero-filled) into a 4-stage ring;
-//   warps 2-5 split: thread = row of x: its 32 floats of the block go to TENSOR MEMORY as two A operands (x as it is
-//             -- the core ignores the low 13 bits -- and x_lo), so the three MMAs of a k-step read x from TMEM instead
-//             of three times from shared memory; the W tile gets its lo tile beside it (same swizzled offsets, so the
-//             split never needs the layout); fence to the async proxy, arrive.  After the main loop the same warps
-//             are the epilogue (tcgen05.ld of their TMEM lane quarter, bias / relu or K-slice partial, 16-byte stores);
-//   warp 1    one elected lane issues 12 tcgen05.mma (4 k-steps of 8 x 3 terms, A from TMEM, B from shared memory)
+// The layer is computed TRANSPOSED: out^T [N, rows] = W^T [N, K] . x^T [K, rows].  The weights are the M side of the
+// MMA (128 output features = 128 TMEM lanes), the decode batch the N side, so a small batch costs a small MMA
+// (tcgen05 time is max(M,128) * N / 256 cycles: 32 for 64 rows, where batch-as-M would pay 64 for anything <= 128)
+// and the accumulator tile [128 features][rows] is what the epilogue wants: lane = feature, so every store
+// instruction writes 32 consecutive features of one row (128 bytes).  W is consumed in the reference's [K, N]
+// layout and x where it lies; the weights stream from HBM exactly once per 256 rows of x.
+//
+// One CTA = 128 features x NP rows (NP = 64, 128 or 256 by batch) over one K slice; 320 threads:
+//   warp 0    TMA producer, per 32-float K block: four W boxes [32 k][32 n] (no swizzle: only threads read them) and
+//             the x tile [NP rows][128 B] (128-byte swizzle, K-major B operand; rows / k out of range zero-filled);
+//   warps 2-9 split: thread = (feature n, half of the block's k): reads its 16 weights W[k][n] down the column
+//             (conflict-free: a warp reads 32 consecutive floats of one k-row), stores them and their lo parts into
+//             TENSOR MEMORY as the A operands (lane n, 32 + 32 columns per stage) -- the weights never touch shared
+//             memory again; x gets its lo tile beside it (same swizzled offsets, so the split never needs the
+//             layout); fence to the async proxy, arrive.  After the main loop the same warps are the epilogue;
+//   warp 1    one elected lane issues 12 tcgen05.mma (4 k-steps of 8 x 3 terms; A from TMEM, B from shared memory)
 //             per stage, commit frees the stage.
-// Shared-memory traffic per stage is what bounds the loop next to the tensor pipe: 48 KB of W operand reads + 48 KB
-// of split traffic (x 16, W 16 read, W_lo 16 written) per 16 KB of weights streamed from HBM.
+// Shared-memory traffic per stage at 64 rows: 16 KB W written + 16 KB read, x 8 + 8 (lo) written, 8 read, 24 KB of
+// B-operand reads = 80 KB per 16 KB of weights, against 128 KB for the batch-as-M form measured first (r02_notes.md).
 // K slices (grid.z) write fp32 partial tiles that linear_reduce_kernel (decoder_ops.cu) sums in slice order.
 #include <cuda.h>
 
@@ -34,16 +40,20 @@
 namespace pa {
 namespace tf32x3 {
 
-constexpr int BM = 128;            // rows per tile = UMMA M = TMEM lanes
-constexpr int BN = 128;            // columns per tile = UMMA N = TMEM columns
-constexpr int BKF = 32;            // floats of K per stage (one 128-byte swizzle row)
-constexpr int TILE = BM * 128;     // 16 KiB: one operand tile
-constexpr int STAGE = 3 * TILE;    // x, W, W_lo
-constexpr int NST = 4;
-constexpr int ACC_COLS = BN;                 // TMEM: accumulator, then per stage x (32 columns) and x_lo (32 columns)
-constexpr int TMEM_COLS = 512;               // 128 + 4 * 64 = 384 -> next power of two
-constexpr int NTHREADS = 192;
-constexpr int W_BOX = BKF * 128;   // one W box: 32 k-rows x 32 columns = 4 KiB; four of them side by side per tile
+constexpr int BF = 128;            // output features per tile = UMMA M = TMEM lanes
+constexpr int BKF = 32;            // floats of K per stage (one 128-byte swizzle row of x)
+constexpr int W_TILE = BF * 128;   // 16 KiB: W block [4 boxes][32 k][32 n]
+constexpr int W_BOX = BKF * 128;   // one W box: 32 k-rows x 32 features = 4 KiB
+constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 split + epilogue (two per TMEM lane quarter)
+// per row-tile width NP: stage = W (16 KB) + x + x_lo (NP * 128 B each); TMEM = NP accumulator columns + 64 per stage
+template <int NP> struct Cfg {
+    static constexpr int X_TILE = NP * 128;
+    static constexpr int STAGE = W_TILE + 2 * X_TILE;
+    static constexpr int NST = NP == 64 ? 6 : (NP == 128 ? 4 : 2);
+    static constexpr int TMEM_COLS = 512;
+    static_assert(NP + NST * 64 <= TMEM_COLS, "TMEM budget");
+    static_assert(NST * STAGE <= 200 * 1024, "shared-memory budget");
+};
 
 struct Args {
     const float* bias;
@@ -95,6 +105,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -109,31 +126,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// UMMA shared-memory descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30),
-// SBO >> 4 [32,46), version 1 [46,48), layout [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1.
-//   K-major  (x):  rows of 128 B (32 floats of K); 8-row groups 1024 B apart (SBO); LBO unused (one swizzle row of K).
-//   MN-major (W):  32-bit operands transpose at 32-byte granularity, so the layout is SWIZZLE_128B_BASE32B = 1
-//                  (Swizzle<2,5,2>; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), canonical form
-//                  ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp:246): 128 B of N
-//                  (32 floats) contiguous, the next 32 columns LBO bytes on, k-rows 128 B apart, 4-row groups SBO = 512
-//                  bytes apart.  (The plain 128-byte swizzle, layout 2, is accepted for MN-major tf32 but the tensor
-//                  core then returns zeros -- measured during bring-up.)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14),
+// LBO >> 4 [16,30) (unused: one swizzle row of K), SBO >> 4 [32,46) = 1024 (8-row groups), version 1 [46,48),
+// SWIZZLE_128B = 2 [61,64).  x tile: rows of 128 B (32 floats of K).
+// (Bring-up note: W as an MN-major tf32 B operand works only with layout 1, SWIZZLE_128B_BASE32B, fed by
+//  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; with the plain 128-byte swizzle the tensor core returns zeros.  That form
+//  was measured and replaced by this one, see profiles/r02_notes.md.)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
-// Instruction descriptor: c = F32 (1) [4,6), a = b = TF32 (2) [7,10) [10,13), a K-major (0) [15], b MN-major (1) [16],
+// Instruction descriptor: c = F32 (1) [4,6), a = b = TF32 (2) [7,10) [10,13), a (TMEM) and b K-major (0) [15] [16],
 // N >> 3 [17,23), M >> 4 [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
-                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-// v - (v with the low 13 mantissa bits cleared); 0 for inf / nan inputs' hi part is the value itself (inf - inf
-// would poison finite columns of the same row with NaN through the lo terms, so non-finite values get lo = 0).
-__device__ __forceinline__ float lo_part(float v) {
-    const uint32_t u = __float_as_uint(v);
-    const float hi = __uint_as_float(u & 0xffffe000u);
-    return ((u & 0x7f800000u) == 0x7f800000u) ? 0.f : v - hi;
+__host__ __device__ constexpr uint32_t idesc_for(int np) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(np >> 3) << 17) | ((uint32_t)(BF >> 4) << 24);
 }
+
+// v - (v with the low 13 mantissa bits cleared): exact in fp32.  (A non-finite v gives lo = NaN, so an inf in x or W
+// turns its whole output row / column into NaN where the scalar loop would give +-inf or NaN per element.)
+__device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
     // a lost arrival would otherwise hang the GPU box: ~2 s of polling, then trap
@@ -142,8 +153,11 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
     __trap();
 }
 
+template <int NP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Args g) {
+    using C = Cfg<NP>;
+    constexpr int NST = C::NST, STAGE = C::STAGE, X_TILE = C::X_TILE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + NST * STAGE;
@@ -154,7 +168,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t tmem_slot = tmem_full_bar + 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, slice = blockIdx.z;
+    const int m0 = blockIdx.x * NP, n0 = blockIdx.y * BF, slice = blockIdx.z;
     const int k_begin = slice * g.kslice;
     const int k_end = min(g.K, k_begin + g.kslice);
     const int nkb = (k_end - k_begin + BKF - 1) / BKF;   // kslice is a multiple of BKF: blocks never straddle slices
@@ -162,7 +176,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(split_bar(s), 128);
+            mbar_init(split_bar(s), 256);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
@@ -170,12 +184,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW));
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // stage layout: W [4][32 k][32 n] | x [NP][128 B] | x_lo;  TMEM: accumulator [0, NP), then per stage W (32) W_lo (32)
 
     if (warp == 0) {
         if (elect_one()) {
@@ -183,15 +198,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int s = i % NST;
                 mbar_wait_bounded(empty_bar(s), ((i / NST) & 1) ^ 1);
                 const uint32_t st = base + s * STAGE;
-                mbar_arrive_expect_tx(full_bar(s), 2 * TILE);
+                mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
                 const int k0 = k_begin + i * BKF;
-                tma_load_2d(st, &tmX, k0, m0, full_bar(s));
 #pragma unroll
-                for (int j = 0; j < BN / 32; ++j) tma_load_2d(st + TILE + j * W_BOX, &tmW, n0 + j * 32, k0, full_bar(s));
+                for (int j = 0; j < BF / 32; ++j) tma_load_2d(st + j * W_BOX, &tmW, n0 + j * 32, k0, full_bar(s));
+                tma_load_2d(st + W_TILE, &tmX, k0, m0, full_bar(s));
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
+            constexpr uint32_t idesc = idesc_for(NP);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % NST;
                 mbar_wait_bounded(split_bar(s), (i / NST) & 1);
@@ -199,94 +215,85 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const uint32_t st = base + s * STAGE;
 #pragma unroll
                 for (int ks = 0; ks < BKF / 8; ++ks) {
-                    const uint32_t xa = tmem_base + ACC_COLS + s * 64 + ks * 8;
-                    const uint32_t xl = xa + 32;
-                    const uint64_t wa = make_desc(st + TILE + ks * 1024, W_BOX, 512, 1);
-                    const uint64_t wl = make_desc(st + 2 * TILE + ks * 1024, W_BOX, 512, 1);
-                    umma_tf32_ts(tmem_base, xl, wa, kIdesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                    umma_tf32_ts(tmem_base, xa, wl, kIdesc, 1u);
-                    umma_tf32_ts(tmem_base, xa, wa, kIdesc, 1u);
+                    const uint32_t wa = tmem_base + NP + s * 64 + ks * 8;
+                    const uint32_t wl = wa + 32;
+                    const uint64_t xa = make_desc(st + W_TILE + ks * 32);
+                    const uint64_t xl = make_desc(st + W_TILE + X_TILE + ks * 32);
+                    umma_tf32_ts(tmem_base, wl, xa, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                    umma_tf32_ts(tmem_base, wa, xl, idesc, 1u);
+                    umma_tf32_ts(tmem_base, wa, xa, idesc, 1u);
                 }
                 umma_commit(empty_bar(s));
             }
             umma_commit(tmem_full_bar);
         }
     } else {
-        const int t = threadIdx.x - 64;   // 0..127
+        const int t = threadIdx.x - 64;      // 0..255
+        const int qtr = warp & 3;            // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;    // which half of a block's k (split) / of the row tile (epilogue)
+        const int f = qtr * 32 + lane;       // feature of the tile = TMEM lane
         for (int i = 0; i < nkb; ++i) {
             const int s = i % NST;
             mbar_wait_bounded(full_bar(s), (i / NST) & 1);
             const uint32_t st = base + s * STAGE;
-            // x: this thread's row (TMEM lane) of the block: 8 swizzled 16-byte chunks -> 32 columns of x and of x_lo
+            // W: column f of the block, k rows [half * 16, half * 16 + 16) -> 16 columns of W and of W_lo in TMEM
             {
-                const int r = (warp & 3) * 32 + lane;
-                uint32_t xv[32], xlo[32];
+                uint32_t wv[16], wlo[16];
+                const uint32_t col = st + qtr * W_BOX + lane * 4 + half * 16 * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 v = lds_128(st + r * 128 + ((c ^ (r & 7)) << 4));
-                    xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
-                }
+                for (int j = 0; j < 16; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[j]) : "r"(col + j * 128));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) xlo[j] = __float_as_uint(lo_part(__uint_as_float(xv[j])));
-                const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COLS + s * 64;
-                tmem_st32(ta, xv);
-                tmem_st32(ta + 32, xlo);
+                for (int j = 0; j < 16; ++j) wlo[j] = __float_as_uint(lo_part(__uint_as_float(wv[j])));
+                const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + NP + s * 64 + half * 16;
+                tmem_st16(ta, wv);
+                tmem_st16(ta + 32, wlo);
             }
-            // W tile -> W_lo: 1024 chunks of 16 bytes, 8 per thread
-            {
-                const uint32_t src = st + TILE, dst = src + TILE;
-                uint4 v[8];
+            // x tile -> x_lo: NP * 8 chunks of 16 bytes
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = lds_128(src + (j * 128 + t) * 16);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float a = lo_part(__uint_as_float(v[j].x)), b = lo_part(__uint_as_float(v[j].y));
-                    const float c = lo_part(__uint_as_float(v[j].z)), d = lo_part(__uint_as_float(v[j].w));
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (j * 128 + t) * 16), "f"(a), "f"(b),
-                                 "f"(c), "f"(d)
-                                 : "memory");
-                }
+            for (int j = 0; j < NP / 32; ++j) {
+                const uint32_t off = (j * 256 + t) * 16;
+                const uint4 v = lds_128(st + W_TILE + off);
+                const float a = lo_part(__uint_as_float(v.x)), b = lo_part(__uint_as_float(v.y));
+                const float c = lo_part(__uint_as_float(v.z)), d = lo_part(__uint_as_float(v.w));
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + W_TILE + X_TILE + off), "f"(a), "f"(b), "f"(c),
+                             "f"(d)
+                             : "memory");
             }
+            fence_proxy_async();
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            fence_proxy_async();
             mbar_arrive(split_bar(s));
         }
-        // ---- epilogue: this warp's TMEM lane quarter, 32 columns at a time ----
-        const int qtr = warp & 3;
-        const int row = m0 + qtr * 32 + lane;
-        const bool row_ok = row < g.rows;
+        // ---- epilogue: lane = feature, columns = rows of x; this warp takes half of the row tile, 32 rows at a time ----
+        const int n = n0 + f;
+        const bool n_ok = n < g.N;
         if (nkb > 0) {
             mbar_wait_bounded(tmem_full_bar, 0);
             tc_fence_after();
         }
-        float* dst_row = g.nslices > 1 ? g.partial + ((int64_t)slice * g.rows + row) * g.N : g.out + (int64_t)row * g.N;
+        const float bias = (g.nslices == 1 && g.bias && n_ok) ? __ldg(g.bias + n) : 0.f;
+        float* dst = g.nslices > 1 ? g.partial + (int64_t)slice * g.rows * g.N : g.out;
+        constexpr int CH = NP / 64;   // 32-row chunks per warp
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
+        for (int c = half * CH; c < half * CH + CH; ++c) {
+            uint32_t rr[32];
             if (nkb > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(qtr * 32) << 16) + c * 32, r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(qtr * 32) << 16) + c * 32, rr);
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+                for (int j = 0; j < 32; ++j) rr[j] = 0u;
             }
-            if (!row_ok) continue;
+            if (!n_ok) continue;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int n = n0 + c * 32 + j;
-                if (n >= g.N) break;   // N % 4 == 0: whole float4 groups
-                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                       __uint_as_float(r[j + 3]));
+            for (int j = 0; j < 32; ++j) {
+                const int row = m0 + c * 32 + j;
+                if (row >= g.rows) break;
+                float v = __uint_as_float(rr[j]);
                 if (g.nslices == 1) {
-                    if (g.bias) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                    }
-                    if (g.act == PA_ACT_RELU) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
+                    v += bias;
+                    if (g.act == PA_ACT_RELU) v = fmaxf(v, 0.f);
                 }
-                *reinterpret_cast<float4*>(dst_row + n) = v;
+                dst[(int64_t)row * g.N + n] = v;
             }
         }
         tc_fence_before();
@@ -294,7 +301,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -313,7 +320,7 @@ static EncodeTiledFn encode_fn() {
     });
     return fn;
 }
-// 2-D f32 tensor [rows][cols] (cols contiguous), box [box_rows][32 floats], 128-byte swizzle, zero fill out of range.
+// 2-D f32 tensor [rows][cols] (cols contiguous), box [box_rows][32 floats], zero fill out of range.
 static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows,
                          CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
@@ -327,17 +334,37 @@ static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint6
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int row_tile(int rows) { return rows <= 64 ? 64 : (rows <= 128 ? 128 : 256); }
+
+template <int NP>
+static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g, int nslices, cudaStream_t st) {
+    using C = Cfg<NP>;
+    const size_t smem = (size_t)C::NST * C::STAGE + (3 * C::NST + 1) * 8 + 16 + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[dev & 63] = true;
+    }
+    dim3 grid((unsigned)((g.rows + NP - 1) / NP), (unsigned)((g.N + BF - 1) / BF), (unsigned)nslices);
+    linear_tf32x3_kernel<NP><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
+    PA_RETURN_LAUNCH_STATUS();
+}
+
 }  // namespace tf32x3
 }  // namespace pa
 
 using namespace pa;
 
-// K-slice geometry.  One CTA per SM is resident (192 KB ring), so the grid runs in waves of sm_count CTAs: pick the
-// slice count that minimises waves x K blocks per CTA (+ half a block per slice for the partial-tile traffic);
-// every slice holds >= 8 K blocks (256 k-rows).
+// K-slice geometry.  One CTA per SM is resident, so the grid runs in waves of sm_count CTAs: pick the slice count
+// that minimises waves x (K blocks per CTA + per-CTA set-up, ~2 blocks), + half a block per slice for the
+// partial-tile traffic; every slice holds >= 8 K blocks (256 k-rows).
 int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     using namespace pa::tf32x3;
-    const int64_t tiles = (int64_t)((rows + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int np = row_tile(rows);
+    const int64_t tiles = (int64_t)((rows + np - 1) / np) * ((N + BF - 1) / BF);
     const int total_kb = (K + BKF - 1) / BKF;
     int max_ns = total_kb / 8;
     if (max_ns > 16) max_ns = 16;
@@ -361,21 +388,13 @@ int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
 int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
                         float* d_out, float* d_partial, int nslices, int kslice, cudaStream_t st) {
     using namespace pa::tf32x3;
+    const int np = row_tile(rows);
     CUtensorMap tmX, tmW;
-    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, (uint32_t)np, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
         return PA_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)NST * STAGE + (3 * NST + 1) * 8 + 16 + 1024;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set[dev & 63] = true;
-    }
     Args g{d_bias, d_out, d_partial, rows, N, K, act, kslice, nslices};
-    dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)nslices);
-    linear_tf32x3_kernel<<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
-    PA_RETURN_LAUNCH_STATUS();
+    if (np == 64) return launch<64>(tmX, tmW, g, nslices, st);
+    if (np == 128) return launch<128>(tmX, tmW, g, nslices, st);
+    return launch<256>(tmX, tmW, g, nslices, st);
 }
