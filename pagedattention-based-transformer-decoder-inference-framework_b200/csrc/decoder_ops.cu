@@ -215,6 +215,27 @@ __global__ void linear_reduce_kernel(const float* __restrict__ partial, const fl
     out[i] = s;
 }
 
+// K-slice sum behind the tensor-core kernel: 16-byte lanes (N % 4 == 0 there), launched with programmatic dependent
+// launch so its blocks are resident when the last partial tile lands (griddepcontrol.wait = all of the primary grid's
+// memory is visible).  Slices are added in index order: the result does not depend on the schedule.
+__global__ void __launch_bounds__(256) linear_reduce4_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                             int rows, int N, int nslices, int act, float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t total = (int64_t)rows * N;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total && bias) s = __ldg(reinterpret_cast<const float4*>(bias + i % N));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (i >= total) return;
+    for (int z = 0; z < nslices; ++z) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)z * total + i));
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    if (act == PA_ACT_RELU) {
+        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+}
+
 // ---- logits against the tied embedding E [vocab, hidden]: one warp per vocab row, 16-byte loads.
 // Optionally folds the greedy sampler in: best[r] = max over v of the 64-bit key
 // (order-preserving bits of (logit / T or logit * T) << 32 | ~v), so the maximum key is the FIRST maximum
@@ -534,8 +555,8 @@ int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias,
 static bool linear_uses_tc(const void* x, const void* W, const void* out, const void* bias, int rows, int K, int N) {
     if (const char* env = getenv("PA_LINEAR_TC")) {
         if (atoi(env) == 0) return false;
-    } else if ((int64_t)rows * K * N < 500000000ll) {
-        return false;
+    } else if ((int64_t)rows * K * N < 50000000ll) {
+        return false;   // tiny layers: launch-bound either way, keep the fp32 kernels
     }
     return rows >= 16 && N % 4 == 0 && K % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)W % 16 == 0 &&
            (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
@@ -618,6 +639,20 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    if (nslices > 1 && tc) {
+        const int64_t n4 = ((int64_t)rows * N + 3) / 4;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)((n4 + 255) / 256));
+        cfg.blockDim = dim3(256);
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, linear_reduce4_kernel, (const float*)partial, d_bias, rows, N, nslices, act, d_out);
+        return e == cudaSuccess ? PA_OK : (int)e;
+    }
     if (nslices > 1) {
         const int64_t n = (int64_t)rows * N;
         linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, d_bias, rows, N,

@@ -29,7 +29,8 @@
 //             per stage, commit frees the stage.
 // Shared-memory traffic per stage at 64 rows: 16 KB W written + 16 KB read, x 8 + 8 (lo) written, 8 read, 24 KB of
 // B-operand reads = 80 KB per 16 KB of weights, against 128 KB for the batch-as-M form measured first (r02_notes.md).
-// K slices (grid.z) write fp32 partial tiles that linear_reduce_kernel (decoder_ops.cu) sums in slice order.
+// K slices (grid.z) write fp32 partial tiles that linear_reduce4_kernel (decoder_ops.cu, chained by programmatic
+// dependent launch) sums in slice order.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -167,6 +168,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t tmem_full_bar = bar0 + 3 * NST * 8;
     const uint32_t tmem_slot = tmem_full_bar + 8;
 
+    asm volatile("griddepcontrol.launch_dependents;");   // the K-slice sum behind this grid may become resident
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * NP, n0 = blockIdx.y * BF, slice = blockIdx.z;
     const int k_begin = slice * g.kslice;
@@ -359,8 +361,10 @@ static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g,
 using namespace pa;
 
 // K-slice geometry.  One CTA per SM is resident, so the grid runs in waves of sm_count CTAs: pick the slice count
-// that minimises waves x (K blocks per CTA + per-CTA set-up, ~2 blocks), + half a block per slice for the
-// partial-tile traffic; every slice holds >= 8 K blocks (256 k-rows).
+// that minimises waves x (K blocks per CTA + per-CTA set-up, ~2 blocks, + when sliced the partial tile's write and
+// re-read, NP / 16 blocks' worth of bytes); every slice holds >= 8 K blocks (256 k-rows).
+// (Summing the slices inside the kernel -- last slice of a tile to arrive, one counter per tile -- was measured and
+//  rejected: fence + counter + the last CTA's serial sum lengthen every wave, fc1 at batch 64 60 -> 88 us.)
 int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
@@ -373,7 +377,7 @@ int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     double best_cost = 1e30;
     for (int ns = 1; ns <= max_ns; ++ns) {
         const int64_t waves = (tiles * ns + sm_count - 1) / sm_count;
-        const double cost = (double)waves * ((total_kb + ns - 1) / ns + 2) + 0.5 * (ns - 1);
+        const double cost = (double)waves * ((total_kb + ns - 1) / ns + 2 + (ns > 1 ? np / 16 : 0));
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best_ns = ns;
