@@ -53,3 +53,11 @@ def test_decode_kernels_stream_pages_with_bulk_copies():
     # the producers issue their copies under elect.sync: no R2UR + BRA.U.ANY uniformisation loop around any UBLKCP /
     # UTMALDG (r01 had 40 of them in this object: every bulk copy of the streaming kernels)
     assert _count(sass, "BRA.U.ANY") == 0
+
+
+def test_fp32_linear_kernel_runs_tf32_mma_with_weights_in_tensor_memory():
+    sass = _sass("linear_tf32x3.cu.o")
+    assert _count(sass, "UTCHMMA tmem[") >= 12               # tcgen05.mma kind::tf32, A operand (the weights) from TMEM
+    assert _count(sass, "STTM") > 0                          # tcgen05.st of W / W_lo into tensor memory
+    assert _count(sass, "UTMALDG.2D") > 0                    # TMA boxes of W and x
+    assert _count(sass, "BRA.U.ANY") == 0
