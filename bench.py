@@ -20,7 +20,7 @@ cpu_baseline / --impl reference = the reference's CPU attention path (oracle por
          on a bounded sample (a few rows of one layer), scaled to the same metric.
 extra  = the other BASELINE.json configurations under the same clock (benchmarks/extras.py), each with its
          achieved rate, fraction of the measured peak and a max-abs-err against the CPU oracle on a bounded
-         sample: c4_int8_decode, c4_gemm_pair (+ an int8 library peak measured in the same run), c3_group,
+         sample: c4_int8_decode, c4_gemm_pair (+ an int8 library peak measured in the same run), c3_group, c2_fp32_mlp,
          c5_splitkv (one 128K-token sequence split over the N ranks: decode + merge + exchange in ONE launch, the
          stand-alone peer-memory exchange, and the NCCL all-gather form).  --no-extra skips them.
 N > 1: one process per GPU (torchrun), rows sharded across ranks, no data-path collective in the headline
@@ -382,6 +382,7 @@ def run_ours(args):
             run_extra("c4_int8_decode", extras.c4_int8_decode, dev, peak)
             run_extra("c4_gemm_pair", extras.c4_gemm_pair, dev)
             run_extra("c3_group", extras.c3_group, dev, peak)
+            run_extra("c2_fp32_mlp", extras.c2_fp32_mlp, dev, peak)
         run_extra("c5_splitkv", extras.c5_splitkv, dev, world, rank, peak)
 
     if rank != 0:

@@ -264,6 +264,60 @@ def c4_gemm_pair(dev, M=256, iters=10):
     return res
 
 
+def c2_fp32_mlp(dev, hbm_peak, M=64, iters=10):
+    """The fp32 decoder's MLP at the C2 shape (decoder/mlp.hpp:23-41): fc1 (relu) and fc2 through pa_linear_f32 on the
+    tcgen05 3xTF32 kernel, weights rotated over sets larger than L2; error against a float64 product on sampled rows,
+    in units of sum_k |x||W| (the bound the tests state is 1e-5)."""
+    from llm_decoder import _cabi
+    HID, INTER = 4096, 11008
+    lib = _cabi.lib()
+    g = torch.Generator(device=dev).manual_seed(77)
+    nw = 3  # 3 x 172 MiB per matrix (> L2)
+    W1 = [torch.randn((HID, INTER), generator=g, device=dev) / HID ** 0.5 for _ in range(nw)]
+    W2 = [torch.randn((INTER, HID), generator=g, device=dev) / INTER ** 0.5 for _ in range(nw)]
+    b1, b2 = torch.randn(INTER, generator=g, device=dev), torch.randn(HID, generator=g, device=dev)
+    x = torch.randn((M, HID), generator=g, device=dev)
+    h = torch.empty((M, INTER), device=dev)
+    y = torch.empty((M, HID), device=dev)
+    need = max(lib.pa_linear_workspace_bytes(M, HID, INTER), lib.pa_linear_workspace_bytes(M, INTER, HID), 16)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    relu, none = _cabi.ACT["relu"], _cabi.ACT[""]
+
+    def fc1(i):
+        _cabi.check(lib.pa_linear_f32(x.data_ptr(), W1[i].data_ptr(), b1.data_ptr(), M, HID, INTER, relu, h.data_ptr(),
+                                      ws.data_ptr(), need, _cabi.stream()))
+
+    def fc2(i):
+        _cabi.check(lib.pa_linear_f32(h.data_ptr(), W2[i].data_ptr(), b2.data_ptr(), M, INTER, HID, none, y.data_ptr(),
+                                      ws.data_ptr(), need, _cabi.stream()))
+
+    us_1, _ = graph_time([lambda i=i: fc1(i) for i in range(nw)], iters, dev)
+    us_2, _ = graph_time([lambda i=i: fc2(i) for i in range(nw)], iters, dev)
+    us_pair, us_pair_min = graph_time([lambda i=i: (fc1(i), fc2(i)) for i in range(nw)], iters, dev)
+    fc1(0)
+    fc2(0)
+    torch.cuda.synchronize(dev)
+    rows = torch.tensor([0, M // 2, M - 1], device=dev)
+    e1 = (x[rows].double() @ W1[0].double() + b1.double()).clamp_min(0)
+    d1 = x[rows].double().abs() @ W1[0].double().abs() + b1.double().abs()
+    err1 = float(((h[rows].double() - e1).abs() / d1).max())
+    e2 = h[rows].double() @ W2[0].double() + b2.double()
+    d2 = h[rows].double().abs() @ W2[0].double().abs() + b2.double().abs()
+    err2 = float(((y[rows].double() - e2).abs() / d2).max())
+    wbytes = 2.0 * HID * INTER * 4
+    gbs = wbytes / us_pair / 1e3
+    res = {"workload": f"C2-shape fp32 MLP, [{M} x 4096].[4096 x 11008] relu -> [{M} x 11008].[11008 x 4096], fp32 weights",
+           "kernel": "linear_tf32x3_kernel<64> (tcgen05 kind::tf32, 3-term operand split, weights through TMEM)",
+           "us": round(us_pair, 2), "us_min": round(us_pair_min, 2), "fc1_us": round(us_1, 2), "fc2_us": round(us_2, 2),
+           "achieved": round(gbs, 1), "unit": "GB/s", "peak": hbm_peak, "frac": round(gbs / hbm_peak, 4),
+           "algorithmic_bytes": int(wbytes), "bytes_note": "the two weight matrices, read once (activations < 2 %)",
+           "max_err_over_sum_abs_products": max(err1, err2), "tolerance": 1e-5, "parity_ok": max(err1, err2) <= 1e-5,
+           "oracle_sample": "3 rows of each layer against a float64 product (torch, on the device)"}
+    del W1, W2
+    torch.cuda.empty_cache()
+    return res
+
+
 def c3_group(dev, hbm_peak, iters=10, sets=3):
     import llm_decoder as ld
     groups, W, T, shared = 32, 4, 2048, 1792
