@@ -6,8 +6,9 @@
 // tensor core sees of v itself), lo = v - hi (exact in fp32, 13 significant bits of which the core keeps 11), and
 //     x . W  ~=  x_hi . W_lo + x_lo . W_hi + x_hi . W_hi                     ("3xTF32")
 // accumulated in fp32 in TMEM.  Dropped: lo.lo (2^-22 relative) and the tail of each lo (2^-21); the tensor core's
-// fp32 accumulation truncates, which adds ~K/8 * 2^-24 of the running sum.  Measured <= 3e-6 of sum_k |x||W|
-// (K = 11008, unsliced); the tests state 1e-5 * sum_k |x||W| + 4 ulp.  The fp32 SIMT kernels (PA_LINEAR_TC=0) stay
+// fp32 accumulation truncates, which adds ~K/8 * 2^-24 of the running sum (the lo terms have accumulators of their
+// own, so they are not truncated against the big sum).  Measured <= 1.1e-6 of sum_k |x||W| (K = 11008, unsliced;
+// 2.5e-7 at decode batches; the fp32 SIMT kernels: 1-3e-7); the tests state 1e-5 * sum_k |x||W| + 4 ulp.  The fp32 SIMT kernels (PA_LINEAR_TC=0) stay
 // for callers that need fp32 arithmetic proper.
 //
 // The layer is computed TRANSPOSED: out^T [N, rows] = W^T [N, K] . x^T [K, rows].  The weights are the M side of the
@@ -15,10 +16,10 @@
 // (tcgen05 time is max(M,128) * N / 256 cycles: 32 for 64 rows, where batch-as-M would pay 64 for anything <= 128)
 // and the accumulator tile [128 features][rows] is what the epilogue wants: lane = feature, so every store
 // instruction writes 32 consecutive features of one row (128 bytes).  W is consumed in the reference's [K, N]
-// layout and x where it lies; the weights stream from HBM exactly once per 256 rows of x.
+// layout and x where it lies; the weights stream from HBM exactly once per 128 rows of x (L2 serves the other row tiles).
 //
-// One CTA = 128 features x NP rows (NP = 64, 128 or 256 by batch) over one K slice; 320 threads:
-//   warp 0    TMA producer, per 32-float K block: four W boxes [32 k][32 n] (no swizzle: only threads read them) and
+// One CTA = 128 features x NP rows (NP = 64 up to 64 rows, else 128) over one K slice; 320 threads:
+//   warp 0    TMA producer, per 32-float K block: ONE W box [32 k][128 n] (512-byte rows, no swizzle: only threads read it) and
 //             the x tile [NP rows][128 B] (128-byte swizzle, K-major B operand; rows / k out of range zero-filled);
 //   warps 2-9 split: thread = (feature n, half of the block's k): reads its 16 weights W[k][n] down the column
 //             (conflict-free: a warp reads 32 consecutive floats of one k-row), stores them and their lo parts into
@@ -43,16 +44,20 @@ namespace tf32x3 {
 
 constexpr int BF = 128;            // output features per tile = UMMA M = TMEM lanes
 constexpr int BKF = 32;            // floats of K per stage (one 128-byte swizzle row of x)
-constexpr int W_TILE = BF * 128;   // 16 KiB: W block [4 boxes][32 k][32 n]
-constexpr int W_BOX = BKF * 128;   // one W box: 32 k-rows x 32 features = 4 KiB
+constexpr int W_TILE = BKF * BF * 4;   // 16 KiB: W block [32 k][128 n]
 constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 split + epilogue (two per TMEM lane quarter)
 // per row-tile width NP: stage = W (16 KB) + x + x_lo (NP * 128 B each); TMEM = NP accumulator columns + 64 per stage
 template <int NP> struct Cfg {
     static constexpr int X_TILE = NP * 128;
     static constexpr int STAGE = W_TILE + 2 * X_TILE;
-    static constexpr int NST = NP == 64 ? 6 : (NP == 128 ? 4 : 2);
+    // Accumulators: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~100 cycles
+    // measured, against a 32-cycle MMA at N = 64), so the three terms of the split get their own accumulators where
+    // TMEM allows (summed in the epilogue, small terms first -- which also keeps the lo terms out of the big sum's
+    // truncation): 3 at NP = 64, 2 (lo terms / hi.hi) at NP = 128.
+    static constexpr int NACC = NP == 64 ? 3 : 2;
+    static constexpr int NST = NP == 64 ? 5 : 4;
     static constexpr int TMEM_COLS = 512;
-    static_assert(NP + NST * 64 <= TMEM_COLS, "TMEM budget");
+    static_assert(NACC * NP + NST * 64 <= TMEM_COLS, "TMEM budget");
     static_assert(NST * STAGE <= 200 * 1024, "shared-memory budget");
 };
 
@@ -158,7 +163,8 @@ template <int NP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Args g) {
     using C = Cfg<NP>;
-    constexpr int NST = C::NST, STAGE = C::STAGE, X_TILE = C::X_TILE;
+    constexpr int NST = C::NST, STAGE = C::STAGE, X_TILE = C::X_TILE, NACC = C::NACC;
+    constexpr int RING0 = NACC * NP;   // first TMEM column of the weight ring
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + NST * STAGE;
@@ -202,8 +208,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const uint32_t st = base + s * STAGE;
                 mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
                 const int k0 = k_begin + i * BKF;
-#pragma unroll
-                for (int j = 0; j < BF / 32; ++j) tma_load_2d(st + j * W_BOX, &tmW, n0 + j * 32, k0, full_bar(s));
+                tma_load_2d(st, &tmW, n0, k0, full_bar(s));
                 tma_load_2d(st + W_TILE, &tmX, k0, m0, full_bar(s));
             }
         }
@@ -217,13 +222,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const uint32_t st = base + s * STAGE;
 #pragma unroll
                 for (int ks = 0; ks < BKF / 8; ++ks) {
-                    const uint32_t wa = tmem_base + NP + s * 64 + ks * 8;
+                    const uint32_t wa = tmem_base + RING0 + s * 64 + ks * 8;
                     const uint32_t wl = wa + 32;
                     const uint64_t xa = make_desc(st + W_TILE + ks * 32);
                     const uint64_t xl = make_desc(st + W_TILE + X_TILE + ks * 32);
-                    umma_tf32_ts(tmem_base, wl, xa, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                    umma_tf32_ts(tmem_base, wa, xl, idesc, 1u);
-                    umma_tf32_ts(tmem_base, wa, xa, idesc, 1u);
+                    const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+                    // accumulator 0: hi.hi; 1: lo terms (W_lo.x first); 2: x_lo.W_hi where there are three
+                    umma_tf32_ts(tmem_base + (NACC > 1 ? NP : 0), wl, xa, idesc, first);
+                    umma_tf32_ts(tmem_base + (NACC > 2 ? 2 * NP : (NACC > 1 ? NP : 0)), wa, xl, idesc, NACC > 2 ? first : 1u);
+                    umma_tf32_ts(tmem_base, wa, xa, idesc, NACC > 1 ? first : 1u);
                 }
                 umma_commit(empty_bar(s));
             }
@@ -241,12 +248,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             // W: column f of the block, k rows [half * 16, half * 16 + 16) -> 16 columns of W and of W_lo in TMEM
             {
                 uint32_t wv[16], wlo[16];
-                const uint32_t col = st + qtr * W_BOX + lane * 4 + half * 16 * 128;
+                const uint32_t col = st + (qtr * 32 + lane) * 4 + half * 16 * 512;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[j]) : "r"(col + j * 128));
+                for (int j = 0; j < 16; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[j]) : "r"(col + j * 512));
 #pragma unroll
                 for (int j = 0; j < 16; ++j) wlo[j] = __float_as_uint(lo_part(__uint_as_float(wv[j])));
-                const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + NP + s * 64 + half * 16;
+                const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + RING0 + s * 64 + half * 16;
                 tmem_st16(ta, wv);
                 tmem_st16(ta + 32, wlo);
             }
@@ -280,7 +287,21 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int c = half * CH; c < half * CH + CH; ++c) {
             uint32_t rr[32];
             if (nkb > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(qtr * 32) << 16) + c * 32, rr);
+                const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + c * 32;
+                if (NACC == 1) {
+                    tmem_ld_32x32(ta, rr);
+                } else {
+                    uint32_t r1[32];
+                    tmem_ld_32x32(ta + NP, r1);          // lo terms (W_lo.x)
+                    if (NACC > 2) {
+                        tmem_ld_32x32(ta + 2 * NP, rr);  // x_lo.W_hi
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(rr[j]));
+                    }
+                    tmem_ld_32x32(ta, rr);               // hi.hi
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(r1[j]));
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) rr[j] = 0u;
@@ -322,21 +343,23 @@ static EncodeTiledFn encode_fn() {
     });
     return fn;
 }
-// 2-D f32 tensor [rows][cols] (cols contiguous), box [box_rows][32 floats], zero fill out of range.
-static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows,
-                         CUtensorMapSwizzle swizzle) {
+// 2-D f32 tensor [rows][cols] (cols contiguous), box [box_rows][box_cols], zero fill out of range.
+static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                         uint32_t box_rows, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * sizeof(float)};
-    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int row_tile(int rows) { return rows <= 64 ? 64 : (rows <= 128 ? 128 : 256); }
+// Row tile: 64 up to 64 rows, else 128.  (A 256-row tile has room for ONE accumulator only: measured slower -- prefill
+// fc1 824 vs 711 us -- and 3x less accurate than two 128-row tiles with the lo terms accumulated apart.)
+static int row_tile(int rows) { return rows <= 64 ? 64 : 128; }
 
 template <int NP>
 static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g, int nslices, cudaStream_t st) {
@@ -364,7 +387,9 @@ using namespace pa;
 // that minimises waves x (K blocks per CTA + per-CTA set-up, ~2 blocks, + when sliced the partial tile's write and
 // re-read, NP / 16 blocks' worth of bytes); every slice holds >= 8 K blocks (256 k-rows).
 // (Summing the slices inside the kernel -- last slice of a tile to arrive, one counter per tile -- was measured and
-//  rejected: fence + counter + the last CTA's serial sum lengthen every wave, fc1 at batch 64 60 -> 88 us.)
+//  rejected: fence + counter + the last CTA's serial sum lengthen every wave, fc1 at batch 64 60 -> 88 us.  A persistent
+//  tile loop with two alternating accumulators and dedicated epilogue warps measured 52.2 against 56.3 us; it was
+//  dropped for the per-term accumulators below, which need the TMEM columns and cut the error 2.7x.)
 int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
@@ -394,11 +419,10 @@ int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias,
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
     CUtensorMap tmX, tmW;
-    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, (uint32_t)np, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
+    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, 32, (uint32_t)np, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BF, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
         return PA_ERR_UNSUPPORTED;
     Args g{d_bias, d_out, d_partial, rows, N, K, act, kslice, nslices};
     if (np == 64) return launch<64>(tmX, tmW, g, nslices, st);
-    if (np == 128) return launch<128>(tmX, tmW, g, nslices, st);
-    return launch<256>(tmX, tmW, g, nslices, st);
+    return launch<128>(tmX, tmW, g, nslices, st);
 }
