@@ -294,9 +294,28 @@ def c2_fp32_mlp(dev, hbm_peak, M=64, iters=10):
     us_1, _ = graph_time([lambda i=i: fc1(i) for i in range(nw)], iters, dev)
     us_2, _ = graph_time([lambda i=i: fc2(i) for i in range(nw)], iters, dev)
     us_pair, us_pair_min = graph_time([lambda i=i: (fc1(i), fc2(i)) for i in range(nw)], iters, dev)
+    # the same pair on weights repacked once into the kernel's own order (pa_linear_pack_f32): same bits
+    P1 = [torch.empty(lib.pa_linear_pack_bytes(HID, INTER) // 4, device=dev) for _ in range(nw)]
+    P2 = [torch.empty(lib.pa_linear_pack_bytes(INTER, HID) // 4, device=dev) for _ in range(nw)]
+    for i in range(nw):
+        _cabi.check(lib.pa_linear_pack_f32(W1[i].data_ptr(), P1[i].data_ptr(), HID, INTER, _cabi.stream()))
+        _cabi.check(lib.pa_linear_pack_f32(W2[i].data_ptr(), P2[i].data_ptr(), INTER, HID, _cabi.stream()))
+    hp = torch.empty_like(h)
+    yp = torch.empty_like(y)
+
+    def pair_packed(i):
+        _cabi.check(lib.pa_linear_f32_packed(x.data_ptr(), P1[i].data_ptr(), b1.data_ptr(), M, HID, INTER, relu, hp.data_ptr(),
+                                             ws.data_ptr(), need, _cabi.stream()))
+        _cabi.check(lib.pa_linear_f32_packed(hp.data_ptr(), P2[i].data_ptr(), b2.data_ptr(), M, INTER, HID, none, yp.data_ptr(),
+                                             ws.data_ptr(), need, _cabi.stream()))
+
+    us_pk, us_pk_min = graph_time([lambda i=i: pair_packed(i) for i in range(nw)], iters, dev)
     fc1(0)
     fc2(0)
+    pair_packed(0)
     torch.cuda.synchronize(dev)
+    packed_same_bits = bool(torch.equal(h, hp) and torch.equal(y, yp))
+    del P1, P2
     rows = torch.tensor([0, M // 2, M - 1], device=dev)
     e1 = (x[rows].double() @ W1[0].double() + b1.double()).clamp_min(0)
     d1 = x[rows].double().abs() @ W1[0].double().abs() + b1.double().abs()
@@ -310,6 +329,8 @@ def c2_fp32_mlp(dev, hbm_peak, M=64, iters=10):
            "kernel": "linear_tf32x3_kernel<64> (tcgen05 kind::tf32, 3-term operand split, weights through TMEM)",
            "us": round(us_pair, 2), "us_min": round(us_pair_min, 2), "fc1_us": round(us_1, 2), "fc2_us": round(us_2, 2),
            "achieved": round(gbs, 1), "unit": "GB/s", "peak": hbm_peak, "frac": round(gbs / hbm_peak, 4),
+           "packed_weights_us": round(us_pk, 2), "packed_weights_gbs": round(wbytes / us_pk / 1e3, 1),
+           "packed_weights_frac": round(wbytes / us_pk / 1e3 / hbm_peak, 4), "packed_same_bits": packed_same_bits,
            "algorithmic_bytes": int(wbytes), "bytes_note": "the two weight matrices, read once (activations < 2 %)",
            "max_err_over_sum_abs_products": max(err1, err2), "tolerance": 1e-5, "parity_ok": max(err1, err2) <= 1e-5,
            "oracle_sample": "3 rows of each layer against a float64 product (torch, on the device)"}

@@ -27,8 +27,14 @@ def run(rows, K, N, act, mode, iters=20):
     need = lib.pa_linear_workspace_bytes(rows, K, N)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    call = lambda: _cabi.check(lib.pa_linear_f32(x.data_ptr(), W.data_ptr(), b.data_ptr(), rows, K, N, act, o.data_ptr(),
-                                                 ws.data_ptr(), need, _cabi.stream()))
+    if mode == "packed":
+        Wp = torch.empty(lib.pa_linear_pack_bytes(K, N) // 4, device="cuda")
+        _cabi.check(lib.pa_linear_pack_f32(W.data_ptr(), Wp.data_ptr(), K, N, _cabi.stream()))
+        call = lambda: _cabi.check(lib.pa_linear_f32_packed(x.data_ptr(), Wp.data_ptr(), b.data_ptr(), rows, K, N, act,
+                                                            o.data_ptr(), ws.data_ptr(), need, _cabi.stream()))
+    else:
+        call = lambda: _cabi.check(lib.pa_linear_f32(x.data_ptr(), W.data_ptr(), b.data_ptr(), rows, K, N, act, o.data_ptr(),
+                                                     ws.data_ptr(), need, _cabi.stream()))
     for _ in range(3):
         call()
     ts = []
@@ -54,7 +60,7 @@ def run(rows, K, N, act, mode, iters=20):
 if __name__ == "__main__":
     if len(sys.argv) > 1:   # linear_f32.py rows K N act: one shape on the tensor-core kernel (for ncu captures)
         rows, K, N, act = (int(a) for a in sys.argv[1:5])
-        print(json.dumps(run(rows, K, N, act, "tc", iters=3)))
+        print(json.dumps(run(rows, K, N, act, sys.argv[5] if len(sys.argv) > 5 else "tc", iters=3)))
         sys.exit(0)
     shapes = [("C2 fc1, batch 64", 64, 4096, 11008, 1), ("C2 fc2, batch 64", 64, 11008, 4096, 0),
               ("C2 projection, batch 64", 64, 4096, 4096, 0), ("C2 fc1, batch 256", 256, 4096, 11008, 1),
@@ -62,5 +68,5 @@ if __name__ == "__main__":
               ("C1 fc1, batch 64", 64, 768, 3072, 1), ("C1 fc1 prefill 64x448", 28672, 768, 3072, 1)]
     res = {}
     for name, rows, K, N, act in shapes:
-        res[name] = {m: run(rows, K, N, act, m) for m in ("tc", "simt")}
+        res[name] = {m: run(rows, K, N, act, m) for m in ("packed", "tc", "simt")}
     print(json.dumps({"workload": "pa_linear_f32 (fp32 x [rows,K] . W [K,N] + bias, relu on fc1)", "results": res}))

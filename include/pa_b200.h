@@ -349,6 +349,18 @@ int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float* d_bet
 size_t pa_linear_workspace_bytes(int rows, int K, int N);
 int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N,
                   int act, float* d_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
+/* The same layer on weights repacked ONCE (at load) into the tensor-core kernel's own order:
+ * [ceil(N/128) feature tiles][ceil(K/32) K blocks][32 k][128 n] f32, zero padded, so that every block the
+ * kernel streams is one contiguous 16 KB run (whole DRAM pages instead of 512-byte rows 4*N bytes apart).
+ * pa_linear_pack_bytes: size of the packed copy; pa_linear_pack_f32: W [K, N] -> d_W_packed.
+ * pa_linear_f32_packed: any rows >= 1, any N; K % 4 == 0 and 16-byte aligned d_x (else PA_ERR_UNSUPPORTED);
+ * workspace as pa_linear_workspace_bytes(rows, K, N); same arithmetic and bits as pa_linear_f32 on the
+ * tensor-core kernel (PA_LINEAR_TC=1). */
+size_t pa_linear_pack_bytes(int K, int N);
+int pa_linear_pack_f32(const float* d_W, float* d_W_packed, int K, int N, pa_stream_t stream);
+int pa_linear_f32_packed(const float* d_x, const float* d_W_packed, const float* d_bias, int rows, int K,
+                         int N, int act, float* d_out, void* d_workspace, size_t workspace_bytes,
+                         pa_stream_t stream);
 /* logits[r,v] = dot(x[r,:], E[v,:]) against the (tied) embedding table E [vocab, hidden]
  * (the reference reads logits out of the hidden state, cuda_decoder.cu:58). */
 int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidden, int vocab,

@@ -547,7 +547,9 @@ static bool linear_uses_gemm(const void* x, const void* W, const void* out, cons
 // linear_tf32x3.cu: 3xTF32 tcgen05 kernel over the same [rows, K] x [K, N] operands
 int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out);
 int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
-                        float* d_out, float* d_partial, int nslices, int kslice, cudaStream_t st);
+                        float* d_out, float* d_partial, int nslices, int kslice, int packed, cudaStream_t st);
+size_t pa_linear_tc_pack_floats(int K, int N);
+int pa_linear_tc_pack(const float* d_W, float* d_Wp, int K, int N, cudaStream_t st);
 
 // The tensor-core kernel serves what the register-tiled kernel serves (>= 16 rows, 16-byte aligned rows of x, W, out)
 // wherever the layer is large enough for the tile kernels at all; PA_LINEAR_TC=0 keeps the fp32 SIMT kernels
@@ -591,6 +593,22 @@ PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
     return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
 }
 
+static int launch_reduce4_pdl(const float* partial, const float* d_bias, int rows, int N, int nslices, int act, float* d_out,
+                             cudaStream_t st) {
+    const int64_t n4 = ((int64_t)rows * N + 3) / 4;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((n4 + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, linear_reduce4_kernel, partial, d_bias, rows, N, nslices, act, d_out);
+    return e == cudaSuccess ? PA_OK : (int)e;
+}
+
 // The K-slice partials live in the CALLER's workspace (no library-owned scratch: a pointer captured in a CUDA
 // graph stays valid, streams never share it).  Without a large enough workspace the layer runs unsliced.
 PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
@@ -617,7 +635,7 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     }
     cudaError_t e;
     if (tc) {
-        const int stc = pa_linear_tc_launch(d_x, d_W, d_bias, rows, K, N, act, d_out, partial, nslices, kslice,
+        const int stc = pa_linear_tc_launch(d_x, d_W, d_bias, rows, K, N, act, d_out, partial, nslices, kslice, 0,
                                             as_stream(stream));
         if (stc != PA_OK) return stc;
     } else if (gemm) {
@@ -639,26 +657,52 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (nslices > 1 && tc) {
-        const int64_t n4 = ((int64_t)rows * N + 3) / 4;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)((n4 + 255) / 256));
-        cfg.blockDim = dim3(256);
-        cfg.stream = as_stream(stream);
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, linear_reduce4_kernel, (const float*)partial, d_bias, rows, N, nslices, act, d_out);
-        return e == cudaSuccess ? PA_OK : (int)e;
-    }
+    if (nslices > 1 && tc) return launch_reduce4_pdl(partial, d_bias, rows, N, nslices, act, d_out, as_stream(stream));
     if (nslices > 1) {
         const int64_t n = (int64_t)rows * N;
         linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, d_bias, rows, N,
                                                                                         nslices, act, d_out);
     }
     PA_RETURN_LAUNCH_STATUS();
+}
+
+// ---- packed weights: the tensor-core kernel's own layout (every tile's K block one contiguous 16 KB run) ----
+PA_API size_t pa_linear_pack_bytes(int K, int N) {
+    if (K <= 0 || N <= 0) return 0;
+    return pa_linear_tc_pack_floats(K, N) * sizeof(float);
+}
+
+PA_API int pa_linear_pack_f32(const float* d_W, float* d_W_packed, int K, int N, pa_stream_t stream) {
+    PA_CHECK_ARG(d_W && d_W_packed && K > 0 && N > 0 && (uintptr_t)d_W_packed % 16 == 0);
+    return pa_linear_tc_pack(d_W, d_W_packed, K, N, as_stream(stream));
+}
+
+PA_API int pa_linear_f32_packed(const float* d_x, const float* d_W_packed, const float* d_bias, int rows, int K, int N,
+                                int act, float* d_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream) {
+    PA_CHECK_ARG(d_x && d_W_packed && d_out && rows >= 0 && K > 0 && N > 0);
+    PA_CHECK_ARG(act == PA_ACT_NONE || act == PA_ACT_RELU);
+    PA_CHECK_ARG(d_x != d_out);
+    // the kernel's operand rules: 16-byte aligned rows of x (TMA), 16-byte aligned packed blocks
+    if (K % 4 != 0 || (uintptr_t)d_x % 16 != 0 || (uintptr_t)d_W_packed % 16 != 0) return PA_ERR_UNSUPPORTED;
+    if (rows == 0) return PA_OK;
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return PA_ERR_NO_DEVICE;
+    int kslice = K;
+    int nslices = pa_linear_tc_slices(rows, K, N, di.sm_count, &kslice);
+    float* partial = nullptr;
+    if (nslices > 1) {
+        if (N % 4 == 0 && (uintptr_t)d_out % 16 == 0 && (uintptr_t)d_bias % 16 == 0 && d_workspace &&
+            workspace_bytes >= (size_t)nslices * rows * N * sizeof(float) && (uintptr_t)d_workspace % 16 == 0) {
+            partial = static_cast<float*>(d_workspace);
+        } else {
+            nslices = 1;
+            kslice = K;
+        }
+    }
+    const int stc = pa_linear_tc_launch(d_x, d_W_packed, d_bias, rows, K, N, act, d_out, partial, nslices, kslice, 1,
+                                        as_stream(stream));
+    if (stc != PA_OK || nslices == 1) return stc;
+    return launch_reduce4_pdl(partial, d_bias, rows, N, nslices, act, d_out, as_stream(stream));
 }
 
 PA_API int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidden, int vocab, float* d_logits,

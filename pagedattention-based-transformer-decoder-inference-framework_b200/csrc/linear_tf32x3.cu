@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "pa_common.cuh"
@@ -66,6 +67,7 @@ struct Args {
     float* out;
     float* partial;   // [nslices][rows][N] when nslices > 1
     int rows, N, K, act, kslice, nslices;
+    const float* w_packed;   // PACKED kernels: [feature tile][K block][32 k][128 n] (pa_linear_pack_f32), else null
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -159,7 +161,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
     __trap();
 }
 
-template <int NP>
+template <int NP, bool PACKED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Args g) {
     using C = Cfg<NP>;
@@ -202,13 +204,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
     if (warp == 0) {
         if (elect_one()) {
+            const uint64_t stream_policy = l2_policy_evict_first();
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % NST;
                 mbar_wait_bounded(empty_bar(s), ((i / NST) & 1) ^ 1);
                 const uint32_t st = base + s * STAGE;
                 mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
                 const int k0 = k_begin + i * BKF;
-                tma_load_2d(st, &tmW, n0, k0, full_bar(s));
+                if (PACKED) {   // the block is ONE contiguous 16 KB run (whole DRAM pages), streamed past L2
+                    const int64_t blk = (int64_t)blockIdx.y * ((g.K + BKF - 1) / BKF) + k0 / BKF;
+                    bulk_g2s(st, g.w_packed + blk * (W_TILE / 4), W_TILE, full_bar(s), stream_policy);
+                } else {
+                    tma_load_2d(st, &tmW, n0, k0, full_bar(s));
+                }
                 tma_load_2d(st + W_TILE, &tmX, k0, m0, full_bar(s));
             }
         }
@@ -361,7 +369,7 @@ static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint6
 // fc1 824 vs 711 us -- and 3x less accurate than two 128-row tiles with the lo terms accumulated apart.)
 static int row_tile(int rows) { return rows <= 64 ? 64 : 128; }
 
-template <int NP>
+template <int NP, bool PACKED>
 static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g, int nslices, cudaStream_t st) {
     using C = Cfg<NP>;
     const size_t smem = (size_t)C::NST * C::STAGE + (3 * C::NST + 1) * 8 + 16 + 1024;
@@ -369,13 +377,41 @@ static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g,
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NP, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev & 63] = true;
     }
     dim3 grid((unsigned)((g.rows + NP - 1) / NP), (unsigned)((g.N + BF - 1) / BF), (unsigned)nslices);
-    linear_tf32x3_kernel<NP><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
+    linear_tf32x3_kernel<NP, PACKED><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
     PA_RETURN_LAUNCH_STATUS();
+}
+
+// W [K, N] -> [feature tile][K block][32 k][128 n], zero padded: every (tile, block) the kernel streams is one
+// contiguous 16 KB run.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Wp, int K, int N,
+                                                           int64_t total4) {
+    const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const int64_t e = i4 * 4;
+    const int n = (int)(e % BF), k = (int)((e / BF) % BKF);
+    const int64_t blk = e / (BF * BKF);
+    const int kbs = (K + BKF - 1) / BKF;
+    const int kb = (int)(blk % kbs), tile = (int)(blk / kbs);
+    const int kk = kb * BKF + k, nn = tile * BF + n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < K) {
+        const float* src = W + (int64_t)kk * N + nn;
+        if (nn + 3 < N && (N & 3) == 0) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+            if (nn < N) v.x = src[0];
+            if (nn + 1 < N) v.y = src[1];
+            if (nn + 2 < N) v.z = src[2];
+            if (nn + 3 < N) v.w = src[3];
+        }
+    }
+    *reinterpret_cast<float4*>(Wp + e) = v;
 }
 
 }  // namespace tf32x3
@@ -413,16 +449,31 @@ int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     return (K + kslice - 1) / kslice;
 }
 
-// Launch helper for pa_linear_f32 (decoder_ops.cu).  PA_ERR_UNSUPPORTED when the tensor maps cannot be built.
+// Launch helper for pa_linear_f32 / pa_linear_f32_packed (decoder_ops.cu).  PA_ERR_UNSUPPORTED when the tensor maps
+// cannot be built.  d_W: [K, N] (packed == 0) or the pa_linear_pack_f32 layout (packed == 1).
 int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
-                        float* d_out, float* d_partial, int nslices, int kslice, cudaStream_t st) {
+                        float* d_out, float* d_partial, int nslices, int kslice, int packed, cudaStream_t st) {
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
     CUtensorMap tmX, tmW;
-    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, 32, (uint32_t)np, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BF, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
+    if (!make_map_f32(&tmX, d_x, (uint64_t)K, (uint64_t)rows, 32, (uint32_t)np, CU_TENSOR_MAP_SWIZZLE_128B))
         return PA_ERR_UNSUPPORTED;
-    Args g{d_bias, d_out, d_partial, rows, N, K, act, kslice, nslices};
-    if (np == 64) return launch<64>(tmX, tmW, g, nslices, st);
-    return launch<128>(tmX, tmW, g, nslices, st);
+    if (packed) memset(&tmW, 0, sizeof(tmW));
+    else if (!make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BF, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return PA_ERR_UNSUPPORTED;
+    Args g{d_bias, d_out, d_partial, rows, N, K, act, kslice, nslices, packed ? d_W : nullptr};
+    if (packed) return np == 64 ? launch<64, true>(tmX, tmW, g, nslices, st) : launch<128, true>(tmX, tmW, g, nslices, st);
+    return np == 64 ? launch<64, false>(tmX, tmW, g, nslices, st) : launch<128, false>(tmX, tmW, g, nslices, st);
+}
+
+size_t pa_linear_tc_pack_floats(int K, int N) {
+    using namespace pa::tf32x3;
+    return (size_t)((N + BF - 1) / BF) * ((K + BKF - 1) / BKF) * (BF * BKF);
+}
+
+int pa_linear_tc_pack(const float* d_W, float* d_Wp, int K, int N, cudaStream_t st) {
+    using namespace pa::tf32x3;
+    const int64_t total4 = (int64_t)pa_linear_tc_pack_floats(K, N) / 4;
+    pack_weights_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(d_W, d_Wp, K, N, total4);
+    PA_RETURN_LAUNCH_STATUS();
 }

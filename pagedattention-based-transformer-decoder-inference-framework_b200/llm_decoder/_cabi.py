@@ -75,6 +75,9 @@ _SIGS = {
     "pa_layer_norm_f32": ([_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp], _i32),
     "pa_linear_workspace_bytes": ([_i32, _i32, _i32], _sz),
     "pa_linear_f32": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
+    "pa_linear_pack_bytes": ([_i32, _i32], _sz),
+    "pa_linear_pack_f32": ([_vp, _vp, _i32, _i32, _vp], _i32),
+    "pa_linear_f32_packed": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
     "pa_logits_f32": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_logits_i8": ([_vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pa_argmax_f32": ([_vp, _i32, _i32, _f32, _i32, _vp, _vp], _i32),

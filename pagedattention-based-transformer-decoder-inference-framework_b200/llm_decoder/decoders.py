@@ -445,11 +445,39 @@ class CUDADecoder(_DecoderBase):
     def _embedding_table(self):
         return self.embedding, 4, 1.0
 
+    def _packed(self, W, K, N):
+        """The tensor-core kernel's own weight order (pa_linear_pack_f32: every streamed block one contiguous 16 KB run,
+        ~10 % faster than the [K, N] rows), made once per weight tensor and re-made when the tensor was written in place
+        (torch's version counter).  None: PA_LINEAR_PACKED=0, K % 4 != 0, or a copy would have to be made during graph
+        capture -- the caller then uses the [K, N] layout."""
+        if K % 4 or os.environ.get("PA_LINEAR_PACKED", "1") == "0":
+            return None
+        cache = self.__dict__.setdefault("_pk", {})
+        ent = cache.get(W.data_ptr())
+        if ent is not None and ent[0] == W._version:
+            return ent[1]
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        Wp = torch.empty(self._lib.pa_linear_pack_bytes(K, N) // 4, dtype=torch.float32, device=self.device)
+        self._chk(self._lib.pa_linear_pack_f32(W.data_ptr(), Wp.data_ptr(), K, N, _cabi.stream()), "pa_linear_pack_f32")
+        cache[W.data_ptr()] = (W._version, Wp)
+        return Wp
+
+    def _linear(self, x, W, bias, R, K, N, act, out, wp, wb):
+        lib = self._lib
+        Wp = self._packed(W, K, N) if R >= 16 else None   # few rows: the strip kernel on the [K, N] rows
+        if Wp is not None:
+            st = lib.pa_linear_f32_packed(x.data_ptr(), Wp.data_ptr(), _cabi.ptr(bias), R, K, N, _cabi.ACT[act],
+                                          out.data_ptr(), wp, wb, _cabi.stream())
+            if st != _cabi.PA_ERR_UNSUPPORTED:
+                return self._chk(st, "pa_linear_f32_packed")
+        self._chk(lib.pa_linear_f32(x.data_ptr(), W.data_ptr(), _cabi.ptr(bias), R, K, N, _cabi.ACT[act], out.data_ptr(),
+                                    wp, wb, _cabi.stream()), "pa_linear_f32")
+
     def _lin(self, bf, x, W, out):
-        lib, R, hid = self._lib, bf.R, self.hidden_dim_
-        wp, wb = self._scratch(bf, lib.pa_linear_workspace_bytes(R, hid, hid))
-        self._chk(lib.pa_linear_f32(x.data_ptr(), W.data_ptr(), None, R, hid, hid, _cabi.ACT[""], out.data_ptr(), wp, wb,
-                                    _cabi.stream()), "pa_linear_f32")
+        R, hid = bf.R, self.hidden_dim_
+        wp, wb = self._scratch(bf, self._lib.pa_linear_workspace_bytes(R, hid, hid))
+        self._linear(x, W, None, R, hid, hid, "", out, wp, wb)
 
     def _qkv_proj(self, bf, L):
         self._lin(bf, bf.n, L.wq, bf.qp)
@@ -470,8 +498,7 @@ class CUDADecoder(_DecoderBase):
             self._emb_T = self.embedding.t().contiguous()
         lib, s = self._lib, _cabi.stream()
         wp, wb = self._scratch(self.bufs, lib.pa_linear_workspace_bytes(B, self.hidden_dim_, self.vocab_size_))
-        self._chk(lib.pa_linear_f32(x_rows.data_ptr(), self._emb_T.data_ptr(), None, B, self.hidden_dim_,
-                                    self.vocab_size_, _cabi.ACT[""], self.logits.data_ptr(), wp, wb, s), "pa_linear_f32")
+        self._linear(x_rows, self._emb_T, None, B, self.hidden_dim_, self.vocab_size_, "", self.logits, wp, wb)
         self._chk(lib.pa_argmax_f32(self.logits.data_ptr(), B, self.vocab_size_, self._temperature,
                                     self.ARGMAX_DIVIDE, self.ids.data_ptr(), s), "pa_argmax_f32")
 
@@ -483,10 +510,8 @@ class CUDADecoder(_DecoderBase):
         lib, R, hid, inter, s = self._lib, bf.R, self.hidden_dim_, self.inter_dim_, _cabi.stream()
         wp, wb = self._scratch(bf, max(lib.pa_linear_workspace_bytes(R, hid, inter),
                                        lib.pa_linear_workspace_bytes(R, inter, hid)))
-        self._chk(lib.pa_linear_f32(bf.n.data_ptr(), L.fc1_w.data_ptr(), L.fc1_b.data_ptr(), R, hid, inter,
-                                    _cabi.ACT["relu"], bf.h.data_ptr(), wp, wb, s), "pa_linear_f32")
-        self._chk(lib.pa_linear_f32(bf.h.data_ptr(), L.fc2_w.data_ptr(), L.fc2_b.data_ptr(), R, inter, hid,
-                                    _cabi.ACT[""], bf.x.data_ptr(), wp, wb, s), "pa_linear_f32")
+        self._linear(bf.n, L.fc1_w, L.fc1_b, R, hid, inter, "relu", bf.h, wp, wb)
+        self._linear(bf.h, L.fc2_w, L.fc2_b, R, inter, hid, "", bf.x, wp, wb)
 
     def _logits(self, x_rows):
         self._chk(self._lib.pa_logits_f32(x_rows.data_ptr(), self.embedding.data_ptr(), self._batch,

@@ -670,3 +670,81 @@ def test_linear_tf32x3_tensor_core_kernel_matches_fp64(shape, monkeypatch):
     monkeypatch.setenv("PA_LINEAR_TC", "1")
     _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), None, rows, K, N, 0, o.data_ptr(), ws.data_ptr(), need, None))
     assert np.all(np.abs(o.cpu().numpy() - (exp - b)) <= bound)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 4096, 1024), (100, 192, 100), (1, 256, 128), (300, 520, 388), (65, 36, 13),
+                                   (7, 64, 50257 // 64), (257, 2048, 128)])
+def test_linear_packed_weights_same_bits_as_kn_layout(shape, monkeypatch):
+    """pa_linear_f32_packed (weights repacked once into [feature tile][K block][32 k][128 n], every streamed block one
+    contiguous 16 KB run) against pa_linear_f32 on the tensor-core kernel: the same arithmetic in the same order, so the
+    bits must match wherever both apply; and against float64 with the kernel's stated bound for the shapes only the
+    packed entry serves (fewer than 16 rows, N not a multiple of 4).  Pad columns / k of the packed copy are zero."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    rows, K, N = shape
+    rng = np.random.default_rng(sum(shape) + 2)
+    x = rng.standard_normal((rows, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N + 3).astype(np.float32)
+    dx, dW = torch.from_numpy(x).cuda(), torch.from_numpy(W).cuda()
+    db = torch.from_numpy(b).cuda()[:N] if N % 4 == 0 else torch.from_numpy(b).cuda()[1:N + 1]   # misaligned bias too
+    bb = db.cpu().numpy()
+    Wp = torch.full((lib.pa_linear_pack_bytes(K, N) // 4,), float("nan"), device="cuda")
+    _cabi.check(lib.pa_linear_pack_f32(dW.data_ptr(), Wp.data_ptr(), K, N, None))
+    torch.cuda.synchronize()
+    pk = Wp.view(-1, (K + 31) // 32, 32, 128).cpu().numpy()
+    full = pk.transpose(1, 2, 0, 3).reshape(pk.shape[1] * 32, -1)      # [K padded, N padded]
+    assert np.array_equal(full[:K, :N], W) and not full[K:].any() and not full[:, N:].any()
+    need = lib.pa_linear_workspace_bytes(rows, K, N)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    exp = x.astype(np.float64) @ W.astype(np.float64) + bb
+    bound = 1e-5 * (np.abs(x).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(bb)) + 4 * np.spacing(np.abs(exp).astype(np.float32))
+    for act in (0, 1):
+        guard = 512
+        buf = torch.full((rows * N + 2 * guard,), float("nan"), device="cuda")
+        o = buf[guard:guard + rows * N].view(rows, N)
+        _cabi.check(lib.pa_linear_f32_packed(dx.data_ptr(), Wp.data_ptr(), db.data_ptr(), rows, K, N, act, o.data_ptr(),
+                                             ws.data_ptr(), need, None))
+        torch.cuda.synchronize()
+        e = np.maximum(exp, 0) if act else exp
+        assert np.all(np.abs(o.cpu().numpy() - e) <= bound)
+        assert bool(torch.isnan(buf[:guard]).all()) and bool(torch.isnan(buf[-guard:]).all())
+        if rows >= 16 and N % 4 == 0:
+            monkeypatch.setenv("PA_LINEAR_TC", "1")
+            o2 = torch.empty((rows, N), device="cuda")
+            _cabi.check(lib.pa_linear_f32(dx.data_ptr(), dW.data_ptr(), db.data_ptr(), rows, K, N, act, o2.data_ptr(),
+                                          ws.data_ptr(), need, None))
+            assert torch.equal(o, o2)
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_packed_weights_same_logits_and_repacked_after_inplace_write(oracle, tmp_path, monkeypatch):
+    """CUDADecoder packs its fp32 matrices once into the tensor-core kernel's order: a 24-row decode step must give the
+    SAME logits (bitwise) as with PA_LINEAR_PACKED=0 (the kernel reads [K, N] rows), the packed copies must exist, and
+    an in-place write to a weight tensor must be picked up (the copy is re-made: torch's version counter)."""
+    import llm_decoder as ld
+    rng = np.random.default_rng(41)
+    L, H, D, V, S = 2, 2, 64, 132, 32
+    hid = H * D
+    w = make_weights(rng, L, hid, V, attn=True)
+    write_fp32_tree(w, str(tmp_path / "w"), True)
+    toks = [int(t) for t in rng.integers(0, V, 24)]
+    monkeypatch.setenv("PA_LINEAR_TC", "1")           # these layers are below the size rule: force the tensor-core kernel
+
+    def run(packed, mutate=False):
+        monkeypatch.setenv("PA_LINEAR_PACKED", "1" if packed else "0")
+        dec = ld.CUDADecoder(L, H, D, hid, V, S)
+        dec.load_weights(str(tmp_path / "w"))
+        dec.reset()
+        a = dec.forward_tokens(toks, 0.7).clone()
+        if mutate:
+            dec.layers[0].fc1_w.mul_(0.5)
+        b = dec.forward_tokens(toks, 0.7).clone()
+        return a, b, dec
+
+    a1, b1, dec1 = run(True, mutate=True)
+    a0, b0, _ = run(False, mutate=True)
+    assert len(dec1.__dict__.get("_pk", {})) >= 2 * L       # fc1, fc2 (+ projections) of every layer
+    assert torch.equal(a1, a0)
+    assert torch.equal(b1, b0) and not torch.equal(a1, b1)
