@@ -441,6 +441,7 @@ class CUDADecoder(_DecoderBase):
                                                        f"attn_{nm}").reshape(hid, hid)))
         self._graph = None
         self._emb_T = None
+        self._pk = {}   # packed copies belong to the replaced tensors
 
     def _embedding_table(self):
         return self.embedding, 4, 1.0
@@ -454,13 +455,13 @@ class CUDADecoder(_DecoderBase):
             return None
         cache = self.__dict__.setdefault("_pk", {})
         ent = cache.get(W.data_ptr())
-        if ent is not None and ent[0] == W._version:
-            return ent[1]
+        if ent is not None and ent[0] is W and ent[1] == W._version:   # (the entry keeps W alive: its address is not reused)
+            return ent[2]
         if torch.cuda.is_current_stream_capturing():
             return None
         Wp = torch.empty(self._lib.pa_linear_pack_bytes(K, N) // 4, dtype=torch.float32, device=self.device)
         self._chk(self._lib.pa_linear_pack_f32(W.data_ptr(), Wp.data_ptr(), K, N, _cabi.stream()), "pa_linear_pack_f32")
-        cache[W.data_ptr()] = (W._version, Wp)
+        cache[W.data_ptr()] = (W, W._version, Wp)
         return Wp
 
     def _linear(self, x, W, bias, R, K, N, act, out, wp, wb):
