@@ -470,7 +470,8 @@ def c5_splitkv(dev, world, rank, hbm_peak, ctx=131072, iters=30):
     ach = kv_bytes_rank / us / 1e3
     res = {"workload": f"C5: 1 sequence x {ctx} ctx, {H} heads, D=128, fp16 KV pages split over {world} GPU(s)",
            "kernel": "paged_decode_direct_kernel<128,f16> + splitkv_merge_exchange_kernel chained by programmatic dependent "
-                     "launch (<= 0.5 GB of K/V per GPU); paged_decode_overlap_kernel<...,TAIL> in one launch above that",
+                     "launch (<= 0.5 GB of K/V per GPU); above that paged_decode_overlap_kernel + combine_chunks_kernel (PDL) whose emit "
+                     "step sends / receives / combines the row",
            "n_gpus": world, "kv_bytes_per_gpu": kv_bytes_rank, "payload_bytes_per_rank": H * (D + 2) * 4,
            "us": round(us, 2), "us_min": round(res_us["fused"][1], 2),
            "us_by_form": {k: round(v[0], 2) for k, v in res_us.items()},

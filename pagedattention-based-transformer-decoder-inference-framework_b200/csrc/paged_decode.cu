@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(NW * 32, 1) paged_decode_overlap_kernel(const 
         }
         // Chunk done: warp-level merge, then lanes 0..7 write their dim chunks.
         warp_merge<D, KV>(acc);
-        const bool final_row = (nc == 1) && !(TAIL && a.xch_peers);
+        const bool final_row = (nc == 1) && !a.xch_peers;  // across GPUs every row goes through the workspace
         if (final_row) {
             if (lane < 8) {
                 if (!a.part_m) {
@@ -948,6 +948,11 @@ __global__ void __launch_bounds__(256) combine_chunks_kernel(const DecodeArgs a,
     }
     if (skip || wsub != 0) return;
     // ---- emit: this warp holds the merged row (M log2-domain, L, O[VEC] for dims lane*VEC..) ----
+    if (a.xch_peers) {  // split-KV across GPUs behind the streaming kernel: send this GPU's row, combine the peers' rows
+        xchg::send_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, O, M * kLn2, L, lane);
+        xchg::recv_row<D>(a.xch_peers, a.xch_epochs, a.xch_rank, a.xch_world, nrows, row, a.out, a.lse_out, a.xch_status, lane);
+        return;
+    }
     if (a.part_m) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) a.part_o[row * D + lane * VEC + e] = O[e];
@@ -1570,7 +1575,14 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     using C = Cfg<D, KV>;
     const int G = di.sm_count;
     constexpr int NWk = OvCfg<D, KV>::NW;
-    const int cu = choose_cu(rows, max_units, di.sm_count, NWk, a.xch_peers != nullptr);
+    // Across GPUs above the grid kernel's size range: the PLAIN streaming kernel, then the chunk-merge kernel chained by
+    // programmatic dependent launch, whose emit step sends / receives / combines the row.  (r02 first merged the rows
+    // inside a TAIL instance of the streaming kernel: at 2 GPUs x 1 GB the fence + counter per finished chunk cost 9 us
+    // on top of the 8 us exchange -- 193.9 us against 183.4 for partial + stand-alone exchange kernel.
+    // PA_DECODE_MERGE_KERNEL=0 still selects that form.)
+    const char* merge_env = getenv("PA_DECODE_MERGE_KERNEL");
+    const bool xch_tail = a.xch_peers && merge_env && atoi(merge_env) == 0;
+    const int cu = choose_cu(rows, max_units, di.sm_count, NWk, xch_tail);
     const size_t prefix_bytes = a.ctx_lens ? (size_t)(a.B + 1) * sizeof(int) : 0;
     const size_t smem = (size_t)NWk * S * C::STAGE_BYTES + (size_t)NWk * S * (8 + 4) + 8 +
                         (size_t)NWk * 16 * sizeof(int64_t) + prefix_bytes;
@@ -1582,13 +1594,13 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     // step) and across GPUs (the exchange needs it); the separate merge kernel otherwise.
     // PA_DECODE_MERGE_KERNEL=0 / 1 forces in-kernel / separate merging where both are possible.
     const bool static_chunks = rows * (int64_t)((max_units + cu - 1) / cu) <= (int64_t)G * NWk;
-    const char* merge_env = getenv("PA_DECODE_MERGE_KERNEL");
-    const bool fused_merge = a.xch_peers || (merge_env ? atoi(merge_env) == 0 : static_chunks);
+    const bool fused_merge = a.xch_peers ? xch_tail : (merge_env ? atoi(merge_env) == 0 : static_chunks);
+    if (a.xch_peers && !fused_merge) a.all_rows_in_ws = 1;
     a.row_done = fused_merge ? counter + 64 : nullptr;
     // Across GPUs with one static chunk per warp nothing in the workspace header is needed: the chunk counter is not
     // used and the row counters live behind the caller's zero-initialised, self-resetting epoch array (d_epochs
     // [2 * rows]) -- no memset node in front of the kernel (~2 us of a ~50 us step).
-    const bool no_memset = a.xch_peers && static_chunks;
+    const bool no_memset = xch_tail && static_chunks;
     if (no_memset) a.row_done = a.xch_epochs + rows;
     auto kern = fused_merge ? paged_decode_overlap_kernel<D, KV, NWk, S, true> : paged_decode_overlap_kernel<D, KV, NWk, S, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1600,7 +1612,7 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     if (e != cudaSuccess || fused_merge) return e == cudaSuccess ? PA_OK : (int)e;
     // Rows of a single chunk were finished by the main kernel; everything else is merged here.
     const int nc_uniform = (units_of_ctx_host(a.T, a.num_tiles * a.tile_size) + cu - 1) / cu;
-    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1;
+    const bool need_combine = a.ctx_lens != nullptr || nc_uniform != 1 || a.xch_peers != nullptr;
     if (need_combine) {
         const int nc_max = (max_units + cu - 1) / cu;
         const int wpr = nc_max >= 64 ? 8 : (nc_max >= 32 ? 4 : (nc_max >= 16 ? 2 : 1));
