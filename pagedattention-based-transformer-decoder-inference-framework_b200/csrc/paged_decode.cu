@@ -1416,6 +1416,14 @@ static cudaError_t launch_combine_pdl(const DecodeArgs& a, int cu, int wpr, int 
     return cudaLaunchKernelEx(&cfg, combine_chunks_kernel<D>, a, cu, wpr);
 }
 
+// Few rows with a long context each (the C5 family: one sequence's 32 heads) stay on the grid kernel up to 4x that:
+// measured at 32 rows x 16K / 24K / 32K / 48K / 64K tokens: 49.2 / 68.4 / 87.3 / 125.3 / 162.7 us (5.5 ... 6.6 TB/s)
+// against 57.7 / 79.2 / 102.4 / 133.5 / 172.1 us for the streaming kernel.
+static bool grid_kernel_range(int64_t rows, int64_t units_per_row) {
+    const int64_t units = rows * units_per_row;
+    return units <= 65536 || (rows <= 64 && units <= 262144);
+}
+
 static int units_of_ctx_host(int T, int cap) {
     int ctx = T < 0 ? 0 : (T > cap ? cap : T);
     return (ctx + kUnitTok - 1) / kUnitTok;
@@ -1529,13 +1537,13 @@ static int launch_decode(DecodeArgs& a, bool overlap, void* ws, size_t ws_bytes,
     a.ws_l = w + nslots;
     a.ws_o = w + 2 * nslots;
     if (a.xch_peers) {
-        // Inter-GPU exchange.  Up to ~0.5 GB of K/V per GPU (C5: 268 MB) the split-KV grid kernel streams fastest
-        // (one GPU's C5 share: 46 us vs 56 us for the streaming kernel, whose static split waits for the slowest SM),
+        // Inter-GPU exchange.  In the grid kernel's range (grid_kernel_range: C5 shares up to 1 GB of K/V per GPU) the
+        // split-KV grid kernel streams fastest (one GPU's C5 share of 268 MB: 46 us vs 56 us for the streaming kernel),
         // so: grid kernel -> row partials in the workspace -> merge + exchange kernel chained by PROGRAMMATIC
         // DEPENDENT LAUNCH (resident before the decode grid ends, no launch gap).  Above that size: the streaming
-        // kernel, ONE launch.  PA_PARTIAL_DIRECT=0 / 1 forces either.
+        // kernel + the chunk-merge kernel (PDL) that exchanges in its emit step.  PA_PARTIAL_DIRECT=0 / 1 forces either.
         const char* env = getenv("PA_PARTIAL_DIRECT");
-        overlap = env ? atoi(env) != 1 : !(rows * (int64_t)max_units <= 65536 && rows <= 1024);
+        overlap = env ? atoi(env) != 1 : !(grid_kernel_range(rows, max_units) && rows <= 1024);
         if (!overlap) {
             a.num_splits = choose_splits(rows, max_units, di.sm_count);  // <= 64 = 4 warps x 16 in the merge kernel
             dim3 grid((unsigned)rows, (unsigned)a.num_splits);
@@ -1798,7 +1806,7 @@ PA_API int pa_paged_decode_f32_overlap(const float* d_q, float* d_out, const flo
 static bool partial_uses_streaming(int B, int num_heads, int T) {
     const char* env = getenv("PA_PARTIAL_DIRECT");
     if (env) return atoi(env) != 1;
-    return (int64_t)B * num_heads * ((T + kUnitTok - 1) / kUnitTok) > 65536;
+    return !grid_kernel_range((int64_t)B * num_heads, (T + kUnitTok - 1) / kUnitTok);
 }
 
 PA_API int pa_paged_decode_f16_partial(const float* d_q, float* d_part_m, float* d_part_l,
