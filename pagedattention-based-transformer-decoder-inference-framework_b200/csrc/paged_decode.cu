@@ -1430,6 +1430,22 @@ static int units_of_ctx_host(int T, int cap) {
 }
 
 static int choose_splits(int64_t rows, int max_units, int sm_count) {
+    if (const char* e = getenv("PA_DECODE_SPLITS")) {   // experiments
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) return v;
+    }
+    // Few rows with a long context each (one sequence split over GPUs: 32 rows x 1024+ units): ONE resident wave (4 CTAs
+    // per SM) of long splits beats many short ones -- measured on the 8-GPU C5 share (32 x 1024 units), fused step:
+    // 64 splits 48.6 us, 32: 47.4, 16-18: 46.8, 12: 47.7, 8: 53.6, and 20-24 (a second, partial wave) 54-57.  So: as
+    // many splits as fit one wave, at least 64 units each; very long rows (> 192 units per split) take two or more waves
+    // of 128-unit splits instead (4096 units: 32 splits 160.7 us, 16: 162.4, 64: 162.6).
+    if (rows <= 64 && max_units >= 512) {
+        int ns = (int)((4 * (int64_t)sm_count) / rows);
+        if (ns > max_units / 64) ns = max_units / 64;
+        if (ns > 64) ns = 64;
+        if (ns >= 1 && (max_units + ns - 1) / ns > 192) ns = max_units / 128 < 64 ? max_units / 128 : 64;
+        if (ns >= 1) return ns;
+    }
     const int64_t target = (int64_t)sm_count * 15;  // ~5 resident CTAs/SM x 3 waves
     int64_t ns = (target + rows - 1) / rows;
     const int cap_units = max_units / 4 > 0 ? max_units / 4 : 1;  // >= 4 units (1 per warp) per split
