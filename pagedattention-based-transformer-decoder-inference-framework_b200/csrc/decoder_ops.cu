@@ -215,27 +215,6 @@ __global__ void linear_reduce_kernel(const float* __restrict__ partial, const fl
     out[i] = s;
 }
 
-// K-slice sum behind the tensor-core kernel: 16-byte lanes (N % 4 == 0 there), launched with programmatic dependent
-// launch so its blocks are resident when the last partial tile lands (griddepcontrol.wait = all of the primary grid's
-// memory is visible).  Slices are added in index order: the result does not depend on the schedule.
-__global__ void __launch_bounds__(256) linear_reduce4_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                                                             int rows, int N, int nslices, int act, float* __restrict__ out) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int64_t total = (int64_t)rows * N;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < total && bias) s = __ldg(reinterpret_cast<const float4*>(bias + i % N));
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (i >= total) return;
-    for (int z = 0; z < nslices; ++z) {
-        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)z * total + i));
-        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
-    }
-    if (act == PA_ACT_RELU) {
-        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
-    }
-    *reinterpret_cast<float4*>(out + i) = s;
-}
-
 // ---- logits against the tied embedding E [vocab, hidden]: one warp per vocab row, 16-byte loads.
 // Optionally folds the greedy sampler in: best[r] = max over v of the 64-bit key
 // (order-preserving bits of (logit / T or logit * T) << 32 | ~v), so the maximum key is the FIRST maximum
@@ -544,10 +523,10 @@ static bool linear_uses_gemm(const void* x, const void* W, const void* out, cons
            (uintptr_t)out % 16 == 0 && (uintptr_t)bias % 16 == 0;
 }
 
-// linear_tf32x3.cu: 3xTF32 tcgen05 kernel over the same [rows, K] x [K, N] operands
-int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out);
-int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
-                        float* d_out, float* d_partial, int nslices, int kslice, int packed, cudaStream_t st);
+// linear_tf32x3.cu: 3xTF32 tcgen05 kernel over the same [rows, K] x [K, N] operands (stream-K or K-sliced grid + sum kernel)
+size_t pa_linear_tc_workspace_bytes(int rows, int K, int N, int sm_count);
+int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
+                     float* d_out, void* d_ws, size_t ws_bytes, int packed, int sm_count, cudaStream_t st);
 size_t pa_linear_tc_pack_floats(int K, int N);
 int pa_linear_tc_pack(const float* d_W, float* d_Wp, int K, int N, cudaStream_t st);
 
@@ -584,29 +563,13 @@ PA_API size_t pa_linear_workspace_bytes(int rows, int K, int N) {
     if (rows <= 0 || K <= 0 || N <= 0) return 0;
     const DeviceInfo& di = device_info();
     const int sm = di.ok ? di.sm_count : 148;
-    // either kernel may run (the choice also depends on pointer alignment): size for the larger need
+    // any of the kernels may run (the choice also depends on pointer alignment): size for the largest need
     const int a = linear_slices(rows, K, N, sm, nullptr, false);
     const int b = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? linear_slices(rows, K, N, sm, nullptr, true) : 1;  // (env may force it)
-    const int c = (rows >= 16 && N % 4 == 0 && K % 4 == 0) ? pa_linear_tc_slices(rows, K, N, sm, nullptr) : 1;
-    int nslices = a > b ? a : b;
-    if (c > nslices) nslices = c;
-    return nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
-}
-
-static int launch_reduce4_pdl(const float* partial, const float* d_bias, int rows, int N, int nslices, int act, float* d_out,
-                             cudaStream_t st) {
-    const int64_t n4 = ((int64_t)rows * N + 3) / 4;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((n4 + 255) / 256));
-    cfg.blockDim = dim3(256);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, linear_reduce4_kernel, partial, d_bias, rows, N, nslices, act, d_out);
-    return e == cudaSuccess ? PA_OK : (int)e;
+    const int nslices = a > b ? a : b;
+    const size_t simt = nslices > 1 ? (size_t)nslices * rows * N * sizeof(float) : 0;
+    const size_t tc = K % 4 == 0 ? pa_linear_tc_workspace_bytes(rows, K, N, sm) : 0;
+    return simt > tc ? simt : tc;
 }
 
 // The K-slice partials live in the CALLER's workspace (no library-owned scratch: a pointer captured in a CUDA
@@ -619,11 +582,12 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     if (rows == 0) return PA_OK;
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
-    const bool tc = linear_uses_tc(d_x, d_W, d_out, d_bias, rows, K, N);
-    const bool gemm = !tc && linear_uses_gemm(d_x, d_W, d_out, d_bias, rows, K, N);
+    if (linear_uses_tc(d_x, d_W, d_out, d_bias, rows, K, N))
+        return pa_linear_tc_run(d_x, d_W, d_bias, rows, K, N, act, d_out, d_workspace, workspace_bytes, 0, di.sm_count,
+                                as_stream(stream));
+    const bool gemm = linear_uses_gemm(d_x, d_W, d_out, d_bias, rows, K, N);
     int kslice = K;
-    int nslices = tc ? pa_linear_tc_slices(rows, K, N, di.sm_count, &kslice)
-                     : linear_slices(rows, K, N, di.sm_count, &kslice, gemm);
+    int nslices = linear_slices(rows, K, N, di.sm_count, &kslice, gemm);
     float* partial = nullptr;
     if (nslices > 1) {
         if (d_workspace && workspace_bytes >= (size_t)nslices * rows * N * sizeof(float) && (uintptr_t)d_workspace % 16 == 0) {
@@ -634,11 +598,7 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
         }
     }
     cudaError_t e;
-    if (tc) {
-        const int stc = pa_linear_tc_launch(d_x, d_W, d_bias, rows, K, N, act, d_out, partial, nslices, kslice, 0,
-                                            as_stream(stream));
-        if (stc != PA_OK) return stc;
-    } else if (gemm) {
+    if (gemm) {
         const size_t smem = (size_t)kGemmStages * (kGemmKT * kGemmBN + kGemmBM * kGemmXStride) * sizeof(float);
         static bool attr_set[64] = {};
         int dev = 0;
@@ -657,7 +617,6 @@ PA_API int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (nslices > 1 && tc) return launch_reduce4_pdl(partial, d_bias, rows, N, nslices, act, d_out, as_stream(stream));
     if (nslices > 1) {
         const int64_t n = (int64_t)rows * N;
         linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, d_bias, rows, N,
@@ -687,22 +646,8 @@ PA_API int pa_linear_f32_packed(const float* d_x, const float* d_W_packed, const
     if (rows == 0) return PA_OK;
     const DeviceInfo& di = device_info();
     if (!di.ok) return PA_ERR_NO_DEVICE;
-    int kslice = K;
-    int nslices = pa_linear_tc_slices(rows, K, N, di.sm_count, &kslice);
-    float* partial = nullptr;
-    if (nslices > 1) {
-        if (N % 4 == 0 && (uintptr_t)d_out % 16 == 0 && (uintptr_t)d_bias % 16 == 0 && d_workspace &&
-            workspace_bytes >= (size_t)nslices * rows * N * sizeof(float) && (uintptr_t)d_workspace % 16 == 0) {
-            partial = static_cast<float*>(d_workspace);
-        } else {
-            nslices = 1;
-            kslice = K;
-        }
-    }
-    const int stc = pa_linear_tc_launch(d_x, d_W_packed, d_bias, rows, K, N, act, d_out, partial, nslices, kslice, 1,
-                                        as_stream(stream));
-    if (stc != PA_OK || nslices == 1) return stc;
-    return launch_reduce4_pdl(partial, d_bias, rows, N, nslices, act, d_out, as_stream(stream));
+    return pa_linear_tc_run(d_x, d_W_packed, d_bias, rows, K, N, act, d_out, d_workspace, workspace_bytes, 1, di.sm_count,
+                            as_stream(stream));
 }
 
 PA_API int pa_logits_f32(const float* d_x, const float* d_E, int rows, int hidden, int vocab, float* d_logits,

@@ -30,8 +30,10 @@
 //             per stage, commit frees the stage.
 // Shared-memory traffic per stage at 64 rows: 16 KB W written + 16 KB read, x 8 + 8 (lo) written, 8 read, 24 KB of
 // B-operand reads = 80 KB per 16 KB of weights, against 128 KB for the batch-as-M form measured first (r02_notes.md).
-// K slices (grid.z) write fp32 partial tiles that linear_reduce4_kernel (decoder_ops.cu, chained by programmatic
-// dependent launch) sums in slice order.
+// Work split: a K-sliced grid (row tile, feature tile, K slice) whose fp32 partial tiles linear_reduce4_kernel sums in
+// slice order, or -- where that grid would not fit one wave -- the stream-K form (equal contiguous ranges of the
+// (tile, K block) list, one CTA per SM, partial tiles summed in range order by linear_streamk_reduce_kernel).  Both sum
+// kernels are chained by programmatic dependent launch.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -68,6 +70,11 @@ struct Args {
     float* partial;   // [nslices][rows][N] when nslices > 1
     int rows, N, K, act, kslice, nslices;
     const float* w_packed;   // PACKED kernels: [feature tile][K block][32 k][128 n] (pa_linear_pack_f32), else null
+    // STREAMK kernels: the (tile, K block) work list is cut into equal contiguous ranges, one per CTA
+    int sk_per;              // K blocks per CTA
+    int sk_maxseg;           // partial-tile slots per CTA
+    int n_ft, n_mt;          // feature tiles, row tiles (tile index = ft * n_mt + mt: CTAs that run side by side share W)
+    int64_t sk_total;        // tiles * K blocks
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -161,7 +168,63 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
     __trap();
 }
 
-template <int NP, bool PACKED>
+// Work of one CTA = a list of SEGMENTS (tile, K-block range).  Plain grid: one segment, from blockIdx (row tile,
+// feature tile, K slice).  STREAMK: the list of all (tile, K block) pairs, tile-major, is cut into equal contiguous
+// ranges, one per CTA (one CTA per SM, every CTA the same number of blocks -- no wave quantisation, one prologue per
+// SM); a range covers the tail of one tile, whole tiles, and the head of another.  A segment that is a whole tile
+// is finished in place (bias / relu -> out); the others leave a partial tile in the CTA's own slots, summed in
+// range order by linear_streamk_reduce_kernel.  The shared-memory and TMEM rings run on across segment boundaries.
+struct Segment {
+    int m0, n0, ft, kb0, nkb, whole, slot;
+};
+
+template <int NP, bool STREAMK>
+struct SegmentIter {
+    const Args& g;
+    int tk;
+    int64_t w, end;
+    int sg;
+    __device__ SegmentIter(const Args& g_) : g(g_), tk((g_.K + BKF - 1) / BKF), sg(0) {
+        if (STREAMK) {
+            w = (int64_t)blockIdx.x * g.sk_per;
+            end = w + g.sk_per < g.sk_total ? w + g.sk_per : g.sk_total;
+        } else {
+            w = 0;
+            end = 1;
+        }
+    }
+    __device__ bool next(Segment& sgm) {
+        if (STREAMK) {
+            if (w >= end) return false;
+            const int tile = (int)(w / tk);
+            sgm.kb0 = (int)(w - (int64_t)tile * tk);
+            const int64_t left = end - w;
+            sgm.nkb = left < tk - sgm.kb0 ? (int)left : tk - sgm.kb0;
+            sgm.ft = tile / g.n_mt;
+            sgm.n0 = sgm.ft * BF;
+            sgm.m0 = (tile % g.n_mt) * NP;
+            sgm.whole = sgm.kb0 == 0 && sgm.nkb == tk;
+            sgm.slot = blockIdx.x * g.sk_maxseg + sg;
+            w += sgm.nkb;
+            ++sg;
+            return true;
+        }
+        if (w >= end) return false;
+        w = end;
+        const int k_begin = blockIdx.z * g.kslice;               // kslice is a multiple of BKF
+        const int k_end = min(g.K, k_begin + g.kslice);
+        sgm.kb0 = k_begin / BKF;
+        sgm.nkb = (k_end - k_begin + BKF - 1) / BKF;
+        sgm.ft = blockIdx.y;
+        sgm.n0 = blockIdx.y * BF;
+        sgm.m0 = blockIdx.x * NP;
+        sgm.whole = g.nslices == 1;
+        sgm.slot = blockIdx.z;
+        return true;
+    }
+};
+
+template <int NP, bool PACKED, bool STREAMK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Args g) {
     using C = Cfg<NP>;
@@ -173,15 +236,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     auto full_bar = [&](int s) { return bar0 + s * 8; };
     auto split_bar = [&](int s) { return bar0 + (NST + s) * 8; };
     auto empty_bar = [&](int s) { return bar0 + (2 * NST + s) * 8; };
-    const uint32_t tmem_full_bar = bar0 + 3 * NST * 8;
-    const uint32_t tmem_slot = tmem_full_bar + 8;
+    const uint32_t tmem_full_bar = bar0 + 3 * NST * 8;   // MMAs of a segment complete -> epilogue
+    const uint32_t acc_free_bar = tmem_full_bar + 8;      // epilogue has read the accumulators -> next segment's MMAs
+    const uint32_t tmem_slot = acc_free_bar + 8;
 
-    asm volatile("griddepcontrol.launch_dependents;");   // the K-slice sum behind this grid may become resident
+    asm volatile("griddepcontrol.launch_dependents;");   // the partial-tile sum behind this grid may become resident
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * NP, n0 = blockIdx.y * BF, slice = blockIdx.z;
-    const int k_begin = slice * g.kslice;
-    const int k_end = min(g.K, k_begin + g.kslice);
-    const int nkb = (k_end - k_begin + BKF - 1) / BKF;   // kslice is a multiple of BKF: blocks never straddle slices
+    const int tk = (g.K + BKF - 1) / BKF;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -190,6 +251,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(acc_free_bar, 256);
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW));
@@ -200,101 +262,132 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    // stage layout: W [4][32 k][32 n] | x [NP][128 B] | x_lo;  TMEM: accumulator [0, NP), then per stage W (32) W_lo (32)
+    // stage layout: W [32 k][128 n] | x [NP][128 B] | x_lo;  TMEM: NACC accumulators of NP columns, then per stage W (32)
+    // and W_lo (32)
 
     if (warp == 0) {
         if (elect_one()) {
             const uint64_t stream_policy = l2_policy_evict_first();
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % NST;
-                mbar_wait_bounded(empty_bar(s), ((i / NST) & 1) ^ 1);
-                const uint32_t st = base + s * STAGE;
-                mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
-                const int k0 = k_begin + i * BKF;
-                if (PACKED) {   // the block is ONE contiguous 16 KB run (whole DRAM pages), streamed past L2
-                    const int64_t blk = (int64_t)blockIdx.y * ((g.K + BKF - 1) / BKF) + k0 / BKF;
-                    bulk_g2s(st, g.w_packed + blk * (W_TILE / 4), W_TILE, full_bar(s), stream_policy);
-                } else {
-                    tma_load_2d(st, &tmW, n0, k0, full_bar(s));
+            SegmentIter<NP, STREAMK> segs(g);
+            Segment sg;
+            int it = 0;
+            while (segs.next(sg)) {
+                for (int i = 0; i < sg.nkb; ++i, ++it) {
+                    const int s = it % NST;
+                    mbar_wait_bounded(empty_bar(s), ((it / NST) & 1) ^ 1);
+                    const uint32_t st = base + s * STAGE;
+                    mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
+                    const int kb = sg.kb0 + i;
+                    if (PACKED) {   // the block is ONE contiguous 16 KB run (whole DRAM pages), streamed past L2
+                        const int64_t blk = (int64_t)sg.ft * tk + kb;
+                        bulk_g2s(st, g.w_packed + blk * (W_TILE / 4), W_TILE, full_bar(s), stream_policy);
+                    } else {
+                        tma_load_2d(st, &tmW, sg.n0, kb * BKF, full_bar(s));
+                    }
+                    tma_load_2d(st + W_TILE, &tmX, kb * BKF, sg.m0, full_bar(s));
                 }
-                tma_load_2d(st + W_TILE, &tmX, k0, m0, full_bar(s));
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = idesc_for(NP);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % NST;
-                mbar_wait_bounded(split_bar(s), (i / NST) & 1);
-                tc_fence_after();
-                const uint32_t st = base + s * STAGE;
-#pragma unroll
-                for (int ks = 0; ks < BKF / 8; ++ks) {
-                    const uint32_t wa = tmem_base + RING0 + s * 64 + ks * 8;
-                    const uint32_t wl = wa + 32;
-                    const uint64_t xa = make_desc(st + W_TILE + ks * 32);
-                    const uint64_t xl = make_desc(st + W_TILE + X_TILE + ks * 32);
-                    const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-                    // accumulator 0: hi.hi; 1: lo terms (W_lo.x first); 2: x_lo.W_hi where there are three
-                    umma_tf32_ts(tmem_base + (NACC > 1 ? NP : 0), wl, xa, idesc, first);
-                    umma_tf32_ts(tmem_base + (NACC > 2 ? 2 * NP : (NACC > 1 ? NP : 0)), wa, xl, idesc, NACC > 2 ? first : 1u);
-                    umma_tf32_ts(tmem_base, wa, xa, idesc, NACC > 1 ? first : 1u);
+            SegmentIter<NP, STREAMK> segs(g);
+            Segment sg;
+            int it = 0, nseg = 0;
+            while (segs.next(sg)) {
+                if (nseg > 0) {   // the epilogue of the previous segment has drained the accumulators
+                    mbar_wait_bounded(acc_free_bar, (uint32_t)((nseg - 1) & 1));
+                    tc_fence_after();
                 }
-                umma_commit(empty_bar(s));
+                for (int i = 0; i < sg.nkb; ++i, ++it) {
+                    const int s = it % NST;
+                    mbar_wait_bounded(split_bar(s), (it / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t st = base + s * STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < BKF / 8; ++ks) {
+                        const uint32_t wa = tmem_base + RING0 + s * 64 + ks * 8;
+                        const uint32_t wl = wa + 32;
+                        const uint64_t xa = make_desc(st + W_TILE + ks * 32);
+                        const uint64_t xl = make_desc(st + W_TILE + X_TILE + ks * 32);
+                        const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+                        // accumulator 0: hi.hi; 1: lo terms (W_lo.x first); 2: x_lo.W_hi where there are three
+                        umma_tf32_ts(tmem_base + (NACC > 1 ? NP : 0), wl, xa, idesc, first);
+                        umma_tf32_ts(tmem_base + (NACC > 2 ? 2 * NP : (NACC > 1 ? NP : 0)), wa, xl, idesc, NACC > 2 ? first : 1u);
+                        umma_tf32_ts(tmem_base, wa, xa, idesc, NACC > 1 ? first : 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tmem_full_bar);
+                ++nseg;
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
         const int t = threadIdx.x - 64;      // 0..255
         const int qtr = warp & 3;            // TMEM lane quarter this warp may touch
         const int half = (warp - 2) >> 2;    // which half of a block's k (split) / of the row tile (epilogue)
         const int f = qtr * 32 + lane;       // feature of the tile = TMEM lane
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % NST;
-            mbar_wait_bounded(full_bar(s), (i / NST) & 1);
-            const uint32_t st = base + s * STAGE;
-            // W: column f of the block, k rows [half * 16, half * 16 + 16) -> 16 columns of W and of W_lo in TMEM
-            {
-                uint32_t wv[16], wlo[16];
-                const uint32_t col = st + (qtr * 32 + lane) * 4 + half * 16 * 512;
+        SegmentIter<NP, STREAMK> segs(g);
+        Segment sg;
+        int it = 0, nseg = 0;
+        while (segs.next(sg)) {
+            for (int i = 0; i < sg.nkb; ++i, ++it) {
+                const int s = it % NST;
+                mbar_wait_bounded(full_bar(s), (it / NST) & 1);
+                const uint32_t st = base + s * STAGE;
+                // W: column f of the block, k rows [half * 16, half * 16 + 16) -> 16 columns of W and of W_lo in TMEM
+                {
+                    uint32_t wv[16], wlo[16];
+                    const uint32_t col = st + f * 4 + half * 16 * 512;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[j]) : "r"(col + j * 512));
+                    for (int j = 0; j < 16; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[j]) : "r"(col + j * 512));
 #pragma unroll
-                for (int j = 0; j < 16; ++j) wlo[j] = __float_as_uint(lo_part(__uint_as_float(wv[j])));
-                const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + RING0 + s * 64 + half * 16;
-                tmem_st16(ta, wv);
-                tmem_st16(ta + 32, wlo);
+                    for (int j = 0; j < 16; ++j) wlo[j] = __float_as_uint(lo_part(__uint_as_float(wv[j])));
+                    const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + RING0 + s * 64 + half * 16;
+                    tmem_st16(ta, wv);
+                    tmem_st16(ta + 32, wlo);
+                }
+                // x tile -> x_lo: NP * 8 chunks of 16 bytes
+#pragma unroll
+                for (int j = 0; j < NP / 32; ++j) {
+                    const uint32_t off = (j * 256 + t) * 16;
+                    const uint4 v = lds_128(st + W_TILE + off);
+                    const float a = lo_part(__uint_as_float(v.x)), b = lo_part(__uint_as_float(v.y));
+                    const float c = lo_part(__uint_as_float(v.z)), d = lo_part(__uint_as_float(v.w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + W_TILE + X_TILE + off), "f"(a), "f"(b),
+                                 "f"(c), "f"(d)
+                                 : "memory");
+                }
+                fence_proxy_async();
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(split_bar(s));
             }
-            // x tile -> x_lo: NP * 8 chunks of 16 bytes
-#pragma unroll
-            for (int j = 0; j < NP / 32; ++j) {
-                const uint32_t off = (j * 256 + t) * 16;
-                const uint4 v = lds_128(st + W_TILE + off);
-                const float a = lo_part(__uint_as_float(v.x)), b = lo_part(__uint_as_float(v.y));
-                const float c = lo_part(__uint_as_float(v.z)), d = lo_part(__uint_as_float(v.w));
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + W_TILE + X_TILE + off), "f"(a), "f"(b), "f"(c),
-                             "f"(d)
-                             : "memory");
-            }
-            fence_proxy_async();
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(split_bar(s));
-        }
-        // ---- epilogue: lane = feature, columns = rows of x; this warp takes half of the row tile, 32 rows at a time ----
-        const int n = n0 + f;
-        const bool n_ok = n < g.N;
-        if (nkb > 0) {
-            mbar_wait_bounded(tmem_full_bar, 0);
+            // ---- epilogue of the segment: lane = feature, columns = rows of x; this warp takes half of the row tile ----
+            const int n = sg.n0 + f;
+            const bool n_ok = n < g.N;
+            mbar_wait_bounded(tmem_full_bar, (uint32_t)(nseg & 1));
             tc_fence_after();
-        }
-        const float bias = (g.nslices == 1 && g.bias && n_ok) ? __ldg(g.bias + n) : 0.f;
-        float* dst = g.nslices > 1 ? g.partial + (int64_t)slice * g.rows * g.N : g.out;
-        constexpr int CH = NP / 64;   // 32-row chunks per warp
+            const float bias = (sg.whole && g.bias && n_ok) ? __ldg(g.bias + n) : 0.f;
+            // whole tile: out [rows][N]; K slice of the plain grid: partial [slice][rows][N]; stream-K: this CTA's slot
+            // [NP rows][128 features]
+            float* dst;
+            int64_t ld;
+            if (sg.whole) {
+                dst = g.out + (int64_t)sg.m0 * g.N + n;
+                ld = g.N;
+            } else if (STREAMK) {
+                dst = g.partial + (int64_t)sg.slot * NP * BF + f;
+                ld = BF;
+            } else {
+                dst = g.partial + ((int64_t)sg.slot * g.rows + sg.m0) * g.N + n;
+                ld = g.N;
+            }
+            const bool store_ok = n_ok || (STREAMK && !sg.whole);   // pad features of a slot are written (zeros), never read
+            constexpr int CH = NP / 64;   // 32-row chunks per warp
 #pragma unroll 1
-        for (int c = half * CH; c < half * CH + CH; ++c) {
-            uint32_t rr[32];
-            if (nkb > 0) {
+            for (int c = half * CH; c < half * CH + CH; ++c) {
+                uint32_t rr[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(qtr * 32) << 16) + c * 32;
                 if (NACC == 1) {
                     tmem_ld_32x32(ta, rr);
@@ -310,30 +403,64 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(r1[j]));
                 }
-            } else {
+                if (!store_ok) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rr[j] = 0u;
-            }
-            if (!n_ok) continue;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int row = m0 + c * 32 + j;
-                if (row >= g.rows) break;
-                float v = __uint_as_float(rr[j]);
-                if (g.nslices == 1) {
-                    v += bias;
-                    if (g.act == PA_ACT_RELU) v = fmaxf(v, 0.f);
+                for (int j = 0; j < 32; ++j) {
+                    const int rl = c * 32 + j;
+                    if (sg.m0 + rl >= g.rows && !(STREAMK && !sg.whole)) break;
+                    float v = __uint_as_float(rr[j]);
+                    if (sg.whole) {
+                        v += bias;
+                        if (g.act == PA_ACT_RELU) v = fmaxf(v, 0.f);
+                    }
+                    dst[(int64_t)rl * ld] = v;
                 }
-                dst[(int64_t)row * g.N + n] = v;
             }
+            tc_fence_before();
+            mbar_arrive(acc_free_bar);
+            ++nseg;
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+}
+
+// Sum of the partial tiles of the stream-K form: tile t was computed by the CTAs c0 .. c1 whose ranges intersect its K
+// blocks (c0 == c1: the tile was finished in place, nothing to do); they are added in range order -- the result does
+// not depend on the schedule.  Launched with programmatic dependent launch behind the main kernel.
+template <int NP>
+__global__ void __launch_bounds__(256) linear_streamk_reduce_kernel(const float* __restrict__ partial,
+                                                                    const float* __restrict__ bias, int rows, int N, int tk,
+                                                                    int per, int maxseg, int n_mt, int act,
+                                                                    float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t total = (int64_t)rows * N;
+    int row = 0, n = 0, c0 = 0, c1 = 0, tile = 0;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total) {
+        row = (int)(i / N);
+        n = (int)(i - (int64_t)row * N);
+        tile = (n / BF) * n_mt + row / NP;
+        c0 = (int)(((int64_t)tile * tk) / per);
+        c1 = (int)((((int64_t)tile + 1) * tk - 1) / per);
+        if (c0 != c1 && bias) s = __ldg(reinterpret_cast<const float4*>(bias + n));
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (i >= total || c0 == c1) return;
+    for (int c = c0; c <= c1; ++c) {
+        const int first_tile = (int)(((int64_t)c * per) / tk);
+        const int64_t slot = (int64_t)c * maxseg + (tile - first_tile);
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (slot * NP + row % NP) * BF + n % BF));
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    if (act == PA_ACT_RELU) {
+        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -369,22 +496,79 @@ static bool make_map_f32(CUtensorMap* map, const void* ptr, uint64_t cols, uint6
 // fc1 824 vs 711 us -- and 3x less accurate than two 128-row tiles with the lo terms accumulated apart.)
 static int row_tile(int rows) { return rows <= 64 ? 64 : 128; }
 
-template <int NP, bool PACKED>
-static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g, int nslices, cudaStream_t st) {
+template <int NP, bool PACKED, bool STREAMK>
+static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g, dim3 grid, cudaStream_t st) {
     using C = Cfg<NP>;
-    const size_t smem = (size_t)C::NST * C::STAGE + (3 * C::NST + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)C::NST * C::STAGE + (3 * C::NST + 2) * 8 + 16 + 1024;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NP, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NP, PACKED, STREAMK>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev & 63] = true;
     }
-    dim3 grid((unsigned)((g.rows + NP - 1) / NP), (unsigned)((g.N + BF - 1) / BF), (unsigned)nslices);
-    linear_tf32x3_kernel<NP, PACKED><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
+    linear_tf32x3_kernel<NP, PACKED, STREAMK><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
     PA_RETURN_LAUNCH_STATUS();
+}
+
+template <typename... A>
+static int launch_pdl(void (*kern)(A...), unsigned blocks, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    return e == cudaSuccess ? PA_OK : (int)e;
+}
+
+// K-slice sum behind the plain grid: 16-byte lanes (N % 4 == 0), programmatic dependent launch (its blocks are resident
+// when the last partial tile lands; griddepcontrol.wait = all of the primary grid's memory is visible).  Slices are
+// added in index order: the result does not depend on the schedule.
+__global__ void __launch_bounds__(256) linear_reduce4_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                             int rows, int N, int nslices, int act, float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t total = (int64_t)rows * N;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total && bias) s = __ldg(reinterpret_cast<const float4*>(bias + i % N));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (i >= total) return;
+    for (int z = 0; z < nslices; ++z) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)z * total + i));
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    if (act == PA_ACT_RELU) {
+        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+}
+
+// Stream-K geometry: equal contiguous ranges of the (tile, K block) list, one CTA per SM (at least 8 blocks each).
+struct StreamK {
+    int grid, per, maxseg, n_ft, tk;
+    int64_t total;
+    size_t ws_bytes;
+};
+static StreamK streamk_plan(int rows, int K, int N, int sm_count) {
+    StreamK p;
+    const int np = row_tile(rows);
+    p.n_ft = (N + BF - 1) / BF;
+    p.tk = (K + BKF - 1) / BKF;
+    p.total = (int64_t)((rows + np - 1) / np) * p.n_ft * p.tk;
+    int64_t gmax = p.total / 8;
+    if (gmax < 1) gmax = 1;
+    const int64_t G = gmax < sm_count ? gmax : sm_count;
+    p.per = (int)((p.total + G - 1) / G);
+    p.grid = (int)((p.total + p.per - 1) / p.per);
+    p.maxseg = (p.per + p.tk - 1) / p.tk + 1;
+    p.ws_bytes = (size_t)p.grid * p.maxseg * np * BF * sizeof(float);
+    return p;
 }
 
 // W [K, N] -> [feature tile][K block][32 k][128 n], zero padded: every (tile, block) the kernel streams is one
@@ -419,14 +603,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 
 using namespace pa;
 
-// K-slice geometry.  One CTA per SM is resident, so the grid runs in waves of sm_count CTAs: pick the slice count
-// that minimises waves x (K blocks per CTA + per-CTA set-up, ~2 blocks, + when sliced the partial tile's write and
-// re-read, NP / 16 blocks' worth of bytes); every slice holds >= 8 K blocks (256 k-rows).
+// K-slice geometry of the plain grid (the fallback when the stream-K form cannot be used: no workspace for its slots).
+// One CTA per SM is resident, so the grid runs in waves of sm_count CTAs: pick the slice count that minimises
+// waves x (K blocks per CTA + per-CTA set-up, ~2 blocks, + when sliced the partial tile's write and re-read, NP / 16
+// blocks' worth of bytes); every slice holds >= 8 K blocks (256 k-rows).
 // (Summing the slices inside the kernel -- last slice of a tile to arrive, one counter per tile -- was measured and
-//  rejected: fence + counter + the last CTA's serial sum lengthen every wave, fc1 at batch 64 60 -> 88 us.  A persistent
-//  tile loop with two alternating accumulators and dedicated epilogue warps measured 52.2 against 56.3 us; it was
-//  dropped for the per-term accumulators below, which need the TMEM columns and cut the error 2.7x.)
-int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
+//  rejected: fence + counter + the last CTA's serial sum lengthen every wave, fc1 at batch 64 60 -> 88 us.)
+static int tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
     const int64_t tiles = (int64_t)((rows + np - 1) / np) * ((N + BF - 1) / BF);
@@ -449,10 +632,21 @@ int pa_linear_tc_slices(int rows, int K, int N, int sm_count, int* kslice_out) {
     return (K + kslice - 1) / kslice;
 }
 
-// Launch helper for pa_linear_f32 / pa_linear_f32_packed (decoder_ops.cu).  PA_ERR_UNSUPPORTED when the tensor maps
-// cannot be built.  d_W: [K, N] (packed == 0) or the pa_linear_pack_f32 layout (packed == 1).
-int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
-                        float* d_out, float* d_partial, int nslices, int kslice, int packed, cudaStream_t st) {
+// Scratch for either form (pa_linear_workspace_bytes adds it to the SIMT kernels' need).
+size_t pa_linear_tc_workspace_bytes(int rows, int K, int N, int sm_count) {
+    using namespace pa::tf32x3;
+    const int ns = tc_slices(rows, K, N, sm_count, nullptr);
+    const size_t sliced = ns > 1 ? (size_t)ns * rows * N * sizeof(float) : 0;
+    const size_t sk = streamk_plan(rows, K, N, sm_count).ws_bytes;
+    return sliced > sk ? sliced : sk;
+}
+
+// pa_linear_f32 / pa_linear_f32_packed on the tensor cores.  d_W: [K, N] (packed == 0) or the pa_linear_pack_f32
+// layout (packed == 1).  Form: stream-K when the workspace holds its slots and the sum kernel's 16-byte lanes apply
+// (N % 4 == 0, aligned out / bias; PA_LINEAR_STREAMK=0 disables), else the plain grid, K-sliced if the workspace
+// allows.  PA_ERR_UNSUPPORTED when the tensor maps cannot be built.
+int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N, int act,
+                     float* d_out, void* d_ws, size_t ws_bytes, int packed, int sm_count, cudaStream_t st) {
     using namespace pa::tf32x3;
     const int np = row_tile(rows);
     CUtensorMap tmX, tmW;
@@ -461,9 +655,54 @@ int pa_linear_tc_launch(const float* d_x, const float* d_W, const float* d_bias,
     if (packed) memset(&tmW, 0, sizeof(tmW));
     else if (!make_map_f32(&tmW, d_W, (uint64_t)N, (uint64_t)K, BF, BKF, CU_TENSOR_MAP_SWIZZLE_NONE))
         return PA_ERR_UNSUPPORTED;
-    Args g{d_bias, d_out, d_partial, rows, N, K, act, kslice, nslices, packed ? d_W : nullptr};
-    if (packed) return np == 64 ? launch<64, true>(tmX, tmW, g, nslices, st) : launch<128, true>(tmX, tmW, g, nslices, st);
-    return np == 64 ? launch<64, false>(tmX, tmW, g, nslices, st) : launch<128, false>(tmX, tmW, g, nslices, st);
+    const bool lanes16 = N % 4 == 0 && (uintptr_t)d_out % 16 == 0 && (uintptr_t)d_bias % 16 == 0 && d_ws &&
+                         (uintptr_t)d_ws % 16 == 0;
+    Args g{};
+    g.bias = d_bias; g.out = d_out; g.partial = static_cast<float*>(d_ws);
+    g.rows = rows; g.N = N; g.K = K; g.act = act; g.kslice = K; g.nslices = 1;
+    g.w_packed = packed ? d_W : nullptr;
+    const unsigned n_mt = (unsigned)((rows + np - 1) / np), n_ft = (unsigned)((N + BF - 1) / BF);
+    g.n_ft = (int)n_ft;
+    g.n_mt = (int)n_mt;
+    const StreamK sk = streamk_plan(rows, K, N, sm_count);
+    int kslice = K;
+    int nslices = tc_slices(rows, K, N, sm_count, &kslice);
+    // Stream-K where the plain grid would need more than one wave (measured, L2 flushed: fc1 at batch 64, 430 CTAs in 2.9
+    // waves, 58.3 -> 54.2 us; 256 rows 123.9 -> 111.6); a grid that fits ONE wave already has one prologue per SM, and the
+    // accumulator hand-over at a range's tile boundary then only costs (fc2 54.1 -> 56.3, projection 27.6 -> 31.7).
+    // PA_LINEAR_STREAMK=0 / 1 forces either.
+    const char* env = getenv("PA_LINEAR_STREAMK");
+    // ... and only for K-sliced grids of few tiles: with many whole tiles per CTA (prefill: 688 tiles) the plain grid's
+    // block order keeps neighbouring CTAs on the same weights and wins (2048 rows: 714 vs 859 us).
+    const bool multi_wave = (int64_t)n_mt * n_ft * nslices > sm_count && (int64_t)n_mt * n_ft <= 2 * (int64_t)sm_count;
+    const bool use_sk = (env ? atoi(env) != 0 : multi_wave) && lanes16 && sk.tk >= 8 && ws_bytes >= sk.ws_bytes;
+    int rc;
+    if (use_sk) {
+        g.sk_per = sk.per; g.sk_maxseg = sk.maxseg; g.sk_total = sk.total;
+        const dim3 grid((unsigned)sk.grid);
+        if (packed) rc = np == 64 ? launch<64, true, true>(tmX, tmW, g, grid, st) : launch<128, true, true>(tmX, tmW, g, grid, st);
+        else rc = np == 64 ? launch<64, false, true>(tmX, tmW, g, grid, st) : launch<128, false, true>(tmX, tmW, g, grid, st);
+        if (rc != PA_OK || sk.per % sk.tk == 0) return rc;   // ranges that end on tile boundaries leave no partial tiles
+        const unsigned blocks = (unsigned)((((int64_t)rows * N + 3) / 4 + 255) / 256);
+        const float* part = g.partial;
+        if (np == 64)
+            return launch_pdl(linear_streamk_reduce_kernel<64>, blocks, st, part, d_bias, rows, N, sk.tk, sk.per, sk.maxseg,
+                              (int)n_mt, act, d_out);
+        return launch_pdl(linear_streamk_reduce_kernel<128>, blocks, st, part, d_bias, rows, N, sk.tk, sk.per, sk.maxseg,
+                          (int)n_mt, act, d_out);
+    }
+    if (nslices > 1 && !(lanes16 && ws_bytes >= (size_t)nslices * rows * N * sizeof(float))) {
+        nslices = 1;
+        kslice = K;
+    }
+    g.kslice = kslice; g.nslices = nslices;
+    const dim3 grid(n_mt, n_ft, (unsigned)nslices);
+    if (packed) rc = np == 64 ? launch<64, true, false>(tmX, tmW, g, grid, st) : launch<128, true, false>(tmX, tmW, g, grid, st);
+    else rc = np == 64 ? launch<64, false, false>(tmX, tmW, g, grid, st) : launch<128, false, false>(tmX, tmW, g, grid, st);
+    if (rc != PA_OK || nslices == 1) return rc;
+    const unsigned blocks = (unsigned)((((int64_t)rows * N + 3) / 4 + 255) / 256);
+    const float* part = g.partial;
+    return launch_pdl(linear_reduce4_kernel, blocks, st, part, d_bias, rows, N, nslices, act, d_out);
 }
 
 size_t pa_linear_tc_pack_floats(int K, int N) {
