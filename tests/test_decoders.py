@@ -631,8 +631,9 @@ def test_linear_register_tiled_gemm_matches_fp64(shape, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(64, 4096, 1024), (100, 192, 100), (16, 256, 128), (300, 520, 388), (65, 36, 12),
-                                   (128, 64, 260), (257, 2048, 128)])
-def test_linear_tf32x3_tensor_core_kernel_matches_fp64(shape, monkeypatch):
+                                   (128, 64, 260), (257, 2048, 128), (64, 2048, 1536), (200, 1024, 2048)])
+@pytest.mark.parametrize("streamk", ["0", "1"])
+def test_linear_tf32x3_tensor_core_kernel_matches_fp64(shape, streamk, monkeypatch):
     """pa_linear_f32 on tcgen05 kind::tf32 with the 3-term operand split (linear_tf32x3.cu, PA_LINEAR_TC=1 forces it
     for small shapes): against a float64 product with the stated bound 1e-5 * sum_k |x||W| + 4 fp32 ulps of the
     result (measured <= 3e-6: operand split 2^-21, plus the tensor core's truncating fp32 accumulation over K) -- K-sliced and unsliced, bias / relu, ragged M / N / K tiles (TMA zero fill), rows past the tile untouched;
@@ -640,6 +641,9 @@ def test_linear_tf32x3_tensor_core_kernel_matches_fp64(shape, monkeypatch):
     from llm_decoder import _cabi
     lib = _cabi.lib()
     rows, K, N = shape
+    # both work splits: K-sliced grid, and stream-K (equal contiguous ranges of the (tile, K block) list per CTA: ranges
+    # that start / end inside a tile, whole tiles finished in place, ragged last range)
+    monkeypatch.setenv("PA_LINEAR_STREAMK", streamk)
     rng = np.random.default_rng(sum(shape) + 1)
     x = (rng.standard_normal((rows, K)) * np.exp(rng.uniform(-3, 3, (rows, 1)))).astype(np.float32)
     W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
