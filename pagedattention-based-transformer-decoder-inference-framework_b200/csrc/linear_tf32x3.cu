@@ -75,6 +75,7 @@ struct Args {
     int sk_maxseg;           // partial-tile slots per CTA
     int n_ft, n_mt;          // feature tiles, row tiles (tile index = ft * n_mt + mt: CTAs that run side by side share W)
     int64_t sk_total;        // tiles * K blocks
+    unsigned long long* probe;   // bring-up aid (pa_debug_linear_probe): per-CTA cycle sums, null in production
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -243,6 +244,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     asm volatile("griddepcontrol.launch_dependents;");   // the partial-tile sum behind this grid may become resident
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tk = (g.K + BKF - 1) / BKF;
+    const long long t_cta0 = g.probe ? clock64() : 0;
+    const int cta_id = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -271,10 +274,35 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             SegmentIter<NP, STREAMK> segs(g);
             Segment sg;
             int it = 0;
+            long long pr_wait = 0;
+            // The kernel is launched with programmatic stream serialisation: it may start while the kernel before it
+            // in the stream (the producer of x: a LayerNorm, the previous layer's sum kernel) is still running.  The
+            // WEIGHTS do not depend on that kernel, so the first ring-full of W blocks is requested at once; x -- and
+            // everything downstream of it: the split, the MMAs, every store -- waits for griddepcontrol.wait.
+            int x_it = 0;           // blocks whose x tile has been requested
+            bool dep_ok = false;    // griddepcontrol.wait executed
+            auto load_x_upto = [&](int upto) {   // request the x tiles of blocks [x_it, upto) of the work list, in order
+                SegmentIter<NP, STREAMK> xs(g);
+                Segment xsg;
+                int j = 0;
+                while (xs.next(xsg) && j < upto) {
+                    for (int i = 0; i < xsg.nkb && j < upto; ++i, ++j)
+                        if (j >= x_it)
+                            tma_load_2d(base + (j % NST) * STAGE + W_TILE, &tmX, (xsg.kb0 + i) * BKF, xsg.m0, full_bar(j % NST));
+                }
+                x_it = upto > x_it ? upto : x_it;
+            };
             while (segs.next(sg)) {
                 for (int i = 0; i < sg.nkb; ++i, ++it) {
                     const int s = it % NST;
+                    if (it >= NST && !dep_ok) {   // the ring is full of weights: now x is needed
+                        asm volatile("griddepcontrol.wait;" ::: "memory");
+                        dep_ok = true;
+                        load_x_upto(it);
+                    }
+                    const long long tp0 = g.probe ? clock64() : 0;
                     mbar_wait_bounded(empty_bar(s), ((it / NST) & 1) ^ 1);
+                    if (g.probe) pr_wait += clock64() - tp0;
                     const uint32_t st = base + s * STAGE;
                     mbar_arrive_expect_tx(full_bar(s), W_TILE + X_TILE);
                     const int kb = sg.kb0 + i;
@@ -284,9 +312,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     } else {
                         tma_load_2d(st, &tmW, sg.n0, kb * BKF, full_bar(s));
                     }
-                    tma_load_2d(st + W_TILE, &tmX, kb * BKF, sg.m0, full_bar(s));
+                    if (dep_ok) {
+                        tma_load_2d(st + W_TILE, &tmX, kb * BKF, sg.m0, full_bar(s));
+                        x_it = it + 1;
+                    }
                 }
             }
+            if (!dep_ok) {   // fewer blocks than ring stages
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                load_x_upto(it);
+            }
+            if (g.probe) g.probe[cta_id * 8 + 0] = pr_wait;
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -294,6 +330,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             SegmentIter<NP, STREAMK> segs(g);
             Segment sg;
             int it = 0, nseg = 0;
+            long long mm_wait = 0, mm_issue = 0;
             while (segs.next(sg)) {
                 if (nseg > 0) {   // the epilogue of the previous segment has drained the accumulators
                     mbar_wait_bounded(acc_free_bar, (uint32_t)((nseg - 1) & 1));
@@ -301,7 +338,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
                 for (int i = 0; i < sg.nkb; ++i, ++it) {
                     const int s = it % NST;
+                    const long long tm0 = g.probe ? clock64() : 0;
                     mbar_wait_bounded(split_bar(s), (it / NST) & 1);
+                    const long long tm1 = g.probe ? clock64() : 0;
                     tc_fence_after();
                     const uint32_t st = base + s * STAGE;
 #pragma unroll
@@ -317,9 +356,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                         umma_tf32_ts(tmem_base, wa, xa, idesc, NACC > 1 ? first : 1u);
                     }
                     umma_commit(empty_bar(s));
+                    if (g.probe) {
+                        mm_wait += tm1 - tm0;
+                        mm_issue += clock64() - tm1;
+                    }
                 }
                 umma_commit(tmem_full_bar);
                 ++nseg;
+            }
+            if (g.probe) {
+                g.probe[cta_id * 8 + 1] = mm_wait;
+                g.probe[cta_id * 8 + 2] = mm_issue;
             }
         }
     } else {
@@ -330,10 +377,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         SegmentIter<NP, STREAMK> segs(g);
         Segment sg;
         int it = 0, nseg = 0;
+        long long cv_wait = 0, cv_work = 0, cv_blocks = 0, cv_epi = 0;
         while (segs.next(sg)) {
             for (int i = 0; i < sg.nkb; ++i, ++it) {
                 const int s = it % NST;
+                const long long tc0 = (g.probe && t == 0) ? clock64() : 0;
                 mbar_wait_bounded(full_bar(s), (it / NST) & 1);
+                const long long tc1 = (g.probe && t == 0) ? clock64() : 0;
                 const uint32_t st = base + s * STAGE;
                 // W: column f of the block, k rows [half * 16, half * 16 + 16) -> 16 columns of W and of W_lo in TMEM
                 {
@@ -362,7 +412,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(split_bar(s));
+                if (g.probe && t == 0) {
+                    cv_wait += tc1 - tc0;
+                    cv_work += clock64() - tc1;
+                    cv_blocks += 1;
+                }
             }
+            const long long te0 = (g.probe && t == 0) ? clock64() : 0;
             // ---- epilogue of the segment: lane = feature, columns = rows of x; this warp takes half of the row tile ----
             const int n = sg.n0 + f;
             const bool n_ok = n < g.N;
@@ -418,11 +474,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             tc_fence_before();
             mbar_arrive(acc_free_bar);
+            if (g.probe && t == 0) cv_epi += clock64() - te0;
             ++nseg;
+        }
+        if (g.probe && t == 0) {
+            g.probe[cta_id * 8 + 3] = cv_wait;
+            g.probe[cta_id * 8 + 4] = cv_work;
+            g.probe[cta_id * 8 + 6] = cv_epi;
+            g.probe[cta_id * 8 + 7] = cv_blocks;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (g.probe && threadIdx.x == 0) g.probe[cta_id * 8 + 5] = clock64() - t_cta0;
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -437,6 +501,7 @@ __global__ void __launch_bounds__(256) linear_streamk_reduce_kernel(const float*
                                                                     const float* __restrict__ bias, int rows, int N, int tk,
                                                                     int per, int maxseg, int n_mt, int act,
                                                                     float* __restrict__ out) {
+    asm volatile("griddepcontrol.launch_dependents;");   // the next layer's kernel may start streaming its weights
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int64_t total = (int64_t)rows * N;
     int row = 0, n = 0, c0 = 0, c1 = 0, tile = 0;
@@ -509,8 +574,18 @@ static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g,
         if (e != cudaSuccess) return (int)e;
         attr_set[dev & 63] = true;
     }
-    linear_tf32x3_kernel<NP, PACKED, STREAMK><<<grid, NTHREADS, smem, st>>>(tmX, tmW, g);
-    PA_RETURN_LAUNCH_STATUS();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, linear_tf32x3_kernel<NP, PACKED, STREAMK>, tmX, tmW, g);
+    return e == cudaSuccess ? PA_OK : (int)e;
 }
 
 template <typename... A>
@@ -533,6 +608,7 @@ static int launch_pdl(void (*kern)(A...), unsigned blocks, cudaStream_t st, A...
 // added in index order: the result does not depend on the schedule.
 __global__ void __launch_bounds__(256) linear_reduce4_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
                                                              int rows, int N, int nslices, int act, float* __restrict__ out) {
+    asm volatile("griddepcontrol.launch_dependents;");   // the next layer's kernel may start streaming its weights
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int64_t total = (int64_t)rows * N;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -641,6 +717,11 @@ size_t pa_linear_tc_workspace_bytes(int rows, int K, int N, int sm_count) {
     return sliced > sk ? sliced : sk;
 }
 
+static unsigned long long* g_linear_probe = nullptr;
+extern "C" __attribute__((visibility("default"))) void pa_debug_linear_probe(unsigned long long* d_counters) {
+    g_linear_probe = d_counters;   // [CTAs][8] device counters, zeroed by the caller; null switches the probe off
+}
+
 // pa_linear_f32 / pa_linear_f32_packed on the tensor cores.  d_W: [K, N] (packed == 0) or the pa_linear_pack_f32
 // layout (packed == 1).  Form: stream-K when the workspace holds its slots and the sum kernel's 16-byte lanes apply
 // (N % 4 == 0, aligned out / bias; PA_LINEAR_STREAMK=0 disables), else the plain grid, K-sliced if the workspace
@@ -661,6 +742,7 @@ int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, in
     g.bias = d_bias; g.out = d_out; g.partial = static_cast<float*>(d_ws);
     g.rows = rows; g.N = N; g.K = K; g.act = act; g.kslice = K; g.nslices = 1;
     g.w_packed = packed ? d_W : nullptr;
+    g.probe = g_linear_probe;
     const unsigned n_mt = (unsigned)((rows + np - 1) / np), n_ft = (unsigned)((N + BF - 1) / BF);
     g.n_ft = (int)n_ft;
     g.n_mt = (int)n_mt;
