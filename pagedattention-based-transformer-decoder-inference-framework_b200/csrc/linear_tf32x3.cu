@@ -8,8 +8,8 @@
 // accumulated in fp32 in TMEM.  Dropped: lo.lo (2^-22 relative) and the tail of each lo (2^-21); the tensor core's
 // fp32 accumulation truncates, which adds ~K/8 * 2^-24 of the running sum (the lo terms have accumulators of their
 // own, so they are not truncated against the big sum).  Measured <= 1.1e-6 of sum_k |x||W| (K = 11008, unsliced;
-// 2.5e-7 at decode batches; the fp32 SIMT kernels: 1-3e-7); the tests state 1e-5 * sum_k |x||W| + 4 ulp.  The fp32 SIMT kernels (PA_LINEAR_TC=0) stay
-// for callers that need fp32 arithmetic proper.
+// 2.5e-7 at decode batches; the fp32 SIMT kernels: 1-3e-7); the tests state 1e-5 * sum_k |x||W| + 4 ulp.
+// The fp32 SIMT kernels (PA_LINEAR_TC=0) stay for callers that need fp32 arithmetic proper.
 //
 // The layer is computed TRANSPOSED: out^T [N, rows] = W^T [N, K] . x^T [K, rows].  The weights are the M side of the
 // MMA (128 output features = 128 TMEM lanes), the decode batch the N side, so a small batch costs a small MMA
@@ -19,8 +19,8 @@
 // layout and x where it lies; the weights stream from HBM exactly once per 128 rows of x (L2 serves the other row tiles).
 //
 // One CTA = 128 features x NP rows (NP = 64 up to 64 rows, else 128) over one K slice; 320 threads:
-//   warp 0    TMA producer, per 32-float K block: ONE W box [32 k][128 n] (512-byte rows, no swizzle: only threads read it) and
-//             the x tile [NP rows][128 B] (128-byte swizzle, K-major B operand; rows / k out of range zero-filled);
+//   warp 0    TMA producer, per 32-float K block: ONE W box [32 k][128 n] (512-byte rows, no swizzle: only threads
+//             read it; or one 16 KB bulk copy of a packed block) and the x tile [NP rows][128 B] (128-byte swizzle, K-major B operand; rows / k out of range zero-filled);
 //   warps 2-9 split: thread = (feature n, half of the block's k): reads its 16 weights W[k][n] down the column
 //             (conflict-free: a warp reads 32 consecutive floats of one k-row), stores them and their lo parts into
 //             TENSOR MEMORY as the A operands (lane n, 32 + 32 columns per stage) -- the weights never touch shared
@@ -53,10 +53,10 @@ constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 split + 
 template <int NP> struct Cfg {
     static constexpr int X_TILE = NP * 128;
     static constexpr int STAGE = W_TILE + 2 * X_TILE;
-    // Accumulators: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~100 cycles
-    // measured, against a 32-cycle MMA at N = 64), so the three terms of the split get their own accumulators where
-    // TMEM allows (summed in the epilogue, small terms first -- which also keeps the lo terms out of the big sum's
-    // truncation): 3 at NP = 64, 2 (lo terms / hi.hi) at NP = 128.
+    // Accumulators: the tensor core's fp32 accumulation truncates, so the small terms of the split get accumulators of
+    // their own where TMEM allows (summed in the epilogue, small terms first): the lo terms are then not truncated against
+    // the big sum -- measured error 6.6e-7 -> 2.5e-7 of sum |x||W| at decode batches, speed-neutral.  3 at NP = 64,
+    // 2 (lo terms / hi.hi) at NP = 128.
     static constexpr int NACC = NP == 64 ? 3 : 2;
     static constexpr int NST = NP == 64 ? 5 : 4;
     static constexpr int TMEM_COLS = 512;
