@@ -260,6 +260,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // programmatic dependent launch: everything above ran under the tail of the kernel in front; its results are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef PA_GEMM_PROBE
     long long t_epi0 = 0;
     const long long t_setup = clock64();
@@ -570,6 +572,9 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // Launched with programmatic stream serialisation: barriers, TMEM and the cluster handshake above were set up while the
+    // kernel in front of this one in the stream was still draining; its results (A, the split-K workspace) are touched below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef PA_GEMM_PROBE
     const long long t_setup = clock64();
     if (threadIdx.x == 0 && probe_cta) g.probe[4] = t_setup - t_entry;
@@ -1042,7 +1047,8 @@ gemm_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <int ACT>
 __global__ void gemm_i8_splitk_epilogue_kernel(const Args g, int64_t rows) {
     // launched with programmatic stream serialisation behind the GEMM: resident early, blocks here until the partial
-    // tiles are complete and visible (a no-op for an ordinary launch)
+    // tiles are complete and visible (a no-op for an ordinary launch); the GEMM behind it may set itself up meanwhile
+    asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t n4 = rows * g.N / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1310,6 +1316,11 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
             attr[1].id = cudaLaunchAttributeCooperative;
             attr[1].val.cooperative = 1;
             cfg.numAttrs = 2;
+        } else if (!(getenv("PA_GEMM_PDL") && atoi(getenv("PA_GEMM_PDL")) == 0)) {
+            // set-up (barriers, TMEM, cluster handshake) under the tail of the kernel in front: see griddepcontrol.wait
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
         }
         e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
         if (e != cudaSuccess) return (int)e;
@@ -1334,13 +1345,18 @@ static int gemm_i8_launch(const int8_t* d_A, const int8_t* d_B, int8_t* d_C_s8, 
         cfg.blockDim = dim3(NTHREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)CLs;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (!(getenv("PA_GEMM_PDL") && atoi(getenv("PA_GEMM_PDL")) == 0)) {
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
+        }
         e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
         if (e != cudaSuccess) return (int)e;
         e = cudaGetLastError();
