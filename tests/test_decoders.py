@@ -752,3 +752,69 @@ def test_cuda_decoder_packed_weights_same_logits_and_repacked_after_inplace_writ
     assert len(dec1.__dict__.get("_pk", {})) >= 2 * L       # fc1, fc2 (+ projections) of every layer
     assert torch.equal(a1, a0)
     assert torch.equal(b1, b0) and not torch.equal(a1, b1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("streamk", ["0", "1"])
+def test_linear_chain_in_a_graph_is_deterministic(packed, streamk, monkeypatch):
+    """fc1 -> fc2 -> fc1 ... chains of the tensor-core linear kernel (launched with programmatic stream serialisation: the
+    next layer's weights start streaming under the previous kernel, x waits for griddepcontrol.wait) captured in ONE CUDA
+    graph and replayed: every replay must reproduce, bit for bit, what the same calls give one at a time with a device
+    synchronisation after each -- an ordering bug between a layer's sum kernel and the next layer's loads or partial
+    tiles would show up as a difference."""
+    from llm_decoder import _cabi
+    lib = _cabi.lib()
+    monkeypatch.setenv("PA_LINEAR_STREAMK", streamk)   # both work splits (K-sliced grid + sum kernel, stream-K + its sum kernel)
+    M, HID, INTER, NL = 48, 1024, 2816, 6
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W1 = [torch.randn((HID, INTER), device="cuda", generator=g) / HID ** 0.5 for _ in range(NL)]
+    W2 = [torch.randn((INTER, HID), device="cuda", generator=g) / INTER ** 0.5 for _ in range(NL)]
+    b1 = torch.randn(INTER, device="cuda", generator=g)
+    b2 = torch.randn(HID, device="cuda", generator=g)
+    if packed:
+        def pack(W, K, N):
+            Wp = torch.empty(lib.pa_linear_pack_bytes(K, N) // 4, device="cuda")
+            _cabi.check(lib.pa_linear_pack_f32(W.data_ptr(), Wp.data_ptr(), K, N, None))
+            return Wp
+        W1 = [pack(w, HID, INTER) for w in W1]
+        W2 = [pack(w, INTER, HID) for w in W2]
+    x0 = torch.randn((M, HID), device="cuda", generator=g)
+    xs = [torch.empty((M, HID), device="cuda") for _ in range(NL + 1)]
+    hs = [torch.empty((M, INTER), device="cuda") for _ in range(NL)]
+    need = max(lib.pa_linear_workspace_bytes(M, HID, INTER), lib.pa_linear_workspace_bytes(M, INTER, HID), 16)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    fn = lib.pa_linear_f32_packed if packed else lib.pa_linear_f32
+    os.environ["PA_LINEAR_TC"] = "1"
+
+    def chain(sync):
+        for i in range(NL):
+            _cabi.check(fn(xs[i].data_ptr(), W1[i].data_ptr(), b1.data_ptr(), M, HID, INTER, 1, hs[i].data_ptr(),
+                           ws.data_ptr(), need, _cabi.stream()))
+            if sync:
+                torch.cuda.synchronize()
+            _cabi.check(fn(hs[i].data_ptr(), W2[i].data_ptr(), b2.data_ptr(), M, INTER, HID, 0, xs[i + 1].data_ptr(),
+                           ws.data_ptr(), need, _cabi.stream()))
+            if sync:
+                torch.cuda.synchronize()
+
+    try:
+        xs[0].copy_(x0)
+        chain(True)
+        ref = [t.clone() for t in xs[1:]] + [t.clone() for t in hs]
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            chain(False)   # warm (attribute set-up) outside capture
+            side.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                chain(False)
+        for rep in range(20):
+            for t in xs[1:] + hs:
+                t.fill_(float("nan"))
+            gr.replay()
+            torch.cuda.synchronize()
+            got = xs[1:] + hs
+            assert all(torch.equal(a, b) for a, b in zip(got, ref)), f"replay {rep}"
+    finally:
+        os.environ.pop("PA_LINEAR_TC", None)
