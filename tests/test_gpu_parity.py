@@ -1166,3 +1166,46 @@ def test_in_kernel_row_merge_equals_separate_merge_kernel(ld, oracle, kv, monkey
     long_case = make_case(B=1, H=4, D=128, T=16384, seed=65, kv=kv)
     got, _ = run_decode(ld, long_case, True)
     np.testing.assert_allclose(got, oracle_attention(long_case), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [96, 256])
+def test_int8_gemm_chain_in_a_graph_is_deterministic(ld, M):
+    """fc1 -> fc2 chains of the int8 GEMM (1-CTA kernel at M = 96, 2-CTA + split-K epilogue at M = 256; both launched with
+    programmatic stream serialisation, set-up under the previous kernel's tail) captured in one CUDA graph: 20 replays must
+    reproduce the results of the same calls run one at a time with a synchronisation after each, bit for bit."""
+    HID, INTER, NL = 1024, 4096, 5
+    g = torch.Generator(device="cuda").manual_seed(M)
+    W1 = [torch.randint(-127, 128, (1, HID, INTER), generator=g, device="cuda", dtype=torch.int8) for _ in range(NL)]
+    W2 = [torch.randint(-127, 128, (1, INTER, HID), generator=g, device="cuda", dtype=torch.int8) for _ in range(NL)]
+    b1, b2 = torch.randn(INTER, generator=g, device="cuda"), torch.randn(HID, generator=g, device="cuda")
+    x0 = torch.randint(-127, 128, (1, M, HID), generator=g, device="cuda", dtype=torch.int8)
+    xs = [torch.empty((1, M, HID), dtype=torch.int8, device="cuda") for _ in range(NL + 1)]
+    hs = [torch.empty((1, M, INTER), dtype=torch.int8, device="cuda") for _ in range(NL)]
+
+    def chain(sync):
+        for i in range(NL):
+            assert ld.dnnl_matmul_int8(xs[i], W1[i], hs[i], 1, M, INTER, HID, 1 / 16, 1 / 16, 16.0, b1, "relu")
+            if sync:
+                torch.cuda.synchronize()
+            assert ld.dnnl_matmul_int8(hs[i], W2[i], xs[i + 1], 1, M, HID, INTER, 1 / 16, 1 / 16, 64.0, b2, "")
+            if sync:
+                torch.cuda.synchronize()
+
+    xs[0].copy_(x0)
+    chain(True)
+    ref = [t.clone() for t in xs[1:] + hs]
+    assert any(int(t.float().abs().max()) > 0 for t in ref)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        chain(False)
+        side.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            chain(False)
+    for rep in range(20):
+        for t in xs[1:] + hs:
+            t.fill_(-128)
+        gr.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(xs[1:] + hs, ref)), f"replay {rep}"
