@@ -345,7 +345,12 @@ int pa_layer_norm_f32(const float* d_x, const float* d_gamma, const float* d_bet
 /* decoder/mlp.hpp:23-41, one layer of the float MLP: out[r,n] = act(bias[n] + sum_k x[r,k]*W[k*N+n]),
  * act in {PA_ACT_NONE, PA_ACT_RELU}.  d_out must not alias d_x.  d_workspace: caller-owned scratch for the
  * K-slice partials, >= pa_linear_workspace_bytes(rows, K, N) bytes (NULL / too small: unsliced, same result
- * up to the summation order). */
+ * up to the summation order).
+ * Arithmetic: layers with >= 16 rows, N % 4 == 0, K % 4 == 0, 16-byte aligned operands and >= 5e7 MACs run on
+ * the tensor cores (tcgen05 kind::tf32 with every operand split into hi + lo: x.W ~= x_hi.W_lo + x_lo.W_hi +
+ * x_hi.W_hi, fp32 accumulation; error <= 1e-5 * sum_k |x||W| stated, <= 1.1e-6 measured -- the fp32 SIMT
+ * kernels: 1-3e-7); everything else, and everything with PA_LINEAR_TC=0 in the environment, in fp32 FMA
+ * arithmetic proper (only the summation order differs from the reference's scalar loop). */
 size_t pa_linear_workspace_bytes(int rows, int K, int N);
 int pa_linear_f32(const float* d_x, const float* d_W, const float* d_bias, int rows, int K, int N,
                   int act, float* d_out, void* d_workspace, size_t workspace_bytes, pa_stream_t stream);
