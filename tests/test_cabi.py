@@ -62,3 +62,18 @@ def test_missing_library_fails_loudly(cabi, monkeypatch):
     monkeypatch.setattr(cabi, "LIB_PATH", "/nonexistent/libpa_b200.so")
     with pytest.raises(cabi.PAError):
         cabi.lib()
+
+
+def test_packed_linear_geometry_and_argument_rules_need_no_gpu(cabi):
+    """pa_linear_pack_bytes is pure geometry ([ceil(N/128)][ceil(K/32)][32][128] f32) and pa_linear_f32_packed rejects
+    what its kernel cannot take before touching the device (K % 4 != 0 -> PA_ERR_UNSUPPORTED; null pointers and unknown
+    activations -> PA_ERR_INVALID_ARG)."""
+    lib = cabi.lib()
+    assert lib.pa_linear_pack_bytes(32, 128) == 32 * 128 * 4
+    assert lib.pa_linear_pack_bytes(33, 129) == 2 * 2 * 32 * 128 * 4
+    assert lib.pa_linear_pack_bytes(4096, 11008) == 86 * 128 * 32 * 128 * 4
+    assert lib.pa_linear_pack_bytes(0, 5) == 0
+    # (the pointers are never dereferenced: the argument rules come first)
+    assert lib.pa_linear_f32_packed(0x1000, 0x1000, None, 4, 6, 8, 0, 0x2000, None, 0, None) == -2
+    assert lib.pa_linear_f32_packed(None, 0x1000, None, 4, 8, 8, 0, 0x2000, None, 0, None) == -1
+    assert lib.pa_linear_f32_packed(0x1000, 0x1000, None, 4, 8, 8, 7, 0x2000, None, 0, None) == -1
