@@ -502,30 +502,31 @@ __global__ void __launch_bounds__(256) linear_streamk_reduce_kernel(const float*
                                                                     int per, int maxseg, int n_mt, int act,
                                                                     float* __restrict__ out) {
     asm volatile("griddepcontrol.launch_dependents;");   // the next layer's kernel may start streaming its weights
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int64_t total = (int64_t)rows * N;
-    int row = 0, n = 0, c0 = 0, c1 = 0, tile = 0;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < total) {
-        row = (int)(i / N);
-        n = (int)(i - (int64_t)row * N);
-        tile = (n / BF) * n_mt + row / NP;
-        c0 = (int)(((int64_t)tile * tk) / per);
-        c1 = (int)((((int64_t)tile + 1) * tk - 1) / per);
-        if (c0 != c1 && bias) s = __ldg(reinterpret_cast<const float4*>(bias + n));
-    }
+    // grid: x = 16-byte column groups of a row, y = rows (strided); 32-bit index arithmetic (tiles * tk < 2^31, host-checked)
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool n_ok = n < N;
+    const int ft = n / BF;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_ok && bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (i >= total || c0 == c1) return;
-    for (int c = c0; c <= c1; ++c) {
-        const int first_tile = (int)(((int64_t)c * per) / tk);
-        const int64_t slot = (int64_t)c * maxseg + (tile - first_tile);
-        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (slot * NP + row % NP) * BF + n % BF));
-        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    if (!n_ok) return;
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int tile = ft * n_mt + row / NP;
+        const unsigned w0 = (unsigned)tile * (unsigned)tk;
+        const int c0 = (int)(w0 / (unsigned)per), c1 = (int)((w0 + (unsigned)tk - 1u) / (unsigned)per);
+        if (c0 == c1) continue;   // the tile was finished in place by its one CTA
+        float4 s = b4;
+        for (int c = c0; c <= c1; ++c) {
+            const int first_tile = (int)(((unsigned)c * (unsigned)per) / (unsigned)tk);
+            const int64_t slot = (int64_t)c * maxseg + (tile - first_tile);
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (slot * NP + row % NP) * BF + n % BF));
+            s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+        }
+        if (act == PA_ACT_RELU) {
+            s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)row * N + n) = s;
     }
-    if (act == PA_ACT_RELU) {
-        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
-    }
-    *reinterpret_cast<float4*>(out + i) = s;
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -589,9 +590,9 @@ static int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const Args& g,
 }
 
 template <typename... A>
-static int launch_pdl(void (*kern)(A...), unsigned blocks, cudaStream_t st, A... args) {
+static int launch_pdl(void (*kern)(A...), dim3 blocks, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(blocks);
+    cfg.gridDim = blocks;
     cfg.blockDim = dim3(256);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -757,7 +758,8 @@ int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, in
     // ... and only for K-sliced grids of few tiles: with many whole tiles per CTA (prefill: 688 tiles) the plain grid's
     // block order keeps neighbouring CTAs on the same weights and wins (2048 rows: 714 vs 859 us).
     const bool multi_wave = (int64_t)n_mt * n_ft * nslices > sm_count && (int64_t)n_mt * n_ft <= 2 * (int64_t)sm_count;
-    const bool use_sk = (env ? atoi(env) != 0 : multi_wave) && lanes16 && sk.tk >= 8 && ws_bytes >= sk.ws_bytes;
+    const bool use_sk = (env ? atoi(env) != 0 : multi_wave) && lanes16 && sk.tk >= 8 && ws_bytes >= sk.ws_bytes &&
+                        sk.total + sk.tk < 0x7fffffffll;
     int rc;
     if (use_sk) {
         g.sk_per = sk.per; g.sk_maxseg = sk.maxseg; g.sk_total = sk.total;
@@ -765,7 +767,7 @@ int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, in
         if (packed) rc = np == 64 ? launch<64, true, true>(tmX, tmW, g, grid, st) : launch<128, true, true>(tmX, tmW, g, grid, st);
         else rc = np == 64 ? launch<64, false, true>(tmX, tmW, g, grid, st) : launch<128, false, true>(tmX, tmW, g, grid, st);
         if (rc != PA_OK || sk.per % sk.tk == 0) return rc;   // ranges that end on tile boundaries leave no partial tiles
-        const unsigned blocks = (unsigned)((((int64_t)rows * N + 3) / 4 + 255) / 256);
+        const dim3 blocks((unsigned)((N / 4 + 255) / 256), (unsigned)(rows < 32768 ? rows : 32768));
         const float* part = g.partial;
         if (np == 64)
             return launch_pdl(linear_streamk_reduce_kernel<64>, blocks, st, part, d_bias, rows, N, sk.tk, sk.per, sk.maxseg,
@@ -782,7 +784,7 @@ int pa_linear_tc_run(const float* d_x, const float* d_W, const float* d_bias, in
     if (packed) rc = np == 64 ? launch<64, true, false>(tmX, tmW, g, grid, st) : launch<128, true, false>(tmX, tmW, g, grid, st);
     else rc = np == 64 ? launch<64, false, false>(tmX, tmW, g, grid, st) : launch<128, false, false>(tmX, tmW, g, grid, st);
     if (rc != PA_OK || nslices == 1) return rc;
-    const unsigned blocks = (unsigned)((((int64_t)rows * N + 3) / 4 + 255) / 256);
+    const dim3 blocks((unsigned)((((int64_t)rows * N + 3) / 4 + 255) / 256));
     const float* part = g.partial;
     return launch_pdl(linear_reduce4_kernel, blocks, st, part, d_bias, rows, N, nslices, act, d_out);
 }
